@@ -1,0 +1,108 @@
+// MatrixVectorizer (utils/matrix_vectorizer.py) as index-math gather / scatter kernels.
+//   vectorize      :24-58  strict upper triangle, COLUMN-major walk: (r, c), r < c, lands at
+//                          start(c) + r with start(c) = c(c-1)/2; include_diagonal appends the
+//                          SUB-diagonal element (c+1, c) after column c, so start(c) = c(c-1)/2 + c.
+//   anti_vectorize :61-95  ROW-major strict upper fill (torch.triu_indices order), mirrored;
+//                          include_diagonal puts vec[n_el + i] on the MAIN diagonal; fp32 output.
+// Both are pure byte movement (bit exact).  vectorize reads 32x32 tiles row-wise (coalesced),
+// transposes them through shared memory and writes runs of consecutive r (coalesced).
+#include "common.cuh"
+
+namespace gsr {
+
+__device__ __forceinline__ long long vec_start(int c, int diag) {
+    return (long long)c * (c - 1) / 2 + (diag ? c : 0);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+vectorize_kernel(const T* __restrict__ M, T* __restrict__ out, int n, long long len, int diag) {
+    __shared__ T tile[32][33];
+    const int ct = blockIdx.x, rt = blockIdx.y;
+    if (rt > ct) return;                       // tile entirely below the diagonal
+    const T* Mb = M + (size_t)blockIdx.z * n * n;
+    T* ob = out + (size_t)blockIdx.z * len;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;      // 8 warps
+    const int r0 = rt * 32, c0 = ct * 32;
+    for (int rr = w; rr < 32; rr += 8) {
+        const int r = r0 + rr, c = c0 + lane;
+        if (r < n && c < n) tile[rr][lane] = Mb[(size_t)r * n + c];
+    }
+    __syncthreads();
+    for (int cc = w; cc < 32; cc += 8) {
+        const int c = c0 + cc, r = r0 + lane;
+        if (c < n && r < c) ob[vec_start(c, diag) + r] = tile[lane][cc];
+    }
+    if (diag && rt == ct) {                    // sub-diagonal element (c+1, c) closes column c
+        const int c = c0 + threadIdx.x;
+        if (threadIdx.x < 32 && c + 1 < n) ob[vec_start(c, 1) + c] = Mb[(size_t)(c + 1) * n + c];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+anti_vectorize_kernel(const float* __restrict__ vec, float* __restrict__ out, int n, long long vec_len, int diag) {
+    const float* vb = vec + (size_t)blockIdx.y * vec_len;
+    float* ob = out + (size_t)blockIdx.y * n * n;
+    const long long n_el = (long long)n * (n - 1) / 2;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)n * n;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / n), c = (int)(e - (long long)r * n);
+        float v = 0.f;
+        if (r != c) {
+            const int a = min(r, c), b = max(r, c);
+            v = vb[(long long)a * n - (long long)a * (a + 1) / 2 + (b - a - 1)];
+        } else if (diag) {
+            v = vb[n_el + r];
+        }
+        ob[e] = v;
+    }
+}
+
+template <typename T>
+static int launch_vectorize(const void* M, void* out, int batch, int n, int diag, cudaStream_t st) {
+    const int tiles = (n + 31) / 32;
+    dim3 grid(tiles, tiles, batch);
+    vectorize_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(M), static_cast<T*>(out), n,
+                                              gsr_vectorize_len(n, diag), diag);
+    return launched("vectorize");
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" long long gsr_vectorize_len(int n, int include_diagonal) {
+    if (n <= 0) return 0;
+    return (long long)n * (n - 1) / 2 + (include_diagonal ? (n - 1) : 0);
+}
+
+extern "C" int gsr_vectorize(const void* matrix, void* out, int batch, int n, int elem_size,
+                             int include_diagonal, void* stream) {
+    if (!matrix || !out || batch < 0 || n <= 0) return fail(GSR_E_ARG, "vectorize: bad argument");
+    if (batch == 0 || n == 1) return 0;
+    if (batch > 65535) return fail(GSR_E_UNSUPPORTED, "vectorize: batch > 65535");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int d = include_diagonal ? 1 : 0;
+    switch (elem_size) {
+        case 1: return launch_vectorize<uint8_t>(matrix, out, batch, n, d, st);
+        case 2: return launch_vectorize<uint16_t>(matrix, out, batch, n, d, st);
+        case 4: return launch_vectorize<uint32_t>(matrix, out, batch, n, d, st);
+        case 8: return launch_vectorize<uint64_t>(matrix, out, batch, n, d, st);
+        case 16: return launch_vectorize<uint4>(matrix, out, batch, n, d, st);
+        default: return fail(GSR_E_UNSUPPORTED, "vectorize: elem_size must be 1, 2, 4, 8 or 16");
+    }
+}
+
+extern "C" int gsr_anti_vectorize(const float* vec, float* out, int batch, int n, long long vec_len,
+                                  int include_diagonal, void* stream) {
+    if (!vec || !out || batch < 0 || n <= 0) return fail(GSR_E_ARG, "anti_vectorize: bad argument");
+    const long long n_el = (long long)n * (n - 1) / 2;
+    if (vec_len < n_el) return fail(GSR_E_ARG, "anti_vectorize: vector shorter than n(n-1)/2");
+    if (include_diagonal && vec_len < n_el + n) return fail(GSR_E_ARG, "anti_vectorize: vector too short for the diagonal");
+    if (batch == 0) return 0;
+    if (batch > 65535) return fail(GSR_E_UNSUPPORTED, "anti_vectorize: batch > 65535");
+    const long long total = (long long)n * n;
+    const int bx = (int)min((long long)64, (total + 255) / 256);
+    anti_vectorize_kernel<<<dim3(bx, batch), 256, 0, (cudaStream_t)stream>>>(vec, out, n, vec_len, include_diagonal ? 1 : 0);
+    return launched("anti_vectorize");
+}

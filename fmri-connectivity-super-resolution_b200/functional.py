@@ -1,0 +1,242 @@
+"""torch.autograd.Functions over the sm_100a kernels -- the differentiable ops of the GSR-Net path.
+
+Every op accepts the reference's 2-D tensors and, as an extension, a leading subject
+dimension ([B, n, n]).  Shared operands (weights, the U-Net output) stay 2-D; their
+gradients are reduced over the subjects on the device (gsr_bgemm_reduce_f32).
+Backward formulas: SURVEY.md Appendix A (restated from the reference's autograd graph).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import kernels as K
+
+
+def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if t is None else t.contiguous()
+
+
+def _wgrad(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB: bool = False) -> torch.Tensor:
+    """sum over subjects of op(A[b]) @ op(B[b]) (or the plain product for 2-D operands)."""
+    if A.dim() == 3:
+        return K.bgemm_reduce(A, B, transA=transA, transB=transB)
+    return K.bgemm(A, B, transA=transA, transB=transB)
+
+
+# ----------------------------------------------------------------------------- a1
+class NormalizeAdjFn(Function):
+    """utils/preprocessing.py:16-25."""
+
+    @staticmethod
+    def forward(ctx, mx):
+        out, r, _ = K.normalize_adj_fwd(mx, pre=False)
+        ctx.save_for_backward(mx, r)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        mx, r = ctx.saved_tensors
+        return K.normalize_adj_bwd(mx, r, _c(g), pre=False)
+
+
+def normalize_adj(mx: torch.Tensor) -> torch.Tensor:
+    return NormalizeAdjFn.apply(mx)
+
+
+# ----------------------------------------------------------------------------- a2
+class EighError(torch.linalg.LinAlgError):
+    pass
+
+
+def raise_on_eigh_info(info: torch.Tensor) -> None:
+    """torch.linalg.eigh's error contract (synchronises: reads `info` back)."""
+    worst = int(info.min().item())
+    if worst == -1:
+        raise EighError("linalg.eigh: the input contains non-finite values")
+    if worst == -2:
+        raise EighError("linalg.eigh: the Jacobi iteration failed to converge")
+
+
+def eigh(A: torch.Tensor, UPLO: str = "U", check_errors: bool = True, canonical_sign: bool = True):
+    """models/layers.py:27 / utils/gsr_train.py:34 -- eigh(A, UPLO='U'): ascending eigenvalues,
+    eigenvectors in columns, sign-canonicalised.  Not differentiable (the reference never
+    differentiates through it: its input carries no gradient)."""
+    if UPLO != "U":
+        raise NotImplementedError("eigh: only UPLO='U' is on the GSR-Net path")
+    if A.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("eigh: gradients through the eigendecomposition are not on the GSR-Net path")
+    w, U, info = K.eigh_jacobi(A.detach(), canonical_sign=canonical_sign)
+    if check_errors:
+        raise_on_eigh_info(info)
+    return w, U, info
+
+
+# ----------------------------------------------------------------------------- Linear (models/ops.py:60)
+class LinearFn(Function):
+    @staticmethod
+    def forward(ctx, X, W, b):
+        ctx.save_for_backward(X, W)
+        return K.bgemm(X, W, transB=True, bias=b)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gY):
+        X, W = ctx.saved_tensors
+        gY = _c(gY)
+        gX = K.bgemm(gY, W) if ctx.needs_input_grad[0] else None
+        gW = K.bgemm(gY, X, transA=True) if ctx.needs_input_grad[1] else None
+        gb = K.colsum(gY) if ctx.needs_input_grad[2] else None
+        return gX, gW, gb
+
+
+# ----------------------------------------------------------------------------- a8 / a9
+class GraphPoolFn(Function):
+    """models/ops.py:35-45: scores, top-k (stated tie rule), gather * score."""
+
+    @staticmethod
+    def forward(ctx, X, pw, pb, k):
+        scores = K.pool_scores(X, pw, pb)
+        vals, idx = K.pool_topk(scores, k)
+        new_X = K.pool_gather_scale(X, idx, vals)
+        ctx.save_for_backward(X, pw, scores, idx)
+        ctx.mark_non_differentiable(idx, scores)
+        return new_X, idx, scores
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_new, _gi, _gs):
+        X, pw, scores, idx = ctx.saved_tensors
+        gX, gp, gc = K.pool_bwd(X, pw, scores, idx, _c(g_new))
+        return gX, gp.view_as(pw), gc, None
+
+
+class GraphUnpoolFn(Function):
+    """models/ops.py:22-23."""
+
+    @staticmethod
+    def forward(ctx, X, idx, n):
+        ctx.save_for_backward(idx)
+        return K.unpool_fwd(X, idx, n)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        return K.unpool_bwd(_c(g), idx), None, None
+
+
+# ----------------------------------------------------------------------------- a3 / a4
+class GSRLayerFn(Function):
+    """models/layers.py:20-63 without the dead zero padding:
+        (lambda, U) = eigh(A);  P = W U^T;  F = P f;  G = |F|, G_ii = 1
+        adj = normalize(G);  X = adj adj^T;  X = (X + X^T)/2, X_ii = 1;  Z = |X|
+    Returns (adj, Z, F).  F is the raw product (f_d = |F| with unit diagonal)."""
+
+    @staticmethod
+    def forward(ctx, W, A, f, U):
+        Pt = K.bgemm(U, W, transB=True)                 # P^T = U W^T         [B, lr, hr]  (stacked over subjects)
+        F = K.bgemm(Pt, f, transA=True)                 # F   = P f           [B, hr, hr]
+        adj, r, _ = K.normalize_adj_fwd(F, pre=True)    # abs + unit diagonal fused in front
+        X0 = K.bgemm(adj, adj, transB=True)             # adj adj^T
+        Z = K.sym_diag_abs_fwd(X0)
+        ctx.save_for_backward(W, f, U, Pt, F, r, adj, X0)
+        ctx.mark_non_differentiable(F)
+        return adj, Z, F
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_adj, g_Z, _gF):
+        W, f, U, Pt, F, r, adj, X0 = ctx.saved_tensors
+        g_adj, g_Z = _c(g_adj), _c(g_Z)
+        # dX0 = (dX + dX^T)/2 with dX = dZ * sgn(X), zero diagonal;  d_adj += (dX0 + dX0^T) adj = 2 dX0 adj
+        gX0 = K.sym_diag_abs_bwd(X0, g_Z)
+        d_adj = K.bgemm(gX0, adj, alpha=2.0, add=g_adj)
+        gF = K.normalize_adj_bwd(F, r, d_adj, pre=True)          # through normalise, abs and the diagonal fill
+        gP = K.bgemm(gF, f, transB=True)                         # dP = dF f^T     [B, hr, lr] (stacked)
+        gf = _wgrad(Pt, gF) if ctx.needs_input_grad[2] else None           # sum_b P^T dF
+        gW = _wgrad(gP, U) if ctx.needs_input_grad[0] else None            # sum_b dP U
+        return gW, None, gf, None
+
+
+# ----------------------------------------------------------------------------- a5
+class GraphConvFn(Function):
+    """models/layers.py:83-88: adj @ (x @ W); no bias, activation or dropout."""
+
+    @staticmethod
+    def forward(ctx, x, adj, W):
+        S = K.bgemm(x, W)                                # support  (stacked over subjects)
+        H = K.bgemm(adj, S)
+        ctx.save_for_backward(x, adj, W, S)
+        return H
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gH):
+        x, adj, W, S = ctx.saved_tensors
+        gH = _c(gH)
+        gS = K.bgemm(adj, gH, transA=True)               # adj^T dH
+        g_adj = K.bgemm(gH, S, transB=True) if ctx.needs_input_grad[1] else None   # dH S^T
+        gW = _wgrad(x, gS, transA=True) if ctx.needs_input_grad[2] else None       # sum_b x^T dS
+        gx = K.bgemm(gS, W, transB=True) if ctx.needs_input_grad[0] else None      # dS W^T
+        return gx, g_adj, gW
+
+
+# ----------------------------------------------------------------------------- a6
+class SymDiagAbsFn(Function):
+    """models/gsr_model.py:32-37: z = (z + z^T)/2; z[diag] = 1; |z|."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return K.sym_diag_abs_fwd(x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return K.sym_diag_abs_bwd(x, _c(g))
+
+
+def sym_diag_abs(x: torch.Tensor) -> torch.Tensor:
+    return SymDiagAbsFn.apply(x)
+
+
+# ----------------------------------------------------------------------------- a13
+class L1LossFn(Function):
+    """nn.L1Loss() (utils/gsr_train.py:9): mean |x - y|, per subject when `batch` > 1.
+    y may be shared by the subjects (y.dim() == x.dim() - 1)."""
+
+    @staticmethod
+    def forward(ctx, x, y, batch):
+        shared = y.numel() != x.numel()
+        if shared and y.numel() * batch != x.numel():
+            raise ValueError(f"l1_loss: shapes {tuple(x.shape)} and {tuple(y.shape)} do not match")
+        x, y = x.contiguous(), y.contiguous()
+        ctx.save_for_backward(x, y)
+        ctx.batch, ctx.shared = batch, shared
+        return K.l1_loss_fwd(x, y, batch, shared)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        gx = K.l1_loss_bwd(x, y, _c(g), ctx.batch, ctx.shared)
+        gy = None
+        if ctx.needs_input_grad[1]:
+            gy = (-gx).reshape(y.shape) if not ctx.shared else -gx.reshape((ctx.batch,) + tuple(y.shape)).sum(0)
+        return (gx if ctx.needs_input_grad[0] else None), gy, None
+
+
+def l1_loss(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Scalar mean |x - y| over all elements (nn.L1Loss default reduction)."""
+    return L1LossFn.apply(x, y, 1)[0]
+
+
+def l1_loss_per_subject(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """[B] per-subject means for x = [B, ...]; y is [B, ...] or shared [...]."""
+    return L1LossFn.apply(x, y, x.shape[0])

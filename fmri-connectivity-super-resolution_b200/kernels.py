@@ -1,0 +1,365 @@
+"""Tensor-level wrappers around the C ABI (include/gsr_sm100.h).
+
+Each function checks device / dtype / layout, allocates outputs with torch (the
+library never allocates) and launches on torch's current CUDA stream.  Inputs
+may carry a leading subject dimension.  No function here has a non-CUDA path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import check, lib
+
+EPI_NONE, EPI_BIAS, EPI_ADD = 0, 1, 2
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the GSR-Net kernels have no CPU path), got {t.device}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _i64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda or t.dtype != torch.int64:
+        raise TypeError(f"{name}: expected a CUDA int64 tensor, got {t.dtype} on {t.device}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _square_batch(t: torch.Tensor, name: str) -> Tuple[int, int]:
+    if t.dim() not in (2, 3) or t.shape[-1] != t.shape[-2]:
+        raise ValueError(f"{name}: expected [n, n] or [batch, n, n], got {tuple(t.shape)}")
+    return (1 if t.dim() == 2 else t.shape[0]), t.shape[-1]
+
+
+# --------------------------------------------------------------------- a1
+def normalize_adj_fwd(mx: torch.Tensor, pre: bool = False, want_m: bool = False):
+    mx = _f32(mx, "normalize_adj: mx")
+    batch, n = _square_batch(mx, "normalize_adj: mx")
+    out = torch.empty_like(mx)
+    r = torch.empty(mx.shape[:-1], device=mx.device, dtype=torch.float32)
+    m = torch.empty_like(mx) if want_m else None
+    check(lib().gsr_normalize_adj_fwd(mx.data_ptr(), out.data_ptr(), r.data_ptr(),
+                                      m.data_ptr() if want_m else None, batch, n, int(pre), _stream()),
+          "gsr_normalize_adj_fwd")
+    return out, r, m
+
+
+def normalize_adj_bwd(mx: torch.Tensor, r: torch.Tensor, grad_out: torch.Tensor, pre: bool = False) -> torch.Tensor:
+    mx, r, grad_out = _f32(mx, "mx"), _f32(r, "r"), _f32(grad_out, "grad_out")
+    batch, n = _square_batch(mx, "normalize_adj_bwd: mx")
+    grad = torch.empty_like(mx)
+    check(lib().gsr_normalize_adj_bwd(mx.data_ptr(), r.data_ptr(), grad_out.data_ptr(), grad.data_ptr(),
+                                      batch, n, int(pre), _stream()), "gsr_normalize_adj_bwd")
+    return grad
+
+
+# --------------------------------------------------------------------- a2
+def eigh_jacobi(A: torch.Tensor, canonical_sign: bool = True, tol: float = 0.0, max_sweeps: int = 0):
+    """Returns (w, U, info) -- see gsr_eigh_jacobi_f32.  No synchronisation."""
+    A = _f32(A, "eigh: A")
+    batch, n = _square_batch(A, "eigh: A")
+    w = torch.empty(A.shape[:-1], device=A.device, dtype=torch.float32)
+    U = torch.empty_like(A)
+    info = torch.empty((batch,), device=A.device, dtype=torch.int32)
+    check(lib().gsr_eigh_jacobi_f32(A.data_ptr(), w.data_ptr(), U.data_ptr(), info.data_ptr(), batch, n,
+                                    int(canonical_sign), float(tol), int(max_sweeps), _stream()),
+          "gsr_eigh_jacobi_f32")
+    return w, U, info
+
+
+# --------------------------------------------------------------------- GEMMs
+def bgemm(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB: bool = False, alpha: float = 1.0,
+          bias: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C[b] = alpha * op(A[b]) @ op(B[b]) (+ bias[n] | + add[b]).  2-D operands are shared by
+    all subjects.  A 3-D non-transposed A against a shared B is run as ONE stacked GEMM
+    (M = batch * rows): the weight tile is reused across subjects and no tile is ragged."""
+    A, B = _f32(A, "bgemm: A"), _f32(B, "bgemm: B")
+    if A.dim() not in (2, 3) or B.dim() not in (2, 3):
+        raise ValueError("bgemm: operands must be 2-D or 3-D")
+    ba = A.shape[0] if A.dim() == 3 else 1
+    bb = B.shape[0] if B.dim() == 3 else 1
+    if A.dim() == 3 and B.dim() == 3 and ba != bb:
+        raise ValueError(f"bgemm: batch mismatch {ba} vs {bb}")
+    batch = max(ba, bb)
+    ar, ac = A.shape[-2], A.shape[-1]
+    br, bc = B.shape[-2], B.shape[-1]
+    M, K = (ac, ar) if transA else (ar, ac)
+    K2, N = (bc, br) if transB else (br, bc)
+    if K != K2:
+        raise RuntimeError(f"bgemm: inner dimensions differ: op(A) is {M}x{K}, op(B) is {K2}x{N}")
+    batched_out = A.dim() == 3 or B.dim() == 3
+    out = torch.empty((batch, M, N) if batched_out else (M, N), device=A.device, dtype=torch.float32)
+    sA = ar * ac if A.dim() == 3 else 0
+    sB = br * bc if B.dim() == 3 else 0
+    epi, extra, ld_extra, s_extra = EPI_NONE, None, 0, 0
+    if bias is not None and add is not None:
+        raise ValueError("bgemm: bias and add are mutually exclusive")
+    if bias is not None:
+        bias = _f32(bias, "bgemm: bias")
+        if bias.numel() != N:
+            raise ValueError("bgemm: bias length != N")
+        epi, extra = EPI_BIAS, bias
+    if add is not None:
+        add = _f32(add, "bgemm: add")
+        if tuple(add.shape) != tuple(out.shape):
+            raise ValueError(f"bgemm: add shape {tuple(add.shape)} != output shape {tuple(out.shape)}")
+        epi, extra, ld_extra, s_extra = EPI_ADD, add, N, M * N
+    Mk, bk, sAk, sCk, sEk = M, batch, sA, M * N, s_extra
+    if A.dim() == 3 and B.dim() == 2 and not transA:          # stack the subjects along M
+        Mk, bk, sAk, sCk, sEk = batch * M, 1, 0, 0, 0
+    check(lib().gsr_bgemm_f32(A.data_ptr(), B.data_ptr(), out.data_ptr(), Mk, N, K, ac, bc, N,
+                              sAk, sB, sCk, int(transA), int(transB), bk, float(alpha),
+                              epi, extra.data_ptr() if extra is not None else None, ld_extra, sEk, _stream()),
+          "gsr_bgemm_f32")
+    return out
+
+
+def bgemm_reduce(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB: bool = False,
+                 alpha: float = 1.0, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C = alpha * sum_b op(A[b]) @ op(B[b]) (+ add): weight gradients over the subject batch."""
+    A, B = _f32(A, "bgemm_reduce: A"), _f32(B, "bgemm_reduce: B")
+    if A.dim() != 3 or B.dim() != 3 or A.shape[0] != B.shape[0]:
+        raise ValueError("bgemm_reduce: both operands must be [batch, ., .] with equal batch")
+    batch = A.shape[0]
+    ar, ac = A.shape[-2], A.shape[-1]
+    br, bc = B.shape[-2], B.shape[-1]
+    M, K = (ac, ar) if transA else (ar, ac)
+    K2, N = (bc, br) if transB else (br, bc)
+    if K != K2:
+        raise RuntimeError(f"bgemm_reduce: inner dimensions differ ({K} vs {K2})")
+    out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    splits = C.c_int(0)
+    ws_floats = lib().gsr_bgemm_reduce_workspace(M, N, batch, C.byref(splits))
+    ws = torch.empty((ws_floats,), device=A.device, dtype=torch.float32)
+    epi, extra = EPI_NONE, None
+    if add is not None:
+        add = _f32(add, "bgemm_reduce: add")
+        if tuple(add.shape) != (M, N):
+            raise ValueError("bgemm_reduce: add shape != (M, N)")
+        epi, extra = EPI_ADD, add
+    check(lib().gsr_bgemm_reduce_f32(A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, ac, bc, N,
+                                     ar * ac, br * bc, int(transA), int(transB), batch, float(alpha),
+                                     epi, extra.data_ptr() if extra is not None else None, N,
+                                     ws.data_ptr(), splits.value, _stream()), "gsr_bgemm_reduce_f32")
+    return out
+
+
+def colsum(X: torch.Tensor) -> torch.Tensor:
+    X = _f32(X, "colsum: X")
+    X2 = X.reshape(-1, X.shape[-1])
+    out = torch.empty((X2.shape[1],), device=X.device, dtype=torch.float32)
+    check(lib().gsr_colsum_f32(X2.data_ptr(), out.data_ptr(), X2.shape[0], X2.shape[1], X2.shape[1], _stream()),
+          "gsr_colsum_f32")
+    return out
+
+
+# --------------------------------------------------------------------- sym / diag / abs
+def sym_diag_abs_fwd(x: torch.Tensor) -> torch.Tensor:
+    x = _f32(x, "sym_diag_abs: x")
+    batch, n = _square_batch(x, "sym_diag_abs: x")
+    out = torch.empty_like(x)
+    check(lib().gsr_sym_diag_abs_fwd(x.data_ptr(), out.data_ptr(), batch, n, _stream()), "gsr_sym_diag_abs_fwd")
+    return out
+
+
+def sym_diag_abs_bwd(x: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    x, grad_out = _f32(x, "x"), _f32(grad_out, "grad_out")
+    batch, n = _square_batch(x, "sym_diag_abs_bwd: x")
+    grad = torch.empty_like(x)
+    check(lib().gsr_sym_diag_abs_bwd(x.data_ptr(), grad_out.data_ptr(), grad.data_ptr(), batch, n, _stream()),
+          "gsr_sym_diag_abs_bwd")
+    return grad
+
+
+def abs_diag1(x: torch.Tensor) -> torch.Tensor:
+    x = _f32(x, "abs_diag1: x")
+    batch, n = _square_batch(x, "abs_diag1: x")
+    out = torch.empty_like(x)
+    check(lib().gsr_abs_diag1_fwd(x.data_ptr(), out.data_ptr(), batch, n, _stream()), "gsr_abs_diag1_fwd")
+    return out
+
+
+# --------------------------------------------------------------------- graph U-Net ops
+def pool_scores(X: torch.Tensor, p: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+    X, p, c = _f32(X, "pool: X"), _f32(p, "pool: proj.weight"), _f32(c, "pool: proj.bias")
+    n, d = X.shape
+    if p.numel() != d or c.numel() != 1:
+        raise ValueError("pool_scores: projection shape mismatch")
+    s = torch.empty((n,), device=X.device, dtype=torch.float32)
+    check(lib().gsr_pool_scores(X.data_ptr(), p.data_ptr(), c.data_ptr(), s.data_ptr(), n, d, _stream()),
+          "gsr_pool_scores")
+    return s
+
+
+def pool_topk(scores: torch.Tensor, k: int):
+    scores = _f32(scores, "topk: scores")
+    n = scores.numel()
+    idx = torch.empty((k,), device=scores.device, dtype=torch.int64)
+    vals = torch.empty((k,), device=scores.device, dtype=torch.float32)
+    check(lib().gsr_pool_topk(scores.data_ptr(), n, int(k), idx.data_ptr(), vals.data_ptr(), _stream()),
+          "gsr_pool_topk")
+    return vals, idx
+
+
+def pool_gather_scale(X: torch.Tensor, idx: torch.Tensor, vals: torch.Tensor) -> torch.Tensor:
+    X, idx, vals = _f32(X, "X"), _i64(idx, "idx"), _f32(vals, "values")
+    k, d = idx.numel(), X.shape[1]
+    out = torch.empty((k, d), device=X.device, dtype=torch.float32)
+    check(lib().gsr_pool_gather_scale_fwd(X.data_ptr(), idx.data_ptr(), vals.data_ptr(), out.data_ptr(), k, d, _stream()),
+          "gsr_pool_gather_scale_fwd")
+    return out
+
+
+def pool_bwd(X, p, scores, idx, grad_new_X):
+    X, p, scores, idx, g = _f32(X, "X"), _f32(p, "p"), _f32(scores, "scores"), _i64(idx, "idx"), _f32(grad_new_X, "grad")
+    n, d = X.shape
+    k = idx.numel()
+    gX = torch.empty_like(X)
+    gp = torch.empty((d,), device=X.device, dtype=torch.float32)
+    gc = torch.empty((1,), device=X.device, dtype=torch.float32)
+    ws = torch.empty((n,), device=X.device, dtype=torch.float32)
+    check(lib().gsr_pool_bwd(X.data_ptr(), p.data_ptr(), scores.data_ptr(), idx.data_ptr(), g.data_ptr(),
+                             gX.data_ptr(), gp.data_ptr(), gc.data_ptr(), ws.data_ptr(), n, k, d, _stream()),
+          "gsr_pool_bwd")
+    return gX, gp, gc
+
+
+def gather_rows_cols(A: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    A, idx = _f32(A, "A"), _i64(idx, "idx")
+    batch, n = _square_batch(A, "gather_rows_cols: A")
+    k = idx.numel()
+    out = torch.empty(A.shape[:-2] + (k, k), device=A.device, dtype=torch.float32)
+    check(lib().gsr_gather_rows_cols(A.data_ptr(), idx.data_ptr(), out.data_ptr(), batch, n, k, _stream()),
+          "gsr_gather_rows_cols")
+    return out
+
+
+def unpool_fwd(X: torch.Tensor, idx: torch.Tensor, n: int) -> torch.Tensor:
+    X, idx = _f32(X, "X"), _i64(idx, "idx")
+    k, d = X.shape
+    if idx.numel() != k:
+        raise ValueError("unpool: idx length != rows of X")
+    out = torch.empty((n, d), device=X.device, dtype=torch.float32)
+    check(lib().gsr_unpool_fwd(X.data_ptr(), idx.data_ptr(), out.data_ptr(), n, k, d, _stream()), "gsr_unpool_fwd")
+    return out
+
+
+def unpool_bwd(grad_new_X: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    g, idx = _f32(grad_new_X, "grad"), _i64(idx, "idx")
+    k, d = idx.numel(), g.shape[1]
+    out = torch.empty((k, d), device=g.device, dtype=torch.float32)
+    check(lib().gsr_unpool_bwd(g.data_ptr(), idx.data_ptr(), out.data_ptr(), k, d, _stream()), "gsr_unpool_bwd")
+    return out
+
+
+# --------------------------------------------------------------------- L1 loss
+def l1_loss_fwd(x: torch.Tensor, y: torch.Tensor, batch: int, shared_y: bool) -> torch.Tensor:
+    """x viewed as [batch, count]; y is [batch, count] or, with shared_y, [count]."""
+    x, y = _f32(x, "l1: x"), _f32(y, "l1: y")
+    count = x.numel() // batch
+    loss = torch.empty((batch,), device=x.device, dtype=torch.float32)
+    chunks = lib().gsr_l1_partials(count)
+    part = torch.empty((batch * chunks,), device=x.device, dtype=torch.float64)
+    check(lib().gsr_l1_loss_fwd(x.data_ptr(), y.data_ptr(), 0 if shared_y else count, loss.data_ptr(),
+                                part.data_ptr(), batch, count, _stream()), "gsr_l1_loss_fwd")
+    return loss
+
+
+def l1_loss_bwd(x: torch.Tensor, y: torch.Tensor, grad_loss: torch.Tensor, batch: int, shared_y: bool) -> torch.Tensor:
+    x, y, grad_loss = _f32(x, "l1: x"), _f32(y, "l1: y"), _f32(grad_loss, "l1: grad")
+    count = x.numel() // batch
+    gx = torch.empty_like(x)
+    check(lib().gsr_l1_loss_bwd(x.data_ptr(), y.data_ptr(), 0 if shared_y else count, grad_loss.data_ptr(),
+                                gx.data_ptr(), batch, count, _stream()), "gsr_l1_loss_bwd")
+    return gx
+
+
+# --------------------------------------------------------------------- vectoriser
+def vectorize_len(n: int, include_diagonal: bool) -> int:
+    return int(lib().gsr_vectorize_len(int(n), int(include_diagonal)))
+
+
+def vectorize(matrix: torch.Tensor, include_diagonal: bool = False) -> torch.Tensor:
+    if not matrix.is_cuda:
+        raise RuntimeError("vectorize: expected a CUDA tensor")
+    matrix = matrix.contiguous()
+    batch, n = _square_batch(matrix, "vectorize: matrix")
+    L = vectorize_len(n, include_diagonal)
+    out = torch.empty(matrix.shape[:-2] + (L,), device=matrix.device, dtype=matrix.dtype)
+    if L:
+        check(lib().gsr_vectorize(matrix.data_ptr(), out.data_ptr(), batch, n, matrix.element_size(),
+                                  int(include_diagonal), _stream()), "gsr_vectorize")
+    return out
+
+
+def anti_vectorize(vec: torch.Tensor, n: int, include_diagonal: bool = False) -> torch.Tensor:
+    vec = _f32(vec, "anti_vectorize: vector")
+    if vec.dim() not in (1, 2):
+        raise ValueError("anti_vectorize: expected [len] or [batch, len]")
+    batch = 1 if vec.dim() == 1 else vec.shape[0]
+    out = torch.empty(vec.shape[:-1] + (n, n), device=vec.device, dtype=torch.float32)
+    check(lib().gsr_anti_vectorize(vec.data_ptr(), out.data_ptr(), batch, int(n), vec.shape[-1],
+                                   int(include_diagonal), _stream()), "gsr_anti_vectorize")
+    return out
+
+
+# --------------------------------------------------------------------- evaluation
+def eval_reduce(pred: torch.Tensor, gt: torch.Tensor, upper: bool) -> torch.Tensor:
+    """Returns a device fp64 tensor [mae, pcc, js_distance]."""
+    pred, gt = _f32(pred, "eval: pred"), _f32(gt, "eval: gt")
+    if pred.shape != gt.shape:
+        raise ValueError("eval_reduce: shape mismatch")
+    if upper:
+        if pred.dim() == 2:
+            pred, gt = pred[None], gt[None]
+        batch, n = pred.shape[0], pred.shape[-1]
+    else:
+        batch, n = 1, pred.numel()
+        if n >= 2 ** 31:
+            n = pred.shape[-1]
+            batch = pred.numel() // n
+    ws = torch.empty((lib().gsr_eval_workspace(),), device=pred.device, dtype=torch.float64)
+    res = torch.empty((3,), device=pred.device, dtype=torch.float64)
+    check(lib().gsr_eval_reduce(pred.data_ptr(), gt.data_ptr(), batch, n, int(upper), ws.data_ptr(),
+                                res.data_ptr(), _stream()), "gsr_eval_reduce")
+    return res
+
+
+# --------------------------------------------------------------------- flat gradient bucket
+class FlatBucket:
+    """Device-side table (pointers + offsets) of a list of fp32 tensors, for the one-launch
+    pack / unpack around the NCCL all-reduce of the subject-data-parallel step."""
+
+    def __init__(self, tensors):
+        self.tensors = [t for t in tensors]
+        for t in self.tensors:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise TypeError("FlatBucket: tensors must be contiguous CUDA float32")
+        dev = self.tensors[0].device
+        offs = [0]
+        for t in self.tensors:
+            offs.append(offs[-1] + t.numel())
+        self.total = offs[-1]
+        self.ptrs = torch.tensor([t.data_ptr() for t in self.tensors], dtype=torch.int64, device=dev)
+        self.offsets = torch.tensor(offs, dtype=torch.int64, device=dev)
+        self.flat = torch.empty((self.total,), device=dev, dtype=torch.float32)
+
+    def pack(self, scale: float = 1.0) -> torch.Tensor:
+        check(lib().gsr_flat_pack(self.ptrs.data_ptr(), self.offsets.data_ptr(), len(self.tensors),
+                                  self.flat.data_ptr(), self.total, float(scale), _stream()), "gsr_flat_pack")
+        return self.flat
+
+    def unpack(self, scale: float = 1.0) -> None:
+        check(lib().gsr_flat_unpack(self.ptrs.data_ptr(), self.offsets.data_ptr(), len(self.tensors),
+                                    self.flat.data_ptr(), self.total, float(scale), _stream()), "gsr_flat_unpack")

@@ -1,0 +1,44 @@
+"""GSRNet -- drop-in for the reference's models/gsr_model.py:10-37.
+
+Same constructor (``GSRNet(ks, args)`` with args.lr_dim / hr_dim / hidden_dim), same
+sub-module and parameter names (31 state_dict keys), same 4-tuple return and cached
+attributes.  Extension: ``forward`` also accepts a subject batch [B, lr, lr] and then returns
+[B, hr, hr] predictions; the Graph U-Net runs ONCE per call because its output does not depend
+on the subject (it is fed the identity and its GCN ignores the adjacency).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import functional as F_
+from .layers import GSRLayer, GraphConvolution
+from .ops import GraphUnet
+
+device = torch.device("cuda")
+
+
+class GSRNet(nn.Module):
+    def __init__(self, ks, args):
+        super().__init__()
+        self.lr_dim = args.lr_dim
+        self.hr_dim = args.hr_dim
+        self.hidden_dim = args.hidden_dim
+        self.layer = GSRLayer(self.hr_dim, self.lr_dim)
+        self.net = GraphUnet(ks, self.lr_dim, self.hr_dim)
+        self.gc1 = GraphConvolution(self.hr_dim, self.hidden_dim, 0, act=F.relu)
+        self.gc2 = GraphConvolution(self.hidden_dim, self.hr_dim, 0, act=F.relu)
+
+    def forward(self, lr, U=None):
+        lr = lr if lr.is_cuda else lr.to(device)
+        if self.layer.weights.device.type != "cuda":
+            raise RuntimeError("GSRNet: move the model to the GPU first (model.to('cuda')); there is no CPU path")
+        I = torch.eye(self.lr_dim, device=lr.device)                                  # :24
+        A = F_.normalize_adj(lr)                                                      # :25
+        self.net_outs, self.start_gcn_outs = self.net(A, I)                           # :27
+        self.outputs, self.Z = self.layer(A, self.net_outs, U=U)                      # :28
+        self.hidden1 = self.gc1(self.Z, self.outputs)                                 # :29
+        self.hidden2 = self.gc2(self.hidden1, self.outputs)                           # :30
+        z = F_.sym_diag_abs(self.hidden2)                                             # :32-37
+        return z, self.net_outs, self.start_gcn_outs, self.outputs

@@ -1,0 +1,166 @@
+"""train / test -- drop-ins for the reference's utils/gsr_train.py:11-85, plus the batched
+step the B200 path is built around.
+
+``train`` and ``test`` keep the reference's per-subject semantics (one optimiser step per
+subject, numpy inputs, print-only, return None).  ``GSRTrainStep`` / ``train_batched`` run B
+subjects per step with frozen weights inside the step: the loss is the MEAN over the subjects of
+the reference's per-subject loss, so the gradients equal the average of the reference's
+per-subject gradients.  Importing this module has no side effects (the reference
+loads its CSVs at import time, utils/gsr_train.py:88 -- deliberately not reproduced).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import functional as F_
+from .preprocessing import pad_HR_adj, unpad
+
+
+def criterion(x, y):
+    """nn.L1Loss() of utils/gsr_train.py:9 on the sm_100a reduction kernels."""
+    return F_.l1_loss(x, y)
+
+
+def hr_target_basis(hr, lr_dim, padding=0, check_errors=True):
+    """utils/gsr_train.py:33-36: eigenvectors of the ``lr_dim`` SMALLEST eigenvalues of the
+    padded, unit-diagonal HR target.  Data-only: callers may cache it across epochs."""
+    padded_hr = pad_HR_adj(hr, padding)
+    _, U_hr, _ = F_.eigh(padded_hr, "U", check_errors=check_errors)
+    return U_hr[..., :, :lr_dim].contiguous()
+
+
+def train(model, optimizer, subjects_adj, subjects_labels, args):
+    """utils/gsr_train.py:11-53."""
+    device = torch.device("cuda")
+    model.to(device)
+    i = 0
+    all_epochs_loss = []
+    no_epochs = args.epochs
+    for epoch in range(no_epochs):
+        epoch_loss = []
+        epoch_error = []
+        for lr, hr in zip(subjects_adj, subjects_labels):
+            model.train()
+            optimizer.zero_grad()
+            lr = torch.from_numpy(lr).type(torch.FloatTensor).to(device)
+            hr = torch.from_numpy(hr).type(torch.FloatTensor).to(device)
+            model_outputs, net_outs, start_gcn_outs, layer_outs = model(lr)
+            model_outputs = unpad(model_outputs, args.padding)
+            U_hr_reduced = hr_target_basis(hr, model.layer.lr_dim, args.padding)
+            loss = args.lmbda * criterion(net_outs, start_gcn_outs) + \
+                criterion(model.layer.weights, U_hr_reduced) + \
+                criterion(model_outputs, hr)
+            error = criterion(model_outputs, hr)
+            loss.backward()
+            optimizer.step()
+            epoch_loss.append(loss.item())
+            epoch_error.append(error.item())
+        i += 1
+        print(f"Epoch: {i}, Loss: {np.mean(epoch_loss)}, Error (MAE): {np.mean(epoch_error)}")
+        all_epochs_loss.append(np.mean(epoch_loss))
+
+
+def test(model, test_adj, test_labels, args):
+    """utils/gsr_train.py:55-85 (including the in-place unit diagonal on the caller's array)."""
+    device = torch.device("cuda")
+    model.to(device)
+    test_error = []
+    preds_list = []
+    g_t = []
+    i = 0
+    for lr, hr in zip(test_adj, test_labels):
+        all_zeros_lr = not np.any(lr)
+        all_zeros_hr = not np.any(hr)
+        if not all_zeros_lr and not all_zeros_hr:
+            lr = torch.from_numpy(lr).type(torch.FloatTensor).to(device)
+            np.fill_diagonal(hr, 1)
+            hr = torch.from_numpy(hr).type(torch.FloatTensor).to(device)
+            with torch.no_grad():           # the reference builds and discards a graph here
+                preds, _, _, _ = model(lr)
+            preds = unpad(preds, args.padding)
+            preds_list.append(preds.flatten().detach().cpu().numpy())
+            error = criterion(preds, hr)
+            g_t.append(hr.flatten().cpu().numpy())
+            print(f"MAE: {error.item()}")
+            test_error.append(error.item())
+            i += 1
+    print(f"Test error MAE: {np.mean(test_error)}")
+
+
+# ----------------------------------------------------------------------------- batched step
+class GSRTrainStep:
+    """One forward + backward of the reference's loss (utils/gsr_train.py:30-45) over a batch
+    of subjects resident on the device.
+
+        step = GSRTrainStep(model, lmbda=16, padding=0)
+        loss, error = step(lr_batch, hr_batch)        # [B,lr,lr], [B,hr,hr]; gradients in .grad
+
+    ``loss`` / ``error`` are device scalars (means over the subjects); nothing synchronises
+    unless ``check_errors`` asks for torch.linalg.eigh's raise-on-failure contract.
+    ``U_hr_reduced`` may be passed when the caller caches the data-only HR target basis."""
+
+    def __init__(self, model, lmbda=16, padding=0, check_errors=False):
+        self.model, self.lmbda, self.padding, self.check_errors = model, lmbda, padding, check_errors
+        model.layer.check_eigh = False
+
+    def forward_loss(self, lr, hr, U_hr_reduced=None, U_lr=None):
+        model = self.model
+        out, net_outs, start_gcn_outs, _ = model(lr, U=U_lr)
+        out = unpad(out, self.padding)
+        if U_hr_reduced is None:
+            U_hr_reduced = hr_target_basis(hr, model.layer.lr_dim, self.padding, check_errors=False)
+        err_b = F_.l1_loss_per_subject(out, hr)                                  # [B]
+        w_b = F_.l1_loss_per_subject(U_hr_reduced, model.layer.weights)          # |W - U_hr| per subject
+        reg = F_.l1_loss(net_outs, start_gcn_outs)
+        error = err_b.mean()
+        loss = self.lmbda * reg + w_b.mean() + error
+        return loss, error
+
+    def __call__(self, lr, hr, U_hr_reduced=None, U_lr=None):
+        loss, error = self.forward_loss(lr, hr, U_hr_reduced, U_lr)
+        loss.backward()
+        if self.check_errors and self.model.layer.eigh_info is not None:
+            F_.raise_on_eigh_info(self.model.layer.eigh_info)
+        return loss.detach(), error.detach()
+
+
+def train_batched(model, optimizer, subjects_adj, subjects_labels, args, batch_size=64,
+                  cache_eigenbases=True, grad_sync=None, verbose=True):
+    """Batched counterpart of ``train``: one optimiser step per ``batch_size`` subjects.
+    The LR / HR eigenbases depend on the data only and are computed once (first epoch) when
+    ``cache_eigenbases`` is set.  ``grad_sync`` (e.g. SubjectParallel.sync_gradients) is called
+    between backward and the optimiser step.  Returns the list of epoch mean losses."""
+    device = torch.device("cuda")
+    model.to(device)
+    lr_all = torch.as_tensor(np.asarray(subjects_adj), dtype=torch.float32).to(device)
+    hr_all = torch.as_tensor(np.asarray(subjects_labels), dtype=torch.float32).to(device)
+    step = GSRTrainStep(model, args.lmbda, args.padding)
+    n = lr_all.shape[0]
+    U_lr_cache, U_hr_cache = {}, {}
+    history = []
+    for epoch in range(args.epochs):
+        losses, errors = [], []
+        for s in range(0, n, batch_size):
+            lr, hr = lr_all[s:s + batch_size], hr_all[s:s + batch_size]
+            model.train()
+            optimizer.zero_grad(set_to_none=True)
+            U_lr = U_hr = None
+            if cache_eigenbases:
+                if s not in U_hr_cache:
+                    U_hr_cache[s] = hr_target_basis(hr, model.layer.lr_dim, args.padding)
+                    from .preprocessing import normalize_adj_torch
+                    U_lr_cache[s] = F_.eigh(normalize_adj_torch(lr), "U")[1]
+                U_lr, U_hr = U_lr_cache[s], U_hr_cache[s]
+            loss, error = step(lr, hr, U_hr_reduced=U_hr, U_lr=U_lr)
+            if grad_sync is not None:
+                grad_sync()
+            optimizer.step()
+            losses.append(loss)
+            errors.append(error)
+        ml = float(torch.stack(losses).mean())
+        me = float(torch.stack(errors).mean())
+        history.append(ml)
+        if verbose:
+            print(f"Epoch: {epoch + 1}, Loss: {ml}, Error (MAE): {me}")
+    return history

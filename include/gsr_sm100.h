@@ -1,0 +1,214 @@
+/*
+ * gsr_sm100.h -- C ABI of libgsr_sm100.so, the B200 (sm_100a) kernels behind the
+ * GSR-Net hot path of denisfouchard/fMRI-connectivity-super-resolution.
+ *
+ * The reference has no FFI of its own (it is pure Python on PyTorch eager ops);
+ * the boundary a maintainer binds is therefore "one entry point per eager op (or
+ * fused group of eager ops) the reference calls on this path".  Every
+ * declaration below cites the reference lines it replaces (paths relative to
+ * the reference repository root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     its name ends in _host; matrices are fp32, row-major, contiguous, with a
+ *     leading batch ("subjects") dimension; indices are int64 (torch's dtype);
+ *   - `stream` is a cudaStream_t passed as void*; calls never synchronise,
+ *     never allocate, never throw; the caller owns all memory and keeps it
+ *     alive until the stream has consumed it;
+ *   - return value: 0 = ok, < 0 = bad argument (GSR_E_*), > 0 = cudaError_t of
+ *     the launch.  gsr_last_error() gives a static, thread-local description.
+ */
+#ifndef GSR_SM100_H
+#define GSR_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define GSR_API __attribute__((visibility("default")))
+#else
+#define GSR_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_ABI_VERSION 1
+
+#define GSR_E_ARG        (-1)   /* null pointer / negative size                     */
+#define GSR_E_UNSUPPORTED (-2)  /* size outside what the kernels are built for      */
+#define GSR_E_ALIGN      (-3)   /* pointer / leading dimension not 16-byte aligned  */
+
+GSR_API int         gsr_abi_version(void);
+GSR_API const char* gsr_last_error(void);
+/* Number of kernels launched by this library since load (bench.py "gpu_launches"). */
+GSR_API uint64_t    gsr_launch_count(void);
+/* Kernel-variant selection for benchmarking ("gemm_variant": 0, 1, 2; see csrc/bgemm.cu).
+ * Results are identical across variants (same arithmetic order).                 */
+GSR_API int         gsr_set_tuning(const char* key, int value);
+
+/* ------------------------------------------------------------------ a1
+ * utils/preprocessing.py:16-25  normalize_adj_torch
+ *   r = rowsum(M)^-1/2 (inf -> 0);  out[i,j] = (M[j,i] * r_i) * r_j   (no +I, transposed)
+ * pre = 0: M = mx.   pre = 1: M = |mx| with unit diagonal, i.e. the
+ *   `f_d = abs(f_d); f_d.fill_diagonal_(1)` of models/layers.py:55-56 fused in
+ *   front (mx is then the raw W.U^T.f product).
+ * r_out [batch,n] is kept for the backward; m_out (nullable) receives M.        */
+GSR_API int gsr_normalize_adj_fwd(const float* mx, float* out, float* r_out, float* m_out,
+                          int batch, int n, int pre, void* stream);
+/* autograd of the above: grad_mx = d/d mx  sum(out * grad_out).  With pre = 1
+ * the gradient passes through abs (sgn(0) = 0) and is zero on the diagonal
+ * (fill_diagonal_ overwrites it).                                     */
+GSR_API int gsr_normalize_adj_bwd(const float* mx, const float* r, const float* grad_out,
+                          float* grad_mx, int batch, int n, int pre, void* stream);
+
+/* ------------------------------------------------------------------ a2 / a12
+ * models/layers.py:27 and utils/gsr_train.py:34  torch.linalg.eigh(A, UPLO='U')
+ * Batched one-sided (Hestenes) Jacobi on A + sigma*I held in shared memory, one
+ * CTA per graph (n <= GSR_EIGH_MAX_N_CTA) or one 2-CTA cluster per graph over
+ * distributed shared memory (n <= GSR_EIGH_MAX_N).  Only the upper triangle of
+ * A is read.  Eigenvalues ascending in w[batch,n]; eigenvector k in COLUMN k of
+ * U[batch,n,n].  canonical_sign != 0 applies the documented sign rule: the
+ * component of largest magnitude (lowest row on ties) of every eigenvector is
+ * positive.  info[batch]: > 0 = sweeps used; -1 = non-finite input (outputs are
+ * NaN); -2 = not converged after max_sweeps (torch raises LinAlgError in both
+ * cases; the Python wrapper does the same).  tol <= 0 / max_sweeps <= 0 select
+ * the defaults (1e-6, 30).                                                       */
+#define GSR_EIGH_MAX_N_CTA 224
+#define GSR_EIGH_MAX_N     288
+GSR_API int gsr_eigh_jacobi_f32(const float* A, float* w, float* U, int32_t* info,
+                        int batch, int n, int canonical_sign, float tol, int max_sweeps,
+                        void* stream);
+
+/* ------------------------------------------------------------------ a3-a5, a7
+ * Every torch.mm / torch.matmul / nn.Linear on the path:
+ *   models/layers.py:37,45,54 (W.U^T.f, without the zero padding), :59 (adj.adj^T),
+ *   :85-86 (adj @ (x @ W)), models/ops.py:60 (Linear) and their autograd.
+ * C[b] = alpha * op(A[b]) . op(B[b]) (+ epilogue), b < batch, fp32 SIMT FMA.
+ *   op = transpose when trans* != 0; A is M x K (or K x M when transposed) with
+ *   leading dimension lda; stride* are ELEMENT strides between subjects, 0 = the
+ *   operand is shared by all subjects (a weight).
+ * epilogue: GSR_EPI_NONE; GSR_EPI_BIAS adds extra[n] (Linear bias);
+ *   GSR_EPI_ADD adds extra[b][m][n] (ld_extra, stride_extra) -- the "+=" of a
+ *   gradient with several producers and the U-Net skip connection.
+ * Leading dimensions and strides must be multiples of 4 and pointers 16-byte
+ * aligned for the fast path; anything else takes a scalar-load variant of the
+ * same kernel (same arithmetic order).                                           */
+#define GSR_EPI_NONE 0
+#define GSR_EPI_BIAS 1
+#define GSR_EPI_ADD  2
+GSR_API int gsr_bgemm_f32(const float* A, const float* B, float* C,
+                  int M, int N, int K, int lda, int ldb, int ldc,
+                  long long strideA, long long strideB, long long strideC,
+                  int transA, int transB, int batch, float alpha,
+                  int epilogue, const float* extra, int ld_extra, long long stride_extra,
+                  void* stream);
+/* Weight gradients: C = alpha * sum_b op(A[b]) . op(B[b]) (+ extra[m][n] when
+ * epilogue == GSR_EPI_ADD).  Subjects are dealt to `splits` CTAs per tile which
+ * each accumulate in registers; partial tiles go to workspace
+ * [splits, M, N] and are summed in a fixed order (deterministic).
+ * gsr_bgemm_reduce_workspace() returns the floats needed and the split count
+ * the library would pick for (M, N, batch).                                      */
+GSR_API size_t gsr_bgemm_reduce_workspace(int M, int N, int batch, int* splits_out);
+GSR_API int gsr_bgemm_reduce_f32(const float* A, const float* B, float* C,
+                         int M, int N, int K, int lda, int ldb, int ldc,
+                         long long strideA, long long strideB,
+                         int transA, int transB, int batch, float alpha,
+                         int epilogue, const float* extra, int ld_extra,
+                         float* workspace, int splits, void* stream);
+/* Column sums of a [rows, cols] matrix (Linear bias gradient, models/ops.py:60). */
+GSR_API int gsr_colsum_f32(const float* X, float* out, int rows, int cols, int ld, void* stream);
+
+/* ------------------------------------------------------------------ a4 / a6
+ * models/layers.py:60-63 and models/gsr_model.py:32-37:
+ *   X = (X + X^T)/2; X[diag] = 1; return |X|                                     */
+GSR_API int gsr_sym_diag_abs_fwd(const float* x, float* out, int batch, int n, void* stream);
+/* autograd of the above: with z = (x + x^T)/2, dz = grad_out * sgn(z) (0 on the
+ * diagonal), grad_x = (dz + dz^T)/2.                                             */
+GSR_API int gsr_sym_diag_abs_bwd(const float* x, const float* grad_out, float* grad_x,
+                         int batch, int n, void* stream);
+/* models/layers.py:55-56 alone (the stored `self.f_d`): out = |x|, unit diagonal. */
+GSR_API int gsr_abs_diag1_fwd(const float* x, float* out, int batch, int n, void* stream);
+
+/* ------------------------------------------------------------------ a8-a10
+ * models/ops.py:35-38  scores = sigmoid((X . p + c) / 100)                       */
+GSR_API int gsr_pool_scores(const float* X, const float* p, const float* c, float* scores,
+                    int n, int d, void* stream);
+/* models/ops.py:42  torch.topk(scores, k) under the stated tie rule (score
+ * descending, index ascending; NaN sorts first as in torch).  One CTA, n <= 4096. */
+GSR_API int gsr_pool_topk(const float* scores, int n, int k, int64_t* idx, float* values,
+                  void* stream);
+/* models/ops.py:43-45  new_X = X[idx, :] * values[:, None]                       */
+GSR_API int gsr_pool_gather_scale_fwd(const float* X, const int64_t* idx, const float* values,
+                              float* new_X, int k, int d, void* stream);
+/* autograd of pool_scores + topk values + gather_scale w.r.t. X, p, c.           */
+GSR_API int gsr_pool_bwd(const float* X, const float* p, const float* scores, const int64_t* idx,
+                 const float* grad_new_X, float* grad_X, float* grad_p, float* grad_c,
+                 float* ds_workspace /* n floats */, int n, int k, int d, void* stream);
+/* models/ops.py:46-47  A[idx, :][:, idx]  (bit exact gather)                     */
+GSR_API int gsr_gather_rows_cols(const float* A, const int64_t* idx, float* out,
+                         int batch, int n, int k, void* stream);
+/* models/ops.py:22-23  new_X = zeros(n, d); new_X[idx] = X   and its autograd
+ * (row gather).                                                                  */
+GSR_API int gsr_unpool_fwd(const float* X, const int64_t* idx, float* new_X, int n, int k, int d,
+                   void* stream);
+GSR_API int gsr_unpool_bwd(const float* grad_new_X, const int64_t* idx, float* grad_X, int k, int d,
+                   void* stream);
+
+/* ------------------------------------------------------------------ a13
+ * utils/gsr_train.py:9,39-43  nn.L1Loss(): per-subject mean |x - y|.
+ *   x, y: [batch, count]; y_stride = 0 shares y across the batch.
+ *   loss_out[batch] (fp32).  Deterministic two-stage reduction; partials needs
+ *   gsr_l1_partials(count) * batch doubles.                                      */
+GSR_API int gsr_l1_partials(long long count);
+GSR_API int gsr_l1_loss_fwd(const float* x, const float* y, long long y_stride, float* loss_out,
+                    double* partials, int batch, long long count, void* stream);
+/* grad_x[b,i] = sgn(x - y) * grad_loss[b] / count   (sgn(0) = 0)                 */
+GSR_API int gsr_l1_loss_bwd(const float* x, const float* y, long long y_stride, const float* grad_loss,
+                    float* grad_x, int batch, long long count, void* stream);
+
+/* ------------------------------------------------------------------ a16 / a17
+ * utils/matrix_vectorizer.py:24-58  vectorize: strict upper triangle walked
+ * COLUMN-major; include_diagonal appends the SUB-diagonal element (c+1, c)
+ * after each column.  elem_size in {1,2,4,8,16} bytes (dtype is preserved, so
+ * this is a byte gather).  out: [batch, gsr_vectorize_len(n, include_diagonal)]. */
+GSR_API long long gsr_vectorize_len(int n, int include_diagonal);
+GSR_API int gsr_vectorize(const void* matrix, void* out, int batch, int n, int elem_size,
+                  int include_diagonal, void* stream);
+/* utils/matrix_vectorizer.py:61-95  anti_vectorize: ROW-major strict upper fill
+ * (torch.triu_indices order) mirrored; include_diagonal puts
+ * vec[n_el : n_el + n] on the MAIN diagonal; fp32 out.  vec_len >= n(n-1)/2 is
+ * the reference's assert (checked on the host side as well).                     */
+GSR_API int gsr_anti_vectorize(const float* vec, float* out, int batch, int n, long long vec_len,
+                       int include_diagonal, void* stream);
+
+/* ------------------------------------------------------------------ a18
+ * utils/evaluation.py:96-112  MAE, Pearson r, Jensen-Shannon distance over the
+ * concatenated vectorised upper triangles of pred / gt.  The three numbers do
+ * not depend on the order of the concatenation, so the kernels read the strict
+ * upper triangle of [batch, n, n] directly (upper != 0) or flat vectors
+ * (upper == 0, n = row length).  fp64 accumulators.
+ *   pass 1 -> sums[0..5] = { sum|p-g|, sum p, sum g, sum p^2, sum g^2, sum p*g }
+ *   pass 2 -> sums[6..7] = { sum a*log(a/m), sum b*log(b/m) },  a = g/sum g,
+ *             b = p/sum p, m = (a+b)/2   (rel_entr conventions of scipy)
+ * results_out[0..2] = { mae, pcc, js_distance } (device, fp64).
+ * workspace: gsr_eval_workspace() doubles.                                       */
+GSR_API size_t gsr_eval_workspace(void);
+GSR_API int gsr_eval_reduce(const float* pred, const float* gt, long long batch, int n, int upper,
+                    double* workspace, double* results_out, void* stream);
+
+/* ------------------------------------------------------------------ (e)
+ * Pack / unpack the 31 gradient tensors into one flat fp32 bucket for the
+ * single NCCL all-reduce of the subject-data-parallel step.  ptrs_dev[n_tensors] is a
+ * DEVICE array of device pointers, offsets_dev[n_tensors + 1] the DEVICE array of
+ * element offsets of each tensor inside the bucket; values are multiplied by scale. */
+GSR_API int gsr_flat_pack(const float* const* ptrs_dev, const long long* offsets_dev, int n_tensors,
+                  float* flat, long long total, float scale, void* stream);
+GSR_API int gsr_flat_unpack(float* const* ptrs_dev, const long long* offsets_dev, int n_tensors,
+                    const float* flat, long long total, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_SM100_H */

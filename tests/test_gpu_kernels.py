@@ -1,0 +1,481 @@
+"""GPU parity tests, kernel level: every libgsr_sm100 entry point against the CPU oracle
+(oracle/*.py, pinned to the reference by tests/test_oracle_golden.py) or, for the plain
+contractions, against a float64 torch product.  Run on the B200 box with ``-m gpu``.
+
+Tolerances (fp32): bit-exact for the vectoriser, top-k indices and gathers; 1e-6-level
+absolute / relative elsewhere, stated at each assert.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gsr_oracle as O
+from oracle import vectorizer_oracle as VO
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def dev(x):
+    return torch.as_tensor(x).cuda()
+
+
+@pytest.fixture(scope="module")
+def K(cuda_pkg):
+    return cuda_pkg.kernels
+
+
+# ------------------------------------------------------------------ vectoriser (bit exact)
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 33, 160, 268])
+@pytest.mark.parametrize("diag", [False, True])
+def test_vectorize_bit_exact(cuda_pkg, n, diag):
+    MV = cuda_pkg.MatrixVectorizer
+    rng = np.random.default_rng(n)
+    for dt in (np.float64, np.float32, np.int64, np.int16, np.uint8):
+        m = (rng.random((n, n)) * 100).astype(dt)
+        got = MV.vectorize(m, include_diagonal=diag)
+        want = VO.vectorize(m, include_diagonal=diag)
+        assert got.dtype == want.dtype and got.shape == want.shape, (n, dt)
+        assert np.array_equal(got, want), (n, dt)
+
+
+def test_vectorize_golden_digests(cuda_pkg, golden):
+    G = golden("vectorizer")
+    MV = cuda_pkg.MatrixVectorizer
+    for n in (160, 268):
+        m = G[f"vec_n{n}_in"]
+        assert sha(MV.vectorize(m)) == str(G[f"vec_n{n}_f32_d0_sha"])
+        assert sha(MV.vectorize(m, include_diagonal=True)) == str(G[f"vec_n{n}_f32_d1_sha"])
+    for key in G.files:
+        if key.startswith("vec_") and key.endswith("_in") and "_d" in key:
+            diag = key.split("_d")[1][0] == "1"
+            got = MV.vectorize(G[key], include_diagonal=diag)
+            assert got.dtype == G[key[:-3] + "_out"].dtype
+            assert np.array_equal(got, G[key[:-3] + "_out"]), key
+
+
+def test_vectorize_batched_device(K):
+    x = torch.rand(7, 268, 268, device="cuda")
+    for diag in (False, True):
+        got = K.vectorize(x, diag).cpu().numpy()
+        for b in range(7):
+            assert np.array_equal(got[b], VO.vectorize(x[b].cpu().numpy(), diag))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 160, 268])
+def test_anti_vectorize_bit_exact(cuda_pkg, golden, n):
+    G = golden("vectorizer")
+    MV = cuda_pkg.MatrixVectorizer
+    v = torch.from_numpy(G[f"anti_n{n}_in"])
+    for diag in (False, True):
+        for src in (v, v.cuda()):
+            got = MV.anti_vectorize(src, n, include_diagonal=diag)
+            assert got.dtype == torch.float32 and got.device == src.device
+            got = got.cpu().numpy()
+            assert np.array_equal(got, VO.anti_vectorize(v.numpy(), n, diag))
+            if n <= 8:
+                assert np.array_equal(got, G[f"anti_n{n}_d{int(diag)}_out"])
+            else:
+                assert sha(got) == str(G[f"anti_n{n}_d{int(diag)}_sha"])
+
+
+def test_anti_vectorize_errors(cuda_pkg):
+    MV = cuda_pkg.MatrixVectorizer
+    with pytest.raises(AssertionError):
+        MV.anti_vectorize(torch.zeros(5), 5)
+    with pytest.raises(TypeError):
+        MV.anti_vectorize(np.zeros(10), 5)
+    with pytest.raises(RuntimeError):
+        MV.anti_vectorize(torch.zeros(10, dtype=torch.float64), 5)
+
+
+def test_vectorizer_not_inverse_and_roundtrip_property(K):
+    # the two maps use different orders ...
+    v = torch.arange(10, dtype=torch.float32, device="cuda")
+    m = K.anti_vectorize(v, 5)
+    assert not torch.equal(K.vectorize(m), v)
+    # ... but both are permutations of the strict upper triangle: full-size property
+    x = torch.rand(64, 35778, device="cuda")
+    m = K.anti_vectorize(x, 268)
+    assert torch.equal(m, m.transpose(1, 2)) and float(m.diagonal(dim1=1, dim2=2).abs().max()) == 0.0
+    back = K.vectorize(m)
+    assert torch.equal(back.sort(dim=1).values, x.sort(dim=1).values)
+
+
+# ------------------------------------------------------------------ normalise
+@pytest.mark.parametrize("tag", ["sym12", "sym160", "nonsym9", "zerorow6", "negrow5"])
+def test_normalize_golden(cuda_pkg, golden, tag):
+    G = golden("ops")
+    got = cuda_pkg.normalize_adj_torch(dev(G[f"norm_{tag}_in"])).cpu().numpy()
+    want = G[f"norm_{tag}_out"]
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.allclose(got, want, rtol=2e-6, atol=1e-8, equal_nan=True)
+    if tag == "zerorow6":
+        assert np.all(got[2] == 0) and np.all(got[:, 2] == 0)
+
+
+@pytest.mark.parametrize("n,batch", [(10, 1), (160, 3), (268, 2), (37, 5)])
+def test_normalize_fwd_bwd_vs_oracle(cuda_pkg, n, batch):
+    g = torch.Generator().manual_seed(n)
+    mx = torch.rand(batch, n, n, generator=g)
+    T = torch.randn(batch, n, n, generator=g)
+    ref_in = mx.clone().requires_grad_(True)
+    ref = torch.stack([O.normalize_adj(ref_in[b]) for b in range(batch)])
+    (ref * T).sum().backward()
+    x = mx.cuda().requires_grad_(True)
+    out = cuda_pkg.normalize_adj_torch(x)
+    (out * T.cuda()).sum().backward()
+    assert torch.allclose(out.cpu(), ref.detach(), rtol=2e-6, atol=1e-9)
+    scale = float(ref_in.grad.abs().max())
+    assert torch.allclose(x.grad.cpu(), ref_in.grad, rtol=0, atol=2e-6 * scale)
+
+
+def test_normalize_pre_abs_diag(K):
+    g = torch.Generator().manual_seed(3)
+    F = torch.randn(2, 268, 268, generator=g)
+    T = torch.randn(2, 268, 268, generator=g)
+    ref_in = F.clone().requires_grad_(True)
+    outs = []
+    for b in range(2):
+        fd = torch.abs(ref_in[b])
+        fd = fd.fill_diagonal_(1)
+        outs.append(O.normalize_adj(fd))
+    ref = torch.stack(outs)
+    (ref * T).sum().backward()
+    out, r, m = K.normalize_adj_fwd(F.cuda(), pre=True, want_m=True)
+    assert torch.allclose(out.cpu(), ref.detach(), rtol=2e-6, atol=1e-9)
+    fd_ref = F.abs()
+    fd_ref.diagonal(dim1=1, dim2=2).fill_(1)
+    assert torch.equal(m.cpu(), fd_ref)
+    assert torch.equal(K.abs_diag1(F.cuda()).cpu(), fd_ref)
+    grad = K.normalize_adj_bwd(F.cuda(), r, T.cuda(), pre=True)
+    scale = float(ref_in.grad.abs().max())
+    assert torch.allclose(grad.cpu(), ref_in.grad, rtol=0, atol=2e-6 * scale)
+    assert float(grad.diagonal(dim1=1, dim2=2).abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ eigh
+def _eigh_checks(A32, w, U, tol_w=2e-6, tol_res=5e-6, tol_orth=1e-5):
+    A = A32.double().numpy()
+    A = np.triu(A) + np.triu(A, 1).T                      # only the upper triangle is read
+    w64 = np.linalg.eigvalsh(A)
+    scale = max(1.0, np.abs(w64).max())
+    w, U = w.double().numpy(), U.double().numpy()
+    assert np.all(np.diff(w) >= 0)
+    assert np.abs(w - w64).max() <= tol_w * scale
+    assert np.abs(A @ U - U * w).max() <= tol_res * scale
+    assert np.abs(U.T @ U - np.eye(A.shape[0])).max() <= tol_orth
+    # sign rule: the largest-|.| component of every column is positive
+    piv = np.abs(U).argmax(0)
+    assert np.all(U[piv, np.arange(U.shape[1])] > 0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 12, 31, 64, 136, 160, 161, 224])
+def test_eigh_properties(cuda_pkg, n):
+    F_ = cuda_pkg.functional
+    A = torch.stack([O.normalize_adj(O.synth_connectome(n, 50 + s)) if n > 1 else torch.tensor([[0.7]])
+                     for s in range(3)])
+    w, U, info = F_.eigh(A.cuda())
+    assert int(info.min()) > 0
+    for b in range(3):
+        _eigh_checks(A[b], w[b].cpu(), U[b].cpu())
+
+
+def test_eigh_generic_symmetric_and_upper_only(cuda_pkg):
+    F_ = cuda_pkg.functional
+    g = torch.Generator().manual_seed(0)
+    M = torch.randn(4, 96, 96, generator=g)
+    A = (M + M.transpose(1, 2)) / 2
+    junk = A.clone()
+    junk += torch.tril(torch.randn(96, 96, generator=g), -1)       # lower triangle must be ignored
+    w, U, _ = F_.eigh(junk.cuda())
+    for b in range(4):
+        _eigh_checks(A[b], w[b].cpu(), U[b].cpu(), tol_w=3e-6, tol_res=1e-5)
+
+
+def test_eigh_vs_oracle_vectors(cuda_pkg):
+    """Canonicalised eigenvectors against LAPACK's (oracle): compared where the spectrum is
+    well separated (gap > 1e-3), since eigenvectors of close pairs are ill conditioned in
+    fp32 for BOTH implementations."""
+    F_ = cuda_pkg.functional
+    A = O.normalize_adj(O.synth_connectome(160, 1000))
+    w_ref, U_ref = O.eigh_canonical(A)
+    w, U, _ = F_.eigh(A.cuda())
+    w, U = w.cpu(), U.cpu()
+    assert torch.allclose(w, w_ref, rtol=0, atol=2e-6)
+    gaps = torch.minimum(torch.diff(w_ref, prepend=w_ref[:1] - 1), torch.diff(w_ref, append=w_ref[-1:] + 1))
+    sep = gaps > 1e-3
+    assert int(sep.sum()) >= 10
+    assert torch.allclose(U[:, sep], U_ref[:, sep], rtol=0, atol=2e-3)
+    # subspace agreement for everything: |U^T U_ref| is a permutation-free near-identity in blocks
+    P = (U.double().T @ U_ref.double()).abs()
+    assert float((P.max(0).values).min()) > 0.5
+
+
+def test_eigh_error_contract(cuda_pkg):
+    F_ = cuda_pkg.functional
+    A = O.normalize_adj(O.synth_connectome(32, 1)).repeat(2, 1, 1)
+    A[1, 3, 5] = float("nan")
+    with pytest.raises(torch.linalg.LinAlgError):
+        F_.eigh(A.cuda())
+    w, U, info = F_.eigh(A.cuda(), check_errors=False)
+    assert info.tolist()[1] == -1 and info.tolist()[0] > 0
+    assert bool(torch.isnan(U[1]).all()) and not bool(torch.isnan(U[0]).any())
+    with pytest.raises(Exception):
+        cuda_pkg.kernels.eigh_jacobi(torch.zeros(1, 400, 400, device="cuda"))      # too large: loud, no fallback
+
+
+def test_eigh_full_batch_properties(cuda_pkg):
+    """BASELINE size: 1024 normalised 160-node graphs; size-independent properties."""
+    F_ = cuda_pkg.functional
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand(1024, 160, 160, device="cuda", generator=g)
+    lr = (x + x.transpose(1, 2)) / 2
+    lr.diagonal(dim1=1, dim2=2).zero_()
+    A = cuda_pkg.normalize_adj_torch(lr)
+    w, U, info = F_.eigh(A)
+    assert int(info.min()) > 0 and int(info.max()) <= 16
+    Ad, Ud, wd = A.double(), U.double(), w.double()
+    As = torch.triu(Ad) + torch.triu(Ad, 1).transpose(1, 2)
+    res = (As @ Ud - Ud * wd[:, None, :]).abs().amax()
+    orth = (Ud.transpose(1, 2) @ Ud - torch.eye(160, device="cuda", dtype=torch.float64)).abs().amax()
+    assert float(res) < 5e-6 and float(orth) < 1e-5
+    assert float((wd[:, -1] - 1).abs().max()) < 5e-6          # lambda_max of D^-1/2 A D^-1/2 is 1
+    tr = As.diagonal(dim1=1, dim2=2).sum(1)
+    assert float((wd.sum(1) - tr).abs().max()) < 2e-5         # trace is preserved
+
+
+# ------------------------------------------------------------------ GEMMs
+@pytest.mark.parametrize("tA", [False, True])
+@pytest.mark.parametrize("tB", [False, True])
+@pytest.mark.parametrize("shape", [(268, 268, 268), (268, 160, 160), (160, 268, 536), (101, 268, 268), (30, 7, 5), (1, 1, 1), (137, 139, 17)])
+def test_bgemm_vs_float64(K, tA, tB, shape):
+    M, N, Kd = shape
+    g = torch.Generator().manual_seed(M * 7 + N)
+    for batch, sharedB in ((1, False), (3, False), (3, True)):
+        A = torch.randn((batch, Kd, M) if tA else (batch, M, Kd), generator=g)
+        B = torch.randn((Kd, N) if not tB else (N, Kd), generator=g) if sharedB else \
+            torch.randn((batch, Kd, N) if not tB else (batch, N, Kd), generator=g)
+        opA = A.transpose(-1, -2) if tA else A
+        opB = B.transpose(-1, -2) if tB else B
+        want = (opA.double() @ opB.double())
+        got = K.bgemm(A.cuda(), B.cuda(), transA=tA, transB=tB).cpu()
+        tol = 2e-6 * float((opA.abs().double() @ opB.abs().double()).max())
+        assert got.shape == want.shape
+        assert float((got.double() - want).abs().max()) <= tol, (shape, tA, tB, batch, sharedB)
+
+
+def test_bgemm_epilogues_and_2d(K):
+    g = torch.Generator().manual_seed(5)
+    X, W, b = torch.randn(144, 268, generator=g), torch.randn(268, 268, generator=g), torch.randn(268, generator=g)
+    want = torch.nn.functional.linear(X.double(), W.double(), b.double())
+    got = K.bgemm(X.cuda(), W.cuda(), transB=True, bias=b.cuda()).cpu()
+    assert got.dim() == 2 and float((got.double() - want).abs().max()) < 2e-4
+    add = torch.randn(4, 268, 268, generator=g)
+    A, B = torch.randn(4, 268, 268, generator=g), torch.randn(4, 268, 268, generator=g)
+    want = 2.0 * (A.double() @ B.double()) + add.double()
+    got = K.bgemm(A.cuda(), B.cuda(), alpha=2.0, add=add.cuda()).cpu()
+    assert float((got.double() - want).abs().max()) < 5e-4
+    # stacked path with an addend (A 3-D, B shared)
+    Wm = torch.randn(268, 160, generator=g)
+    add2 = torch.randn(4, 268, 160, generator=g)
+    want = A.double() @ Wm.double() + add2.double()
+    got = K.bgemm(A.cuda(), Wm.cuda(), add=add2.cuda()).cpu()
+    assert float((got.double() - want).abs().max()) < 3e-4
+
+
+def test_bgemm_variants_agree_bitwise(cuda_pkg, K):
+    g = torch.Generator().manual_seed(9)
+    A, B = torch.randn(3, 268, 268, generator=g).cuda(), torch.randn(3, 268, 268, generator=g).cuda()
+    outs = []
+    for v in (0, 1, 2):
+        cuda_pkg.set_tuning("gemm_variant", v)
+        outs.append(K.bgemm(A, B, transB=True))
+    cuda_pkg.set_tuning("gemm_variant", 1)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
+@pytest.mark.parametrize("tA,tB", [(False, False), (True, False), (False, True)])
+def test_bgemm_reduce(K, tA, tB):
+    g = torch.Generator().manual_seed(11)
+    batch, M, N, Kd = 37, 160, 268, 268
+    A = torch.randn((batch, Kd, M) if tA else (batch, M, Kd), generator=g)
+    B = torch.randn((batch, N, Kd) if tB else (batch, Kd, N), generator=g)
+    add = torch.randn(M, N, generator=g)
+    opA = A.transpose(-1, -2) if tA else A
+    opB = B.transpose(-1, -2) if tB else B
+    want = (opA.double() @ opB.double()).sum(0) * 0.5 + add.double()
+    got = K.bgemm_reduce(A.cuda(), B.cuda(), transA=tA, transB=tB, alpha=0.5, add=add.cuda()).cpu()
+    tol = 2e-6 * float((opA.abs().double() @ opB.abs().double()).sum(0).max())
+    assert float((got.double() - want).abs().max()) <= tol
+    again = K.bgemm_reduce(A.cuda(), B.cuda(), transA=tA, transB=tB, alpha=0.5, add=add.cuda()).cpu()
+    assert torch.equal(got, again)                       # deterministic reduction order
+
+
+def test_bgemm_linearity_full_batch(K):
+    """BASELINE size (1024 subjects): C(A1 + A2) = C(A1) + C(A2) up to fp32 rounding, and the
+    stacked shared-weight path equals the per-subject path bit for bit."""
+    g = torch.Generator(device="cuda").manual_seed(2)
+    A1 = torch.rand(1024, 268, 268, device="cuda", generator=g)
+    A2 = torch.rand(1024, 268, 268, device="cuda", generator=g)
+    W = torch.randn(268, 268, device="cuda", generator=g)
+    c12 = K.bgemm(A1 + A2, W)
+    c1, c2 = K.bgemm(A1, W), K.bgemm(A2, W)
+    assert float((c12 - (c1 + c2)).abs().max()) < 1e-3 * float(c12.abs().max())
+    per_subject = K.bgemm(A1, W.expand(1024, 268, 268).contiguous())
+    assert torch.equal(per_subject, c1)
+    assert K.colsum(c1[0]).shape == (268,)
+    assert torch.allclose(K.colsum(c1[0]), c1[0].sum(0), rtol=1e-5, atol=1e-3)
+
+
+# ------------------------------------------------------------------ sym / diag / abs
+@pytest.mark.parametrize("n,batch", [(268, 2), (5, 1), (33, 3)])
+def test_sym_diag_abs(cuda_pkg, n, batch):
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(batch, n, n, generator=g)
+    T = torch.randn(batch, n, n, generator=g)
+    xr = x.clone().requires_grad_(True)
+    outs = []
+    for b in range(batch):
+        z = (xr[b] + xr[b].t()) / 2
+        z[torch.eye(n, dtype=torch.bool)] = 1
+        outs.append(torch.abs(z))
+    ref = torch.stack(outs)
+    (ref * T).sum().backward()
+    xc = x.cuda().requires_grad_(True)
+    out = cuda_pkg.functional.sym_diag_abs(xc)
+    (out * T.cuda()).sum().backward()
+    assert torch.equal(out.cpu(), ref.detach())
+    assert torch.allclose(xc.grad.cpu(), xr.grad, rtol=0, atol=1e-6)
+
+
+# ------------------------------------------------------------------ pooling
+def test_topk_bit_exact_with_ties(K, golden):
+    G = golden("ops")
+    _, idx = K.pool_topk(torch.full((160,), 0.5, device="cuda"), 144)
+    assert np.array_equal(idx.cpu().numpy(), G["tie_idx_stable"])
+    g = torch.Generator().manual_seed(4)
+    for n, k in ((160, 144), (144, 101), (101, 61), (61, 30), (9, 1), (7, 7)):
+        s = (torch.randint(0, 12, (n,), generator=g).float() / 16 + 0.25)      # many exact ties
+        vals, idx = K.pool_topk(s.cuda(), k)
+        rv, ri = O.stable_topk(s, k)
+        assert torch.equal(idx.cpu(), ri) and torch.equal(vals.cpu(), rv)
+    for i in range(4):
+        Gf = golden("gsrnet_full")
+        s = torch.from_numpy(Gf[f"pool{i}_scores"])
+        k = Gf[f"pool{i}_idx"].shape[0]
+        _, idx = K.pool_topk(s.cuda(), k)
+        assert np.array_equal(idx.cpu().numpy(), Gf[f"pool{i}_idx"])           # reference scores -> reference idx
+
+
+def test_pool_unpool_gather_vs_oracle(cuda_pkg, golden):
+    G = golden("ops")
+    pkg = cuda_pkg
+    pool = pkg.GraphPool(0.5, 4).cuda()
+    with torch.no_grad():
+        pool.proj.weight.copy_(dev(G["pool_w"]))
+        pool.proj.bias.copy_(dev(G["pool_b"]))
+    A2, X2, idx = pool(dev(G["pool_A"]), dev(G["pool_X"]))
+    assert np.array_equal(idx.cpu().numpy(), G["pool_idx"])
+    assert np.array_equal(A2.cpu().numpy(), G["pool_A_out"])                  # gather: bit exact
+    assert np.allclose(X2.detach().cpu().numpy(), G["pool_X_out"], rtol=1e-6, atol=1e-7)
+    unp = pkg.GraphUnpool()
+    _, up = unp(torch.zeros(6, 6, device="cuda"), dev(G["unpool_X"]), dev(G["unpool_idx"]))
+    assert np.array_equal(up.cpu().numpy(), G["unpool_out"])
+
+
+def test_pool_backward_vs_oracle(cuda_pkg):
+    g = torch.Generator().manual_seed(8)
+    n, d, k = 101, 268, 0.6
+    X = torch.randn(n, d, generator=g)
+    pw, pb = torch.randn(1, d, generator=g) * 0.5, torch.randn(1, generator=g)
+    T = torch.randn(O.pool_size(k, n), d, generator=g)
+    sd = {"p.proj.weight": pw.clone().requires_grad_(True), "p.proj.bias": pb.clone().requires_grad_(True)}
+    Xr = X.clone().requires_grad_(True)
+    _, newX, idx, scores = O.graph_pool(sd, "p", k, torch.zeros(n, n), Xr)
+    (newX * T).sum().backward()
+    pool = cuda_pkg.GraphPool(k, d).cuda()
+    with torch.no_grad():
+        pool.proj.weight.copy_(pw.cuda())
+        pool.proj.bias.copy_(pb.cuda())
+    Xc = X.cuda().requires_grad_(True)
+    new2, idx2, sc2 = pool.select(Xc)
+    (new2 * T.cuda()).sum().backward()
+    assert torch.allclose(sc2.cpu(), scores.detach(), rtol=0, atol=2e-7)
+    assert torch.equal(idx2.cpu(), idx)
+    assert torch.allclose(new2.detach().cpu(), newX.detach(), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(Xc.grad.cpu(), Xr.grad, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(pool.proj.weight.grad.cpu(), sd["p.proj.weight"].grad, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(pool.proj.bias.grad.cpu(), sd["p.proj.bias"].grad, rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------ L1 / evaluation
+def test_l1_loss(cuda_pkg):
+    F_ = cuda_pkg.functional
+    g = torch.Generator().manual_seed(6)
+    x, y = torch.randn(5, 268, 268, generator=g), torch.randn(5, 268, 268, generator=g)
+    y[0, :4] = x[0, :4]                                        # exact zeros: sgn(0) = 0
+    xr = x.clone().requires_grad_(True)
+    ref = torch.nn.L1Loss()(xr, y)
+    ref.backward()
+    xc = x.cuda().requires_grad_(True)
+    got = F_.l1_loss(xc, y.cuda())
+    got.backward()
+    assert float(got) == pytest.approx(float(ref), rel=2e-6)
+    assert torch.allclose(xc.grad.cpu(), xr.grad, rtol=1e-6, atol=0)
+    per = F_.l1_loss_per_subject(x.cuda(), y.cuda()).cpu()
+    assert torch.allclose(per, (x - y).abs().mean((1, 2)), rtol=2e-6)
+    # shared target + gradient into it (criterion(net_outs, start_gcn_outs) has grads on both sides)
+    a = torch.randn(160, 268, generator=g)
+    b = torch.randn(160, 268, generator=g)
+    ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    torch.nn.L1Loss()(ar, br).backward()
+    ac, bc = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    F_.l1_loss(ac, bc).backward()
+    assert torch.allclose(ac.grad.cpu(), ar.grad) and torch.allclose(bc.grad.cpu(), br.grad)
+    # shared y across a batch, gradient reduced over the subjects
+    u = torch.randn(4, 268, 160, generator=g)
+    w = torch.randn(268, 160, generator=g)
+    wr = w.clone().requires_grad_(True)
+    torch.stack([torch.nn.L1Loss()(wr, u[i]) for i in range(4)]).mean().backward()
+    wc = w.cuda().requires_grad_(True)
+    F_.l1_loss_per_subject(u.cuda(), wc).mean().backward()
+    assert torch.allclose(wc.grad.cpu(), wr.grad, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("tag", ["small", "hr"])
+def test_eval_reductions_golden(cuda_pkg, golden, tag):
+    G = golden("eval")
+    N, n = int(G[f"{tag}_N"]), int(G[f"{tag}_n"])
+    gts, preds = [], []
+    for i in range(N):
+        gt = O.synth_connectome(n, 900 + i)
+        g = torch.Generator().manual_seed(1900 + i)
+        noise = torch.randn(n, n, generator=g) * 0.1
+        pred = torch.clamp(gt + (noise + noise.t()) / 2, 0, 1)
+        pred.fill_diagonal_(0)
+        gts.append(gt.numpy()); preds.append(pred.numpy())
+    mae, pcc, js = cuda_pkg.evaluation_reductions(np.stack(preds), np.stack(gts))
+    assert mae == pytest.approx(float(G[f"{tag}_mae64"]), rel=1e-12)
+    assert pcc == pytest.approx(float(G[f"{tag}_pcc64"]), rel=1e-9)
+    assert js == pytest.approx(float(G[f"{tag}_js64"]), rel=1e-9)
+    # flat (already vectorised) entry agrees
+    p1 = np.concatenate([VO.vectorize(m) for m in preds]); g1 = np.concatenate([VO.vectorize(m) for m in gts])
+    from importlib import import_module
+    ev = import_module(cuda_pkg.__name__ + ".utils.evaluation")
+    mae2, pcc2, js2 = ev.evaluation_reductions_flat(p1, g1)
+    assert mae2 == pytest.approx(mae, rel=1e-12) and pcc2 == pytest.approx(pcc, rel=1e-10) and js2 == pytest.approx(js, rel=1e-10)
+
+
+def test_eval_reductions_zero_entries(cuda_pkg):
+    # rel_entr conventions: zeros in gt and pred contribute 0, not NaN
+    gt = torch.rand(3, 20, 20); pred = torch.rand(3, 20, 20)
+    gt[0, 1, 5] = 0; pred[1, 2, 7] = 0; gt[2, 3, 9] = 0; pred[2, 3, 9] = 0
+    mae, pcc, js = cuda_pkg.evaluation_reductions(pred.numpy(), gt.numpy())
+    m2, p2, j2 = VO.eval_reductions(pred.numpy(), gt.numpy())
+    assert mae == pytest.approx(m2, rel=1e-12) and pcc == pytest.approx(p2, rel=1e-9) and js == pytest.approx(j2, rel=1e-9)
