@@ -56,6 +56,7 @@ PROTOTYPES = {
     "gsr_eval_reduce": (i32, [c_ptr, c_ptr, i64, i32, i32, c_ptr, c_ptr, c_ptr]),
     "gsr_flat_pack": (i32, [c_ptr, c_ptr, i32, c_ptr, i64, f32, c_ptr]),
     "gsr_flat_unpack": (i32, [c_ptr, c_ptr, i32, c_ptr, i64, f32, c_ptr]),
+    "gsr_ffma_probe": (C.c_double, [i32, c_ptr, c_ptr]),
 }
 
 

@@ -42,3 +42,28 @@ extern "C" int gsr_flat_unpack(float* const* ptrs_dev, const long long* offsets_
         ptrs_dev, offsets_dev, const_cast<float*>(flat), scale);
     return launched("flat_unpack");
 }
+
+// ---------------------------------------------------------------- measurement aid
+// FP32 FFMA peak probe for the roofline denominator of the SIMT contraction kernels (the
+// driver-written MEASURED_PEAKS.json only has HBM and bf16 tensor numbers): every thread runs
+// 8 independent FMA chains; flops = 2 * 8 * iters * threads.
+namespace gsr {
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float* __restrict__ out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 8
+    for (int i = 0; i < iters; ++i) {
+        x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+        x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+    const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678f) out[0] = s;        // never true in practice; keeps the chains alive
+}
+}  // namespace gsr
+
+extern "C" double gsr_ffma_probe(int iters, float* scratch, void* stream) {
+    if (!scratch || iters <= 0) return 0.0;
+    const int blocks = kNumSMs * 8, threads = 256;
+    ffma_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(scratch, iters, 0.999f, 0.001f);
+    if (launched("ffma_probe")) return 0.0;
+    return 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+}

@@ -16,6 +16,32 @@ from ._lib import check, lib
 EPI_NONE, EPI_BIAS, EPI_ADD = 0, 1, 2
 
 
+class KernelTimer:
+    """CUDA-event pairs around individual launches on the launching stream (bench.py sets
+    ``GEMM_TIMER`` to one of these to measure the contraction kernel inside the timed region)."""
+
+    def __init__(self):
+        self.records = []
+
+    def start(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def stop(self, e0, work: float) -> None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.records.append((e0, e1, work))
+
+    def totals(self):
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b, _ in self.records)
+        return ms, sum(w for _, _, w in self.records), len(self.records)
+
+
+GEMM_TIMER = None
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -118,10 +144,14 @@ def bgemm(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB: bool =
     Mk, bk, sAk, sCk, sEk = M, batch, sA, M * N, s_extra
     if A.dim() == 3 and B.dim() == 2 and not transA:          # stack the subjects along M
         Mk, bk, sAk, sCk, sEk = batch * M, 1, 0, 0, 0
+    timer = GEMM_TIMER
+    e0 = timer.start() if timer is not None else None
     check(lib().gsr_bgemm_f32(A.data_ptr(), B.data_ptr(), out.data_ptr(), Mk, N, K, ac, bc, N,
                               sAk, sB, sCk, int(transA), int(transB), bk, float(alpha),
                               epi, extra.data_ptr() if extra is not None else None, ld_extra, sEk, _stream()),
           "gsr_bgemm_f32")
+    if timer is not None:
+        timer.stop(e0, 2.0 * M * N * K * batch)
     return out
 
 
@@ -148,10 +178,14 @@ def bgemm_reduce(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB:
         if tuple(add.shape) != (M, N):
             raise ValueError("bgemm_reduce: add shape != (M, N)")
         epi, extra = EPI_ADD, add
+    timer = GEMM_TIMER
+    e0 = timer.start() if timer is not None else None
     check(lib().gsr_bgemm_reduce_f32(A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, ac, bc, N,
                                      ar * ac, br * bc, int(transA), int(transB), batch, float(alpha),
                                      epi, extra.data_ptr() if extra is not None else None, N,
                                      ws.data_ptr(), splits.value, _stream()), "gsr_bgemm_reduce_f32")
+    if timer is not None:
+        timer.stop(e0, 2.0 * M * N * K * batch)
     return out
 
 

@@ -208,6 +208,12 @@ GSR_API int gsr_flat_pack(const float* const* ptrs_dev, const long long* offsets
 GSR_API int gsr_flat_unpack(float* const* ptrs_dev, const long long* offsets_dev, int n_tensors,
                     const float* flat, long long total, float scale, void* stream);
 
+/* ------------------------------------------------------------------ measurement aid
+ * Launches an FFMA-only kernel (8 independent chains per thread, 148*8 CTAs of 256 threads)
+ * and returns the flops it executes; timed by the caller with CUDA events to obtain the
+ * FP32 SIMT peak that bounds the contraction kernels (bench.py roofline).           */
+GSR_API double gsr_ffma_probe(int iters, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

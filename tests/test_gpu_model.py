@@ -58,22 +58,36 @@ def test_graph_unet_forward_and_pool_indices(setup, golden):
     net_outs, start = model.net(A, torch.eye(160, device="cuda"))
     assert np.allclose(start.detach().cpu().numpy(), G["start_gcn_outs"], rtol=0, atol=2e-6)
     assert np.allclose(net_outs.detach().cpu().numpy(), G["net_outs"], rtol=0, atol=1e-5)
-    ref_trace = {}
-    O.graph_unet(sd, A.cpu(), torch.eye(160), trace=ref_trace)
+    # Pool levels: compare per ORIGINAL node.  The order inside the selected set never changes
+    # the U-Net output (every op is row-wise and the unpool scatters back by index), but it
+    # permutes the rows of the next level, so scores / indices are mapped back to node ids.
+    ids_ref, ids_got = torch.arange(160), torch.arange(160)
     for i in range(4):
         s_ref = torch.from_numpy(G[f"pool{i}_scores"])
-        assert torch.allclose(model.net.pool_scores[i].cpu(), s_ref, rtol=0, atol=3e-7)
-        idx, idx_ref = model.net.pool_indices[i].cpu(), torch.from_numpy(G[f"pool{i}_idx"])
-        assert idx.dtype == torch.int64
-        # the selected SET is exact whenever the reference's boundary gap exceeds the score noise
+        s_got = model.net.pool_scores[i].cpu()
+        idx_ref = torch.from_numpy(G[f"pool{i}_idx"])
+        idx_got = model.net.pool_indices[i].cpu()
+        assert idx_got.dtype == torch.int64 and idx_got.numel() == idx_ref.numel()
+        by_node_ref = dict(zip(ids_ref.tolist(), s_ref.tolist()))
+        by_node_got = dict(zip(ids_got.tolist(), s_got.tolist()))
+        common = set(by_node_ref) & set(by_node_got)
+        assert len(common) >= len(by_node_ref) - 2, f"level {i}: different node sets enter the pool"
+        assert max(abs(by_node_ref[k] - by_node_got[k]) for k in common) < 3e-7, f"level {i}"
         k = idx_ref.numel()
         srt = torch.sort(s_ref, descending=True).values
-        gap = float(srt[k - 1] - srt[k]) if k < s_ref.numel() else 1.0
-        if gap > 1e-6:
-            assert set(idx.tolist()) == set(idx_ref.tolist()), f"level {i}"
-        # and the order is exact wherever neighbouring scores are further apart than the noise
-        if float(torch.diff(srt[:k + 1]).abs().min()) > 1e-6:
-            assert torch.equal(idx, idx_ref), f"level {i}"
+        boundary = float(srt[k - 1])
+        sel_ref, sel_got = ids_ref[idx_ref], ids_got[idx_got]
+        # The selected SET is exact up to nodes whose reference score sits within the score noise
+        # (3e-7) of the k-th score: sigmoid(x/100) squeezes 160 scores into ~3500 fp32 bins, so
+        # near-ties at the boundary are normal (this fixture has one 1 ulp apart) and no
+        # implementation of the preceding mat-mul can promise their order.
+        for node in set(sel_ref.tolist()) ^ set(sel_got.tolist()):
+            if node in by_node_ref:
+                assert abs(by_node_ref[node] - boundary) < 1e-6, f"level {i}: node {node} is not a near-tie"
+        # and the ORDER (bit-exact idx) wherever neighbouring reference scores are separated
+        if torch.equal(ids_ref, ids_got) and float(torch.diff(srt[:k + 1]).abs().min()) > 1e-6:
+            assert torch.equal(idx_got, idx_ref), f"level {i}"
+        ids_ref, ids_got = sel_ref, sel_got
 
 
 def test_graph_unet_backward(setup):
