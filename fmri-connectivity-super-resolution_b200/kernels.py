@@ -98,7 +98,10 @@ def eigh_jacobi(A: torch.Tensor, canonical_sign: bool = True, tol: float = 0.0, 
     w = torch.empty(A.shape[:-1], device=A.device, dtype=torch.float32)
     U = torch.empty_like(A)
     info = torch.empty((batch,), device=A.device, dtype=torch.int32)
-    check(lib().gsr_eigh_jacobi_f32(A.data_ptr(), w.data_ptr(), U.data_ptr(), info.data_ptr(), batch, n,
+    ws_floats = lib().gsr_eigh_workspace(batch, n)
+    ws = torch.empty((ws_floats,), device=A.device, dtype=torch.float32) if ws_floats else None
+    check(lib().gsr_eigh_jacobi_f32(A.data_ptr(), w.data_ptr(), U.data_ptr(), info.data_ptr(),
+                                    ws.data_ptr() if ws is not None else None, batch, n,
                                     int(canonical_sign), float(tol), int(max_sweeps), _stream()),
           "gsr_eigh_jacobi_f32")
     return w, U, info

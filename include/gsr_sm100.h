@@ -65,9 +65,12 @@ GSR_API int gsr_normalize_adj_bwd(const float* mx, const float* r, const float* 
 
 /* ------------------------------------------------------------------ a2 / a12
  * models/layers.py:27 and utils/gsr_train.py:34  torch.linalg.eigh(A, UPLO='U')
- * Batched one-sided (Hestenes) Jacobi on A + sigma*I held in shared memory, one
- * CTA per graph (n <= GSR_EIGH_MAX_N_CTA) or one 2-CTA cluster per graph over
- * distributed shared memory (n <= GSR_EIGH_MAX_N).  Only the upper triangle of
+ * Batched one-sided (Hestenes) Jacobi on A + sigma*I, one CTA per graph, the working matrix
+ * resident in shared memory (n <= GSR_EIGH_MAX_N_CTA); for n <= ~170 a second, polishing
+ * phase (implicit two-sided Jacobi on a freshly computed A.U) brings the eigenvectors to
+ * LAPACK's accuracy class.  Larger n (the 268-node HR target, up to GSR_EIGH_MAX_N) keep the
+ * working matrix in the caller's `workspace` (gsr_eigh_workspace(batch, n) floats, 0 when none
+ * is needed; L2 resident) -- the once-per-dataset, hoisted path.  Only the upper triangle of
  * A is read.  Eigenvalues ascending in w[batch,n]; eigenvector k in COLUMN k of
  * U[batch,n,n].  canonical_sign != 0 applies the documented sign rule: the
  * component of largest magnitude (lowest row on ties) of every eigenvector is
@@ -77,7 +80,8 @@ GSR_API int gsr_normalize_adj_bwd(const float* mx, const float* r, const float* 
  * the defaults (1e-6, 30).                                                       */
 #define GSR_EIGH_MAX_N_CTA 224
 #define GSR_EIGH_MAX_N     288
-GSR_API int gsr_eigh_jacobi_f32(const float* A, float* w, float* U, int32_t* info,
+GSR_API size_t gsr_eigh_workspace(int batch, int n);
+GSR_API int gsr_eigh_jacobi_f32(const float* A, float* w, float* U, int32_t* info, float* workspace,
                         int batch, int n, int canonical_sign, float tol, int max_sweeps,
                         void* stream);
 

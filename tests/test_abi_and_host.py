@@ -46,6 +46,7 @@ def test_library_loads_and_exports_every_declared_symbol(pkg):
     assert lib.gsr_vectorize_len(268, 1) == 35778 + 267
     assert lib.gsr_l1_partials(268 * 268) >= 1
     assert lib.gsr_eval_workspace() > 0
+    assert lib.gsr_eigh_workspace(4, 160) == 0 and lib.gsr_eigh_workspace(4, 268) == 4 * 268 * 292
     assert lib.gsr_launch_count() == 0           # nothing may launch on a CPU-only box
 
 
@@ -59,7 +60,7 @@ def test_bad_arguments_are_rejected_without_a_gpu(pkg):
     lib = pkg.lib()
     assert lib.gsr_normalize_adj_fwd(None, None, None, None, 1, 4, 0, None) == -1
     assert b"normalize_adj_fwd" in lib.gsr_last_error()
-    assert lib.gsr_eigh_jacobi_f32(None, None, None, None, 1, 4, 1, 0.0, 0, None) == -1
+    assert lib.gsr_eigh_jacobi_f32(None, None, None, None, None, 1, 4, 1, 0.0, 0, None) == -1
     assert lib.gsr_set_tuning(b"no_such_knob", 1) == -1
 
 

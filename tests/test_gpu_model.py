@@ -302,6 +302,68 @@ def test_gsrnet_small_lr_dim_fixture(cuda_pkg, golden):
         assert np.allclose(adj.cpu().numpy()[::rs], G[f"s{s}_adj"], rtol=0, atol=5e-6)
 
 
+def test_train_and_test_loops_match_oracle(cuda_pkg, capsys):
+    """utils/gsr_train.py train() / test() driven exactly as the notebook does (numpy float64 in,
+    per-subject Adam steps, print-only) against the same loop over the oracle."""
+    sd = O.make_state_dict(0)
+    model = make_model(cuda_pkg, sd)
+    n_subj = 3
+    lrs = np.stack([O.synth_connectome(160, 3000 + s).numpy().astype(np.float64) for s in range(n_subj)])
+    hrs = np.stack([O.synth_connectome(268, 3500 + s).numpy().astype(np.float64) for s in range(n_subj)])
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    assert cuda_pkg.train(model, opt, lrs, hrs, Args(epochs=1)) is None
+    printed = capsys.readouterr().out
+    assert printed.startswith("Epoch: 1, Loss: ")
+    loss_got = float(printed.split("Loss: ")[1].split(",")[0])
+    err_got = float(printed.split("Error (MAE): ")[1])
+    # oracle loop: same init, same optimiser, its own LAPACK bases
+    params = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in sd.items())
+    opt_ref = torch.optim.Adam(list(params.values()), lr=1e-4)
+    losses, errs = [], []
+    for s in range(n_subj):
+        opt_ref.zero_grad()
+        loss, err, _ = O.train_loss(params, torch.from_numpy(lrs[s]).float(), torch.from_numpy(hrs[s]).float())
+        loss.backward()
+        opt_ref.step()
+        losses.append(float(loss)); errs.append(float(err))
+    assert loss_got == pytest.approx(np.mean(losses), abs=1e-4)
+    assert err_got == pytest.approx(np.mean(errs), abs=1e-5)
+    # parameters moved the same way (Adam's first steps are +-lr per element: compare in bulk)
+    moved = 0.0
+    for k, p in model.named_parameters():
+        moved = max(moved, float((p.detach().cpu() - sd[k]).abs().max()))
+        agree = float(((p.detach().cpu() - sd[k]).sign() == (params[k].detach() - sd[k]).sign()).float().mean())
+        assert agree > 0.97, (k, agree)
+    assert 1e-4 < moved < 1e-3
+    # test(): per-subject MAE against unit-diagonal targets, all-zero samples skipped, caller's
+    # array mutated in place (utils/gsr_train.py:70)
+    frozen = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    lr_t = np.concatenate([lrs, np.zeros((1, 160, 160))]); hr_t = np.concatenate([hrs, np.zeros((1, 268, 268))])
+    assert cuda_pkg.test(model, lr_t, hr_t, Args()) is None
+    out = capsys.readouterr().out.strip().splitlines()
+    maes = [float(l.split("MAE: ")[1]) for l in out if l.startswith("MAE: ")]
+    assert len(maes) == n_subj and out[-1].startswith("Test error MAE: ")
+    assert np.all(np.diagonal(hr_t[:n_subj], axis1=1, axis2=2) == 1.0) and np.all(hr_t[n_subj] == 0)
+    ref = O.test_errors(frozen, [torch.from_numpy(a).float() for a in lrs], [torch.from_numpy(a).float() for a in hrs])
+    assert np.allclose(maes, ref, rtol=0, atol=1e-5)
+
+
+def test_train_batched_runs_and_caches(cuda_pkg, capsys):
+    sd = O.make_state_dict(0)
+    model = make_model(cuda_pkg, sd)
+    lrs = np.stack([O.synth_connectome(160, 4000 + s).numpy() for s in range(6)])
+    hrs = np.stack([O.synth_connectome(268, 4500 + s).numpy() for s in range(6)])
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    hist = cuda_pkg.train_batched(model, opt, lrs, hrs, Args(epochs=3), batch_size=4, verbose=False)
+    assert len(hist) == 3 and all(np.isfinite(hist)) and hist[2] < hist[0]
+    # first-epoch loss == mean of the oracle's per-subject losses at the initial weights (first batch)
+    losses = [float(O.train_loss(sd, torch.from_numpy(lrs[s]), torch.from_numpy(hrs[s]))[0]) for s in range(4)]
+    model2 = make_model(cuda_pkg, sd)
+    step = cuda_pkg.GSRTrainStep(model2)
+    loss, _ = step(torch.from_numpy(lrs[:4]).cuda(), torch.from_numpy(hrs[:4]).cuda())     # own LR and HR eigh
+    assert float(loss) == pytest.approx(np.mean(losses), abs=1e-4)
+
+
 def test_model_requires_gpu_and_library(cuda_pkg):
     model = cuda_pkg.GSRNet(list(O.DEFAULT_KS), Args())
     with pytest.raises(RuntimeError):
