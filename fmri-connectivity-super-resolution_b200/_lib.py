@@ -36,6 +36,12 @@ PROTOTYPES = {
     "gsr_bgemm_reduce_workspace": (C.c_size_t, [i32, i32, i32, C.POINTER(i32)]),
     "gsr_bgemm_reduce_f32": (i32, [c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, i32, i32, i64, i64,
                                    i32, i32, i32, f32, i32, c_ptr, i32, c_ptr, i32, c_ptr]),
+    "gsr_tcgemm_supported": (i32, [i32, i32, i32, i32, i32]),
+    "gsr_tcgemm_f32": (i32, [c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, i32, i32, i64, i64, i64,
+                             i32, i32, i32, f32, i32, c_ptr, i32, i64, c_ptr]),
+    "gsr_tcgemm_reduce_workspace": (C.c_size_t, [i32, i32, i32, C.POINTER(i32)]),
+    "gsr_tcgemm_reduce_f32": (i32, [c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, i32, i32, i64, i64,
+                                    i32, i32, i32, f32, i32, c_ptr, i32, c_ptr, i32, c_ptr]),
     "gsr_colsum_f32": (i32, [c_ptr, c_ptr, i32, i32, i32, c_ptr]),
     "gsr_sym_diag_abs_fwd": (i32, [c_ptr, c_ptr, i32, i32, c_ptr]),
     "gsr_sym_diag_abs_bwd": (i32, [c_ptr, c_ptr, c_ptr, i32, i32, c_ptr]),

@@ -41,6 +41,22 @@ class KernelTimer:
 
 GEMM_TIMER = None
 
+# "simt": the SIMT FP32 kernel (gsr_bgemm_f32); "tc": tcgen05 3xTF32 (gsr_tcgemm_f32) wherever the
+# operands meet its alignment contract, SIMT otherwise.  Same results to fp32 tolerance.
+GEMM_BACKEND = "simt"
+
+
+def set_gemm_backend(name: str) -> None:
+    global GEMM_BACKEND
+    if name not in ("simt", "tc"):
+        raise ValueError("gemm backend must be 'simt' or 'tc'")
+    GEMM_BACKEND = name
+
+
+def _tc_ok(A: torch.Tensor, B: torch.Tensor, lda: int, ldb: int, sA: int, sB: int) -> bool:
+    return (GEMM_BACKEND == "tc" and lda % 4 == 0 and ldb % 4 == 0 and sA % 4 == 0 and sB % 4 == 0
+            and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0)
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -149,10 +165,11 @@ def bgemm(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB: bool =
         Mk, bk, sAk, sCk, sEk = batch * M, 1, 0, 0, 0
     timer = GEMM_TIMER
     e0 = timer.start() if timer is not None else None
-    check(lib().gsr_bgemm_f32(A.data_ptr(), B.data_ptr(), out.data_ptr(), Mk, N, K, ac, bc, N,
-                              sAk, sB, sCk, int(transA), int(transB), bk, float(alpha),
-                              epi, extra.data_ptr() if extra is not None else None, ld_extra, sEk, _stream()),
-          "gsr_bgemm_f32")
+    fn = lib().gsr_tcgemm_f32 if _tc_ok(A, B, ac, bc, sAk, sB) else lib().gsr_bgemm_f32
+    check(fn(A.data_ptr(), B.data_ptr(), out.data_ptr(), Mk, N, K, ac, bc, N,
+             sAk, sB, sCk, int(transA), int(transB), bk, float(alpha),
+             epi, extra.data_ptr() if extra is not None else None, ld_extra, sEk, _stream()),
+          "gsr_bgemm_f32 / gsr_tcgemm_f32")
     if timer is not None:
         timer.stop(e0, 2.0 * M * N * K * batch)
     return out
@@ -173,7 +190,9 @@ def bgemm_reduce(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB:
         raise RuntimeError(f"bgemm_reduce: inner dimensions differ ({K} vs {K2})")
     out = torch.empty((M, N), device=A.device, dtype=torch.float32)
     splits = C.c_int(0)
-    ws_floats = lib().gsr_bgemm_reduce_workspace(M, N, batch, C.byref(splits))
+    use_tc = _tc_ok(A, B, ac, bc, ar * ac, br * bc)
+    ws_fn = lib().gsr_tcgemm_reduce_workspace if use_tc else lib().gsr_bgemm_reduce_workspace
+    ws_floats = ws_fn(M, N, batch, C.byref(splits))
     ws = torch.empty((ws_floats,), device=A.device, dtype=torch.float32)
     epi, extra = EPI_NONE, None
     if add is not None:
@@ -183,10 +202,11 @@ def bgemm_reduce(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB:
         epi, extra = EPI_ADD, add
     timer = GEMM_TIMER
     e0 = timer.start() if timer is not None else None
-    check(lib().gsr_bgemm_reduce_f32(A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, ac, bc, N,
-                                     ar * ac, br * bc, int(transA), int(transB), batch, float(alpha),
-                                     epi, extra.data_ptr() if extra is not None else None, N,
-                                     ws.data_ptr(), splits.value, _stream()), "gsr_bgemm_reduce_f32")
+    fn = lib().gsr_tcgemm_reduce_f32 if use_tc else lib().gsr_bgemm_reduce_f32
+    check(fn(A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, ac, bc, N,
+             ar * ac, br * bc, int(transA), int(transB), batch, float(alpha),
+             epi, extra.data_ptr() if extra is not None else None, N,
+             ws.data_ptr(), splits.value, _stream()), "gsr_bgemm_reduce_f32 / gsr_tcgemm_reduce_f32")
     if timer is not None:
         timer.stop(e0, 2.0 * M * N * K * batch)
     return out

@@ -121,6 +121,26 @@ GSR_API int gsr_bgemm_reduce_f32(const float* A, const float* B, float* C,
                          int transA, int transB, int batch, float alpha,
                          int epilogue, const float* extra, int ld_extra,
                          float* workspace, int splits, void* stream);
+/* The same two entry points on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
+ * accumulators in tensor memory) at fp32 accuracy: every operand is split hi + lo into two
+ * TF32 values by the producer warps and three MMA passes (lo.hi + hi.lo + hi.hi) feed one fp32
+ * accumulator.  Same arguments and semantics as gsr_bgemm_f32 / gsr_bgemm_reduce_f32; operands
+ * must be 16-byte aligned with leading dimensions % 4 == 0 (GSR_E_ALIGN otherwise -- callers
+ * fall back to the SIMT entry, e.g. for the ragged Graph U-Net shapes).              */
+GSR_API int gsr_tcgemm_supported(int M, int N, int K, int lda, int ldb);
+GSR_API int gsr_tcgemm_f32(const float* A, const float* B, float* C,
+                   int M, int N, int K, int lda, int ldb, int ldc,
+                   long long strideA, long long strideB, long long strideC,
+                   int transA, int transB, int batch, float alpha,
+                   int epilogue, const float* extra, int ld_extra, long long stride_extra,
+                   void* stream);
+GSR_API size_t gsr_tcgemm_reduce_workspace(int M, int N, int batch, int* splits_out);
+GSR_API int gsr_tcgemm_reduce_f32(const float* A, const float* B, float* C,
+                          int M, int N, int K, int lda, int ldb, int ldc,
+                          long long strideA, long long strideB,
+                          int transA, int transB, int batch, float alpha,
+                          int epilogue, const float* extra, int ld_extra,
+                          float* workspace, int splits, void* stream);
 /* Column sums of a [rows, cols] matrix (Linear bias gradient, models/ops.py:60). */
 GSR_API int gsr_colsum_f32(const float* X, float* out, int rows, int cols, int ld, void* stream);
 
