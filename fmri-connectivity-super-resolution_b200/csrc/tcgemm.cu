@@ -8,7 +8,7 @@
 // term is 2^-22 relative).  Per CTA:
 //   * tile 128 (M) x up to 288 (N = 160 + up to 128, two UMMA N ranges) x 32 (K per stage), so
 //     one 268-column subject row block needs a single N tile;
-//   * 8 producer warps read the fp32 operands from global memory (float4, any layout: the
+//   * 15 producer warps read the fp32 operands from global memory (float4, any layout: the
 //     transposes of the backward pass are absorbed by the UMMA K-major / MN-major descriptor
 //     bit), split them and store hi / lo tiles in UMMA canonical layouts: K-major tiles use
 //     the no-swizzle layout (8 x 16 B core matrices), MN-major tiles the 128B_BASE32B layout
@@ -17,8 +17,9 @@
 //     per instruction, conflict free;
 //   * 1 MMA warp: an elected lane issues 4 k-steps x 3 passes x 1-2 N ranges per stage, then
 //     `tcgen05.commit` releases the stage (mbarrier) back to the producers; 2 stages;
-//   * epilogue: the 8 producer warps read the accumulator with `tcgen05.ld.32x32b.x8`
-//     (warp w: TMEM lanes 32*(w%4).., column half w/4), apply alpha / bias / addend and store.
+//   * epilogue: 12 warps read the accumulator with `tcgen05.ld.32x32b.x32` (warp w: TMEM lanes
+//     32*(w%4).., column group w/4) into a row-major staging tile in the idle operand buffers;
+//     all warps then apply alpha / bias / addend and write full coalesced rows.
 // Weight gradients (sum over subjects) keep accumulating in TMEM across the subjects dealt to
 // the CTA; partial tiles are then reduced in a fixed order (same scheme as the SIMT kernel).
 #include "common.cuh"
@@ -31,7 +32,8 @@ constexpr int BN = 288;                 // 160 + up to 128 (multiple of the 32-e
 constexpr int BN0 = 160;
 constexpr int BK = 32;
 constexpr int STAGES = 2;
-constexpr int PRODUCER_WARPS = 8;
+constexpr int PRODUCER_WARPS = 15;    // + 1 MMA warp = 512 threads -> 128 registers each
+constexpr int EPILOGUE_WARPS = 12;    // 3 column groups x 4 TMEM lane quarters
 constexpr int THREADS = 32 * (PRODUCER_WARPS + 1);
 constexpr int A_TILE = BM * BK * 4;     // bytes of one tf32 A tile (hi or lo)
 constexpr int B_TILE = BN * BK * 4;
@@ -41,7 +43,7 @@ constexpr int TMEM_COLS = 512;
 constexpr int A_PATCHES = BM * BK / 128;                        // 32 patches of 128 floats (one per warp instruction)
 constexpr int B_PATCHES = BN * BK / 128;                        // 72
 constexpr int PATCHES = A_PATCHES + B_PATCHES;                  // 104
-constexpr int PATCH_ITERS = (PATCHES + PRODUCER_WARPS - 1) / PRODUCER_WARPS;   // 13
+constexpr int PATCH_ITERS = (PATCHES + PRODUCER_WARPS - 1) / PRODUCER_WARPS;   // 7
 
 struct Params {
     const float* A; const float* B; float* C;
@@ -91,11 +93,27 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] . B[smem], kind::tf32, issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+// D[tmem] (+)= A[smem] . B[smem], kind::tf32, issued by ONE thread.  The 64-bit matrix
+// descriptors are passed as (low word, high word): only the low word (start address) changes
+// from one MMA to the next, so the issuing thread spends one integer add per operand.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                 "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "setp.ne.b32 p, %6, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+                 :: "r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
@@ -107,16 +125,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Shared-memory matrix descriptor (sm_100 version bit set).  layout_type: 0 = SWIZZLE_NONE
-// ("interleave"), 1 = SWIZZLE_128B_BASE32B.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)(layout_type & 7u) << 61;
-    return d;
+// Shared-memory matrix descriptor (sm_100 version bit set), as two 32-bit words.
+//   low  word: start address >> 4 in bits [0,14), leading byte offset >> 4 in bits [16,30)
+//   high word: stride byte offset >> 4 in bits [0,14), version = 1 at bit 14, layout type in
+//              bits [29,32): 0 = SWIZZLE_NONE ("interleave"), 1 = SWIZZLE_128B_BASE32B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo_bytes) {
+    return ((addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
 }
 // Instruction descriptor: fp32 accumulate, tf32 x tf32, M = 128, runtime N, operand majors.
 __device__ __forceinline__ uint32_t instr_desc(int n, int a_mn_major, int b_mn_major) {
@@ -124,10 +141,12 @@ __device__ __forceinline__ uint32_t instr_desc(int n, int a_mn_major, int b_mn_m
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// Round-to-nearest (ties away) to the 10-bit TF32 mantissa with two integer ops: add half an
+// ulp of the dropped 13 bits to the magnitude, clear them.  (`cvt.rna.tf32.f32` compiles to the
+// same pair plus an FSETP / SEL for Inf / NaN, which the split does not need: Inf stays Inf --
+// 0x1000 is masked away again -- and NaN stays NaN.)
 __device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 // ---------------------------------------------------------------- operand staging
@@ -181,7 +200,6 @@ __device__ __forceinline__ float4 load_patch(const float* __restrict__ base, int
     return v;
 }
 
-template <bool SWIZZLE32>
 __device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t soff, float4 v) {
     float4 h, l;
     h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
@@ -223,51 +241,77 @@ tcgemm_kernel(const Params p) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < PRODUCER_WARPS) {
-        // ===== producers: global fp32 -> (hi, lo) tf32 tiles in shared memory
-        for (int it = 0; it < total_kb; ++it) {
-            const int s = it % STAGES, use = it / STAGES;
+        // ===== producers: global fp32 -> (hi, lo) tf32 tiles in shared memory.
+        // Per-thread patch state (global offset, validity, shared offset) is computed once; the
+        // k loop only advances pointers.  The k loop is unrolled by two over two register sets so
+        // that the loads of k-block it+1 are in flight while k-block it is split and stored.
+        long long goff[PATCH_ITERS];        // element offset of this thread's float4 at k-block 0
+        uint32_t so[PATCH_ITERS];           // byte offset inside the (hi or lo) tile
+        uint32_t ok_mask = 0;               // bit i: the float4 of patch i lies inside the operand (rows)
+#pragma unroll
+        for (int i = 0; i < PATCH_ITERS; ++i) {
+            const int patch = warp + i * PRODUCER_WARPS;
+            int row = 0, k = 0;
+            goff[i] = 0; so[i] = 0;
+            if (patch < A_PATCHES) {
+                patch_coords<BM, !TA>(patch, lane, row, k, so[i]);
+                row += m0;
+                goff[i] = TA ? (long long)k * p.lda + row : (long long)row * p.lda + k;
+                if (TA ? (row + 3 < p.M) : (row < p.M)) ok_mask |= 1u << i;
+            } else if (patch < PATCHES) {
+                patch_coords<BN, TB>(patch - A_PATCHES, lane, row, k, so[i]);
+                row += n0;
+                goff[i] = TB ? (long long)row * p.ldb + k : (long long)k * p.ldb + row;
+                if (TB ? (row < p.N) : (row + 3 < p.N)) ok_mask |= 1u << i;
+            }
+        }
+        const long long a_kadv = TA ? (long long)BK * p.lda : BK, b_kadv = TB ? BK : (long long)BK * p.ldb;
+
+        auto issue_loads = [&](int it, float4 (&dst)[PATCH_ITERS]) {
             const int b = b_first + (it / nkb) * b_step, kb = it % nkb;
             const float* A = p.A + (size_t)b * p.sA;
             const float* B = p.B + (size_t)b * p.sB;
-            float4 v[PATCH_ITERS];
-            uint32_t so[PATCH_ITERS];
+            if ((kb + 1) * BK <= p.K) {                                    // whole k-block inside K: no k predicates
 #pragma unroll
-            for (int i = 0; i < PATCH_ITERS; ++i) {
-                const int patch = warp + i * PRODUCER_WARPS;
-                if (patch < A_PATCHES) v[i] = load_patch<BM, !TA>(A, p.lda, p.M, p.K, m0, kb * BK, patch, lane, so[i]);
-                else if (patch < PATCHES) v[i] = load_patch<BN, TB>(B, p.ldb, p.N, p.K, n0, kb * BK, patch - A_PATCHES, lane, so[i]);
+                for (int i = 0; i < PATCH_ITERS; ++i) {
+                    const int patch = warp + i * PRODUCER_WARPS;
+                    dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (patch < PATCHES && ((ok_mask >> i) & 1u)) {
+                        const float* src = patch < A_PATCHES ? A + goff[i] + kb * a_kadv : B + goff[i] + kb * b_kadv;
+                        dst[i] = __ldg(reinterpret_cast<const float4*>(src));
+                    }
+                }
+            } else {                                                       // ragged tail (k and row edges): generic path
+                uint32_t dummy;
+#pragma unroll
+                for (int i = 0; i < PATCH_ITERS; ++i) {
+                    const int patch = warp + i * PRODUCER_WARPS;
+                    if (patch < A_PATCHES) dst[i] = load_patch<BM, !TA>(A, p.lda, p.M, p.K, m0, kb * BK, patch, lane, dummy);
+                    else if (patch < PATCHES) dst[i] = load_patch<BN, TB>(B, p.ldb, p.N, p.K, n0, kb * BK, patch - A_PATCHES, lane, dummy);
+                }
             }
+        };
+        auto split_store = [&](int it, const float4 (&src)[PATCH_ITERS]) {
+            const int s = it % STAGES, use = it / STAGES;
             if (use > 0) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);      // MMA has drained this stage
             uint8_t* st = smem + s * STAGE_BYTES;
 #pragma unroll
             for (int i = 0; i < PATCH_ITERS; ++i) {
                 const int patch = warp + i * PRODUCER_WARPS;
-                if (p.mn_swap) {
-                    // bring-up probe: A (K-major) selects k = m % 8, every word of the B tile holds
-                    // (part of) its own word index, so C[m][n] names the word read as B(n, m % 8)
-                    if (patch < A_PATCHES) {
-                        int row, k; uint32_t so2;
-                        patch_coords<BM, true>(patch, lane, row, k, so2);
-                        float4 a;
-                        a.x = (k + 0 == (row & 7)) ? 1.f : 0.f; a.y = (k + 1 == (row & 7)) ? 1.f : 0.f;
-                        a.z = (k + 2 == (row & 7)) ? 1.f : 0.f; a.w = (k + 3 == (row & 7)) ? 1.f : 0.f;
-                        *reinterpret_cast<float4*>(st + so2) = a;
-                        *reinterpret_cast<float4*>(st + A_TILE + so2) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    } else if (patch < PATCHES) {
-                        const uint32_t w = so[i] >> 2;
-                        float4 b;
-                        if (p.mn_swap == 1) b = make_float4((float)((w + 0) & 1023u), (float)((w + 1) & 1023u), (float)((w + 2) & 1023u), (float)((w + 3) & 1023u));
-                        else b = make_float4((float)((w + 0) >> 10), (float)((w + 1) >> 10), (float)((w + 2) >> 10), (float)((w + 3) >> 10));
-                        *reinterpret_cast<float4*>(st + 2 * A_TILE + so[i]) = b;
-                        *reinterpret_cast<float4*>(st + 2 * A_TILE + B_TILE + so[i]) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    continue;
-                }
-                if (patch < A_PATCHES) store_split<TA>(st, st + A_TILE, so[i], v[i]);
-                else if (patch < PATCHES) store_split<!TB>(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, so[i], v[i]);
+                if (patch < A_PATCHES) store_split(st, st + A_TILE, so[i], src[i]);
+                else if (patch < PATCHES) store_split(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, so[i], src[i]);
             }
             fence_async_smem();                                            // generic-proxy writes -> async proxy (UMMA)
             mbar_arrive(bar_full + 8 * s);
+        };
+        float4 va[PATCH_ITERS], vb[PATCH_ITERS];
+        issue_loads(0, va);
+        for (int it = 0; it < total_kb; it += 2) {
+            if (it + 1 < total_kb) issue_loads(it + 1, vb);
+            split_store(it, va);
+            if (it + 1 >= total_kb) break;
+            if (it + 2 < total_kb) issue_loads(it + 2, va);
+            split_store(it + 1, vb);
         }
     } else {
         // ===== MMA issuer: one elected lane
@@ -281,29 +325,36 @@ tcgemm_kernel(const Params p) {
             const uint32_t b_lbo = TB ? 128 : 512, b_sbo = TB ? (BK / 4) * 128 : (BN / 32) * 512;
             const uint32_t a_kstep = TA ? 2 * (BM / 32) * 512 : 256, b_kstep = TB ? 256 : 2 * (BN / 32) * 512;
             const uint32_t b_n1 = TB ? (BN0 / 8) * ((BK / 4) * 128) : (BN0 / 32) * 512;
+            const uint32_t a_dhi = desc_hi(a_sbo, a_lt), b_dhi = desc_hi(b_sbo, b_lt);
+            const uint32_t a_step = a_kstep >> 4, b_step = b_kstep >> 4;     // descriptor address units (16 B)
+            uint32_t base_lo[STAGES][4];                                      // A hi, A lo, B hi, B lo of every stage
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) {
+                const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+                base_lo[s][0] = desc_lo(st, a_lbo);
+                base_lo[s][1] = desc_lo(st + A_TILE, a_lbo);
+                base_lo[s][2] = desc_lo(st + 2 * A_TILE, b_lbo);
+                base_lo[s][3] = desc_lo(st + 2 * A_TILE + B_TILE, b_lbo);
+            }
+            const uint32_t n1 = b_n1 >> 4;
+            uint32_t acc = 0;                                                 // 0 only for the very first k-step
             for (int it = 0; it < total_kb; ++it) {
                 const int s = it % STAGES, use = it / STAGES;
                 mbar_wait(bar_full + 8 * s, use & 1);
                 tc_fence_after();
-                const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                const uint32_t a_hi = st, a_lo = st + A_TILE, b_hi = st + 2 * A_TILE, b_lo = st + 2 * A_TILE + B_TILE;
+                uint32_t ah = base_lo[s][0], al = base_lo[s][1], bh = base_lo[s][2], bl = base_lo[s][3];
 #pragma unroll
                 for (int j = 0; j < BK / 8; ++j) {
-                    const uint64_t dah = smem_desc(a_hi + j * a_kstep, a_lbo, a_sbo, a_lt);
-                    const uint64_t dal = smem_desc(a_lo + j * a_kstep, a_lbo, a_sbo, a_lt);
-                    const uint64_t dbh = smem_desc(b_hi + j * b_kstep, b_lbo, b_sbo, b_lt);
-                    const uint64_t dbl = smem_desc(b_lo + j * b_kstep, b_lbo, b_sbo, b_lt);
-                    const uint32_t first = (it == 0 && j == 0) ? 0u : 1u;
-                    umma_tf32(tmem_base, dal, dbh, idesc0, first);          // small terms first
-                    umma_tf32(tmem_base, dah, dbl, idesc0, 1u);
-                    umma_tf32(tmem_base, dah, dbh, idesc0, 1u);
+                    umma_tf32(tmem_base, al, a_dhi, bh, b_dhi, idesc0, acc);          // small terms first
+                    umma_tf32(tmem_base, ah, a_dhi, bl, b_dhi, idesc0, 1u);
+                    umma_tf32(tmem_base, ah, a_dhi, bh, b_dhi, idesc0, 1u);
                     if (n_second > 0) {
-                        const uint64_t dbh1 = smem_desc(b_hi + b_n1 + j * b_kstep, b_lbo, b_sbo, b_lt);
-                        const uint64_t dbl1 = smem_desc(b_lo + b_n1 + j * b_kstep, b_lbo, b_sbo, b_lt);
-                        umma_tf32(tmem_base + BN0, dal, dbh1, idesc1, first);
-                        umma_tf32(tmem_base + BN0, dah, dbl1, idesc1, 1u);
-                        umma_tf32(tmem_base + BN0, dah, dbh1, idesc1, 1u);
+                        umma_tf32(tmem_base + BN0, al, a_dhi, bh + n1, b_dhi, idesc1, acc);
+                        umma_tf32(tmem_base + BN0, ah, a_dhi, bl + n1, b_dhi, idesc1, 1u);
+                        umma_tf32(tmem_base + BN0, ah, a_dhi, bh + n1, b_dhi, idesc1, 1u);
                     }
+                    acc = 1u;
+                    ah += a_step; al += a_step; bh += b_step; bl += b_step;
                 }
                 umma_commit(bar_empty + 8 * s);                              // stage free once these MMAs retire
             }
@@ -312,42 +363,46 @@ tcgemm_kernel(const Params p) {
         __syncwarp();
     }
 
-    // ===== epilogue: TMEM -> registers -> global (producer warps)
-    if (warp < PRODUCER_WARPS) {
+    // ===== epilogue: TMEM -> registers -> shared staging tile -> global.
+    // tcgen05.ld hands every thread one accumulator ROW (lane = row), so storing straight to
+    // global memory would scatter 16-byte pieces over 32 rows per instruction.  The tile is
+    // staged row-major in the (now idle) operand buffers with an odd pitch (conflict-free both
+    // ways) and written out by all warps as full, coalesced rows.
+    constexpr int CPITCH = BN + 1;                                          // 289 floats
+    float* Cs = reinterpret_cast<float*>(smem);
+    if (warp < EPILOGUE_WARPS) {
         mbar_wait(bar_accum, 0);
         tc_fence_after();
-        const int q = warp & 3, half = warp >> 2;
-        const int row = m0 + q * 32 + lane;
-        const int c_begin = half * (BN / 2), c_end = min(c_begin + BN / 2, ncols);
+        const int q = warp & 3, part = warp >> 2;                          // TMEM lane quarter, column group
+        constexpr int COLS_PER_PART = BN / (EPILOGUE_WARPS / 4);            // 96
+        const int r = q * 32 + lane;
+        const int c_begin = part * COLS_PER_PART, c_end = min(c_begin + COLS_PER_PART, ncols);
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);   // whole warp, convergent
+#pragma unroll
+            for (int i = 0; i < 32; ++i) Cs[r * CPITCH + c0 + i] = __uint_as_float(v[i]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    {
         float* C;
         int ldc;
         if (REDUCE) { C = p.C + (size_t)blockIdx.z * p.M * p.N; ldc = p.N; }
         else        { C = p.C + (size_t)blockIdx.z * p.sC;      ldc = p.ldc; }
         const float* extra = (!REDUCE && p.epilogue == GSR_EPI_ADD) ? p.extra + (size_t)blockIdx.z * p.s_extra : nullptr;
-        const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
-        for (int c = c_begin; c < c_end; c += 8) {
-            float v[8];
-            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);     // whole warp, convergent
-            if (row < p.M) {
-                const int n = n0 + c;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (!REDUCE) {
-                        v[i] *= p.alpha;
-                        if (n + i < p.N) {
-                            if (p.epilogue == GSR_EPI_BIAS) v[i] += __ldg(p.extra + n + i);
-                            else if (p.epilogue == GSR_EPI_ADD) v[i] += __ldg(extra + (size_t)row * p.ld_extra + n + i);
-                        }
-                    }
-                }
-                float* dst = C + (size_t)row * ldc + n;
-                if (vec && n + 7 < p.N) {
-                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) if (n + i < p.N) dst[i] = v[i];
-                }
+        const int rows = min(BM, p.M - m0), cols = min(BN, p.N - n0);
+        const int epi = REDUCE ? GSR_EPI_NONE : p.epilogue;
+        const float alpha = REDUCE ? 1.0f : p.alpha;
+        for (int r = warp; r < rows; r += PRODUCER_WARPS + 1) {
+            const float* src = Cs + r * CPITCH;
+            float* dst = C + (size_t)(m0 + r) * ldc + n0;
+            for (int c = lane; c < cols; c += 32) {
+                float v = src[c] * alpha;
+                if (epi == GSR_EPI_BIAS) v += __ldg(p.extra + n0 + c);
+                else if (epi == GSR_EPI_ADD) v += __ldg(extra + (size_t)(m0 + r) * p.ld_extra + n0 + c);
+                dst[c] = v;
             }
         }
     }

@@ -7,6 +7,7 @@ may carry a leading subject dimension.  No function here has a non-CUDA path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -41,9 +42,11 @@ class KernelTimer:
 
 GEMM_TIMER = None
 
-# "simt": the SIMT FP32 kernel (gsr_bgemm_f32); "tc": tcgen05 3xTF32 (gsr_tcgemm_f32) wherever the
-# operands meet its alignment contract, SIMT otherwise.  Same results to fp32 tolerance.
-GEMM_BACKEND = "simt"
+# "tc" (default): tcgen05 3xTF32 (gsr_tcgemm_f32) wherever the operands meet its alignment
+# contract and the product is large enough to fill a 128-row tile, the SIMT FP32 kernel
+# (gsr_bgemm_f32) otherwise; "simt": always the SIMT kernel.  Same results to fp32 tolerance.
+GEMM_BACKEND = os.environ.get("GSR_GEMM_BACKEND", "tc")
+TC_MIN_ROWS = 256          # smaller products (the Graph U-Net linears) cannot fill a 128-row tensor-core tile
 
 
 def set_gemm_backend(name: str) -> None:
@@ -53,8 +56,8 @@ def set_gemm_backend(name: str) -> None:
     GEMM_BACKEND = name
 
 
-def _tc_ok(A: torch.Tensor, B: torch.Tensor, lda: int, ldb: int, sA: int, sB: int) -> bool:
-    return (GEMM_BACKEND == "tc" and lda % 4 == 0 and ldb % 4 == 0 and sA % 4 == 0 and sB % 4 == 0
+def _tc_ok(A: torch.Tensor, B: torch.Tensor, lda: int, ldb: int, sA: int, sB: int, rows: int = 1 << 30) -> bool:
+    return (GEMM_BACKEND == "tc" and rows >= TC_MIN_ROWS and lda % 4 == 0 and ldb % 4 == 0 and sA % 4 == 0 and sB % 4 == 0
             and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0)
 
 
@@ -165,7 +168,7 @@ def bgemm(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB: bool =
         Mk, bk, sAk, sCk, sEk = batch * M, 1, 0, 0, 0
     timer = GEMM_TIMER
     e0 = timer.start() if timer is not None else None
-    fn = lib().gsr_tcgemm_f32 if _tc_ok(A, B, ac, bc, sAk, sB) else lib().gsr_bgemm_f32
+    fn = lib().gsr_tcgemm_f32 if _tc_ok(A, B, ac, bc, sAk, sB, Mk * bk) else lib().gsr_bgemm_f32
     check(fn(A.data_ptr(), B.data_ptr(), out.data_ptr(), Mk, N, K, ac, bc, N,
              sAk, sB, sCk, int(transA), int(transB), bk, float(alpha),
              epi, extra.data_ptr() if extra is not None else None, ld_extra, sEk, _stream()),

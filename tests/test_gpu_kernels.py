@@ -30,6 +30,18 @@ def K(cuda_pkg):
     return cuda_pkg.kernels
 
 
+@pytest.fixture(params=["simt", "tc"])
+def gemm_backend(request, cuda_pkg):
+    """Every contraction test runs on the SIMT FP32 kernel and on the tcgen05 3xTF32 kernel."""
+    Kmod = cuda_pkg.kernels
+    old, old_rows = Kmod.GEMM_BACKEND, Kmod.TC_MIN_ROWS
+    Kmod.set_gemm_backend(request.param)
+    Kmod.TC_MIN_ROWS = 0
+    yield request.param
+    Kmod.set_gemm_backend(old)
+    Kmod.TC_MIN_ROWS = old_rows
+
+
 # ------------------------------------------------------------------ vectoriser (bit exact)
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 33, 160, 268])
 @pytest.mark.parametrize("diag", [False, True])
@@ -276,7 +288,7 @@ def test_eigh_full_batch_properties(cuda_pkg):
 @pytest.mark.parametrize("tA", [False, True])
 @pytest.mark.parametrize("tB", [False, True])
 @pytest.mark.parametrize("shape", [(268, 268, 268), (268, 160, 160), (160, 268, 536), (101, 268, 268), (30, 7, 5), (1, 1, 1), (137, 139, 17)])
-def test_bgemm_vs_float64(K, tA, tB, shape):
+def test_bgemm_vs_float64(K, gemm_backend, tA, tB, shape):
     M, N, Kd = shape
     g = torch.Generator().manual_seed(M * 7 + N)
     for batch, sharedB in ((1, False), (3, False), (3, True)):
@@ -292,7 +304,7 @@ def test_bgemm_vs_float64(K, tA, tB, shape):
         assert float((got.double() - want).abs().max()) <= tol, (shape, tA, tB, batch, sharedB)
 
 
-def test_bgemm_epilogues_and_2d(K):
+def test_bgemm_epilogues_and_2d(K, gemm_backend):
     g = torch.Generator().manual_seed(5)
     X, W, b = torch.randn(144, 268, generator=g), torch.randn(268, 268, generator=g), torch.randn(268, generator=g)
     want = torch.nn.functional.linear(X.double(), W.double(), b.double())
@@ -312,6 +324,7 @@ def test_bgemm_epilogues_and_2d(K):
 
 
 def test_bgemm_variants_agree_bitwise(cuda_pkg, K):
+    K.set_gemm_backend("simt")
     g = torch.Generator().manual_seed(9)
     A, B = torch.randn(3, 268, 268, generator=g).cuda(), torch.randn(3, 268, 268, generator=g).cuda()
     outs = []
@@ -319,11 +332,12 @@ def test_bgemm_variants_agree_bitwise(cuda_pkg, K):
         cuda_pkg.set_tuning("gemm_variant", v)
         outs.append(K.bgemm(A, B, transB=True))
     cuda_pkg.set_tuning("gemm_variant", 0)
+    K.set_gemm_backend("tc")
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
 
 
 @pytest.mark.parametrize("tA,tB", [(False, False), (True, False), (False, True)])
-def test_bgemm_reduce(K, tA, tB):
+def test_bgemm_reduce(K, gemm_backend, tA, tB):
     g = torch.Generator().manual_seed(11)
     batch, M, N, Kd = 37, 160, 268, 268
     A = torch.randn((batch, Kd, M) if tA else (batch, M, Kd), generator=g)
@@ -339,7 +353,7 @@ def test_bgemm_reduce(K, tA, tB):
     assert torch.equal(got, again)                       # deterministic reduction order
 
 
-def test_bgemm_linearity_full_batch(K):
+def test_bgemm_linearity_full_batch(K, gemm_backend):
     """BASELINE size (1024 subjects): C(A1 + A2) = C(A1) + C(A2) up to fp32 rounding, and the
     stacked shared-weight path equals the per-subject path bit for bit."""
     g = torch.Generator(device="cuda").manual_seed(2)

