@@ -95,14 +95,41 @@ __device__ __forceinline__ void rr_pair(int slot, int r, int m, int n_pad, int& 
     else { p = r + slot; if (p >= m) p -= m; q = r - slot; if (q < 0) q += m; }
 }
 
+// One rotation of the register-resident columns x, y (cached squared norms nx, ny).
+template <int R>
+__device__ __forceinline__ bool rotate_regs(float (&x)[R], float (&y)[R], float& nx, float& ny, float tol2, unsigned gmask) {
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < R; e += 2) {
+        d0 = fmaf(x[e], y[e], d0);
+        d1 = fmaf(x[e + 1], y[e + 1], d1);
+    }
+    const float xy = group_sum8(d0 + d1, gmask);
+    if (!(xy * xy > tol2 * nx * ny)) return false;
+    float c, s, t;
+    jacobi_cs(nx, ny, xy, c, s, t);
+#pragma unroll
+    for (int e = 0; e < R; ++e) {
+        const float a = x[e], b = y[e];
+        x[e] = c * a - s * b;
+        y[e] = s * a + c * b;
+    }
+    nx -= t * xy;
+    ny += t * xy;
+    return true;
+}
+
 // KR     : rows per lane / 4 (column pitch LD = 32 KR + 4 floats)
 // POLISH : second phase (needs a second n x LD buffer in shared memory)
 // GLOBAL : working matrix in the global workspace instead of shared memory
-template <int KR, bool POLISH, bool GLOBAL, int MAXT>
+// BLOCK2 : phase 1 walks BLOCKS of two adjacent columns: a slot holds four columns in registers
+//          and applies the four cross rotations before writing them back, so a sweep reads and
+//          writes the matrix ~n/2 times instead of n times (the kernel is bound by that traffic)
+template <int KR, bool POLISH, bool GLOBAL, bool BLOCK2, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* __restrict__ Uout,
                    int32_t* __restrict__ info, float* __restrict__ workspace,
-                   int n, int canonical, float tol, int max_sweeps) {
+                   int n, int canonical, float tol, int max_sweeps, int g_wave_flag) {
     static_assert(!(POLISH && GLOBAL), "the polish phase needs both buffers in shared memory");
     constexpr int LD = 32 * KR + 4;
     constexpr int R = 4 * KR;
@@ -115,6 +142,7 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
     float* sgn = lam + n;                                       // [n]
     float* nrm = sgn + n;                                       // [n]  cached squared column norms
     int* inv = reinterpret_cast<int*>(nrm + n);                 // [n]
+    __shared__ int s_prog[512];                                 // rounds completed per pair slot (wavefront mode)
     __shared__ float s_red[32];
     __shared__ float s_sigma;
 
@@ -124,6 +152,17 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
     const int ngroups = nthr >> 3;
     const unsigned gmask = 0xFFu << (lane & 24);                // the 8 lanes of this slot
     const int n_pad = (n + 1) & ~1, npairs = n_pad >> 1, m = n_pad - 1;
+    // Wavefront mode (one pair slot per 8-lane group, working matrix in shared memory): a slot's
+    // columns at round r+1 were held by slots i-1 and i+1 at round r (the round-robin passes
+    // every column to a neighbouring slot), so instead of a CTA barrier per round each slot
+    // publishes the number of rounds it has completed and waits only for its two neighbours.
+    // Loads, arithmetic and stores of different warps then overlap instead of moving in phases.
+    const bool wave = !GLOBAL && !BLOCK2 && ngroups >= npairs && npairs <= 512 && g_wave_flag != 0;
+    volatile int* prog = s_prog;
+    const int dep_lo = g > 0 ? g - 1 : (npairs > 1 ? 1 : 0);
+    const int dep_hi = g + 1 < npairs ? g + 1 : (npairs > 1 ? g - 1 : 0);
+    int t_done = 0;                                               // rounds completed by every slot so far
+    for (int i = tid; i < 512; i += nthr) s_prog[i] = 0;
     const float* A = Ain + (size_t)blockIdx.x * n * n;
     float* Wg = Wout + (size_t)blockIdx.x * n;
     float* Ug = Uout + (size_t)blockIdx.x * n * n;
@@ -190,41 +229,83 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
         }
         __syncthreads();
         int rotated = 0;
-        for (int r = 0; r < m; ++r) {
-            for (int slot = g; slot < npairs; slot += ngroups) {
-                int p, q;
-                rr_pair(slot, r, m, n_pad, p, q);
-                if (p < n && q < n) {
+        const float tol2 = tol * tol;
+        if (BLOCK2) {
+            const int nblk = n_pad >> 1, nblk_pad = (nblk + 1) & ~1, mb = nblk_pad - 1, nslots = nblk_pad >> 1;
+            // (a) the pair inside every block, once per sweep
+            for (int blk = g; blk < nblk; blk += ngroups) {
+                const int p = 2 * blk, q = p + 1;
+                if (q < n) {
                     float a[R], b[R];
-                    float* cp = G + (size_t)p * LD;
-                    float* cq = G + (size_t)q * LD;
-                    load_col<KR, GLOBAL>(cp, j, a);
-                    load_col<KR, GLOBAL>(cq, j, b);
-                    const float aa = nrm[p], bb = nrm[q];
-                    float ab0 = 0.f, ab1 = 0.f;
-#pragma unroll
-                    for (int e = 0; e < R; e += 2) {
-                        ab0 = fmaf(a[e], b[e], ab0);
-                        ab1 = fmaf(a[e + 1], b[e + 1], ab1);
-                    }
-                    const float ab = group_sum8(ab0 + ab1, gmask);
-                    if (ab * ab > tol * tol * aa * bb) {
-                        float c, s, t;
-                        jacobi_cs(aa, bb, ab, c, s, t);
-#pragma unroll
-                        for (int e = 0; e < R; ++e) {
-                            const float x = a[e], y = b[e];
-                            a[e] = c * x - s * y;
-                            b[e] = s * x + c * y;
-                        }
-                        store_col<KR, GLOBAL>(cp, j, a);
-                        store_col<KR, GLOBAL>(cq, j, b);
-                        if (j == 0) { nrm[p] = aa - t * ab; nrm[q] = bb + t * ab; }
+                    load_col<KR, GLOBAL>(G + (size_t)p * LD, j, a);
+                    load_col<KR, GLOBAL>(G + (size_t)q * LD, j, b);
+                    float na = nrm[p], nb = nrm[q];
+                    if (rotate_regs<R>(a, b, na, nb, tol2, gmask)) {
+                        store_col<KR, GLOBAL>(G + (size_t)p * LD, j, a);
+                        store_col<KR, GLOBAL>(G + (size_t)q * LD, j, b);
+                        if (j == 0) { nrm[p] = na; nrm[q] = nb; }
                         rotated = 1;
                     }
                 }
             }
             __syncthreads();
+            // (b) the four cross pairs of every pair of blocks, round-robin over the blocks
+            for (int r = 0; r < mb; ++r) {
+                for (int slot = g; slot < nslots; slot += ngroups) {
+                    int P, Q;
+                    rr_pair(slot, r, mb, nblk_pad, P, Q);
+                    if (P < nblk && Q < nblk) {
+                        const int p0 = 2 * P, p1 = p0 + 1, q0 = 2 * Q, q1 = q0 + 1;
+                        const bool vp1 = p1 < n, vq1 = q1 < n;                  // only an odd n has a phantom column
+                        float a0[R], a1[R], b0[R], b1[R];
+                        load_col<KR, GLOBAL>(G + (size_t)p0 * LD, j, a0);
+                        load_col<KR, GLOBAL>(G + (size_t)q0 * LD, j, b0);
+                        load_col<KR, GLOBAL>(G + (size_t)(vp1 ? p1 : p0) * LD, j, a1);
+                        load_col<KR, GLOBAL>(G + (size_t)(vq1 ? q1 : q0) * LD, j, b1);
+                        float na0 = nrm[p0], nb0 = nrm[q0], na1 = vp1 ? nrm[p1] : 1.f, nb1 = vq1 ? nrm[q1] : 1.f;
+                        bool ra0 = false, ra1 = false, rb0 = false, rb1 = false;
+                        if (rotate_regs<R>(a0, b0, na0, nb0, tol2, gmask)) { ra0 = rb0 = true; }
+                        if (vp1 && vq1 && rotate_regs<R>(a1, b1, na1, nb1, tol2, gmask)) { ra1 = rb1 = true; }
+                        if (vq1 && rotate_regs<R>(a0, b1, na0, nb1, tol2, gmask)) { ra0 = rb1 = true; }
+                        if (vp1 && rotate_regs<R>(a1, b0, na1, nb0, tol2, gmask)) { ra1 = rb0 = true; }
+                        if (ra0) { store_col<KR, GLOBAL>(G + (size_t)p0 * LD, j, a0); if (j == 0) nrm[p0] = na0; }
+                        if (ra1) { store_col<KR, GLOBAL>(G + (size_t)p1 * LD, j, a1); if (j == 0) nrm[p1] = na1; }
+                        if (rb0) { store_col<KR, GLOBAL>(G + (size_t)q0 * LD, j, b0); if (j == 0) nrm[q0] = nb0; }
+                        if (rb1) { store_col<KR, GLOBAL>(G + (size_t)q1 * LD, j, b1); if (j == 0) nrm[q1] = nb1; }
+                        if (ra0 | ra1 | rb0 | rb1) rotated = 1;
+                    }
+                }
+                __syncthreads();
+            }
+        } else {
+        for (int r = 0; r < m; ++r) {
+            if (wave && g < npairs) {
+                for (unsigned spin = 0; min(prog[dep_lo], prog[dep_hi]) < t_done; ++spin) if (spin > (1u << 24)) __trap();
+                __threadfence_block();
+            }
+            for (int slot = g; slot < npairs; slot += ngroups) {
+                int p, q;
+                rr_pair(slot, r, m, n_pad, p, q);
+                if (p < n && q < n) {
+                    float a[R], b[R];
+                    load_col<KR, GLOBAL>(G + (size_t)p * LD, j, a);
+                    load_col<KR, GLOBAL>(G + (size_t)q * LD, j, b);
+                    float na = nrm[p], nb = nrm[q];
+                    if (rotate_regs<R>(a, b, na, nb, tol2, gmask)) {
+                        store_col<KR, GLOBAL>(G + (size_t)p * LD, j, a);
+                        store_col<KR, GLOBAL>(G + (size_t)q * LD, j, b);
+                        if (j == 0) { nrm[p] = na; nrm[q] = nb; }
+                        rotated = 1;
+                    }
+                }
+            }
+            ++t_done;
+            if (wave) {
+                if (g < npairs) { __threadfence_block(); __syncwarp(gmask); if (j == 0) prog[g] = t_done; }
+            } else {
+                __syncthreads();
+            }
+        }
         }
         ++sweeps;
         if (__syncthreads_count(rotated) <= few_threads) { converged = 1; break; }
@@ -284,6 +365,10 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
         for (int psweep = 0; psweep < 6; ++psweep) {
             int rotated = 0;
             for (int r = 0; r < m; ++r) {
+                if (wave && g < npairs) {
+                    for (unsigned spin = 0; min(prog[dep_lo], prog[dep_hi]) < t_done; ++spin) if (spin > (1u << 24)) __trap();
+                    __threadfence_block();
+                }
                 for (int slot = g; slot < npairs; slot += ngroups) {
                     int p, q;
                     rr_pair(slot, r, m, n_pad, p, q);
@@ -325,7 +410,12 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
                         }
                     }
                 }
-                __syncthreads();
+                ++t_done;
+                if (wave) {
+                    if (g < npairs) { __threadfence_block(); __syncwarp(gmask); if (j == 0) prog[g] = t_done; }
+                } else {
+                    __syncthreads();
+                }
             }
             if (__syncthreads_count(rotated) <= few_threads) break;
         }
@@ -418,22 +508,29 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
     if (tid == 0) info[blockIdx.x] = converged ? sweeps : -2;
 }
 
-static int eigh_threads(int n) {
+int g_eigh_block2 = 0;          // gsr_set_tuning("eigh_block2", 0|1): measured slower on B200 (19.0 vs 17.6 ms / 1024 graphs)
+int g_eigh_wave = 1;            // gsr_set_tuning("eigh_wave", 0|1): neighbour flags instead of a CTA barrier per round
+
+static int eigh_threads(int n, bool block2) {
     const int npairs = ((n + 1) & ~1) / 2;
+    if (block2) {                                                 // one slot per pair of 2-column blocks
+        const int nslots = ((npairs + 1) & ~1) / 2;
+        return 32 * ((nslots * kGroup + 31) / 32);
+    }
     const int iters = (npairs * kGroup + 1023) / 1024;            // pair slots per group per round
     const int groups = (npairs + iters - 1) / iters;
     return 32 * ((groups * kGroup + 31) / 32);
 }
 
-template <int KR, bool POLISH, bool GLOBAL, int MAXT>
+template <int KR, bool POLISH, bool GLOBAL, bool BLOCK2, int MAXT>
 static int launch_one(const float* A, float* w, float* U, int32_t* info, float* ws, int batch, int n,
                       int canonical, float tol, int max_sweeps, size_t smem, cudaStream_t st) {
-    auto k = eigh_jacobi_kernel<KR, POLISH, GLOBAL, MAXT>;
+    auto k = eigh_jacobi_kernel<KR, POLISH, GLOBAL, BLOCK2, MAXT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "eigh_jacobi: cudaFuncSetAttribute failed");
-    const int threads = eigh_threads(n);
+    const int threads = eigh_threads(n, BLOCK2);
     if (threads > MAXT) return fail(GSR_E_UNSUPPORTED, "eigh_jacobi: internal thread-count mismatch");
-    k<<<batch, threads, smem, st>>>(A, w, U, info, ws, n, canonical, tol, max_sweeps);
+    k<<<batch, threads, smem, st>>>(A, w, U, info, ws, n, canonical, tol, max_sweeps, g_eigh_wave);
     return launched("eigh_jacobi");
 }
 
@@ -442,13 +539,20 @@ static int launch_eigh(const float* A, float* w, float* U, int32_t* info, float*
                        int canonical, float tol, int max_sweeps, cudaStream_t st) {
     constexpr int LD = 32 * KR + 4;
     constexpr int MAXT = (128 * KR < 1024) ? 128 * KR : (KR >= 9 ? 576 : 1024);
+    constexpr int MAXT_B2 = 64 * KR + 32;                        // block mode: a quarter as many slots as columns
     const size_t small = 4 * (size_t)n * sizeof(float);
     const size_t one = (size_t)n * LD * sizeof(float) + small, two = 2 * (size_t)n * LD * sizeof(float) + small;
     const size_t cap = 227 * 1024;
-    if (two <= cap) return launch_one<KR, true, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, two, st);
-    if (one <= cap) return launch_one<KR, false, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, one, st);
+    if (two <= cap) {
+        if (g_eigh_block2) return launch_one<KR, true, false, true, MAXT_B2>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, two, st);
+        return launch_one<KR, true, false, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, two, st);
+    }
+    if (one <= cap) {
+        if (g_eigh_block2) return launch_one<KR, false, false, true, MAXT_B2>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, one, st);
+        return launch_one<KR, false, false, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, one, st);
+    }
     if (!ws) return fail(GSR_E_ARG, "eigh_jacobi: this n needs a global workspace (gsr_eigh_workspace)");
-    return launch_one<KR, false, true, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, small, st);
+    return launch_one<KR, false, true, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, small, st);
 }
 
 }  // namespace gsr

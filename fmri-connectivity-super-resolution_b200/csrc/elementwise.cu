@@ -9,7 +9,7 @@
 
 namespace gsr {
 
-constexpr int kEwThreads = 512;
+constexpr int kEwThreads = 1024;   // one or two CTAs per SM: a matrix re-read by its CTA is still in L2
 constexpr int kEwWarps = kEwThreads / 32;
 constexpr int kStripPad = 33;   // 32 + 1: conflict-free transposed reads
 
@@ -66,10 +66,12 @@ normalize_fwd_kernel(const float* __restrict__ mx, float* __restrict__ out,
         load_col_strip<PRE>(mx, n, i0, strip);
         __syncthreads();
         const int rows = min(32, n - i0);
-        for (int e = threadIdx.x; e < rows * n; e += kEwThreads) {
-            const int ii = e / n, j = e - ii * n;
+        for (int ii = warp; ii < rows; ii += kEwWarps) {
             const int i = i0 + ii;
-            out[(size_t)i * n + j] = (strip[j * kStripPad + ii] * r[i]) * r[j];
+            const float ri = r[i];
+            float* dst = out + (size_t)i * n;
+#pragma unroll 4
+            for (int j = lane; j < n; j += 32) dst[j] = (strip[j * kStripPad + ii] * ri) * r[j];
         }
         __syncthreads();
     }
@@ -133,15 +135,17 @@ normalize_bwd_kernel(const float* __restrict__ mx, const float* __restrict__ r_i
         load_col_strip<0>(T, n, a0, strip);               // strip[b][aa] = T[b, a0+aa]
         __syncthreads();
         const int rows = min(32, n - a0);
-        for (int e = threadIdx.x; e < rows * n; e += kEwThreads) {
-            const int aa = e / n, b = e - aa * n;
+        for (int aa = warp; aa < rows; aa += kEwWarps) {
             const int a = a0 + aa;
-            float g = (strip[b * kStripPad + aa] * r[a]) * r[b] + dr[a];
-            if (PRE) {
-                const float v = __ldg(mx + (size_t)a * n + b);
-                g = (a == b) ? 0.f : g * sgnf(v);
+            const float ra = r[a], da = dr[a];
+            const float* mrow = mx + (size_t)a * n;
+            float* drow = dmx + (size_t)a * n;
+#pragma unroll 4
+            for (int b = lane; b < n; b += 32) {
+                float g = (strip[b * kStripPad + aa] * ra) * r[b] + da;
+                if (PRE) g = (a == b) ? 0.f : g * sgnf(__ldg(mrow + b));
+                drow[b] = g;
             }
-            dmx[(size_t)a * n + b] = g;
         }
         __syncthreads();
     }
@@ -158,11 +162,16 @@ sym_diag_abs_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, in
         load_col_strip<0>(x, n, i0, strip);               // strip[j][ii] = x[j, i0+ii]
         __syncthreads();
         const int rows = min(32, n - i0);
-        for (int e = threadIdx.x; e < rows * n; e += kEwThreads) {
-            const int ii = e / n, j = e - ii * n;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int ii = warp; ii < rows; ii += kEwWarps) {
             const int i = i0 + ii;
-            const float z = (__ldg(x + (size_t)i * n + j) + strip[j * kStripPad + ii]) / 2.0f;
-            out[(size_t)i * n + j] = (i == j) ? 1.0f : fabsf(z);
+            const float* xrow = x + (size_t)i * n;
+            float* orow = out + (size_t)i * n;
+#pragma unroll 4
+            for (int j = lane; j < n; j += 32) {
+                const float z = (__ldg(xrow + j) + strip[j * kStripPad + ii]) / 2.0f;
+                orow[j] = (i == j) ? 1.0f : fabsf(z);
+            }
         }
         __syncthreads();
     }
@@ -181,16 +190,19 @@ sym_diag_abs_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g
         load_col_strip<0>(g, n, i0, sg);
         __syncthreads();
         const int rows = min(32, n - i0);
-        for (int e = threadIdx.x; e < rows * n; e += kEwThreads) {
-            const int ii = e / n, j = e - ii * n;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int ii = warp; ii < rows; ii += kEwWarps) {
             const int i = i0 + ii;
-            float v = 0.f;
-            if (i != j) {
-                const float z = (__ldg(x + (size_t)i * n + j) + sx[j * kStripPad + ii]) / 2.0f;
+            const float* xrow = x + (size_t)i * n;
+            const float* grow = g + (size_t)i * n;
+            float* drow = dx + (size_t)i * n;
+#pragma unroll 4
+            for (int j = lane; j < n; j += 32) {
+                const float z = (__ldg(xrow + j) + sx[j * kStripPad + ii]) / 2.0f;
                 const float s = sgnf(z);
-                v = (__ldg(g + (size_t)i * n + j) * s + sg[j * kStripPad + ii] * s) / 2.0f;
+                const float v = (__ldg(grow + j) * s + sg[j * kStripPad + ii] * s) / 2.0f;
+                drow[j] = (i == j) ? 0.f : v;
             }
-            dx[(size_t)i * n + j] = v;
         }
         __syncthreads();
     }
