@@ -8,7 +8,7 @@
 // term is 2^-22 relative).  Per CTA:
 //   * tile 128 (M) x up to 288 (N = 160 + up to 128, two UMMA N ranges) x 32 (K per stage), so
 //     one 268-column subject row block needs a single N tile;
-//   * 15 producer warps read the fp32 operands from global memory (float4, any layout: the
+//   * 14 producer warps (two groups alternating k-blocks) read the fp32 operands from global memory (float4, any layout: the
 //     transposes of the backward pass are absorbed by the UMMA K-major / MN-major descriptor
 //     bit), split them and store hi / lo tiles in UMMA canonical layouts: K-major tiles use
 //     the no-swizzle layout (8 x 16 B core matrices), MN-major tiles the 128B_BASE32B layout
@@ -32,7 +32,8 @@ constexpr int BN = 288;                 // 160 + up to 128 (multiple of the 32-e
 constexpr int BN0 = 160;
 constexpr int BK = 32;
 constexpr int STAGES = 2;
-constexpr int PRODUCER_WARPS = 15;    // + 1 MMA warp = 512 threads -> 128 registers each
+constexpr int PRODUCER_WARPS = 14;    // two groups of 7 (+ 1 MMA warp = 480 threads -> 128 registers each)
+constexpr int GROUP_WARPS = PRODUCER_WARPS / 2;
 constexpr int EPILOGUE_WARPS = 12;    // 3 column groups x 4 TMEM lane quarters
 constexpr int THREADS = 32 * (PRODUCER_WARPS + 1);
 constexpr int A_TILE = BM * BK * 4;     // bytes of one tf32 A tile (hi or lo)
@@ -43,7 +44,7 @@ constexpr int TMEM_COLS = 512;
 constexpr int A_PATCHES = BM * BK / 128;                        // 32 patches of 128 floats (one per warp instruction)
 constexpr int B_PATCHES = BN * BK / 128;                        // 72
 constexpr int PATCHES = A_PATCHES + B_PATCHES;                  // 104
-constexpr int PATCH_ITERS = (PATCHES + PRODUCER_WARPS - 1) / PRODUCER_WARPS;   // 7
+constexpr int PATCH_ITERS = (PATCHES + GROUP_WARPS - 1) / GROUP_WARPS;   // 15: one group stages a whole k-block
 
 struct Params {
     const float* A; const float* B; float* C;
@@ -230,7 +231,7 @@ tcgemm_kernel(const Params p) {
     const int total_kb = nsub * nkb;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, PRODUCER_WARPS * 32); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, GROUP_WARPS * 32); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_accum, 1);
         fence_barrier_init();
     }
@@ -242,15 +243,20 @@ tcgemm_kernel(const Params p) {
 
     if (warp < PRODUCER_WARPS) {
         // ===== producers: global fp32 -> (hi, lo) tf32 tiles in shared memory.
-        // Per-thread patch state (global offset, validity, shared offset) is computed once; the
-        // k loop only advances pointers.  The k loop is unrolled by two over two register sets so
-        // that the loads of k-block it+1 are in flight while k-block it is split and stored.
+        // The producer warps form two groups; group g stages the k-blocks it % 2 == g into stage g.
+        // A group's iteration is load -> split -> store -> proxy fence -> arrive, and the fence
+        // (MEMBAR) waits for every outstanding access of its thread, so a thread cannot keep the
+        // next k-block's loads in flight across it; instead the OTHER group's loads are in
+        // flight while this one splits and stores.  Per-thread patch state (global offset,
+        // validity, shared offset) is computed once; the k loop only advances pointers.
+        static_assert(STAGES == 2, "one stage per producer group");
+        const int grp = warp / GROUP_WARPS, gw = warp % GROUP_WARPS;
         long long goff[PATCH_ITERS];        // element offset of this thread's float4 at k-block 0
         uint32_t so[PATCH_ITERS];           // byte offset inside the (hi or lo) tile
         uint32_t ok_mask = 0;               // bit i: the float4 of patch i lies inside the operand (rows)
 #pragma unroll
         for (int i = 0; i < PATCH_ITERS; ++i) {
-            const int patch = warp + i * PRODUCER_WARPS;
+            const int patch = gw + i * GROUP_WARPS;
             int row = 0, k = 0;
             goff[i] = 0; so[i] = 0;
             if (patch < A_PATCHES) {
@@ -266,52 +272,41 @@ tcgemm_kernel(const Params p) {
             }
         }
         const long long a_kadv = TA ? (long long)BK * p.lda : BK, b_kadv = TB ? BK : (long long)BK * p.ldb;
-
-        auto issue_loads = [&](int it, float4 (&dst)[PATCH_ITERS]) {
+        uint8_t* st = smem + grp * STAGE_BYTES;
+        for (int it = grp; it < total_kb; it += 2) {
+            const int use = it / STAGES;
             const int b = b_first + (it / nkb) * b_step, kb = it % nkb;
             const float* A = p.A + (size_t)b * p.sA;
             const float* B = p.B + (size_t)b * p.sB;
+            float4 v[PATCH_ITERS];
             if ((kb + 1) * BK <= p.K) {                                    // whole k-block inside K: no k predicates
 #pragma unroll
                 for (int i = 0; i < PATCH_ITERS; ++i) {
-                    const int patch = warp + i * PRODUCER_WARPS;
-                    dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int patch = gw + i * GROUP_WARPS;
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (patch < PATCHES && ((ok_mask >> i) & 1u)) {
                         const float* src = patch < A_PATCHES ? A + goff[i] + kb * a_kadv : B + goff[i] + kb * b_kadv;
-                        dst[i] = __ldg(reinterpret_cast<const float4*>(src));
+                        v[i] = __ldg(reinterpret_cast<const float4*>(src));
                     }
                 }
             } else {                                                       // ragged tail (k and row edges): generic path
                 uint32_t dummy;
 #pragma unroll
                 for (int i = 0; i < PATCH_ITERS; ++i) {
-                    const int patch = warp + i * PRODUCER_WARPS;
-                    if (patch < A_PATCHES) dst[i] = load_patch<BM, !TA>(A, p.lda, p.M, p.K, m0, kb * BK, patch, lane, dummy);
-                    else if (patch < PATCHES) dst[i] = load_patch<BN, TB>(B, p.ldb, p.N, p.K, n0, kb * BK, patch - A_PATCHES, lane, dummy);
+                    const int patch = gw + i * GROUP_WARPS;
+                    if (patch < A_PATCHES) v[i] = load_patch<BM, !TA>(A, p.lda, p.M, p.K, m0, kb * BK, patch, lane, dummy);
+                    else if (patch < PATCHES) v[i] = load_patch<BN, TB>(B, p.ldb, p.N, p.K, n0, kb * BK, patch - A_PATCHES, lane, dummy);
                 }
             }
-        };
-        auto split_store = [&](int it, const float4 (&src)[PATCH_ITERS]) {
-            const int s = it % STAGES, use = it / STAGES;
-            if (use > 0) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);      // MMA has drained this stage
-            uint8_t* st = smem + s * STAGE_BYTES;
+            if (use > 0) mbar_wait(bar_empty + 8 * grp, (use - 1) & 1);    // MMA has drained this stage
 #pragma unroll
             for (int i = 0; i < PATCH_ITERS; ++i) {
-                const int patch = warp + i * PRODUCER_WARPS;
-                if (patch < A_PATCHES) store_split(st, st + A_TILE, so[i], src[i]);
-                else if (patch < PATCHES) store_split(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, so[i], src[i]);
+                const int patch = gw + i * GROUP_WARPS;
+                if (patch < A_PATCHES) store_split(st, st + A_TILE, so[i], v[i]);
+                else if (patch < PATCHES) store_split(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, so[i], v[i]);
             }
             fence_async_smem();                                            // generic-proxy writes -> async proxy (UMMA)
-            mbar_arrive(bar_full + 8 * s);
-        };
-        float4 va[PATCH_ITERS], vb[PATCH_ITERS];
-        issue_loads(0, va);
-        for (int it = 0; it < total_kb; it += 2) {
-            if (it + 1 < total_kb) issue_loads(it + 1, vb);
-            split_store(it, va);
-            if (it + 1 >= total_kb) break;
-            if (it + 2 < total_kb) issue_loads(it + 2, va);
-            split_store(it + 1, vb);
+            mbar_arrive(bar_full + 8 * grp);
         }
     } else {
         // ===== MMA issuer: one elected lane
