@@ -233,7 +233,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    K.GEMM_TIMER = K.KernelTimer()
+    K.GEMM_TIMER, K.EIGH_TIMER, K.EW_TIMER = K.KernelTimer(), K.KernelTimer(), K.KernelTimer()
     launches0 = pkg.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -245,7 +245,10 @@ def run_ours(args):
     elapsed_ms = e0.elapsed_time(e1)
     launches = pkg.launch_count() - launches0
     gemm_ms, gemm_flops, gemm_launches = K.GEMM_TIMER.totals()
-    K.GEMM_TIMER = None
+    eigh_ms, eigh_graphs, eigh_launches = K.EIGH_TIMER.totals()
+    ew_ms, ew_bytes, ew_launches = K.EW_TIMER.totals()
+    eigh_info = getattr(K.EIGH_TIMER, "last_info", None)
+    K.GEMM_TIMER = K.EIGH_TIMER = K.EW_TIMER = None
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -303,20 +306,58 @@ def run_ours(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
+    backend = K.GEMM_BACKEND
     gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-    roofline = {
-        "kernel": "gsr::bgemm_kernel (136x136x8 SIMT FP32 tile, all subject-dependent contractions)",
-        "bound": "fp32",
-        "achieved": gemm_tflops, "peak": ffma_best, "unit": "TFLOP/s",
-        "frac": (gemm_tflops / ffma_best) if (gemm_tflops and ffma_best) else None,
-        "peak_source": "FP32 FFMA probe kernel measured in this run (MEASURED_PEAKS.json holds HBM and bf16 "
-                       "tensor peaks only; the contraction kernel of this round is SIMT FP32, not tensor-core)",
-        "share_of_step": gemm_ms / elapsed_ms if elapsed_ms else None,
-        "launches": gemm_launches,
-        "algorithmic_flop_per_subject": GEMM_FLOP_PER_SUBJECT_FWD_BWD,
-        "traffic": None,
-        "hbm_peak_gbs": peaks.get("hbm_gbs"), "bf16_peak_tflops": peaks.get("bf16_tflops_sustained"),
+    bf16_peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    # --- contraction kernel: tensor-bound.  tcgen05 kind::tf32 runs at half the bf16 rate and the 3xTF32 split
+    #     issues three MMAs per algorithmic product, both stated so that `frac` is against the MEASURED bf16 peak.
+    gemm_roof = {
+        "kernel": ("gsr::tc::tcgemm_kernel (tcgen05.mma kind::tf32, 3xTF32 split, 128x288x32 tile, accumulators in TMEM)"
+                   if backend == "tc" else "gsr::bgemm_kernel (136x136x16 SIMT FP32 tile)"),
+        "bound": "tensor" if backend == "tc" else "fp32",
+        "achieved": gemm_tflops, "unit": "TFLOP/s (algorithmic fp32 flops of the contractions)",
+        "peak": bf16_peak if backend == "tc" else ffma_best,
+        "frac": (gemm_tflops / (bf16_peak if backend == "tc" else ffma_best)) if gemm_tflops else None,
+        "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the step); TF32 peak is half of it "
+                        "and 3xTF32 needs 3 MMAs per product, so the fp32-accurate ceiling of this kernel is peak/6"
+                        if backend == "tc" else "FP32 FFMA probe kernel measured in this run"),
+        "frac_of_3xtf32_ceiling": (gemm_tflops / (bf16_peak / 6.0)) if (gemm_tflops and backend == "tc") else None,
+        "share_of_step": gemm_ms / elapsed_ms if elapsed_ms else None, "launches": gemm_launches,
+        "algorithmic_flop_per_subject": GEMM_FLOP_PER_SUBJECT_FWD_BWD, "traffic": None,
     }
+    # --- LR eigendecomposition: resident in shared memory, bound by the LSU / shared-memory data pipe
+    eigh_roof = None
+    if eigh_ms > 0 and eigh_info is not None:
+        sw = (eigh_info & 0xFF).double().sum().item()
+        ps = (eigh_info >> 8).double().sum().item()
+        n = LR_DIM
+        # every one-sided round reads and writes all n columns once; a polish round reads 2n columns
+        # (U and A.U) and writes the rotated ones (counted as read only: the algorithmic minimum)
+        bytes_per_launch = (sw * (n - 1) * 2 * n * n * 4.0) + (ps * (n - 1) * 2 * n * n * 4.0)
+        launches_per_timer = max(eigh_launches, 1)
+        gbs = bytes_per_launch / (eigh_ms / launches_per_timer * 1e-3) / 1e9
+        smem_peak = 148 * 128 * sm_mhz * 1e6 / 1e9
+        eigh_roof = {
+            "kernel": "gsr::eigh_jacobi_kernel<5, polish> (one CTA per 160-node graph, 212 KB shared memory)",
+            "bound": "smem", "achieved": gbs, "unit": "GB/s (shared-memory bytes the Jacobi rounds must move)",
+            "peak": smem_peak, "frac": gbs / smem_peak,
+            "peak_source": f"148 SMs x 128 B/clk x {sm_mhz:.0f} MHz (clock sampled in this run); ncu: lsu data-pipe 66 % busy",
+            "share_of_step": eigh_ms / elapsed_ms, "launches": eigh_launches,
+            "us_per_graph": eigh_ms * 1e3 / eigh_graphs if eigh_graphs else None,
+            "sweeps_mean": sw / eigh_info.numel(), "polish_sweeps_mean": ps / eigh_info.numel(), "traffic": None,
+        }
+    ew_roof = None
+    if ew_ms > 0:
+        gbs = ew_bytes / (ew_ms * 1e-3) / 1e9
+        ew_roof = {"kernel": "normalize_{fwd,bwd}_kernel + sym_diag_abs_{fwd,bwd}_kernel (memory-bound n x n kernels)",
+                   "bound": "hbm", "achieved": gbs, "unit": "GB/s", "peak": peaks.get("hbm_gbs"),
+                   "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                   "peak_source": "MEASURED_PEAKS.json hbm_gbs", "share_of_step": ew_ms / elapsed_ms,
+                   "launches": ew_launches, "traffic": None}
+    by_kernel = [r for r in (eigh_roof, gemm_roof, ew_roof) if r]
+    roofline = max(by_kernel, key=lambda r: r["share_of_step"] or 0.0)          # the dominant kernel of the step
+    others = [r for r in by_kernel if r is not roofline]
     cpu_baseline = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -334,6 +375,7 @@ def run_ours(args):
                    "subjects_per_gpu": B, "global_subjects_per_step": world * B,
                    "parallelism": f"subject-data-parallel x{world}, one NCCL all-reduce of the flat 4.09 MB gradient bucket",
                    "lr_eigh": "in step (batched Jacobi kernel)", "hr_target_eigh": hr_note,
+                   "gemm_backend": K.GEMM_BACKEND,
                    "l2": "inputs of one step are 400 MB per GPU (> 126 MB L2); no flush needed",
                    "optimizer": "torch.optim.Adam(fused=True), in the timed region"},
         "clocks": clocks,
@@ -342,6 +384,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": world * 4},
         "gpu_launches": launches,
         "roofline": roofline,
+        "roofline_other_kernels": others,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)

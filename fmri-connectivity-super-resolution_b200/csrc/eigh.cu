@@ -9,8 +9,8 @@
 //     rotations that orthogonalise G converge to G.V = U.diag(lambda + sigma)
 //     with V -> U, so no separate eigenvector accumulator is kept: the
 //     normalised columns ARE the eigenvectors.
-//   * columns are stored contiguously (ld = 32*KR + 4 floats); 8 lanes own one
-//     column pair, 4*KR rows each, read and written as conflict-free float4s;
+//   * columns are stored contiguously (ld = 32*KR + 4 floats); 8 (or 16) lanes own one
+//     column pair, 4*KR (2*KR) rows each, read and written as conflict-free float4s (float2s);
 //     the pivot dot product is reduced with 3 xor-shuffles; squared column norms
 //     are cached (exact once per sweep, updated as aa -= t*ab, bb += t*ab).
 //   * pairs follow the round-robin ("circle") tournament, computed analytically
@@ -45,7 +45,9 @@ constexpr int kGroup = 8;        // lanes per column pair
 // Butterfly over the 8 lanes of one pair slot.  `mask` names only those 8 lanes, so
 // slots of the same warp may sit in different branches.  Every lane ends with the
 // bitwise-identical sum (each level adds the same two operands in both partners).
-__device__ __forceinline__ float group_sum8(float v, unsigned mask) {
+template <int LG>
+__device__ __forceinline__ float group_sum(float v, unsigned mask) {
+    if (LG == 16) v += __shfl_xor_sync(mask, v, 8);
     v += __shfl_xor_sync(mask, v, 4);
     v += __shfl_xor_sync(mask, v, 2);
     v += __shfl_xor_sync(mask, v, 1);
@@ -54,22 +56,36 @@ __device__ __forceinline__ float group_sum8(float v, unsigned mask) {
 
 // GLOBAL: the working matrix lives in a global-memory workspace; .cg accesses (L2) keep the
 // CTA coherent across its own barriers.
-template <int KR, bool GLOBAL>
-__device__ __forceinline__ void load_col(const float* col, int j, float (&v)[4 * KR]) {
+// LG lanes share a column: lane j owns rows VEC*j + 32*k + (0..VEC-1), VEC = 32 / LG, so that the
+// LG lanes of one access cover 128 contiguous bytes (conflict free).
+template <int KR, bool GLOBAL, int LG>
+__device__ __forceinline__ void load_col(const float* col, int j, float (&v)[(32 / LG) * KR]) {
 #pragma unroll
     for (int k = 0; k < KR; ++k) {
-        const float4* ptr = reinterpret_cast<const float4*>(col + 4 * j + 32 * k);
-        const float4 t = GLOBAL ? __ldcg(ptr) : *ptr;
-        v[4 * k + 0] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+        if (LG == 8) {
+            const float4* ptr = reinterpret_cast<const float4*>(col + 4 * j + 32 * k);
+            const float4 t = GLOBAL ? __ldcg(ptr) : *ptr;
+            v[4 * k + 0] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+        } else {
+            const float2* ptr = reinterpret_cast<const float2*>(col + 2 * j + 32 * k);
+            const float2 t = GLOBAL ? __ldcg(ptr) : *ptr;
+            v[2 * k + 0] = t.x; v[2 * k + 1] = t.y;
+        }
     }
 }
-template <int KR, bool GLOBAL>
-__device__ __forceinline__ void store_col(float* col, int j, const float (&v)[4 * KR]) {
+template <int KR, bool GLOBAL, int LG>
+__device__ __forceinline__ void store_col(float* col, int j, const float (&v)[(32 / LG) * KR]) {
 #pragma unroll
     for (int k = 0; k < KR; ++k) {
-        float4* ptr = reinterpret_cast<float4*>(col + 4 * j + 32 * k);
-        const float4 t = make_float4(v[4 * k + 0], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-        if (GLOBAL) __stcg(ptr, t); else *ptr = t;
+        if (LG == 8) {
+            float4* ptr = reinterpret_cast<float4*>(col + 4 * j + 32 * k);
+            const float4 t = make_float4(v[4 * k + 0], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            if (GLOBAL) __stcg(ptr, t); else *ptr = t;
+        } else {
+            float2* ptr = reinterpret_cast<float2*>(col + 2 * j + 32 * k);
+            const float2 t = make_float2(v[2 * k + 0], v[2 * k + 1]);
+            if (GLOBAL) __stcg(ptr, t); else *ptr = t;
+        }
     }
 }
 template <bool GLOBAL>
@@ -96,7 +112,7 @@ __device__ __forceinline__ void rr_pair(int slot, int r, int m, int n_pad, int& 
 }
 
 // One rotation of the register-resident columns x, y (cached squared norms nx, ny).
-template <int R>
+template <int R, int LG>
 __device__ __forceinline__ bool rotate_regs(float (&x)[R], float (&y)[R], float& nx, float& ny, float tol2, unsigned gmask) {
     float d0 = 0.f, d1 = 0.f;
 #pragma unroll
@@ -104,7 +120,7 @@ __device__ __forceinline__ bool rotate_regs(float (&x)[R], float (&y)[R], float&
         d0 = fmaf(x[e], y[e], d0);
         d1 = fmaf(x[e + 1], y[e + 1], d1);
     }
-    const float xy = group_sum8(d0 + d1, gmask);
+    const float xy = group_sum<LG>(d0 + d1, gmask);
     if (!(xy * xy > tol2 * nx * ny)) return false;
     float c, s, t;
     jacobi_cs(nx, ny, xy, c, s, t);
@@ -125,14 +141,15 @@ __device__ __forceinline__ bool rotate_regs(float (&x)[R], float (&y)[R], float&
 // BLOCK2 : phase 1 walks BLOCKS of two adjacent columns: a slot holds four columns in registers
 //          and applies the four cross rotations before writing them back, so a sweep reads and
 //          writes the matrix ~n/2 times instead of n times (the kernel is bound by that traffic)
-template <int KR, bool POLISH, bool GLOBAL, bool BLOCK2, int MAXT>
+template <int KR, bool POLISH, bool GLOBAL, bool BLOCK2, int MAXT, int LG>
 __global__ void __launch_bounds__(MAXT, 1)
 eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* __restrict__ Uout,
                    int32_t* __restrict__ info, float* __restrict__ workspace,
                    int n, int canonical, float tol, int max_sweeps, int g_wave_flag) {
     static_assert(!(POLISH && GLOBAL), "the polish phase needs both buffers in shared memory");
     constexpr int LD = 32 * KR + 4;
-    constexpr int R = 4 * KR;
+    constexpr int VEC = 32 / LG;
+    constexpr int R = VEC * KR;
     extern __shared__ __align__(16) float smem[];
     float* G;                                                   // [n][LD], column c at G + c*LD
     float* H;                                                   // [n][LD] (POLISH only)
@@ -148,9 +165,9 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int g = tid >> 3, j = tid & 7;                        // pair slot, lane inside the slot
-    const int ngroups = nthr >> 3;
-    const unsigned gmask = 0xFFu << (lane & 24);                // the 8 lanes of this slot
+    const int g = tid / LG, j = tid % LG;                       // pair slot, lane inside the slot
+    const int ngroups = nthr / LG;
+    const unsigned gmask = (LG == 8) ? (0xFFu << (lane & 24)) : (0xFFFFu << (lane & 16));   // the lanes of this slot
     const int n_pad = (n + 1) & ~1, npairs = n_pad >> 1, m = n_pad - 1;
     // Wavefront mode (one pair slot per 8-lane group, working matrix in shared memory): a slot's
     // columns at round r+1 were held by slots i-1 and i+1 at round r (the round-robin passes
@@ -212,19 +229,19 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
 
     // A sweep that rotated at most this many pairs is the last one: what is left is second
     // order, and (POLISH) the next phase removes it anyway.
-    const int few_threads = kGroup * (POLISH ? (n >> 3) : 0);
+    const int few_threads = LG * (POLISH ? (n >> 3) : 0);
 
     // ---- phase 1: cyclic one-sided Jacobi sweeps on G
-    int sweeps = 0, converged = 0;
+    int sweeps = 0, converged = 0, polish_sweeps = 0;
     while (sweeps < max_sweeps) {
         // exact squared norms once per sweep; inside the sweep they follow aa -= t ab, bb += t ab
         for (int k = g; k < n; k += ngroups) {
             float u[R];
-            load_col<KR, GLOBAL>(G + (size_t)k * LD, j, u);
+            load_col<KR, GLOBAL, LG>(G + (size_t)k * LD, j, u);
             float ss = 0.f;
 #pragma unroll
             for (int e = 0; e < R; ++e) ss = fmaf(u[e], u[e], ss);
-            ss = group_sum8(ss, gmask);
+            ss = group_sum<LG>(ss, gmask);
             if (j == 0) nrm[k] = ss;
         }
         __syncthreads();
@@ -237,12 +254,12 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
                 const int p = 2 * blk, q = p + 1;
                 if (q < n) {
                     float a[R], b[R];
-                    load_col<KR, GLOBAL>(G + (size_t)p * LD, j, a);
-                    load_col<KR, GLOBAL>(G + (size_t)q * LD, j, b);
+                    load_col<KR, GLOBAL, LG>(G + (size_t)p * LD, j, a);
+                    load_col<KR, GLOBAL, LG>(G + (size_t)q * LD, j, b);
                     float na = nrm[p], nb = nrm[q];
-                    if (rotate_regs<R>(a, b, na, nb, tol2, gmask)) {
-                        store_col<KR, GLOBAL>(G + (size_t)p * LD, j, a);
-                        store_col<KR, GLOBAL>(G + (size_t)q * LD, j, b);
+                    if (rotate_regs<R, LG>(a, b, na, nb, tol2, gmask)) {
+                        store_col<KR, GLOBAL, LG>(G + (size_t)p * LD, j, a);
+                        store_col<KR, GLOBAL, LG>(G + (size_t)q * LD, j, b);
                         if (j == 0) { nrm[p] = na; nrm[q] = nb; }
                         rotated = 1;
                     }
@@ -258,20 +275,20 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
                         const int p0 = 2 * P, p1 = p0 + 1, q0 = 2 * Q, q1 = q0 + 1;
                         const bool vp1 = p1 < n, vq1 = q1 < n;                  // only an odd n has a phantom column
                         float a0[R], a1[R], b0[R], b1[R];
-                        load_col<KR, GLOBAL>(G + (size_t)p0 * LD, j, a0);
-                        load_col<KR, GLOBAL>(G + (size_t)q0 * LD, j, b0);
-                        load_col<KR, GLOBAL>(G + (size_t)(vp1 ? p1 : p0) * LD, j, a1);
-                        load_col<KR, GLOBAL>(G + (size_t)(vq1 ? q1 : q0) * LD, j, b1);
+                        load_col<KR, GLOBAL, LG>(G + (size_t)p0 * LD, j, a0);
+                        load_col<KR, GLOBAL, LG>(G + (size_t)q0 * LD, j, b0);
+                        load_col<KR, GLOBAL, LG>(G + (size_t)(vp1 ? p1 : p0) * LD, j, a1);
+                        load_col<KR, GLOBAL, LG>(G + (size_t)(vq1 ? q1 : q0) * LD, j, b1);
                         float na0 = nrm[p0], nb0 = nrm[q0], na1 = vp1 ? nrm[p1] : 1.f, nb1 = vq1 ? nrm[q1] : 1.f;
                         bool ra0 = false, ra1 = false, rb0 = false, rb1 = false;
-                        if (rotate_regs<R>(a0, b0, na0, nb0, tol2, gmask)) { ra0 = rb0 = true; }
-                        if (vp1 && vq1 && rotate_regs<R>(a1, b1, na1, nb1, tol2, gmask)) { ra1 = rb1 = true; }
-                        if (vq1 && rotate_regs<R>(a0, b1, na0, nb1, tol2, gmask)) { ra0 = rb1 = true; }
-                        if (vp1 && rotate_regs<R>(a1, b0, na1, nb0, tol2, gmask)) { ra1 = rb0 = true; }
-                        if (ra0) { store_col<KR, GLOBAL>(G + (size_t)p0 * LD, j, a0); if (j == 0) nrm[p0] = na0; }
-                        if (ra1) { store_col<KR, GLOBAL>(G + (size_t)p1 * LD, j, a1); if (j == 0) nrm[p1] = na1; }
-                        if (rb0) { store_col<KR, GLOBAL>(G + (size_t)q0 * LD, j, b0); if (j == 0) nrm[q0] = nb0; }
-                        if (rb1) { store_col<KR, GLOBAL>(G + (size_t)q1 * LD, j, b1); if (j == 0) nrm[q1] = nb1; }
+                        if (rotate_regs<R, LG>(a0, b0, na0, nb0, tol2, gmask)) { ra0 = rb0 = true; }
+                        if (vp1 && vq1 && rotate_regs<R, LG>(a1, b1, na1, nb1, tol2, gmask)) { ra1 = rb1 = true; }
+                        if (vq1 && rotate_regs<R, LG>(a0, b1, na0, nb1, tol2, gmask)) { ra0 = rb1 = true; }
+                        if (vp1 && rotate_regs<R, LG>(a1, b0, na1, nb0, tol2, gmask)) { ra1 = rb0 = true; }
+                        if (ra0) { store_col<KR, GLOBAL, LG>(G + (size_t)p0 * LD, j, a0); if (j == 0) nrm[p0] = na0; }
+                        if (ra1) { store_col<KR, GLOBAL, LG>(G + (size_t)p1 * LD, j, a1); if (j == 0) nrm[p1] = na1; }
+                        if (rb0) { store_col<KR, GLOBAL, LG>(G + (size_t)q0 * LD, j, b0); if (j == 0) nrm[q0] = nb0; }
+                        if (rb1) { store_col<KR, GLOBAL, LG>(G + (size_t)q1 * LD, j, b1); if (j == 0) nrm[q1] = nb1; }
                         if (ra0 | ra1 | rb0 | rb1) rotated = 1;
                     }
                 }
@@ -288,12 +305,12 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
                 rr_pair(slot, r, m, n_pad, p, q);
                 if (p < n && q < n) {
                     float a[R], b[R];
-                    load_col<KR, GLOBAL>(G + (size_t)p * LD, j, a);
-                    load_col<KR, GLOBAL>(G + (size_t)q * LD, j, b);
+                    load_col<KR, GLOBAL, LG>(G + (size_t)p * LD, j, a);
+                    load_col<KR, GLOBAL, LG>(G + (size_t)q * LD, j, b);
                     float na = nrm[p], nb = nrm[q];
-                    if (rotate_regs<R>(a, b, na, nb, tol2, gmask)) {
-                        store_col<KR, GLOBAL>(G + (size_t)p * LD, j, a);
-                        store_col<KR, GLOBAL>(G + (size_t)q * LD, j, b);
+                    if (rotate_regs<R, LG>(a, b, na, nb, tol2, gmask)) {
+                        store_col<KR, GLOBAL, LG>(G + (size_t)p * LD, j, a);
+                        store_col<KR, GLOBAL, LG>(G + (size_t)q * LD, j, b);
                         if (j == 0) { nrm[p] = na; nrm[q] = nb; }
                         rotated = 1;
                     }
@@ -315,15 +332,15 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
     for (int k = g; k < n; k += ngroups) {
         float u[R];
         float* ck = G + (size_t)k * LD;
-        load_col<KR, GLOBAL>(ck, j, u);
+        load_col<KR, GLOBAL, LG>(ck, j, u);
         float ss = 0.f;
 #pragma unroll
         for (int e = 0; e < R; ++e) ss = fmaf(u[e], u[e], ss);
-        ss = group_sum8(ss, gmask);
+        ss = group_sum<LG>(ss, gmask);
         const float inv_norm = 1.0f / sqrtf(ss);
 #pragma unroll
         for (int e = 0; e < R; ++e) u[e] *= inv_norm;
-        store_col<KR, GLOBAL>(ck, j, u);
+        store_col<KR, GLOBAL, LG>(ck, j, u);
     }
     __syncthreads();
 
@@ -341,28 +358,27 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
                 const float* Ar = Ug + (size_t)mm * n;
 #pragma unroll
                 for (int kk = 0; kk < KR; ++kk) {
-                    const int i0 = 4 * j + 32 * kk;
-                    float4 av;
-                    if (vec_ok && i0 + 3 < n) av = *reinterpret_cast<const float4*>(Ar + i0);
-                    else {
-                        av.x = (i0 + 0 < n) ? Ar[i0 + 0] : 0.f;
-                        av.y = (i0 + 1 < n) ? Ar[i0 + 1] : 0.f;
-                        av.z = (i0 + 2 < n) ? Ar[i0 + 2] : 0.f;
-                        av.w = (i0 + 3 < n) ? Ar[i0 + 3] : 0.f;
+                    const int i0 = VEC * j + 32 * kk;
+                    float av[VEC];
+                    if (vec_ok && i0 + VEC - 1 < n) {
+                        if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(Ar + i0); av[0] = t.x; av[1] = t.y; av[VEC - 2] = t.z; av[VEC - 1] = t.w; }
+                        else { const float2 t = *reinterpret_cast<const float2*>(Ar + i0); av[0] = t.x; av[1] = t.y; }
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < VEC; ++t) av[t] = (i0 + t < n) ? Ar[i0 + t] : 0.f;
                     }
-                    h[4 * kk + 0] = fmaf(av.x, u, h[4 * kk + 0]);
-                    h[4 * kk + 1] = fmaf(av.y, u, h[4 * kk + 1]);
-                    h[4 * kk + 2] = fmaf(av.z, u, h[4 * kk + 2]);
-                    h[4 * kk + 3] = fmaf(av.w, u, h[4 * kk + 3]);
+#pragma unroll
+                    for (int t = 0; t < VEC; ++t) h[VEC * kk + t] = fmaf(av[t], u, h[VEC * kk + t]);
                 }
             }
-            store_col<KR, false>(H + (size_t)k * LD, j, h);
+            store_col<KR, false, LG>(H + (size_t)k * LD, j, h);
         }
         __syncthreads();
         // ---- phase 2b: implicit two-sided Jacobi on T = U^T H (pivots are dot products of a
         //      U column with an H column; the rotation is applied to the columns of both).
         const float theta_tol = 2e-6f, noise = 3e-8f;
         for (int psweep = 0; psweep < 6; ++psweep) {
+            ++polish_sweeps;
             int rotated = 0;
             for (int r = 0; r < m; ++r) {
                 if (wave && g < npairs) {
@@ -374,17 +390,17 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
                     rr_pair(slot, r, m, n_pad, p, q);
                     if (p < n && q < n) {
                         float up[R], uq[R], hx[R];
-                        load_col<KR, false>(G + (size_t)p * LD, j, up);
-                        load_col<KR, false>(G + (size_t)q * LD, j, uq);
-                        load_col<KR, false>(H + (size_t)p * LD, j, hx);            // h_p
+                        load_col<KR, false, LG>(G + (size_t)p * LD, j, up);
+                        load_col<KR, false, LG>(G + (size_t)q * LD, j, uq);
+                        load_col<KR, false, LG>(H + (size_t)p * LD, j, hx);            // h_p
                         float tpp = 0.f, tqp = 0.f, tqq = 0.f, tpq = 0.f;
 #pragma unroll
                         for (int e = 0; e < R; ++e) { tpp = fmaf(up[e], hx[e], tpp); tqp = fmaf(uq[e], hx[e], tqp); }
-                        load_col<KR, false>(H + (size_t)q * LD, j, hx);            // h_q
+                        load_col<KR, false, LG>(H + (size_t)q * LD, j, hx);            // h_q
 #pragma unroll
                         for (int e = 0; e < R; ++e) { tqq = fmaf(uq[e], hx[e], tqq); tpq = fmaf(up[e], hx[e], tpq); }
-                        tpp = group_sum8(tpp, gmask); tqq = group_sum8(tqq, gmask);
-                        const float off = 0.5f * group_sum8(tpq + tqp, gmask);
+                        tpp = group_sum<LG>(tpp, gmask); tqq = group_sum<LG>(tqq, gmask);
+                        const float off = 0.5f * group_sum<LG>(tpq + tqp, gmask);
                         const float thr = fmaxf(theta_tol * fabsf(tqq - tpp), noise * (fabsf(tpp) + fabsf(tqq)));
                         if (fabsf(off) > thr) {
                             float c, s, t;
@@ -395,17 +411,17 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
                                 up[e] = c * x - s * y;
                                 uq[e] = s * x + c * y;
                             }
-                            store_col<KR, false>(G + (size_t)p * LD, j, up);
-                            store_col<KR, false>(G + (size_t)q * LD, j, uq);
-                            load_col<KR, false>(H + (size_t)p * LD, j, up);        // reuse registers: h_p
+                            store_col<KR, false, LG>(G + (size_t)p * LD, j, up);
+                            store_col<KR, false, LG>(G + (size_t)q * LD, j, uq);
+                            load_col<KR, false, LG>(H + (size_t)p * LD, j, up);        // reuse registers: h_p
 #pragma unroll
                             for (int e = 0; e < R; ++e) {
                                 const float x = up[e], y = hx[e];
                                 up[e] = c * x - s * y;
                                 hx[e] = s * x + c * y;
                             }
-                            store_col<KR, false>(H + (size_t)p * LD, j, up);
-                            store_col<KR, false>(H + (size_t)q * LD, j, hx);
+                            store_col<KR, false, LG>(H + (size_t)p * LD, j, up);
+                            store_col<KR, false, LG>(H + (size_t)q * LD, j, hx);
                             rotated = 1;
                         }
                     }
@@ -425,23 +441,23 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
     for (int k = g; k < n; k += ngroups) {
         float u[R];
         float* ck = G + (size_t)k * LD;
-        load_col<KR, GLOBAL>(ck, j, u);
+        load_col<KR, GLOBAL, LG>(ck, j, u);
         float ss = 0.f;
 #pragma unroll
         for (int e = 0; e < R; ++e) ss = fmaf(u[e], u[e], ss);
-        ss = group_sum8(ss, gmask);
+        ss = group_sum<LG>(ss, gmask);
         const float inv_norm = 1.0f / sqrtf(ss);
         float best = -1.f; int best_i = 0; float best_v = 0.f;
 #pragma unroll
         for (int e = 0; e < R; ++e) {
             u[e] *= inv_norm;
-            const int row = 4 * j + 32 * (e >> 2) + (e & 3);
+            const int row = VEC * j + 32 * (e / VEC) + (e % VEC);
             const float mag = fabsf(u[e]);
             if (row < n && mag > best) { best = mag; best_i = row; best_v = u[e]; }
         }
-        store_col<KR, GLOBAL>(ck, j, u);
+        store_col<KR, GLOBAL, LG>(ck, j, u);
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
+        for (int o = LG / 2; o > 0; o >>= 1) {
             const float ob = __shfl_xor_sync(gmask, best, o);
             const int oi = __shfl_xor_sync(gmask, best_i, o);
             const float ov = __shfl_xor_sync(gmask, best_v, o);
@@ -451,7 +467,7 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
         float acc = 0.f;
         if (POLISH) {
             float hk[R];
-            load_col<KR, false>(H + (size_t)k * LD, j, hk);
+            load_col<KR, false, LG>(H + (size_t)k * LD, j, hk);
 #pragma unroll
             for (int e = 0; e < R; ++e) acc = fmaf(u[e], hk[e], acc);       // u normalised, h = A u_old
             acc *= inv_norm;                                                 // -> u^T A u
@@ -464,26 +480,19 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
                 float part = 0.f;
 #pragma unroll
                 for (int kk = 0; kk < KR; ++kk) {
-                    const int m0 = 4 * j + 32 * kk;
-                    if (m0 + 3 < i) continue;
-                    float4 av;
-                    av.x = (m0 + 0 < n) ? __ldg(Ar + m0 + 0) : 0.f;
-                    av.y = (m0 + 1 < n) ? __ldg(Ar + m0 + 1) : 0.f;
-                    av.z = (m0 + 2 < n) ? __ldg(Ar + m0 + 2) : 0.f;
-                    av.w = (m0 + 3 < n) ? __ldg(Ar + m0 + 3) : 0.f;
-                    const float f0 = (m0 + 0 > i) ? 2.f : ((m0 + 0 == i) ? 1.f : 0.f);
-                    const float f1 = (m0 + 1 > i) ? 2.f : ((m0 + 1 == i) ? 1.f : 0.f);
-                    const float f2 = (m0 + 2 > i) ? 2.f : ((m0 + 2 == i) ? 1.f : 0.f);
-                    const float f3 = (m0 + 3 > i) ? 2.f : ((m0 + 3 == i) ? 1.f : 0.f);
-                    part = fmaf(av.x * f0, u[4 * kk + 0], part);
-                    part = fmaf(av.y * f1, u[4 * kk + 1], part);
-                    part = fmaf(av.z * f2, u[4 * kk + 2], part);
-                    part = fmaf(av.w * f3, u[4 * kk + 3], part);
+                    const int m0 = VEC * j + 32 * kk;
+                    if (m0 + VEC - 1 < i) continue;
+#pragma unroll
+                    for (int t = 0; t < VEC; ++t) {
+                        const float av = (m0 + t < n) ? __ldg(Ar + m0 + t) : 0.f;
+                        const float f = (m0 + t > i) ? 2.f : ((m0 + t == i) ? 1.f : 0.f);
+                        part = fmaf(av * f, u[VEC * kk + t], part);
+                    }
                 }
                 acc = fmaf(ui, part, acc);
             }
         }
-        acc = group_sum8(acc, gmask);
+        acc = group_sum<LG>(acc, gmask);
         if (j == 0) lam[k] = acc;
     }
     __syncthreads();
@@ -505,30 +514,30 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
         const int k = inv[c];
         Ug[e] = load_1<GLOBAL>(G + (size_t)k * LD + i) * sgn[k];
     }
-    if (tid == 0) info[blockIdx.x] = converged ? sweeps : -2;
+    if (tid == 0) info[blockIdx.x] = converged ? (sweeps | (polish_sweeps << 8)) : -2;
 }
 
 int g_eigh_block2 = 0;          // gsr_set_tuning("eigh_block2", 0|1): measured slower on B200 (19.0 vs 17.6 ms / 1024 graphs)
-int g_eigh_wave = 1;            // gsr_set_tuning("eigh_wave", 0|1): neighbour flags instead of a CTA barrier per round
+int g_eigh_wave = 0;            // gsr_set_tuning("eigh_wave", 0|1): neighbour flags instead of a CTA barrier per round; measured slower (21.5 vs 17.6 ms)
 
-static int eigh_threads(int n, bool block2) {
+static int eigh_threads(int n, bool block2, int lg) {
     const int npairs = ((n + 1) & ~1) / 2;
     if (block2) {                                                 // one slot per pair of 2-column blocks
         const int nslots = ((npairs + 1) & ~1) / 2;
-        return 32 * ((nslots * kGroup + 31) / 32);
+        return 32 * ((nslots * lg + 31) / 32);
     }
-    const int iters = (npairs * kGroup + 1023) / 1024;            // pair slots per group per round
+    const int iters = (npairs * lg + 1023) / 1024;                // pair slots per group per round
     const int groups = (npairs + iters - 1) / iters;
-    return 32 * ((groups * kGroup + 31) / 32);
+    return 32 * ((groups * lg + 31) / 32);
 }
 
-template <int KR, bool POLISH, bool GLOBAL, bool BLOCK2, int MAXT>
+template <int KR, bool POLISH, bool GLOBAL, bool BLOCK2, int MAXT, int LG = 8>
 static int launch_one(const float* A, float* w, float* U, int32_t* info, float* ws, int batch, int n,
                       int canonical, float tol, int max_sweeps, size_t smem, cudaStream_t st) {
-    auto k = eigh_jacobi_kernel<KR, POLISH, GLOBAL, BLOCK2, MAXT>;
+    auto k = eigh_jacobi_kernel<KR, POLISH, GLOBAL, BLOCK2, MAXT, LG>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "eigh_jacobi: cudaFuncSetAttribute failed");
-    const int threads = eigh_threads(n, BLOCK2);
+    const int threads = eigh_threads(n, BLOCK2, LG);
     if (threads > MAXT) return fail(GSR_E_UNSUPPORTED, "eigh_jacobi: internal thread-count mismatch");
     k<<<batch, threads, smem, st>>>(A, w, U, info, ws, n, canonical, tol, max_sweeps, g_eigh_wave);
     return launched("eigh_jacobi");
@@ -544,6 +553,7 @@ static int launch_eigh(const float* A, float* w, float* U, int32_t* info, float*
     const size_t one = (size_t)n * LD * sizeof(float) + small, two = 2 * (size_t)n * LD * sizeof(float) + small;
     const size_t cap = 227 * 1024;
     if (two <= cap) {
+        if (g_eigh_block2 == 2) return launch_one<KR, true, false, true, MAXT, 16>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, two, st);
         if (g_eigh_block2) return launch_one<KR, true, false, true, MAXT_B2>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, two, st);
         return launch_one<KR, true, false, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, two, st);
     }

@@ -41,6 +41,8 @@ class KernelTimer:
 
 
 GEMM_TIMER = None
+EIGH_TIMER = None      # same, around gsr_eigh_jacobi_f32 (work = number of graphs)
+EW_TIMER = None        # same, around the memory-bound n x n kernels (work = algorithmic bytes)
 
 # "tc" (default): tcgen05 3xTF32 (gsr_tcgemm_f32) wherever the operands meet its alignment
 # contract and the product is large enough to fill a 128-row tile, the SIMT FP32 kernel
@@ -94,9 +96,13 @@ def normalize_adj_fwd(mx: torch.Tensor, pre: bool = False, want_m: bool = False)
     out = torch.empty_like(mx)
     r = torch.empty(mx.shape[:-1], device=mx.device, dtype=torch.float32)
     m = torch.empty_like(mx) if want_m else None
+    timer = EW_TIMER
+    e0 = timer.start() if timer is not None else None
     check(lib().gsr_normalize_adj_fwd(mx.data_ptr(), out.data_ptr(), r.data_ptr(),
                                       m.data_ptr() if want_m else None, batch, n, int(pre), _stream()),
           "gsr_normalize_adj_fwd")
+    if timer is not None:
+        timer.stop(e0, 8.0 * batch * n * n)
     return out, r, m
 
 
@@ -104,8 +110,12 @@ def normalize_adj_bwd(mx: torch.Tensor, r: torch.Tensor, grad_out: torch.Tensor,
     mx, r, grad_out = _f32(mx, "mx"), _f32(r, "r"), _f32(grad_out, "grad_out")
     batch, n = _square_batch(mx, "normalize_adj_bwd: mx")
     grad = torch.empty_like(mx)
+    timer = EW_TIMER
+    e0 = timer.start() if timer is not None else None
     check(lib().gsr_normalize_adj_bwd(mx.data_ptr(), r.data_ptr(), grad_out.data_ptr(), grad.data_ptr(),
                                       batch, n, int(pre), _stream()), "gsr_normalize_adj_bwd")
+    if timer is not None:
+        timer.stop(e0, 12.0 * batch * n * n)
     return grad
 
 
@@ -119,10 +129,15 @@ def eigh_jacobi(A: torch.Tensor, canonical_sign: bool = True, tol: float = 0.0, 
     info = torch.empty((batch,), device=A.device, dtype=torch.int32)
     ws_floats = lib().gsr_eigh_workspace(batch, n)
     ws = torch.empty((ws_floats,), device=A.device, dtype=torch.float32) if ws_floats else None
+    timer = EIGH_TIMER
+    e0 = timer.start() if timer is not None else None
     check(lib().gsr_eigh_jacobi_f32(A.data_ptr(), w.data_ptr(), U.data_ptr(), info.data_ptr(),
                                     ws.data_ptr() if ws is not None else None, batch, n,
                                     int(canonical_sign), float(tol), int(max_sweeps), _stream()),
           "gsr_eigh_jacobi_f32")
+    if timer is not None:
+        timer.stop(e0, float(batch))
+        timer.last_info = info
     return w, U, info
 
 
@@ -229,7 +244,11 @@ def sym_diag_abs_fwd(x: torch.Tensor) -> torch.Tensor:
     x = _f32(x, "sym_diag_abs: x")
     batch, n = _square_batch(x, "sym_diag_abs: x")
     out = torch.empty_like(x)
+    timer = EW_TIMER
+    e0 = timer.start() if timer is not None else None
     check(lib().gsr_sym_diag_abs_fwd(x.data_ptr(), out.data_ptr(), batch, n, _stream()), "gsr_sym_diag_abs_fwd")
+    if timer is not None:
+        timer.stop(e0, 8.0 * batch * n * n)
     return out
 
 
@@ -237,8 +256,12 @@ def sym_diag_abs_bwd(x: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
     x, grad_out = _f32(x, "x"), _f32(grad_out, "grad_out")
     batch, n = _square_batch(x, "sym_diag_abs_bwd: x")
     grad = torch.empty_like(x)
+    timer = EW_TIMER
+    e0 = timer.start() if timer is not None else None
     check(lib().gsr_sym_diag_abs_bwd(x.data_ptr(), grad_out.data_ptr(), grad.data_ptr(), batch, n, _stream()),
           "gsr_sym_diag_abs_bwd")
+    if timer is not None:
+        timer.stop(e0, 12.0 * batch * n * n)
     return grad
 
 

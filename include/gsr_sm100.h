@@ -74,7 +74,8 @@ GSR_API int gsr_normalize_adj_bwd(const float* mx, const float* r, const float* 
  * A is read.  Eigenvalues ascending in w[batch,n]; eigenvector k in COLUMN k of
  * U[batch,n,n].  canonical_sign != 0 applies the documented sign rule: the
  * component of largest magnitude (lowest row on ties) of every eigenvector is
- * positive.  info[batch]: > 0 = sweeps used; -1 = non-finite input (outputs are
+ * positive.  info[batch]: > 0 = sweeps used (bits 0-7: one-sided sweeps, bits 8-15: polish
+ * sweeps); -1 = non-finite input (outputs are
  * NaN); -2 = not converged after max_sweeps (torch raises LinAlgError in both
  * cases; the Python wrapper does the same).  tol <= 0 / max_sweeps <= 0 select
  * the defaults (1e-6, 30).                                                       */
