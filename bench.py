@@ -332,9 +332,10 @@ def run_ours(args):
         sw = (eigh_info & 0xFF).double().sum().item()
         ps = (eigh_info >> 8).double().sum().item()
         n = LR_DIM
-        # every one-sided round reads and writes all n columns once; a polish round reads 2n columns
-        # (U and A.U) and writes the rotated ones (counted as read only: the algorithmic minimum)
-        bytes_per_launch = (sw * (n - 1) * 2 * n * n * 4.0) + (ps * (n - 1) * 2 * n * n * 4.0)
+        # a one-sided sweep is n steps in which every slot loads one column and stores one (the other stays
+        # in registers): n * n * 4 B read + as much written per step; a polish round reads 2n columns (U and
+        # A.U) and writes back only what it rotates (counted as read only: the algorithmic minimum)
+        bytes_per_launch = (sw * n * 2 * n * n * 4.0 / 2.0) + (ps * (n - 1) * 2 * n * n * 4.0)
         launches_per_timer = max(eigh_launches, 1)
         gbs = bytes_per_launch / (eigh_ms / launches_per_timer * 1e-3) / 1e9
         smem_peak = 148 * 128 * sm_mhz * 1e6 / 1e9

@@ -33,8 +33,8 @@ constexpr int kThreads = 320;        // 289 compute threads, all 320 load
 //   1: BK =  8, two CTAs per SM (96 registers, a few spills, 20 warps / SM)
 //   2: BK =  8, one CTA per SM
 int g_gemm_variant = 0;
-extern int g_eigh_block2;
-extern int g_eigh_wave;
+extern int g_eigh_oddeven;
+extern int g_eigh_max_polish;
 
 struct GemmParams {
     const float* A; const float* B; float* C;
@@ -298,8 +298,8 @@ extern "C" int gsr_bgemm_f32(const float* A, const float* B, float* C,
 extern "C" int gsr_set_tuning(const char* key, int value) {
     if (!key) return fail(GSR_E_ARG, "set_tuning: null key");
     if (!strcmp(key, "gemm_variant")) { gsr::g_gemm_variant = value; return 0; }
-    if (!strcmp(key, "eigh_block2")) { gsr::g_eigh_block2 = value; return 0; }
-    if (!strcmp(key, "eigh_wave")) { gsr::g_eigh_wave = value; return 0; }
+    if (!strcmp(key, "eigh_oddeven")) { gsr::g_eigh_oddeven = value; return 0; }
+    if (!strcmp(key, "eigh_max_polish")) { gsr::g_eigh_max_polish = value; return 0; }
     return fail(GSR_E_ARG, "set_tuning: unknown key");
 }
 

@@ -13,10 +13,18 @@
 //     column pair, 4*KR (2*KR) rows each, read and written as conflict-free float4s (float2s);
 //     the pivot dot product is reduced with 3 xor-shuffles; squared column norms
 //     are cached (exact once per sweep, updated as aa -= t*ab, bb += t*ab).
-//   * pairs follow the round-robin ("circle") tournament, computed analytically
-//     from the round number: n_pad/2 disjoint pairs rotate concurrently, n_pad-1
-//     rounds per sweep, one __syncthreads per round.  The kernel is bound by
-//     shared-memory bandwidth: every round reads and writes all n columns once.
+//   * pair ordering: odd-even transposition.  Columns sit at positions 0..n-1; even steps
+//     pair positions (2g, 2g+1), odd steps (2g+1, 2g+2), and the two columns swap positions
+//     after every rotation, so n_pad steps bring every pair together exactly once.  Slot g
+//     keeps the column at position 2g+1 in REGISTERS for the whole sweep and exchanges only
+//     the other one through shared memory: half the LDS / STS instructions and bytes of the
+//     round-robin ("circle") ordering at the same occupancy -- the kernel is bound by the
+//     LSU / shared-memory pipe (ncu: mio_throttle + short_scoreboard, data pipe 66 % busy),
+//     and this took 1024 graphs from 19.6 to 14.6 ms.  (Tried and measured slower on B200:
+//     2-column block rotations with 8 or 16 lanes per slot, and neighbour-flag wavefront
+//     synchronisation instead of the per-step barrier.)  The polish phase and the
+//     global-workspace variant use the round-robin ordering, n_pad-1 rounds per sweep,
+//     computed analytically from the round number.
 //   * polish (when a second n x LD buffer fits in shared memory, n <= ~170): the
 //     shift puts sigma-sized entries on the diagonal of G, so ~1500 fp32 rotations
 //     per column leave eigenvector errors of O(eps*sigma*sqrt(1500)/gap) ~ 2e-3 in
@@ -138,16 +146,14 @@ __device__ __forceinline__ bool rotate_regs(float (&x)[R], float (&y)[R], float&
 // KR     : rows per lane / 4 (column pitch LD = 32 KR + 4 floats)
 // POLISH : second phase (needs a second n x LD buffer in shared memory)
 // GLOBAL : working matrix in the global workspace instead of shared memory
-// BLOCK2 : phase 1 walks BLOCKS of two adjacent columns: a slot holds four columns in registers
-//          and applies the four cross rotations before writing them back, so a sweep reads and
-//          writes the matrix ~n/2 times instead of n times (the kernel is bound by that traffic)
-template <int KR, bool POLISH, bool GLOBAL, bool BLOCK2, int MAXT, int LG>
+template <int KR, bool POLISH, bool GLOBAL, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* __restrict__ Uout,
                    int32_t* __restrict__ info, float* __restrict__ workspace,
-                   int n, int canonical, float tol, int max_sweeps, int g_wave_flag) {
+                   int n, int canonical, float tol, int max_sweeps, int use_oddeven, int max_polish) {
     static_assert(!(POLISH && GLOBAL), "the polish phase needs both buffers in shared memory");
     constexpr int LD = 32 * KR + 4;
+    constexpr int LG = kGroup;                                  // lanes per pair slot
     constexpr int VEC = 32 / LG;
     constexpr int R = VEC * KR;
     extern __shared__ __align__(16) float smem[];
@@ -159,7 +165,6 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
     float* sgn = lam + n;                                       // [n]
     float* nrm = sgn + n;                                       // [n]  cached squared column norms
     int* inv = reinterpret_cast<int*>(nrm + n);                 // [n]
-    __shared__ int s_prog[512];                                 // rounds completed per pair slot (wavefront mode)
     __shared__ float s_red[32];
     __shared__ float s_sigma;
 
@@ -169,17 +174,8 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
     const int ngroups = nthr / LG;
     const unsigned gmask = (LG == 8) ? (0xFFu << (lane & 24)) : (0xFFFFu << (lane & 16));   // the lanes of this slot
     const int n_pad = (n + 1) & ~1, npairs = n_pad >> 1, m = n_pad - 1;
-    // Wavefront mode (one pair slot per 8-lane group, working matrix in shared memory): a slot's
-    // columns at round r+1 were held by slots i-1 and i+1 at round r (the round-robin passes
-    // every column to a neighbouring slot), so instead of a CTA barrier per round each slot
-    // publishes the number of rounds it has completed and waits only for its two neighbours.
-    // Loads, arithmetic and stores of different warps then overlap instead of moving in phases.
-    const bool wave = !GLOBAL && !BLOCK2 && ngroups >= npairs && npairs <= 512 && g_wave_flag != 0;
-    volatile int* prog = s_prog;
-    const int dep_lo = g > 0 ? g - 1 : (npairs > 1 ? 1 : 0);
-    const int dep_hi = g + 1 < npairs ? g + 1 : (npairs > 1 ? g - 1 : 0);
-    int t_done = 0;                                               // rounds completed by every slot so far
-    for (int i = tid; i < 512; i += nthr) s_prog[i] = 0;
+    // odd-even transposition ordering (default): needs one pair slot per lane group and shared memory
+    const bool oddeven = !GLOBAL && ngroups >= npairs && use_oddeven != 0;
     const float* A = Ain + (size_t)blockIdx.x * n * n;
     float* Wg = Wout + (size_t)blockIdx.x * n;
     float* Ug = Uout + (size_t)blockIdx.x * n * n;
@@ -247,59 +243,52 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
         __syncthreads();
         int rotated = 0;
         const float tol2 = tol * tol;
-        if (BLOCK2) {
-            const int nblk = n_pad >> 1, nblk_pad = (nblk + 1) & ~1, mb = nblk_pad - 1, nslots = nblk_pad >> 1;
-            // (a) the pair inside every block, once per sweep
-            for (int blk = g; blk < nblk; blk += ngroups) {
-                const int p = 2 * blk, q = p + 1;
-                if (q < n) {
-                    float a[R], b[R];
-                    load_col<KR, GLOBAL, LG>(G + (size_t)p * LD, j, a);
-                    load_col<KR, GLOBAL, LG>(G + (size_t)q * LD, j, b);
-                    float na = nrm[p], nb = nrm[q];
-                    if (rotate_regs<R, LG>(a, b, na, nb, tol2, gmask)) {
-                        store_col<KR, GLOBAL, LG>(G + (size_t)p * LD, j, a);
-                        store_col<KR, GLOBAL, LG>(G + (size_t)q * LD, j, b);
-                        if (j == 0) { nrm[p] = na; nrm[q] = nb; }
-                        rotated = 1;
-                    }
-                }
-            }
+        if (oddeven) {
+            // Odd-even transposition ordering: columns sit at POSITIONS 0..n-1; even steps pair
+            // positions (2g, 2g+1), odd steps (2g+1, 2g+2); after every rotation the two columns
+            // swap positions, so in n_pad steps every pair of columns meets exactly once.  Slot g
+            // keeps the column at position 2g+1 in REGISTERS for the whole sweep and exchanges
+            // only the other one through shared memory: it loads position 2g (even step) or 2g+2
+            // (odd step), rotates, stores its previously kept column to that same position and
+            // keeps the freshly loaded one.  Half the shared-memory traffic and half the LDS / STS
+            // instructions of the round-robin formulation at the same number of resident warps.
+            const int pk = 2 * g + 1;                                    // position of the kept column
+            const bool have = g < npairs && pk < n;
+            float ka[R], kb[R];                                            // the kept column alternates between the two
+            float nka = 1.f, nkb = 1.f;
+            if (have) { load_col<KR, GLOBAL, LG>(G + (size_t)pk * LD, j, ka); nka = nrm[pk]; }
             __syncthreads();
-            // (b) the four cross pairs of every pair of blocks, round-robin over the blocks
-            for (int r = 0; r < mb; ++r) {
-                for (int slot = g; slot < nslots; slot += ngroups) {
-                    int P, Q;
-                    rr_pair(slot, r, mb, nblk_pad, P, Q);
-                    if (P < nblk && Q < nblk) {
-                        const int p0 = 2 * P, p1 = p0 + 1, q0 = 2 * Q, q1 = q0 + 1;
-                        const bool vp1 = p1 < n, vq1 = q1 < n;                  // only an odd n has a phantom column
-                        float a0[R], a1[R], b0[R], b1[R];
-                        load_col<KR, GLOBAL, LG>(G + (size_t)p0 * LD, j, a0);
-                        load_col<KR, GLOBAL, LG>(G + (size_t)q0 * LD, j, b0);
-                        load_col<KR, GLOBAL, LG>(G + (size_t)(vp1 ? p1 : p0) * LD, j, a1);
-                        load_col<KR, GLOBAL, LG>(G + (size_t)(vq1 ? q1 : q0) * LD, j, b1);
-                        float na0 = nrm[p0], nb0 = nrm[q0], na1 = vp1 ? nrm[p1] : 1.f, nb1 = vq1 ? nrm[q1] : 1.f;
-                        bool ra0 = false, ra1 = false, rb0 = false, rb1 = false;
-                        if (rotate_regs<R, LG>(a0, b0, na0, nb0, tol2, gmask)) { ra0 = rb0 = true; }
-                        if (vp1 && vq1 && rotate_regs<R, LG>(a1, b1, na1, nb1, tol2, gmask)) { ra1 = rb1 = true; }
-                        if (vq1 && rotate_regs<R, LG>(a0, b1, na0, nb1, tol2, gmask)) { ra0 = rb1 = true; }
-                        if (vp1 && rotate_regs<R, LG>(a1, b0, na1, nb0, tol2, gmask)) { ra1 = rb0 = true; }
-                        if (ra0) { store_col<KR, GLOBAL, LG>(G + (size_t)p0 * LD, j, a0); if (j == 0) nrm[p0] = na0; }
-                        if (ra1) { store_col<KR, GLOBAL, LG>(G + (size_t)p1 * LD, j, a1); if (j == 0) nrm[p1] = na1; }
-                        if (rb0) { store_col<KR, GLOBAL, LG>(G + (size_t)q0 * LD, j, b0); if (j == 0) nrm[q0] = nb0; }
-                        if (rb1) { store_col<KR, GLOBAL, LG>(G + (size_t)q1 * LD, j, b1); if (j == 0) nrm[q1] = nb1; }
-                        if (ra0 | ra1 | rb0 | rb1) rotated = 1;
-                    }
+            for (int stp = 0; stp < n_pad; stp += 2) {
+                // even step: exchange position 2g, kept column in ka -> afterwards kept in kb
+                if (have) {
+                    float* cx = G + (size_t)(2 * g) * LD;
+                    load_col<KR, GLOBAL, LG>(cx, j, kb);
+                    nkb = nrm[2 * g];
+                    if (rotate_regs<R, LG>(kb, ka, nkb, nka, tol2, gmask)) rotated = 1;
+                    store_col<KR, GLOBAL, LG>(cx, j, ka);
+                    if (j == 0) nrm[2 * g] = nka;
+                }
+                __syncthreads();
+                // odd step: exchange position 2g+2, kept column in kb -> afterwards kept in ka
+                const bool odd_ok = have && (2 * g + 2 < n);
+                if (odd_ok) {
+                    float* cx = G + (size_t)(2 * g + 2) * LD;
+                    load_col<KR, GLOBAL, LG>(cx, j, ka);
+                    nka = nrm[2 * g + 2];
+                    if (rotate_regs<R, LG>(kb, ka, nkb, nka, tol2, gmask)) rotated = 1;
+                    store_col<KR, GLOBAL, LG>(cx, j, kb);
+                    if (j == 0) nrm[2 * g + 2] = nkb;
+                } else if (have) {
+#pragma unroll
+                    for (int e = 0; e < R; ++e) ka[e] = kb[e];                // idle end slot: the kept column just stays
+                    nka = nkb;
                 }
                 __syncthreads();
             }
+            if (have) { store_col<KR, GLOBAL, LG>(G + (size_t)pk * LD, j, ka); if (j == 0) nrm[pk] = nka; }
+            __syncthreads();
         } else {
         for (int r = 0; r < m; ++r) {
-            if (wave && g < npairs) {
-                for (unsigned spin = 0; min(prog[dep_lo], prog[dep_hi]) < t_done; ++spin) if (spin > (1u << 24)) __trap();
-                __threadfence_block();
-            }
             for (int slot = g; slot < npairs; slot += ngroups) {
                 int p, q;
                 rr_pair(slot, r, m, n_pad, p, q);
@@ -316,12 +305,7 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
                     }
                 }
             }
-            ++t_done;
-            if (wave) {
-                if (g < npairs) { __threadfence_block(); __syncwarp(gmask); if (j == 0) prog[g] = t_done; }
-            } else {
-                __syncthreads();
-            }
+            __syncthreads();
         }
         }
         ++sweeps;
@@ -377,14 +361,10 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
         // ---- phase 2b: implicit two-sided Jacobi on T = U^T H (pivots are dot products of a
         //      U column with an H column; the rotation is applied to the columns of both).
         const float theta_tol = 2e-6f, noise = 3e-8f;
-        for (int psweep = 0; psweep < 6; ++psweep) {
+        for (int psweep = 0; psweep < max_polish; ++psweep) {
             ++polish_sweeps;
             int rotated = 0;
             for (int r = 0; r < m; ++r) {
-                if (wave && g < npairs) {
-                    for (unsigned spin = 0; min(prog[dep_lo], prog[dep_hi]) < t_done; ++spin) if (spin > (1u << 24)) __trap();
-                    __threadfence_block();
-                }
                 for (int slot = g; slot < npairs; slot += ngroups) {
                     int p, q;
                     rr_pair(slot, r, m, n_pad, p, q);
@@ -426,12 +406,7 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
                         }
                     }
                 }
-                ++t_done;
-                if (wave) {
-                    if (g < npairs) { __threadfence_block(); __syncwarp(gmask); if (j == 0) prog[g] = t_done; }
-                } else {
-                    __syncthreads();
-                }
+                __syncthreads();
             }
             if (__syncthreads_count(rotated) <= few_threads) break;
         }
@@ -517,29 +492,27 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
     if (tid == 0) info[blockIdx.x] = converged ? (sweeps | (polish_sweeps << 8)) : -2;
 }
 
-int g_eigh_block2 = 0;          // gsr_set_tuning("eigh_block2", 0|1): measured slower on B200 (19.0 vs 17.6 ms / 1024 graphs)
-int g_eigh_wave = 0;            // gsr_set_tuning("eigh_wave", 0|1): neighbour flags instead of a CTA barrier per round; measured slower (21.5 vs 17.6 ms)
+int g_eigh_max_polish = 1;      // gsr_set_tuning("eigh_max_polish", k): polish sweeps.  One is enough: it starts ~2e-3 from the
+                                // solution and Jacobi converges quadratically there (measured: a 2nd sweep rotates 6-19 of 12720
+                                // pairs and changes max |dU| vs float64 from 4.074e-4 to 4.084e-4, median 3.9e-5 both; costs 1.3 ms)
+int g_eigh_oddeven = 1;         // gsr_set_tuning("eigh_oddeven", 0|1): 0 = round-robin ordering (19.6 ms / 1024 graphs), 1 = odd-even (14.6 ms)
 
-static int eigh_threads(int n, bool block2, int lg) {
+static int eigh_threads(int n) {
     const int npairs = ((n + 1) & ~1) / 2;
-    if (block2) {                                                 // one slot per pair of 2-column blocks
-        const int nslots = ((npairs + 1) & ~1) / 2;
-        return 32 * ((nslots * lg + 31) / 32);
-    }
-    const int iters = (npairs * lg + 1023) / 1024;                // pair slots per group per round
+    const int iters = (npairs * kGroup + 1023) / 1024;            // pair slots per group per round
     const int groups = (npairs + iters - 1) / iters;
-    return 32 * ((groups * lg + 31) / 32);
+    return 32 * ((groups * kGroup + 31) / 32);
 }
 
-template <int KR, bool POLISH, bool GLOBAL, bool BLOCK2, int MAXT, int LG = 8>
+template <int KR, bool POLISH, bool GLOBAL, int MAXT>
 static int launch_one(const float* A, float* w, float* U, int32_t* info, float* ws, int batch, int n,
                       int canonical, float tol, int max_sweeps, size_t smem, cudaStream_t st) {
-    auto k = eigh_jacobi_kernel<KR, POLISH, GLOBAL, BLOCK2, MAXT, LG>;
+    auto k = eigh_jacobi_kernel<KR, POLISH, GLOBAL, MAXT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "eigh_jacobi: cudaFuncSetAttribute failed");
-    const int threads = eigh_threads(n, BLOCK2, LG);
+    const int threads = eigh_threads(n);
     if (threads > MAXT) return fail(GSR_E_UNSUPPORTED, "eigh_jacobi: internal thread-count mismatch");
-    k<<<batch, threads, smem, st>>>(A, w, U, info, ws, n, canonical, tol, max_sweeps, g_eigh_wave);
+    k<<<batch, threads, smem, st>>>(A, w, U, info, ws, n, canonical, tol, max_sweeps, g_eigh_oddeven, g_eigh_max_polish);
     return launched("eigh_jacobi");
 }
 
@@ -548,21 +521,13 @@ static int launch_eigh(const float* A, float* w, float* U, int32_t* info, float*
                        int canonical, float tol, int max_sweeps, cudaStream_t st) {
     constexpr int LD = 32 * KR + 4;
     constexpr int MAXT = (128 * KR < 1024) ? 128 * KR : (KR >= 9 ? 576 : 1024);
-    constexpr int MAXT_B2 = 64 * KR + 32;                        // block mode: a quarter as many slots as columns
     const size_t small = 4 * (size_t)n * sizeof(float);
     const size_t one = (size_t)n * LD * sizeof(float) + small, two = 2 * (size_t)n * LD * sizeof(float) + small;
     const size_t cap = 227 * 1024;
-    if (two <= cap) {
-        if (g_eigh_block2 == 2) return launch_one<KR, true, false, true, MAXT, 16>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, two, st);
-        if (g_eigh_block2) return launch_one<KR, true, false, true, MAXT_B2>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, two, st);
-        return launch_one<KR, true, false, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, two, st);
-    }
-    if (one <= cap) {
-        if (g_eigh_block2) return launch_one<KR, false, false, true, MAXT_B2>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, one, st);
-        return launch_one<KR, false, false, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, one, st);
-    }
+    if (two <= cap) return launch_one<KR, true, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, two, st);
+    if (one <= cap) return launch_one<KR, false, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, one, st);
     if (!ws) return fail(GSR_E_ARG, "eigh_jacobi: this n needs a global workspace (gsr_eigh_workspace)");
-    return launch_one<KR, false, true, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, small, st);
+    return launch_one<KR, false, true, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, small, st);
 }
 
 }  // namespace gsr
