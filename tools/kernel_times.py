@@ -59,18 +59,19 @@ def main():
            sweeps_mean=float((info & 0xFF).float().mean()), polish_mean=float((info >> 8).float().mean()))
     ms = timeit(lambda: torch.linalg.eigh(A, UPLO="U"), reps=1, warm=1)
     report("torch.linalg.eigh_160 (cuSOLVER, for context)", ms, us_per_graph=round(ms * 1e3 / B, 2))
-    for variant in (0, 1, 2):
-        pkg.set_tuning("gemm_variant", variant)
+    Wl = torch.randn(268, 160, device=dev, generator=g)
+    for backend in ("tc", "simt"):
+        K.set_gemm_backend(backend)
+        tag = "tcgemm (tcgen05 3xTF32)" if backend == "tc" else "bgemm (SIMT FP32)"
         f = 2 * 268 ** 3 * B
-        report(f"bgemm NN per-subject 268^3 v{variant}", timeit(lambda: K.bgemm(H, H2)), flops=f)
-        report(f"bgemm NT per-subject 268^3 v{variant}", timeit(lambda: K.bgemm(H, H2, transB=True)), flops=f)
-        report(f"bgemm TN per-subject 268^3 v{variant}", timeit(lambda: K.bgemm(H, H2, transA=True)), flops=f)
-        report(f"bgemm NN stacked shared-W 268^3 v{variant}", timeit(lambda: K.bgemm(H, W)), flops=f)
-        report(f"bgemm NT stacked shared-W 268^3 v{variant}", timeit(lambda: K.bgemm(H, W, transB=True)), flops=f)
-        report(f"bgemm_reduce TN 268^3 v{variant}", timeit(lambda: K.bgemm_reduce(H, H2, transA=True)), flops=f)
-        Wl = torch.randn(268, 160, device=dev, generator=g)
-        report(f"bgemm NT stacked U.W^T 160x268x160 v{variant}", timeit(lambda: K.bgemm(A, Wl, transB=True)), flops=2 * 160 * 268 * 160 * B)
-    pkg.set_tuning("gemm_variant", 0)
+        report(f"{tag} NN per-subject 268^3", timeit(lambda: K.bgemm(H, H2)), flops=f)
+        report(f"{tag} NT per-subject 268^3", timeit(lambda: K.bgemm(H, H2, transB=True)), flops=f)
+        report(f"{tag} TN per-subject 268^3", timeit(lambda: K.bgemm(H, H2, transA=True)), flops=f)
+        report(f"{tag} NN stacked shared-W 268^3", timeit(lambda: K.bgemm(H, W)), flops=f)
+        report(f"{tag} NT stacked shared-W 268^3", timeit(lambda: K.bgemm(H, W, transB=True)), flops=f)
+        report(f"{tag} reduce TN 268^3", timeit(lambda: K.bgemm_reduce(H, H2, transA=True)), flops=f)
+        report(f"{tag} NT stacked U.W^T 160x268x160", timeit(lambda: K.bgemm(A, Wl, transB=True)), flops=2 * 160 * 268 * 160 * B)
+    K.set_gemm_backend("tc")
     ms = timeit(lambda: torch.bmm(H, H2))
     report("torch.bmm 268^3 fp32 (cuBLAS, for context)", ms, flops=2 * 268 ** 3 * B)
     torch.backends.cuda.matmul.allow_tf32 = True
