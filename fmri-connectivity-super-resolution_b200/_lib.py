@@ -31,6 +31,8 @@ PROTOTYPES = {
     "gsr_normalize_adj_bwd": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, c_ptr]),
     "gsr_eigh_workspace": (C.c_size_t, [i32, i32]),
     "gsr_eigh_jacobi_f32": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, f32, i32, c_ptr]),
+    "gsr_eigh_tridiag_workspace": (C.c_size_t, [i32, i32]),
+    "gsr_eigh_tridiag_f32": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, i32, i32, i32, c_ptr]),
     "gsr_bgemm_f32": (i32, [c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, i32, i32, i64, i64, i64,
                             i32, i32, i32, f32, i32, c_ptr, i32, i64, c_ptr]),
     "gsr_bgemm_reduce_workspace": (C.c_size_t, [i32, i32, i32, C.POINTER(i32)]),

@@ -70,8 +70,19 @@ def eigh(A: torch.Tensor, UPLO: str = "U", check_errors: bool = True, canonical_
         raise NotImplementedError("eigh: only UPLO='U' is on the GSR-Net path")
     if A.requires_grad and torch.is_grad_enabled():
         raise NotImplementedError("eigh: gradients through the eigendecomposition are not on the GSR-Net path")
-    w, U, info = K.eigh_jacobi(A.detach(), canonical_sign=canonical_sign)
+    A = A.detach()
+    w, U, info = K.eigh(A, canonical_sign=canonical_sign)
     if check_errors:
+        worst = int(info.min().item())                  # torch.linalg.eigh's error contract costs one sync
+        if worst == -2 and K.EIGH_METHOD == "auto" and A.shape[-1] <= K.EIGH_TRIDIAG_MAX_N:
+            # the QL iteration gave up on some graphs (more than 2 n^2 rotations): those go through
+            # the Jacobi kernel, which always converges
+            bad = (info == -2).nonzero().flatten()
+            Ab = A.reshape(-1, A.shape[-2], A.shape[-1])[bad]
+            wb, Ub, ib = K.eigh_jacobi(Ab, canonical_sign=canonical_sign)
+            w.reshape(-1, A.shape[-1])[bad] = wb
+            U.reshape(-1, A.shape[-2], A.shape[-1])[bad] = Ub
+            info[bad] = ib
         raise_on_eigh_info(info)
     return w, U, info
 

@@ -138,7 +138,54 @@ def eigh_jacobi(A: torch.Tensor, canonical_sign: bool = True, tol: float = 0.0, 
     if timer is not None:
         timer.stop(e0, float(batch))
         timer.last_info = info
+        timer.last_method = "jacobi"
     return w, U, info
+
+
+EIGH_TRIDIAG_MAX_N = 160
+EIGH_METHOD = os.environ.get("GSR_EIGH_METHOD", "auto")     # "auto" | "jacobi" | "tridiag"
+
+
+def eigh_tridiag(A: torch.Tensor, canonical_sign: bool = True, _return_workspace: bool = False):
+    """Returns (w, U, info) -- see gsr_eigh_tridiag_f32 (n <= 160).  No synchronisation."""
+    A = _f32(A, "eigh: A")
+    batch, n = _square_batch(A, "eigh: A")
+    w = torch.empty(A.shape[:-1], device=A.device, dtype=torch.float32)
+    U = torch.empty_like(A)
+    info = torch.empty((batch,), device=A.device, dtype=torch.int32)
+    ws_bytes = lib().gsr_eigh_tridiag_workspace(batch, n)
+    if ws_bytes == 0 and batch > 0:
+        raise ValueError(f"eigh_tridiag: n = {n} is outside 1..{EIGH_TRIDIAG_MAX_N}")
+    ws = torch.empty((max(ws_bytes, 16),), device=A.device, dtype=torch.uint8)
+    timer = EIGH_TIMER
+    e0 = timer.start() if timer is not None else None
+    check(lib().gsr_eigh_tridiag_f32(A.data_ptr(), w.data_ptr(), U.data_ptr(), info.data_ptr(), ws.data_ptr(),
+                                     ws_bytes, batch, n, int(canonical_sign), _stream()),
+          "gsr_eigh_tridiag_f32")
+    if timer is not None:
+        timer.stop(e0, float(batch))
+        timer.last_info = info
+        timer.last_method = "tridiag"
+    if _return_workspace:
+        return w, U, info, ws
+    return w, U, info
+
+
+def eigh(A: torch.Tensor, canonical_sign: bool = True, method: Optional[str] = None):
+    """torch.linalg.eigh(A, 'U') on the device: the tridiagonal-QL kernels for n <= 160 (the in-step
+    LR decomposition), the Jacobi kernel above that (the hoisted 268-node HR target)."""
+    method = method or EIGH_METHOD
+    n = A.shape[-1]
+    if method == "tridiag" or (method == "auto" and n <= EIGH_TRIDIAG_MAX_N):
+        return eigh_tridiag(A, canonical_sign=canonical_sign)
+    return eigh_jacobi(A, canonical_sign=canonical_sign)
+
+
+def set_eigh_method(name: str) -> None:
+    global EIGH_METHOD
+    if name not in ("auto", "jacobi", "tridiag"):
+        raise ValueError("eigh method must be 'auto', 'jacobi' or 'tridiag'")
+    EIGH_METHOD = name
 
 
 # --------------------------------------------------------------------- GEMMs

@@ -1,0 +1,48 @@
+"""Accuracy + timing of both eigh paths (tridiagonal-QL, Jacobi) against a float64 decomposition."""
+import importlib, os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+pkg = importlib.import_module("fmri-connectivity-super-resolution_b200"); K = pkg.kernels
+from oracle import gsr_oracle as O
+
+def report(tag, A, w, U, info, ms=None):
+    Ad, Ud, wd = A.double(), U.double(), w.double()
+    n = A.shape[-1]
+    As = torch.triu(Ad) + torch.triu(Ad, 1).transpose(1, 2)
+    res = float((As @ Ud - Ud * wd[:, None, :]).abs().amax())
+    orth = float((Ud.transpose(1, 2) @ Ud - torch.eye(n, device=A.device, dtype=torch.float64)).abs().amax())
+    nb = min(A.shape[0], 32)
+    w64, U64 = torch.linalg.eigh(As[:nb].cpu()); U64 = O.canonicalize_signs(U64)
+    werr = float((w[:nb].cpu().double() - w64).abs().max())
+    errs = sorted(float((U[s].cpu().double() - U64[s]).abs().max()) for s in range(nb))
+    out = {"tag": tag, "n": n, "batch": A.shape[0], "info_min": int(info.min()), "info_max": int(info.max()), "info_mean": float(info.float().mean()),
+           "w_err": werr, "residual": res, "orth": orth, "U_err_max": errs[-1], "U_err_median": errs[len(errs) // 2]}
+    if ms is not None:
+        out["ms"] = round(ms, 3); out["us_per_graph"] = round(ms * 1e3 / A.shape[0], 2)
+    print(json.dumps(out), flush=True)
+
+def timed(fn, A, reps=3):
+    for _ in range(2): fn(A)
+    torch.cuda.synchronize(); best = 1e9
+    for _ in range(reps):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); r = fn(A); b.record(); torch.cuda.synchronize(); best = min(best, a.elapsed_time(b))
+    return r, best
+
+for n in (1, 2, 3, 5, 12, 31, 64, 100, 136, 159, 160):
+    A = torch.stack([O.normalize_adj(O.synth_connectome(n, 50 + s)) if n > 1 else torch.tensor([[0.7]]) for s in range(4)]).cuda()
+    w, U, info = K.eigh_tridiag(A)
+    report("tridiag", A, w, U, info)
+g = torch.Generator().manual_seed(0)
+M = torch.randn(4, 96, 96, generator=g); A = ((M + M.transpose(1, 2)) / 2).cuda()
+w, U, info = K.eigh_tridiag(A); report("tridiag randn96", A, w, U, info)
+A2 = A * 1e-12; w, U, info = K.eigh_tridiag(A2); print("scaled 1e-12: w ratio err", float((w * 1e12 - K.eigh_tridiag(A)[0]).abs().max()), int(info.min()))
+A3 = torch.zeros(2, 40, 40, device="cuda"); w, U, info = K.eigh_tridiag(A3); print("zeros:", float(w.abs().max()), float((U - torch.eye(40, device="cuda")).abs().max()), info.tolist())
+A4 = torch.eye(40, device="cuda")[None] * 3.0; w, U, info = K.eigh_tridiag(A4); print("3I:", float((w - 3).abs().max()), info.tolist())
+A5 = torch.ones(1, 64, 64, device="cuda"); w, U, info = K.eigh_tridiag(A5); report("ones64", A5, w, U, info)
+
+gen = torch.Generator(device="cuda").manual_seed(0)
+x = torch.rand(1024, 160, 160, device="cuda", generator=gen); lr = (x + x.transpose(1, 2)) / 2; lr.diagonal(dim1=1, dim2=2).zero_()
+A = pkg.normalize_adj_torch(lr)
+(w, U, info), ms = timed(K.eigh_tridiag, A); report("tridiag 1024x160", A, w, U, info, ms)
+(w, U, info), ms = timed(K.eigh_jacobi, A); report("jacobi 1024x160", A, w, U, info, ms)
