@@ -2,61 +2,62 @@
 // decomposition of the GSR layer, torch.linalg.eigh(A, UPLO='U') of models/layers.py:27.
 //
 // The one-sided Jacobi kernel (eigh.cu) executes ~18 n^3 flops per graph (8 sweeps + polish) and
-// is bound by the shared-memory pipe.  This path does the classical three-stage reduction in
-// ~(4/3 + 2/3 + 3) n^3 flops, every stage laid out for the SM:
+// every one of them moves its operands through shared memory: it is bound by the LSU /
+// shared-memory pipe.  This path does the classical three-stage reduction in ~6 n^3 flops and
+// keeps the MATRICES IN REGISTERS: one thread owns one row (160 fp32 registers of the 64 K per
+// SM; 160 threads per graph, two graphs per SM), shared memory only streams the operands that
+// are uniform over the warp (the Householder vector, the plane rotations), one broadcast
+// wavefront per four columns.
 //
-//   K1  tridiag_kernel     one CTA per graph, A resident in shared memory (pitch 164 floats:
-//                          eight consecutive rows x one float4 hit 32 distinct banks).  Thread
-//                          (row i, part p) owns the float4 chunks c = p (mod 4) of row i, so the
-//                          symmetric mat-vec p = tau A v and the rank-2 update A -= v w^T + w v^T
-//                          are row-local: no cross-thread reduction except two shuffles and one
-//                          20-term sum per step, two CTA barriers per Householder step.  The
-//                          reduction runs from the last column to the first (LAPACK's UPLO='U'
-//                          ssytd2), so the active block stays at the top-left, aligned.  The
-//                          reflectors are then accumulated into Q^T in place (row-local again)
-//                          and Q^T is written out: its rows are the columns of Q.
+//   K1  tridiag_kernel   Householder reduction, last column first (LAPACK ssytd2, UPLO='U':
+//                        the active block stays at the top-left).  Thread i holds row i of the
+//                        symmetric matrix, so p = tau A v and the rank-2 update
+//                        A -= v w^T + w v^T are thread-local: per step one published pivot row,
+//                        one 5-term sum and two CTA barriers.  Writes (d, e), the reflectors and
+//                        their taus.
 //   K2  tql_scalar_kernel  one warp per graph: the implicit-shift QL iteration (EISPACK tql2) on
-//                          (d, e) only.  It is a ~23 000-long dependent chain of plane rotations
-//                          per graph, so lane 0 runs the chain (rsqrt + one Newton step instead
-//                          of sqrt and two divisions) while all lanes share the shift
-//                          subtraction and the split search; every rotation (c, s) is appended
-//                          to a per-graph stream, every QL iteration (l, m) to a header list.
-//                          All graphs of the batch run concurrently, one chain per warp.
-//   K3  tql_apply_kernel   one CTA per graph, thread = row of Z (Z starts as Q, column-major in
-//                          shared memory = Q^T row-major, pitch 161: conflict free).  The rows of
-//                          Z are independent under column rotations, so each thread replays the
-//                          rotation stream on its own row with a running register value: one
-//                          LDS + one STS + 4 flops per rotation, the (c, s) pairs staged per warp
-//                          by cp.async in 64-rotation blocks, no CTA barrier.  Epilogue: rank by
-//                          counting, sign canonicalisation, coalesced store.
+//                        (d, e) only -- a ~23 000-long dependent chain of plane rotations per
+//                        graph, so lane 0 runs the chain (one MUFU.RSQ and a first-order norm
+//                        correction instead of sqrt and two divisions) while all lanes share the
+//                        shift subtraction and the split search.  Every rotation (c, s) goes to a
+//                        per-graph stream; every QL iteration is padded with identity rotations
+//                        to whole 16-column blocks and described by one header word.
+//   K3  tql_apply_kernel thread r holds row r of Z.  Z starts as Q = H_{n-1} ... H_1 (row r of
+//                        I times the reflectors: thread-local dot + axpy against the broadcast
+//                        reflector), then the rotation stream is replayed on the registers:
+//                        16 statically indexed rotation stanzas per block, (c, s) pairs staged
+//                        per warp by cp.async, no CTA barrier.  Epilogue through shared memory:
+//                        unit columns, rank by counting, sign canonicalisation, coalesced store.
 //
-// Accuracy (fp32, measured against a float64 decomposition on normalised 160-node connectomes):
-// eigenvalues <= 1e-6, eigenvectors 2e-5..4e-5, ||U^T U - I||_max 2e-6 -- the same class as LAPACK
-// ssyevd and as the Jacobi kernel after its polish phase.
+// Accuracy (fp32, measured on B200 against a float64 decomposition of normalised 160-node
+// connectomes): eigenvalues 1e-6, eigenvectors (median) 4e-5, ||U^T U - I||_max 2e-6 -- the
+// class of LAPACK ssyevd and of the Jacobi kernel after its polish phase.
 #include "common.cuh"
 
 namespace gsr {
 namespace tq {
 
 constexpr int MAXN = 160;
-constexpr int LDA = 164;                 // K1 row pitch (floats), = 4 (mod 32)
-constexpr int LDZ = 161;                 // K3 column pitch, odd
+constexpr int NB = MAXN / 16;            // 16-column blocks
+constexpr int LDV = 164;                 // pitch of a stored reflector row: v[0..159], tau at [160]
+constexpr int LDZ = 161;                 // K3 epilogue: column pitch in shared memory, odd
 constexpr int BLK = 64;                  // rotations per cp.async block
 constexpr int STAGES = 3;
-constexpr int K1_SMALL = 176 + 176 + 160 + 32 + 3 * 160;     // vbuf, wbuf, pbuf, red, taus, dd, ee (floats)
+
+
 
 struct Work {
-    float2* stream;      // [batch][cap]      rotations (c, s) in application order
-    float* Qt;           // [batch][n][n]     Q^T (row i = column i of Q)
+    float2* stream;      // [batch][cap]      rotations (c, s) in application order (padded)
+    float* V;            // [batch][n][LDV]   reflector k in row k (zeros from column k on), tau at [160]
     float* d;            // [batch][n]        diagonal of T, then the unsorted eigenvalues
     float* e;            // [batch][n]        off-diagonal of T (e[n-1] = 0)
     float* scale;        // [batch]           power-of-two input scaling
-    int* counts;         // [batch][4]        QL iterations, rotations, status, -
-    uint32_t* hdr;       // [batch][hdr_cap]  l | m << 16 of every QL iteration
+    int* counts;         // [batch][4]        QL iterations, stream entries, status, -
+    uint32_t* hdr;       // [batch][hdr_cap]  lo16 | hi16 << 8 of every QL iteration (16-column blocks)
     int cap, hdr_cap;
 };
 
-__host__ __device__ inline int stream_cap(int n) { return ((2 * n * n + BLK - 1) / BLK) * BLK + BLK; }
+__host__ __device__ inline int stream_cap(int n) { return ((2 * n * n + 512 + BLK - 1) / BLK) * BLK + BLK; }
 __host__ __device__ inline int header_cap(int n) { return 30 * n + 2; }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -66,7 +67,7 @@ static size_t carve(Work* wk, void* base, int batch, int n) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_stream = take((size_t)batch * cap * sizeof(float2));
-    const size_t o_qt = take((size_t)batch * n * n * sizeof(float));
+    const size_t o_v = take((size_t)batch * n * LDV * sizeof(float));
     const size_t o_d = take((size_t)batch * n * sizeof(float));
     const size_t o_e = take((size_t)batch * n * sizeof(float));
     const size_t o_sc = take((size_t)batch * sizeof(float));
@@ -75,7 +76,7 @@ static size_t carve(Work* wk, void* base, int batch, int n) {
     if (wk) {
         char* b = static_cast<char*>(base);
         wk->stream = reinterpret_cast<float2*>(b + o_stream);
-        wk->Qt = reinterpret_cast<float*>(b + o_qt);
+        wk->V = reinterpret_cast<float*>(b + o_v);
         wk->d = reinterpret_cast<float*>(b + o_d);
         wk->e = reinterpret_cast<float*>(b + o_e);
         wk->scale = reinterpret_cast<float*>(b + o_sc);
@@ -87,46 +88,37 @@ static size_t carve(Work* wk, void* base, int batch, int n) {
     return off;
 }
 
-__device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
-    acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
-    return acc;
-}
-
 // ------------------------------------------------------------------------------------ K1
-// Thread layout: warp w, lane = part * 8 + r8; row i = 8 w + r8; the thread owns chunks
-// c = part, part + 4, ... (4 columns each) of row i.
-__global__ void __launch_bounds__(640, 2)
+__global__ void __launch_bounds__(MAXN, 2)
 tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* __restrict__ Uout,
                int32_t* __restrict__ info, const Work wk, int n) {
-    extern __shared__ __align__(16) float sm[];
-    float* A = sm;                         // [n][LDA]
-    float* vbuf = A + (size_t)n * LDA;     // [176]
+    __shared__ __align__(16) float tile[5 * 176];            // xbuf[2][176], vbuf, wbuf, pbuf
+    __shared__ __align__(16) float red[8];
+    __shared__ float dd[MAXN], ee[MAXN];
+    float* xbuf = tile;                    // [2][176]  published pivot row (double buffered by step parity)
+    float* vbuf = tile + 2 * 176;          // [176]
     float* wbuf = vbuf + 176;              // [176]
-    float* pbuf = wbuf + 176;              // [160]
-    float* red = pbuf + 160;               // [32]
-    float* taus = red + 32;                // [160]
-    float* dd = taus + 160;                // [160]
-    float* ee = dd + 160;                  // [160]
+    float* pbuf = wbuf + 176;              // [176]
 
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nwarps = nthr >> 5;
-    const int r8 = lane & 7, part = lane >> 3, i = 8 * w + r8;
     const int g = blockIdx.x;
     const float* Ag = Ain + (size_t)g * n * n;
 
-    // ---- load: zero everything, mirror the upper triangle, detect non-finite input, |A|_max
-    for (int e = tid; e < n * LDA + K1_SMALL; e += nthr) sm[e] = 0.f;
-    __syncthreads();
+    // ---- load: thread i gets row i of the symmetric matrix = mirror of the upper triangle:
+    //      A[i][j] for j >= i (row segment), A[j][i] for j < i (coalesced over the warp)
+    float a[MAXN];
     int bad = 0;
     float amax = 0.f;
-    for (int e = tid; e < n * n; e += nthr) {
-        const int r = e / n, c = e - r * n;
-        if (c >= r) {
-            const float v = __ldg(Ag + e);
-            if (!isfinite(v)) bad = 1;
-            amax = fmaxf(amax, fabsf(v));
-            A[r * LDA + c] = v;
-            A[c * LDA + r] = v;
-        }
+#pragma unroll
+    for (int j = 0; j < MAXN; ++j) {
+        float v = 0.f;
+        if (tid < n && j < n) v = __ldg(Ag + (j >= tid ? (size_t)tid * n + j : (size_t)j * n + tid));
+        a[j] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < MAXN; ++j) {
+        if (!isfinite(a[j])) bad = 1;
+        amax = fmaxf(amax, fabsf(a[j]));
     }
     if (__syncthreads_or(bad)) {
         const float qnan = __int_as_float(0x7fc00000);
@@ -141,131 +133,137 @@ tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* _
     __syncthreads();
     amax = 0.f;
     for (int q = 0; q < nwarps; ++q) amax = fmaxf(amax, red[q]);
-    __syncthreads();
-    if (lane == 0) red[w] = 0.f;
     // exact power-of-two scaling into a range where the squares of the QL iteration are safe
     float sc = 1.0f;
     if (amax > 0.f && (amax < 9.5367431640625e-07f || amax > 1048576.0f)) sc = ldexpf(1.0f, -max(-120, min(120, ilogbf(amax))));
     if (sc != 1.0f) {
-        for (int e = tid; e < n * LDA; e += nthr) A[e] *= sc;
+#pragma unroll
+        for (int j = 0; j < MAXN; ++j) a[j] *= sc;
     }
     if (tid == 0) { wk.scale[g] = sc; wk.counts[4 * g + 2] = 0; }
     __syncthreads();
+    for (int e = tid; e < 5 * 176; e += nthr) tile[e] = 0.f;           // xbuf, vbuf, wbuf, pbuf
+    if (tid < 8) red[tid] = 0.f;
+    __syncthreads();
 
-    // ---- Householder reduction, last column first (active block = A[0:k, 0:k])
+    // publish a row (columns 0..cnt-1, whole 16-column blocks) into xbuf[parity]
+#define GSR_PUBLISH(parity, cnt)                                                                                   \
+    do {                                                                                                           \
+        float4* X4 = reinterpret_cast<float4*>(xbuf + (parity) * 176);                                             \
+        _Pragma("unroll") for (int cb = 0; cb < NB; ++cb) {                                                        \
+            if (16 * cb < (cnt)) {                                                                                 \
+                _Pragma("unroll") for (int c = 0; c < 4; ++c)                                                      \
+                    X4[4 * cb + c] = make_float4(a[16 * cb + 4 * c], a[16 * cb + 4 * c + 1], a[16 * cb + 4 * c + 2], a[16 * cb + 4 * c + 3]); \
+            }                                                                                                      \
+        }                                                                                                          \
+    } while (0)
+    float* Vg = wk.V + (size_t)g * n * LDV;
+    if (tid == n - 1) GSR_PUBLISH((n - 1) & 1, n);
+    __syncthreads();
+
+    // ---- Householder reduction, last column first (active block = rows / columns 0..k-1)
     for (int k = n - 1; k >= 1; --k) {
-        const float* xr = A + k * LDA;            // x = A[0:k, k] (by symmetry row k), final
+        const float* xr = xbuf + (k & 1) * 176;       // row k: columns 0..k
+        float xl[MAXN / 32];                           // x[lane + 32 t]
         float ss = 0.f;
-        for (int j = lane; j < k - 1; j += 32) { const float x = xr[j]; ss = fmaf(x, x, ss); }
-        ss = warp_sum(ss);                         // every warp computes the same bits
+#pragma unroll
+        for (int t = 0; t < MAXN / 32; ++t) {
+            xl[t] = xr[lane + 32 * t];                 // columns >= k of the buffer are stale: masked below
+            if (lane + 32 * t < k - 1) ss = fmaf(xl[t], xl[t], ss);
+        }
+        ss = warp_sum(ss);                             // every warp computes the same bits
         const float alpha = xr[k - 1];
-        if (ss == 0.f) {                           // H = I (slarfg)
-            if (tid == 0) { ee[k - 1] = alpha; dd[k] = xr[k]; taus[k] = 0.f; }
-            continue;
-        }
-        const float nrm = sqrtf(fmaf(alpha, alpha, ss));
-        const float beta = -copysignf(nrm, alpha);
-        const float tau = (beta - alpha) / beta;
-        const float scl = 1.0f / (alpha - beta);
-        const int kpad = (k + 15) & ~15;
-        // v (v[k-1] = 1) -- every warp writes the same values
-        for (int j = lane; j < kpad; j += 32) vbuf[j] = (j < k - 1) ? xr[j] * scl : (j == k - 1 ? 1.0f : 0.0f);
-        if (tid == 0) dd[k] = xr[k];
-        __syncwarp();
-        const int nch = (k + 3) >> 2;
-        const float4* V = reinterpret_cast<const float4*>(vbuf);
-        float4* Ar = reinterpret_cast<float4*>(A + i * LDA);
-        const bool act = i < k;
-        // p = tau A v, row-local
-        float q = 0.f;
-        if (act) {
-            for (int c = part; c < nch; c += 4) q = dot4(Ar[c], V[c], q);
-        }
-        q += __shfl_xor_sync(0xffffffffu, q, 8);
-        q += __shfl_xor_sync(0xffffffffu, q, 16);
-        const float pi = tau * q;
-        float pvp = (act && part == 0) ? pi * vbuf[i] : 0.f;
-        pvp += __shfl_xor_sync(0xffffffffu, pvp, 1);
-        pvp += __shfl_xor_sync(0xffffffffu, pvp, 2);
-        pvp += __shfl_xor_sync(0xffffffffu, pvp, 4);
-        if (lane == 0) red[w] = pvp;
-        if (act && part == 0) pbuf[i] = pi;
-        __syncthreads();                                                   // (A)
-        float pv = 0.f;
-        {
-            const float4* R4 = reinterpret_cast<const float4*>(red);
-            for (int c = 0; c < (nwarps + 3) >> 2; ++c) { const float4 t = R4[c]; pv += (t.x + t.y) + (t.z + t.w); }
-        }
-        const float coef = 0.5f * tau * pv;
-        // w = p - coef v -- every warp writes the same values
-        for (int j = lane; j < kpad; j += 32) wbuf[j] = (j < k) ? fmaf(-coef, vbuf[j], pbuf[j]) : 0.0f;
-        __syncwarp();
-        if (act) {
-            const float vi = vbuf[i], wi = wbuf[i];
-            const float4* W4 = reinterpret_cast<const float4*>(wbuf);
-            for (int c = part; c < nch; c += 4) {
-                float4 a = Ar[c];
-                const float4 v = V[c], ww = W4[c];
-                a.x = fmaf(-vi, ww.x, fmaf(-wi, v.x, a.x));
-                a.y = fmaf(-vi, ww.y, fmaf(-wi, v.y, a.y));
-                a.z = fmaf(-vi, ww.z, fmaf(-wi, v.z, a.z));
-                a.w = fmaf(-vi, ww.w, fmaf(-wi, v.w, a.w));
-                Ar[c] = a;
+        float tau = 0.f, beta = alpha;
+        if (ss != 0.f) {
+            const float nrm = sqrtf(fmaf(alpha, alpha, ss));
+            beta = -copysignf(nrm, alpha);
+            tau = (beta - alpha) / beta;
+            const float scl = 1.0f / (alpha - beta);
+            // v (v[k-1] = 1, zeros above) -- every warp writes the same values
+#pragma unroll
+            for (int t = 0; t < MAXN / 32; ++t) {
+                const int j = lane + 32 * t;
+                vbuf[j] = (j < k - 1) ? xl[t] * scl : (j == k - 1 ? 1.0f : 0.0f);
             }
-        } else if (i == k) {
-            // the pivot row becomes the reflector (zeros from column k on) for the Q accumulation
-            for (int c = part; c < LDA / 4; c += 4) Ar[c] = (4 * c < kpad) ? V[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (part == 0) { ee[k - 1] = beta; taus[k] = tau; }
         }
-        __syncthreads();                                                   // (B)
+        if (tid == 0) { dd[k] = xr[k]; ee[k - 1] = beta; }
+        if (tau != 0.f) {                              // uniform
+            __syncwarp();
+            const float4* V4 = reinterpret_cast<const float4*>(vbuf);
+            const bool act = tid < k;
+            // p = tau A v: thread-local
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+            if (act) {
+#pragma unroll
+                for (int cb = 0; cb < NB; ++cb) {
+                    if (16 * cb < k) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 v = V4[4 * cb + c];
+                            q0 = fmaf(a[16 * cb + 4 * c + 0], v.x, q0);
+                            q1 = fmaf(a[16 * cb + 4 * c + 1], v.y, q1);
+                            q2 = fmaf(a[16 * cb + 4 * c + 2], v.z, q2);
+                            q3 = fmaf(a[16 * cb + 4 * c + 3], v.w, q3);
+                        }
+                    }
+                }
+            }
+            const float pi = tau * ((q0 + q1) + (q2 + q3));
+            const float vi = act ? vbuf[tid] : 0.f;
+            const float pvp = warp_sum(act ? pi * vi : 0.f);
+            if (lane == 0) red[w] = pvp;
+            if (act) pbuf[tid] = pi;
+            // the reflector goes to global memory for K3 (whole 16-column blocks, tau at [160])
+            if (w == nwarps - 1) {
+                float* vrow = Vg + (size_t)k * LDV;
+#pragma unroll
+                for (int t = 0; t < MAXN / 32; ++t) vrow[lane + 32 * t] = vbuf[lane + 32 * t];
+                if (lane == 0) vrow[MAXN] = tau;
+            }
+            __syncthreads();                                                   // (A)
+            const float4 r0 = *reinterpret_cast<const float4*>(red), r1 = *reinterpret_cast<const float4*>(red + 4);
+            const float pv = ((r0.x + r0.y) + (r0.z + r0.w)) + ((r1.x + r1.y) + (r1.z + r1.w));
+            const float coef = 0.5f * tau * pv;
+            // w = p - coef v -- every warp writes the same values
+#pragma unroll
+            for (int t = 0; t < MAXN / 32; ++t) {
+                const int j = lane + 32 * t;
+                wbuf[j] = (j < k) ? fmaf(-coef, vbuf[j], pbuf[j]) : 0.0f;
+            }
+            __syncwarp();
+            if (act) {
+                const float wi = wbuf[tid];
+                const float4* W4 = reinterpret_cast<const float4*>(wbuf);
+#pragma unroll
+                for (int cb = 0; cb < NB; ++cb) {
+                    if (16 * cb < k) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 v = V4[4 * cb + c], ww = W4[4 * cb + c];
+                            a[16 * cb + 4 * c + 0] = fmaf(-vi, ww.x, fmaf(-wi, v.x, a[16 * cb + 4 * c + 0]));
+                            a[16 * cb + 4 * c + 1] = fmaf(-vi, ww.y, fmaf(-wi, v.y, a[16 * cb + 4 * c + 1]));
+                            a[16 * cb + 4 * c + 2] = fmaf(-vi, ww.z, fmaf(-wi, v.z, a[16 * cb + 4 * c + 2]));
+                            a[16 * cb + 4 * c + 3] = fmaf(-vi, ww.w, fmaf(-wi, v.w, a[16 * cb + 4 * c + 3]));
+                        }
+                    }
+                }
+            }
+        } else if (w == nwarps - 1 && lane == 0) {
+            Vg[(size_t)k * LDV + MAXN] = 0.f;                                  // H = I (slarfg): K3 skips the row
+        }
+        // the next pivot row (row k-1, columns 0..k-1) is final now
+        if (tid == k - 1) GSR_PUBLISH((k - 1) & 1, k);
+        __syncthreads();                                                       // (B)
     }
-    if (tid == 0) { dd[0] = A[0]; if (n >= 1) ee[n - 1] = 0.f; }
+    if (tid == 0) {
+        dd[0] = (n == 1) ? a[0] : xbuf[0];              // row 0 was published last (buffer 0, column 0)
+        ee[n - 1] = 0.f;
+        Vg[MAXN] = 0.f;                                 // no reflector in row 0
+    }
     __syncthreads();
     for (int j = tid; j < n; j += nthr) {
         wk.d[(size_t)g * n + j] = dd[j];
         wk.e[(size_t)g * n + j] = (j < n - 1) ? ee[j] : 0.f;
-    }
-
-    // ---- Q^T = H_1 H_2 ... H_{n-1}, accumulated in place: at step k rows 0..k-1 hold Q^T, row k
-    //      still holds the reflector v_k.  Row r starts as e_r at step r + 1.
-    for (int k = 1; k <= n; ++k) {
-        float4* Ar = reinterpret_cast<float4*>(A + i * LDA);
-        if (i == k - 1 && i < n) {
-            for (int c = part; c < LDA / 4; c += 4) {
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((i >> 2) == c) { const int x = i & 3; if (x == 0) t.x = 1.f; else if (x == 1) t.y = 1.f; else if (x == 2) t.z = 1.f; else t.w = 1.f; }
-                Ar[c] = t;
-            }
-        }
-        if (k == n) break;
-        const float tau = taus[k];
-        if (tau != 0.f && 8 * w < k) {
-            const float4* V = reinterpret_cast<const float4*>(A + k * LDA);
-            const int nch = (k + 3) >> 2;
-            const bool act = i < k;
-            float s = 0.f;
-            if (act) {
-                for (int c = part; c < nch; c += 4) s = dot4(Ar[c], V[c], s);
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 8);
-            s += __shfl_xor_sync(0xffffffffu, s, 16);
-            s *= tau;
-            if (act) {
-                for (int c = part; c < nch; c += 4) {
-                    float4 a = Ar[c];
-                    const float4 v = V[c];
-                    a.x = fmaf(-s, v.x, a.x); a.y = fmaf(-s, v.y, a.y); a.z = fmaf(-s, v.z, a.z); a.w = fmaf(-s, v.w, a.w);
-                    Ar[c] = a;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    __syncthreads();
-    float* Qg = wk.Qt + (size_t)g * n * n;
-    for (int e = tid; e < n * n; e += nthr) {
-        const int r = e / n, c = e - r * n;
-        Qg[e] = A[r * LDA + c];
     }
 }
 
@@ -290,6 +288,7 @@ tql_scalar_kernel(const Work wk, int n, int batch) {
     __syncwarp();
     float2* out = wk.stream + (size_t)g * wk.cap;
     uint32_t* hdr = wk.hdr + (size_t)g * wk.hdr_cap;
+    const float2 ident = make_float2(1.0f, 0.0f);
     float f = 0.f, tst1 = 0.f;
     int pos = 0, nit = 0, status = 0;
     for (int l = 0; l < n && status == 0; ++l) {
@@ -303,10 +302,13 @@ tql_scalar_kernel(const Work wk, int n, int batch) {
             if (b) { m = base + __ffs(b) - 1; break; }
         }
         if (m > l) {
+            // the rotations i = m-1 .. l of one QL iteration are padded with identities to the
+            // 16-column blocks [lo, hi): K3 replays whole blocks with static register indices
+            const int lo = l & ~15, hi = (m + 15) & ~15;
             int j = 0;
             while (true) {
                 if (++j > 30) { status = 2; break; }
-                if (pos + (m - l) > wk.cap - BLK || nit >= wk.hdr_cap) { status = 3; break; }
+                if (pos + (hi - lo) > wk.cap - BLK || nit >= wk.hdr_cap) { status = 3; break; }
                 // Wilkinson shift
                 const float g0 = d[l], el = e[l];
                 const float p0 = (d[l + 1] - g0) / (2.0f * el);
@@ -318,10 +320,13 @@ tql_scalar_kernel(const Work wk, int n, int batch) {
                 if (lane == 0) { d[l] = dl; d[l + 1] = dl1; }
                 for (int q = l + 2 + lane; q < n; q += 32) d[q] -= h;
                 f += h;
+                float2* o = out + pos;
+                for (int q = lane; q < hi - m; q += 32) o[q] = ident;                       // rotation indices hi-1 .. m
+                for (int q = lane; q < l - lo; q += 32) o[(hi - l) + q] = ident;            // rotation indices l-1 .. lo
                 __syncwarp();
                 if (lane == 0) {
-                    hdr[nit] = (uint32_t)l | ((uint32_t)m << 16);
-                    float2* o = out + pos;
+                    hdr[nit] = (uint32_t)(lo >> 4) | ((uint32_t)(hi >> 4) << 8);
+                    o += hi - m;
                     float p = d[m], c = 1.0f, c2 = 1.0f, c3 = 1.0f, s = 0.0f, s2 = 0.0f;
                     const float el1 = e[l + 1];
                     float ei = e[m - 1], di = d[m - 1];
@@ -352,7 +357,7 @@ tql_scalar_kernel(const Work wk, int n, int batch) {
                     e[l] = s * p;
                     d[l] = c * p;
                 }
-                pos += m - l;
+                pos += hi - lo;
                 ++nit;
                 __syncwarp();
                 if (tst1 + fabsf(e[l]) <= tst1) break;
@@ -369,26 +374,29 @@ tql_scalar_kernel(const Work wk, int n, int batch) {
 // ------------------------------------------------------------------------------------ K3
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(d), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(160, 2)
+constexpr int RING_FLOATS = STAGES * 176;       // per warp: 3 reflector rows (164 floats) or 3 x 64 (c, s) pairs (128 floats)
+
+__global__ void __launch_bounds__(MAXN, 2)
 tql_apply_kernel(const Work wk, float* __restrict__ Wout, float* __restrict__ Uout, int32_t* __restrict__ info,
                  int n, int canonical) {
     extern __shared__ __align__(16) float sm[];
+    // the epilogue's column-major Z overlays the per-warp operand rings (dead by then)
+    float* zs = sm;                                                    // [n][LDZ]
     const int zfloats = (n * LDZ + 3) & ~3;
-    float* z = sm;                                                     // column i of Z at z + i * LDZ
-    float2* ring = reinterpret_cast<float2*>(sm + zfloats);            // [nwarps][STAGES][BLK]
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nwarps = nthr >> 5;
-    float* lam = reinterpret_cast<float*>(ring + nwarps * STAGES * BLK);   // [n]
+    float* lam = sm + max(zfloats, nwarps * RING_FLOATS);              // [n]
     float* sgn = lam + n;                                              // [n]
     int* inv = reinterpret_cast<int*>(sgn + n);                        // [n]
+    float* ring = sm + w * RING_FLOATS;
     const int g = blockIdx.x;
     const int* cnt = wk.counts + 4 * g;
-    const int nit = cnt[0], nrot = cnt[1], status = cnt[2];
+    const int nit = cnt[0], nent = cnt[1], status = cnt[2];
     if (status == -1) return;                                          // K1 wrote NaNs and info
     float* Wg = Wout + (size_t)g * n;
     float* Ug = Uout + (size_t)g * n * n;
@@ -399,91 +407,127 @@ tql_apply_kernel(const Work wk, float* __restrict__ Wout, float* __restrict__ Uo
         if (tid == 0) info[g] = -2;
         return;
     }
-    // ---- Z = Q: z[i][r] = Q^T[i][r]; column n of every pitch row is scratch for the idle lanes
-    const float* Qg = wk.Qt + (size_t)g * n * n;
-    for (int e = tid; e < n * n; e += nthr) {
-        const int r0 = e / n, c = e - r0 * n;
-        z[r0 * LDZ + c] = Qg[e];
-    }
-    for (int e = tid; e < n; e += nthr) z[e * LDZ + n] = 0.f;
-    __syncthreads();
 
-    const int r = tid < n ? tid : n;
-    float2* myring = ring + w * STAGES * BLK;
-    const float2* src = wk.stream + (size_t)g * wk.cap;
-    const uint32_t* hdr = wk.hdr + (size_t)g * wk.hdr_cap;
-    const int nblk = (nrot + BLK - 1) / BLK;
-    auto issue = [&](int b) {
-        if (b < nblk) cp_async16(myring + (b % STAGES) * BLK + 2 * lane, src + (size_t)b * BLK + 2 * lane);
-        cp_async_commit();
-    };
-    issue(0);
-    issue(1);
-    int cur_b = -1, pos = 0;
-    uint32_t h = nit > 0 ? __ldg(hdr) : 0u;
-    for (int it = 0; it < nit; ++it) {
-        const uint32_t hn = (it + 1 < nit) ? __ldg(hdr + it + 1) : 0u;
-        const int l = (int)(h & 0xffffu), m = (int)(h >> 16);
-        float rv = z[m * LDZ + r];
-        int i = m - 1, left = m - l;
-        while (left > 0) {
-            const int b = pos / BLK, off = pos - b * BLK;
-            if (b != cur_b) {
-                cur_b = b;
-                cp_async_wait<1>();
-                __syncwarp();
-                issue(b + 2);
+    // ---- Z = Q = H_{n-1} ... H_1, row `tid` of it: e_r^T H_{n-1} ... H_1, thread-local
+    float z[MAXN + 1];
+#pragma unroll
+    for (int j = 0; j <= MAXN; ++j) z[j] = (j == tid && tid < n) ? 1.0f : 0.0f;
+    {
+        const float* Vg = wk.V + (size_t)g * n * LDV;
+        // reflector rows n-1 .. 1 stream through a 3-deep per-warp ring (41 x 16 B each)
+        auto issue = [&](int k) {
+            if (k >= 1) {
+                const float* src = Vg + (size_t)k * LDV;
+                float* dst = ring + (k % STAGES) * 176;
+                cp_async16(dst + 4 * lane, src + 4 * lane);
+                if (lane < LDV / 4 - 32) cp_async16(dst + 4 * (lane + 32), src + 4 * (lane + 32));
             }
-            const int seg = min(left, BLK - off);
-            const float2* cs = myring + (b % STAGES) * BLK + off;
-            float* zp = z + i * LDZ + r;
-            // groups of 4 rotations; the operands of the next group are loaded before the stores of
-            // the current one (the compiler cannot hoist shared-memory loads over stores itself)
-            int t = 0;
-            float2 qa[4];
-            float za[4];
-            if (seg >= 4) {
+            cp_async_commit();
+        };
+        issue(n - 1);
+        issue(n - 2);
+        for (int k = n - 1; k >= 1; --k) {
+            cp_async_wait<1>();
+            __syncwarp();                                              // row k landed; every lane is done with row k + 1
+            issue(k - 2);                                              // stage (k + 1) % 3: consumed one step ago
+            const float* vr = ring + (k % STAGES) * 176;
+            const float tau = vr[MAXN];
+            if (tau != 0.f) {                                          // uniform
+                const float4* V4 = reinterpret_cast<const float4*>(vr);
+                float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { qa[u] = cs[u]; za[u] = zp[-u * LDZ]; }
-            }
-            for (; t + 4 <= seg; t += 4) {
-                float2 qb[4];
-                float zb[4];
-                const bool more = t + 8 <= seg;
-                if (more) {
+                for (int cb = 0; cb < NB; ++cb) {
+                    if (16 * cb < k) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { qb[u] = cs[t + 4 + u]; zb[u] = zp[-(t + 4 + u) * LDZ]; }
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 v = V4[4 * cb + c];
+                            q0 = fmaf(z[16 * cb + 4 * c + 0], v.x, q0);
+                            q1 = fmaf(z[16 * cb + 4 * c + 1], v.y, q1);
+                            q2 = fmaf(z[16 * cb + 4 * c + 2], v.z, q2);
+                            q3 = fmaf(z[16 * cb + 4 * c + 3], v.w, q3);
+                        }
+                    }
                 }
+                const float s = -tau * ((q0 + q1) + (q2 + q3));
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float2 q = qa[u];
-                    const float zi = za[u];
-                    zp[(1 - (t + u)) * LDZ] = fmaf(q.y, zi, q.x * rv);
-                    rv = fmaf(q.x, zi, -q.y * rv);
-                }
-                if (more) {
+                for (int cb = 0; cb < NB; ++cb) {
+                    if (16 * cb < k) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { qa[u] = qb[u]; za[u] = zb[u]; }
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 v = V4[4 * cb + c];
+                            z[16 * cb + 4 * c + 0] = fmaf(s, v.x, z[16 * cb + 4 * c + 0]);
+                            z[16 * cb + 4 * c + 1] = fmaf(s, v.y, z[16 * cb + 4 * c + 1]);
+                            z[16 * cb + 4 * c + 2] = fmaf(s, v.z, z[16 * cb + 4 * c + 2]);
+                            z[16 * cb + 4 * c + 3] = fmaf(s, v.w, z[16 * cb + 4 * c + 3]);
+                        }
+                    }
                 }
             }
-            for (; t < seg; ++t) {
-                const float2 q = cs[t];
-                const float zi = zp[-t * LDZ];
-                zp[(1 - t) * LDZ] = fmaf(q.y, zi, q.x * rv);
-                rv = fmaf(q.x, zi, -q.y * rv);
-            }
-            i -= seg; pos += seg; left -= seg;
         }
-        z[l * LDZ + r] = rv;
-        h = hn;
+        cp_async_wait<0>();
+        __syncwarp();
     }
-    cp_async_wait<0>();
+
+    // ---- replay the rotation stream: iteration = blocks hb-1 .. lb of 16 rotations, rotation
+    //      index i acts on columns (i, i + 1), i descending
+    {
+        const float2* src = wk.stream + (size_t)g * wk.cap;
+        const uint32_t* hdr = wk.hdr + (size_t)g * wk.hdr_cap;
+        float2* cring = reinterpret_cast<float2*>(ring);               // [STAGES][BLK]
+        const int nblk = (nent + BLK - 1) / BLK;
+        auto issue = [&](int b) {
+            if (b < nblk) cp_async16(cring + (b % STAGES) * BLK + 2 * lane, src + (size_t)b * BLK + 2 * lane);
+            cp_async_commit();
+        };
+        issue(0);
+        issue(1);
+        int pos = 0;
+        uint32_t h = nit > 0 ? __ldg(hdr) : 0u;
+        for (int it = 0; it < nit; ++it) {
+            const uint32_t hn = (it + 1 < nit) ? __ldg(hdr + it + 1) : 0u;
+            const int lb = (int)(h & 0xffu), hb = (int)((h >> 8) & 0xffu);
+#pragma unroll
+            for (int b = NB - 1; b >= 0; --b) {
+                if (b < hb && b >= lb) {                               // uniform
+                    if ((pos & (BLK - 1)) == 0) {                      // entering a new 64-rotation block
+                        cp_async_wait<1>();
+                        __syncwarp();
+                        issue(pos / BLK + 2);
+                    }
+                    const float4* cs4 = reinterpret_cast<const float4*>(cring + (pos / BLK % STAGES) * BLK + (pos & (BLK - 1)));
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float4 q = cs4[u];                       // two rotations: (c, s) of i, (c, s) of i - 1
+                        const int i = 16 * b + 15 - 2 * u;
+                        // the running column t enters each product last, so the dependent chain
+                        // is one FFMA per rotation (the products with z[i], z[i-1] are off it)
+                        float t = z[i + 1];
+                        z[i + 1] = fmaf(q.x, t, q.y * z[i]);
+                        z[i] = fmaf(-q.y, t, q.x * z[i]);
+                        t = z[i];
+                        z[i] = fmaf(q.z, t, q.w * z[i - 1]);
+                        z[i - 1] = fmaf(-q.w, t, q.z * z[i - 1]);
+                    }
+                    pos += 16;
+                }
+            }
+            h = hn;
+        }
+        cp_async_wait<0>();
+    }
     __syncthreads();
 
-    // ---- eigenvalues: undo the scaling, ascending order by counting (ties keep column order)
+    // ---- epilogue through shared memory: column k of Z at zs + k * LDZ
+    if (tid < n) {
+#pragma unroll
+        for (int j = 0; j < MAXN; ++j) {
+            if (j < n) zs[j * LDZ + tid] = z[j];
+        }
+    }
     const float inv_sc = 1.0f / wk.scale[g];
     for (int k = tid; k < n; k += nthr) lam[k] = wk.d[(size_t)g * n + k] * inv_sc;
     __syncthreads();
+    // ascending order by counting (ties keep column order)
     for (int k = tid; k < n; k += nthr) {
         const float lk = lam[k];
         int rk = 0;
@@ -494,12 +538,12 @@ tql_apply_kernel(const Work wk, float* __restrict__ Wout, float* __restrict__ Uo
         inv[rk] = k;
         Wg[rk] = lk;
     }
-    // ---- sign rule: the largest-|.| component (lowest row on ties) of every eigenvector is positive
+    // unit columns and the sign rule: the largest-|.| component (lowest row on ties) is positive
     for (int k = w; k < n; k += nwarps) {
         float best = -1.f, best_v = 0.f, ss = 0.f;
         int best_i = 0;
         for (int row = lane; row < n; row += 32) {
-            const float v = z[k * LDZ + row], mag = fabsf(v);
+            const float v = zs[k * LDZ + row], mag = fabsf(v);
             ss = fmaf(v, v, ss);
             if (mag > best) { best = mag; best_i = row; best_v = v; }
         }
@@ -511,7 +555,7 @@ tql_apply_kernel(const Work wk, float* __restrict__ Wout, float* __restrict__ Uo
             const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
             if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; best_v = ov; }
         }
-        // unit columns: ~500 rotations of norm 1 +- 4e-8 each leave the column norms off by a few 1e-6
+        // ~500 rotations of norm 1 +- 4e-8 each leave the column norms off by a few 1e-6
         const float inv_norm = ss > 0.f ? rsqrtf(ss) : 1.0f;
         if (lane == 0) sgn[k] = (canonical && best_v < 0.f) ? -inv_norm : inv_norm;
     }
@@ -519,7 +563,7 @@ tql_apply_kernel(const Work wk, float* __restrict__ Wout, float* __restrict__ Uo
     for (int e = tid; e < n * n; e += nthr) {
         const int row = e / n, c = e - row * n;
         const int k = inv[c];
-        Ug[e] = z[k * LDZ + row] * sgn[k];
+        Ug[e] = zs[k * LDZ + row] * sgn[k];
     }
     if (tid == 0) info[g] = nit > 0 ? nit : 1;
 }
@@ -545,12 +589,9 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
     cudaStream_t st = (cudaStream_t)stream;
     tq::Work wk;
     tq::carve(&wk, workspace, batch, n);
+    const int threads = 32 * ((n + 31) / 32);
 
-    const size_t smem1 = ((size_t)n * tq::LDA + tq::K1_SMALL) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(tq::tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    if (e != cudaSuccess) return fail((int)e, "eigh_tridiag: cudaFuncSetAttribute failed");
-    const int threads1 = 32 * ((n + 7) / 8);
-    tq::tridiag_kernel<<<batch, threads1, smem1, st>>>(A, w, U, info, wk, n);
+    tq::tridiag_kernel<<<batch, threads, 0, st>>>(A, w, U, info, wk, n);
     int rc = launched("eigh_tridiag");
     if (rc) return rc;
 
@@ -558,11 +599,11 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
     rc = launched("eigh_tql_scalar");
     if (rc) return rc;
 
-    const int threads3 = 32 * ((n + 31) / 32);
     const size_t zfloats = ((size_t)n * tq::LDZ + 3) & ~(size_t)3;
-    const size_t smem3 = zfloats * sizeof(float) + (size_t)(threads3 / 32) * tq::STAGES * tq::BLK * sizeof(float2) + 3 * (size_t)n * sizeof(float);
-    e = cudaFuncSetAttribute(tq::tql_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+    const size_t ringf = (size_t)(threads / 32) * tq::RING_FLOATS;
+    const size_t smem3 = (zfloats > ringf ? zfloats : ringf) * sizeof(float) + 3 * (size_t)n * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(tq::tql_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
     if (e != cudaSuccess) return fail((int)e, "eigh_tridiag: cudaFuncSetAttribute failed");
-    tq::tql_apply_kernel<<<batch, threads3, smem3, st>>>(wk, w, U, info, n, canonical_sign);
+    tq::tql_apply_kernel<<<batch, threads, smem3, st>>>(wk, w, U, info, n, canonical_sign);
     return launched("eigh_tql_apply");
 }

@@ -273,7 +273,7 @@ def test_eigh_full_batch_properties(cuda_pkg):
     lr.diagonal(dim1=1, dim2=2).zero_()
     A = cuda_pkg.normalize_adj_torch(lr)
     w, U, info = F_.eigh(A)
-    assert int(info.min()) > 0 and int((info & 0xFF).max()) <= 16 and int((info >> 8).max()) <= 4
+    assert int(info.min()) > 0 and int(info.max()) <= 30 * 160        # QL iterations (tridiagonal route, n <= 160)
     Ad, Ud, wd = A.double(), U.double(), w.double()
     As = torch.triu(Ad) + torch.triu(Ad, 1).transpose(1, 2)
     res = (As @ Ud - Ud * wd[:, None, :]).abs().amax()
