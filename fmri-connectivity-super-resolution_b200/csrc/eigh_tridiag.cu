@@ -49,6 +49,7 @@ constexpr int STAGES = 3;
 struct Work {
     float2* stream;      // [batch][cap]      rotations (c, s) in application order (padded)
     float* V;            // [batch][n][LDV]   reflector k in row k (zeros from column k on), tau at [160]
+    float* Zt;           // [batch][n][n]     K3 -> K4: column k of Z in row k (unsorted, un-normalised)
     float* d;            // [batch][n]        diagonal of T, then the unsorted eigenvalues
     float* e;            // [batch][n]        off-diagonal of T (e[n-1] = 0)
     float* scale;        // [batch]           power-of-two input scaling
@@ -68,6 +69,7 @@ static size_t carve(Work* wk, void* base, int batch, int n) {
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_stream = take((size_t)batch * cap * sizeof(float2));
     const size_t o_v = take((size_t)batch * n * LDV * sizeof(float));
+    const size_t o_zt = take((size_t)batch * n * n * sizeof(float));
     const size_t o_d = take((size_t)batch * n * sizeof(float));
     const size_t o_e = take((size_t)batch * n * sizeof(float));
     const size_t o_sc = take((size_t)batch * sizeof(float));
@@ -77,6 +79,7 @@ static size_t carve(Work* wk, void* base, int batch, int n) {
         char* b = static_cast<char*>(base);
         wk->stream = reinterpret_cast<float2*>(b + o_stream);
         wk->V = reinterpret_cast<float*>(b + o_v);
+        wk->Zt = reinterpret_cast<float*>(b + o_zt);
         wk->d = reinterpret_cast<float*>(b + o_d);
         wk->e = reinterpret_cast<float*>(b + o_e);
         wk->scale = reinterpret_cast<float*>(b + o_sc);
@@ -381,32 +384,22 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 constexpr int RING_FLOATS = STAGES * 176;       // per warp: 3 reflector rows (164 floats) or 3 x 64 (c, s) pairs (128 floats)
+constexpr int K3_WARPS = 4;                     // warp units per CTA; 2 CTAs per SM = 2 warps per scheduler at <= 255 registers
 
-__global__ void __launch_bounds__(MAXN, 2)
-tql_apply_kernel(const Work wk, float* __restrict__ Wout, float* __restrict__ Uout, int32_t* __restrict__ info,
-                 int n, int canonical) {
+// One WARP per (graph, block of 32 rows of Z): rows are independent under column operations, so
+// the unit of work is a warp and nothing synchronises across warps.  Output: Zt[g][col][row]
+// (unsorted, un-normalised; coalesced: a warp stores 32 consecutive rows of one column).
+__global__ void __launch_bounds__(32 * K3_WARPS, 2)
+tql_apply_kernel(const Work wk, int n, int units_per_graph, int total_units) {
     extern __shared__ __align__(16) float sm[];
-    // the epilogue's column-major Z overlays the per-warp operand rings (dead by then)
-    float* zs = sm;                                                    // [n][LDZ]
-    const int zfloats = (n * LDZ + 3) & ~3;
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nwarps = nthr >> 5;
-    float* lam = sm + max(zfloats, nwarps * RING_FLOATS);              // [n]
-    float* sgn = lam + n;                                              // [n]
-    int* inv = reinterpret_cast<int*>(sgn + n);                        // [n]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int unit = blockIdx.x * K3_WARPS + w;
+    if (unit >= total_units) return;
+    const int g = unit / units_per_graph, tid = (unit - g * units_per_graph) * 32 + lane;     // tid = row of Z
     float* ring = sm + w * RING_FLOATS;
-    const int g = blockIdx.x;
     const int* cnt = wk.counts + 4 * g;
     const int nit = cnt[0], nent = cnt[1], status = cnt[2];
-    if (status == -1) return;                                          // K1 wrote NaNs and info
-    float* Wg = Wout + (size_t)g * n;
-    float* Ug = Uout + (size_t)g * n * n;
-    if (status != 0) {                                                 // QL did not converge / stream overflow
-        const float qnan = __int_as_float(0x7fc00000);
-        for (int e = tid; e < n * n; e += nthr) Ug[e] = qnan;
-        for (int e = tid; e < n; e += nthr) Wg[e] = qnan;
-        if (tid == 0) info[g] = -2;
-        return;
-    }
+    if (status != 0) return;                                           // K1 / K4 write the error outputs
 
     // ---- Z = Q = H_{n-1} ... H_1, row `tid` of it: e_r^T H_{n-1} ... H_1, thread-local
     float z[MAXN + 1];
@@ -515,19 +508,47 @@ tql_apply_kernel(const Work wk, float* __restrict__ Wout, float* __restrict__ Uo
         }
         cp_async_wait<0>();
     }
-    __syncthreads();
-
-    // ---- epilogue through shared memory: column k of Z at zs + k * LDZ
     if (tid < n) {
+        float* Zg = wk.Zt + (size_t)g * n * n;
 #pragma unroll
         for (int j = 0; j < MAXN; ++j) {
-            if (j < n) zs[j * LDZ + tid] = z[j];
+            if (j < n) Zg[(size_t)j * n + tid] = z[j];
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------ K4
+// One CTA per graph: unit columns, ascending order by counting, sign rule, coalesced store.
+__global__ void __launch_bounds__(256)
+tql_finish_kernel(const Work wk, float* __restrict__ Wout, float* __restrict__ Uout, int32_t* __restrict__ info,
+                  int n, int canonical) {
+    extern __shared__ __align__(16) float sm[];
+    float* zs = sm;                                                    // column k of Z at zs + k * LDZ
+    float* lam = sm + (size_t)n * LDZ;                                 // [n]
+    float* sgn = lam + n;                                              // [n]
+    int* inv = reinterpret_cast<int*>(sgn + n);                        // [n]
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nwarps = nthr >> 5;
+    const int g = blockIdx.x;
+    const int* cnt = wk.counts + 4 * g;
+    const int nit = cnt[0], status = cnt[2];
+    if (status == -1) return;                                          // K1 wrote NaNs and info
+    float* Wg = Wout + (size_t)g * n;
+    float* Ug = Uout + (size_t)g * n * n;
+    if (status != 0) {                                                 // QL did not converge / stream overflow
+        const float qnan = __int_as_float(0x7fc00000);
+        for (int e = tid; e < n * n; e += nthr) Ug[e] = qnan;
+        for (int e = tid; e < n; e += nthr) Wg[e] = qnan;
+        if (tid == 0) info[g] = -2;
+        return;
+    }
+    const float* Zg = wk.Zt + (size_t)g * n * n;
+    for (int e = tid; e < n * n; e += nthr) {
+        const int k = e / n, row = e - k * n;
+        zs[k * LDZ + row] = Zg[e];
     }
     const float inv_sc = 1.0f / wk.scale[g];
     for (int k = tid; k < n; k += nthr) lam[k] = wk.d[(size_t)g * n + k] * inv_sc;
     __syncthreads();
-    // ascending order by counting (ties keep column order)
     for (int k = tid; k < n; k += nthr) {
         const float lk = lam[k];
         int rk = 0;
@@ -599,11 +620,15 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
     rc = launched("eigh_tql_scalar");
     if (rc) return rc;
 
-    const size_t zfloats = ((size_t)n * tq::LDZ + 3) & ~(size_t)3;
-    const size_t ringf = (size_t)(threads / 32) * tq::RING_FLOATS;
-    const size_t smem3 = (zfloats > ringf ? zfloats : ringf) * sizeof(float) + 3 * (size_t)n * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(tq::tql_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+    const int units_per_graph = threads / 32, total_units = units_per_graph * batch;
+    const size_t smem3 = (size_t)tq::K3_WARPS * tq::RING_FLOATS * sizeof(float);
+    tq::tql_apply_kernel<<<(total_units + tq::K3_WARPS - 1) / tq::K3_WARPS, 32 * tq::K3_WARPS, smem3, st>>>(wk, n, units_per_graph, total_units);
+    rc = launched("eigh_tql_apply");
+    if (rc) return rc;
+
+    const size_t smem4 = ((size_t)n * tq::LDZ + 3 * (size_t)n) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(tq::tql_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
     if (e != cudaSuccess) return fail((int)e, "eigh_tridiag: cudaFuncSetAttribute failed");
-    tq::tql_apply_kernel<<<batch, threads, smem3, st>>>(wk, w, U, info, n, canonical_sign);
-    return launched("eigh_tql_apply");
+    tq::tql_finish_kernel<<<batch, 256, smem4, st>>>(wk, w, U, info, n, canonical_sign);
+    return launched("eigh_tql_finish");
 }
