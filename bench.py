@@ -244,7 +244,10 @@ def run_ours(args):
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
     launches = pkg.launch_count() - launches0
-    gemm_ms, gemm_flops, gemm_launches = K.GEMM_TIMER.totals()
+    # contractions on the tensor-core kernel (per-subject and stacked 268-wide products) and, separately, the small
+    # Graph U-Net products on the SIMT kernel (they run on a side stream under the eigendecomposition)
+    gemm_ms, gemm_flops, gemm_launches = K.GEMM_TIMER.totals("tc" if K.GEMM_BACKEND == "tc" else None)
+    simt_ms, simt_flops, simt_launches = K.GEMM_TIMER.totals("simt") if K.GEMM_BACKEND == "tc" else (0.0, 0.0, 0)
     eigh_ms, eigh_graphs, eigh_launches = K.EIGH_TIMER.totals()
     ew_ms, ew_bytes, ew_launches = K.EW_TIMER.totals()
     eigh_info = getattr(K.EIGH_TIMER, "last_info", None)
@@ -348,6 +351,9 @@ def run_ours(args):
         "frac_of_3xtf32_ceiling": (gemm_tflops / (bf16_peak / 6.0)) if (gemm_tflops and backend == "tc") else None,
         "share_of_step": gemm_ms / elapsed_ms if elapsed_ms else None, "launches": gemm_launches,
         "algorithmic_flop_per_subject": GEMM_FLOP_PER_SUBJECT_FWD_BWD, "traffic": None,
+        "unet_simt_products": {"launches": simt_launches, "gflop_per_step": simt_flops / max(args.steps, 1) / 1e9,
+                               "note": "Graph U-Net linears (once per step, subject independent) on gsr::bgemm_kernel, "
+                                       "side stream under the eigendecomposition; not part of `achieved`"},
     }
     # --- LR eigendecomposition
     eigh_roof = None

@@ -254,6 +254,10 @@ tcgemm_kernel(const Params p) {
         long long goff[PATCH_ITERS];        // element offset of this thread's float4 at k-block 0
         uint32_t so[PATCH_ITERS];           // byte offset inside the (hi or lo) tile
         uint32_t ok_mask = 0;               // bit i: the float4 of patch i lies inside the operand (rows)
+        uint32_t dead_mask = 0;             // bit i: an A patch whose rows all lie below the operand (ragged last M tile,
+                                            //        12 of 128 rows for the 268-row subject matrices): neither loaded nor
+                                            //        staged -- accumulator rows are independent and those rows are never stored
+        const int rows_valid = p.M - m0;
 #pragma unroll
         for (int i = 0; i < PATCH_ITERS; ++i) {
             const int patch = gw + i * GROUP_WARPS;
@@ -261,6 +265,7 @@ tcgemm_kernel(const Params p) {
             goff[i] = 0; so[i] = 0;
             if (patch < A_PATCHES) {
                 patch_coords<BM, !TA>(patch, lane, row, k, so[i]);
+                if ((TA ? (patch % (BM / 32)) * 32 : (patch >> 1) * 8) >= rows_valid) dead_mask |= 1u << i;
                 row += m0;
                 goff[i] = TA ? (long long)k * p.lda + row : (long long)row * p.lda + k;
                 if (TA ? (row + 3 < p.M) : (row < p.M)) ok_mask |= 1u << i;
@@ -294,7 +299,7 @@ tcgemm_kernel(const Params p) {
 #pragma unroll
                 for (int i = 0; i < PATCH_ITERS; ++i) {
                     const int patch = gw + i * GROUP_WARPS;
-                    if (patch < A_PATCHES) v[i] = load_patch<BM, !TA>(A, p.lda, p.M, p.K, m0, kb * BK, patch, lane, dummy);
+                    if (patch < A_PATCHES) { if (!((dead_mask >> i) & 1u)) v[i] = load_patch<BM, !TA>(A, p.lda, p.M, p.K, m0, kb * BK, patch, lane, dummy); }
                     else if (patch < PATCHES) v[i] = load_patch<BN, TB>(B, p.ldb, p.N, p.K, n0, kb * BK, patch - A_PATCHES, lane, dummy);
                 }
             }
@@ -302,7 +307,7 @@ tcgemm_kernel(const Params p) {
 #pragma unroll
             for (int i = 0; i < PATCH_ITERS; ++i) {
                 const int patch = gw + i * GROUP_WARPS;
-                if (patch < A_PATCHES) store_split(st, st + A_TILE, so[i], v[i]);
+                if (patch < A_PATCHES) { if (!((dead_mask >> i) & 1u)) store_split(st, st + A_TILE, so[i], v[i]); }
                 else if (patch < PATCHES) store_split(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, so[i], v[i]);
             }
             fence_async_smem();                                            // generic-proxy writes -> async proxy (UMMA)
@@ -371,7 +376,8 @@ tcgemm_kernel(const Params p) {
         const int q = warp & 3, part = warp >> 2;                          // TMEM lane quarter, column group
         constexpr int COLS_PER_PART = BN / (EPILOGUE_WARPS / 4);            // 96
         const int r = q * 32 + lane;
-        const int c_begin = part * COLS_PER_PART, c_end = min(c_begin + COLS_PER_PART, ncols);
+        const int c_begin = part * COLS_PER_PART;
+        const int c_end = (q * 32 < p.M - m0) ? min(c_begin + COLS_PER_PART, ncols) : c_begin;   // no output rows in this quarter
         for (int c0 = c_begin; c0 < c_end; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);   // whole warp, convergent

@@ -29,15 +29,17 @@ class KernelTimer:
         e.record()
         return e
 
-    def stop(self, e0, work: float) -> None:
+    def stop(self, e0, work: float, tag: str = "") -> None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        self.records.append((e0, e1, work))
+        self.records.append((e0, e1, work, tag))
 
-    def totals(self):
+    def totals(self, tag: Optional[str] = None):
+        """(milliseconds, work, launches) of all records, or of the records carrying `tag`."""
         torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b, _ in self.records)
-        return ms, sum(w for _, _, w in self.records), len(self.records)
+        recs = [r for r in self.records if tag is None or r[3] == tag]
+        ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
+        return ms, sum(w for _, _, w, _ in recs), len(recs)
 
 
 GEMM_TIMER = None
@@ -230,13 +232,14 @@ def bgemm(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB: bool =
         Mk, bk, sAk, sCk, sEk = batch * M, 1, 0, 0, 0
     timer = GEMM_TIMER
     e0 = timer.start() if timer is not None else None
-    fn = lib().gsr_tcgemm_f32 if _tc_ok(A, B, ac, bc, sAk, sB, Mk * bk) else lib().gsr_bgemm_f32
+    use_tc = _tc_ok(A, B, ac, bc, sAk, sB, Mk * bk)
+    fn = lib().gsr_tcgemm_f32 if use_tc else lib().gsr_bgemm_f32
     check(fn(A.data_ptr(), B.data_ptr(), out.data_ptr(), Mk, N, K, ac, bc, N,
              sAk, sB, sCk, int(transA), int(transB), bk, float(alpha),
              epi, extra.data_ptr() if extra is not None else None, ld_extra, sEk, _stream()),
           "gsr_bgemm_f32 / gsr_tcgemm_f32")
     if timer is not None:
-        timer.stop(e0, 2.0 * M * N * K * batch)
+        timer.stop(e0, 2.0 * M * N * K * batch, "tc" if use_tc else "simt")
     return out
 
 
@@ -273,7 +276,7 @@ def bgemm_reduce(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB:
              epi, extra.data_ptr() if extra is not None else None, N,
              ws.data_ptr(), splits.value, _stream()), "gsr_bgemm_reduce_f32 / gsr_tcgemm_reduce_f32")
     if timer is not None:
-        timer.stop(e0, 2.0 * M * N * K * batch)
+        timer.stop(e0, 2.0 * M * N * K * batch, "tc" if use_tc else "simt")
     return out
 
 

@@ -29,6 +29,8 @@ class GSRNet(nn.Module):
         self.net = GraphUnet(ks, self.lr_dim, self.hr_dim)
         self.gc1 = GraphConvolution(self.hr_dim, self.hidden_dim, 0, act=F.relu)
         self.gc2 = GraphConvolution(self.hidden_dim, self.hr_dim, 0, act=F.relu)
+        self.overlap_unet = True        # batched forward: U-Net on a side stream under the eigendecomposition
+        self._side_stream = None
 
     def forward(self, lr, U=None):
         lr = lr if lr.is_cuda else lr.to(device)
@@ -36,7 +38,23 @@ class GSRNet(nn.Module):
             raise RuntimeError("GSRNet: move the model to the GPU first (model.to('cuda')); there is no CPU path")
         I = torch.eye(self.lr_dim, device=lr.device)                                  # :24
         A = F_.normalize_adj(lr)                                                      # :25
-        self.net_outs, self.start_gcn_outs = self.net(A, I)                           # :27
+        if U is None and self.overlap_unet and lr.dim() == 3:
+            # The Graph U-Net depends on the weights only and the LR eigendecomposition on the data only:
+            # the ~25 small U-Net launches run on a side stream underneath the eigh kernels (autograd
+            # replays the same stream assignment in the backward pass).
+            main = torch.cuda.current_stream()
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream()
+            side = self._side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.net_outs, self.start_gcn_outs = self.net(A, I)                   # :27
+            self.layer.eig_val_lr, U, self.layer.eigh_info = F_.eigh(A, "U", check_errors=self.layer.check_eigh)   # layers.py:27
+            main.wait_stream(side)
+            self.net_outs.record_stream(main)
+            self.start_gcn_outs.record_stream(main)
+        else:
+            self.net_outs, self.start_gcn_outs = self.net(A, I)                       # :27
         self.outputs, self.Z = self.layer(A, self.net_outs, U=U)                      # :28
         self.hidden1 = self.gc1(self.Z, self.outputs)                                 # :29
         self.hidden2 = self.gc2(self.hidden1, self.outputs)                           # :30
