@@ -208,6 +208,96 @@ sym_diag_abs_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g
     }
 }
 
+// ---------------------------------------------------------------- sym / diag / abs, tile pairs
+// The outputs are symmetric functions of (x_ij, x_ji) (and (g_ij, g_ji)), so the natural unit of
+// work is the PAIR of 64 x 64 tiles (I, J), (J, I), I <= J: one 256-thread CTA loads both tiles
+// with float4 row segments (all loads of the CTA are issued before the first use), combines tile
+// (I, J) in registers against the transposed partner tile in padded shared memory, writes it, and
+// writes the mirror tile from a transposed read of the result.  15 pairs per 268 x 268 matrix
+// x 1024 subjects: enough independent CTAs (several per SM) to keep HBM busy, where the
+// one-CTA-per-matrix strip kernels above are bound by their own barriers (34-44 % of HBM).
+constexpr int kTS = 64;                 // tile edge
+constexpr int kTP = kTS + 1;            // padded pitch
+constexpr int kTileThreads = 256;       // thread (ty, tx): rows ty + 16 p (p < 4), columns 4 tx .. 4 tx + 3
+
+__device__ __forceinline__ void tile_pair_of(int pair, int T, int& I, int& J) {
+    I = 0;
+    while (pair >= T - I) { pair -= T - I; ++I; }       // row I of the upper triangle holds T - I pairs
+    J = I + pair;
+}
+__device__ __forceinline__ float4 ld4_masked(const float* __restrict__ base, int n, int row, int col) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n && col < n) v = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * n + col));   // n % 4 == 0: all or nothing
+    return v;
+}
+__device__ __forceinline__ void st_tile(float* t, int r, int c, float4 v) {
+    t[r * kTP + c] = v.x; t[r * kTP + c + 1] = v.y; t[r * kTP + c + 2] = v.z; t[r * kTP + c + 3] = v.w;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kTileThreads)
+sym_diag_abs_tiles_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ out, int n, int T) {
+    extern __shared__ float smem[];
+    float* bx = smem;                          // partner tile of x:  bx[jj][ii] = x[J0 + jj][I0 + ii]
+    float* res = smem + kTS * kTP;             // result tile (I, J)
+    float* bg = res + kTS * kTP;               // BWD: partner tile of g
+    const size_t base = (size_t)blockIdx.y * n * n;
+    x += base; out += base;
+    if (BWD) g += base;
+    int I, J;
+    tile_pair_of(blockIdx.x, T, I, J);
+    const int I0 = I * kTS, J0 = J * kTS;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float4 ax[4], pbx[4], ag[4], pbg[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int r = ty + 16 * p;
+        ax[p] = ld4_masked(x, n, I0 + r, J0 + 4 * tx);
+        pbx[p] = ld4_masked(x, n, J0 + r, I0 + 4 * tx);
+        if (BWD) { ag[p] = ld4_masked(g, n, I0 + r, J0 + 4 * tx); pbg[p] = ld4_masked(g, n, J0 + r, I0 + 4 * tx); }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        st_tile(bx, ty + 16 * p, 4 * tx, pbx[p]);
+        if (BWD) st_tile(bg, ty + 16 * p, 4 * tx, pbg[p]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int ii = ty + 16 * p, i = I0 + ii;
+        float a[4] = {ax[p].x, ax[p].y, ax[p].z, ax[p].w};
+        float ga[4] = {0.f, 0.f, 0.f, 0.f};
+        if (BWD) { ga[0] = ag[p].x; ga[1] = ag[p].y; ga[2] = ag[p].z; ga[3] = ag[p].w; }
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int jj = 4 * tx + u, j = J0 + jj;
+            const float z = (a[u] + bx[jj * kTP + ii]) / 2.0f;                  // (x + x^T) / 2
+            if (!BWD) {
+                o[u] = (i == j) ? 1.0f : fabsf(z);
+            } else {
+                const float sg = sgnf(z);
+                const float v = (ga[u] * sg + bg[jj * kTP + ii] * sg) / 2.0f;
+                o[u] = (i == j) ? 0.f : v;
+            }
+        }
+        const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+        if (i < n && J0 + 4 * tx < n) *reinterpret_cast<float4*>(out + (size_t)i * n + J0 + 4 * tx) = o4;
+        st_tile(res, ii, 4 * tx, o4);
+    }
+    if (I == J) return;                                                          // the diagonal tile is its own mirror
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int jj = ty + 16 * p, j = J0 + jj;                                // row of the mirror tile (J, I)
+        if (j < n && I0 + 4 * tx < n) {
+            const float4 o4 = make_float4(res[(4 * tx) * kTP + jj], res[(4 * tx + 1) * kTP + jj],
+                                          res[(4 * tx + 2) * kTP + jj], res[(4 * tx + 3) * kTP + jj]);
+            *reinterpret_cast<float4*>(out + (size_t)j * n + I0 + 4 * tx) = o4;
+        }
+    }
+}
+
 __global__ void abs_diag1_kernel(const float* __restrict__ x, float* __restrict__ out,
                                  long long total, int n) {
     const long long nn = (long long)n * n;
@@ -261,6 +351,11 @@ extern "C" int gsr_normalize_adj_bwd(const float* mx, const float* r, const floa
 extern "C" int gsr_sym_diag_abs_fwd(const float* x, float* out, int batch, int n, void* stream) {
     if (!x || !out || batch < 0 || n <= 0) return fail(GSR_E_ARG, "sym_diag_abs_fwd: bad argument");
     if (batch == 0) return 0;
+    if (n % 4 == 0 && aligned16(x) && aligned16(out) && batch <= 65535) {
+        const int T = (n + kTS - 1) / kTS;
+        sym_diag_abs_tiles_kernel<false><<<dim3(T * (T + 1) / 2, batch), kTileThreads, 2 * kTS * kTP * sizeof(float), (cudaStream_t)stream>>>(x, nullptr, out, n, T);
+        return launched("sym_diag_abs_fwd");
+    }
     const size_t smem = (size_t)n * kStripPad * sizeof(float);
     int rc = set_smem(sym_diag_abs_fwd_kernel, smem);
     if (rc) return fail(rc, "sym_diag_abs_fwd: n too large for one CTA");
@@ -272,6 +367,14 @@ extern "C" int gsr_sym_diag_abs_bwd(const float* x, const float* grad_out, float
                                     int batch, int n, void* stream) {
     if (!x || !grad_out || !grad_x || batch < 0 || n <= 0) return fail(GSR_E_ARG, "sym_diag_abs_bwd: bad argument");
     if (batch == 0) return 0;
+    if (n % 4 == 0 && aligned16(x) && aligned16(grad_out) && aligned16(grad_x) && batch <= 65535) {
+        const int T = (n + kTS - 1) / kTS;
+        const size_t tsmem = 3 * kTS * kTP * sizeof(float);
+        int rc2 = set_smem(sym_diag_abs_tiles_kernel<true>, tsmem);
+        if (rc2) return fail(rc2, "sym_diag_abs_bwd: cudaFuncSetAttribute failed");
+        sym_diag_abs_tiles_kernel<true><<<dim3(T * (T + 1) / 2, batch), kTileThreads, tsmem, (cudaStream_t)stream>>>(x, grad_out, grad_x, n, T);
+        return launched("sym_diag_abs_bwd");
+    }
     const size_t smem = 2 * (size_t)n * kStripPad * sizeof(float);
     int rc = set_smem(sym_diag_abs_bwd_kernel, smem);
     if (rc) return fail(rc, "sym_diag_abs_bwd: n too large for one CTA");
