@@ -35,6 +35,7 @@ constexpr int kThreads = 320;        // 289 compute threads, all 320 load
 int g_gemm_variant = 0;
 extern int g_eigh_oddeven;
 extern int g_eigh_max_polish;
+extern int g_eigh_ql_max_iter;
 
 struct GemmParams {
     const float* A; const float* B; float* C;
@@ -300,6 +301,7 @@ extern "C" int gsr_set_tuning(const char* key, int value) {
     if (!strcmp(key, "gemm_variant")) { gsr::g_gemm_variant = value; return 0; }
     if (!strcmp(key, "eigh_oddeven")) { gsr::g_eigh_oddeven = value; return 0; }
     if (!strcmp(key, "eigh_max_polish")) { gsr::g_eigh_max_polish = value; return 0; }
+    if (!strcmp(key, "eigh_ql_max_iter")) { gsr::g_eigh_ql_max_iter = value; return 0; }
     return fail(GSR_E_ARG, "set_tuning: unknown key");
 }
 

@@ -35,6 +35,7 @@
 #include "common.cuh"
 
 namespace gsr {
+int g_eigh_ql_max_iter = 30;    // gsr_set_tuning("eigh_ql_max_iter", k): QL iterations allowed per eigenvalue (EISPACK: 30)
 namespace tq {
 
 constexpr int MAXN = 160;
@@ -275,7 +276,7 @@ tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* _
 constexpr int K2_WARPS = 4;
 
 __global__ void __launch_bounds__(32 * K2_WARPS)
-tql_scalar_kernel(const Work wk, int n, int batch) {
+tql_scalar_kernel(const Work wk, int n, int batch, int max_iter) {
     __shared__ float sd[K2_WARPS][MAXN + 8], se[K2_WARPS][MAXN + 8];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int g = blockIdx.x * K2_WARPS + wl;
@@ -310,7 +311,7 @@ tql_scalar_kernel(const Work wk, int n, int batch) {
             const int lo = l & ~15, hi = (m + 15) & ~15;
             int j = 0;
             while (true) {
-                if (++j > 30) { status = 2; break; }
+                if (++j > max_iter) { status = 2; break; }
                 if (pos + (hi - lo) > wk.cap - BLK || nit >= wk.hdr_cap) { status = 3; break; }
                 // Wilkinson shift
                 const float g0 = d[l], el = e[l];
@@ -616,7 +617,7 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
     int rc = launched("eigh_tridiag");
     if (rc) return rc;
 
-    tq::tql_scalar_kernel<<<(batch + tq::K2_WARPS - 1) / tq::K2_WARPS, 32 * tq::K2_WARPS, 0, st>>>(wk, n, batch);
+    tq::tql_scalar_kernel<<<(batch + tq::K2_WARPS - 1) / tq::K2_WARPS, 32 * tq::K2_WARPS, 0, st>>>(wk, n, batch, g_eigh_ql_max_iter);
     rc = launched("eigh_tql_scalar");
     if (rc) return rc;
 

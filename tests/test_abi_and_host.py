@@ -30,7 +30,7 @@ def header_symbols():
 def test_header_declares_the_path():
     syms = header_symbols()
     assert len(syms) >= 30
-    for must in ("gsr_eigh_jacobi_f32", "gsr_bgemm_f32", "gsr_normalize_adj_fwd", "gsr_vectorize",
+    for must in ("gsr_eigh_jacobi_f32", "gsr_eigh_tridiag_f32", "gsr_tcgemm_f32", "gsr_bgemm_f32", "gsr_normalize_adj_fwd", "gsr_vectorize",
                  "gsr_anti_vectorize", "gsr_pool_topk", "gsr_l1_loss_fwd", "gsr_eval_reduce", "gsr_flat_pack"):
         assert must in syms
 
@@ -47,6 +47,10 @@ def test_library_loads_and_exports_every_declared_symbol(pkg):
     assert lib.gsr_l1_partials(268 * 268) >= 1
     assert lib.gsr_eval_workspace() > 0
     assert lib.gsr_eigh_workspace(4, 160) == 0 and lib.gsr_eigh_workspace(4, 268) == 4 * 268 * 292
+    # tridiagonal route: n <= 160 only, workspace grows linearly with the batch
+    assert lib.gsr_eigh_tridiag_workspace(4, 161) == 0 and lib.gsr_eigh_tridiag_workspace(0, 160) == 0
+    w1, w8 = lib.gsr_eigh_tridiag_workspace(1, 160), lib.gsr_eigh_tridiag_workspace(8, 160)
+    assert w1 > 2 * 160 * 160 * 8 and 7 * w1 < w8 <= 8 * w1
     assert lib.gsr_launch_count() == 0           # nothing may launch on a CPU-only box
 
 
@@ -61,6 +65,8 @@ def test_bad_arguments_are_rejected_without_a_gpu(pkg):
     assert lib.gsr_normalize_adj_fwd(None, None, None, None, 1, 4, 0, None) == -1
     assert b"normalize_adj_fwd" in lib.gsr_last_error()
     assert lib.gsr_eigh_jacobi_f32(None, None, None, None, None, 1, 4, 1, 0.0, 0, None) == -1
+    assert lib.gsr_eigh_tridiag_f32(None, None, None, None, None, 0, 1, 4, 1, None) == -1
+    assert b"eigh_tridiag" in lib.gsr_last_error()
     assert lib.gsr_set_tuning(b"no_such_knob", 1) == -1
 
 

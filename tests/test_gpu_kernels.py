@@ -264,6 +264,75 @@ def test_eigh_error_contract(cuda_pkg):
         cuda_pkg.kernels.eigh_jacobi(torch.zeros(1, 400, 400, device="cuda"))      # too large: loud, no fallback
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 7, 16, 17, 33, 96, 128, 159, 160])
+def test_eigh_both_routes_agree(cuda_pkg, n):
+    """n <= 160: the tridiagonal-QL kernels (default route) and the Jacobi kernel decompose the same
+    matrices; both are held to the float64 properties and their eigenvalues to each other."""
+    K = cuda_pkg.kernels
+    A = torch.stack([O.normalize_adj(O.synth_connectome(n, 900 + s)) if n > 1 else torch.tensor([[-0.3]])
+                     for s in range(5)]).cuda()
+    wt, Ut, it = K.eigh_tridiag(A)
+    wj, Uj, ij = K.eigh_jacobi(A)
+    assert int(it.min()) > 0 and int(ij.min()) > 0
+    assert torch.allclose(wt, wj, rtol=0, atol=3e-6)
+    for b in range(5):
+        _eigh_checks(A[b].cpu(), wt[b].cpu(), Ut[b].cpu(), tol_w=3e-6, tol_res=5e-6, tol_orth=1e-5)
+    assert cuda_pkg.kernels.eigh(A)[2].equal(it)                       # "auto" = tridiagonal route up to 160 nodes
+    with pytest.raises(ValueError):
+        K.eigh_tridiag(torch.zeros(1, 161, 161, device="cuda"))
+
+
+@pytest.mark.gpu
+def test_eigh_ql_failure_falls_back_to_jacobi(cuda_pkg):
+    """info = -2 (QL gave up) is not an error for functional.eigh: those graphs are redone by the
+    Jacobi kernel.  The failure is provoked by allowing one QL iteration per eigenvalue."""
+    F_, K = cuda_pkg.functional, cuda_pkg.kernels
+    A = torch.stack([O.normalize_adj(O.synth_connectome(64, 40 + s)) for s in range(4)]).cuda()
+    cuda_pkg.set_tuning("eigh_ql_max_iter", 1)
+    try:
+        w, U, info = K.eigh_tridiag(A)
+        assert int(info.max()) == -2 and bool(torch.isnan(U).all())          # raw kernel contract
+        w, U, info = F_.eigh(A)                                               # wrapper: transparent fallback
+    finally:
+        cuda_pkg.set_tuning("eigh_ql_max_iter", 30)
+    assert int(info.min()) > 0
+    for b in range(4):
+        _eigh_checks(A[b].cpu(), w[b].cpu(), U[b].cpu())
+
+
+@pytest.mark.gpu
+def test_eigh_tridiag_special_matrices(cuda_pkg):
+    """Zero, identity multiples, rank one, repeated eigenvalues, tiny and huge scales (the kernel
+    rescales by an exact power of two), diagonal input, and the NaN contract."""
+    K = cuda_pkg.kernels
+    dev = "cuda"
+    w, U, info = K.eigh_tridiag(torch.zeros(2, 40, 40, device=dev))
+    assert float(w.abs().max()) == 0.0 and torch.equal(U, torch.eye(40, device=dev).expand(2, 40, 40)) and int(info.min()) > 0
+    w, U, info = K.eigh_tridiag(3.0 * torch.eye(24, device=dev)[None])
+    assert torch.equal(w, torch.full((1, 24), 3.0, device=dev))
+    ones = torch.ones(1, 64, 64, device=dev)
+    w, U, _ = K.eigh_tridiag(ones)
+    _eigh_checks(ones[0].cpu(), w[0].cpu(), U[0].cpu(), tol_w=3e-6, tol_res=1e-5)          # eigenvalues 0 (x63) and 64
+    g = torch.Generator().manual_seed(5)
+    M = torch.randn(3, 80, 80, generator=g)
+    A = (M + M.transpose(1, 2)) / 2
+    for scale in (1e-20, 1.0, 1e18):
+        w, U, info = K.eigh_tridiag((A * scale).cuda())
+        assert int(info.min()) > 0
+        for b in range(3):
+            _eigh_checks(A[b] * scale, w[b].cpu(), U[b].cpu(), tol_w=4e-6, tol_res=2e-5)
+    D = torch.diag(torch.tensor([3.0, -1.0, 2.0, 2.0, 0.0, 5.0]))[None].cuda()
+    w, U, _ = K.eigh_tridiag(D)
+    assert torch.equal(w.cpu(), torch.tensor([[-1.0, 0.0, 2.0, 2.0, 3.0, 5.0]]))
+    assert torch.equal(U.abs().cpu()[0], torch.eye(6)[:, [1, 4, 2, 3, 0, 5]])
+    bad = O.normalize_adj(O.synth_connectome(48, 3)).repeat(3, 1, 1)
+    bad[1, 0, 7] = float("inf")
+    w, U, info = K.eigh_tridiag(bad.cuda())
+    assert info.tolist()[1] == -1 and info.tolist()[0] > 0 and info.tolist()[2] > 0
+    assert bool(torch.isnan(U[1]).all()) and bool(torch.isnan(w[1]).all()) and not bool(torch.isnan(U[[0, 2]]).any())
+
+
 def test_eigh_full_batch_properties(cuda_pkg):
     """BASELINE size: 1024 normalised 160-node graphs; size-independent properties."""
     F_ = cuda_pkg.functional
