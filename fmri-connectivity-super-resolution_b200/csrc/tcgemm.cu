@@ -59,6 +59,16 @@ struct Params {
 
 int g_mn_swap = 0;      // bring-up knob (unused)
 
+#ifdef GSR_TC_TRACE
+// Pipeline trace (tools/tc_trace.py builds a private copy of the library with -DGSR_TC_TRACE):
+// one CTA stamps %globaltimer at its pipeline events; slot layout [role][k-block][event].
+__device__ unsigned long long g_trace[4 * 16 * 8];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TC_STAMP(role, kb, ev) do { if (blockIdx.x == 1 && blockIdx.z == 7 && (kb) < 16) g_trace[((role) * 16 + (kb)) * 8 + (ev)] = gtime(); } while (0)
+#else
+#define TC_STAMP(role, kb, ev) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -284,6 +294,7 @@ tcgemm_kernel(const Params p) {
             const float* A = p.A + (size_t)b * p.sA;
             const float* B = p.B + (size_t)b * p.sB;
             float4 v[PATCH_ITERS];
+            if (gw == 0 && lane == 0) TC_STAMP(grp, it, 0);                 // loads issued from here
             if ((kb + 1) * BK <= p.K) {                                    // whole k-block inside K: no k predicates
 #pragma unroll
                 for (int i = 0; i < PATCH_ITERS; ++i) {
@@ -303,14 +314,21 @@ tcgemm_kernel(const Params p) {
                     else if (patch < PATCHES) v[i] = load_patch<BN, TB>(B, p.ldb, p.N, p.K, n0, kb * BK, patch - A_PATCHES, lane, dummy);
                 }
             }
+            if (gw == 0 && lane == 0) TC_STAMP(grp, it, 1);                 // loads in flight, waiting for the stage
             if (use > 0) mbar_wait(bar_empty + 8 * grp, (use - 1) & 1);    // MMA has drained this stage
+            if (gw == 0 && lane == 0) TC_STAMP(grp, it, 2);                 // stage free
+#ifdef GSR_TC_TRACE
+            if (gw == 0 && lane == 0) { volatile float sink = v[PATCH_ITERS - 1].x + v[0].x; (void)sink; TC_STAMP(grp, it, 3); }   // loads landed
+#endif
 #pragma unroll
             for (int i = 0; i < PATCH_ITERS; ++i) {
                 const int patch = gw + i * GROUP_WARPS;
                 if (patch < A_PATCHES) { if (!((dead_mask >> i) & 1u)) store_split(st, st + A_TILE, so[i], v[i]); }
                 else if (patch < PATCHES) store_split(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, so[i], v[i]);
             }
+            if (gw == 0 && lane == 0) TC_STAMP(grp, it, 4);                 // split + stores issued
             fence_async_smem();                                            // generic-proxy writes -> async proxy (UMMA)
+            if (gw == 0 && lane == 0) TC_STAMP(grp, it, 5);                 // fence done
             mbar_arrive(bar_full + 8 * grp);
         }
     } else {
@@ -340,7 +358,9 @@ tcgemm_kernel(const Params p) {
             uint32_t acc = 0;                                                 // 0 only for the very first k-step
             for (int it = 0; it < total_kb; ++it) {
                 const int s = it % STAGES, use = it / STAGES;
+                TC_STAMP(2, it, 0);                                          // MMA thread waits for the stage
                 mbar_wait(bar_full + 8 * s, use & 1);
+                TC_STAMP(2, it, 1);                                          // stage full
                 tc_fence_after();
                 uint32_t ah = base_lo[s][0], al = base_lo[s][1], bh = base_lo[s][2], bl = base_lo[s][3];
 #pragma unroll
@@ -357,6 +377,7 @@ tcgemm_kernel(const Params p) {
                     ah += a_step; al += a_step; bh += b_step; bl += b_step;
                 }
                 umma_commit(bar_empty + 8 * s);                              // stage free once these MMAs retire
+                TC_STAMP(2, it, 2);                                          // MMAs issued + committed
             }
             umma_commit(bar_accum);                                          // accumulator complete
         }
@@ -455,6 +476,11 @@ extern "C" __attribute__((visibility("default"))) int gsr_tcgemm_debug(int key, 
     if (key == 0) tc::g_mn_swap = value;
     return 0;
 }
+#ifdef GSR_TC_TRACE
+extern "C" __attribute__((visibility("default"))) int gsr_tcgemm_trace_read(unsigned long long* host, int count) {
+    return (int)cudaMemcpyFromSymbol(host, tc::g_trace, sizeof(unsigned long long) * count);
+}
+#endif
 
 extern "C" int gsr_tcgemm_supported(int M, int N, int K, int lda, int ldb) {
     return (M > 0 && N > 0 && K > 0 && lda % 4 == 0 && ldb % 4 == 0) ? 1 : 0;
