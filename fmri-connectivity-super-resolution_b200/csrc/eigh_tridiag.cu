@@ -277,17 +277,17 @@ constexpr int K2_WARPS = 4;
 
 __global__ void __launch_bounds__(32 * K2_WARPS)
 tql_scalar_kernel(const Work wk, int n, int batch, int max_iter) {
-    __shared__ float sd[K2_WARPS][MAXN + 8], se[K2_WARPS][MAXN + 8];
+    __shared__ float sd[K2_WARPS][MAXN + 16], se[K2_WARPS][MAXN + 16];      // [8] pad | n values | pad: index -1 is readable
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int g = blockIdx.x * K2_WARPS + wl;
     if (g >= batch) return;
     int* cnt = wk.counts + 4 * g;
     if (cnt[2] == -1) return;                       // non-finite input (K1 wrote the outputs)
-    float* d = sd[wl];
-    float* e = se[wl];
-    for (int j = lane; j < n + 8; j += 32) {
-        d[j] = (j < n) ? wk.d[(size_t)g * n + j] : 0.f;
-        e[j] = (j < n - 1) ? wk.e[(size_t)g * n + j] : 0.f;
+    float* d = sd[wl] + 8;
+    float* e = se[wl] + 8;
+    for (int j = lane - 8; j < n + 8; j += 32) {
+        d[j] = (j >= 0 && j < n) ? wk.d[(size_t)g * n + j] : 0.f;
+        e[j] = (j >= 0 && j < n - 1) ? wk.e[(size_t)g * n + j] : 0.f;
     }
     __syncwarp();
     float2* out = wk.stream + (size_t)g * wk.cap;
@@ -331,12 +331,11 @@ tql_scalar_kernel(const Work wk, int n, int batch, int max_iter) {
                 if (lane == 0) {
                     hdr[nit] = (uint32_t)(lo >> 4) | ((uint32_t)(hi >> 4) << 8);
                     o += hi - m;
-                    float p = d[m], c = 1.0f, c2 = 1.0f, c3 = 1.0f, s = 0.0f, s2 = 0.0f;
+                    float p = d[m], c = 1.0f, s = 0.0f;
                     const float el1 = e[l + 1];
                     float ei = e[m - 1], di = d[m - 1];
                     for (int q = m - 1; q >= l; --q) {
-                        const float ein = e[q > 0 ? q - 1 : 0], din = d[q > 0 ? q - 1 : 0];     // next rotation's operands
-                        c3 = c2; c2 = c; s2 = s;
+                        const float ein = e[q - 1], din = d[q - 1];             // next rotation's operands (index -1 is padding)
                         const float gg = c * ei, hh = c * p;
                         const float x = fmaf(p, p, ei * ei);
                         // (c, s) = (p, e_i) / r with one MUFU: c0, s0 share the relative error of
@@ -346,9 +345,8 @@ tql_scalar_kernel(const Work wk, int n, int batch, int max_iter) {
                         float rinv;
                         asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(x));
                         const float c0 = p * rinv, s0 = ei * rinv, xr = x * rinv;
-                        const float delta = fmaf(-c0, c0, fmaf(-s0, s0, 1.0f));
-                        float cn = fmaf(0.5f * c0, delta, c0), sn = fmaf(0.5f * s0, delta, s0);
-                        float r = fmaf(0.5f * xr, delta, xr);
+                        const float hd = 0.5f * fmaf(-c0, c0, fmaf(-s0, s0, 1.0f));
+                        float cn = fmaf(c0, hd, c0), sn = fmaf(s0, hd, s0), r = fmaf(xr, hd, xr);
                         if (x < 1.17549435e-38f) { r = 0.f; cn = 1.0f; sn = 0.0f; }       // p = e_i = 0 (to fp32 range): identity
                         e[q + 1] = s * r;
                         s = sn; c = cn;
@@ -357,6 +355,11 @@ tql_scalar_kernel(const Work wk, int n, int batch, int max_iter) {
                         *o++ = make_float2(c, s);
                         ei = ein; di = din;
                     }
+                    // tql2's closing step needs s of the previous and c of the one-before-previous rotation:
+                    // read back from the stream just written (same thread) instead of carrying them through the loop
+                    const int cnt = m - l;
+                    const float s2 = cnt >= 2 ? o[-2].y : 0.0f;
+                    const float c3 = cnt >= 3 ? o[-3].x : 1.0f;
                     p = -s * s2 * c3 * el1 * e[l] / dl1;
                     e[l] = s * p;
                     d[l] = c * p;
