@@ -389,7 +389,8 @@ tcgemm_kernel(const Params p) {
     // global memory would scatter 16-byte pieces over 32 rows per instruction.  The tile is
     // staged row-major in the (now idle) operand buffers with an odd pitch (conflict-free both
     // ways) and written out by all warps as full, coalesced rows.
-    constexpr int CPITCH = BN + 1;                                          // 289 floats
+    constexpr int CPITCH = BN + 4;                                          // 292 floats: float4 aligned, 4 (mod 32) -> a quarter
+                                                                            // warp of row-owning lanes hits 32 distinct banks
     float* Cs = reinterpret_cast<float*>(smem);
     if (warp < EPILOGUE_WARPS) {
         mbar_wait(bar_accum, 0);
@@ -403,7 +404,8 @@ tcgemm_kernel(const Params p) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);   // whole warp, convergent
 #pragma unroll
-            for (int i = 0; i < 32; ++i) Cs[r * CPITCH + c0 + i] = __uint_as_float(v[i]);
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<uint4*>(Cs + r * CPITCH + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
     }
     tc_fence_before();
@@ -417,6 +419,26 @@ tcgemm_kernel(const Params p) {
         const int rows = min(BM, p.M - m0), cols = min(BN, p.N - n0);
         const int epi = REDUCE ? GSR_EPI_NONE : p.epilogue;
         const float alpha = REDUCE ? 1.0f : p.alpha;
+        const bool vec = ((cols & 3) == 0) && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0) &&
+                         (epi == GSR_EPI_NONE || ((reinterpret_cast<uintptr_t>(p.extra) & 15u) == 0 &&
+                                                  (epi != GSR_EPI_ADD || ((p.ld_extra & 3) == 0 && (p.s_extra & 3) == 0))));
+        if (vec) {
+            // float4 per thread over the flattened (row, 4-column group) space: full 16-byte stores, rows stay contiguous
+            const int c4n = cols >> 2;
+            for (int e = tid; e < rows * c4n; e += THREADS) {
+                const int r = e / c4n, c = (e - r * c4n) << 2;
+                float4 v = *reinterpret_cast<const float4*>(Cs + r * CPITCH + c);
+                v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
+                if (epi == GSR_EPI_BIAS) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.extra + n0 + c));
+                    v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                } else if (epi == GSR_EPI_ADD) {
+                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(extra + (size_t)(m0 + r) * p.ld_extra + n0 + c));
+                    v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+                }
+                *reinterpret_cast<float4*>(C + (size_t)(m0 + r) * ldc + n0 + c) = v;
+            }
+        } else {
         for (int r = warp; r < rows; r += PRODUCER_WARPS + 1) {
             const float* src = Cs + r * CPITCH;
             float* dst = C + (size_t)(m0 + r) * ldc + n0;
@@ -426,6 +448,7 @@ tcgemm_kernel(const Params p) {
                 else if (epi == GSR_EPI_ADD) v += __ldg(extra + (size_t)(m0 + r) * p.ld_extra + n0 + c);
                 dst[c] = v;
             }
+        }
         }
     }
     tc_fence_before();
