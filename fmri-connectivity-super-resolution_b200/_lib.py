@@ -61,6 +61,7 @@ PROTOTYPES = {
     "gsr_vectorize_len": (i64, [i32, i32]),
     "gsr_vectorize": (i32, [c_ptr, c_ptr, i32, i32, i32, i32, c_ptr]),
     "gsr_anti_vectorize": (i32, [c_ptr, c_ptr, i32, i32, i64, i32, c_ptr]),
+    "gsr_triu_flatten": (i32, [c_ptr, c_ptr, i32, i32, c_ptr]),
     "gsr_eval_workspace": (C.c_size_t, []),
     "gsr_eval_reduce": (i32, [c_ptr, c_ptr, i64, i32, i32, c_ptr, c_ptr, c_ptr]),
     "gsr_flat_pack": (i32, [c_ptr, c_ptr, i32, c_ptr, i64, f32, c_ptr]),

@@ -58,6 +58,26 @@ anti_vectorize_kernel(const float* __restrict__ vec, float* __restrict__ out, in
     }
 }
 
+// training_gsr.ipynb:112-121 (submission): matrix[np.triu_indices(n, k=1)] -- the strict upper triangle in
+// ROW-major order, the exact inverse of anti_vectorize's fill.  Element t of the output is (r, c) with
+// t = r n - r (r + 1) / 2 + (c - r - 1); one thread per output element (coalesced writes, the reads of one
+// matrix row are contiguous), r recovered from t with a float estimate fixed up exactly in integers.
+__global__ void __launch_bounds__(256)
+triu_flatten_kernel(const float* __restrict__ M, float* __restrict__ out, int n, long long n_el) {
+    const float* Mb = M + (size_t)blockIdx.y * n * n;
+    float* ob = out + (size_t)blockIdx.y * n_el;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_el; t += (long long)gridDim.x * blockDim.x) {
+        // rows before r hold S(r) = r n - r (r + 1) / 2 elements; largest r with S(r) <= t
+        const double nn = 2.0 * n - 1.0;
+        int r = (int)((nn - sqrt(nn * nn - 8.0 * (double)t)) * 0.5);
+        r = max(0, min(r, n - 2));
+        while (r > 0 && (long long)r * n - (long long)r * (r + 1) / 2 > t) --r;
+        while ((long long)(r + 1) * n - (long long)(r + 1) * (r + 2) / 2 <= t) ++r;
+        const int c = (int)(t - ((long long)r * n - (long long)r * (r + 1) / 2)) + r + 1;
+        ob[t] = Mb[(size_t)r * n + c];
+    }
+}
+
 template <typename T>
 static int launch_vectorize(const void* M, void* out, int batch, int n, int diag, cudaStream_t st) {
     const int tiles = (n + 31) / 32;
@@ -105,4 +125,14 @@ extern "C" int gsr_anti_vectorize(const float* vec, float* out, int batch, int n
     const int bx = (int)min((long long)64, (total + 255) / 256);
     anti_vectorize_kernel<<<dim3(bx, batch), 256, 0, (cudaStream_t)stream>>>(vec, out, n, vec_len, include_diagonal ? 1 : 0);
     return launched("anti_vectorize");
+}
+
+extern "C" int gsr_triu_flatten(const float* matrix, float* out, int batch, int n, void* stream) {
+    if (!matrix || !out || batch < 0 || n <= 0) return fail(GSR_E_ARG, "triu_flatten: bad argument");
+    if (batch == 0 || n == 1) return 0;
+    if (batch > 65535) return fail(GSR_E_UNSUPPORTED, "triu_flatten: batch > 65535");
+    const long long n_el = (long long)n * (n - 1) / 2;
+    const int bx = (int)min((long long)64, (n_el + 255) / 256);
+    triu_flatten_kernel<<<dim3(bx, batch), 256, 0, (cudaStream_t)stream>>>(matrix, out, n, n_el);
+    return launched("triu_flatten");
 }

@@ -447,6 +447,16 @@ def anti_vectorize(vec: torch.Tensor, n: int, include_diagonal: bool = False) ->
     return out
 
 
+def triu_flatten(matrix: torch.Tensor) -> torch.Tensor:
+    """matrix[np.triu_indices(n, k=1)] for every matrix of the batch (row-major strict upper triangle)."""
+    matrix = _f32(matrix, "triu_flatten: matrix")
+    batch, n = _square_batch(matrix, "triu_flatten: matrix")
+    out = torch.empty(matrix.shape[:-2] + (n * (n - 1) // 2,), device=matrix.device, dtype=torch.float32)
+    if out.numel():
+        check(lib().gsr_triu_flatten(matrix.data_ptr(), out.data_ptr(), batch, n, _stream()), "gsr_triu_flatten")
+    return out
+
+
 # --------------------------------------------------------------------- evaluation
 def eval_reduce(pred: torch.Tensor, gt: torch.Tensor, upper: bool) -> torch.Tensor:
     """Returns a device fp64 tensor [mae, pcc, js_distance]."""

@@ -221,6 +221,11 @@ GSR_API int gsr_vectorize(const void* matrix, void* out, int batch, int n, int e
  * the reference's assert (checked on the host side as well).                     */
 GSR_API int gsr_anti_vectorize(const float* vec, float* out, int batch, int n, long long vec_len,
                        int include_diagonal, void* stream);
+/* training_gsr.ipynb:112-121 (submission file)  matrix[np.triu_indices(n, k=1)]: the strict upper
+ * triangle in ROW-major order (the inverse of anti_vectorize's fill; utils/data.py:214-231 writes
+ * the COLUMN-major gsr_vectorize order instead).  out: [batch, n(n-1)/2] fp32.                  */
+GSR_API int gsr_triu_flatten(const float* matrix, float* out, int batch, int n, void* stream);
+
 
 /* ------------------------------------------------------------------ a18
  * utils/evaluation.py:96-112  MAE, Pearson r, Jensen-Shannon distance over the

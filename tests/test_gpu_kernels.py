@@ -12,6 +12,7 @@ import pytest
 import torch
 
 from oracle import gsr_oracle as O
+from oracle import vectorizer_oracle as O_vec
 from oracle import vectorizer_oracle as VO
 
 pytestmark = pytest.mark.gpu
@@ -584,3 +585,42 @@ def test_eval_reductions_zero_entries(cuda_pkg):
     mae, pcc, js = cuda_pkg.evaluation_reductions(pred.numpy(), gt.numpy())
     m2, p2, j2 = VO.eval_reductions(pred.numpy(), gt.numpy())
     assert mae == pytest.approx(m2, rel=1e-12) and pcc == pytest.approx(p2, rel=1e-9) and js == pytest.approx(j2, rel=1e-9)
+
+
+# ------------------------------------------------------------------ N4: the on-disk edge
+@pytest.mark.parametrize("n", [2, 3, 5, 33, 160, 268])
+def test_triu_flatten_is_numpy_triu_indices(cuda_pkg, n):
+    """training_gsr.ipynb:112-117: bit exact against matrix[np.triu_indices(n, k=1)], batched."""
+    g = torch.Generator().manual_seed(n)
+    M = torch.randn(3, n, n, generator=g)
+    got = cuda_pkg.kernels.triu_flatten(M.cuda()).cpu().numpy()
+    iu = np.triu_indices(n, k=1)
+    for b in range(3):
+        assert np.array_equal(got[b], M[b].numpy()[iu])
+    # inverse of anti_vectorize on symmetric zero-diagonal matrices
+    v = torch.randn(2, n * (n - 1) // 2, generator=g).cuda()
+    assert torch.equal(cuda_pkg.kernels.triu_flatten(cuda_pkg.kernels.anti_vectorize(v, n)), v)
+
+
+def test_submission_edge(cuda_pkg, tmp_path):
+    """extract_data's NaN rule + anti-vectorise (utils/preprocessing.py:60-75) and both submission orders."""
+    from importlib import import_module
+    sub = import_module(cuda_pkg.__name__ + ".utils.submission")
+    rng = np.random.default_rng(0)
+    rows = rng.random((4, 12720))
+    rows[1, 5] = np.nan
+    mats = sub.extract_matrices(rows, is_hr=False)
+    assert mats.shape == (4, 160, 160) and mats.dtype == np.float64
+    ref = np.stack([O_vec.anti_vectorize(np.nan_to_num(r, nan=0.0).astype(np.float32), 160) for r in rows])
+    assert np.array_equal(mats, ref.astype(np.float64))
+    preds = rng.random((3, 268, 268)).astype(np.float32)
+    row = sub.submission_vector(preds, "row")
+    col = sub.submission_vector(preds, "column")
+    iu = np.triu_indices(268, k=1)
+    assert np.array_equal(row, np.concatenate([p[iu] for p in preds]))
+    assert np.array_equal(col, np.concatenate([O_vec.vectorize(p) for p in preds]))
+    path = tmp_path / "submission.csv"
+    assert sub.write_submission(str(path), row[:5]) == 5
+    lines = path.read_text().splitlines()
+    assert lines[0] == "ID,Predicted" and lines[1].startswith("1,") and len(lines) == 6
+    assert float(lines[3].split(",")[1]) == float(row[2])
