@@ -29,6 +29,8 @@ PROTOTYPES = {
     "gsr_set_tuning": (i32, [C.c_char_p, i32]),
     "gsr_normalize_adj_fwd": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, c_ptr]),
     "gsr_normalize_adj_bwd": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, c_ptr]),
+    "gsr_normalize_adj_bwd_workspace": (C.c_size_t, [i32, i32]),
+    "gsr_normalize_adj_bwd_tiles": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, c_ptr]),
     "gsr_eigh_workspace": (C.c_size_t, [i32, i32]),
     "gsr_eigh_jacobi_f32": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, f32, i32, c_ptr]),
     "gsr_eigh_tridiag_workspace": (C.c_size_t, [i32, i32]),

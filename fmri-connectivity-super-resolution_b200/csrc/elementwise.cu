@@ -298,6 +298,250 @@ sym_diag_abs_tiles_kernel(const float* __restrict__ x, const float* __restrict__
     }
 }
 
+// ---------------------------------------------------------------- normalise, tile pairs
+// Same decomposition as sym_diag_abs_tiles_kernel for utils/preprocessing.py:16-25 and its autograd:
+//   fwd   rowsum kernel (warp per row, float4) -> r;  tile-pair kernel: out(I,J) = r_i r_j M(J,I)^T and its mirror
+//   bwd   pass 1 (tile pairs): S = T(I,J) .* M(J,I)^T + T(J,I)^T .* M(I,J); partial sums S r over the tile go to
+//         a [batch][tiles][n] workspace slot written by exactly one CTA (deterministic); a small kernel folds the
+//         slots into drho;  pass 2 (tile pairs): dM(I,J) = r_i r_j T(J,I)^T + drho_i (x sgn(mx), zero diagonal if PRE)
+template <int PRE>
+__global__ void __launch_bounds__(256)
+normalize_rowsum_kernel(const float* __restrict__ mx, float* __restrict__ r_out, float* __restrict__ m_out, int n) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const size_t base = (size_t)blockIdx.y * n * n + (size_t)i * n;
+    float acc = 0.f;
+    for (int c = lane; c < (n >> 2); c += 32) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(mx + base) + c);
+        v.x = pre_value<PRE>(v.x, i, 4 * c); v.y = pre_value<PRE>(v.y, i, 4 * c + 1);
+        v.z = pre_value<PRE>(v.z, i, 4 * c + 2); v.w = pre_value<PRE>(v.w, i, 4 * c + 3);
+        if (m_out) reinterpret_cast<float4*>(m_out + base)[c] = v;
+        acc += (v.x + v.y) + (v.z + v.w);
+    }
+    acc = warp_sum(acc);
+    float ri = 1.0f / sqrtf(acc);          // pow(rowsum, -0.5)
+    if (isinf(ri)) ri = 0.f;
+    if (lane == 0) r_out[(size_t)blockIdx.y * n + i] = ri;
+}
+
+template <int PRE>
+__device__ __forceinline__ float4 ld4_pre(const float* __restrict__ base, int n, int row, int col) {
+    float4 v = ld4_masked(base, n, row, col);
+    if (PRE) {
+        v.x = pre_value<1>(v.x, row, col); v.y = pre_value<1>(v.y, row, col + 1);
+        v.z = pre_value<1>(v.z, row, col + 2); v.w = pre_value<1>(v.w, row, col + 3);
+        if (row >= n || col >= n) v = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return v;
+}
+
+template <int PRE>
+__global__ void __launch_bounds__(kTileThreads)
+normalize_scale_tiles_kernel(const float* __restrict__ mx, const float* __restrict__ r, float* __restrict__ out, int n, int T) {
+    extern __shared__ float smem[];
+    float* ta = smem;                          // ta[ii][jj] = M[I0 + ii][J0 + jj]
+    float* tb = smem + kTS * kTP;              // tb[jj][ii] = M[J0 + jj][I0 + ii]
+    float* rI = tb + kTS * kTP;                // [64]
+    float* rJ = rI + kTS;                      // [64]
+    const size_t base = (size_t)blockIdx.y * n * n;
+    mx += base; out += base;
+    r += (size_t)blockIdx.y * n;
+    int I, J;
+    tile_pair_of(blockIdx.x, T, I, J);
+    const int I0 = I * kTS, J0 = J * kTS;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float4 va[4], vb[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        va[p] = ld4_pre<PRE>(mx, n, I0 + ty + 16 * p, J0 + 4 * tx);
+        vb[p] = ld4_pre<PRE>(mx, n, J0 + ty + 16 * p, I0 + 4 * tx);
+    }
+    if (threadIdx.x < kTS) rI[threadIdx.x] = (I0 + threadIdx.x < n) ? r[I0 + threadIdx.x] : 0.f;
+    else if (threadIdx.x < 2 * kTS) rJ[threadIdx.x - kTS] = (J0 + threadIdx.x - kTS < n) ? r[J0 + threadIdx.x - kTS] : 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { st_tile(ta, ty + 16 * p, 4 * tx, va[p]); st_tile(tb, ty + 16 * p, 4 * tx, vb[p]); }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int ii = ty + 16 * p, i = I0 + ii;
+        if (i < n && J0 + 4 * tx < n) {                          // out[i][j] = (M[j][i] r_i) r_j
+            const float ri = rI[ii];
+            float4 o;
+            o.x = (tb[(4 * tx) * kTP + ii] * ri) * rJ[4 * tx];
+            o.y = (tb[(4 * tx + 1) * kTP + ii] * ri) * rJ[4 * tx + 1];
+            o.z = (tb[(4 * tx + 2) * kTP + ii] * ri) * rJ[4 * tx + 2];
+            o.w = (tb[(4 * tx + 3) * kTP + ii] * ri) * rJ[4 * tx + 3];
+            *reinterpret_cast<float4*>(out + (size_t)i * n + J0 + 4 * tx) = o;
+        }
+        if (I != J) {
+            const int jj = ty + 16 * p, j = J0 + jj;
+            if (j < n && I0 + 4 * tx < n) {                      // mirror tile: out[j][i] = (M[i][j] r_j) r_i
+                const float rj = rJ[jj];
+                float4 o;
+                o.x = (ta[(4 * tx) * kTP + jj] * rj) * rI[4 * tx];
+                o.y = (ta[(4 * tx + 1) * kTP + jj] * rj) * rI[4 * tx + 1];
+                o.z = (ta[(4 * tx + 2) * kTP + jj] * rj) * rI[4 * tx + 2];
+                o.w = (ta[(4 * tx + 3) * kTP + jj] * rj) * rI[4 * tx + 3];
+                *reinterpret_cast<float4*>(out + (size_t)j * n + I0 + 4 * tx) = o;
+            }
+        }
+    }
+}
+
+// bwd pass 1: partial dr over one tile pair.  part[b][slot][row]: rows of I from the pair (I, J) go to slot J,
+// rows of J to slot I (every (slot, row block) is written by exactly one CTA).
+template <int PRE>
+__global__ void __launch_bounds__(kTileThreads)
+normalize_bwd_partial_tiles_kernel(const float* __restrict__ mx, const float* __restrict__ r, const float* __restrict__ Tg,
+                                   float* __restrict__ part, int n, int T) {
+    extern __shared__ float smem[];
+    float* mb = smem;                          // M(J,I):  mb[jj][ii]
+    float* tb = smem + kTS * kTP;              // T(J,I):  tb[jj][ii]
+    float* sS = tb + kTS * kTP;                // S[ii][jj]
+    float* rI = sS + kTS * kTP;
+    float* rJ = rI + kTS;
+    const size_t base = (size_t)blockIdx.y * n * n;
+    mx += base; Tg += base;
+    r += (size_t)blockIdx.y * n;
+    part += (size_t)blockIdx.y * T * n;
+    int I, J;
+    tile_pair_of(blockIdx.x, T, I, J);
+    const int I0 = I * kTS, J0 = J * kTS;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float4 ma[4], vmb[4], tA[4], vtb[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        ma[p] = ld4_pre<PRE>(mx, n, I0 + ty + 16 * p, J0 + 4 * tx);
+        vmb[p] = ld4_pre<PRE>(mx, n, J0 + ty + 16 * p, I0 + 4 * tx);
+        tA[p] = ld4_masked(Tg, n, I0 + ty + 16 * p, J0 + 4 * tx);
+        vtb[p] = ld4_masked(Tg, n, J0 + ty + 16 * p, I0 + 4 * tx);
+    }
+    if (threadIdx.x < kTS) rI[threadIdx.x] = (I0 + threadIdx.x < n) ? r[I0 + threadIdx.x] : 0.f;
+    else if (threadIdx.x < 2 * kTS) rJ[threadIdx.x - kTS] = (J0 + threadIdx.x - kTS < n) ? r[J0 + threadIdx.x - kTS] : 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { st_tile(mb, ty + 16 * p, 4 * tx, vmb[p]); st_tile(tb, ty + 16 * p, 4 * tx, vtb[p]); }
+    __syncthreads();
+    // S[ii][jj] = T[i][j] M[j][i] + T[j][i] M[i][j]   (on the diagonal tile the two terms are the (i,j) and (j,i) of one sum)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int ii = ty + 16 * p;
+        const float a4[4] = {ma[p].x, ma[p].y, ma[p].z, ma[p].w};
+        const float t4[4] = {tA[p].x, tA[p].y, tA[p].z, tA[p].w};
+        float4 o;
+        float* op = &o.x;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int jj = 4 * tx + u;
+            op[u] = t4[u] * mb[jj * kTP + ii] + tb[jj * kTP + ii] * a4[u];
+        }
+        st_tile(sS, ii, 4 * tx, o);
+    }
+    __syncthreads();
+    // row sums (rows of I, weights r_J) by threads 0..63, column sums (rows of J, weights r_I) by threads 64..127
+    if (threadIdx.x < kTS) {
+        const int ii = threadIdx.x;
+        if (I0 + ii < n) {
+            float acc = 0.f;
+            for (int jj = 0; jj < kTS; ++jj) acc = fmaf(sS[ii * kTP + jj], rJ[jj], acc);
+            part[(size_t)J * n + I0 + ii] = acc;
+        }
+    } else if (threadIdx.x < 2 * kTS && I != J) {
+        const int jj = threadIdx.x - kTS;
+        if (J0 + jj < n) {
+            float acc = 0.f;
+            for (int ii = 0; ii < kTS; ++ii) acc = fmaf(sS[ii * kTP + jj], rI[ii], acc);
+            part[(size_t)I * n + J0 + jj] = acc;
+        }
+    }
+}
+
+// drho_k = -1/2 r_k^3 sum_slots part[slot][k]   (fixed order)
+__global__ void normalize_bwd_drho_kernel(const float* __restrict__ part, const float* __restrict__ r, float* __restrict__ drho,
+                                          int n, int T, long long total) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const long long b = e / n;
+    const int k = (int)(e - b * n);
+    float acc = 0.f;
+    for (int sl = 0; sl < T; ++sl) acc += part[((size_t)b * T + sl) * n + k];
+    const float rk = r[e];
+    drho[e] = -0.5f * rk * rk * rk * acc;
+}
+
+// bwd pass 2: dM(I,J)[i][j] = (T[j][i] r_i) r_j + drho_i;  PRE: x sgn(mx[i][j]), zero diagonal
+template <int PRE>
+__global__ void __launch_bounds__(kTileThreads)
+normalize_bwd_apply_tiles_kernel(const float* __restrict__ mx, const float* __restrict__ r, const float* __restrict__ drho,
+                                 const float* __restrict__ Tg, float* __restrict__ dmx, int n, int T) {
+    extern __shared__ float smem[];
+    float* ta = smem;                          // T(I,J): ta[ii][jj]
+    float* tb = smem + kTS * kTP;              // T(J,I): tb[jj][ii]
+    float* rI = tb + kTS * kTP;
+    float* rJ = rI + kTS;
+    float* dI = rJ + kTS;
+    float* dJ = dI + kTS;
+    const size_t base = (size_t)blockIdx.y * n * n;
+    mx += base; Tg += base; dmx += base;
+    r += (size_t)blockIdx.y * n;
+    drho += (size_t)blockIdx.y * n;
+    int I, J;
+    tile_pair_of(blockIdx.x, T, I, J);
+    const int I0 = I * kTS, J0 = J * kTS;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float4 vta[4], vtb[4], xa[4], xb[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        vta[p] = ld4_masked(Tg, n, I0 + ty + 16 * p, J0 + 4 * tx);
+        vtb[p] = ld4_masked(Tg, n, J0 + ty + 16 * p, I0 + 4 * tx);
+        if (PRE) { xa[p] = ld4_masked(mx, n, I0 + ty + 16 * p, J0 + 4 * tx); xb[p] = ld4_masked(mx, n, J0 + ty + 16 * p, I0 + 4 * tx); }
+    }
+    if (threadIdx.x < kTS) {
+        const int k = I0 + threadIdx.x;
+        rI[threadIdx.x] = k < n ? r[k] : 0.f; dI[threadIdx.x] = k < n ? drho[k] : 0.f;
+    } else if (threadIdx.x < 2 * kTS) {
+        const int k = J0 + threadIdx.x - kTS;
+        rJ[threadIdx.x - kTS] = k < n ? r[k] : 0.f; dJ[threadIdx.x - kTS] = k < n ? drho[k] : 0.f;
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { st_tile(ta, ty + 16 * p, 4 * tx, vta[p]); st_tile(tb, ty + 16 * p, 4 * tx, vtb[p]); }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int ii = ty + 16 * p, i = I0 + ii;
+        if (i < n && J0 + 4 * tx < n) {
+            const float ri = rI[ii], di = dI[ii];
+            const float xs[4] = {PRE ? xa[p].x : 0.f, PRE ? xa[p].y : 0.f, PRE ? xa[p].z : 0.f, PRE ? xa[p].w : 0.f};
+            float4 o;
+            float* op = &o.x;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int jj = 4 * tx + u;
+                float gv = (tb[jj * kTP + ii] * ri) * rJ[jj] + di;
+                if (PRE) gv = (i == J0 + jj) ? 0.f : gv * sgnf(xs[u]);
+                op[u] = gv;
+            }
+            *reinterpret_cast<float4*>(dmx + (size_t)i * n + J0 + 4 * tx) = o;
+        }
+        if (I != J) {
+            const int jj = ty + 16 * p, j = J0 + jj;
+            if (j < n && I0 + 4 * tx < n) {
+                const float rj = rJ[jj], dj = dJ[jj];
+                const float xs[4] = {PRE ? xb[p].x : 0.f, PRE ? xb[p].y : 0.f, PRE ? xb[p].z : 0.f, PRE ? xb[p].w : 0.f};
+                float4 o;
+                float* op = &o.x;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ii2 = 4 * tx + u;
+                    float gv = (ta[ii2 * kTP + jj] * rj) * rI[ii2] + dj;
+                    if (PRE) gv = (j == I0 + ii2) ? 0.f : gv * sgnf(xs[u]);
+                    op[u] = gv;
+                }
+                *reinterpret_cast<float4*>(dmx + (size_t)j * n + I0 + 4 * tx) = o;
+            }
+        }
+    }
+}
+
 __global__ void abs_diag1_kernel(const float* __restrict__ x, float* __restrict__ out,
                                  long long total, int n) {
     const long long nn = (long long)n * n;
@@ -327,6 +571,18 @@ extern "C" int gsr_normalize_adj_fwd(const float* mx, float* out, float* r_out, 
                                      int batch, int n, int pre, void* stream) {
     if (!mx || !out || !r_out || batch < 0 || n <= 0) return fail(GSR_E_ARG, "normalize_adj_fwd: bad argument");
     if (batch == 0) return 0;
+    if (n % 4 == 0 && n >= 2 * kTS && aligned16(mx) && aligned16(out) && (!m_out || aligned16(m_out)) && batch <= 65535) {
+        cudaStream_t st = (cudaStream_t)stream;
+        const int T = (n + kTS - 1) / kTS;
+        const size_t tsmem = (2 * kTS * kTP + 2 * kTS) * sizeof(float);
+        if (pre) normalize_rowsum_kernel<1><<<dim3((n + 7) / 8, batch), 256, 0, st>>>(mx, r_out, m_out, n);
+        else     normalize_rowsum_kernel<0><<<dim3((n + 7) / 8, batch), 256, 0, st>>>(mx, r_out, m_out, n);
+        int rc1 = launched("normalize_rowsum");
+        if (rc1) return rc1;
+        if (pre) normalize_scale_tiles_kernel<1><<<dim3(T * (T + 1) / 2, batch), kTileThreads, tsmem, st>>>(mx, r_out, out, n, T);
+        else     normalize_scale_tiles_kernel<0><<<dim3(T * (T + 1) / 2, batch), kTileThreads, tsmem, st>>>(mx, r_out, out, n, T);
+        return launched("normalize_adj_fwd");
+    }
     const size_t smem = ((size_t)((n + 31) & ~31) + (size_t)n * kStripPad) * sizeof(float);
     auto k = pre ? normalize_fwd_kernel<1> : normalize_fwd_kernel<0>;
     int rc = set_smem(k, smem);
@@ -389,4 +645,35 @@ extern "C" int gsr_abs_diag1_fwd(const float* x, float* out, int batch, int n, v
     const int blocks = (int)min((long long)kNumSMs * 8, (total + 255) / 256);
     abs_diag1_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, out, total, n);
     return launched("abs_diag1_fwd");
+}
+
+extern "C" size_t gsr_normalize_adj_bwd_workspace(int batch, int n) {
+    if (batch <= 0 || n <= 0) return 0;
+    const size_t T = (n + kTS - 1) / kTS;
+    return (size_t)batch * (T + 1) * n;                     // floats: [batch][T][n] partial sums + [batch][n] drho
+}
+
+extern "C" int gsr_normalize_adj_bwd_tiles(const float* mx, const float* r, const float* grad_out, float* grad_mx,
+                                           float* workspace, int batch, int n, int pre, void* stream) {
+    if (!mx || !r || !grad_out || !grad_mx || batch < 0 || n <= 0) return fail(GSR_E_ARG, "normalize_adj_bwd_tiles: bad argument");
+    if (batch == 0) return 0;
+    if (!workspace || n % 4 != 0 || !aligned16(mx) || !aligned16(grad_out) || !aligned16(grad_mx) || batch > 65535)
+        return gsr_normalize_adj_bwd(mx, r, grad_out, grad_mx, batch, n, pre, stream);      // strip kernel: any n, no workspace
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = (n + kTS - 1) / kTS;
+    float* part = workspace;
+    float* drho = workspace + (size_t)batch * T * n;
+    const size_t smem1 = (3 * kTS * kTP + 2 * kTS) * sizeof(float), smem2 = (2 * kTS * kTP + 4 * kTS) * sizeof(float);
+    int rc = pre ? set_smem(normalize_bwd_partial_tiles_kernel<1>, smem1) : set_smem(normalize_bwd_partial_tiles_kernel<0>, smem1);
+    if (rc) return fail(rc, "normalize_adj_bwd_tiles: cudaFuncSetAttribute failed");
+    const dim3 grid(T * (T + 1) / 2, batch);
+    if (pre) normalize_bwd_partial_tiles_kernel<1><<<grid, kTileThreads, smem1, st>>>(mx, r, grad_out, part, n, T);
+    else     normalize_bwd_partial_tiles_kernel<0><<<grid, kTileThreads, smem1, st>>>(mx, r, grad_out, part, n, T);
+    if ((rc = launched("normalize_bwd_partial"))) return rc;
+    const long long total = (long long)batch * n;
+    normalize_bwd_drho_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(part, r, drho, n, T, total);
+    if ((rc = launched("normalize_bwd_drho"))) return rc;
+    if (pre) normalize_bwd_apply_tiles_kernel<1><<<grid, kTileThreads, smem2, st>>>(mx, r, drho, grad_out, grad_mx, n, T);
+    else     normalize_bwd_apply_tiles_kernel<0><<<grid, kTileThreads, smem2, st>>>(mx, r, drho, grad_out, grad_mx, n, T);
+    return launched("normalize_adj_bwd");
 }

@@ -114,8 +114,10 @@ def normalize_adj_bwd(mx: torch.Tensor, r: torch.Tensor, grad_out: torch.Tensor,
     grad = torch.empty_like(mx)
     timer = EW_TIMER
     e0 = timer.start() if timer is not None else None
-    check(lib().gsr_normalize_adj_bwd(mx.data_ptr(), r.data_ptr(), grad_out.data_ptr(), grad.data_ptr(),
-                                      batch, n, int(pre), _stream()), "gsr_normalize_adj_bwd")
+    ws_floats = lib().gsr_normalize_adj_bwd_workspace(batch, n)
+    ws = torch.empty((max(ws_floats, 1),), device=mx.device, dtype=torch.float32)
+    check(lib().gsr_normalize_adj_bwd_tiles(mx.data_ptr(), r.data_ptr(), grad_out.data_ptr(), grad.data_ptr(),
+                                            ws.data_ptr(), batch, n, int(pre), _stream()), "gsr_normalize_adj_bwd_tiles")
     if timer is not None:
         timer.stop(e0, 12.0 * batch * n * n)
     return grad

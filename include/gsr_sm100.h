@@ -62,6 +62,13 @@ GSR_API int gsr_normalize_adj_fwd(const float* mx, float* out, float* r_out, flo
  * (fill_diagonal_ overwrites it).                                     */
 GSR_API int gsr_normalize_adj_bwd(const float* mx, const float* r, const float* grad_out,
                           float* grad_mx, int batch, int n, int pre, void* stream);
+/* Same gradient, tile-pair kernels (two passes over 64 x 64 tile pairs with a deterministic partial-sum
+ * workspace of gsr_normalize_adj_bwd_workspace(batch, n) FLOATS): the fast path for n % 4 == 0 and 16-byte
+ * aligned operands; anything else (or workspace == NULL) runs gsr_normalize_adj_bwd.                    */
+GSR_API size_t gsr_normalize_adj_bwd_workspace(int batch, int n);
+GSR_API int gsr_normalize_adj_bwd_tiles(const float* mx, const float* r, const float* grad_out, float* grad_mx,
+                                float* workspace, int batch, int n, int pre, void* stream);
+
 
 /* ------------------------------------------------------------------ a2 / a12
  * models/layers.py:27 and utils/gsr_train.py:34  torch.linalg.eigh(A, UPLO='U')
