@@ -448,7 +448,7 @@ def run_ours(args):
     roofline = max(by_kernel, key=lambda r: r["share_of_step"] or 0.0)          # the dominant kernel of the step
     others = [r for r in by_kernel if r is not roofline]
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:        # reported on rank 0 at N = 1 only
         threads = os.cpu_count() or 1
         n_cpu = args.cpu_sample or 96
         secs = oracle_step_seconds(n_cpu, threads)
