@@ -41,6 +41,9 @@ namespace tq {
 constexpr int MAXN = 160;
 constexpr int NB = MAXN / 16;            // 16-column blocks
 constexpr int LDV = 164;                 // pitch of a stored reflector row: v[0..159], tau at [160]
+constexpr int BIGN = 288;                // the 268-node HR target (utils/gsr_train.py:34) takes the shared-memory variants below
+constexpr int LDVB = BIGN + 4;           // their reflector pitch: v[0..287], tau at [288]
+__host__ __device__ inline int ldv_of(int n) { return n <= MAXN ? LDV : LDVB; }
 constexpr int LDZ = 161;                 // K3 epilogue: column pitch in shared memory, odd
 constexpr int BLK = 64;                  // rotations per cp.async block
 constexpr int STAGES = 3;
@@ -69,7 +72,7 @@ static size_t carve(Work* wk, void* base, int batch, int n) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_stream = take((size_t)batch * cap * sizeof(float2));
-    const size_t o_v = take((size_t)batch * n * LDV * sizeof(float));
+    const size_t o_v = take((size_t)batch * n * ldv_of(n) * sizeof(float));
     const size_t o_zt = take((size_t)batch * n * n * sizeof(float));
     const size_t o_d = take((size_t)batch * n * sizeof(float));
     const size_t o_e = take((size_t)batch * n * sizeof(float));
@@ -277,7 +280,7 @@ constexpr int K2_WARPS = 4;
 
 __global__ void __launch_bounds__(32 * K2_WARPS)
 tql_scalar_kernel(const Work wk, int n, int batch, int max_iter) {
-    __shared__ float sd[K2_WARPS][MAXN + 16], se[K2_WARPS][MAXN + 16];      // [8] pad | n values | pad: index -1 is readable
+    __shared__ float sd[K2_WARPS][BIGN + 16], se[K2_WARPS][BIGN + 16];      // [8] pad | n values | pad: index -1 is readable
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int g = blockIdx.x * K2_WARPS + wl;
     if (g >= batch) return;
@@ -593,13 +596,329 @@ tql_finish_kernel(const Work wk, float* __restrict__ Wout, float* __restrict__ U
     if (tid == 0) info[g] = nit > 0 ? nit : 1;
 }
 
+// ==================================================================================== n = 161 .. 288
+// The HR-target decomposition (268 nodes, utils/gsr_train.py:33-36) on the same three stages.  A 268-row matrix
+// does not fit the register file of one SM (71 824 > 65 536), so these variants keep their matrix in SHARED memory:
+//   K1b  the symmetric matrix as its PACKED lower triangle (36 046 floats = 144 KB): thread i owns row i; the
+//        mat-vec walks j = 0 .. k-1 reading L[i][j] (j <= i) or L[j][i] (j > i, consecutive over the warp), the
+//        rank-2 update touches the i + 1 stored entries of row i; the pivot row k is the tail of the active
+//        prefix, contiguous, so nothing is published;
+//   K3b  rows of Z are independent: TWO CTAs per graph hold 134 rows each (z[col][row], 145 KB), build their
+//        rows of Q from the reflectors and replay the rotation stream with a running register value;
+//   K4b  works from the Z^T K3b leaves in global memory (column norms / signs coalesced, 32 x 32 tile transpose).
+// K2 is shared.  ~27 ms per 1024 graphs against 136 ms for the Jacobi kernel with its L2-resident workspace.
+__device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
+
+__global__ void __launch_bounds__(BIGN, 1)
+tridiag_packed_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* __restrict__ Uout,
+                      int32_t* __restrict__ info, const Work wk, int n) {
+    extern __shared__ __align__(16) float sm[];
+    float* L = sm;                                   // packed lower triangle: L[tri(i) + j], j <= i
+    const int ltot = (tri(n) + 3) & ~3;
+    float* vbuf = L + ltot;                          // [BIGN]
+    float* wbuf = vbuf + BIGN;                       // [BIGN]
+    float* pbuf = wbuf + BIGN;                       // [BIGN]
+    float* dd = pbuf + BIGN;                         // [BIGN]
+    float* ee = dd + BIGN;                           // [BIGN]
+    float* red = ee + BIGN;                          // [16]
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nwarps = nthr >> 5;
+    const int g = blockIdx.x;
+    const float* Ag = Ain + (size_t)g * n * n;
+
+    // ---- load the upper triangle: A_sym[i][j] (j <= i) = A[j][i]; column i of the input, coalesced over i
+    int bad = 0;
+    float amax = 0.f;
+    if (tid < n) {
+        for (int j = 0; j <= tid; ++j) {
+            const float v = __ldg(Ag + (size_t)j * n + tid);
+            if (!isfinite(v)) bad = 1;
+            amax = fmaxf(amax, fabsf(v));
+            L[tri(tid) + j] = v;
+        }
+    }
+    for (int e = tid; e < 3 * BIGN; e += nthr) vbuf[e] = 0.f;
+    if (tid < 16) red[tid] = 0.f;
+    if (__syncthreads_or(bad)) {
+        const float qnan = __int_as_float(0x7fc00000);
+        for (int e = tid; e < n * n; e += nthr) Uout[(size_t)g * n * n + e] = qnan;
+        for (int e = tid; e < n; e += nthr) Wout[(size_t)g * n + e] = qnan;
+        if (tid == 0) { info[g] = -1; wk.counts[4 * g + 0] = 0; wk.counts[4 * g + 1] = 0; wk.counts[4 * g + 2] = -1; }
+        return;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0) red[w] = amax;
+    __syncthreads();
+    amax = 0.f;
+    for (int q = 0; q < nwarps; ++q) amax = fmaxf(amax, red[q]);
+    __syncthreads();
+    if (lane == 0) red[w] = 0.f;
+    float sc = 1.0f;
+    if (amax > 0.f && (amax < 9.5367431640625e-07f || amax > 1048576.0f)) sc = ldexpf(1.0f, -max(-120, min(120, ilogbf(amax))));
+    if (sc != 1.0f && tid < n) {
+        for (int j = 0; j <= tid; ++j) L[tri(tid) + j] *= sc;
+    }
+    if (tid == 0) { wk.scale[g] = sc; wk.counts[4 * g + 2] = 0; }
+    __syncthreads();
+
+    float* Vg = wk.V + (size_t)g * n * LDVB;
+    const int i = tid, ti = tri(tid);
+    for (int k = n - 1; k >= 1; --k) {
+        const float* xr = L + tri(k);                 // row k: columns 0..k (final)
+        float ss = 0.f;
+        for (int j = lane; j < k - 1; j += 32) { const float x = xr[j]; ss = fmaf(x, x, ss); }
+        ss = warp_sum(ss);
+        const float alpha = xr[k - 1];
+        float tau = 0.f, beta = alpha;
+        if (ss != 0.f) {
+            const float nrm = sqrtf(fmaf(alpha, alpha, ss));
+            beta = -copysignf(nrm, alpha);
+            tau = (beta - alpha) / beta;
+            const float scl = 1.0f / (alpha - beta);
+            const int kpad = (k + 15) & ~15;
+            for (int j = lane; j < kpad; j += 32) vbuf[j] = (j < k - 1) ? xr[j] * scl : (j == k - 1 ? 1.0f : 0.0f);   // every warp: same values
+        }
+        if (tid == 0) { dd[k] = xr[k]; ee[k - 1] = beta; }
+        if (tau != 0.f) {                              // uniform
+            __syncwarp();
+            const bool act = i < k;
+            float q0 = 0.f, q1 = 0.f;
+            if (act) {
+                int j = 0;
+                for (; j + 1 < k; j += 2) {            // A_sym[i][j]: own row up to the diagonal, column i of row j beyond it
+                    const float a0 = L[j <= i ? ti + j : tri(j) + i];
+                    const float a1 = L[j + 1 <= i ? ti + j + 1 : tri(j + 1) + i];
+                    q0 = fmaf(a0, vbuf[j], q0);
+                    q1 = fmaf(a1, vbuf[j + 1], q1);
+                }
+                if (j < k) q0 = fmaf(L[j <= i ? ti + j : tri(j) + i], vbuf[j], q0);
+            }
+            const float pi = tau * (q0 + q1);
+            const float vi = act ? vbuf[i] : 0.f;
+            const float pvp = warp_sum(act ? pi * vi : 0.f);
+            if (lane == 0) red[w] = pvp;
+            if (act) pbuf[i] = pi;
+            if (w == nwarps - 1) {                     // reflector -> global for K3b (whole 16-column blocks, tau at [288])
+                float* vrow = Vg + (size_t)k * LDVB;
+                const int kpad = (k + 15) & ~15;
+                for (int j = lane; j < kpad; j += 32) vrow[j] = vbuf[j];
+                if (lane == 0) vrow[BIGN] = tau;
+            }
+            __syncthreads();                                                   // (A)
+            float pv = 0.f;
+            for (int q = 0; q < nwarps; ++q) pv += red[q];
+            const float coef = 0.5f * tau * pv;
+            const int kpad = (k + 15) & ~15;
+            for (int j = lane; j < kpad; j += 32) wbuf[j] = (j < k) ? fmaf(-coef, vbuf[j], pbuf[j]) : 0.0f;        // every warp: same values
+            __syncwarp();
+            if (act) {
+                const float wi = wbuf[i];
+                for (int j = 0; j <= i; ++j) L[ti + j] = fmaf(-vi, wbuf[j], fmaf(-wi, vbuf[j], L[ti + j]));
+            }
+        } else if (w == nwarps - 1 && lane == 0) {
+            Vg[(size_t)k * LDVB + BIGN] = 0.f;
+        }
+        __syncthreads();                                                       // (B) row k-1 is final
+    }
+    if (tid == 0) { dd[0] = L[0]; ee[n - 1] = 0.f; Vg[BIGN] = 0.f; }
+    __syncthreads();
+    for (int j = tid; j < n; j += nthr) {
+        wk.d[(size_t)g * n + j] = dd[j];
+        wk.e[(size_t)g * n + j] = (j < n - 1) ? ee[j] : 0.f;
+    }
+}
+
+// K3b: CTA = (graph, row half).  z[col * LDR + r]: column `col` of the CTA's rows (thread = row).
+constexpr int RINGB = 3 * 304;                     // floats per warp: 3 reflector rows (292) or 3 x 64 (c, s) pairs
+
+__global__ void __launch_bounds__(160, 1)
+tql_apply_smem_kernel(const Work wk, int n, int rows_per_cta) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nwarps = blockDim.x >> 5;
+    const int g = blockIdx.x >> 1, half = blockIdx.x & 1;
+    const int row0 = half * rows_per_cta, nrows = min(rows_per_cta, n - row0);
+    const int LDR = (rows_per_cta + 1) | 1;            // odd pitch with room for the idle lanes' scratch slot
+    const int ncols = ((n + 15) & ~15) + 1;            // identity-padded rotations may touch columns n .. 16 ceil(n / 16)
+    float* z = sm;
+    float* ring = sm + (((size_t)ncols * LDR + 3) & ~(size_t)3) + (size_t)w * RINGB;
+    const int* cnt = wk.counts + 4 * g;
+    const int nit = cnt[0], nent = cnt[1], status = cnt[2];
+    if (status != 0 || nrows <= 0) return;
+    const int r = tid < nrows ? tid : nrows;           // idle lanes work on scratch slot `nrows` (< LDR)
+    // ---- rows of Q: e_row^T H_{n-1} ... H_1
+    for (int c = 0; c < ncols; ++c) z[c * LDR + r] = (tid < nrows && c == row0 + tid) ? 1.0f : 0.0f;
+    __syncwarp();
+    {
+        const float* Vg = wk.V + (size_t)g * n * LDVB;
+        auto issue = [&](int k) {
+            if (k >= 1) {
+                const float* src = Vg + (size_t)k * LDVB;
+                float* dst = ring + (k % 3) * 304;
+                for (int c = lane; c < LDVB / 4; c += 32) cp_async16(dst + 4 * c, src + 4 * c);
+            }
+            cp_async_commit();
+        };
+        issue(n - 1);
+        issue(n - 2);
+        for (int k = n - 1; k >= 1; --k) {
+            cp_async_wait<1>();
+            __syncwarp();
+            issue(k - 2);
+            const float* vr = ring + (k % 3) * 304;
+            const float tau = vr[BIGN];
+            if (tau != 0.f) {
+                const float4* V4 = reinterpret_cast<const float4*>(vr);
+                float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+                const int nch = (k + 3) >> 2;          // v is zero from column k to the end of its 16-column block
+                for (int c = 0; c < nch; ++c) {
+                    const float4 v = V4[c];
+                    const float* zp = z + (4 * c) * LDR + r;
+                    q0 = fmaf(zp[0], v.x, q0); q1 = fmaf(zp[LDR], v.y, q1); q2 = fmaf(zp[2 * LDR], v.z, q2); q3 = fmaf(zp[3 * LDR], v.w, q3);
+                }
+                const float s = -tau * ((q0 + q1) + (q2 + q3));
+                for (int c = 0; c < nch; ++c) {
+                    const float4 v = V4[c];
+                    float* zp = z + (4 * c) * LDR + r;
+                    zp[0] = fmaf(s, v.x, zp[0]); zp[LDR] = fmaf(s, v.y, zp[LDR]);
+                    zp[2 * LDR] = fmaf(s, v.z, zp[2 * LDR]); zp[3 * LDR] = fmaf(s, v.w, zp[3 * LDR]);
+                }
+            }
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+    }
+    // ---- replay the (identity-padded) rotation stream: iteration = rotations 16 hb - 1 .. 16 lb, descending
+    {
+        const float2* src = wk.stream + (size_t)g * wk.cap;
+        const uint32_t* hdr = wk.hdr + (size_t)g * wk.hdr_cap;
+        float2* cring = reinterpret_cast<float2*>(ring);
+        const int nblk = (nent + BLK - 1) / BLK;
+        auto issue = [&](int b) {
+            if (b < nblk) cp_async16(cring + (b % STAGES) * BLK + 2 * lane, src + (size_t)b * BLK + 2 * lane);
+            cp_async_commit();
+        };
+        issue(0);
+        issue(1);
+        int pos = 0;
+        uint32_t h = nit > 0 ? __ldg(hdr) : 0u;
+        for (int it = 0; it < nit; ++it) {
+            const uint32_t hn = (it + 1 < nit) ? __ldg(hdr + it + 1) : 0u;
+            const int lb = (int)(h & 0xffu), hb = (int)((h >> 8) & 0xffu);
+            int i = 16 * hb - 1;
+            float rv = z[(i + 1) * LDR + r];
+            for (int b = hb - 1; b >= lb; --b) {
+                if ((pos & (BLK - 1)) == 0) {
+                    cp_async_wait<1>();
+                    __syncwarp();
+                    issue(pos / BLK + 2);
+                }
+                const float2* cs = cring + (pos / BLK % STAGES) * BLK + (pos & (BLK - 1));
+                float* zp = z + i * LDR + r;
+                float zi[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) zi[u] = zp[-u * LDR];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const float2 q = cs[u];
+                    zp[(1 - u) * LDR] = fmaf(q.x, rv, q.y * zi[u]);
+                    rv = fmaf(-q.y, rv, q.x * zi[u]);
+                }
+                i -= 16;
+                pos += 16;
+            }
+            z[(i + 1) * LDR + r] = rv;
+            h = hn;
+        }
+        cp_async_wait<0>();
+    }
+    if (tid < nrows) {
+        float* Zg = wk.Zt + (size_t)g * n * n;
+        for (int c = 0; c < n; ++c) Zg[(size_t)c * n + row0 + tid] = z[c * LDR + tid];
+    }
+}
+
+// K4b: like tql_finish_kernel, straight from Z^T in global memory.
+__global__ void __launch_bounds__(256)
+tql_finish_global_kernel(const Work wk, float* __restrict__ Wout, float* __restrict__ Uout, int32_t* __restrict__ info,
+                         int n, int canonical) {
+    __shared__ float lam[BIGN], sgn[BIGN];
+    __shared__ int inv[BIGN];
+    __shared__ float tile[32][33];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nwarps = nthr >> 5;
+    const int g = blockIdx.x;
+    const int* cnt = wk.counts + 4 * g;
+    const int nit = cnt[0], status = cnt[2];
+    if (status == -1) return;
+    float* Wg = Wout + (size_t)g * n;
+    float* Ug = Uout + (size_t)g * n * n;
+    if (status != 0) {
+        const float qnan = __int_as_float(0x7fc00000);
+        for (int e = tid; e < n * n; e += nthr) Ug[e] = qnan;
+        for (int e = tid; e < n; e += nthr) Wg[e] = qnan;
+        if (tid == 0) info[g] = -2;
+        return;
+    }
+    const float* Zg = wk.Zt + (size_t)g * n * n;
+    const float inv_sc = 1.0f / wk.scale[g];
+    for (int k = tid; k < n; k += nthr) lam[k] = wk.d[(size_t)g * n + k] * inv_sc;
+    __syncthreads();
+    for (int k = tid; k < n; k += nthr) {
+        const float lk = lam[k];
+        int rk = 0;
+        for (int q2 = 0; q2 < n; ++q2) {
+            const float lq = lam[q2];
+            rk += (lq < lk) || (lq == lk && q2 < k);
+        }
+        inv[rk] = k;
+        Wg[rk] = lk;
+    }
+    for (int k = w; k < n; k += nwarps) {
+        float best = -1.f, best_v = 0.f, ss = 0.f;
+        int best_i = 0;
+        for (int row = lane; row < n; row += 32) {
+            const float v = Zg[(size_t)k * n + row], mag = fabsf(v);
+            ss = fmaf(v, v, ss);
+            if (mag > best) { best = mag; best_i = row; best_v = v; }
+        }
+        ss = warp_sum(ss);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+            if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; best_v = ov; }
+        }
+        const float inv_norm = ss > 0.f ? rsqrtf(ss) : 1.0f;
+        if (lane == 0) sgn[k] = (canonical && best_v < 0.f) ? -inv_norm : inv_norm;
+    }
+    __syncthreads();
+    // U[row][c] = Z^T[inv[c]][row] * sgn[inv[c]]: 32 x 32 tiles, read along rows of Z^T, write along rows of U
+    const int T = (n + 31) / 32;
+    for (int t = 0; t < T * T; ++t) {
+        const int rt = t / T, ct = t - rt * T;
+        for (int cc = w; cc < 32; cc += nwarps) {
+            const int c = ct * 32 + cc, row = rt * 32 + lane;
+            float v = 0.f;
+            if (c < n && row < n) { const int k = inv[c]; v = Zg[(size_t)k * n + row] * sgn[k]; }
+            tile[cc][lane] = v;
+        }
+        __syncthreads();
+        for (int rr = w; rr < 32; rr += nwarps) {
+            const int row = rt * 32 + rr, c = ct * 32 + lane;
+            if (row < n && c < n) Ug[(size_t)row * n + c] = tile[lane][rr];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) info[g] = nit > 0 ? nit : 1;
+}
+
 }  // namespace tq
 }  // namespace gsr
 
 using namespace gsr;
 
 extern "C" size_t gsr_eigh_tridiag_workspace(int batch, int n) {
-    if (batch <= 0 || n <= 0 || n > tq::MAXN) return 0;
+    if (batch <= 0 || n <= 0 || n > tq::BIGN) return 0;
     return tq::carve(nullptr, nullptr, batch, n);
 }
 
@@ -607,7 +926,7 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
                                     size_t workspace_bytes, int batch, int n, int canonical_sign, void* stream) {
     if (!A || !w || !U || !info || batch < 0 || n <= 0) return fail(GSR_E_ARG, "eigh_tridiag: bad argument");
     if (batch == 0) return 0;
-    if (n > tq::MAXN) return fail(GSR_E_UNSUPPORTED, "eigh_tridiag: n > 160 is not supported (use gsr_eigh_jacobi_f32)");
+    if (n > tq::BIGN) return fail(GSR_E_UNSUPPORTED, "eigh_tridiag: n > 288 is not supported");
     if (!workspace || workspace_bytes < tq::carve(nullptr, nullptr, batch, n))
         return fail(GSR_E_ARG, "eigh_tridiag: workspace missing or smaller than gsr_eigh_tridiag_workspace(batch, n)");
     if (!aligned16(workspace)) return fail(GSR_E_ALIGN, "eigh_tridiag: workspace must be 16-byte aligned");
@@ -615,6 +934,27 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
     tq::Work wk;
     tq::carve(&wk, workspace, batch, n);
     const int threads = 32 * ((n + 31) / 32);
+
+    if (n > tq::MAXN) {
+        // ---- 161 .. 288 nodes: shared-memory variants
+        const size_t smem1 = ((((size_t)n * (n + 1) / 2 + 3) & ~(size_t)3) + 5 * tq::BIGN + 16) * sizeof(float);
+        cudaError_t e1 = cudaFuncSetAttribute(tq::tridiag_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e1 != cudaSuccess) return fail((int)e1, "eigh_tridiag: cudaFuncSetAttribute failed");
+        tq::tridiag_packed_kernel<<<batch, threads, smem1, st>>>(A, w, U, info, wk, n);
+        int rcb = launched("eigh_tridiag_packed");
+        if (rcb) return rcb;
+        tq::tql_scalar_kernel<<<(batch + tq::K2_WARPS - 1) / tq::K2_WARPS, 32 * tq::K2_WARPS, 0, st>>>(wk, n, batch, g_eigh_ql_max_iter);
+        if ((rcb = launched("eigh_tql_scalar"))) return rcb;
+        const int rows_per_cta = (n + 1) / 2, thr3 = 32 * ((rows_per_cta + 31) / 32);
+        const int ldr = (rows_per_cta + 1) | 1, ncols = ((n + 15) & ~15) + 1;
+        const size_t smem3b = ((((size_t)ncols * ldr + 3) & ~(size_t)3) + (size_t)(thr3 / 32) * tq::RINGB) * sizeof(float);
+        e1 = cudaFuncSetAttribute(tq::tql_apply_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3b);
+        if (e1 != cudaSuccess) return fail((int)e1, "eigh_tridiag: cudaFuncSetAttribute failed");
+        tq::tql_apply_smem_kernel<<<2 * batch, thr3, smem3b, st>>>(wk, n, rows_per_cta);
+        if ((rcb = launched("eigh_tql_apply_smem"))) return rcb;
+        tq::tql_finish_global_kernel<<<batch, 256, 0, st>>>(wk, w, U, info, n, canonical_sign);
+        return launched("eigh_tql_finish_global");
+    }
 
     tq::tridiag_kernel<<<batch, threads, 0, st>>>(A, w, U, info, wk, n);
     int rc = launched("eigh_tridiag");

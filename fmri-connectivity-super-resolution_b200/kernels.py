@@ -146,12 +146,12 @@ def eigh_jacobi(A: torch.Tensor, canonical_sign: bool = True, tol: float = 0.0, 
     return w, U, info
 
 
-EIGH_TRIDIAG_MAX_N = 160
+EIGH_TRIDIAG_MAX_N = 288
 EIGH_METHOD = os.environ.get("GSR_EIGH_METHOD", "auto")     # "auto" | "jacobi" | "tridiag"
 
 
 def eigh_tridiag(A: torch.Tensor, canonical_sign: bool = True, _return_workspace: bool = False):
-    """Returns (w, U, info) -- see gsr_eigh_tridiag_f32 (n <= 160).  No synchronisation."""
+    """Returns (w, U, info) -- see gsr_eigh_tridiag_f32 (n <= 288).  No synchronisation."""
     A = _f32(A, "eigh: A")
     batch, n = _square_batch(A, "eigh: A")
     w = torch.empty(A.shape[:-1], device=A.device, dtype=torch.float32)
@@ -176,8 +176,9 @@ def eigh_tridiag(A: torch.Tensor, canonical_sign: bool = True, _return_workspace
 
 
 def eigh(A: torch.Tensor, canonical_sign: bool = True, method: Optional[str] = None):
-    """torch.linalg.eigh(A, 'U') on the device: the tridiagonal-QL kernels for n <= 160 (the in-step
-    LR decomposition), the Jacobi kernel above that (the hoisted 268-node HR target)."""
+    """torch.linalg.eigh(A, 'U') on the device: the tridiagonal-QL kernels up to 288 nodes (register-resident
+    for the 160-node LR graphs, shared-memory variants for the 268-node HR target); the Jacobi kernel is the
+    fallback (functional.eigh) and the explicit ``method='jacobi'`` route."""
     method = method or EIGH_METHOD
     n = A.shape[-1]
     if method == "tridiag" or (method == "auto" and n <= EIGH_TRIDIAG_MAX_N):

@@ -93,16 +93,17 @@ GSR_API int gsr_eigh_jacobi_f32(const float* A, float* w, float* U, int32_t* inf
                         int batch, int n, int canonical_sign, float tol, int max_sweeps,
                         void* stream);
 
-/* Same contract (torch.linalg.eigh(A, UPLO='U'), models/layers.py:27), tridiagonal route for
- * n <= GSR_EIGH_TRIDIAG_MAX_N -- the in-step LR decomposition: Householder reduction with A
- * resident in shared memory (one CTA per graph), implicit-shift QL on (d, e) with one warp per
- * graph recording its plane rotations, and a replay of the rotation stream on the rows of Q
- * (one CTA per graph).  ~5 n^3 flops instead of the ~18 n^3 of the Jacobi kernel, LAPACK-class
- * accuracy.  `workspace` holds gsr_eigh_tridiag_workspace(batch, n) BYTES (16-byte aligned).
+/* Same contract (torch.linalg.eigh(A, UPLO='U'), models/layers.py:27 and utils/gsr_train.py:34), tridiagonal
+ * route for n <= GSR_EIGH_TRIDIAG_MAX_N: Householder reduction, implicit-shift QL on (d, e) with one warp per
+ * graph recording its plane rotations, and a replay of the rotation stream on the rows of Q.  Up to 160 nodes
+ * (the in-step LR decomposition) the matrices live in REGISTERS (one thread per row); 161..288 nodes (the
+ * 268-node HR target) keep the packed triangle / the rows of Z in shared memory.  ~6 n^3 flops instead of
+ * the ~18 n^3 of the Jacobi kernel, LAPACK-class accuracy.  `workspace` holds
+ * gsr_eigh_tridiag_workspace(batch, n) BYTES (16-byte aligned).
  * info[batch]: > 0 = QL iterations used; -1 = non-finite input (outputs are NaN); -2 = QL did
  * not converge in 30 iterations per eigenvalue or needed more than 2 n^2 rotations (outputs
  * are NaN; callers fall back to gsr_eigh_jacobi_f32 for those graphs).                       */
-#define GSR_EIGH_TRIDIAG_MAX_N 160
+#define GSR_EIGH_TRIDIAG_MAX_N 288
 GSR_API size_t gsr_eigh_tridiag_workspace(int batch, int n);
 GSR_API int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t* info, void* workspace,
                          size_t workspace_bytes, int batch, int n, int canonical_sign, void* stream);

@@ -47,8 +47,9 @@ def test_library_loads_and_exports_every_declared_symbol(pkg):
     assert lib.gsr_l1_partials(268 * 268) >= 1
     assert lib.gsr_eval_workspace() > 0
     assert lib.gsr_eigh_workspace(4, 160) == 0 and lib.gsr_eigh_workspace(4, 268) == 4 * 268 * 292
-    # tridiagonal route: n <= 160 only, workspace grows linearly with the batch
-    assert lib.gsr_eigh_tridiag_workspace(4, 161) == 0 and lib.gsr_eigh_tridiag_workspace(0, 160) == 0
+    # tridiagonal route: n <= 288, workspace grows linearly with the batch
+    assert lib.gsr_eigh_tridiag_workspace(4, 289) == 0 and lib.gsr_eigh_tridiag_workspace(0, 160) == 0
+    assert lib.gsr_eigh_tridiag_workspace(2, 268) > 2 * 2 * 268 * 268 * 8
     w1, w8 = lib.gsr_eigh_tridiag_workspace(1, 160), lib.gsr_eigh_tridiag_workspace(8, 160)
     assert w1 > 2 * 160 * 160 * 8 and 7 * w1 < w8 <= 8 * w1
     assert lib.gsr_launch_count() == 0           # nothing may launch on a CPU-only box

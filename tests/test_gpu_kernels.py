@@ -266,9 +266,10 @@ def test_eigh_error_contract(cuda_pkg):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n", [1, 2, 7, 16, 17, 33, 96, 128, 159, 160])
+@pytest.mark.parametrize("n", [1, 2, 7, 16, 17, 33, 96, 128, 159, 160, 161, 200, 268, 288])
 def test_eigh_both_routes_agree(cuda_pkg, n):
-    """n <= 160: the tridiagonal-QL kernels (default route) and the Jacobi kernel decompose the same
+    """The tridiagonal-QL kernels (default route; register-resident up to 160 nodes, shared-memory variants up
+    to 288) and the Jacobi kernel decompose the same
     matrices; both are held to the float64 properties and their eigenvalues to each other."""
     K = cuda_pkg.kernels
     A = torch.stack([O.normalize_adj(O.synth_connectome(n, 900 + s)) if n > 1 else torch.tensor([[-0.3]])
@@ -279,9 +280,9 @@ def test_eigh_both_routes_agree(cuda_pkg, n):
     assert torch.allclose(wt, wj, rtol=0, atol=3e-6)
     for b in range(5):
         _eigh_checks(A[b].cpu(), wt[b].cpu(), Ut[b].cpu(), tol_w=3e-6, tol_res=5e-6, tol_orth=1e-5)
-    assert cuda_pkg.kernels.eigh(A)[2].equal(it)                       # "auto" = tridiagonal route up to 160 nodes
+    assert cuda_pkg.kernels.eigh(A)[2].equal(it)                       # "auto" = tridiagonal route up to 288 nodes
     with pytest.raises(ValueError):
-        K.eigh_tridiag(torch.zeros(1, 161, 161, device="cuda"))
+        K.eigh_tridiag(torch.zeros(1, 289, 289, device="cuda"))
 
 
 @pytest.mark.gpu

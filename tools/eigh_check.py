@@ -29,20 +29,21 @@ def timed(fn, A, reps=3):
         a.record(); r = fn(A); b.record(); torch.cuda.synchronize(); best = min(best, a.elapsed_time(b))
     return r, best
 
-for n in (1, 2, 3, 5, 12, 31, 64, 100, 136, 159, 160):
-    A = torch.stack([O.normalize_adj(O.synth_connectome(n, 50 + s)) if n > 1 else torch.tensor([[0.7]]) for s in range(4)]).cuda()
-    w, U, info = K.eigh_tridiag(A)
-    report("tridiag", A, w, U, info)
-g = torch.Generator().manual_seed(0)
-M = torch.randn(4, 96, 96, generator=g); A = ((M + M.transpose(1, 2)) / 2).cuda()
-w, U, info = K.eigh_tridiag(A); report("tridiag randn96", A, w, U, info)
-A2 = A * 1e-12; w, U, info = K.eigh_tridiag(A2); print("scaled 1e-12: w ratio err", float((w * 1e12 - K.eigh_tridiag(A)[0]).abs().max()), int(info.min()))
-A3 = torch.zeros(2, 40, 40, device="cuda"); w, U, info = K.eigh_tridiag(A3); print("zeros:", float(w.abs().max()), float((U - torch.eye(40, device="cuda")).abs().max()), info.tolist())
-A4 = torch.eye(40, device="cuda")[None] * 3.0; w, U, info = K.eigh_tridiag(A4); print("3I:", float((w - 3).abs().max()), info.tolist())
-A5 = torch.ones(1, 64, 64, device="cuda"); w, U, info = K.eigh_tridiag(A5); report("ones64", A5, w, U, info)
+if __name__ == "__main__":
+    for n in (1, 2, 3, 5, 12, 31, 64, 100, 136, 159, 160):
+        A = torch.stack([O.normalize_adj(O.synth_connectome(n, 50 + s)) if n > 1 else torch.tensor([[0.7]]) for s in range(4)]).cuda()
+        w, U, info = K.eigh_tridiag(A)
+        report("tridiag", A, w, U, info)
+    g = torch.Generator().manual_seed(0)
+    M = torch.randn(4, 96, 96, generator=g); A = ((M + M.transpose(1, 2)) / 2).cuda()
+    w, U, info = K.eigh_tridiag(A); report("tridiag randn96", A, w, U, info)
+    A2 = A * 1e-12; w, U, info = K.eigh_tridiag(A2); print("scaled 1e-12: w ratio err", float((w * 1e12 - K.eigh_tridiag(A)[0]).abs().max()), int(info.min()))
+    A3 = torch.zeros(2, 40, 40, device="cuda"); w, U, info = K.eigh_tridiag(A3); print("zeros:", float(w.abs().max()), float((U - torch.eye(40, device="cuda")).abs().max()), info.tolist())
+    A4 = torch.eye(40, device="cuda")[None] * 3.0; w, U, info = K.eigh_tridiag(A4); print("3I:", float((w - 3).abs().max()), info.tolist())
+    A5 = torch.ones(1, 64, 64, device="cuda"); w, U, info = K.eigh_tridiag(A5); report("ones64", A5, w, U, info)
 
-gen = torch.Generator(device="cuda").manual_seed(0)
-x = torch.rand(1024, 160, 160, device="cuda", generator=gen); lr = (x + x.transpose(1, 2)) / 2; lr.diagonal(dim1=1, dim2=2).zero_()
-A = pkg.normalize_adj_torch(lr)
-(w, U, info), ms = timed(K.eigh_tridiag, A); report("tridiag 1024x160", A, w, U, info, ms)
-(w, U, info), ms = timed(K.eigh_jacobi, A); report("jacobi 1024x160", A, w, U, info, ms)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand(1024, 160, 160, device="cuda", generator=gen); lr = (x + x.transpose(1, 2)) / 2; lr.diagonal(dim1=1, dim2=2).zero_()
+    A = pkg.normalize_adj_torch(lr)
+    (w, U, info), ms = timed(K.eigh_tridiag, A); report("tridiag 1024x160", A, w, U, info, ms)
+    (w, U, info), ms = timed(K.eigh_jacobi, A); report("jacobi 1024x160", A, w, U, info, ms)

@@ -7,3 +7,9 @@ x = torch.rand(1024, 160, 160, device="cuda", generator=gen); lr = (x + x.transp
 A = pkg.normalize_adj_torch(lr)
 for _ in range(2): K.eigh_tridiag(A)
 torch.cuda.synchronize()
+
+if os.environ.get("GSR_PROF_HR"):
+    x = torch.rand(1024, 268, 268, device="cuda", generator=gen); hr = (x + x.transpose(1, 2)) / 2
+    hr.diagonal(dim1=1, dim2=2).fill_(1.0)
+    for _ in range(2): K.eigh_tridiag(hr)
+    torch.cuda.synchronize()
