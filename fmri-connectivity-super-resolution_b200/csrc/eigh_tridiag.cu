@@ -682,18 +682,28 @@ tridiag_packed_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, f
         if (tau != 0.f) {                              // uniform
             __syncwarp();
             const bool act = i < k;
-            float q0 = 0.f, q1 = 0.f;
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
             if (act) {
+                // A_sym[i][j]: own row up to the diagonal (contiguous), column i of row j beyond it (consecutive over the warp)
+                const int kown = min(k, i + 1);
+                const float4* V4 = reinterpret_cast<const float4*>(vbuf);
                 int j = 0;
-                for (; j + 1 < k; j += 2) {            // A_sym[i][j]: own row up to the diagonal, column i of row j beyond it
-                    const float a0 = L[j <= i ? ti + j : tri(j) + i];
-                    const float a1 = L[j + 1 <= i ? ti + j + 1 : tri(j + 1) + i];
-                    q0 = fmaf(a0, vbuf[j], q0);
-                    q1 = fmaf(a1, vbuf[j + 1], q1);
+                for (; j + 4 <= kown; j += 4) {
+                    const float4 v = V4[j >> 2];
+                    q0 = fmaf(L[ti + j], v.x, q0); q1 = fmaf(L[ti + j + 1], v.y, q1);
+                    q2 = fmaf(L[ti + j + 2], v.z, q2); q3 = fmaf(L[ti + j + 3], v.w, q3);
                 }
-                if (j < k) q0 = fmaf(L[j <= i ? ti + j : tri(j) + i], vbuf[j], q0);
+                for (; j < kown; ++j) q0 = fmaf(L[ti + j], vbuf[j], q0);
+                int tj = tri(j) + i;                   // L[j][i], j > i: address advances by j + 1 per row
+                for (; j + 4 <= k; j += 4) {
+                    const float a0 = L[tj], a1 = L[tj + j + 1], a2 = L[tj + 2 * j + 3], a3 = L[tj + 3 * j + 6];
+                    q0 = fmaf(a0, vbuf[j], q0); q1 = fmaf(a1, vbuf[j + 1], q1);
+                    q2 = fmaf(a2, vbuf[j + 2], q2); q3 = fmaf(a3, vbuf[j + 3], q3);
+                    tj += 4 * j + 10;
+                }
+                for (; j < k; ++j) { q0 = fmaf(L[tj], vbuf[j], q0); tj += j + 1; }
             }
-            const float pi = tau * (q0 + q1);
+            const float pi = tau * ((q0 + q1) + (q2 + q3));
             const float vi = act ? vbuf[i] : 0.f;
             const float pvp = warp_sum(act ? pi * vi : 0.f);
             if (lane == 0) red[w] = pvp;
@@ -713,6 +723,7 @@ tridiag_packed_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, f
             __syncwarp();
             if (act) {
                 const float wi = wbuf[i];
+#pragma unroll 4
                 for (int j = 0; j <= i; ++j) L[ti + j] = fmaf(-vi, wbuf[j], fmaf(-wi, vbuf[j], L[ti + j]));
             }
         } else if (w == nwarps - 1 && lane == 0) {
@@ -769,18 +780,37 @@ tql_apply_smem_kernel(const Work wk, int n, int rows_per_cta) {
             if (tau != 0.f) {
                 const float4* V4 = reinterpret_cast<const float4*>(vr);
                 float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-                const int nch = (k + 3) >> 2;          // v is zero from column k to the end of its 16-column block
-                for (int c = 0; c < nch; ++c) {
-                    const float4 v = V4[c];
+                const int nch = (k + 15) >> 4 << 2;    // whole 16-column blocks: v is zero from column k to the end of its block
+#pragma unroll 1
+                for (int c = 0; c < nch; c += 4) {     // 16 columns per trip: all 20 loads issued before the first FMA
+                    float4 v[4];
+                    float zz[16];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = V4[c + u];
                     const float* zp = z + (4 * c) * LDR + r;
-                    q0 = fmaf(zp[0], v.x, q0); q1 = fmaf(zp[LDR], v.y, q1); q2 = fmaf(zp[2 * LDR], v.z, q2); q3 = fmaf(zp[3 * LDR], v.w, q3);
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) zz[u] = zp[u * LDR];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        q0 = fmaf(zz[4 * u], v[u].x, q0); q1 = fmaf(zz[4 * u + 1], v[u].y, q1);
+                        q2 = fmaf(zz[4 * u + 2], v[u].z, q2); q3 = fmaf(zz[4 * u + 3], v[u].w, q3);
+                    }
                 }
                 const float s = -tau * ((q0 + q1) + (q2 + q3));
-                for (int c = 0; c < nch; ++c) {
-                    const float4 v = V4[c];
+#pragma unroll 1
+                for (int c = 0; c < nch; c += 4) {
+                    float4 v[4];
+                    float zz[16];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = V4[c + u];
                     float* zp = z + (4 * c) * LDR + r;
-                    zp[0] = fmaf(s, v.x, zp[0]); zp[LDR] = fmaf(s, v.y, zp[LDR]);
-                    zp[2 * LDR] = fmaf(s, v.z, zp[2 * LDR]); zp[3 * LDR] = fmaf(s, v.w, zp[3 * LDR]);
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) zz[u] = zp[u * LDR];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        zp[(4 * u) * LDR] = fmaf(s, v[u].x, zz[4 * u]); zp[(4 * u + 1) * LDR] = fmaf(s, v[u].y, zz[4 * u + 1]);
+                        zp[(4 * u + 2) * LDR] = fmaf(s, v[u].z, zz[4 * u + 2]); zp[(4 * u + 3) * LDR] = fmaf(s, v[u].w, zz[4 * u + 3]);
+                    }
                 }
             }
         }
@@ -812,16 +842,20 @@ tql_apply_smem_kernel(const Work wk, int n, int rows_per_cta) {
                     __syncwarp();
                     issue(pos / BLK + 2);
                 }
-                const float2* cs = cring + (pos / BLK % STAGES) * BLK + (pos & (BLK - 1));
+                const float4* cs4 = reinterpret_cast<const float4*>(cring + (pos / BLK % STAGES) * BLK + (pos & (BLK - 1)));
                 float* zp = z + i * LDR + r;
                 float zi[16];
+                float4 q4[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) q4[u] = cs4[u];
 #pragma unroll
                 for (int u = 0; u < 16; ++u) zi[u] = zp[-u * LDR];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const float2 q = cs[u];
-                    zp[(1 - u) * LDR] = fmaf(q.x, rv, q.y * zi[u]);
-                    rv = fmaf(-q.y, rv, q.x * zi[u]);
+                for (int u = 0; u < 8; ++u) {
+                    zp[(1 - 2 * u) * LDR] = fmaf(q4[u].x, rv, q4[u].y * zi[2 * u]);
+                    rv = fmaf(-q4[u].y, rv, q4[u].x * zi[2 * u]);
+                    zp[(-2 * u) * LDR] = fmaf(q4[u].z, rv, q4[u].w * zi[2 * u + 1]);
+                    rv = fmaf(-q4[u].w, rv, q4[u].z * zi[2 * u + 1]);
                 }
                 i -= 16;
                 pos += 16;
