@@ -53,6 +53,16 @@ def main():
     report("vectorize_268", timeit(lambda: K.vectorize(H)), bytes_=2 * 35778 * 4 * B)
     v = K.vectorize(H)
     report("anti_vectorize_268", timeit(lambda: K.anti_vectorize(v, 268)), bytes_=(35778 + 268 * 268) * 4 * B)
+    ms = timeit(lambda: K.eigh_tridiag(A), reps=3, warm=1)
+    w, U, info = K.eigh_tridiag(A)
+    report("eigh_tridiag_160 (K1-K4, the in-step LR route)", ms, flops=9 * 160 ** 3 * B, us_per_graph=round(ms * 1e3 / B, 2),
+           ql_iterations_mean=float(info.float().mean()))
+    hr_t = (H + H.transpose(1, 2)) / 2
+    hr_t.diagonal(dim1=1, dim2=2).fill_(1.0)
+    ms = timeit(lambda: K.eigh_tridiag(hr_t), reps=2, warm=1)
+    report("eigh_tridiag_268 (HR target, shared-memory variants)", ms, flops=9 * 268 ** 3 * B, us_per_graph=round(ms * 1e3 / B, 2))
+    ms = timeit(lambda: K.eigh_jacobi(hr_t), reps=1, warm=1)
+    report("eigh_jacobi_268 (global-workspace variant, for context)", ms, flops=9 * 268 ** 3 * B, us_per_graph=round(ms * 1e3 / B, 2))
     ms = timeit(lambda: K.eigh_jacobi(A), reps=3, warm=1)
     w, U, info = K.eigh_jacobi(A)
     report("eigh_jacobi_160", ms, flops=9 * 160 ** 3 * B, us_per_graph=round(ms * 1e3 / B, 2),
