@@ -337,6 +337,7 @@ tql_scalar_kernel(const Work wk, int n, int batch, int max_iter) {
                     float p = d[m], c = 1.0f, s = 0.0f;
                     const float el1 = e[l + 1];
                     float ei = e[m - 1], di = d[m - 1];
+#pragma unroll 4
                     for (int q = m - 1; q >= l; --q) {
                         const float ein = e[q - 1], din = d[q - 1];             // next rotation's operands (index -1 is padding)
                         const float gg = c * ei, hh = c * p;
