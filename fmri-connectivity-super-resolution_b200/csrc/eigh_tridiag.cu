@@ -722,10 +722,12 @@ tridiag_packed_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, f
             const int kpad = (k + 15) & ~15;
             for (int j = lane; j < kpad; j += 32) wbuf[j] = (j < k) ? fmaf(-coef, vbuf[j], pbuf[j]) : 0.0f;        // every warp: same values
             __syncwarp();
-            if (act) {
-                const float wi = wbuf[i];
-#pragma unroll 4
-                for (int j = 0; j <= i; ++j) L[ti + j] = fmaf(-vi, wbuf[j], fmaf(-wi, vbuf[j], L[ti + j]));
+            // rank-2 update of the stored triangle, rows dealt to the warps round robin (row a has a + 1 entries:
+            // a thread-per-row update would leave the warp of the last rows with twice the average work)
+            for (int a = w; a < k; a += nwarps) {
+                const float va = vbuf[a], wa = wbuf[a];
+                float* La = L + tri(a);
+                for (int j = lane; j <= a; j += 32) La[j] = fmaf(-va, wbuf[j], fmaf(-wa, vbuf[j], La[j]));
             }
         } else if (w == nwarps - 1 && lane == 0) {
             Vg[(size_t)k * LDVB + BIGN] = 0.f;
