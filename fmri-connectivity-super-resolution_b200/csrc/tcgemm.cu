@@ -245,11 +245,10 @@ tcgemm_kernel(const Params p) {
         mbar_init(bar_accum, 1);
         fence_barrier_init();
     }
-    if (warp == PRODUCER_WARPS) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    __syncthreads();                                                      // barriers initialised
+    // The tensor-memory allocation (MMA warp only, below) overlaps with the producers' address set-up and their
+    // first loads: nobody but the MMA thread needs the accumulator address before the accumulator barrier fires.
+    uint32_t tmem_base = 0;
 
     if (warp < PRODUCER_WARPS) {
         // ===== producers: global fp32 -> (hi, lo) tf32 tiles in shared memory.
@@ -333,6 +332,11 @@ tcgemm_kernel(const Params p) {
         }
     } else {
         // ===== MMA issuer: one elected lane
+        tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+        tc_fence_before();
+        __syncwarp();
+        tc_fence_after();
+        tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
         if (lane == 0) {
             const uint32_t idesc0 = instr_desc(n_first, TA ? 1 : 0, TB ? 0 : 1);
             const uint32_t idesc1 = instr_desc(n_second > 0 ? n_second : 16, TA ? 1 : 0, TB ? 0 : 1);
@@ -395,6 +399,7 @@ tcgemm_kernel(const Params p) {
     if (warp < EPILOGUE_WARPS) {
         mbar_wait(bar_accum, 0);
         tc_fence_after();
+        tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
         const int q = warp & 3, part = warp >> 2;                          // TMEM lane quarter, column group
         constexpr int COLS_PER_PART = BN / (EPILOGUE_WARPS / 4);            // 96
         const int r = q * 32 + lane;
