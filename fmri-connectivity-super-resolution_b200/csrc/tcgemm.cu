@@ -58,6 +58,7 @@ struct Params {
 };
 
 int g_mn_swap = 0;      // bring-up knob (unused)
+int g_pairs = 1;        // gsr_tcgemm_debug key 1: CTA-pair kernel (cta_group::2) for gsr_tcgemm_f32 (default), 0 = one CTA per tile
 
 #ifdef GSR_TC_TRACE
 // Pipeline trace (tools/tc_trace.py builds a private copy of the library with -DGSR_TC_TRACE):
@@ -461,6 +462,279 @@ tcgemm_kernel(const Params p) {
     if (warp == PRODUCER_WARPS) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------- the CTA-pair kernel (tcgen05 cta_group::2)
+// Two CTAs on the two SMs of a TPC compute a 256-row block: each stages its own 128 rows of A but only HALF of
+// the B operand, and the leader issues M = 256 MMAs that read both halves (tools/probes/tc2_probe.cu established
+// on the hardware that thread-staged canonical tiles work and that CTA rank r supplies B rows r N/2 ..).  B is
+// 69 % of the staging work of a 128 x 288 tile, so the pair moves 35 % less through the load / split / store path
+// that bounds tcgemm_kernel (profiles/r1_tcgemm_pipeline_trace.txt).
+//   * K-major B (op(B) = B^T): N ranges 160 + 112, the pair member holds rows [80 r, 80 r + 80) and
+//     [160 + 56 r, 160 + 56 r + 56) -- 136 local rows;
+//   * MN-major B: the 128B_BASE32B atoms are 32 columns wide, so the ranges are 192 + 128 (320 >= 268, the
+//     padding costs MMA time only) and the member holds columns [96 r, 96 r + 96) and [192 + 64 r, .. + 64).
+//   * full[s] lives in the leader and counts the producers of BOTH CTAs (the peer arrives through DSMEM with
+//     release.cluster); tcgen05.commit multicasts the stage release and the accumulator-ready signal to both.
+constexpr int B2_ROWS_K = 136, B2_ROWS_MN = 160;
+constexpr int B2_TILE_MAX = B2_ROWS_MN * BK * 4;                 // 20480
+constexpr int STAGE2_BYTES = 2 * A_TILE + 2 * B2_TILE_MAX;       // 73728
+constexpr int STAGES2 = 2;                                       // three stages (216 KB) measured slower: they leave no L1 for the operand loads
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 128;
+constexpr int CPITCH2 = 276;                                     // epilogue staging pitch (128 x 276 floats = 141 KB of the 216 KB of stages)
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait_cluster(bar, parity); ++spin)
+        if (spin > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {     // arrives on `bar` of BOTH CTAs once the MMAs issued so far retire
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                 "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "setp.ne.b32 p, %6, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t}"
+                 :: "r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint32_t instr_desc2(int n, int a_mn_major, int b_mn_major) {      // M = 256
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <bool TA, bool TB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+tcgemm2_kernel(const Params p) {
+    constexpr int BROWS = TB ? B2_ROWS_K : B2_ROWS_MN;            // local B tile rows (N extent held by this CTA)
+    constexpr int R0 = TB ? 80 : 96, R1 = TB ? 56 : 64;           // per-CTA share of the two N ranges
+    constexpr int NR0 = 2 * R0, NR1 = 2 * R1;                     // UMMA N of the two ranges: 160 + 112 / 192 + 128
+    constexpr int B2_TILE = BROWS * BK * 4;
+    constexpr int B2_PATCHES = BROWS * BK / 128;                  // 34 / 40
+    constexpr int PATCHES2 = A_PATCHES + B2_PATCHES;              // 66 / 72
+    constexpr int ITERS2 = (PATCHES2 + GROUP_WARPS - 1) / GROUP_WARPS;   // 10 / 11
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);  // full[3] (leader's are used), empty[3], accum
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 1);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES2), bar_accum = smem_u32(bars + 2 * STAGES2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_rank();
+    const int m0 = (blockIdx.x) * BM;                             // blockIdx.x = 2 pair + rank: consecutive M tiles
+    const int nkb = (p.K + BK - 1) / BK;
+    const int b = blockIdx.z;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(bar_full + 8 * s, 2 * GROUP_WARPS * 32); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_accum, 1);
+        fence_barrier_init();
+    }
+    if (warp == PRODUCER_WARPS) tmem_alloc2(smem_u32(tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                           // both CTAs: barriers initialised, TMEM allocated
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp < PRODUCER_WARPS) {
+        const int grp = warp / GROUP_WARPS, gw = warp % GROUP_WARPS;
+        int goff[ITERS2];
+        uint32_t so[ITERS2];
+        uint32_t ok_mask = 0, dead_mask = 0;
+        const int rows_valid = p.M - m0;
+#pragma unroll
+        for (int i = 0; i < ITERS2; ++i) {
+            const int patch = gw + i * GROUP_WARPS;
+            int row = 0, k = 0;
+            goff[i] = 0; so[i] = 0;
+            if (patch < A_PATCHES) {
+                patch_coords<BM, !TA>(patch, lane, row, k, so[i]);
+                if ((TA ? (patch % (BM / 32)) * 32 : (patch >> 1) * 8) >= rows_valid) dead_mask |= 1u << i;
+                row += m0;
+                goff[i] = TA ? k * p.lda + row : row * p.lda + k;
+                if (TA ? (row + 3 < p.M) : (row < p.M)) ok_mask |= 1u << i;
+            } else if (patch < PATCHES2) {
+                patch_coords<BROWS, TB>(patch - A_PATCHES, lane, row, k, so[i]);
+                // local row / column of the half tile -> column n of op(B)
+                const int n = row < R0 ? R0 * (int)rank + row : NR0 + R1 * (int)rank + (row - R0);
+                goff[i] = TB ? n * p.ldb + k : k * p.ldb + n;
+                if (TB ? (n < p.N) : (n + 3 < p.N)) ok_mask |= 1u << i;
+            }
+        }
+        const int a_kadv = TA ? BK * p.lda : BK, b_kadv = TB ? BK : BK * p.ldb;
+        const float* A = p.A + (size_t)b * p.sA;
+        const float* B = p.B + (size_t)b * p.sB;
+        const uint32_t full_leader0 = map_to_cta(bar_full, 0);
+        for (int kb = grp; kb < nkb; kb += 2) {                        // group g stages the k-blocks g, g + 2, ... ; stage = kb % 3
+            const int sidx = kb % STAGES2, use = kb / STAGES2;
+            uint8_t* st = smem + sidx * STAGE2_BYTES;
+            float4 v[ITERS2];
+            const bool whole = (kb + 1) * BK <= p.K;
+#pragma unroll
+            for (int i = 0; i < ITERS2; ++i) {
+                const int patch = gw + i * GROUP_WARPS;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (patch < PATCHES2 && ((ok_mask >> i) & 1u)) {
+                    const float* src = patch < A_PATCHES ? A + goff[i] + kb * a_kadv : B + goff[i] + kb * b_kadv;
+                    const bool kmajor = patch < A_PATCHES ? !TA : TB;          // float4 runs along k
+                    if (whole) v[i] = __ldg(reinterpret_cast<const float4*>(src));
+                    else {
+                        // ragged last k-block: K % 4 == 0 here (checked by the launcher), so a float4 along k is all in or all
+                        // out; along the rows the whole k-row is in or out
+                        int row, k; uint32_t dummy;
+                        if (patch < A_PATCHES) patch_coords<BM, !TA>(patch, lane, row, k, dummy);
+                        else patch_coords<BROWS, TB>(patch - A_PATCHES, lane, row, k, dummy);
+                        (void)kmajor;
+                        if (kb * BK + k < p.K) v[i] = __ldg(reinterpret_cast<const float4*>(src));
+                    }
+                }
+            }
+            if (use > 0) mbar_wait(bar_empty + 8 * sidx, (use - 1) & 1);
+#pragma unroll
+            for (int i = 0; i < ITERS2; ++i) {
+                const int patch = gw + i * GROUP_WARPS;
+                if (patch < A_PATCHES) { if (!((dead_mask >> i) & 1u)) store_split(st, st + A_TILE, so[i], v[i]); }
+                else if (patch < PATCHES2) store_split(st + 2 * A_TILE, st + 2 * A_TILE + B2_TILE, so[i], v[i]);
+            }
+            fence_async_smem();
+            mbar_arrive_cluster(full_leader0 + 8 * sidx);          // the leader's full[stage] counts both CTAs' producers
+        }
+    } else {
+        if (rank == 0 && lane == 0) {
+            const uint32_t idesc0 = instr_desc2(NR0, TA ? 1 : 0, TB ? 0 : 1);
+            const uint32_t idesc1 = instr_desc2(NR1, TA ? 1 : 0, TB ? 0 : 1);
+            const uint32_t a_lt = TA ? 1u : 0u, b_lt = TB ? 0u : 1u;
+            const uint32_t a_lbo = TA ? 512 : 128, a_sbo = TA ? (BM / 32) * 512 : (BK / 4) * 128;
+            const uint32_t b_lbo = TB ? 128 : 512, b_sbo = TB ? (BK / 4) * 128 : (BROWS / 32) * 512;
+            const uint32_t a_kstep = TA ? 2 * (BM / 32) * 512 : 256, b_kstep = TB ? 256 : 2 * (BROWS / 32) * 512;
+            const uint32_t b_n1 = TB ? (R0 / 8) * ((BK / 4) * 128) : (R0 / 32) * 512;
+            const uint32_t a_dhi = desc_hi(a_sbo, a_lt), b_dhi = desc_hi(b_sbo, b_lt);
+            const uint32_t a_step = a_kstep >> 4, b_step = b_kstep >> 4, n1 = b_n1 >> 4;
+            uint32_t acc = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES2, use = kb / STAGES2;
+                mbar_wait_cluster(bar_full + 8 * s, use & 1);
+                tc_fence_after();
+                const uint32_t stb = smem_u32(smem + s * STAGE2_BYTES);
+                uint32_t ah = desc_lo(stb, a_lbo), al = desc_lo(stb + A_TILE, a_lbo);
+                uint32_t bh = desc_lo(stb + 2 * A_TILE, b_lbo), bl = desc_lo(stb + 2 * A_TILE + B2_TILE, b_lbo);
+#pragma unroll
+                for (int j = 0; j < BK / 8; ++j) {
+                    umma2_tf32(tmem_base, al, a_dhi, bh, b_dhi, idesc0, acc);
+                    umma2_tf32(tmem_base, ah, a_dhi, bl, b_dhi, idesc0, 1u);
+                    umma2_tf32(tmem_base, ah, a_dhi, bh, b_dhi, idesc0, 1u);
+                    umma2_tf32(tmem_base + NR0, al, a_dhi, bh + n1, b_dhi, idesc1, acc);
+                    umma2_tf32(tmem_base + NR0, ah, a_dhi, bl + n1, b_dhi, idesc1, 1u);
+                    umma2_tf32(tmem_base + NR0, ah, a_dhi, bh + n1, b_dhi, idesc1, 1u);
+                    acc = 1u;
+                    ah += a_step; al += a_step; bh += b_step; bl += b_step;
+                }
+                umma_commit2(bar_empty + 8 * s);
+            }
+            umma_commit2(bar_accum);
+        }
+        __syncwarp();
+    }
+
+    // ===== epilogue (each CTA drains its own 128 accumulator rows; accumulator column c = column n of the product)
+    float* Cs = reinterpret_cast<float*>(smem);
+    const int ncols = min(p.N, NR0 + NR1);
+    if (warp < EPILOGUE_WARPS) {
+        mbar_wait(bar_accum, 0);
+        tc_fence_after();
+        const int q = warp & 3, part = warp >> 2;
+        constexpr int COLS_PER_PART = 96;
+        const int r = q * 32 + lane;
+        const int c_begin = part * COLS_PER_PART;
+        const int c_end = (q * 32 < p.M - m0) ? min(c_begin + COLS_PER_PART, (ncols + 31) & ~31) : c_begin;
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+                if (c0 + i < CPITCH2 - 4) *reinterpret_cast<uint4*>(Cs + r * CPITCH2 + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    {
+        float* C = p.C + (size_t)b * p.sC;
+        const int ldc = p.ldc;
+        const float* extra = (p.epilogue == GSR_EPI_ADD) ? p.extra + (size_t)b * p.s_extra : nullptr;
+        const int rows = min(BM, p.M - m0), cols = ncols;
+        const int epi = p.epilogue;
+        const float alpha = p.alpha;
+        const int c4n = cols >> 2;                                   // the launcher guarantees N % 4 == 0 and aligned operands
+        for (int e = tid; e < rows * c4n; e += THREADS) {
+            const int r = e / c4n, c = (e - r * c4n) << 2;
+            float4 v = *reinterpret_cast<const float4*>(Cs + r * CPITCH2 + c);
+            v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
+            if (epi == GSR_EPI_BIAS) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.extra + c));
+                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            } else if (epi == GSR_EPI_ADD) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(extra + (size_t)(m0 + r) * p.ld_extra + c));
+                v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+            }
+            *reinterpret_cast<float4*>(C + (size_t)(m0 + r) * ldc + c) = v;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                           // the peer may still be reading this CTA's B half / TMEM pair
+    if (warp == PRODUCER_WARPS) tmem_dealloc2(tmem_base, TMEM_COLS);
+}
+
+// Pairs cover the first 2 * floor(tiles_m / 2) M tiles; a last odd tile (the 12 ragged rows of a 268-row subject
+// matrix) goes through tcgemm_kernel on an offset view.
+static bool pair_ok(const Params& p) {
+    return p.N <= 268 + 4 && p.N % 4 == 0 && p.K % 4 == 0 && p.M >= 2 * BM && p.ldc % 4 == 0 && aligned16(p.C) && p.sC % 4 == 0 &&
+           (p.epilogue == GSR_EPI_NONE || (aligned16(p.extra) && (p.epilogue != GSR_EPI_ADD || (p.ld_extra % 4 == 0 && p.s_extra % 4 == 0))));
+}
+
+static int launch_pairs(const Params& p, int transA, int transB, cudaStream_t st) {
+    const int tiles_m = (p.M + BM - 1) / BM, pairs = tiles_m / 2;
+    dim3 grid(2 * pairs, 1, p.batch);
+#define GSR_TC2_LAUNCH(TA, TB)                                                                                   \
+    do {                                                                                                          \
+        auto k = tcgemm2_kernel<TA, TB>;                                                                          \
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);        \
+        if (e != cudaSuccess) return fail((int)e, "tcgemm2: cudaFuncSetAttribute failed");                       \
+        k<<<grid, THREADS, SMEM2_BYTES, st>>>(p);                                                                 \
+    } while (0)
+    if (!transA && !transB) GSR_TC2_LAUNCH(false, false);
+    else if (!transA && transB) GSR_TC2_LAUNCH(false, true);
+    else if (transA && !transB) GSR_TC2_LAUNCH(true, false);
+    else GSR_TC2_LAUNCH(true, true);
+#undef GSR_TC2_LAUNCH
+    return launched("tcgemm2");
+}
+
 template <bool REDUCE>
 static int launch(const Params& p, int transA, int transB, dim3 grid, cudaStream_t st) {
 #define GSR_TC_LAUNCH(TA, TB)                                                                                     \
@@ -502,6 +776,7 @@ using namespace gsr;
 
 extern "C" __attribute__((visibility("default"))) int gsr_tcgemm_debug(int key, int value) {
     if (key == 0) tc::g_mn_swap = value;
+    if (key == 1) tc::g_pairs = value;
     return 0;
 }
 #ifdef GSR_TC_TRACE
@@ -528,6 +803,21 @@ extern "C" int gsr_tcgemm_f32(const float* A, const float* B, float* C,
     tc::Params p{A, B, C, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch, 1, alpha,
                  epilogue, extra, ld_extra, stride_extra, tc::g_mn_swap};
     if (!tc::operands_ok(p)) return fail(GSR_E_ALIGN, "tcgemm: operands must be 16-byte aligned with leading dimensions % 4 == 0");
+    if (tc::g_pairs && tc::pair_ok(p) && (long long)(transA ? K : M) * lda < 0x7fffffffLL && (long long)(transB ? N : K) * ldb < 0x7fffffffLL) {
+        // CTA pairs (cta_group::2) for the first 2 * floor(tiles / 2) M tiles, the one-CTA kernel for an odd last tile
+        int rc = tc::launch_pairs(p, transA, transB, (cudaStream_t)stream);
+        if (rc) return rc;
+        const int tiles_m = (M + tc::BM - 1) / tc::BM;
+        if (tiles_m % 2 == 0) return 0;
+        const int m_done = (tiles_m - 1) * tc::BM;
+        tc::Params t = p;
+        t.M = M - m_done;
+        t.A = A + (transA ? (size_t)m_done : (size_t)m_done * lda);
+        t.C = C + (size_t)m_done * ldc;
+        if (epilogue == GSR_EPI_ADD) t.extra = extra + (size_t)m_done * ld_extra;
+        dim3 gt(1, (N + tc::BN - 1) / tc::BN, batch);
+        return tc::launch<false>(t, transA, transB, gt, (cudaStream_t)stream);
+    }
     dim3 grid((M + tc::BM - 1) / tc::BM, (N + tc::BN - 1) / tc::BN, batch);
     if (grid.y > 65535) return fail(GSR_E_UNSUPPORTED, "tcgemm: N too large");
     return tc::launch<false>(p, transA, transB, grid, (cudaStream_t)stream);

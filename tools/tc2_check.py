@@ -1,0 +1,48 @@
+"""CTA-pair tcgemm (gsr_tcgemm_debug key 1): accuracy against float64 and time against the one-CTA kernel."""
+import ctypes, importlib, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+pkg = importlib.import_module("fmri-connectivity-super-resolution_b200"); K = pkg.kernels
+lib = pkg.lib()
+dbg = lib.gsr_tcgemm_debug; dbg.argtypes = [ctypes.c_int, ctypes.c_int]; dbg.restype = ctypes.c_int
+g = torch.Generator(device="cuda").manual_seed(0)
+def timeit(fn, reps=5):
+    for _ in range(2): fn()
+    torch.cuda.synchronize(); ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    return sorted(ts)[len(ts) // 2]
+Bs = 6
+X = torch.randn(Bs, 268, 268, device="cuda", generator=g); Y = torch.randn(Bs, 268, 268, device="cuda", generator=g)
+W = torch.randn(268, 268, device="cuda", generator=g); Wl = torch.randn(268, 160, device="cuda", generator=g)
+U = torch.randn(Bs, 160, 160, device="cuda", generator=g); add = torch.randn(Bs, 268, 268, device="cuda", generator=g)
+cases = {
+    "NN per-subject": (lambda: K.bgemm(X, Y), lambda: X.double() @ Y.double()),
+    "NT per-subject": (lambda: K.bgemm(X, Y, transB=True), lambda: X.double() @ Y.double().transpose(1, 2)),
+    "TN per-subject": (lambda: K.bgemm(X, Y, transA=True), lambda: X.double().transpose(1, 2) @ Y.double()),
+    "NN + add, alpha": (lambda: K.bgemm(X, Y, alpha=2.0, add=add), lambda: 2 * (X.double() @ Y.double()) + add.double()),
+    "NN stacked W": (lambda: K.bgemm(X, W), lambda: X.double() @ W.double()),
+    "NT stacked W": (lambda: K.bgemm(X, W, transB=True), lambda: X.double() @ W.double().T),
+    "NT stacked U.W^T (K=160)": (lambda: K.bgemm(U, Wl, transB=True), lambda: U.double() @ Wl.double().T),
+    "NT stacked N=160 (K=268)": (lambda: K.bgemm(X, Wl.T.contiguous(), transB=True), lambda: X.double() @ Wl.double()),
+}
+for pairs in (0, 1):
+    dbg(1, pairs)
+    for name, (fn, ref) in cases.items():
+        out = fn(); torch.cuda.synchronize()
+        r = ref()
+        err = float((out.double() - r).abs().max()); scale = float(r.abs().max())
+        print(json.dumps({"pairs": pairs, "case": name, "max_err": err, "rel": err / scale}), flush=True)
+B = 1024
+X = torch.rand(B, 268, 268, device="cuda", generator=g); Y = torch.rand(B, 268, 268, device="cuda", generator=g)
+fl = 2 * 268 ** 3 * B
+for pairs in (0, 1):
+    dbg(1, pairs)
+    r = {"pairs": pairs}
+    for name, fn in (("NN per-subject", lambda: K.bgemm(X, Y)), ("NT per-subject", lambda: K.bgemm(X, Y, transB=True)),
+                     ("TN per-subject", lambda: K.bgemm(X, Y, transA=True)), ("NN stacked W", lambda: K.bgemm(X, W)),
+                     ("NT stacked W", lambda: K.bgemm(X, W, transB=True))):
+        ms = timeit(fn); r[name] = [round(ms, 4), round(fl / ms / 1e9, 1)]
+    print(json.dumps(r), flush=True)
+dbg(1, 0)
