@@ -419,7 +419,7 @@ tcgemm_kernel(const Params p) {
     {
         float* C;
         int ldc;
-        if (REDUCE) { C = p.C + (size_t)blockIdx.z * p.M * p.N; ldc = p.N; }
+        if (REDUCE) { C = p.C + (size_t)blockIdx.z * p.sC; ldc = p.N; }
         else        { C = p.C + (size_t)blockIdx.z * p.sC;      ldc = p.ldc; }
         const float* extra = (!REDUCE && p.epilogue == GSR_EPI_ADD) ? p.extra + (size_t)blockIdx.z * p.s_extra : nullptr;
         const int rows = min(BM, p.M - m0), cols = min(BN, p.N - n0);
@@ -528,7 +528,7 @@ __device__ __forceinline__ uint32_t instr_desc2(int n, int a_mn_major, int b_mn_
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
-template <bool TA, bool TB>
+template <bool TA, bool TB, bool REDUCE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tcgemm2_kernel(const Params p) {
     constexpr int BROWS = TB ? B2_ROWS_K : B2_ROWS_MN;            // local B tile rows (N extent held by this CTA)
@@ -547,7 +547,11 @@ tcgemm2_kernel(const Params p) {
     const uint32_t rank = cluster_rank();
     const int m0 = (blockIdx.x) * BM;                             // blockIdx.x = 2 pair + rank: consecutive M tiles
     const int nkb = (p.K + BK - 1) / BK;
-    const int b = blockIdx.z;
+    // REDUCE (weight gradients): the pair accumulates the subjects blockIdx.z, blockIdx.z + splits, ... in TMEM
+    const int b_first = blockIdx.z;
+    const int b_step = REDUCE ? p.splits : p.batch;
+    const int nsub = REDUCE ? (p.batch - b_first + b_step - 1) / b_step : 1;
+    const int total_kb = nsub * nkb;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES2; ++s) { mbar_init(bar_full + 8 * s, 2 * GROUP_WARPS * 32); mbar_init(bar_empty + 8 * s, 1); }
@@ -587,11 +591,13 @@ tcgemm2_kernel(const Params p) {
             }
         }
         const int a_kadv = TA ? BK * p.lda : BK, b_kadv = TB ? BK : BK * p.ldb;
-        const float* A = p.A + (size_t)b * p.sA;
-        const float* B = p.B + (size_t)b * p.sB;
         const uint32_t full_leader0 = map_to_cta(bar_full, 0);
-        for (int kb = grp; kb < nkb; kb += 2) {                        // group g stages the k-blocks g, g + 2, ... ; stage = kb % 3
-            const int sidx = kb % STAGES2, use = kb / STAGES2;
+        int sub = 0, kb = grp;                                         // k-block `it` = (subject sub of this pair, k-block kb)
+        for (int it = grp; it < total_kb; it += 2) {                   // group g stages the k-blocks g, g + 2, ...
+            while (kb >= nkb) { kb -= nkb; ++sub; }
+            const float* A = p.A + (size_t)(b_first + sub * b_step) * p.sA;
+            const float* B = p.B + (size_t)(b_first + sub * b_step) * p.sB;
+            const int sidx = it % STAGES2, use = it / STAGES2;
             uint8_t* st = smem + sidx * STAGE2_BYTES;
             float4 v[ITERS2];
             const bool whole = (kb + 1) * BK <= p.K;
@@ -623,6 +629,7 @@ tcgemm2_kernel(const Params p) {
             }
             fence_async_smem();
             mbar_arrive_cluster(full_leader0 + 8 * sidx);          // the leader's full[stage] counts both CTAs' producers
+            kb += 2;
         }
     } else {
         if (rank == 0 && lane == 0) {
@@ -636,8 +643,8 @@ tcgemm2_kernel(const Params p) {
             const uint32_t a_dhi = desc_hi(a_sbo, a_lt), b_dhi = desc_hi(b_sbo, b_lt);
             const uint32_t a_step = a_kstep >> 4, b_step = b_kstep >> 4, n1 = b_n1 >> 4;
             uint32_t acc = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES2, use = kb / STAGES2;
+            for (int it = 0; it < total_kb; ++it) {
+                const int s = it % STAGES2, use = it / STAGES2;
                 mbar_wait_cluster(bar_full + 8 * s, use & 1);
                 tc_fence_after();
                 const uint32_t stb = smem_u32(smem + s * STAGE2_BYTES);
@@ -683,12 +690,12 @@ tcgemm2_kernel(const Params p) {
     tc_fence_before();
     __syncthreads();
     {
-        float* C = p.C + (size_t)b * p.sC;
-        const int ldc = p.ldc;
-        const float* extra = (p.epilogue == GSR_EPI_ADD) ? p.extra + (size_t)b * p.s_extra : nullptr;
+        float* C = p.C + (size_t)blockIdx.z * p.sC;                 // REDUCE: sC = M * N, the pitch of the partials
+        const int ldc = REDUCE ? p.N : p.ldc;
+        const float* extra = (!REDUCE && p.epilogue == GSR_EPI_ADD) ? p.extra + (size_t)blockIdx.z * p.s_extra : nullptr;
         const int rows = min(BM, p.M - m0), cols = ncols;
-        const int epi = p.epilogue;
-        const float alpha = p.alpha;
+        const int epi = REDUCE ? GSR_EPI_NONE : p.epilogue;
+        const float alpha = REDUCE ? 1.0f : p.alpha;
         const int c4n = cols >> 2;                                   // the launcher guarantees N % 4 == 0 and aligned operands
         for (int e = tid; e < rows * c4n; e += THREADS) {
             const int r = e / c4n, c = (e - r * c4n) << 2;
@@ -717,12 +724,13 @@ static bool pair_ok(const Params& p) {
            (p.epilogue == GSR_EPI_NONE || (aligned16(p.extra) && (p.epilogue != GSR_EPI_ADD || (p.ld_extra % 4 == 0 && p.s_extra % 4 == 0))));
 }
 
-static int launch_pairs(const Params& p, int transA, int transB, cudaStream_t st) {
+template <bool REDUCE>
+static int launch_pairs(const Params& p, int transA, int transB, int zdim, cudaStream_t st) {
     const int tiles_m = (p.M + BM - 1) / BM, pairs = tiles_m / 2;
-    dim3 grid(2 * pairs, 1, p.batch);
+    dim3 grid(2 * pairs, 1, zdim);
 #define GSR_TC2_LAUNCH(TA, TB)                                                                                   \
     do {                                                                                                          \
-        auto k = tcgemm2_kernel<TA, TB>;                                                                          \
+        auto k = tcgemm2_kernel<TA, TB, REDUCE>;                                                                  \
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);        \
         if (e != cudaSuccess) return fail((int)e, "tcgemm2: cudaFuncSetAttribute failed");                       \
         k<<<grid, THREADS, SMEM2_BYTES, st>>>(p);                                                                 \
@@ -732,7 +740,7 @@ static int launch_pairs(const Params& p, int transA, int transB, cudaStream_t st
     else if (transA && !transB) GSR_TC2_LAUNCH(true, false);
     else GSR_TC2_LAUNCH(true, true);
 #undef GSR_TC2_LAUNCH
-    return launched("tcgemm2");
+    return launched(REDUCE ? "tcgemm2_reduce" : "tcgemm2");
 }
 
 template <bool REDUCE>
@@ -756,14 +764,17 @@ static bool operands_ok(const Params& p) {
     return aligned16(p.A) && aligned16(p.B) && (p.lda % 4 == 0) && (p.ldb % 4 == 0) && (p.sA % 4 == 0) && (p.sB % 4 == 0);
 }
 
-// C[m][n] = alpha * sum_z ws[z][m][n] (+ extra[m][n]); fixed summation order.
+// C[m][n] = alpha * sum_z ws[z][m][n] (+ extra[m][n]); fixed summation order.  Rows below m_head hold
+// `splits` partials (CTA-pair launch), the rows from m_head on hold `splits_tail` (one-CTA launch of the odd tile).
 __global__ void reduce_partials_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
-                                       int splits, float alpha, const float* __restrict__ extra, int ld_extra) {
+                                       int splits, int m_head, int splits_tail, float alpha,
+                                       const float* __restrict__ extra, int ld_extra) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= M * N) return;
     const int m = e / N, n = e - m * N;
+    const int nz = m < m_head ? splits : splits_tail;
     float acc = 0.f;
-    for (int z = 0; z < splits; ++z) acc += __ldg(ws + (size_t)z * M * N + e);
+    for (int z = 0; z < nz; ++z) acc += __ldg(ws + (size_t)z * M * N + e);
     acc *= alpha;
     if (extra) acc += __ldg(extra + (size_t)m * ld_extra + n);
     C[(size_t)m * ldc + n] = acc;
@@ -805,7 +816,7 @@ extern "C" int gsr_tcgemm_f32(const float* A, const float* B, float* C,
     if (!tc::operands_ok(p)) return fail(GSR_E_ALIGN, "tcgemm: operands must be 16-byte aligned with leading dimensions % 4 == 0");
     if (tc::g_pairs && tc::pair_ok(p) && (long long)(transA ? K : M) * lda < 0x7fffffffLL && (long long)(transB ? N : K) * ldb < 0x7fffffffLL) {
         // CTA pairs (cta_group::2) for the first 2 * floor(tiles / 2) M tiles, the one-CTA kernel for an odd last tile
-        int rc = tc::launch_pairs(p, transA, transB, (cudaStream_t)stream);
+        int rc = tc::launch_pairs<false>(p, transA, transB, batch, (cudaStream_t)stream);
         if (rc) return rc;
         const int tiles_m = (M + tc::BM - 1) / tc::BM;
         if (tiles_m % 2 == 0) return 0;
@@ -829,7 +840,11 @@ extern "C" size_t gsr_tcgemm_reduce_workspace(int M, int N, int batch, int* spli
     if (splits > batch) splits = batch;
     if (splits < 1) splits = 1;
     if (splits_out) *splits_out = splits;
-    return (size_t)splits * (size_t)M * (size_t)N;
+    // the odd last M tile of the CTA-pair path is split over every SM on its own (gsr_tcgemm_reduce_f32)
+    const int tiles_m = (M + tc::BM - 1) / tc::BM;
+    int most = splits;
+    if (tiles_m > 1 && (tiles_m & 1)) most = std::min(batch, splits * tiles_m);
+    return (size_t)most * (size_t)M * (size_t)N;
 }
 
 extern "C" int gsr_tcgemm_reduce_f32(const float* A, const float* B, float* C,
@@ -843,14 +858,40 @@ extern "C" int gsr_tcgemm_reduce_f32(const float* A, const float* B, float* C,
     if (epilogue != GSR_EPI_NONE && epilogue != GSR_EPI_ADD) return fail(GSR_E_ARG, "tcgemm_reduce: epilogue must be NONE or ADD");
     if (epilogue == GSR_EPI_ADD && !extra) return fail(GSR_E_ARG, "tcgemm_reduce: epilogue needs `extra`");
     if (splits > batch) splits = batch;
-    tc::Params p{A, B, workspace, M, N, K, lda, ldb, N, strideA, strideB, 0, batch, splits, 1.0f,
+    tc::Params p{A, B, workspace, M, N, K, lda, ldb, N, strideA, strideB, (long long)M * N, batch, splits, 1.0f,
                  GSR_EPI_NONE, nullptr, 0, 0, tc::g_mn_swap};
     if (!tc::operands_ok(p)) return fail(GSR_E_ALIGN, "tcgemm_reduce: operands must be 16-byte aligned with leading dimensions % 4 == 0");
-    dim3 grid((M + tc::BM - 1) / tc::BM, (N + tc::BN - 1) / tc::BN, splits);
-    int rc = tc::launch<true>(p, transA, transB, grid, (cudaStream_t)stream);
-    if (rc) return rc;
+    const int tiles_m = (M + tc::BM - 1) / tc::BM;
+    int m_head = M, splits_tail = splits, rc;
+    if (tc::g_pairs && tc::pair_ok(p)) {
+        // CTA pairs take the even number of leading M tiles with half as many splits (one pair = two SMs); the odd
+        // last tile keeps the one-CTA kernel and its own split count.  Both write [split][M][N] partials.
+        const int pairs = tiles_m / 2, m_done = pairs * 2 * tc::BM;
+        const int pair_splits = std::max(1, std::min(batch, (splits * tiles_m) / (2 * pairs)));
+        p.splits = pair_splits;
+        rc = tc::launch_pairs<true>(p, transA, transB, pair_splits, (cudaStream_t)stream);
+        if (rc) return rc;
+        if (tiles_m & 1) {
+            // the tail tile still writes partial z at workspace + z*M*N; only the A rows / C rows move
+            tc::Params q = p;
+            q.splits = std::min(batch, splits * tiles_m);
+            q.A = transA ? A + m_done : A + (size_t)m_done * lda;
+            q.C = workspace + (size_t)m_done * N;
+            q.M = M - m_done;
+            dim3 grid(1, 1, q.splits);
+            rc = tc::launch<true>(q, transA, transB, grid, (cudaStream_t)stream);
+            if (rc) return rc;
+            splits_tail = q.splits;
+            m_head = m_done;
+        }
+        splits = pair_splits;
+    } else {
+        dim3 grid(tiles_m, (N + tc::BN - 1) / tc::BN, splits);
+        rc = tc::launch<true>(p, transA, transB, grid, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     const int total = M * N;
     tc::reduce_partials_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        workspace, C, M, N, ldc, splits, alpha, epilogue == GSR_EPI_ADD ? extra : nullptr, ld_extra);
+        workspace, C, M, N, ldc, splits, m_head, splits_tail, alpha, epilogue == GSR_EPI_ADD ? extra : nullptr, ld_extra);
     return launched("tcgemm_reduce_partials");
 }

@@ -407,10 +407,11 @@ def test_bgemm_variants_agree_bitwise(cuda_pkg, K):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
 
 
+@pytest.mark.parametrize("M", [160, 268, 256])            # 268 = one CTA pair + the odd tail tile on the one-CTA kernel
 @pytest.mark.parametrize("tA,tB", [(False, False), (True, False), (False, True)])
-def test_bgemm_reduce(K, gemm_backend, tA, tB):
+def test_bgemm_reduce(K, gemm_backend, tA, tB, M):
     g = torch.Generator().manual_seed(11)
-    batch, M, N, Kd = 37, 160, 268, 268
+    batch, N, Kd = 37, 268, 268
     A = torch.randn((batch, Kd, M) if tA else (batch, M, Kd), generator=g)
     B = torch.randn((batch, N, Kd) if tB else (batch, Kd, N), generator=g)
     add = torch.randn(M, N, generator=g)
