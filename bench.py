@@ -366,7 +366,9 @@ def run_ours(args):
     # --- contraction kernel: tensor-bound.  tcgen05 kind::tf32 runs at half the bf16 rate and the 3xTF32 split
     #     issues three MMAs per algorithmic product, both stated so that `frac` is against the MEASURED bf16 peak.
     gemm_roof = {
-        "kernel": ("gsr::tc::tcgemm_kernel (tcgen05.mma kind::tf32, 3xTF32 split, 128x288x32 tile, accumulators in TMEM)"
+        "kernel": ("gsr::tc::tcgemm2_kernel (tcgen05.mma.cta_group::2 kind::tf32, 3xTF32 split, CTA pair on a 256x272x32 tile, "
+                   "each CTA stages its 128 rows of A and half of B, accumulators in TMEM; odd last tile of 268 on the "
+                   "one-CTA gsr::tc::tcgemm_kernel, 128x288x32)"
                    if backend == "tc" else "gsr::bgemm_kernel (136x136x16 SIMT FP32 tile)"),
         "bound": "tensor" if backend == "tc" else "fp32",
         "achieved": gemm_tflops, "unit": "TFLOP/s (algorithmic fp32 flops of the contractions)",

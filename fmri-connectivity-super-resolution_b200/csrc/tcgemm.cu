@@ -59,6 +59,7 @@ struct Params {
 
 int g_mn_swap = 0;      // bring-up knob (unused)
 int g_pairs = 1;        // gsr_tcgemm_debug key 1: CTA-pair kernel (cta_group::2) for gsr_tcgemm_f32 (default), 0 = one CTA per tile
+int g_tail = 1;         // gsr_tcgemm_debug key 2: FP32 kernel for the <= 16 ragged rows after the CTA pairs when B is row-major (default), 0 = one-CTA tensor kernel
 
 #ifdef GSR_TC_TRACE
 // Pipeline trace (tools/tc_trace.py builds a private copy of the library with -DGSR_TC_TRACE):
@@ -764,20 +765,196 @@ static bool operands_ok(const Params& p) {
     return aligned16(p.A) && aligned16(p.B) && (p.lda % 4 == 0) && (p.ldb % 4 == 0) && (p.sA % 4 == 0) && (p.sB % 4 == 0);
 }
 
+// ---------------------------------------------------------------- the ragged last rows of M (M % 128 <= 16), FP32 FMAs
+// The 12 rows that 268 leaves after two 128-row tiles cost the tensor kernel 70 % of a full tile (all of B is
+// split and staged for 4.5 % of the rows: 150-160 us per 1024 subjects).  For row-major B they are a memory-shaped
+// product instead: the CTA keeps the <= 16 rows of op(A) in shared memory (k-major, 16 floats per k, quad-swizzled
+// so that the one-off transposing store is at most 4-way conflicted), streams B through a cp.async double buffer
+// (a warp per k row, 16-byte copies), and each thread owns two columns n, n + 136 with all rows in registers: per k
+// two scalar LDS, R4 broadcast LDS.128 and 8 R4 FFMA.  Plain FP32 accumulation in k order (the 3xTF32 products of
+// the tensor kernels differ from it by rounding only; tests compare both against float64).  80 us per 1024
+// subjects.  op(B) = B^T and the subject-reduced products stay on the tensor kernel: a transposing variant of this
+// kernel and a reducing one were measured no faster than it (215 / 145 us against 177 / 150 us).
+namespace tail {
+constexpr int T_THREADS = 160, T_HALF = 136, T_COLS = 2 * T_HALF, T_KC = 16, T_KMAX = 288, T_ROWS = 16;
+constexpr int T_SMEM_FLOATS = T_KMAX * T_ROWS + 2 * T_KC * T_COLS;
+
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool TA, int R4>
+__global__ void __launch_bounds__(T_THREADS, 4) tail_kernel(const Params p) {
+    extern __shared__ __align__(16) float tsm[];
+    float* As = tsm;                                   // [k][16], quad q of row k at ((q ^ ((k >> 1) & 3)) << 2)
+    float* Bs = tsm + T_KMAX * T_ROWS;                 // [2][T_KC][T_COLS]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rows = p.M, K = p.K, N = p.N;
+    const int nchunks = (K + T_KC - 1) / T_KC, kpad = nchunks * T_KC;
+    const float* A = p.A + (size_t)blockIdx.z * p.sA;
+    const float* B = p.B + (size_t)blockIdx.z * p.sB;
+
+    auto copy_b = [&](int c) {                         // a warp per k row; rows past K and columns past N are zero filled
+        float* dst = Bs + (c & 1) * T_KC * T_COLS;
+        const int k0 = c * T_KC;
+        for (int kk = warp; kk < T_KC; kk += T_THREADS / 32) {
+            const bool row_ok = k0 + kk < K;
+            const float* src = B + (size_t)(row_ok ? k0 + kk : 0) * p.ldb;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int n4 = (lane + 32 * j) * 4;
+                if (n4 < T_COLS) { const bool ok = row_ok && n4 < N; cp_async16(dst + kk * T_COLS + n4, src + (ok ? n4 : 0), ok); }
+            }
+        }
+        cp_commit();
+    };
+    copy_b(0);
+    // op(A) rows, zero filled to 4 R4 rows and to whole chunks of k (all loads of a thread are issued before its
+    // first store: one memory round trip, not one per row)
+    if (!TA) {
+        float v[R4 * 4][2];
+#pragma unroll
+        for (int r = 0; r < R4 * 4; ++r)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int k = tid + j * T_THREADS;
+                v[r][j] = (r < rows && k < K) ? __ldg(A + (size_t)r * p.lda + k) : 0.f;
+            }
+#pragma unroll
+        for (int r = 0; r < R4 * 4; ++r)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int k = tid + j * T_THREADS;
+                if (k < kpad) As[k * T_ROWS + ((((r >> 2) ^ (k >> 1)) & 3) << 2) + (r & 3)] = v[r][j];
+            }
+    } else {
+        constexpr int PASSES = (T_KMAX + T_THREADS / 16 - 1) / (T_THREADS / 16);       // 29 k rows per thread
+        const int r = tid & 15;
+        float v[PASSES];
+#pragma unroll
+        for (int j = 0; j < PASSES; ++j) {
+            const int k = (tid >> 4) + j * (T_THREADS / 16);
+            v[j] = (r < rows && k < K) ? __ldg(A + (size_t)k * p.lda + r) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < PASSES; ++j) {
+            const int k = (tid >> 4) + j * (T_THREADS / 16);
+            if (r < R4 * 4 && k < kpad) As[k * T_ROWS + ((((r >> 2) ^ (k >> 1)) & 3) << 2) + (r & 3)] = v[j];
+        }
+    }
+    cp_wait<0>();
+    __syncthreads();
+
+    float acc[R4 * 4][2];
+#pragma unroll
+    for (int r = 0; r < R4 * 4; ++r) acc[r][0] = acc[r][1] = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+        // chunk c + 1 goes to the buffer whose last readers (chunk c - 1) all passed the barrier of iteration c - 1
+        if (c + 1 < nchunks) copy_b(c + 1);
+        if (tid < T_HALF) {
+            const float* bs = Bs + (c & 1) * T_KC * T_COLS + tid;
+            const float* as = As + c * T_KC * T_ROWS;
+#pragma unroll
+            for (int kk = 0; kk < T_KC; ++kk) {
+                const float b0 = bs[kk * T_COLS], b1 = bs[kk * T_COLS + T_HALF];
+#pragma unroll
+                for (int q = 0; q < R4; ++q) {
+                    const float4 a = *reinterpret_cast<const float4*>(as + kk * T_ROWS + (((q ^ (kk >> 1)) & 3) << 2));
+                    acc[4 * q + 0][0] = fmaf(a.x, b0, acc[4 * q + 0][0]); acc[4 * q + 0][1] = fmaf(a.x, b1, acc[4 * q + 0][1]);
+                    acc[4 * q + 1][0] = fmaf(a.y, b0, acc[4 * q + 1][0]); acc[4 * q + 1][1] = fmaf(a.y, b1, acc[4 * q + 1][1]);
+                    acc[4 * q + 2][0] = fmaf(a.z, b0, acc[4 * q + 2][0]); acc[4 * q + 2][1] = fmaf(a.z, b1, acc[4 * q + 2][1]);
+                    acc[4 * q + 3][0] = fmaf(a.w, b0, acc[4 * q + 3][0]); acc[4 * q + 3][1] = fmaf(a.w, b1, acc[4 * q + 3][1]);
+                }
+            }
+        }
+        cp_wait<0>();
+        __syncthreads();
+    }
+    if (tid >= T_HALF) return;
+    float* C = p.C + (size_t)blockIdx.z * p.sC;
+    const int epi = p.epilogue;
+    const float* extra = epi == GSR_EPI_ADD ? p.extra + (size_t)blockIdx.z * p.s_extra : p.extra;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int n = tid + h * T_HALF;
+        if (n >= N) continue;
+        const float bias = epi == GSR_EPI_BIAS ? __ldg(extra + n) : 0.f;
+#pragma unroll
+        for (int r = 0; r < R4 * 4; ++r) {
+            if (r < rows) {
+                float v = acc[r][h] * p.alpha + bias;
+                if (epi == GSR_EPI_ADD) v += __ldg(extra + (size_t)r * p.ld_extra + n);
+                C[(size_t)r * p.ldc + n] = v;
+            }
+        }
+    }
+}
+
+static bool tail_ok(const Params& p, int transB) {     // p already points at the ragged rows
+    return !transB && p.M >= 1 && p.M <= T_ROWS && p.N <= T_COLS && p.N % 4 == 0 && p.K <= T_KMAX &&
+           p.ldb % 4 == 0 && aligned16(p.B) && p.sB % 4 == 0;
+}
+
+static int launch_tail(const Params& p, int transA, cudaStream_t st) {
+    dim3 grid(1, 1, p.batch);
+    const int r4 = (p.M + 3) / 4;
+    constexpr int bytes = T_SMEM_FLOATS * (int)sizeof(float);
+#define GSR_TAIL_LAUNCH(TA, R4)                                                                                  \
+    do {                                                                                                          \
+        auto k = tail_kernel<TA, R4>;                                                                             \
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);              \
+        if (e != cudaSuccess) return fail((int)e, "tcgemm tail: cudaFuncSetAttribute failed");                   \
+        k<<<grid, T_THREADS, bytes, st>>>(p);                                                                     \
+    } while (0)
+#define GSR_TAIL_R4(TA)                                                                                          \
+    do {                                                                                                          \
+        if (r4 == 1) GSR_TAIL_LAUNCH(TA, 1); else if (r4 == 2) GSR_TAIL_LAUNCH(TA, 2);                            \
+        else if (r4 == 3) GSR_TAIL_LAUNCH(TA, 3); else GSR_TAIL_LAUNCH(TA, 4);                                    \
+    } while (0)
+    if (transA) GSR_TAIL_R4(true); else GSR_TAIL_R4(false);
+#undef GSR_TAIL_R4
+#undef GSR_TAIL_LAUNCH
+    return launched("tcgemm_tail");
+}
+}  // namespace tail
+
 // C[m][n] = alpha * sum_z ws[z][m][n] (+ extra[m][n]); fixed summation order.  Rows below m_head hold
-// `splits` partials (CTA-pair launch), the rows from m_head on hold `splits_tail` (one-CTA launch of the odd tile).
+// `splits` partials of pitch M * N; the rows from m_head on (the ragged tile after the CTA pairs, launched on its
+// own) hold `splits_tail` partials of pitch (M - m_head) * N at ws_tail.
 __global__ void reduce_partials_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
-                                       int splits, int m_head, int splits_tail, float alpha,
-                                       const float* __restrict__ extra, int ld_extra) {
+                                       int splits, int m_head, const float* __restrict__ ws_tail, int splits_tail,
+                                       float alpha, const float* __restrict__ extra, int ld_extra) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= M * N) return;
     const int m = e / N, n = e - m * N;
-    const int nz = m < m_head ? splits : splits_tail;
     float acc = 0.f;
-    for (int z = 0; z < nz; ++z) acc += __ldg(ws + (size_t)z * M * N + e);
+    if (m < m_head) {
+        for (int z = 0; z < splits; ++z) acc += __ldg(ws + (size_t)z * M * N + e);
+    } else {
+        const size_t pitch = (size_t)(M - m_head) * N;
+        const float* src = ws_tail + (size_t)(m - m_head) * N + n;
+        for (int z = 0; z < splits_tail; ++z) acc += __ldg(src + z * pitch);
+    }
     acc *= alpha;
     if (extra) acc += __ldg(extra + (size_t)m * ld_extra + n);
     C[(size_t)m * ldc + n] = acc;
+}
+
+// Split counts of gsr_tcgemm_reduce_f32: `splits` CTAs per tile on the one-CTA path (every SM busy once);
+// on the CTA-pair path the pairs share the SMs among themselves and the ragged tile is launched on its own.
+struct ReducePlan { int pairs, m_head, pair_splits, tail_splits; size_t floats; };
+static ReducePlan reduce_plan(int M, int N, int batch, int splits) {
+    ReducePlan r{0, M, splits, 0, (size_t)splits * M * N};
+    const int tiles_m = (M + BM - 1) / BM;
+    if (!g_pairs || tiles_m < 2 || N > BN) return r;
+    r.pairs = tiles_m / 2;
+    r.m_head = std::min(M, r.pairs * 2 * BM);
+    r.pair_splits = std::max(1, std::min(batch, kNumSMs / (2 * r.pairs)));
+    if (r.m_head < M) r.tail_splits = std::max(1, std::min(batch, kNumSMs));
+    r.floats = std::max(r.floats, (size_t)r.pair_splits * M * N + (size_t)r.tail_splits * (M - r.m_head) * N);
+    return r;
 }
 
 }  // namespace tc
@@ -788,6 +965,7 @@ using namespace gsr;
 extern "C" __attribute__((visibility("default"))) int gsr_tcgemm_debug(int key, int value) {
     if (key == 0) tc::g_mn_swap = value;
     if (key == 1) tc::g_pairs = value;
+    if (key == 2) tc::g_tail = value;
     return 0;
 }
 #ifdef GSR_TC_TRACE
@@ -826,6 +1004,7 @@ extern "C" int gsr_tcgemm_f32(const float* A, const float* B, float* C,
         t.A = A + (transA ? (size_t)m_done : (size_t)m_done * lda);
         t.C = C + (size_t)m_done * ldc;
         if (epilogue == GSR_EPI_ADD) t.extra = extra + (size_t)m_done * ld_extra;
+        if (tc::g_tail && tc::tail::tail_ok(t, transB)) return tc::tail::launch_tail(t, transA, (cudaStream_t)stream);
         dim3 gt(1, (N + tc::BN - 1) / tc::BN, batch);
         return tc::launch<false>(t, transA, transB, gt, (cudaStream_t)stream);
     }
@@ -840,11 +1019,7 @@ extern "C" size_t gsr_tcgemm_reduce_workspace(int M, int N, int batch, int* spli
     if (splits > batch) splits = batch;
     if (splits < 1) splits = 1;
     if (splits_out) *splits_out = splits;
-    // the odd last M tile of the CTA-pair path is split over every SM on its own (gsr_tcgemm_reduce_f32)
-    const int tiles_m = (M + tc::BM - 1) / tc::BM;
-    int most = splits;
-    if (tiles_m > 1 && (tiles_m & 1)) most = std::min(batch, splits * tiles_m);
-    return (size_t)most * (size_t)M * (size_t)N;
+    return tc::reduce_plan(M, N, batch, splits).floats;
 }
 
 extern "C" int gsr_tcgemm_reduce_f32(const float* A, const float* B, float* C,
@@ -862,29 +1037,27 @@ extern "C" int gsr_tcgemm_reduce_f32(const float* A, const float* B, float* C,
                  GSR_EPI_NONE, nullptr, 0, 0, tc::g_mn_swap};
     if (!tc::operands_ok(p)) return fail(GSR_E_ALIGN, "tcgemm_reduce: operands must be 16-byte aligned with leading dimensions % 4 == 0");
     const int tiles_m = (M + tc::BM - 1) / tc::BM;
-    int m_head = M, splits_tail = splits, rc;
-    if (tc::g_pairs && tc::pair_ok(p)) {
-        // CTA pairs take the even number of leading M tiles with half as many splits (one pair = two SMs); the odd
-        // last tile keeps the one-CTA kernel and its own split count.  Both write [split][M][N] partials.
-        const int pairs = tiles_m / 2, m_done = pairs * 2 * tc::BM;
-        const int pair_splits = std::max(1, std::min(batch, (splits * tiles_m) / (2 * pairs)));
-        p.splits = pair_splits;
-        rc = tc::launch_pairs<true>(p, transA, transB, pair_splits, (cudaStream_t)stream);
+    const tc::ReducePlan plan = tc::reduce_plan(M, N, batch, splits);
+    const float* ws_tail = workspace;
+    int rc;
+    if (plan.pairs && tc::pair_ok(p)) {
+        // CTA pairs take the even number of leading M tiles; the ragged last tile is launched on its own with its
+        // own split count and compact partials behind those of the pairs.
+        p.splits = plan.pair_splits;
+        rc = tc::launch_pairs<true>(p, transA, transB, plan.pair_splits, (cudaStream_t)stream);
         if (rc) return rc;
-        if (tiles_m & 1) {
-            // the tail tile still writes partial z at workspace + z*M*N; only the A rows / C rows move
+        if (plan.m_head < M) {
             tc::Params q = p;
-            q.splits = std::min(batch, splits * tiles_m);
-            q.A = transA ? A + m_done : A + (size_t)m_done * lda;
-            q.C = workspace + (size_t)m_done * N;
-            q.M = M - m_done;
-            dim3 grid(1, 1, q.splits);
-            rc = tc::launch<true>(q, transA, transB, grid, (cudaStream_t)stream);
+            q.splits = plan.tail_splits;
+            q.A = transA ? A + plan.m_head : A + (size_t)plan.m_head * lda;
+            q.C = workspace + (size_t)plan.pair_splits * M * N;
+            q.M = M - plan.m_head;
+            q.sC = (long long)q.M * N;
+            ws_tail = q.C;
+            rc = tc::launch<true>(q, transA, transB, dim3(1, 1, q.splits), (cudaStream_t)stream);
             if (rc) return rc;
-            splits_tail = q.splits;
-            m_head = m_done;
         }
-        splits = pair_splits;
+        splits = plan.pair_splits;
     } else {
         dim3 grid(tiles_m, (N + tc::BN - 1) / tc::BN, splits);
         rc = tc::launch<true>(p, transA, transB, grid, (cudaStream_t)stream);
@@ -892,6 +1065,7 @@ extern "C" int gsr_tcgemm_reduce_f32(const float* A, const float* B, float* C,
     }
     const int total = M * N;
     tc::reduce_partials_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        workspace, C, M, N, ldc, splits, m_head, splits_tail, alpha, epilogue == GSR_EPI_ADD ? extra : nullptr, ld_extra);
+        workspace, C, M, N, ldc, splits, (plan.pairs && tc::pair_ok(p)) ? plan.m_head : M, ws_tail, plan.tail_splits, alpha,
+        epilogue == GSR_EPI_ADD ? extra : nullptr, ld_extra);
     return launched("tcgemm_reduce_partials");
 }

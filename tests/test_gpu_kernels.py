@@ -436,7 +436,10 @@ def test_bgemm_linearity_full_batch(K, gemm_backend):
     c1, c2 = K.bgemm(A1, W), K.bgemm(A2, W)
     assert float((c12 - (c1 + c2)).abs().max()) < 1e-3 * float(c12.abs().max())
     per_subject = K.bgemm(A1, W.expand(1024, 268, 268).contiguous())
-    assert torch.equal(per_subject, c1)
+    # rows 0..255 of a subject run on the same tensor-core tiles in both paths; the 12 ragged rows of the per-subject
+    # path are FP32 FMAs (csrc/tcgemm.cu, tail_kernel) and differ from the 3xTF32 products by rounding only
+    assert torch.equal(per_subject[:, :256], c1[:, :256])
+    assert float((per_subject[:, 256:] - c1[:, 256:]).abs().max()) < 4e-6 * float(c1.abs().max())
     assert K.colsum(c1[0]).shape == (268,)
     assert torch.allclose(K.colsum(c1[0]), c1[0].sum(0), rtol=1e-5, atol=1e-3)
 

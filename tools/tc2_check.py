@@ -27,13 +27,14 @@ cases = {
     "NT stacked U.W^T (K=160)": (lambda: K.bgemm(U, Wl, transB=True), lambda: U.double() @ Wl.double().T),
     "NT stacked N=160 (K=268)": (lambda: K.bgemm(X, Wl.T.contiguous(), transB=True), lambda: X.double() @ Wl.double()),
 }
-for pairs in (0, 1):
-    dbg(1, pairs)
+MODES = ((0, 0), (1, 0), (1, 1))          # (CTA pairs, FP32 kernel for the ragged rows)
+for pairs, tail in MODES:
+    dbg(1, pairs); dbg(2, tail)
     for name, (fn, ref) in cases.items():
         out = fn(); torch.cuda.synchronize()
         r = ref()
         err = float((out.double() - r).abs().max()); scale = float(r.abs().max())
-        print(json.dumps({"pairs": pairs, "case": name, "max_err": err, "rel": err / scale}), flush=True)
+        print(json.dumps({"pairs": pairs, "tail": tail, "case": name, "max_err": err, "rel": err / scale}), flush=True)
 Br = 37
 Xr = torch.randn(Br, 268, 268, device="cuda", generator=g); Yr = torch.randn(Br, 268, 268, device="cuda", generator=g)
 Wadd = torch.randn(268, 268, device="cuda", generator=g)
@@ -43,23 +44,23 @@ rcases = {
     "reduce NT": (lambda: K.bgemm_reduce(Xr, Yr, transB=True), lambda: (Xr.double() @ Yr.double().transpose(1, 2)).sum(0)),
     "reduce TN M=160": (lambda: K.bgemm_reduce(Xr[:, :, :160].contiguous(), Yr, transA=True), lambda: (Xr[:, :, :160].double().transpose(1, 2) @ Yr.double()).sum(0)),
 }
-for pairs in (0, 1):
-    dbg(1, pairs)
+for pairs, tail in MODES:
+    dbg(1, pairs); dbg(2, tail)
     for name, (fn, ref) in rcases.items():
         out = fn(); torch.cuda.synchronize()
         r = ref()
         err = float((out.double() - r).abs().max()); scale = float(r.abs().max())
-        print(json.dumps({"pairs": pairs, "case": name, "max_err": err, "rel": err / scale}), flush=True)
+        print(json.dumps({"pairs": pairs, "tail": tail, "case": name, "max_err": err, "rel": err / scale}), flush=True)
 B = 1024
 X = torch.rand(B, 268, 268, device="cuda", generator=g); Y = torch.rand(B, 268, 268, device="cuda", generator=g)
 fl = 2 * 268 ** 3 * B
-for pairs in (0, 1):
-    dbg(1, pairs)
-    r = {"pairs": pairs}
+for pairs, tail in MODES:
+    dbg(1, pairs); dbg(2, tail)
+    r = {"pairs": pairs, "tail": tail}
     for name, fn in (("NN per-subject", lambda: K.bgemm(X, Y)), ("NT per-subject", lambda: K.bgemm(X, Y, transB=True)),
                      ("TN per-subject", lambda: K.bgemm(X, Y, transA=True)), ("NN stacked W", lambda: K.bgemm(X, W)),
                      ("NT stacked W", lambda: K.bgemm(X, W, transB=True)),
                      ("reduce TN", lambda: K.bgemm_reduce(X, Y, transA=True)), ("reduce NN", lambda: K.bgemm_reduce(X, Y))):
         ms = timeit(fn); r[name] = [round(ms, 4), round(fl / ms / 1e9, 1)]
     print(json.dumps(r), flush=True)
-dbg(1, 1)
+dbg(1, 1); dbg(2, 1)
