@@ -41,8 +41,8 @@ class Args:
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=1024, help="subjects per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gemm-variant", type=int, default=None)
@@ -53,39 +53,57 @@ def parse():
 
 # ------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  nvidia-smi is started before the
+    warm-up steps (its start-up attaches to the driver and can stall launches for a second on a fresh box, which
+    must not fall into the timed region) and every row is stamped on arrival; `stop()` keeps the rows that arrived
+    between `begin()` and `end()` (plus one sampling period)."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 50
 
     def __init__(self, gpu_index: int):
         self.rows, self.proc, self.thread = [], None, None
         self.gpu_index = gpu_index
+        self.t_begin = self.t_end = None
 
-    def start(self):
+    def start(self, wait_s: float = 10.0):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.PERIOD_MS)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
         def pump():
             for line in self.proc.stdout:
-                self.rows.append(line.strip())
+                self.rows.append((time.monotonic(), line.strip()))
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
+        t0 = time.monotonic()
+        while not self.rows and time.monotonic() - t0 < wait_s and self.proc.poll() is None:
+            time.sleep(0.02)
+
+    def begin(self):
+        self.t_begin = time.monotonic()
+
+    def end(self):
+        self.t_end = time.monotonic()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(1.5 * self.PERIOD_MS / 1e3)          # the row that covers the end of the region
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        lo = self.t_begin if self.t_begin is not None else 0.0
+        hi = (self.t_end if self.t_end is not None else time.monotonic()) + 1.5 * self.PERIOD_MS / 1e3
+        rows = [r for t, r in self.rows if lo <= t <= hi]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
+        for row in rows:
             parts = [p.strip() for p in row.split(",")]
             if len(parts) < 6:
                 continue
@@ -98,7 +116,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "period_ms": self.PERIOD_MS}
 
 
 # ------------------------------------------------------------------------------ CPU reference arm
@@ -226,23 +244,25 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                 # before the warm-up: nvidia-smi's start-up must not fall into the timed region
     for _ in range(max(args.warmup, 3)):
         one_step(lr, hr)
     barrier()
 
     # ---- timed region: K steps, device time, max over ranks
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     K.GEMM_TIMER, K.EIGH_TIMER, K.EW_TIMER = K.KernelTimer(), K.KernelTimer(), K.KernelTimer()
     launches0 = pkg.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     e0.record()
     for _ in range(args.steps):
         one_step(lr, hr)
     e1.record()
     barrier()
+    sampler.end()
     elapsed_ms = e0.elapsed_time(e1)
     launches = pkg.launch_count() - launches0
     # contractions on the tensor-core kernel (per-subject and stacked 268-wide products) and, separately, the small

@@ -59,7 +59,7 @@ struct Params {
 
 int g_mn_swap = 0;      // bring-up knob (unused)
 int g_pairs = 1;        // gsr_tcgemm_debug key 1: CTA-pair kernel (cta_group::2) for gsr_tcgemm_f32 (default), 0 = one CTA per tile
-int g_tail = 1;         // gsr_tcgemm_debug key 2: FP32 kernel for the <= 16 ragged rows after the CTA pairs when B is row-major (default), 0 = one-CTA tensor kernel
+int g_tail = 1;         // gsr_tcgemm_debug key 2: FP32 kernels for the <= 16 ragged rows after the CTA pairs (default), 0 = one-CTA tensor kernel
 
 #ifdef GSR_TC_TRACE
 // Pipeline trace (tools/tc_trace.py builds a private copy of the library with -DGSR_TC_TRACE):
@@ -773,8 +773,8 @@ static bool operands_ok(const Params& p) {
 // (a warp per k row, 16-byte copies), and each thread owns two columns n, n + 136 with all rows in registers: per k
 // two scalar LDS, R4 broadcast LDS.128 and 8 R4 FFMA.  Plain FP32 accumulation in k order (the 3xTF32 products of
 // the tensor kernels differ from it by rounding only; tests compare both against float64).  80 us per 1024
-// subjects.  op(B) = B^T and the subject-reduced products stay on the tensor kernel: a transposing variant of this
-// kernel and a reducing one were measured no faster than it (215 / 145 us against 177 / 150 us).
+// subjects.  op(B) = B^T has its own kernel below (a transposing variant of this one measured 215 us); the
+// subject-reduced products stay on the tensor kernel (a reducing variant was no faster, 145 against 150 us).
 namespace tail {
 constexpr int T_THREADS = 160, T_HALF = 136, T_COLS = 2 * T_HALF, T_KC = 16, T_KMAX = 288, T_ROWS = 16;
 constexpr int T_SMEM_FLOATS = T_KMAX * T_ROWS + 2 * T_KC * T_COLS;
@@ -892,6 +892,99 @@ __global__ void __launch_bounds__(T_THREADS, 4) tail_kernel(const Params p) {
     }
 }
 
+// op(B) = B^T (B stored [n][k]): no staging of B at all.  Thread n streams its own row of B from global memory with
+// 16-byte loads, eight in flight (one 128-byte line per thread), and op(A) comes from the same swizzled
+// shared-memory copy; no barrier after the A staging.  108 us per 1024 subjects against 178 us on the tensor
+// kernel (for row-major B the same scheme with coalesced 4-byte loads measured 90 us, the staged kernel 80 us).
+constexpr int D_THREADS = 288;
+template <bool TA, int R4>
+__global__ void __launch_bounds__(D_THREADS, 4) tail_bt_kernel(const Params p) {
+    __shared__ __align__(16) float As[T_KMAX * T_ROWS];
+    const int tid = threadIdx.x;
+    const int rows = p.M, K = p.K, N = p.N;
+    const int kpad = (K + 31) & ~31;
+    const float* A = p.A + (size_t)blockIdx.z * p.sA;
+    const float* B = p.B + (size_t)blockIdx.z * p.sB;
+    if (!TA) {
+        float v[R4 * 4];
+#pragma unroll
+        for (int r = 0; r < R4 * 4; ++r) v[r] = (r < rows && tid < K) ? __ldg(A + (size_t)r * p.lda + tid) : 0.f;
+#pragma unroll
+        for (int r = 0; r < R4 * 4; ++r)
+            if (tid < kpad) As[tid * T_ROWS + ((((r >> 2) ^ (tid >> 1)) & 3) << 2) + (r & 3)] = v[r];
+    } else {
+        constexpr int PASSES = T_KMAX / (D_THREADS / 16);
+        const int r = tid & 15;
+        float v[PASSES];
+#pragma unroll
+        for (int j = 0; j < PASSES; ++j) {
+            const int k = (tid >> 4) + j * (D_THREADS / 16);
+            v[j] = (r < rows && k < K) ? __ldg(A + (size_t)k * p.lda + r) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < PASSES; ++j) {
+            const int k = (tid >> 4) + j * (D_THREADS / 16);
+            if (r < R4 * 4 && k < kpad) As[k * T_ROWS + ((((r >> 2) ^ (k >> 1)) & 3) << 2) + (r & 3)] = v[j];
+        }
+    }
+    __syncthreads();
+    const int n = tid;
+    if (n >= N) return;
+    float acc[R4 * 4];
+#pragma unroll
+    for (int r = 0; r < R4 * 4; ++r) acc[r] = 0.f;
+    auto fma_k = [&](int k_static, const float* as, float b) {     // k_static: position inside the 32-row block
+#pragma unroll
+        for (int q = 0; q < R4; ++q) {
+            const float4 a = *reinterpret_cast<const float4*>(as + k_static * T_ROWS + (((q ^ (k_static >> 1)) & 3) << 2));
+            acc[4 * q + 0] = fmaf(a.x, b, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(a.y, b, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(a.z, b, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(a.w, b, acc[4 * q + 3]);
+        }
+    };
+    const float4* b = reinterpret_cast<const float4*>(B + (size_t)n * p.ldb);
+    for (int k0 = 0; k0 < kpad; k0 += 32) {
+        float4 bv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bv[i] = (k0 + 4 * i < K) ? __ldg(b + (k0 >> 2) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            fma_k(4 * i + 0, As + k0 * T_ROWS, bv[i].x); fma_k(4 * i + 1, As + k0 * T_ROWS, bv[i].y);
+            fma_k(4 * i + 2, As + k0 * T_ROWS, bv[i].z); fma_k(4 * i + 3, As + k0 * T_ROWS, bv[i].w);
+        }
+    }
+    float* C = p.C + (size_t)blockIdx.z * p.sC;
+    const int epi = p.epilogue;
+    const float* extra = epi == GSR_EPI_ADD ? p.extra + (size_t)blockIdx.z * p.s_extra : p.extra;
+    const float bias = epi == GSR_EPI_BIAS ? __ldg(extra + n) : 0.f;
+#pragma unroll
+    for (int r = 0; r < R4 * 4; ++r) {
+        if (r < rows) {
+            float v = acc[r] * p.alpha + bias;
+            if (epi == GSR_EPI_ADD) v += __ldg(extra + (size_t)r * p.ld_extra + n);
+            C[(size_t)r * p.ldc + n] = v;
+        }
+    }
+}
+
+static bool tail_bt_ok(const Params& p, int transB) {
+    return transB && p.M >= 1 && p.M <= T_ROWS && p.N <= D_THREADS && p.K <= T_KMAX && p.K % 4 == 0 && p.ldb % 4 == 0 && aligned16(p.B) && p.sB % 4 == 0;
+}
+
+static int launch_tail_bt(const Params& p, int transA, cudaStream_t st) {
+    dim3 grid(1, 1, p.batch);
+    const int r4 = (p.M + 3) / 4;
+#define GSR_TAILBT_R4(TA)                                                                                        \
+    do {                                                                                                          \
+        if (r4 == 1) tail_bt_kernel<TA, 1><<<grid, D_THREADS, 0, st>>>(p);                                        \
+        else if (r4 == 2) tail_bt_kernel<TA, 2><<<grid, D_THREADS, 0, st>>>(p);                                   \
+        else if (r4 == 3) tail_bt_kernel<TA, 3><<<grid, D_THREADS, 0, st>>>(p);                                   \
+        else tail_bt_kernel<TA, 4><<<grid, D_THREADS, 0, st>>>(p);                                                \
+    } while (0)
+    if (transA) GSR_TAILBT_R4(true); else GSR_TAILBT_R4(false);
+#undef GSR_TAILBT_R4
+    return launched("tcgemm_tail_bt");
+}
+
 static bool tail_ok(const Params& p, int transB) {     // p already points at the ragged rows
     return !transB && p.M >= 1 && p.M <= T_ROWS && p.N <= T_COLS && p.N % 4 == 0 && p.K <= T_KMAX &&
            p.ldb % 4 == 0 && aligned16(p.B) && p.sB % 4 == 0;
@@ -1004,6 +1097,7 @@ extern "C" int gsr_tcgemm_f32(const float* A, const float* B, float* C,
         t.A = A + (transA ? (size_t)m_done : (size_t)m_done * lda);
         t.C = C + (size_t)m_done * ldc;
         if (epilogue == GSR_EPI_ADD) t.extra = extra + (size_t)m_done * ld_extra;
+        if (tc::g_tail && tc::tail::tail_bt_ok(t, transB)) return tc::tail::launch_tail_bt(t, transA, (cudaStream_t)stream);
         if (tc::g_tail && tc::tail::tail_ok(t, transB)) return tc::tail::launch_tail(t, transA, (cudaStream_t)stream);
         dim3 gt(1, (N + tc::BN - 1) / tc::BN, batch);
         return tc::launch<false>(t, transA, transB, gt, (cudaStream_t)stream);

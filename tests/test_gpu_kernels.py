@@ -375,6 +375,29 @@ def test_bgemm_vs_float64(K, gemm_backend, tA, tB, shape):
         assert float((got.double() - want).abs().max()) <= tol, (shape, tA, tB, batch, sharedB)
 
 
+@pytest.mark.parametrize("tA", [False, True])
+@pytest.mark.parametrize("tB", [False, True])
+@pytest.mark.parametrize("M", [257, 260, 265, 268, 272])
+def test_bgemm_ragged_rows_after_the_cta_pairs(K, tA, tB, M):
+    """Rows 256.. of a per-subject product run on the FP32 kernels of csrc/tcgemm.cu (1..16 rows, both layouts of
+    B, all epilogues); rows 0..255 on the CTA-pair tensor kernel."""
+    g = torch.Generator().manual_seed(M)
+    batch, N, Kd = 5, 268, 164
+    A = torch.randn((batch, Kd, M) if tA else (batch, M, Kd), generator=g)
+    B = torch.randn((batch, N, Kd) if tB else (batch, Kd, N), generator=g)
+    add, bias = torch.randn(batch, M, N, generator=g), torch.randn(N, generator=g)
+    opA = A.transpose(1, 2) if tA else A
+    opB = B.transpose(1, 2) if tB else B
+    ref = opA.double() @ opB.double()
+    tol = 2e-6 * float((opA.abs().double() @ opB.abs().double()).max())
+    got = K.bgemm(A.cuda(), B.cuda(), transA=tA, transB=tB).cpu()
+    assert float((got.double() - ref).abs().max()) <= tol
+    got = K.bgemm(A.cuda(), B.cuda(), transA=tA, transB=tB, alpha=-0.5, add=add.cuda()).cpu()
+    assert float((got.double() - (-0.5 * ref + add.double())).abs().max()) <= tol
+    got = K.bgemm(A.cuda(), B.cuda(), transA=tA, transB=tB, bias=bias.cuda()).cpu()
+    assert float((got.double() - (ref + bias.double())).abs().max()) <= tol
+
+
 def test_bgemm_epilogues_and_2d(K, gemm_backend):
     g = torch.Generator().manual_seed(5)
     X, W, b = torch.randn(144, 268, generator=g), torch.randn(268, 268, generator=g), torch.randn(268, generator=g)
