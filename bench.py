@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gemm-variant", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=None, help="subjects in the CPU baseline sample")
     return ap.parse_args()
 
@@ -213,7 +214,8 @@ def run_ours(args):
     torch.manual_seed(0)
     model = pkg.GSRNet([0.9, 0.7, 0.6, 0.5], Args()).to(dev)
     sp = pkg.SubjectParallel(model) if world > 1 else None
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    use_graph = not args.no_graph
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=use_graph)
     step = pkg.GSRTrainStep(model, lmbda=Args.lmbda, padding=Args.padding)
     lr = synth_batch(torch, LR_DIM, B, 1000 + rank, dev)
     hr = synth_batch(torch, HR_DIM, B, 5000 + rank, dev)
@@ -247,24 +249,45 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                 # before the warm-up: nvidia-smi's start-up must not fall into the timed region
+    # The whole optimiser step (forward, backward, gradient all-reduce, Adam) is captured once in a CUDA graph
+    # (pkg.GraphedTrainStep, SURVEY 8 f row N3) and the timed region replays it: the ~180 launches of a step keep the
+    # host busy for 10 of the 15 ms when issued from Python, so an eager loop is only just device-bound.
+    graphed = None
+    if use_graph:
+        graphed = pkg.GraphedTrainStep(model, opt, B, lmbda=Args.lmbda, padding=Args.padding, hr_basis_in_graph=in_step_hr,
+                                       grad_sync=sp.sync_gradients if sp is not None else None, warmup=max(args.warmup, 3))
+        graphed.load(lr, hr, U_hr)      # the batch is resident in the graph's input buffers when the timed region starts
+        timed_step = graphed.replay
+    else:
+        timed_step = lambda: one_step(lr, hr)
     for _ in range(max(args.warmup, 3)):
-        one_step(lr, hr)
+        timed_step()
     barrier()
 
     # ---- timed region: K steps, device time, max over ranks
-    K.GEMM_TIMER, K.EIGH_TIMER, K.EW_TIMER = K.KernelTimer(), K.KernelTimer(), K.KernelTimer()
     launches0 = pkg.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.begin()
     e0.record()
     for _ in range(args.steps):
-        one_step(lr, hr)
+        timed_step()
     e1.record()
     barrier()
     sampler.end()
     elapsed_ms = e0.elapsed_time(e1)
-    launches = pkg.launch_count() - launches0
+    launches = graphed.launches_per_step * args.steps if use_graph else pkg.launch_count() - launches0
+
+    # ---- per-kernel durations for the rooflines: the same K steps launched eagerly with CUDA events around every
+    #      library call (events cannot be placed inside a graph replay); shares are relative to this pass
+    K.GEMM_TIMER, K.EIGH_TIMER, K.EW_TIMER = K.KernelTimer(), K.KernelTimer(), K.KernelTimer()
+    e0i, e1i = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0i.record()
+    for _ in range(args.steps):
+        one_step(lr, hr)
+    e1i.record()
+    barrier()
+    instrumented_ms = e0i.elapsed_time(e1i)
     # contractions on the tensor-core kernel (per-subject and stacked 268-wide products) and, separately, the small
     # Graph U-Net products on the SIMT kernel (they run on a side stream under the eigendecomposition)
     gemm_ms, gemm_flops, gemm_launches = K.GEMM_TIMER.totals("tc" if K.GEMM_BACKEND == "tc" else None)
@@ -312,8 +335,13 @@ def run_ours(args):
             if i + 1 < nsteps:
                 issue_copy(i + 1)
             main.wait_event(ev_copy[buf])
-            loss = one_step(lr_dev[buf], hr_dev[buf])
-            ev_done[buf].record(main)
+            if use_graph:
+                graphed.load(lr_dev[buf], hr_dev[buf], U_hr)      # device-to-device into the graph's input buffers
+                ev_done[buf].record(main)
+                loss, _ = graphed.replay()
+            else:
+                loss = one_step(lr_dev[buf], hr_dev[buf])
+                ev_done[buf].record(main)
             loss_host[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
         main.synchronize()
         return loss_host
@@ -398,7 +426,7 @@ def run_ours(args):
                         "and 3xTF32 needs 3 MMAs per product, so the fp32-accurate ceiling of this kernel is peak/6"
                         if backend == "tc" else "FP32 FFMA probe kernel measured in this run"),
         "frac_of_3xtf32_ceiling": (gemm_tflops / (bf16_peak / 6.0)) if (gemm_tflops and backend == "tc") else None,
-        "share_of_step": gemm_ms / elapsed_ms if elapsed_ms else None, "launches": gemm_launches,
+        "share_of_step": gemm_ms / instrumented_ms if instrumented_ms else None, "launches": gemm_launches,
         "algorithmic_flop_per_subject": GEMM_FLOP_PER_SUBJECT_FWD_BWD,
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE per-subject 268^3 launch (1024 subjects) inside the step,
         # from the committed ncu --set full capture; the algorithmic bytes of that launch are 3 x 294 MB = 882 MB
@@ -433,7 +461,7 @@ def run_ours(args):
             "bound": "fp32", "achieved": tflops, "unit": "TFLOP/s (executed fp32 flops: 4 n^3 + 6 n per plane rotation)",
             "peak": ffma_best, "frac": tflops / ffma_best if ffma_best else None,
             "peak_source": "FP32 FFMA probe kernel measured in this run",
-            "share_of_step": eigh_ms / elapsed_ms, "launches": eigh_launches,
+            "share_of_step": eigh_ms / instrumented_ms, "launches": eigh_launches,
             "us_per_graph": eigh_ms * 1e3 / eigh_graphs if eigh_graphs else None,
             "ql_iterations_mean": float(eigh_info.double().mean()), "rotations_mean": rot_mean,
             "conventional_9n3_tflops": 9.0 * n ** 3 * eigh_graphs / (eigh_ms * 1e-3) / 1e12, "traffic": None,
@@ -455,7 +483,7 @@ def run_ours(args):
             "bound": "smem", "achieved": gbs, "unit": "GB/s (shared-memory bytes the Jacobi rounds must move)",
             "peak": smem_peak, "frac": gbs / smem_peak,
             "peak_source": f"148 SMs x 128 B/clk x {sm_mhz:.0f} MHz (clock sampled in this run); ncu: lsu data-pipe 66 % busy",
-            "share_of_step": eigh_ms / elapsed_ms, "launches": eigh_launches,
+            "share_of_step": eigh_ms / instrumented_ms, "launches": eigh_launches,
             "us_per_graph": eigh_ms * 1e3 / eigh_graphs if eigh_graphs else None,
             "sweeps_mean": sw / eigh_info.numel(), "polish_sweeps_mean": ps / eigh_info.numel(), "traffic": None,
         }
@@ -465,7 +493,7 @@ def run_ours(args):
         ew_roof = {"kernel": "normalize_{fwd,bwd}_kernel + sym_diag_abs_{fwd,bwd}_kernel (memory-bound n x n kernels)",
                    "bound": "hbm", "achieved": gbs, "unit": "GB/s", "peak": peaks.get("hbm_gbs"),
                    "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
-                   "peak_source": "MEASURED_PEAKS.json hbm_gbs", "share_of_step": ew_ms / elapsed_ms,
+                   "peak_source": "MEASURED_PEAKS.json hbm_gbs", "share_of_step": ew_ms / instrumented_ms,
                    "launches": ew_launches, "traffic": None}
     by_kernel = [r for r in (eigh_roof, gemm_roof, ew_roof) if r]
     roofline = max(by_kernel, key=lambda r: r["share_of_step"] or 0.0)          # the dominant kernel of the step
@@ -490,12 +518,18 @@ def run_ours(args):
                    "with_hr_target_eigh_in_step": hr_in_step,
                    "gemm_backend": K.GEMM_BACKEND,
                    "l2": "inputs of one step are 400 MB per GPU (> 126 MB L2); no flush needed",
-                   "optimizer": "torch.optim.Adam(fused=True), in the timed region"},
+                   "optimizer": "torch.optim.Adam(fused=True, capturable=True), in the timed region",
+                   "cuda_graph": ("the timed region replays one captured graph per step (forward, backward, gradient all-reduce, Adam; "
+                                  "GraphedTrainStep); --no-graph launches every kernel from Python" if use_graph else "off (--no-graph)"),
+                   "kernel_timing": (f"roofline durations and share_of_step come from an instrumented eager pass of the same {args.steps} "
+                                     f"steps right after the timed region (CUDA events around every library call, "
+                                     f"{instrumented_ms / args.steps:.3f} ms per step with the events)")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "subjects/s",
                 "h2d_bytes_per_step": world * B * (LR_DIM * LR_DIM + HR_DIM * HR_DIM) * 4,
                 "d2h_bytes_per_step": world * 4,
-                "pipeline": "H2D of step i+1 overlaps the compute of step i (two device buffers, copy stream)"},
+                "pipeline": "H2D of step i+1 overlaps the compute of step i (two device buffers, copy stream)"
+                            + ("; the step copies the batch device-to-device into the graph's input buffers and replays the graph" if use_graph else "")},
         "gpu_launches": launches,
         "roofline": roofline,
         "roofline_other_kernels": others,

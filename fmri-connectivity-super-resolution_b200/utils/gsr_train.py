@@ -125,6 +125,95 @@ class GSRTrainStep:
         return loss.detach(), error.detach()
 
 
+class GraphedTrainStep:
+    """The whole optimiser step -- forward, backward, (gradient all-reduce,) optimiser update -- captured once
+    in a CUDA graph and replayed (SURVEY 8 f, row N3).  A step is ~180 kernel launches of 10-300 us; replaying
+    them removes the Python / autograd / ctypes launch path, which otherwise bounds the step whenever the host is
+    slower than the device (profiles/README.md).
+
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)     # device-side step counter
+        step = GraphedTrainStep(model, opt, batch=1024)
+        loss, error = step(lr_batch, hr_batch, U_hr_reduced)      # device scalars, valid until the next call
+
+    The inputs are copied into the graph's static buffers (device to device, or from pinned host memory);
+    nothing synchronises.  ``U_hr_reduced=None`` captures the HR-target eigendecomposition inside the graph,
+    as the reference's loop computes it every step.  Capture runs ``warmup`` real steps first (lazy
+    allocations, cudaFuncSetAttribute); parameters and optimiser state are restored afterwards, so the first
+    replay is the first step of the run.  ``grad_sync`` (e.g. ``SubjectParallel.sync_gradients``) is captured
+    between backward and the optimiser update."""
+
+    def __init__(self, model, optimizer, batch, lmbda=16, padding=0, hr_basis_in_graph=False, grad_sync=None,
+                 warmup=3):
+        for group in optimizer.param_groups:
+            if not group.get("capturable", False):
+                raise ValueError("GraphedTrainStep: build the optimiser with capturable=True (its step counter must "
+                                 "live on the device)")
+        layer = model.layer
+        dev = layer.weights.device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedTrainStep: move the model to the GPU first; there is no CPU path")
+        self.model, self.optimizer = model, optimizer
+        self.eager = GSRTrainStep(model, lmbda, padding)
+        hr_dim = layer.hr_dim - 2 * padding
+        self.lr = torch.zeros(batch, layer.lr_dim, layer.lr_dim, device=dev)
+        self.hr = torch.zeros(batch, hr_dim, hr_dim, device=dev)
+        self.U_hr = None if hr_basis_in_graph else torch.zeros(batch, layer.hr_dim, layer.lr_dim, device=dev)
+        # unit-diagonal placeholders keep the warm-up eigendecompositions well defined
+        self.lr.diagonal(dim1=1, dim2=2).fill_(1.0)
+        self.hr.diagonal(dim1=1, dim2=2).fill_(1.0)
+
+        def one():
+            optimizer.zero_grad(set_to_none=True)
+            out = self.eager(self.lr, self.hr, U_hr_reduced=self.U_hr)
+            if grad_sync is not None:
+                grad_sync()
+            optimizer.step()
+            return out
+
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+        saved_params = [p.detach().clone() for p in params]
+        saved_state = {id(p): {k: (v.clone() if torch.is_tensor(v) else v) for k, v in optimizer.state.get(p, {}).items()}
+                       for p in params}
+        from .. import launch_count
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(int(warmup), 1)):
+                one()
+        torch.cuda.current_stream().wait_stream(side)
+        optimizer.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.error = one()
+        self.launches_per_step = launch_count() - n0        # launches of this library inside one replay
+        with torch.no_grad():
+            for p, q in zip(params, saved_params):
+                p.copy_(q)
+            for p in params:
+                old = saved_state[id(p)]
+                for k, v in optimizer.state.get(p, {}).items():
+                    if torch.is_tensor(v):
+                        v.copy_(old[k]) if k in old else v.zero_()
+
+    def load(self, lr, hr, U_hr_reduced=None, non_blocking=True):
+        """Copy one batch into the static buffers (on the current stream)."""
+        self.lr.copy_(lr, non_blocking=non_blocking)
+        self.hr.copy_(hr, non_blocking=non_blocking)
+        if self.U_hr is not None:
+            if U_hr_reduced is None:
+                raise ValueError("GraphedTrainStep: captured with a cached HR basis; pass U_hr_reduced")
+            self.U_hr.copy_(U_hr_reduced, non_blocking=non_blocking)
+
+    def replay(self):
+        self.graph.replay()
+        return self.loss, self.error
+
+    def __call__(self, lr, hr, U_hr_reduced=None):
+        self.load(lr, hr, U_hr_reduced)
+        return self.replay()
+
+
 def train_batched(model, optimizer, subjects_adj, subjects_labels, args, batch_size=64,
                   cache_eigenbases=True, grad_sync=None, verbose=True):
     """Batched counterpart of ``train``: one optimiser step per ``batch_size`` subjects.

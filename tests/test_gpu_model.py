@@ -403,3 +403,45 @@ def test_full_batch_step_properties(setup):
     assert float(loss2) == pytest.approx(float(loss), rel=1e-5)
     for k, p in model.named_parameters():
         assert rel_fro(p.grad, g_ref[k]) < 1e-4, k
+
+
+@pytest.mark.gpu
+def test_graphed_train_step_equals_eager_steps(cuda_pkg):
+    """SURVEY 8 f row N3: the captured CUDA graph (forward, backward, Adam) replays to the same losses and
+    parameters as the eager steps, bit for bit, and capture leaves parameters / optimiser state untouched."""
+    pkg = cuda_pkg
+    import bench
+    B = 6
+    lr = bench.synth_batch(torch, 160, B, 11, torch.device("cuda"))
+    hr = bench.synth_batch(torch, 268, B, 12, torch.device("cuda"))
+    U = pkg.hr_target_basis(hr, 160)
+
+    def build():
+        torch.manual_seed(3)
+        m = pkg.GSRNet([0.9, 0.7, 0.6, 0.5], bench.Args()).cuda()
+        return m, torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
+
+    m1, o1 = build()
+    eager = pkg.GSRTrainStep(m1)
+    m2, o2 = build()
+    before = [p.detach().clone() for p in m2.parameters()]
+    graphed = pkg.GraphedTrainStep(m2, o2, B)
+    assert all(torch.equal(a, b) for a, b in zip(before, m2.parameters()))
+    assert graphed.launches_per_step > 50
+    for i in range(3):
+        o1.zero_grad(set_to_none=True)
+        l1, e1 = eager(lr, hr, U_hr_reduced=U)
+        o1.step()
+        l2, e2 = graphed(lr, hr, U)
+        assert float(l1) == float(l2) and float(e1) == float(e2), i
+        assert all(torch.equal(a, b) for a, b in zip(m1.parameters(), m2.parameters())), i
+    with pytest.raises(ValueError):
+        pkg.GraphedTrainStep(m1, torch.optim.Adam(m1.parameters(), lr=1e-3), B)
+    # the HR-target eigendecomposition inside the graph, as the reference computes it every step
+    m3, o3 = build()
+    g3 = pkg.GraphedTrainStep(m3, o3, B, hr_basis_in_graph=True)
+    l3, _ = g3(lr, hr)
+    m4, o4 = build()
+    o4.zero_grad(set_to_none=True)
+    l4, _ = pkg.GSRTrainStep(m4)(lr, hr)
+    assert float(l3) == float(l4)
