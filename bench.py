@@ -397,9 +397,22 @@ def run_ours(args):
         if it:
             ffma_best = max(ffma_best, flops / (a.elapsed_time(b) * 1e-3) / 1e12)
 
-    if rank != 0:
+    def finish():
+        # N > 1: the captured graph holds the communicator's all-reduce; tearing the process group down with it
+        # alive was observed to block at exit.  Release the graph, meet the other ranks and leave without the
+        # NCCL / interpreter teardown.
+        nonlocal graphed, timed_step
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            graphed = timed_step = None
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     peaks = {}
@@ -536,8 +549,7 @@ def run_ours(args):
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():

@@ -6,18 +6,36 @@ namespace gsr {
 thread_local char g_last_error[256] = "";
 std::atomic<uint64_t> g_launches{0};
 
-// One CTA row per tensor (blockIdx.y), grid-stride over its elements.
+// One CTA row per tensor (blockIdx.y), grid-stride over its elements.  The table of tensor pointers and bucket
+// offsets travels in the kernel parameters (no device table, no host-to-device copy: the launch can be captured
+// in a CUDA graph, where the gradient buffers are only known while capturing).
+constexpr int FLAT_CHUNK = 48;
+struct FlatTable { float* ptr[FLAT_CHUNK]; long long offset[FLAT_CHUNK + 1]; };
 template <bool PACK>
-__global__ void flat_copy_kernel(float* const* __restrict__ ptrs, const long long* __restrict__ offsets,
-                                 float* __restrict__ flat, float scale) {
+__global__ void flat_copy_kernel(const __grid_constant__ FlatTable table, float* __restrict__ flat, float scale) {
     const int t = blockIdx.y;
-    const long long lo = offsets[t], hi = offsets[t + 1];
-    float* p = ptrs[t];
+    const long long lo = table.offset[t], hi = table.offset[t + 1];
+    float* p = table.ptr[t];
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < hi - lo;
          e += (long long)gridDim.x * blockDim.x) {
         if (PACK) flat[lo + e] = p[e] * scale;
         else p[e] = flat[lo + e] * scale;
     }
+}
+
+template <bool PACK>
+static int flat_copy(float* const* ptrs, const long long* offsets, int n_tensors, float* flat, float scale, cudaStream_t st) {
+    for (int first = 0; first < n_tensors; first += FLAT_CHUNK) {
+        const int n = std::min(FLAT_CHUNK, n_tensors - first);
+        FlatTable table;
+        for (int i = 0; i < n; ++i) { table.ptr[i] = ptrs[first + i]; table.offset[i] = offsets[first + i]; }
+        table.offset[n] = offsets[first + n];
+        for (int i = n; i < FLAT_CHUNK; ++i) { table.ptr[i] = nullptr; table.offset[i + 1] = table.offset[n]; }
+        flat_copy_kernel<PACK><<<dim3(32, n), 256, 0, st>>>(table, flat, scale);
+        const int rc = launched(PACK ? "flat_pack" : "flat_unpack");
+        if (rc) return rc;
+    }
+    return 0;
 }
 }  // namespace gsr
 
@@ -27,20 +45,17 @@ extern "C" int gsr_abi_version(void) { return GSR_ABI_VERSION; }
 extern "C" const char* gsr_last_error(void) { return g_last_error; }
 extern "C" uint64_t gsr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-extern "C" int gsr_flat_pack(const float* const* ptrs_dev, const long long* offsets_dev, int n_tensors,
+extern "C" int gsr_flat_pack(const float* const* ptrs, const long long* offsets, int n_tensors,
                              float* flat, long long total, float scale, void* stream) {
-    if (!ptrs_dev || !offsets_dev || !flat || n_tensors <= 0 || total <= 0) return fail(GSR_E_ARG, "flat_pack: bad argument");
-    flat_copy_kernel<true><<<dim3(32, n_tensors), 256, 0, (cudaStream_t)stream>>>(
-        const_cast<float* const*>(reinterpret_cast<const float* const*>(ptrs_dev)), offsets_dev, flat, scale);
-    return launched("flat_pack");
+    if (!ptrs || !offsets || !flat || n_tensors <= 0 || total <= 0) return fail(GSR_E_ARG, "flat_pack: bad argument");
+    return flat_copy<true>(const_cast<float* const*>(reinterpret_cast<const float* const*>(ptrs)), offsets, n_tensors, flat, scale,
+                           (cudaStream_t)stream);
 }
 
-extern "C" int gsr_flat_unpack(float* const* ptrs_dev, const long long* offsets_dev, int n_tensors,
+extern "C" int gsr_flat_unpack(float* const* ptrs, const long long* offsets, int n_tensors,
                                const float* flat, long long total, float scale, void* stream) {
-    if (!ptrs_dev || !offsets_dev || !flat || n_tensors <= 0 || total <= 0) return fail(GSR_E_ARG, "flat_unpack: bad argument");
-    flat_copy_kernel<false><<<dim3(32, n_tensors), 256, 0, (cudaStream_t)stream>>>(
-        ptrs_dev, offsets_dev, const_cast<float*>(flat), scale);
-    return launched("flat_unpack");
+    if (!ptrs || !offsets || !flat || n_tensors <= 0 || total <= 0) return fail(GSR_E_ARG, "flat_unpack: bad argument");
+    return flat_copy<false>(ptrs, offsets, n_tensors, const_cast<float*>(flat), scale, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------- measurement aid

@@ -497,15 +497,16 @@ class FlatBucket:
         for t in self.tensors:
             offs.append(offs[-1] + t.numel())
         self.total = offs[-1]
-        self.ptrs = torch.tensor([t.data_ptr() for t in self.tensors], dtype=torch.int64, device=dev)
-        self.offsets = torch.tensor(offs, dtype=torch.int64, device=dev)
+        # host tables: gsr_flat_pack / _unpack pass them to the kernel by value (capturable in a CUDA graph)
+        self.ptrs = (C.c_void_p * len(self.tensors))(*[t.data_ptr() for t in self.tensors])
+        self.offsets = (C.c_longlong * len(offs))(*offs)
         self.flat = torch.empty((self.total,), device=dev, dtype=torch.float32)
 
     def pack(self, scale: float = 1.0) -> torch.Tensor:
-        check(lib().gsr_flat_pack(self.ptrs.data_ptr(), self.offsets.data_ptr(), len(self.tensors),
+        check(lib().gsr_flat_pack(self.ptrs, self.offsets, len(self.tensors),
                                   self.flat.data_ptr(), self.total, float(scale), _stream()), "gsr_flat_pack")
         return self.flat
 
     def unpack(self, scale: float = 1.0) -> None:
-        check(lib().gsr_flat_unpack(self.ptrs.data_ptr(), self.offsets.data_ptr(), len(self.tensors),
+        check(lib().gsr_flat_unpack(self.ptrs, self.offsets, len(self.tensors),
                                     self.flat.data_ptr(), self.total, float(scale), _stream()), "gsr_flat_unpack")

@@ -81,11 +81,18 @@ class SubjectParallel:
         if grads[0].is_cuda:
             from . import kernels as K
             ptrs = tuple(g.data_ptr() for g in grads)
-            if self._bucket is None or self._bucket_ptrs != ptrs:
-                self._bucket, self._bucket_ptrs = K.FlatBucket(grads), ptrs
-            flat = self._bucket.pack(1.0 / self.world)
+            # one bucket per set of gradient buffers, all kept: a captured CUDA graph (GraphedTrainStep) keeps
+            # replaying into the bucket it was captured with while eager steps use another
+            if self._bucket is None:
+                self._bucket = {}
+            bucket = self._bucket.get(ptrs)
+            if bucket is None:
+                if len(self._bucket) >= 4:
+                    self._bucket.pop(next(iter(self._bucket)))
+                bucket = self._bucket[ptrs] = K.FlatBucket(grads)
+            flat = bucket.pack(1.0 / self.world)
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            self._bucket.unpack(1.0)
+            bucket.unpack(1.0)
         else:   # host-logic tests (gloo): same bucket layout through torch ops
             flat = torch.cat([g.reshape(-1) for g in grads]) / self.world
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)

@@ -252,12 +252,14 @@ GSR_API int gsr_eval_reduce(const float* pred, const float* gt, long long batch,
 
 /* ------------------------------------------------------------------ (e)
  * Pack / unpack the 31 gradient tensors into one flat fp32 bucket for the
- * single NCCL all-reduce of the subject-data-parallel step.  ptrs_dev[n_tensors] is a
- * DEVICE array of device pointers, offsets_dev[n_tensors + 1] the DEVICE array of
- * element offsets of each tensor inside the bucket; values are multiplied by scale. */
-GSR_API int gsr_flat_pack(const float* const* ptrs_dev, const long long* offsets_dev, int n_tensors,
+ * single NCCL all-reduce of the subject-data-parallel step.  ptrs[n_tensors] is a HOST
+ * array of device pointers, offsets[n_tensors + 1] the HOST array of element offsets of
+ * each tensor inside the bucket (both are read during the call and travel in the kernel
+ * parameters, so the launches can be captured in a CUDA graph); values are multiplied by
+ * scale. */
+GSR_API int gsr_flat_pack(const float* const* ptrs, const long long* offsets, int n_tensors,
                   float* flat, long long total, float scale, void* stream);
-GSR_API int gsr_flat_unpack(float* const* ptrs_dev, const long long* offsets_dev, int n_tensors,
+GSR_API int gsr_flat_unpack(float* const* ptrs, const long long* offsets, int n_tensors,
                     const float* flat, long long total, float scale, void* stream);
 
 /* ------------------------------------------------------------------ measurement aid

@@ -652,3 +652,16 @@ def test_submission_edge(cuda_pkg, tmp_path):
     lines = path.read_text().splitlines()
     assert lines[0] == "ID,Predicted" and lines[1].startswith("1,") and len(lines) == 6
     assert float(lines[3].split(",")[1]) == float(row[2])
+
+
+def test_flat_bucket_pack_unpack_roundtrip(K):
+    """(e) gradient bucket: 70 tensors (two parameter-table chunks of csrc/api.cu), scale on the way in."""
+    g = torch.Generator().manual_seed(70)
+    tensors = [torch.randn(int(n), generator=g).cuda() for n in torch.randint(1, 3000, (70,), generator=g)]
+    want = torch.cat([t.reshape(-1) for t in tensors]) * 0.25
+    bucket = K.FlatBucket(tensors)
+    flat = bucket.pack(0.25)
+    assert torch.equal(flat, want)
+    flat.mul_(2.0)
+    bucket.unpack(1.0)
+    assert torch.equal(torch.cat([t.reshape(-1) for t in tensors]), want * 2.0)
