@@ -441,11 +441,12 @@ def run_ours(args):
         "frac_of_3xtf32_ceiling": (gemm_tflops / (bf16_peak / 6.0)) if (gemm_tflops and backend == "tc") else None,
         "share_of_step": gemm_ms / instrumented_ms if instrumented_ms else None, "launches": gemm_launches,
         "algorithmic_flop_per_subject": GEMM_FLOP_PER_SUBJECT_FWD_BWD,
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE per-subject 268^3 launch (1024 subjects) inside the step,
-        # from the committed ncu --set full capture; the algorithmic bytes of that launch are 3 x 294 MB = 882 MB
-        # (part of the operands is still L2 resident from the producing kernel)
-        "traffic": 541.2e6 if backend == "tc" else None,
-        "traffic_source": "profiles/r1_tcgemm_ncu_summary.txt, tcgemm_kernel<0,0,0> grid 3072: 294.5 MB read + 246.7 MB written per launch",
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE per-subject launch (rows 0..255 of 1024 TN products, CTA pairs)
+        # inside the step, from the committed ncu --set full capture; the algorithmic bytes of that launch are
+        # 1024 x (256 x 268 + 268 x 268 + 256 x 268) x 4 B = 856 MB (part of the operands is still L2 resident from the
+        # producing kernel, and the output is written once)
+        "traffic": 404.1e6 if backend == "tc" else None,
+        "traffic_source": "profiles/r1_ncu_summary_tcgemm2_tail.txt, tcgemm2_kernel<1,0,0> grid 2048: 175.8 MB read + 228.2 MB written per launch",
         "unet_simt_products": {"launches": simt_launches, "gflop_per_step": simt_flops / max(args.steps, 1) / 1e9,
                                "note": "Graph U-Net linears (once per step, subject independent) on gsr::bgemm_kernel, "
                                        "side stream under the eigendecomposition; not part of `achieved`"},
