@@ -105,6 +105,39 @@ class LinearFn(Function):
         return gX, gW, gb
 
 
+class BatchNormActFn(Function):
+    """models/mlp.py:14-16 (and :22-24): BatchNorm1d -> Dropout(p) -> ReLU in one pass.  ``mean`` / ``var`` are the
+    batch statistics (training) or the running estimates (eval); the dropout mask is recomputed from ``seed``."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, mean, var, eps, p_drop, seed, relu, batch_stats):
+        ctx.save_for_backward(x, gamma, beta, mean, var)
+        ctx.cfg = (eps, p_drop, seed, relu, batch_stats)
+        return K.bn_act_fwd(x, mean, var, gamma, beta, eps, p_drop, seed, relu)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, gamma, beta, mean, var = ctx.saved_tensors
+        eps, p_drop, seed, relu, batch_stats = ctx.cfg
+        dx, dgamma, dbeta = K.bn_act_bwd(x, mean, var, gamma, beta, _c(gy), eps, p_drop, seed, relu, batch_stats)
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def batch_norm_act(x, gamma, beta, running_mean, running_var, training, momentum=0.1, eps=1e-5, p_drop=0.0,
+                   relu=False, seed=None):
+    """BatchNorm1d (+ Dropout + ReLU) on x [B, H].  Training: batch statistics, running estimates updated in place,
+    dropout active with a seed drawn from torch's default generator unless given.  Eval: running estimates, no
+    dropout."""
+    if training:
+        mean, var = K.bn_stats(x.detach(), running_mean, running_var, momentum)
+        if p_drop > 0 and seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    else:
+        mean, var, p_drop = running_mean, running_var, 0.0
+    return BatchNormActFn.apply(x, gamma, beta, mean, var, float(eps), float(p_drop), int(seed or 0), bool(relu), bool(training))
+
+
 # ----------------------------------------------------------------------------- a8 / a9
 class GraphPoolFn(Function):
     """models/ops.py:35-45: scores, top-k (stated tie rule), gather * score."""

@@ -482,6 +482,41 @@ def eval_reduce(pred: torch.Tensor, gt: torch.Tensor, upper: bool) -> torch.Tens
     return res
 
 
+# --------------------------------------------------------------------- N2: BatchNorm1d + Dropout + ReLU
+def bn_stats(x: torch.Tensor, running_mean=None, running_var=None, momentum: float = 0.1):
+    """Batch mean and biased variance of x [B, H]; updates the running estimates in place when given."""
+    x = _f32(x, "bn_stats: x")
+    B, H = x.shape
+    mean, var = torch.empty((H,), device=x.device), torch.empty((H,), device=x.device)
+    check(lib().gsr_bn_stats_f32(x.data_ptr(), B, H, mean.data_ptr(), var.data_ptr(),
+                                 running_mean.data_ptr() if running_mean is not None else None,
+                                 running_var.data_ptr() if running_var is not None else None,
+                                 float(momentum), _stream()), "gsr_bn_stats_f32")
+    return mean, var
+
+
+def bn_act_fwd(x, mean, var, gamma, beta, eps: float, p_drop: float, seed: int, relu: bool) -> torch.Tensor:
+    x = _f32(x, "bn_act_fwd: x")
+    B, H = x.shape
+    y = torch.empty_like(x)
+    check(lib().gsr_bn_act_fwd_f32(x.data_ptr(), mean.data_ptr(), var.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                   float(eps), float(p_drop), int(seed), int(relu), y.data_ptr(), B, H, _stream()),
+          "gsr_bn_act_fwd_f32")
+    return y
+
+
+def bn_act_bwd(x, mean, var, gamma, beta, dy, eps: float, p_drop: float, seed: int, relu: bool, batch_stats: bool):
+    x, dy = _f32(x, "bn_act_bwd: x"), _f32(dy, "bn_act_bwd: dy")
+    B, H = x.shape
+    dx = torch.empty_like(x)
+    dgamma, dbeta = torch.empty((H,), device=x.device), torch.empty((H,), device=x.device)
+    check(lib().gsr_bn_act_bwd_f32(x.data_ptr(), mean.data_ptr(), var.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                   dy.data_ptr(), float(eps), float(p_drop), int(seed), int(relu), int(batch_stats),
+                                   dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), B, H, _stream()),
+          "gsr_bn_act_bwd_f32")
+    return dx, dgamma, dbeta
+
+
 # --------------------------------------------------------------------- flat gradient bucket
 class FlatBucket:
     """Device-side table (pointers + offsets) of a list of fp32 tensors, for the one-launch

@@ -262,6 +262,30 @@ GSR_API int gsr_flat_pack(const float* const* ptrs, const long long* offsets, in
 GSR_API int gsr_flat_unpack(float* const* ptrs, const long long* offsets, int n_tensors,
                     const float* flat, long long total, float scale, void* stream);
 
+/* ------------------------------------------------------------------ N2 (SURVEY 8 f)
+ * MLP baseline, models/mlp.py:7-27: the BatchNorm1d -> Dropout(p) -> ReLU run between two
+ * Linear layers (the Linear layers themselves are gsr_tcgemm_f32 / gsr_bgemm_f32 with the
+ * BIAS epilogue).  x, y, dy, dx are [batch][features] row-major fp32.
+ * gsr_bn_stats_f32: training statistics of nn.BatchNorm1d -- mean[features], biased
+ *   var[features]; when running_mean / running_var are given they are updated in place as
+ *   torch does ((1 - momentum) * running + momentum * batch value, unbiased variance).
+ * gsr_bn_act_fwd_f32: y = relu?( drop( gamma * (x - mean) / sqrt(var + eps) + beta ) ).
+ *   (mean, var) are the batch statistics when training, the running estimates in eval mode.
+ *   Dropout keeps element e iff u(seed, e) >= p_drop and scales by 1 / (1 - p_drop), u being
+ *   the top 24 bits of splitmix64(seed + e * 0x9E3779B97F4A7C15) / 2^24; p_drop = 0 disables
+ *   it.  Nothing is stored for the backward pass.
+ * gsr_bn_act_bwd_f32: dx, dgamma[features], dbeta[features] from dy with the same seed;
+ *   batch_stats = 1 when (mean, var) were computed from x (training), 0 for constants.  */
+GSR_API int gsr_bn_stats_f32(const float* x, int batch, int features, float* mean, float* var,
+                     float* running_mean, float* running_var, float momentum, void* stream);
+GSR_API int gsr_bn_act_fwd_f32(const float* x, const float* mean, const float* var, const float* gamma,
+                       const float* beta, float eps, float p_drop, unsigned long long seed, int relu,
+                       float* y, int batch, int features, void* stream);
+GSR_API int gsr_bn_act_bwd_f32(const float* x, const float* mean, const float* var, const float* gamma,
+                       const float* beta, const float* dy, float eps, float p_drop,
+                       unsigned long long seed, int relu, int batch_stats, float* dx, float* dgamma,
+                       float* dbeta, int batch, int features, void* stream);
+
 /* ------------------------------------------------------------------ measurement aid
  * Launches an FFMA-only kernel (8 independent chains per thread, 148*8 CTAs of 256 threads)
  * and returns the flops it executes; timed by the caller with CUDA events to obtain the

@@ -606,6 +606,37 @@ def test_eval_reductions_golden(cuda_pkg, golden, tag):
     assert mae2 == pytest.approx(mae, rel=1e-12) and pcc2 == pytest.approx(pcc, rel=1e-10) and js2 == pytest.approx(js, rel=1e-10)
 
 
+def test_eval_reductions_full_sweep_10k(cuda_pkg):
+    """BASELINE configs[4]: 10 000 predictions against ground truth (268 nodes) in one call, checked against
+    float64 sums accumulated chunk by chunk with torch (sklearn / scipy definitions of utils/evaluation.py:106-112)."""
+    N, n, chunk = 10000, 268, 1000
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.rand(N, n, n, device="cuda", generator=g)
+    gt = (x + x.transpose(1, 2)) / 2
+    del x
+    noise = torch.randn(N, n, n, device="cuda", generator=g) * 0.1
+    pred = torch.clamp(gt + (noise + noise.transpose(1, 2)) / 2, 0, 1)
+    del noise
+    mae, pcc, js = cuda_pkg.evaluation_reductions(pred, gt)
+    iu = torch.triu_indices(n, n, 1, device="cuda")
+    S = dict(ad=0.0, p=0.0, g=0.0, pp=0.0, gg=0.0, pg=0.0)
+    for s0 in range(0, N, chunk):
+        pc = pred[s0:s0 + chunk][:, iu[0], iu[1]].double(); gc = gt[s0:s0 + chunk][:, iu[0], iu[1]].double()
+        S["ad"] += float((pc - gc).abs().sum()); S["p"] += float(pc.sum()); S["g"] += float(gc.sum())
+        S["pp"] += float((pc * pc).sum()); S["gg"] += float((gc * gc).sum()); S["pg"] += float((pc * gc).sum())
+    cnt = N * n * (n - 1) // 2
+    assert mae == pytest.approx(S["ad"] / cnt, rel=1e-10)
+    cov = S["pg"] - S["p"] * S["g"] / cnt
+    want_pcc = cov / np.sqrt((S["pp"] - S["p"] ** 2 / cnt) * (S["gg"] - S["g"] ** 2 / cnt))
+    assert pcc == pytest.approx(want_pcc, rel=1e-8)
+    kl = 0.0
+    for s0 in range(0, N, chunk):
+        pc = pred[s0:s0 + chunk][:, iu[0], iu[1]].double() / S["p"]; gc = gt[s0:s0 + chunk][:, iu[0], iu[1]].double() / S["g"]
+        m = (pc + gc) / 2
+        kl += float(torch.special.xlogy(pc, pc / m).sum()) + float(torch.special.xlogy(gc, gc / m).sum())
+    assert js == pytest.approx(np.sqrt(kl / 2), rel=1e-8)
+
+
 def test_eval_reductions_zero_entries(cuda_pkg):
     # rel_entr conventions: zeros in gt and pred contribute 0, not NaN
     gt = torch.rand(3, 20, 20); pred = torch.rand(3, 20, 20)
