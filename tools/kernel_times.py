@@ -91,6 +91,32 @@ def main():
     P = torch.rand(10000 // 8, 268, 268, device=dev, generator=g); Gt = torch.rand(10000 // 8, 268, 268, device=dev, generator=g)
     ms = timeit(lambda: K.eval_reduce(P, Gt, True), reps=3, warm=1)
     report("eval_reduce upper (1250 pairs)", ms, bytes_=2 * 2 * 35778 * 4 * P.shape[0])
+    del P, Gt
+    # N2: the MLP baseline at the challenge size (12 720 LR features -> 268 x 268), batch 512, hidden 1024 x 2
+    Bm, Hm, In, Out = 512, 1024, 12720, 268 * 268
+    torch.manual_seed(0)
+    mlp = pkg.SuperResMLP(In, Out, Hm, 2).to(dev)
+    xm = torch.rand(Bm, In, device=dev, generator=g)
+    fwd_flops = 2 * Bm * (In * Hm + Hm * Hm + Hm * Out)
+    mlp.eval()
+    with torch.no_grad():
+        ms = timeit(lambda: mlp(xm), reps=5, warm=2)
+    report("SuperResMLP 12720-1024-1024-71824 forward (eval), batch 512", ms, flops=fwd_flops)
+    mlp.train()
+    def train_step():
+        mlp.zero_grad(set_to_none=True)
+        mlp(xm).sum().backward()
+    ms = timeit(train_step, reps=5, warm=2)
+    report("SuperResMLP 12720-1024-1024-71824 forward + backward (train), batch 512", ms, flops=3 * fwd_flops - 2 * Bm * In * Hm)
+    xb = torch.randn(4096, 4096, device=dev, generator=g)
+    mean, var = K.bn_stats(xb)
+    ga, be = torch.ones(4096, device=dev), torch.zeros(4096, device=dev)
+    ms = timeit(lambda: K.bn_stats(xb), reps=5, warm=2)
+    report("bn_stats 4096 x 4096 (two passes)", ms, bytes_=2 * xb.numel() * 4)
+    ms = timeit(lambda: K.bn_act_fwd(xb, mean, var, ga, be, 1e-5, 0.1, 7, True), reps=5, warm=2)
+    report("bn_act_fwd 4096 x 4096 (BatchNorm + Dropout 0.1 + ReLU)", ms, bytes_=2 * xb.numel() * 4)
+    ms = timeit(lambda: K.bn_act_bwd(xb, mean, var, ga, be, xb, 1e-5, 0.1, 7, True, True), reps=5, warm=2)
+    report("bn_act_bwd 4096 x 4096 (reduce + apply)", ms, bytes_=5 * xb.numel() * 4)
 
 
 if __name__ == "__main__":
