@@ -2,8 +2,8 @@
 //   [Linear] -> BatchNorm1d -> Dropout(0.1) -> ReLU           (x is [batch][features], row-major)
 // The Linear layers are dense GEMMs on gsr_tcgemm_f32 / gsr_bgemm_f32; the three layers in between are one
 // memory-bound pass here (batch statistics first when training).  The dropout mask is a counter-based hash of
-// (seed, element index): nothing is stored, the backward pass recomputes it, and oracle/mlp_oracle.py reproduces
-// it bit for bit.
+// (seed, element index): nothing is stored, the backward pass recomputes it, and the CPU restatement used by the
+// tests reproduces it bit for bit.
 #include "common.cuh"
 
 namespace gsr {
