@@ -9,7 +9,8 @@
 namespace gsr {
 namespace mlp {
 
-constexpr int TX = 32, TY = 8;
+constexpr int TX = 32, TY = 32;        // column reductions: 32 features x 32 batch phases per CTA
+constexpr int EW_THREADS = 128, EW_ROWS = 16;   // elementwise passes: a thread owns VEC columns over EW_ROWS rows
 
 // splitmix64 of seed + golden * index, top 24 bits as a uniform in [0, 1)
 __device__ __forceinline__ float uniform01(unsigned long long seed, unsigned long long index) {
@@ -58,17 +59,43 @@ __device__ __forceinline__ float keep_scale(float p_drop, unsigned long long see
     return uniform01(seed, index) >= p_drop ? 1.f / (1.f - p_drop) : 0.f;
 }
 
-__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mean,
-                                                         const float* __restrict__ var, const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, float eps, float p_drop,
-                                                         unsigned long long seed, int relu, float* __restrict__ y,
-                                                         long long total, int features) {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int h = (int)(e % features);
-        const float rstd = 1.f / sqrtf(__ldg(var + h) + eps);
-        float z = (__ldg(x + e) - __ldg(mean + h)) * rstd * __ldg(gamma + h) + __ldg(beta + h);
-        z *= keep_scale(p_drop, seed, (unsigned long long)e);
-        y[e] = relu ? fmaxf(z, 0.f) : z;
+// A thread owns VEC consecutive features (float4 when the row length allows) and walks EW_ROWS batch rows: the
+// per-feature constants are loaded and inverted once, the element index of the dropout hash needs no division.
+template <int VEC> struct Pack { float v[VEC]; };
+template <int VEC> __device__ __forceinline__ Pack<VEC> load_pack(const float* p) {
+    Pack<VEC> r;
+    if (VEC == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; }
+    else r.v[0] = __ldg(p);
+    return r;
+}
+template <int VEC> __device__ __forceinline__ void store_pack(float* p, const Pack<VEC>& r) {
+    if (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    else p[0] = r.v[0];
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                                const float* __restrict__ var, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float eps, float p_drop,
+                                                                unsigned long long seed, int relu, float* __restrict__ y,
+                                                                int batch, int features) {
+    const int h = (blockIdx.x * EW_THREADS + threadIdx.x) * VEC;
+    if (h >= features) return;
+    const Pack<VEC> m = load_pack<VEC>(mean + h), va = load_pack<VEC>(var + h), ga = load_pack<VEC>(gamma + h), be = load_pack<VEC>(beta + h);
+    float rstd[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) rstd[i] = 1.f / sqrtf(va.v[i] + eps);
+    const int b0 = blockIdx.y * EW_ROWS, b1 = min(b0 + EW_ROWS, batch);
+    for (int b = b0; b < b1; ++b) {
+        const size_t e = (size_t)b * features + h;
+        Pack<VEC> v = load_pack<VEC>(x + e);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float z = (v.v[i] - m.v[i]) * rstd[i] * ga.v[i] + be.v[i];
+            z *= keep_scale(p_drop, seed, (unsigned long long)(e + i));
+            v.v[i] = relu ? fmaxf(z, 0.f) : z;
+        }
+        store_pack<VEC>(y + e, v);
     }
 }
 
@@ -101,25 +128,40 @@ __global__ void __launch_bounds__(TX * TY) bn_bwd_reduce_kernel(const float* __r
     if (live && threadIdx.y == 0) { dbeta[h] = sb; dgamma[h] = sg; }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
-                                                           const float* __restrict__ var, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, const float* __restrict__ dy,
-                                                           const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-                                                           float eps, float p_drop, unsigned long long seed, int relu,
-                                                           int batch_stats, float* __restrict__ dx, long long total,
-                                                           int batch, int features) {
+template <int VEC>
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                                  const float* __restrict__ var, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, const float* __restrict__ dy,
+                                                                  const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                                                                  float eps, float p_drop, unsigned long long seed, int relu,
+                                                                  int batch_stats, float* __restrict__ dx, int batch, int features) {
+    const int h = (blockIdx.x * EW_THREADS + threadIdx.x) * VEC;
+    if (h >= features) return;
+    const Pack<VEC> m = load_pack<VEC>(mean + h), va = load_pack<VEC>(var + h), ga = load_pack<VEC>(gamma + h), be = load_pack<VEC>(beta + h);
+    const Pack<VEC> dg = load_pack<VEC>(dgamma + h), db = load_pack<VEC>(dbeta + h);
     const float inv_b = 1.f / (float)batch;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int h = (int)(e % features);
-        const float rstd = 1.f / sqrtf(__ldg(var + h) + eps), ga = __ldg(gamma + h);
-        const float xhat = (__ldg(x + e) - __ldg(mean + h)) * rstd;
-        float g = upstream(__ldg(dy + e), xhat, ga, __ldg(beta + h), p_drop, seed, (unsigned long long)e, relu);
-        if (batch_stats) g -= (__ldg(dbeta + h) + xhat * __ldg(dgamma + h)) * inv_b;     // the statistics depend on x
-        dx[e] = ga * rstd * g;
+    float rstd[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) rstd[i] = 1.f / sqrtf(va.v[i] + eps);
+    const int b0 = blockIdx.y * EW_ROWS, b1 = min(b0 + EW_ROWS, batch);
+    for (int b = b0; b < b1; ++b) {
+        const size_t e = (size_t)b * features + h;
+        const Pack<VEC> xv = load_pack<VEC>(x + e), dv = load_pack<VEC>(dy + e);
+        Pack<VEC> out;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float xhat = (xv.v[i] - m.v[i]) * rstd[i];
+            float g = upstream(dv.v[i], xhat, ga.v[i], be.v[i], p_drop, seed, (unsigned long long)(e + i), relu);
+            if (batch_stats) g -= (db.v[i] + xhat * dg.v[i]) * inv_b;                     // the statistics depend on x
+            out.v[i] = ga.v[i] * rstd[i] * g;
+        }
+        store_pack<VEC>(dx + e, out);
     }
 }
 
-static int grid_for(long long total) { return (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 8); }
+static bool vec4_ok(int features, const void* a, const void* b, const void* c) {
+    return features % 4 == 0 && aligned16(a) && aligned16(b) && (!c || aligned16(c));
+}
 
 }  // namespace mlp
 }  // namespace gsr
@@ -139,9 +181,12 @@ extern "C" int gsr_bn_act_fwd_f32(const float* x, const float* mean, const float
                                   float* y, int batch, int features, void* stream) {
     if (!x || !mean || !var || !gamma || !beta || !y || batch <= 0 || features <= 0 || !(p_drop >= 0.f && p_drop < 1.f))
         return fail(GSR_E_ARG, "bn_act_fwd: bad argument");
-    const long long total = (long long)batch * features;
-    mlp::bn_act_fwd_kernel<<<mlp::grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, mean, var, gamma, beta, eps, p_drop, seed,
-                                                                                  relu, y, total, features);
+    const bool v4 = mlp::vec4_ok(features, x, y, nullptr) && aligned16(mean) && aligned16(var) && aligned16(gamma) && aligned16(beta);
+    const int per = mlp::EW_THREADS * (v4 ? 4 : 1);
+    dim3 grid((features + per - 1) / per, (batch + mlp::EW_ROWS - 1) / mlp::EW_ROWS);
+    if (grid.y > 65535) return fail(GSR_E_UNSUPPORTED, "bn_act_fwd: batch too large");
+    if (v4) mlp::bn_act_fwd_kernel<4><<<grid, mlp::EW_THREADS, 0, (cudaStream_t)stream>>>(x, mean, var, gamma, beta, eps, p_drop, seed, relu, y, batch, features);
+    else mlp::bn_act_fwd_kernel<1><<<grid, mlp::EW_THREADS, 0, (cudaStream_t)stream>>>(x, mean, var, gamma, beta, eps, p_drop, seed, relu, y, batch, features);
     return launched("bn_act_fwd");
 }
 
@@ -157,8 +202,12 @@ extern "C" int gsr_bn_act_bwd_f32(const float* x, const float* mean, const float
         x, mean, var, gamma, beta, dy, eps, p_drop, seed, relu, dgamma, dbeta, batch, features);
     int rc = launched("bn_bwd_reduce");
     if (rc) return rc;
-    const long long total = (long long)batch * features;
-    mlp::bn_bwd_apply_kernel<<<mlp::grid_for(total), 256, 0, st>>>(x, mean, var, gamma, beta, dy, dgamma, dbeta, eps, p_drop, seed,
-                                                                  relu, batch_stats, dx, total, batch, features);
+    const bool v4 = mlp::vec4_ok(features, x, dy, dx) && aligned16(mean) && aligned16(var) && aligned16(gamma) && aligned16(beta) &&
+                    aligned16(dgamma) && aligned16(dbeta);
+    const int per = mlp::EW_THREADS * (v4 ? 4 : 1);
+    dim3 grid((features + per - 1) / per, (batch + mlp::EW_ROWS - 1) / mlp::EW_ROWS);
+    if (grid.y > 65535) return fail(GSR_E_UNSUPPORTED, "bn_act_bwd: batch too large");
+    if (v4) mlp::bn_bwd_apply_kernel<4><<<grid, mlp::EW_THREADS, 0, st>>>(x, mean, var, gamma, beta, dy, dgamma, dbeta, eps, p_drop, seed, relu, batch_stats, dx, batch, features);
+    else mlp::bn_bwd_apply_kernel<1><<<grid, mlp::EW_THREADS, 0, st>>>(x, mean, var, gamma, beta, dy, dgamma, dbeta, eps, p_drop, seed, relu, batch_stats, dx, batch, features);
     return launched("bn_bwd_apply");
 }
