@@ -54,12 +54,10 @@ struct Params {
     float alpha;
     int epilogue;
     const float* extra; int ld_extra; long long s_extra;
-    int mn_swap;
 };
 
-int g_mn_swap = 0;      // bring-up knob (unused)
-int g_pairs = 1;        // gsr_tcgemm_debug key 1: CTA-pair kernel (cta_group::2) for gsr_tcgemm_f32 (default), 0 = one CTA per tile
-int g_tail = 1;         // gsr_tcgemm_debug key 2: FP32 kernels for the <= 16 ragged rows after the CTA pairs (default), 0 = one-CTA tensor kernel
+int g_pairs = 1;        // gsr_set_tuning("tcgemm_pairs"): CTA-pair kernel (cta_group::2) for gsr_tcgemm_f32 (default), 0 = one CTA per tile
+int g_tail = 1;         // gsr_set_tuning("tcgemm_ragged_rows"): FP32 kernels for the <= 16 ragged rows after the CTA pairs (default), 0 = one-CTA tensor kernel
 
 #ifdef GSR_TC_TRACE
 // Pipeline trace (tools/tc_trace.py builds a private copy of the library with -DGSR_TC_TRACE):
@@ -1055,12 +1053,6 @@ static ReducePlan reduce_plan(int M, int N, int batch, int splits) {
 
 using namespace gsr;
 
-extern "C" __attribute__((visibility("default"))) int gsr_tcgemm_debug(int key, int value) {
-    if (key == 0) tc::g_mn_swap = value;
-    if (key == 1) tc::g_pairs = value;
-    if (key == 2) tc::g_tail = value;
-    return 0;
-}
 #ifdef GSR_TC_TRACE
 extern "C" __attribute__((visibility("default"))) int gsr_tcgemm_trace_read(unsigned long long* host, int count) {
     return (int)cudaMemcpyFromSymbol(host, tc::g_trace, sizeof(unsigned long long) * count);
@@ -1083,7 +1075,7 @@ extern "C" int gsr_tcgemm_f32(const float* A, const float* B, float* C,
     if (M == 0 || N == 0 || batch == 0) return 0;
     if (batch > 65535) return fail(GSR_E_UNSUPPORTED, "tcgemm: batch > 65535");
     tc::Params p{A, B, C, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch, 1, alpha,
-                 epilogue, extra, ld_extra, stride_extra, tc::g_mn_swap};
+                 epilogue, extra, ld_extra, stride_extra};
     if (!tc::operands_ok(p)) return fail(GSR_E_ALIGN, "tcgemm: operands must be 16-byte aligned with leading dimensions % 4 == 0");
     if (tc::g_pairs && tc::pair_ok(p) && (long long)(transA ? K : M) * lda < 0x7fffffffLL && (long long)(transB ? N : K) * ldb < 0x7fffffffLL) {
         // CTA pairs (cta_group::2) for the first 2 * floor(tiles / 2) M tiles, the one-CTA kernel for an odd last tile
@@ -1128,7 +1120,7 @@ extern "C" int gsr_tcgemm_reduce_f32(const float* A, const float* B, float* C,
     if (epilogue == GSR_EPI_ADD && !extra) return fail(GSR_E_ARG, "tcgemm_reduce: epilogue needs `extra`");
     if (splits > batch) splits = batch;
     tc::Params p{A, B, workspace, M, N, K, lda, ldb, N, strideA, strideB, (long long)M * N, batch, splits, 1.0f,
-                 GSR_EPI_NONE, nullptr, 0, 0, tc::g_mn_swap};
+                 GSR_EPI_NONE, nullptr, 0, 0};
     if (!tc::operands_ok(p)) return fail(GSR_E_ALIGN, "tcgemm_reduce: operands must be 16-byte aligned with leading dimensions % 4 == 0");
     const int tiles_m = (M + tc::BM - 1) / tc::BM;
     const tc::ReducePlan plan = tc::reduce_plan(M, N, batch, splits);

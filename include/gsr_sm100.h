@@ -44,8 +44,10 @@ GSR_API int         gsr_abi_version(void);
 GSR_API const char* gsr_last_error(void);
 /* Number of kernels launched by this library since load (bench.py "gpu_launches"). */
 GSR_API uint64_t    gsr_launch_count(void);
-/* Kernel-variant selection for benchmarking ("gemm_variant": 0, 1, 2; see csrc/bgemm.cu).
- * Results are identical across variants (same arithmetic order).                 */
+/* Kernel-variant selection for benchmarking and tests: "gemm_variant" 0, 1, 2 (csrc/bgemm.cu; identical
+ * results), "tcgemm_pairs" 1 / 0 (CTA-pair tensor kernel or one CTA per tile; identical results),
+ * "tcgemm_ragged_rows" 1 / 0 (FP32 kernels or the tensor kernel for the <= 16 rows after the pairs;
+ * equal to rounding), "eigh_ql_max_iter", "eigh_oddeven", "eigh_max_polish".        */
 GSR_API int         gsr_set_tuning(const char* key, int value);
 
 /* ------------------------------------------------------------------ a1

@@ -375,6 +375,29 @@ def test_bgemm_vs_float64(K, gemm_backend, tA, tB, shape):
         assert float((got.double() - want).abs().max()) <= tol, (shape, tA, tB, batch, sharedB)
 
 
+def test_tcgemm_pair_kernel_equals_one_cta_kernel(cuda_pkg, K):
+    """cta_group::2 pairs (M = 256 per MMA) against one CTA per 128-row tile: same split, same MMA order, so the
+    results are bit identical; the FP32 ragged rows differ from the tensor kernel by rounding only."""
+    g = torch.Generator(device="cuda").manual_seed(31)
+    A = torch.randn(7, 268, 268, device="cuda", generator=g); B = torch.randn(7, 268, 268, device="cuda", generator=g)
+    W = torch.randn(268, 268, device="cuda", generator=g)
+    calls = [lambda: K.bgemm(A, B), lambda: K.bgemm(A, B, transA=True), lambda: K.bgemm(A, B, transB=True),
+             lambda: K.bgemm(A, W), lambda: K.bgemm(A, W, transB=True), lambda: K.bgemm_reduce(A, B, transA=True)]
+    try:
+        cuda_pkg.set_tuning("tcgemm_pairs", 0)
+        one = [c() for c in calls]
+        cuda_pkg.set_tuning("tcgemm_pairs", 1); cuda_pkg.set_tuning("tcgemm_ragged_rows", 0)
+        pairs = [c() for c in calls]
+        cuda_pkg.set_tuning("tcgemm_ragged_rows", 1)
+        ragged = [c() for c in calls]
+    finally:
+        cuda_pkg.set_tuning("tcgemm_pairs", 1); cuda_pkg.set_tuning("tcgemm_ragged_rows", 1)
+    for a, b, c in zip(one, pairs, ragged):
+        assert torch.equal(a, b)
+        assert torch.equal(a[..., :256, :], c[..., :256, :])
+        assert float((a - c).abs().max()) < 4e-6 * float(a.abs().max())
+
+
 @pytest.mark.parametrize("tA", [False, True])
 @pytest.mark.parametrize("tB", [False, True])
 @pytest.mark.parametrize("M", [257, 260, 265, 268, 272])

@@ -1,10 +1,11 @@
-"""CTA-pair tcgemm (gsr_tcgemm_debug key 1): accuracy against float64 and time against the one-CTA kernel."""
+"""CTA-pair tcgemm and the FP32 ragged-row kernels (gsr_set_tuning keys tcgemm_pairs / tcgemm_ragged_rows): accuracy
+against float64 and time against the one-CTA kernel."""
 import ctypes, importlib, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 pkg = importlib.import_module("fmri-connectivity-super-resolution_b200"); K = pkg.kernels
 lib = pkg.lib()
-dbg = lib.gsr_tcgemm_debug; dbg.argtypes = [ctypes.c_int, ctypes.c_int]; dbg.restype = ctypes.c_int
+def dbg(key, value): pkg.set_tuning({1: "tcgemm_pairs", 2: "tcgemm_ragged_rows"}[key], value)
 g = torch.Generator(device="cuda").manual_seed(0)
 def timeit(fn, reps=5):
     for _ in range(2): fn()
