@@ -140,10 +140,14 @@ class GraphedTrainStep:
     as the reference's loop computes it every step.  Capture runs ``warmup`` real steps first (lazy
     allocations, cudaFuncSetAttribute); parameters and optimiser state are restored afterwards, so the first
     replay is the first step of the run.  ``grad_sync`` (e.g. ``SubjectParallel.sync_gradients``) is captured
-    between backward and the optimiser update."""
+    between backward and the optimiser update.
+
+    ``slots=2`` captures the step once per set of input buffers (the graphs share one memory pool): a loader
+    fills ``inputs(1)`` -- e.g. host-to-device copies on another stream -- while ``replay(0)`` runs, and no
+    device-to-device staging copy is needed."""
 
     def __init__(self, model, optimizer, batch, lmbda=16, padding=0, hr_basis_in_graph=False, grad_sync=None,
-                 warmup=3):
+                 warmup=3, slots=1):
         for group in optimizer.param_groups:
             if not group.get("capturable", False):
                 raise ValueError("GraphedTrainStep: build the optimiser with capturable=True (its step counter must "
@@ -155,16 +159,22 @@ class GraphedTrainStep:
         self.model, self.optimizer = model, optimizer
         self.eager = GSRTrainStep(model, lmbda, padding)
         hr_dim = layer.hr_dim - 2 * padding
-        self.lr = torch.zeros(batch, layer.lr_dim, layer.lr_dim, device=dev)
-        self.hr = torch.zeros(batch, hr_dim, hr_dim, device=dev)
-        self.U_hr = None if hr_basis_in_graph else torch.zeros(batch, layer.hr_dim, layer.lr_dim, device=dev)
-        # unit-diagonal placeholders keep the warm-up eigendecompositions well defined
-        self.lr.diagonal(dim1=1, dim2=2).fill_(1.0)
-        self.hr.diagonal(dim1=1, dim2=2).fill_(1.0)
+        self.slots = max(int(slots), 1)
+        self._in = []
+        for _ in range(self.slots):
+            lr = torch.zeros(batch, layer.lr_dim, layer.lr_dim, device=dev)
+            hr = torch.zeros(batch, hr_dim, hr_dim, device=dev)
+            # unit-diagonal placeholders keep the warm-up eigendecompositions well defined
+            lr.diagonal(dim1=1, dim2=2).fill_(1.0)
+            hr.diagonal(dim1=1, dim2=2).fill_(1.0)
+            U = None if hr_basis_in_graph else torch.zeros(batch, layer.hr_dim, layer.lr_dim, device=dev)
+            self._in.append((lr, hr, U))
+        self.lr, self.hr, self.U_hr = self._in[0]
 
-        def one():
+        def one(slot=0):
+            lr, hr, U = self._in[slot]
             optimizer.zero_grad(set_to_none=True)
-            out = self.eager(self.lr, self.hr, U_hr_reduced=self.U_hr)
+            out = self.eager(lr, hr, U_hr_reduced=U)
             if grad_sync is not None:
                 grad_sync()
             optimizer.step()
@@ -181,12 +191,18 @@ class GraphedTrainStep:
             for _ in range(max(int(warmup), 1)):
                 one()
         torch.cuda.current_stream().wait_stream(side)
-        optimizer.zero_grad(set_to_none=True)
-        self.graph = torch.cuda.CUDAGraph()
-        n0 = launch_count()
-        with torch.cuda.graph(self.graph):
-            self.loss, self.error = one()
-        self.launches_per_step = launch_count() - n0        # launches of this library inside one replay
+        self._graphs, self._out = [], []
+        for slot in range(self.slots):
+            optimizer.zero_grad(set_to_none=True)
+            graph = torch.cuda.CUDAGraph()
+            n0 = launch_count()
+            with torch.cuda.graph(graph, pool=self._graphs[0].pool() if self._graphs else None):
+                out = one(slot)
+            self.launches_per_step = launch_count() - n0    # launches of this library inside one replay
+            self._graphs.append(graph)
+            self._out.append(out)
+        self.graph = self._graphs[0]
+        self.loss, self.error = self._out[0]
         with torch.no_grad():
             for p, q in zip(params, saved_params):
                 p.copy_(q)
@@ -196,22 +212,28 @@ class GraphedTrainStep:
                     if torch.is_tensor(v):
                         v.copy_(old[k]) if k in old else v.zero_()
 
-    def load(self, lr, hr, U_hr_reduced=None, non_blocking=True):
-        """Copy one batch into the static buffers (on the current stream)."""
-        self.lr.copy_(lr, non_blocking=non_blocking)
-        self.hr.copy_(hr, non_blocking=non_blocking)
-        if self.U_hr is not None:
+    def inputs(self, slot=0):
+        """(lr, hr, U_hr_reduced or None): the input buffers graph ``slot`` reads; fill them before ``replay(slot)``."""
+        return self._in[slot]
+
+    def load(self, lr, hr, U_hr_reduced=None, non_blocking=True, slot=0):
+        """Copy one batch into the input buffers of ``slot`` (on the current stream)."""
+        lr_s, hr_s, U_s = self._in[slot]
+        lr_s.copy_(lr, non_blocking=non_blocking)
+        hr_s.copy_(hr, non_blocking=non_blocking)
+        if U_s is not None:
             if U_hr_reduced is None:
                 raise ValueError("GraphedTrainStep: captured with a cached HR basis; pass U_hr_reduced")
-            self.U_hr.copy_(U_hr_reduced, non_blocking=non_blocking)
+            U_s.copy_(U_hr_reduced, non_blocking=non_blocking)
 
-    def replay(self):
-        self.graph.replay()
-        return self.loss, self.error
+    def replay(self, slot=0):
+        """Returns (loss, error) device scalars of this slot's graph; valid until its next replay."""
+        self._graphs[slot].replay()
+        return self._out[slot]
 
-    def __call__(self, lr, hr, U_hr_reduced=None):
-        self.load(lr, hr, U_hr_reduced)
-        return self.replay()
+    def __call__(self, lr, hr, U_hr_reduced=None, slot=0):
+        self.load(lr, hr, U_hr_reduced, slot=slot)
+        return self.replay(slot)
 
 
 def train_batched(model, optimizer, subjects_adj, subjects_labels, args, batch_size=64,

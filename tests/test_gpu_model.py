@@ -437,6 +437,18 @@ def test_graphed_train_step_equals_eager_steps(cuda_pkg):
         assert all(torch.equal(a, b) for a, b in zip(m1.parameters(), m2.parameters())), i
     with pytest.raises(ValueError):
         pkg.GraphedTrainStep(m1, torch.optim.Adam(m1.parameters(), lr=1e-3), B)
+    # two input-buffer sets (a loader fills one while the other replays): alternating them continues the same run
+    m5, o5 = build()
+    g5 = pkg.GraphedTrainStep(m5, o5, B, slots=2)
+    m6, o6 = build()
+    eager6 = pkg.GSRTrainStep(m6)
+    for i in range(4):
+        o6.zero_grad(set_to_none=True)
+        l6, _ = eager6(lr, hr, U_hr_reduced=U)
+        o6.step()
+        l5, _ = g5(lr, hr, U, slot=i % 2)
+        assert float(l5) == float(l6), i
+    assert all(torch.equal(a, b) for a, b in zip(m5.parameters(), m6.parameters()))
     # the HR-target eigendecomposition inside the graph, as the reference computes it every step
     m3, o3 = build()
     g3 = pkg.GraphedTrainStep(m3, o3, B, hr_basis_in_graph=True)
