@@ -335,6 +335,7 @@ tql_scalar_kernel(const Work wk, int n, int batch, int max_iter) {
                     hdr[nit] = (uint32_t)(lo >> 4) | ((uint32_t)(hi >> 4) << 8);
                     o += hi - m;
                     float p = d[m], c = 1.0f, s = 0.0f;
+                    float s_prev = 0.0f, c_prev = 1.0f, c_prev2 = 1.0f;    // s of the previous, c of the previous two rotations
                     const float el1 = e[l + 1];
                     float ei = e[m - 1], di = d[m - 1];
 #pragma unroll 4
@@ -342,28 +343,31 @@ tql_scalar_kernel(const Work wk, int n, int batch, int max_iter) {
                         const float ein = e[q - 1], din = d[q - 1];             // next rotation's operands (index -1 is padding)
                         const float gg = c * ei, hh = c * p;
                         const float x = fmaf(p, p, ei * ei);
-                        // (c, s) = (p, e_i) / r with one MUFU: c0, s0 share the relative error of
-                        // rsqrt, so 1 - c0^2 - s0^2 = delta measures it and one first-order step
-                        // removes it (unit norm to ~4e-8, unbiased; a biased norm would drift the
-                        // eigenvalues and the orthogonality of Z over ~300 rotations per column)
+                        // (c, s) = (p, e_i) / r with one MUFU: rsqrt's relative error delta shows as
+                        // 1 - x rinv^2 = 2 delta, and one first-order step removes it (unit norm to ~1e-7,
+                        // unbiased; a biased norm would drift the eigenvalues and the orthogonality of Z over
+                        // ~300 rotations per column).  The running p of the next rotation is linear in (c, s):
+                        // the step is applied to the product, so p does not wait for the corrected c, s --
+                        // the loop-carried chain is x, rsqrt, rinv^2, hd, one FFMA.
                         float rinv;
                         asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(x));
+                        const float hd = fmaf(-0.5f * x, rinv * rinv, 0.5f);
                         const float c0 = p * rinv, s0 = ei * rinv, xr = x * rinv;
-                        const float hd = 0.5f * fmaf(-c0, c0, fmaf(-s0, s0, 1.0f));
-                        float cn = fmaf(c0, hd, c0), sn = fmaf(s0, hd, s0), r = fmaf(xr, hd, xr);
-                        if (x < 1.17549435e-38f) { r = 0.f; cn = 1.0f; sn = 0.0f; }       // p = e_i = 0 (to fp32 range): identity
+                        const float t = fmaf(c0, di, -s0 * gg);
+                        float cn = fmaf(c0, hd, c0), sn = fmaf(s0, hd, s0), r = fmaf(xr, hd, xr), pn = fmaf(t, hd, t);
+                        if (x < 1.17549435e-38f) { r = 0.f; cn = 1.0f; sn = 0.0f; pn = di; }  // p = e_i = 0 (to fp32 range): identity
                         e[q + 1] = s * r;
+                        s_prev = s; c_prev2 = c_prev; c_prev = c;
                         s = sn; c = cn;
-                        p = fmaf(c, di, -s * gg);
+                        p = pn;
                         d[q + 1] = hh + s * fmaf(c, gg, s * di);
                         *o++ = make_float2(c, s);
                         ei = ein; di = din;
                     }
-                    // tql2's closing step needs s of the previous and c of the one-before-previous rotation:
-                    // read back from the stream just written (same thread) instead of carrying them through the loop
-                    const int cnt = m - l;
-                    const float s2 = cnt >= 2 ? o[-2].y : 0.0f;
-                    const float c3 = cnt >= 3 ? o[-3].x : 1.0f;
+                    // tql2's closing step needs s of the previous and c of the one-before-previous rotation
+                    // (carried in registers: reading them back from the stream just written costs a global
+                    // round trip per iteration)
+                    const float s2 = s_prev, c3 = c_prev2;
                     p = -s * s2 * c3 * el1 * e[l] / dl1;
                     e[l] = s * p;
                     d[l] = c * p;
