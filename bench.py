@@ -280,7 +280,7 @@ def run_ours(args):
     launches = graphed.launches_per_step * args.steps if use_graph else pkg.launch_count() - launches0
 
     # ---- per-kernel durations for the rooflines: the same K steps launched eagerly with CUDA events around every
-    #      library call (events cannot be placed inside a graph replay); shares are relative to this pass
+    #      library call (events cannot be placed inside a graph replay); shares are relative to the timed step
     K.GEMM_TIMER, K.EIGH_TIMER, K.EW_TIMER = K.KernelTimer(), K.KernelTimer(), K.KernelTimer()
     e0i, e1i = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0i.record()
@@ -447,7 +447,7 @@ def run_ours(args):
                         "and 3xTF32 needs 3 MMAs per product, so the fp32-accurate ceiling of this kernel is peak/6"
                         if backend == "tc" else "FP32 FFMA probe kernel measured in this run"),
         "frac_of_3xtf32_ceiling": (gemm_tflops / (bf16_peak / 6.0)) if (gemm_tflops and backend == "tc") else None,
-        "share_of_step": gemm_ms / instrumented_ms if instrumented_ms else None, "launches": gemm_launches,
+        "share_of_step": gemm_ms / elapsed_ms if elapsed_ms else None, "launches": gemm_launches,
         "algorithmic_flop_per_subject": GEMM_FLOP_PER_SUBJECT_FWD_BWD,
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE per-subject launch (rows 0..255 of 1024 TN products, CTA pairs)
         # inside the step, from the committed ncu --set full capture; the algorithmic bytes of that launch are
@@ -483,7 +483,7 @@ def run_ours(args):
             "bound": "fp32", "achieved": tflops, "unit": "TFLOP/s (executed fp32 flops: 4 n^3 + 6 n per plane rotation)",
             "peak": ffma_best, "frac": tflops / ffma_best if ffma_best else None,
             "peak_source": "FP32 FFMA probe kernel measured in this run",
-            "share_of_step": eigh_ms / instrumented_ms, "launches": eigh_launches,
+            "share_of_step": eigh_ms / elapsed_ms, "launches": eigh_launches,
             "us_per_graph": eigh_ms * 1e3 / eigh_graphs if eigh_graphs else None,
             "ql_iterations_mean": float(eigh_info.double().mean()), "rotations_mean": rot_mean,
             "conventional_9n3_tflops": 9.0 * n ** 3 * eigh_graphs / (eigh_ms * 1e-3) / 1e12, "traffic": None,
@@ -505,7 +505,7 @@ def run_ours(args):
             "bound": "smem", "achieved": gbs, "unit": "GB/s (shared-memory bytes the Jacobi rounds must move)",
             "peak": smem_peak, "frac": gbs / smem_peak,
             "peak_source": f"148 SMs x 128 B/clk x {sm_mhz:.0f} MHz (clock sampled in this run); ncu: lsu data-pipe 66 % busy",
-            "share_of_step": eigh_ms / instrumented_ms, "launches": eigh_launches,
+            "share_of_step": eigh_ms / elapsed_ms, "launches": eigh_launches,
             "us_per_graph": eigh_ms * 1e3 / eigh_graphs if eigh_graphs else None,
             "sweeps_mean": sw / eigh_info.numel(), "polish_sweeps_mean": ps / eigh_info.numel(), "traffic": None,
         }
@@ -515,7 +515,7 @@ def run_ours(args):
         ew_roof = {"kernel": "normalize_{fwd,bwd}_kernel + sym_diag_abs_{fwd,bwd}_kernel (memory-bound n x n kernels)",
                    "bound": "hbm", "achieved": gbs, "unit": "GB/s", "peak": peaks.get("hbm_gbs"),
                    "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
-                   "peak_source": "MEASURED_PEAKS.json hbm_gbs", "share_of_step": ew_ms / instrumented_ms,
+                   "peak_source": "MEASURED_PEAKS.json hbm_gbs", "share_of_step": ew_ms / elapsed_ms,
                    "launches": ew_launches, "traffic": None}
     by_kernel = [r for r in (eigh_roof, gemm_roof, ew_roof) if r]
     roofline = max(by_kernel, key=lambda r: r["share_of_step"] or 0.0)          # the dominant kernel of the step
@@ -543,9 +543,10 @@ def run_ours(args):
                    "optimizer": "torch.optim.Adam(fused=True, capturable=True), in the timed region",
                    "cuda_graph": ("the timed region replays one captured graph per step (forward, backward, gradient all-reduce, Adam; "
                                   "GraphedTrainStep); --no-graph launches every kernel from Python" if use_graph else "off (--no-graph)"),
-                   "kernel_timing": (f"roofline durations and share_of_step come from an instrumented eager pass of the same {args.steps} "
-                                     f"steps right after the timed region (CUDA events around every library call, "
-                                     f"{instrumented_ms / args.steps:.3f} ms per step with the events)")},
+                   "kernel_timing": (f"roofline kernel durations come from an instrumented eager pass of the same {args.steps} steps right "
+                                     f"after the timed region (CUDA events around every library call; that pass is host bound, "
+                                     f"{instrumented_ms / args.steps:.3f} ms per step); share_of_step = those device-side "
+                                     f"durations / the timed (graph-replayed) step")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "subjects/s",
                 "h2d_bytes_per_step": world * B * (LR_DIM * LR_DIM + HR_DIM * HR_DIM) * 4,
