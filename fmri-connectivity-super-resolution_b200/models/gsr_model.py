@@ -56,7 +56,7 @@ class GSRNet(nn.Module):
         else:
             self.net_outs, self.start_gcn_outs = self.net(A, I)                       # :27
         self.outputs, self.Z = self.layer(A, self.net_outs, U=U)                      # :28
-        self.hidden1 = self.gc1(self.Z, self.outputs)                                 # :29
-        self.hidden2 = self.gc2(self.hidden1, self.outputs)                           # :30
+        # :29-30  hidden1 = gc1(Z, outputs); hidden2 = gc2(hidden1, outputs) -- one autograd node for the two layers
+        self.hidden1, self.hidden2 = F_.GraphConvPairFn.apply(self.Z, self.outputs, self.gc1.weight, self.gc2.weight)
         z = F_.sym_diag_abs(self.hidden2)                                             # :32-37
         return z, self.net_outs, self.start_gcn_outs, self.outputs
