@@ -60,6 +60,7 @@ PROTOTYPES = {
     "gsr_l1_partials": (i32, [i64]),
     "gsr_l1_loss_fwd": (i32, [c_ptr, c_ptr, i64, c_ptr, c_ptr, i32, i64, c_ptr]),
     "gsr_l1_loss_bwd": (i32, [c_ptr, c_ptr, i64, c_ptr, c_ptr, i32, i64, c_ptr]),
+    "gsr_l1_loss_bwd_shared_y": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, i32, i64, c_ptr]),
     "gsr_vectorize_len": (i64, [i32, i32]),
     "gsr_vectorize": (i32, [c_ptr, c_ptr, i32, i32, i32, i32, c_ptr]),
     "gsr_anti_vectorize": (i32, [c_ptr, c_ptr, i32, i32, i64, i32, c_ptr]),

@@ -63,6 +63,30 @@ l1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, long lon
     for (long long e = lo + threadIdx.x; e < hi; e += kRedThreads) gb[e] = sgnf(xb[e] - yb[e]) * scale;
 }
 
+// y shared by the subjects (|W - U_hr|, utils/gsr_train.py:41): grad_y[i] = - sum_b sgn(x[b,i] - y[i]) grad_loss[b] / count
+// in one pass over x -- threads (tx, ty) = (element, batch phase), fixed summation order -- instead of writing the
+// [batch, count] gradient of x and summing it over the batch.
+constexpr int kSharedTX = 32, kSharedTY = 32;
+__global__ void __launch_bounds__(kSharedTX * kSharedTY)
+l1_bwd_shared_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ grad_loss,
+                     float* __restrict__ gy, int batch, long long count) {
+    __shared__ float red[kSharedTY][kSharedTX + 1];
+    const long long i = (long long)blockIdx.x * kSharedTX + threadIdx.x;
+    const bool live = i < count;
+    const float yi = live ? __ldg(y + i) : 0.f;
+    float acc = 0.f;
+    for (int b = threadIdx.y; b < batch; b += kSharedTY)
+        if (live) acc += sgnf(__ldg(x + (size_t)b * count + i) - yi) * __ldg(grad_loss + b);
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && live) {
+        float total = 0.f;
+#pragma unroll
+        for (int j = 0; j < kSharedTY; ++j) total += red[j][threadIdx.x];
+        gy[i] = -total / (float)count;
+    }
+}
+
 // ---------------------------------------------------------------- evaluation sweep
 constexpr int kEvalBlocks = 148 * 8;
 constexpr int kEvalSums = 8;
@@ -183,6 +207,15 @@ extern "C" int gsr_l1_loss_bwd(const float* x, const float* y, long long y_strid
     const int chunks = gsr_l1_partials(count);
     l1_bwd_kernel<<<dim3(chunks, batch), kRedThreads, 0, (cudaStream_t)stream>>>(x, y, y_stride, grad_loss, grad_x, count);
     return launched("l1_bwd");
+}
+
+extern "C" int gsr_l1_loss_bwd_shared_y(const float* x, const float* y, const float* grad_loss, float* grad_y,
+                                       int batch, long long count, void* stream) {
+    if (!x || !y || !grad_loss || !grad_y || batch < 0 || count <= 0) return fail(GSR_E_ARG, "l1_loss_bwd_shared_y: bad argument");
+    const long long blocks = (count + kSharedTX - 1) / kSharedTX;
+    if (blocks > 0x7fffffffLL) return fail(GSR_E_UNSUPPORTED, "l1_loss_bwd_shared_y: count too large");
+    l1_bwd_shared_kernel<<<(unsigned)blocks, dim3(kSharedTX, kSharedTY), 0, (cudaStream_t)stream>>>(x, y, grad_loss, grad_y, batch, count);
+    return launched("l1_bwd_shared_y");
 }
 
 extern "C" size_t gsr_eval_workspace(void) { return (size_t)kEvalSums * kEvalBlocks + kEvalSums; }

@@ -310,6 +310,9 @@ class L1LossFn(Function):
     @once_differentiable
     def backward(ctx, g):
         x, y = ctx.saved_tensors
+        if ctx.shared and ctx.batch > 1 and not ctx.needs_input_grad[0]:
+            # |W - U_hr| of the batched step: only the shared weights need a gradient -- one pass over x
+            return None, (K.l1_loss_bwd_shared_y(x, y, _c(g), ctx.batch) if ctx.needs_input_grad[1] else None), None
         gx = K.l1_loss_bwd(x, y, _c(g), ctx.batch, ctx.shared)
         gy = None
         if ctx.needs_input_grad[1]:

@@ -421,6 +421,16 @@ def l1_loss_bwd(x: torch.Tensor, y: torch.Tensor, grad_loss: torch.Tensor, batch
     return gx
 
 
+def l1_loss_bwd_shared_y(x: torch.Tensor, y: torch.Tensor, grad_loss: torch.Tensor, batch: int) -> torch.Tensor:
+    """Gradient of the shared y of a per-subject L1 loss (x [batch, ...], y [...]), without the gradient of x."""
+    x, y, grad_loss = _f32(x, "l1: x"), _f32(y, "l1: y"), _f32(grad_loss, "l1: grad")
+    count = x.numel() // batch
+    gy = torch.empty_like(y)
+    check(lib().gsr_l1_loss_bwd_shared_y(x.data_ptr(), y.data_ptr(), grad_loss.data_ptr(), gy.data_ptr(), batch, count,
+                                         _stream()), "gsr_l1_loss_bwd_shared_y")
+    return gy
+
+
 # --------------------------------------------------------------------- vectoriser
 def vectorize_len(n: int, include_diagonal: bool) -> int:
     return int(lib().gsr_vectorize_len(int(n), int(include_diagonal)))

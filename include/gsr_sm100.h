@@ -216,6 +216,10 @@ GSR_API int gsr_l1_loss_fwd(const float* x, const float* y, long long y_stride, 
 /* grad_x[b,i] = sgn(x - y) * grad_loss[b] / count   (sgn(0) = 0)                 */
 GSR_API int gsr_l1_loss_bwd(const float* x, const float* y, long long y_stride, const float* grad_loss,
                     float* grad_x, int batch, long long count, void* stream);
+/* y shared by the batch (the |W - U_hr| term, utils/gsr_train.py:41, batched): the gradient of y alone,
+ * grad_y[i] = - sum_b sgn(x[b,i] - y[i]) * grad_loss[b] / count, in one pass over x (fixed order). */
+GSR_API int gsr_l1_loss_bwd_shared_y(const float* x, const float* y, const float* grad_loss, float* grad_y,
+                             int batch, long long count, void* stream);
 
 /* ------------------------------------------------------------------ a16 / a17
  * utils/matrix_vectorizer.py:24-58  vectorize: strict upper triangle walked

@@ -603,6 +603,17 @@ def test_l1_loss(cuda_pkg):
     wc = w.cuda().requires_grad_(True)
     F_.l1_loss_per_subject(u.cuda(), wc).mean().backward()
     assert torch.allclose(wc.grad.cpu(), wr.grad, rtol=1e-5, atol=1e-9)
+    # the one-pass kernel for the shared side (x without gradient) equals the general path (x with gradient), with
+    # non-uniform upstream gradients and more subjects than batch phases; ties (x == y) contribute 0
+    u = torch.randn(70, 33, 7, generator=g); w = torch.randn(33, 7, generator=g); u[3, 2] = w[2]
+    wt = torch.rand(70, generator=g)
+    w1 = w.cuda().requires_grad_(True)
+    (F_.l1_loss_per_subject(u.cuda(), w1) * wt.cuda()).sum().backward()
+    w2, u2 = w.cuda().requires_grad_(True), u.cuda().requires_grad_(True)
+    (F_.l1_loss_per_subject(u2, w2) * wt.cuda()).sum().backward()
+    want = -(torch.sign(u.double() - w.double()) * wt.double()[:, None, None]).sum(0) / (33 * 7)
+    assert torch.allclose(w1.grad.cpu().double(), want, rtol=1e-5, atol=1e-8)
+    assert torch.allclose(w1.grad, w2.grad, rtol=1e-5, atol=1e-8)
 
 
 @pytest.mark.parametrize("tag", ["small", "hr"])
