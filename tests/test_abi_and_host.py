@@ -61,6 +61,19 @@ def test_ctypes_table_matches_header(pkg):
     assert sorted(table) == header_symbols()
 
 
+def test_ctypes_argument_counts_match_header(pkg):
+    """Every ctypes prototype has as many arguments as the C declaration (no silent ABI drift)."""
+    from importlib import import_module
+    table = import_module(PKG_NAME + "._lib").PROTOTYPES
+    text = re.sub(r"/\*.*?\*/", " ", open(HEADER).read(), flags=re.S)
+    decls = dict(re.findall(r"GSR_API\s+[\w\s\*]+?\b(gsr_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S))
+    assert sorted(decls) == header_symbols()
+    for name, params in decls.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(table[name][1]), (name, n, len(table[name][1]))
+
+
 def test_bad_arguments_are_rejected_without_a_gpu(pkg):
     lib = pkg.lib()
     assert lib.gsr_normalize_adj_fwd(None, None, None, None, 1, 4, 0, None) == -1
@@ -69,6 +82,16 @@ def test_bad_arguments_are_rejected_without_a_gpu(pkg):
     assert lib.gsr_eigh_tridiag_f32(None, None, None, None, None, 0, 1, 4, 1, None) == -1
     assert b"eigh_tridiag" in lib.gsr_last_error()
     assert lib.gsr_set_tuning(b"no_such_knob", 1) == -1
+    for knob in (b"tcgemm_pairs", b"tcgemm_ragged_rows", b"gemm_variant"):
+        assert lib.gsr_set_tuning(knob, 1 if knob != b"gemm_variant" else 0) == 0
+    # round-1 additions: MLP passes, shared-target L1 backward, flat bucket, ragged-row / pair GEMM entry
+    assert lib.gsr_bn_stats_f32(None, 4, 4, None, None, None, None, 0.1, None) == -1
+    assert lib.gsr_bn_act_fwd_f32(None, None, None, None, None, 1e-5, 0.1, 0, 1, None, 4, 4, None) == -1
+    assert lib.gsr_bn_act_bwd_f32(None, None, None, None, None, None, 1e-5, 0.1, 0, 1, 1, None, None, None, 4, 4, None) == -1
+    assert lib.gsr_l1_loss_bwd_shared_y(None, None, None, None, 4, 16, None) == -1
+    assert lib.gsr_flat_pack(None, None, 3, None, 10, 1.0, None) == -1
+    assert lib.gsr_tcgemm_f32(None, None, None, 268, 268, 268, 268, 268, 268, 0, 0, 0, 0, 0, 1, 1.0, 0, None, 0, 0, None) == -1
+    assert lib.gsr_launch_count() == 0
 
 
 def test_product_package_never_imports_the_oracle():
