@@ -18,10 +18,11 @@ from . import kernels, functional  # noqa: F401
 from . import models, utils  # noqa: F401
 from .models import GSRNet, GSRLayer, GraphConvolution, GraphUnet, GraphPool, GraphUnpool, GCN, SuperResMLP  # noqa: F401
 from .utils import MatrixVectorizer, normalize_adj_torch, pad_HR_adj, unpad  # noqa: F401
+from .utils.optim import FlatAdam  # noqa: F401
 from .utils.gsr_train import GSRTrainStep, GraphedTrainStep, train, test, train_batched, hr_target_basis  # noqa: F401
 from .utils.evaluation import evaluation_reductions  # noqa: F401
 from .subject_parallel import SubjectParallel, shard_bounds, fold_assignment, fold_groups  # noqa: F401
 
 __all__ = ["lib", "GSRNet", "GSRLayer", "GraphConvolution", "GraphUnet", "GraphPool", "GraphUnpool", "GCN", "SuperResMLP",
            "MatrixVectorizer", "normalize_adj_torch", "pad_HR_adj", "unpad", "train", "test", "train_batched",
-           "GSRTrainStep", "GraphedTrainStep", "evaluation_reductions", "SubjectParallel"]
+           "GSRTrainStep", "GraphedTrainStep", "FlatAdam", "evaluation_reductions", "SubjectParallel"]

@@ -58,6 +58,64 @@ extern "C" int gsr_flat_unpack(float* const* ptrs, const long long* offsets, int
     return flat_copy<false>(ptrs, offsets, n_tensors, const_cast<float*>(flat), scale, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------- N3: Adam over all parameter tensors in one launch
+// torch.optim.Adam (training_gsr.ipynb:72) with the step counter on the device, so that the update can be captured
+// in the CUDA graph of the training step.  Pointer tables travel in the kernel parameters like the flat bucket's.
+namespace gsr {
+constexpr int ADAM_CHUNK = 40;
+struct AdamTable { float* p[ADAM_CHUNK]; const float* g[ADAM_CHUNK]; float* m[ADAM_CHUNK]; float* v[ADAM_CHUNK]; long long n[ADAM_CHUNK]; };
+
+__global__ void adam_tick_kernel(float* step) { step[0] += 1.0f; }
+
+__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamTable t, const float* __restrict__ step, float lr,
+                                                   float beta1, float beta2, float eps, float weight_decay) {
+    const int k = blockIdx.y;
+    const float s = step[0];
+    const float bc1 = 1.0f - powf(beta1, s), bc2_sqrt = sqrtf(1.0f - powf(beta2, s));
+    const float step_size = lr / bc1;
+    float* __restrict__ p = t.p[k];
+    const float* __restrict__ g = t.g[k];
+    float* __restrict__ m = t.m[k];
+    float* __restrict__ v = t.v[k];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < t.n[k]; e += (long long)gridDim.x * blockDim.x) {
+        float grad = g[e];
+        const float param = p[e];
+        if (weight_decay != 0.f) grad = fmaf(weight_decay, param, grad);
+        const float mi = m[e] + (1.0f - beta1) * (grad - m[e]);                 // lerp, as torch
+        const float vi = beta2 * v[e] + (1.0f - beta2) * grad * grad;
+        m[e] = mi;
+        v[e] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[e] = param - step_size * (mi / denom);
+    }
+}
+}  // namespace gsr
+
+extern "C" int gsr_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                             const long long* sizes, int n_tensors, float* step, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !sizes || !step || n_tensors <= 0)
+        return fail(GSR_E_ARG, "adam_step: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    adam_tick_kernel<<<1, 1, 0, st>>>(step);
+    int rc = launched("adam_tick");
+    if (rc) return rc;
+    for (int first = 0; first < n_tensors; first += ADAM_CHUNK) {
+        const int n = std::min(ADAM_CHUNK, n_tensors - first);
+        AdamTable t;
+        for (int i = 0; i < ADAM_CHUNK; ++i) {
+            const bool live = i < n;
+            t.p[i] = live ? params[first + i] : nullptr; t.g[i] = live ? grads[first + i] : nullptr;
+            t.m[i] = live ? exp_avg[first + i] : nullptr; t.v[i] = live ? exp_avg_sq[first + i] : nullptr;
+            t.n[i] = live ? sizes[first + i] : 0;
+            if (live && (!t.p[i] || !t.g[i] || !t.m[i] || !t.v[i] || t.n[i] < 0)) return fail(GSR_E_ARG, "adam_step: null tensor");
+        }
+        adam_kernel<<<dim3(16, n), 256, 0, st>>>(t, step, lr, beta1, beta2, eps, weight_decay);
+        if ((rc = launched("adam"))) return rc;
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------- measurement aid
 // FP32 FFMA peak probe for the roofline denominator of the SIMT contraction kernels (the
 // driver-written MEASURED_PEAKS.json only has HBM and bf16 tensor numbers): every thread runs

@@ -292,6 +292,17 @@ GSR_API int gsr_bn_act_bwd_f32(const float* x, const float* mean, const float* v
                        unsigned long long seed, int relu, int batch_stats, float* dx, float* dgamma,
                        float* dbeta, int batch, int features, void* stream);
 
+/* ------------------------------------------------------------------ N3 (SURVEY 8 f)
+ * torch.optim.Adam(model.parameters(), lr) of training_gsr.ipynb:72 over all parameter tensors in
+ * one launch per 40 tensors: m = lerp(m, g, 1 - beta1); v = beta2 v + (1 - beta2) g^2;
+ * p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps); weight_decay adds wd * p to g (L2).
+ * params / grads / exp_avg / exp_avg_sq / sizes are HOST arrays of n_tensors entries (device pointers and
+ * element counts; read during the call).  step is a DEVICE fp32 scalar holding t - 1; it is incremented on
+ * the stream before the update, so the call needs no host synchronisation and can be captured in a graph. */
+GSR_API int gsr_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                  const long long* sizes, int n_tensors, float* step, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, void* stream);
+
 /* ------------------------------------------------------------------ measurement aid
  * Launches an FFMA-only kernel (8 independent chains per thread, 148*8 CTAs of 256 threads)
  * and returns the flops it executes; timed by the caller with CUDA events to obtain the

@@ -457,3 +457,53 @@ def test_graphed_train_step_equals_eager_steps(cuda_pkg):
     o4.zero_grad(set_to_none=True)
     l4, _ = pkg.GSRTrainStep(m4)(lr, hr)
     assert float(l3) == float(l4)
+
+
+@pytest.mark.gpu
+def test_flat_adam_equals_torch_adam(cuda_pkg):
+    """SURVEY 8 f row N3: gsr_adam_step (one launch for all tensors, device-side step counter) against
+    torch.optim.Adam on the same gradients, with and without weight decay, 45 tensors (two table chunks)."""
+    pkg = cuda_pkg
+    g = torch.Generator().manual_seed(8)
+    shapes = [(int(a), int(b)) for a, b in torch.randint(1, 40, (45, 2), generator=g)]
+    for wd in (0.0, 0.01):
+        init = [torch.randn(s, generator=g) for s in shapes]
+        p_ref = [torch.nn.Parameter(t.clone().cuda()) for t in init]
+        p_new = [torch.nn.Parameter(t.clone().cuda()) for t in init]
+        o_ref = torch.optim.Adam(p_ref, lr=1e-2, weight_decay=wd)
+        o_new = pkg.FlatAdam(p_new, lr=1e-2, weight_decay=wd)
+        for step in range(6):
+            grads = [torch.randn(s, generator=g).cuda() for s in shapes]
+            for a, b, gr in zip(p_ref, p_new, grads):
+                a.grad, b.grad = gr.clone(), gr.clone()
+            o_ref.step(); o_new.step()
+            worst = max(float((a - b).abs().max()) for a, b in zip(p_ref, p_new))
+            assert worst < 2e-6, (wd, step, worst)
+        assert float(o_new.param_groups[0]["step_tensor"]) == 6.0
+    with pytest.raises(RuntimeError):
+        q = torch.nn.Parameter(torch.zeros(3)); q.grad = torch.zeros(3)
+        pkg.FlatAdam([q]).step()
+
+
+@pytest.mark.gpu
+def test_graphed_step_with_flat_adam(cuda_pkg):
+    """The whole step on the library's kernels: GraphedTrainStep + FlatAdam follows eager steps with torch's Adam."""
+    pkg = cuda_pkg
+    import bench
+    B = 4
+    lr = bench.synth_batch(torch, 160, B, 21, torch.device("cuda"))
+    hr = bench.synth_batch(torch, 268, B, 22, torch.device("cuda"))
+    U = pkg.hr_target_basis(hr, 160)
+    torch.manual_seed(5); m1 = pkg.GSRNet([0.9, 0.7, 0.6, 0.5], bench.Args()).cuda()
+    torch.manual_seed(5); m2 = pkg.GSRNet([0.9, 0.7, 0.6, 0.5], bench.Args()).cuda()
+    o1 = torch.optim.Adam(m1.parameters(), lr=1e-4)
+    graphed = pkg.GraphedTrainStep(m2, pkg.FlatAdam(m2.parameters(), lr=1e-4), B)
+    eager = pkg.GSRTrainStep(m1)
+    for i in range(3):
+        o1.zero_grad(set_to_none=True)
+        l1, _ = eager(lr, hr, U_hr_reduced=U)
+        o1.step()
+        l2, _ = graphed(lr, hr, U)
+        assert abs(float(l1) - float(l2)) < 1e-5 * abs(float(l1)), i
+    worst = max(float((a - b).abs().max()) for a, b in zip(m1.parameters(), m2.parameters()))
+    assert worst < 5e-6
