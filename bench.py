@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gemm-variant", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="torch", choices=["torch", "flat"],
+                    help="torch: torch.optim.Adam(fused=True) (default); flat: the library's gsr_adam_step (pkg.FlatAdam)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=None, help="subjects in the CPU baseline sample")
     return ap.parse_args()
@@ -215,7 +217,10 @@ def run_ours(args):
     model = pkg.GSRNet([0.9, 0.7, 0.6, 0.5], Args()).to(dev)
     sp = pkg.SubjectParallel(model) if world > 1 else None
     use_graph = not args.no_graph
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=use_graph)
+    if args.optimizer == "flat":
+        opt = pkg.FlatAdam(model.parameters(), lr=1e-4)
+    else:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=use_graph)
     step = pkg.GSRTrainStep(model, lmbda=Args.lmbda, padding=Args.padding)
     lr = synth_batch(torch, LR_DIM, B, 1000 + rank, dev)
     hr = synth_batch(torch, HR_DIM, B, 5000 + rank, dev)
@@ -540,7 +545,8 @@ def run_ours(args):
                    "with_hr_target_eigh_in_step": hr_in_step,
                    "gemm_backend": K.GEMM_BACKEND,
                    "l2": "inputs of one step are 400 MB per GPU (> 126 MB L2); no flush needed",
-                   "optimizer": "torch.optim.Adam(fused=True, capturable=True), in the timed region",
+                   "optimizer": ("pkg.FlatAdam (gsr_adam_step), in the timed region" if args.optimizer == "flat"
+                                 else "torch.optim.Adam(fused=True, capturable=True), in the timed region"),
                    "cuda_graph": ("the timed region replays one captured graph per step (forward, backward, gradient all-reduce, Adam; "
                                   "GraphedTrainStep); --no-graph launches every kernel from Python" if use_graph else "off (--no-graph)"),
                    "kernel_timing": (f"roofline kernel durations come from an instrumented eager pass of the same {args.steps} steps right "
