@@ -7,8 +7,9 @@
 A "step" is one training step of the reference's loop (utils/gsr_train.py:23-46) over a batch
 of B synthetic subjects per GPU: adjacency normalisation, LR eigendecomposition, Graph U-Net,
 GSR layer, two graph convolutions, the three-term L1 loss, the full backward, the gradient
-all-reduce (N > 1) and the Adam update.  `value` = subjects of all ranks / max-over-ranks
-device time, inputs resident in HBM.  `e2e` = the same step through the public API with the
+all-reduce (N > 1) and the Adam update, captured once in a CUDA graph (GraphedTrainStep) and
+replayed; --no-graph launches every kernel from Python.  `value` = subjects of all ranks /
+max-over-ranks device time, inputs resident in HBM.  `e2e` = the same step through the public API with the
 LR / HR batches coming from pinned host memory and the loss read back, every step.
 Prints ONE JSON line on rank 0.
 """

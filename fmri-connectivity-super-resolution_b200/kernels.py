@@ -529,7 +529,7 @@ def bn_act_bwd(x, mean, var, gamma, beta, dy, eps: float, p_drop: float, seed: i
 
 # --------------------------------------------------------------------- flat gradient bucket
 class FlatBucket:
-    """Device-side table (pointers + offsets) of a list of fp32 tensors, for the one-launch
+    """Table (pointers + offsets, passed to the kernels by value) of a list of fp32 tensors, for the one-launch
     pack / unpack around the NCCL all-reduce of the subject-data-parallel step."""
 
     def __init__(self, tensors):
