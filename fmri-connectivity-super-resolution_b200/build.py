@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libgsr_sm100.so")
 STAMP = os.path.join(OUT_DIR, "libgsr_sm100.stamp")
-SOURCES = ["api.cu", "elementwise.cu", "eigh.cu", "eigh_tridiag.cu", "bgemm.cu", "tcgemm.cu", "reduce.cu", "vectorizer.cu", "graph_unet.cu", "mlp.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "eigh.cu", "eigh_tridiag.cu", "bgemm.cu", "tcgemm.cu", "tcgemm_tma.cu", "reduce.cu", "vectorizer.cu", "graph_unet.cu", "mlp.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

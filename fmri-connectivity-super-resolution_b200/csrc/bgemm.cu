@@ -36,7 +36,8 @@ int g_gemm_variant = 0;
 extern int g_eigh_oddeven;
 extern int g_eigh_max_polish;
 extern int g_eigh_ql_max_iter;
-namespace tc { extern int g_pairs, g_tail; }
+extern int g_eigh_redo;
+namespace tc { extern int g_pairs, g_tail, g_tma; }
 
 struct GemmParams {
     const float* A; const float* B; float* C;
@@ -303,8 +304,10 @@ extern "C" int gsr_set_tuning(const char* key, int value) {
     if (!strcmp(key, "eigh_oddeven")) { gsr::g_eigh_oddeven = value; return 0; }
     if (!strcmp(key, "eigh_max_polish")) { gsr::g_eigh_max_polish = value; return 0; }
     if (!strcmp(key, "eigh_ql_max_iter")) { gsr::g_eigh_ql_max_iter = value; return 0; }
+    if (!strcmp(key, "eigh_redo_failed")) { gsr::g_eigh_redo = value; return 0; }
     if (!strcmp(key, "tcgemm_pairs")) { gsr::tc::g_pairs = value; return 0; }
     if (!strcmp(key, "tcgemm_ragged_rows")) { gsr::tc::g_tail = value; return 0; }
+    if (!strcmp(key, "tcgemm_tma")) { gsr::tc::g_tma = value; return 0; }
     return fail(GSR_E_ARG, "set_tuning: unknown key");
 }
 

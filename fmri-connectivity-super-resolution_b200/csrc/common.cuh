@@ -36,6 +36,10 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 constexpr int kNumSMs = 148;   // B200
 
+// csrc/eigh.cu: Jacobi pass over the graphs whose info is -2 (the fallback behind csrc/eigh_tridiag.cu)
+int eigh_jacobi_redo_failed(const float* A, float* w, float* U, int32_t* info, float* scratch, long long stride,
+                            int batch, int n, int canonical_sign, cudaStream_t st);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -150,8 +150,12 @@ template <int KR, bool POLISH, bool GLOBAL, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* __restrict__ Uout,
                    int32_t* __restrict__ info, float* __restrict__ workspace,
-                   int n, int canonical, float tol, int max_sweeps, int use_oddeven, int max_polish) {
+                   int n, int canonical, float tol, int max_sweeps, int use_oddeven, int max_polish,
+                   int redo_failed, long long ws_stride) {
     static_assert(!(POLISH && GLOBAL), "the polish phase needs both buffers in shared memory");
+    // redo_failed: the fallback pass behind the tridiagonal-QL route -- only the graphs that route flagged with
+    // info == -2 do any work; every other CTA leaves at once (uniform over the block: one word, read by all).
+    if (redo_failed && reinterpret_cast<volatile int32_t*>(info)[blockIdx.x] != -2) return;
     constexpr int LD = 32 * KR + 4;
     constexpr int LG = kGroup;                                  // lanes per pair slot
     constexpr int VEC = 32 / LG;
@@ -160,7 +164,7 @@ eigh_jacobi_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, floa
     float* G;                                                   // [n][LD], column c at G + c*LD
     float* H;                                                   // [n][LD] (POLISH only)
     float* lam;                                                 // [n]
-    if (GLOBAL) { G = workspace + (size_t)blockIdx.x * n * LD; H = nullptr; lam = smem; }
+    if (GLOBAL) { G = workspace + (size_t)blockIdx.x * (size_t)ws_stride; H = nullptr; lam = smem; }
     else        { G = smem; H = G + (size_t)n * LD; lam = POLISH ? H + (size_t)n * LD : H; }
     float* sgn = lam + n;                                       // [n]
     float* nrm = sgn + n;                                       // [n]  cached squared column norms
@@ -506,28 +510,50 @@ static int eigh_threads(int n) {
 
 template <int KR, bool POLISH, bool GLOBAL, int MAXT>
 static int launch_one(const float* A, float* w, float* U, int32_t* info, float* ws, int batch, int n,
-                      int canonical, float tol, int max_sweeps, size_t smem, cudaStream_t st) {
+                      int canonical, float tol, int max_sweeps, size_t smem, cudaStream_t st, int redo, long long ws_stride) {
     auto k = eigh_jacobi_kernel<KR, POLISH, GLOBAL, MAXT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "eigh_jacobi: cudaFuncSetAttribute failed");
     const int threads = eigh_threads(n);
     if (threads > MAXT) return fail(GSR_E_UNSUPPORTED, "eigh_jacobi: internal thread-count mismatch");
-    k<<<batch, threads, smem, st>>>(A, w, U, info, ws, n, canonical, tol, max_sweeps, g_eigh_oddeven, g_eigh_max_polish);
-    return launched("eigh_jacobi");
+    k<<<batch, threads, smem, st>>>(A, w, U, info, ws, n, canonical, tol, max_sweeps, g_eigh_oddeven, g_eigh_max_polish,
+                                    redo, ws_stride);
+    return launched(redo ? "eigh_jacobi_redo" : "eigh_jacobi");
 }
 
 template <int KR>
 static int launch_eigh(const float* A, float* w, float* U, int32_t* info, float* ws, int batch, int n,
-                       int canonical, float tol, int max_sweeps, cudaStream_t st) {
+                       int canonical, float tol, int max_sweeps, cudaStream_t st, int redo = 0, long long ws_stride = 0) {
     constexpr int LD = 32 * KR + 4;
+    if (ws_stride == 0) ws_stride = (long long)n * LD;
     constexpr int MAXT = (128 * KR < 1024) ? 128 * KR : (KR >= 9 ? 576 : 1024);
     const size_t small = 4 * (size_t)n * sizeof(float);
     const size_t one = (size_t)n * LD * sizeof(float) + small, two = 2 * (size_t)n * LD * sizeof(float) + small;
     const size_t cap = 227 * 1024;
-    if (two <= cap) return launch_one<KR, true, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, two, st);
-    if (one <= cap) return launch_one<KR, false, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, one, st);
+    if (two <= cap) return launch_one<KR, true, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, two, st, redo, ws_stride);
+    if (one <= cap) return launch_one<KR, false, false, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, one, st, redo, ws_stride);
     if (!ws) return fail(GSR_E_ARG, "eigh_jacobi: this n needs a global workspace (gsr_eigh_workspace)");
-    return launch_one<KR, false, true, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, small, st);
+    if (ws_stride < (long long)n * LD) return fail(GSR_E_ARG, "eigh_jacobi: workspace stride below n * (32 ceil(n / 32) + 4) floats");
+    return launch_one<KR, false, true, MAXT>(A, w, U, info, ws, batch, n, canonical, tol, max_sweeps, small, st, redo, ws_stride);
+}
+
+static int eigh_dispatch(const float* A, float* w, float* U, int32_t* info, float* workspace, int batch, int n,
+                         int canonical_sign, float tol, int max_sweeps, cudaStream_t st, int redo, long long ws_stride) {
+#define GSR_EIGH_CASE(KR) case KR: return launch_eigh<KR>(A, w, U, info, workspace, batch, n, canonical_sign, tol, max_sweeps, st, redo, ws_stride)
+    switch ((n + 31) / 32) {
+        GSR_EIGH_CASE(1); GSR_EIGH_CASE(2); GSR_EIGH_CASE(3); GSR_EIGH_CASE(4); GSR_EIGH_CASE(5);
+        GSR_EIGH_CASE(6); GSR_EIGH_CASE(7); GSR_EIGH_CASE(8); GSR_EIGH_CASE(9);
+        default: return fail(GSR_E_UNSUPPORTED, "eigh_jacobi: unsupported n");
+    }
+#undef GSR_EIGH_CASE
+}
+
+// Device-side fallback of the tridiagonal-QL route (csrc/eigh_tridiag.cu): the graphs it flagged with info == -2 are
+// redone by the Jacobi kernel in the same stream, no host round trip.  `scratch` (floats, `stride` per graph) is only
+// touched for n whose matrix does not fit shared memory.
+int eigh_jacobi_redo_failed(const float* A, float* w, float* U, int32_t* info, float* scratch, long long stride,
+                            int batch, int n, int canonical_sign, cudaStream_t st) {
+    return eigh_dispatch(A, w, U, info, scratch, batch, n, canonical_sign, 1e-6f, 30, st, 1, stride);
 }
 
 }  // namespace gsr
@@ -550,11 +576,5 @@ extern "C" int gsr_eigh_jacobi_f32(const float* A, float* w, float* U, int32_t* 
     if (max_sweeps <= 0) max_sweeps = 30;
     cudaStream_t st = (cudaStream_t)stream;
     if (n > GSR_EIGH_MAX_N) return fail(GSR_E_UNSUPPORTED, "eigh_jacobi: n > 288 is not supported");
-#define GSR_EIGH_CASE(KR) case KR: return launch_eigh<KR>(A, w, U, info, workspace, batch, n, canonical_sign, tol, max_sweeps, st)
-    switch ((n + 31) / 32) {
-        GSR_EIGH_CASE(1); GSR_EIGH_CASE(2); GSR_EIGH_CASE(3); GSR_EIGH_CASE(4); GSR_EIGH_CASE(5);
-        GSR_EIGH_CASE(6); GSR_EIGH_CASE(7); GSR_EIGH_CASE(8); GSR_EIGH_CASE(9);
-        default: return fail(GSR_E_UNSUPPORTED, "eigh_jacobi: unsupported n");
-    }
-#undef GSR_EIGH_CASE
+    return eigh_dispatch(A, w, U, info, workspace, batch, n, canonical_sign, tol, max_sweeps, st, 0, 0);
 }

@@ -36,6 +36,8 @@
 
 namespace gsr {
 int g_eigh_ql_max_iter = 30;    // gsr_set_tuning("eigh_ql_max_iter", k): QL iterations allowed per eigenvalue (EISPACK: 30)
+int g_eigh_redo = 1;            // gsr_set_tuning("eigh_redo_failed", 0|1): Jacobi pass over the graphs the QL iteration gave up on
+                                // (info == -2), in the same stream (default); 0 leaves them flagged with NaN results
 namespace tq {
 
 constexpr int MAXN = 160;
@@ -994,7 +996,10 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
         tq::tql_apply_smem_kernel<<<2 * batch, thr3, smem3b, st>>>(wk, n, rows_per_cta);
         if ((rcb = launched("eigh_tql_apply_smem"))) return rcb;
         tq::tql_finish_global_kernel<<<batch, 256, 0, st>>>(wk, w, U, info, n, canonical_sign);
-        return launched("eigh_tql_finish_global");
+        if ((rcb = launched("eigh_tql_finish_global"))) return rcb;
+        // QL failures (info == -2) are redone on the device by the Jacobi kernel; its scratch for a matrix that does
+        // not fit shared memory is the graph's own (now dead) rotation stream: 2 cap >= 4 n^2 floats
+        return g_eigh_redo ? eigh_jacobi_redo_failed(A, w, U, info, reinterpret_cast<float*>(wk.stream), 2LL * wk.cap, batch, n, canonical_sign, st) : 0;
     }
 
     tq::tridiag_kernel<<<batch, threads, 0, st>>>(A, w, U, info, wk, n);
@@ -1015,5 +1020,6 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
     cudaError_t e = cudaFuncSetAttribute(tq::tql_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
     if (e != cudaSuccess) return fail((int)e, "eigh_tridiag: cudaFuncSetAttribute failed");
     tq::tql_finish_kernel<<<batch, 256, smem4, st>>>(wk, w, U, info, n, canonical_sign);
-    return launched("eigh_tql_finish");
+    if ((rc = launched("eigh_tql_finish"))) return rc;
+    return g_eigh_redo ? eigh_jacobi_redo_failed(A, w, U, info, reinterpret_cast<float*>(wk.stream), 2LL * wk.cap, batch, n, canonical_sign, st) : 0;
 }

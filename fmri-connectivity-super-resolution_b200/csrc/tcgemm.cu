@@ -22,39 +22,10 @@
 //     all warps then apply alpha / bias / addend and write full coalesced rows.
 // Weight gradients (sum over subjects) keep accumulating in TMEM across the subjects dealt to
 // the CTA; partial tiles are then reduced in a fixed order (same scheme as the SIMT kernel).
-#include "common.cuh"
+#include "tcgemm.cuh"
 
 namespace gsr {
 namespace tc {
-
-constexpr int BM = 128;
-constexpr int BN = 288;                 // 160 + up to 128 (multiple of the 32-element MN atom)
-constexpr int BN0 = 160;
-constexpr int BK = 32;
-constexpr int STAGES = 2;
-constexpr int PRODUCER_WARPS = 14;    // two groups of 7 (+ 1 MMA warp = 480 threads -> 128 registers each)
-constexpr int GROUP_WARPS = PRODUCER_WARPS / 2;
-constexpr int EPILOGUE_WARPS = 12;    // 3 column groups x 4 TMEM lane quarters
-constexpr int THREADS = 32 * (PRODUCER_WARPS + 1);
-constexpr int A_TILE = BM * BK * 4;     // bytes of one tf32 A tile (hi or lo)
-constexpr int B_TILE = BN * BK * 4;
-constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;            // 102400
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 64;           // + barriers, tmem pointer
-constexpr int TMEM_COLS = 512;
-constexpr int A_PATCHES = BM * BK / 128;                        // 32 patches of 128 floats (one per warp instruction)
-constexpr int B_PATCHES = BN * BK / 128;                        // 72
-constexpr int PATCHES = A_PATCHES + B_PATCHES;                  // 104
-constexpr int PATCH_ITERS = (PATCHES + GROUP_WARPS - 1) / GROUP_WARPS;   // 15: one group stages a whole k-block
-
-struct Params {
-    const float* A; const float* B; float* C;
-    int M, N, K, lda, ldb, ldc;
-    long long sA, sB, sC;
-    int batch, splits;
-    float alpha;
-    int epilogue;
-    const float* extra; int ld_extra; long long s_extra;
-};
 
 int g_pairs = 1;        // gsr_set_tuning("tcgemm_pairs"): CTA-pair kernel (cta_group::2) for gsr_tcgemm_f32 (default), 0 = one CTA per tile
 int g_tail = 1;         // gsr_set_tuning("tcgemm_ragged_rows"): FP32 kernels for the <= 16 ragged rows after the CTA pairs (default), 0 = one-CTA tensor kernel
@@ -69,96 +40,22 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #define TC_STAMP(role, kb, ev) do { } while (0)
 #endif
 
-// ---------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must fault (trap) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
-        if (spin > (1u << 26)) __trap();
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] . B[smem], kind::tf32, issued by ONE thread.  The 64-bit matrix
-// descriptors are passed as (low word, high word): only the low word (start address) changes
-// from one MMA to the next, so the issuing thread spends one integer add per operand.
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                          uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-                 "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-                 "setp.ne.b32 p, %6, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
-                 :: "r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Shared-memory matrix descriptor (sm_100 version bit set), as two 32-bit words.
-//   low  word: start address >> 4 in bits [0,14), leading byte offset >> 4 in bits [16,30)
-//   high word: stride byte offset >> 4 in bits [0,14), version = 1 at bit 14, layout type in
-//              bits [29,32): 0 = SWIZZLE_NONE ("interleave"), 1 = SWIZZLE_128B_BASE32B
-__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo_bytes) {
-    return ((addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
-}
-__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
-    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
-}
-// Instruction descriptor: fp32 accumulate, tf32 x tf32, M = 128, runtime N, operand majors.
-__device__ __forceinline__ uint32_t instr_desc(int n, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-
-// Round-to-nearest (ties away) to the 10-bit TF32 mantissa with two integer ops: add half an
-// ulp of the dropped 13 bits to the magnitude, clear them.  (`cvt.rna.tf32.f32` compiles to the
-// same pair plus an FSETP / SEL for Inf / NaN, which the split does not need: Inf stays Inf --
-// 0x1000 is masked away again -- and NaN stays NaN.)
-__device__ __forceinline__ float to_tf32(float x) {
-    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-}
+constexpr int BN = 288;                 // 160 + up to 128 (multiple of the 32-element MN atom)
+constexpr int BN0 = 160;
+constexpr int STAGES = 2;
+constexpr int PRODUCER_WARPS = 14;    // two groups of 7 (+ 1 MMA warp = 480 threads -> 128 registers each)
+constexpr int GROUP_WARPS = PRODUCER_WARPS / 2;
+constexpr int EPILOGUE_WARPS = 12;    // 3 column groups x 4 TMEM lane quarters
+constexpr int THREADS = 32 * (PRODUCER_WARPS + 1);
+constexpr int A_TILE = BM * BK * 4;     // bytes of one tf32 A tile (hi or lo)
+constexpr int B_TILE = BN * BK * 4;
+constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;            // 102400
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 64;           // + barriers, tmem pointer
+constexpr int TMEM_COLS = 512;
+constexpr int A_PATCHES = BM * BK / 128;                        // 32 patches of 128 floats (one per warp instruction)
+constexpr int B_PATCHES = BN * BK / 128;                        // 72
+constexpr int PATCHES = A_PATCHES + B_PATCHES;                  // 104
+constexpr int PATCH_ITERS = (PATCHES + GROUP_WARPS - 1) / GROUP_WARPS;   // 15: one group stages a whole k-block
 
 // ---------------------------------------------------------------- operand staging
 // One operand tile is ROWS (M or N extent) x BK.
@@ -479,53 +376,6 @@ constexpr int STAGE2_BYTES = 2 * A_TILE + 2 * B2_TILE_MAX;       // 73728
 constexpr int STAGES2 = 2;                                       // three stages (216 KB) measured slower: they leave no L1 for the operand loads
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 128;
 constexpr int CPITCH2 = 276;                                     // epilogue staging pitch (128 x 276 floats = 141 KB of the 216 KB of stages)
-
-__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    for (uint32_t spin = 0; !mbar_try_wait_cluster(bar, parity); ++spin)
-        if (spin > (1u << 26)) __trap();
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_commit2(uint32_t bar) {     // arrives on `bar` of BOTH CTAs once the MMAs issued so far retire
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 :: "r"(bar), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                           uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-                 "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-                 "setp.ne.b32 p, %6, 0;\n\t"
-                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t}"
-                 :: "r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ uint32_t instr_desc2(int n, int a_mn_major, int b_mn_major) {      // M = 256
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-}
 
 template <bool TA, bool TB, bool REDUCE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -1078,6 +928,23 @@ extern "C" int gsr_tcgemm_f32(const float* A, const float* B, float* C,
     tc::Params p{A, B, C, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch, 1, alpha,
                  epilogue, extra, ld_extra, stride_extra};
     if (!tc::operands_ok(p)) return fail(GSR_E_ALIGN, "tcgemm: operands must be 16-byte aligned with leading dimensions % 4 == 0");
+    if (tc::g_pairs && tc::pair_ok(p) && tc::tma_ok(p, transA, transB)) {
+        // TMA-fed persistent CTA pairs (csrc/tcgemm_tma.cu) for the first 256 floor(M / 256) rows; the remaining rows on the
+        // FP32 ragged-row kernels (<= 16 rows: the 12 rows a 268-row subject matrix leaves) or the one-CTA tensor kernel
+        int rc = tc::tma_launch(p, transA, transB, false, batch, (cudaStream_t)stream);
+        if (rc) return rc;
+        const int m_done = (M / 256) * 256;
+        if (m_done == M) return 0;
+        tc::Params t = p;
+        t.M = M - m_done;
+        t.A = A + (transA ? (size_t)m_done : (size_t)m_done * lda);
+        t.C = C + (size_t)m_done * ldc;
+        if (epilogue == GSR_EPI_ADD) t.extra = extra + (size_t)m_done * ld_extra;
+        if (tc::g_tail && tc::tail::tail_bt_ok(t, transB)) return tc::tail::launch_tail_bt(t, transA, (cudaStream_t)stream);
+        if (tc::g_tail && tc::tail::tail_ok(t, transB)) return tc::tail::launch_tail(t, transA, (cudaStream_t)stream);
+        dim3 gt((t.M + tc::BM - 1) / tc::BM, (N + tc::BN - 1) / tc::BN, batch);
+        return tc::launch<false>(t, transA, transB, gt, (cudaStream_t)stream);
+    }
     if (tc::g_pairs && tc::pair_ok(p) && (long long)(transA ? K : M) * lda < 0x7fffffffLL && (long long)(transB ? N : K) * ldb < 0x7fffffffLL) {
         // CTA pairs (cta_group::2) for the first 2 * floor(tiles / 2) M tiles, the one-CTA kernel for an odd last tile
         int rc = tc::launch_pairs<false>(p, transA, transB, batch, (cudaStream_t)stream);
@@ -1131,7 +998,8 @@ extern "C" int gsr_tcgemm_reduce_f32(const float* A, const float* B, float* C,
         // CTA pairs take the even number of leading M tiles; the ragged last tile is launched on its own with its
         // own split count and compact partials behind those of the pairs.
         p.splits = plan.pair_splits;
-        rc = tc::launch_pairs<true>(p, transA, transB, plan.pair_splits, (cudaStream_t)stream);
+        if (tc::tma_ok(p, transA, transB) && (M / 256) * 256 == plan.m_head) rc = tc::tma_launch(p, transA, transB, true, plan.pair_splits, (cudaStream_t)stream);
+        else rc = tc::launch_pairs<true>(p, transA, transB, plan.pair_splits, (cudaStream_t)stream);
         if (rc) return rc;
         if (plan.m_head < M) {
             tc::Params q = p;

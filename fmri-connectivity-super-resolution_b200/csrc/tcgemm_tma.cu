@@ -1,0 +1,401 @@
+// TMA-fed persistent CTA-pair GEMM (tcgen05.mma.cta_group::2 kind::tf32, 3xTF32 split) -- round 2.
+//
+// Same arithmetic as csrc/tcgemm.cu (lo.hi + hi.lo + hi.hi into one fp32 accumulator in tensor memory), new data path:
+//   * operands arrive by `cp.async.bulk.tensor` (TMA, 3-D tensor maps {columns, rows, batch item}: out-of-range
+//     rows / columns of a subject matrix are zero filled per subject) straight into the shared-memory layouts the
+//     UMMA descriptors name -- K-major operands with CU_TENSOR_MAP_SWIZZLE_128B (box 32 floats x rows; descriptor
+//     layout SWIZZLE_128B, SBO 1024), MN-major operands with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (one box of
+//     32 floats x 32 k-rows per 32-wide block; layout SWIZZLE_128B_BASE32B, LBO 4096, SBO 512).  Probed on the
+//     hardware first: tools/probes/tma_probe.cu, profiles/r2_tma_tf32_probe.txt;
+//   * kind::tf32 reads 32-bit containers and IGNORES the 13 low mantissa bits (same probe, T1: 3072 of 3072
+//     full-mantissa values were read truncated), so the raw fp32 tile IS the `hi` term; 8 converter warps only
+//     compute lo = tf32(x - trunc(x)) shared memory -> shared memory (element-wise, layout agnostic, conflict free):
+//     no global-load scoreboard, no register staging, half the stores of the thread-staged kernels;
+//   * persistent: one CTA pair per TPC walks the tiles (256 rows x all columns each); the TMA warp runs up to three
+//     k-blocks ahead, across tile boundaries, so the pipeline fill and the epilogue of a tile overlap the loads of
+//     the next one;
+//   * epilogue: 4 warps drain the accumulator (tcgen05.ld 32x32b.x32), apply alpha / bias / addend, stage 32 x 32
+//     blocks in a 128B-swizzled double buffer and write them with TMA stores (clipped at the matrix edge).
+// Warp roles (448 threads): 0 TMA producer, 1 MMA issuer (leader CTA) + tensor-memory allocation, 2-9 converters,
+// 10-13 epilogue (warp % 4 = tensor-memory lane quarter).
+#include <cuda.h>
+
+#include "tcgemm.cuh"
+
+namespace gsr {
+namespace tc {
+
+int g_tma = 1;
+
+namespace t3 {
+
+constexpr int RAW_STAGES = 3, LO_STAGES = 2;
+constexpr int A_TILE = BM * BK * 4;                       // 16384
+constexpr int B_TILE_MAX = 160 * BK * 4;                  // 20480 (MN-major: 96 + 64 columns; K-major: 80 + 56 rows = 17408)
+constexpr int SLOT_BYTES = A_TILE + B_TILE_MAX;           // 36864, multiple of 1024
+constexpr int CONV_WARPS = 8, EPI_WARPS = 4;
+constexpr int THREADS = 32 * (2 + CONV_WARPS + EPI_WARPS);        // 448
+constexpr int STG_BYTES = 32 * 32 * 4;                    // one 32 x 32 staging block
+constexpr int SMEM_DATA = (RAW_STAGES + LO_STAGES) * SLOT_BYTES + EPI_WARPS * 2 * STG_BYTES;      // 217088
+constexpr int SMEM_BYTES = SMEM_DATA + 256 + 1024;        // + barriers / tensor-memory slot, + alignment slack
+constexpr int TMEM_COLS = 512;
+
+struct Plan {
+    int tiles_m;            // pair tiles along M per batch item
+    int items;              // output batch items (REDUCE: splits)
+    int nsub;               // REDUCE: subjects accumulated in all (else 1 per item)
+    int splits;             // REDUCE: stride between the subjects of an item
+    int M, N, K, nkb;
+    int nr0, nr1;           // UMMA N of the two accumulator column ranges (nr1 may be 0)
+    int a_batched, b_batched;
+    float alpha;
+    int epilogue;
+    const float* extra; int ld_extra; long long s_extra;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :: "l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void prefetch_map(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory"); }
+
+// TA: op(A) = A^T (A stored [K][M], MN-major).  TB: op(B) = B^T (B stored [N][K], K-major).
+template <bool TA, bool TB, bool REDUCE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB0,
+               const __grid_constant__ CUtensorMap mapB1, const __grid_constant__ CUtensorMap mapC, const Plan p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* raw = smem;                                              // [RAW_STAGES][A | B]  fp32 as landed = hi
+    uint8_t* lo = smem + RAW_STAGES * SLOT_BYTES;                     // [LO_STAGES][A | B]   tf32(x - trunc(x))
+    uint8_t* stg = lo + LO_STAGES * SLOT_BYTES;                       // [EPI_WARPS][2][32 x 32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_DATA);
+    // raw_full[3] (TMA bytes landed, local), raw_empty[3] / lo_empty[2] (MMA retired: commit multicast),
+    // conv_full[2] (leader's: converter warps of both CTAs), tmem_full (commit multicast), tmem_empty (leader's)
+    const uint32_t bar_raw_full = smem_u32(bars), bar_raw_empty = smem_u32(bars + RAW_STAGES);
+    const uint32_t bar_lo_empty = smem_u32(bars + 2 * RAW_STAGES), bar_conv_full = smem_u32(bars + 2 * RAW_STAGES + LO_STAGES);
+    const uint32_t bar_tmem_full = smem_u32(bars + 2 * RAW_STAGES + 2 * LO_STAGES), bar_tmem_empty = bar_tmem_full + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RAW_STAGES + 2 * LO_STAGES + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_rank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int total_tiles = p.items * p.tiles_m;
+    const int R0 = p.nr0 >> 1, R1 = p.nr1 >> 1;                       // this CTA's share of the two B ranges
+    const uint32_t b_bytes = (uint32_t)(R0 + R1) * 128u;
+    const int kb_per_tile = (REDUCE ? (p.nsub + p.splits - 1) / p.splits : 1) * p.nkb;   // upper bound, exact below
+
+    if (tid == 0) {
+        for (int s = 0; s < RAW_STAGES; ++s) { mbar_init(bar_raw_full + 8 * s, 1); mbar_init(bar_raw_empty + 8 * s, 1); }
+        for (int s = 0; s < LO_STAGES; ++s) { mbar_init(bar_lo_empty + 8 * s, 1); mbar_init(bar_conv_full + 8 * s, 2 * CONV_WARPS); }
+        mbar_init(bar_tmem_full, 1);
+        mbar_init(bar_tmem_empty, 2 * EPI_WARPS);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc2(smem_u32(tmem_slot), TMEM_COLS);
+    if (warp == 0 && lane == 0) { prefetch_map(&mapA); prefetch_map(&mapB0); prefetch_map(&mapB1); prefetch_map(&mapC); }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    (void)kb_per_tile;
+
+    if (warp == 0) {
+        // ===== TMA producer (one lane): every CTA loads its own 128 rows of op(A) and its half of op(B)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+                const int z = tile / p.tiles_m, mp = tile - z * p.tiles_m;
+                const int m0 = mp * 256 + (int)rank * BM;
+                const int nsub = REDUCE ? (p.nsub - z + p.splits - 1) / p.splits : 1;
+                for (int sub = 0; sub < nsub; ++sub) {
+                    const int b = REDUCE ? z + sub * p.splits : z;
+                    const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
+                    for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+                        const uint32_t s = it % RAW_STAGES, use = it / RAW_STAGES;
+                        if (use > 0) mbar_wait(bar_raw_empty + 8 * s, (use - 1) & 1);
+                        const uint32_t full = bar_raw_full + 8 * s;
+                        mbar_expect_tx(full, (uint32_t)A_TILE + b_bytes);
+                        const uint32_t a_dst = smem_u32(raw + s * SLOT_BYTES), b_dst = a_dst + A_TILE;
+                        const int k0 = kb * BK;
+                        if (!TA) tma_load(a_dst, &mapA, full, k0, m0, ba);                         // box {32 k, 128 m}
+                        else {
+#pragma unroll
+                            for (int j = 0; j < BM / 32; ++j) tma_load(a_dst + j * 4096, &mapA, full, m0 + 32 * j, k0, ba);   // box {32 m, 32 k}
+                        }
+                        if (TB) {                                                                   // boxes {32 k, R0 n}, {32 k, R1 n}
+                            tma_load(b_dst, &mapB0, full, k0, R0 * (int)rank, bb);
+                            if (R1 > 0) tma_load(b_dst + R0 * 128, &mapB1, full, k0, p.nr0 + R1 * (int)rank, bb);
+                        } else {                                                                    // box {32 n, 32 k} per 32 columns
+                            for (int j = 0; j < R0 / 32; ++j) tma_load(b_dst + j * 4096, &mapB0, full, R0 * (int)rank + 32 * j, k0, bb);
+                            for (int j = 0; j < R1 / 32; ++j) tma_load(b_dst + R0 * 128 + j * 4096, &mapB0, full, p.nr0 + R1 * (int)rank + 32 * j, k0, bb);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer: one lane of the leader CTA
+        if (rank == 0 && lane == 0) {
+            const uint32_t idesc0 = instr_desc2(p.nr0, TA ? 1 : 0, TB ? 0 : 1);
+            const uint32_t idesc1 = instr_desc2(p.nr1 > 0 ? p.nr1 : 16, TA ? 1 : 0, TB ? 0 : 1);
+            // K-major (SWIZZLE_128B): 8-row groups 1024 bytes apart (SBO), k-step of 8 floats = +32 bytes
+            // MN-major (SWIZZLE_128B_BASE32B): 32-wide blocks 4096 bytes apart (LBO), 4-k groups 512 bytes apart (SBO), k-step = +1024
+            const uint32_t a_dhi = TA ? desc_hi(512, 1) : desc_hi(1024, 2), b_dhi = TB ? desc_hi(1024, 2) : desc_hi(512, 1);
+            const uint32_t a_lbo = TA ? 4096 : 16, b_lbo = TB ? 16 : 4096;
+            const uint32_t a_step = (TA ? 1024u : 32u) >> 4, b_step = (TB ? 32u : 1024u) >> 4;
+            const uint32_t n1 = (uint32_t)(R0 * 128) >> 4;                  // start of the second range inside a B tile
+            uint32_t it = 0, tile_n = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++tile_n) {
+                const int z = tile / p.tiles_m;
+                const int nsub = REDUCE ? (p.nsub - z + p.splits - 1) / p.splits : 1;
+                if (tile_n > 0) { mbar_wait_cluster(bar_tmem_empty, (tile_n - 1) & 1); tc_fence_after(); }   // epilogues of both CTAs drained it
+                uint32_t acc = 0;
+                for (int sub = 0; sub < nsub; ++sub) {
+                    for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+                        const uint32_t rs = it % RAW_STAGES, ls = it % LO_STAGES, luse = it / LO_STAGES;
+                        mbar_wait_cluster(bar_conv_full + 8 * ls, luse & 1);
+                        tc_fence_after();
+                        const uint32_t hb = smem_u32(raw + rs * SLOT_BYTES), lb = smem_u32(lo + ls * SLOT_BYTES);
+                        uint32_t ah = desc_lo(hb, a_lbo), al = desc_lo(lb, a_lbo);
+                        uint32_t bh = desc_lo(hb + A_TILE, b_lbo), bl = desc_lo(lb + A_TILE, b_lbo);
+                        const int ksteps = min(BK / 8, (p.K - kb * BK + 7) >> 3);
+                        for (int j = 0; j < ksteps; ++j) {
+                            umma2_tf32(tmem_base, al, a_dhi, bh, b_dhi, idesc0, acc);              // small terms first
+                            umma2_tf32(tmem_base, ah, a_dhi, bl, b_dhi, idesc0, 1u);
+                            umma2_tf32(tmem_base, ah, a_dhi, bh, b_dhi, idesc0, 1u);
+                            if (p.nr1 > 0) {
+                                umma2_tf32(tmem_base + p.nr0, al, a_dhi, bh + n1, b_dhi, idesc1, acc);
+                                umma2_tf32(tmem_base + p.nr0, ah, a_dhi, bl + n1, b_dhi, idesc1, 1u);
+                                umma2_tf32(tmem_base + p.nr0, ah, a_dhi, bh + n1, b_dhi, idesc1, 1u);
+                            }
+                            acc = 1u;
+                            ah += a_step; al += a_step; bh += b_step; bl += b_step;
+                        }
+                        umma_commit2(bar_raw_empty + 8 * rs);                // both CTAs: raw slot free once these MMAs retire
+                        umma_commit2(bar_lo_empty + 8 * ls);                 //            lo slot free
+                    }
+                }
+                umma_commit2(bar_tmem_full);                                 // accumulator of this tile complete
+            }
+        }
+        __syncwarp();
+    } else if (warp < 2 + CONV_WARPS) {
+        // ===== converters: lo = tf32(x - trunc(x)), shared memory -> shared memory at the same offset
+        const int ct = tid - 64;                                             // 0 .. 255
+        const uint32_t conv_leader = map_to_cta(bar_conv_full, 0);
+        const int b_vec = (R0 + R1) * 8;                                     // float4s of this CTA's B tile
+        uint32_t it = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+            const int z = tile / p.tiles_m;
+            const int nkbt = (REDUCE ? (p.nsub - z + p.splits - 1) / p.splits : 1) * p.nkb;
+            for (int kbt = 0; kbt < nkbt; ++kbt, ++it) {
+                const uint32_t rs = it % RAW_STAGES, ruse = it / RAW_STAGES, ls = it % LO_STAGES, luse = it / LO_STAGES;
+                const float4* src = reinterpret_cast<const float4*>(raw + rs * SLOT_BYTES);
+                float4* dst = reinterpret_cast<float4*>(lo + ls * SLOT_BYTES);
+                mbar_wait(bar_raw_full + 8 * rs, ruse & 1);                  // TMA bytes of this CTA landed
+                float4 v[9];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = src[ct + 256 * i];                               // A: 1024 float4
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    const int e = ct + 256 * i;
+                    v[4 + i] = e < b_vec ? src[A_TILE / 16 + e] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (luse > 0) mbar_wait(bar_lo_empty + 8 * ls, (luse - 1) & 1);                     // MMA drained the lo slot
+#pragma unroll
+                for (int i = 0; i < 9; ++i) {
+                    float4 x = v[i], l;
+                    l.x = to_tf32(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+                    l.y = to_tf32(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+                    l.z = to_tf32(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+                    l.w = to_tf32(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+                    if (i < 4) dst[ct + 256 * i] = l;
+                    else { const int e = ct + 256 * (i - 4); if (e < b_vec) dst[A_TILE / 16 + e] = l; }
+                }
+                fence_async_smem();                                          // generic-proxy writes -> async proxy (UMMA)
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(conv_leader + 8 * ls);    // the leader's conv_full counts the warps of both CTAs
+            }
+        }
+    } else {
+        // ===== epilogue: tensor memory -> registers -> swizzled staging block -> TMA store
+        const int q = warp & 3;                                              // tensor-memory lane quarter of this warp
+        uint8_t* my_stg = stg + (warp - 2 - CONV_WARPS) * 2 * STG_BYTES;
+        const uint32_t empty_leader = map_to_cta(bar_tmem_empty, 0);
+        const int chunks = (p.N + 31) >> 5;
+        uint32_t tile_n = 0, nstore = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++tile_n) {
+            const int z = tile / p.tiles_m, mp = tile - z * p.tiles_m;
+            const int row = mp * 256 + (int)rank * BM + q * 32 + lane;       // output row of this thread
+            const float* extra_row = nullptr;
+            if (!REDUCE && p.epilogue == GSR_EPI_ADD) extra_row = p.extra + (size_t)z * p.s_extra + (size_t)row * p.ld_extra;
+            const float alpha = REDUCE ? 1.0f : p.alpha;
+            const int epi = REDUCE ? GSR_EPI_NONE : p.epilogue;
+            mbar_wait(bar_tmem_full, tile_n & 1);
+            tc_fence_after();
+            for (int c = 0; c < chunks; ++c, ++nstore) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                if (c == chunks - 1) {                                       // accumulator fully read by this warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(empty_leader);
+                }
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * alpha;
+                const int n0 = c * 32;
+                if (epi == GSR_EPI_BIAS) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        if (n0 + i < p.N) {                                  // N % 4 == 0 (launcher)
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.extra + n0 + i));
+                            f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+                        }
+                    }
+                } else if (epi == GSR_EPI_ADD) {
+                    if (row < p.M) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            if (n0 + i < p.N) {
+                                const float4 a4 = __ldg(reinterpret_cast<const float4*>(extra_row + n0 + i));
+                                f[i] += a4.x; f[i + 1] += a4.y; f[i + 2] += a4.z; f[i + 3] += a4.w;
+                            }
+                        }
+                    }
+                }
+                uint8_t* blk = my_stg + (nstore & 1) * STG_BYTES;
+                if (nstore >= 2) { if (lane == 0) tma_wait_read<1>(); __syncwarp(); }     // the store that last read this block is done
+#pragma unroll
+                for (int j = 0; j < 8; ++j)                                  // row = lane; 16-byte chunk j at (j ^ (lane & 7)): conflict free
+                    *reinterpret_cast<float4*>(blk + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) { tma_store(&mapC, smem_u32(blk), n0, mp * 256 + (int)rank * BM + q * 32, z); tma_commit(); }
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                                      // the peer may still read this CTA's operands / signal its barriers
+    if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn encode_fn() {
+    static EncodeFn fn = []() -> EncodeFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        return reinterpret_cast<EncodeFn>(p);
+    }();
+    return fn;
+}
+
+// {cols, rows, items} view of a row-major fp32 operand; strides in elements.
+static bool make_map(CUtensorMap* m, const float* base, long long cols, long long rows, long long items, long long ld,
+                     long long stride_item, int box_cols, int box_rows, CUtensorMapSwizzle sw) {
+    EncodeFn enc = encode_fn();
+    if (!enc) return false;
+    if (items < 1) items = 1;
+    if (stride_item <= 0) stride_item = rows * ld;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)items};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)stride_item * 4};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace t3
+
+bool tma_ok(const Params& p, int transA, int transB) {
+    (void)transA;
+    if (!g_tma || !t3::encode_fn()) return false;
+    if (p.M < 256 || p.K < 1 || p.N % 4 != 0) return false;
+    if (transB ? p.N > 272 : p.N > 320) return false;
+    if (p.lda % 4 || p.ldb % 4 || p.ldc % 4 || p.sA % 4 || p.sB % 4 || p.sC % 4) return false;
+    if (!aligned16(p.A) || !aligned16(p.B) || !aligned16(p.C)) return false;
+    if (p.epilogue != GSR_EPI_NONE && !aligned16(p.extra)) return false;
+    if (p.epilogue == GSR_EPI_ADD && (p.ld_extra % 4 || p.s_extra % 4)) return false;
+    return true;
+}
+
+int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, cudaStream_t st) {
+    using namespace t3;
+    Plan pl{};
+    pl.tiles_m = p.M / 256;
+    pl.items = zdim;
+    pl.nsub = reduce ? p.batch : 1;
+    pl.splits = reduce ? p.splits : 1;
+    pl.M = p.M; pl.N = p.N; pl.K = p.K; pl.nkb = (p.K + BK - 1) / BK;
+    if (transB) {                                   // K-major B: 8-row granularity per CTA
+        const int npad = (p.N + 15) & ~15;
+        if (npad <= 256) { pl.nr0 = npad; pl.nr1 = 0; } else { pl.nr0 = 160; pl.nr1 = npad - 160; }
+    } else {                                        // MN-major B: 32-column blocks per CTA
+        const int npad = (p.N + 63) & ~63;
+        if (npad <= 256) { pl.nr0 = npad; pl.nr1 = 0; } else { pl.nr0 = 192; pl.nr1 = npad - 192; }
+    }
+    pl.a_batched = p.sA != 0; pl.b_batched = p.sB != 0;
+    pl.alpha = p.alpha; pl.epilogue = p.epilogue; pl.extra = p.extra; pl.ld_extra = p.ld_extra; pl.s_extra = p.s_extra;
+    const int R0 = pl.nr0 / 2, R1 = pl.nr1 / 2;
+    const long long a_items = pl.a_batched ? p.batch : 1, b_items = pl.b_batched ? p.batch : 1;
+    CUtensorMap mA, mB0, mB1, mC;
+    bool ok = true;
+    // op(A) rows = M; A stored [M][K] (K-major) or [K][M] (MN-major)
+    if (!transA) ok = ok && make_map(&mA, p.A, p.K, p.M, a_items, p.lda, p.sA, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    else         ok = ok && make_map(&mA, p.A, p.M, p.K, a_items, p.lda, p.sA, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (transB) {                                   // B stored [N][K]
+        ok = ok && make_map(&mB0, p.B, p.K, p.N, b_items, p.ldb, p.sB, 32, R0, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && make_map(&mB1, p.B, p.K, p.N, b_items, p.ldb, p.sB, 32, R1 > 0 ? R1 : 8, CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {                                        // B stored [K][N]
+        ok = ok && make_map(&mB0, p.B, p.N, p.K, b_items, p.ldb, p.sB, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        mB1 = mB0;
+    }
+    // C: [items][M][N]; REDUCE writes partial sums of pitch sC = M * N, one per split
+    ok = ok && make_map(&mC, p.C, p.N, p.M, zdim, reduce ? p.N : p.ldc, p.sC, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (!ok) return fail(GSR_E_UNSUPPORTED, "tcgemm (TMA): cuTensorMapEncodeTiled failed");
+    const int total_tiles = pl.items * pl.tiles_m;
+    const int clusters = std::min(total_tiles, kNumSMs / 2);
+    dim3 grid(2 * clusters, 1, 1);
+#define GSR_T3_LAUNCH(TA, TB, RED)                                                                                \
+    do {                                                                                                          \
+        auto k = tcgemm3_kernel<TA, TB, RED>;                                                                     \
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);         \
+        if (e != cudaSuccess) return fail((int)e, "tcgemm (TMA): cudaFuncSetAttribute failed");                  \
+        k<<<grid, THREADS, SMEM_BYTES, st>>>(mA, mB0, mB1, mC, pl);                                               \
+    } while (0)
+#define GSR_T3_TT(RED)                                                                                            \
+    do {                                                                                                          \
+        if (!transA && !transB) GSR_T3_LAUNCH(false, false, RED);                                                 \
+        else if (!transA && transB) GSR_T3_LAUNCH(false, true, RED);                                              \
+        else if (transA && !transB) GSR_T3_LAUNCH(true, false, RED);                                              \
+        else GSR_T3_LAUNCH(true, true, RED);                                                                      \
+    } while (0)
+    if (reduce) GSR_T3_TT(true); else GSR_T3_TT(false);
+#undef GSR_T3_TT
+#undef GSR_T3_LAUNCH
+    return launched(reduce ? "tcgemm3_reduce" : "tcgemm3");
+}
+
+}  // namespace tc
+}  // namespace gsr

@@ -71,19 +71,12 @@ def eigh(A: torch.Tensor, UPLO: str = "U", check_errors: bool = True, canonical_
     if A.requires_grad and torch.is_grad_enabled():
         raise NotImplementedError("eigh: gradients through the eigendecomposition are not on the GSR-Net path")
     A = A.detach()
+    # QL failures (more than 30 iterations per eigenvalue / 2 n^2 rotations: info == -2) are redone by the Jacobi
+    # kernel inside gsr_eigh_tridiag_f32 itself, on the device and in the same stream -- also when nothing here
+    # synchronises (training steps, CUDA graphs).  `check_errors` only adds torch's raise-on-failure contract.
     w, U, info = K.eigh(A, canonical_sign=canonical_sign)
     if check_errors:
-        worst = int(info.min().item())                  # torch.linalg.eigh's error contract costs one sync
-        if worst == -2 and K.EIGH_METHOD == "auto" and A.shape[-1] <= K.EIGH_TRIDIAG_MAX_N:
-            # the QL iteration gave up on some graphs (more than 2 n^2 rotations): those go through
-            # the Jacobi kernel, which always converges
-            bad = (info == -2).nonzero().flatten()
-            Ab = A.reshape(-1, A.shape[-2], A.shape[-1])[bad]
-            wb, Ub, ib = K.eigh_jacobi(Ab, canonical_sign=canonical_sign)
-            w.reshape(-1, A.shape[-1])[bad] = wb
-            U.reshape(-1, A.shape[-2], A.shape[-1])[bad] = Ub
-            info[bad] = ib
-        raise_on_eigh_info(info)
+        raise_on_eigh_info(info)                        # torch.linalg.eigh's error contract costs one sync
     return w, U, info
 
 

@@ -32,8 +32,12 @@ class GSRNet(nn.Module):
         self.overlap_unet = True        # batched forward: U-Net on a side stream under the eigendecomposition
         self._side_stream = None
 
-    def forward(self, lr, U=None):
+    def forward(self, lr, U=None, check_eigh=None):
+        """``U`` (extension): a precomputed eigenbasis of the normalised LR adjacency.  ``check_eigh`` (extension):
+        override ``self.layer.check_eigh`` for this call (False = no host synchronisation; the device-side Jacobi
+        fallback for QL failures runs either way)."""
         lr = lr if lr.is_cuda else lr.to(device)
+        check = self.layer.check_eigh if check_eigh is None else bool(check_eigh)
         if self.layer.weights.device.type != "cuda":
             raise RuntimeError("GSRNet: move the model to the GPU first (model.to('cuda')); there is no CPU path")
         I = torch.eye(self.lr_dim, device=lr.device)                                  # :24
@@ -49,13 +53,13 @@ class GSRNet(nn.Module):
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 self.net_outs, self.start_gcn_outs = self.net(A, I)                   # :27
-            self.layer.eig_val_lr, U, self.layer.eigh_info = F_.eigh(A, "U", check_errors=self.layer.check_eigh)   # layers.py:27
+            self.layer.eig_val_lr, U, self.layer.eigh_info = F_.eigh(A, "U", check_errors=check)   # layers.py:27
             main.wait_stream(side)
             self.net_outs.record_stream(main)
             self.start_gcn_outs.record_stream(main)
         else:
             self.net_outs, self.start_gcn_outs = self.net(A, I)                       # :27
-        self.outputs, self.Z = self.layer(A, self.net_outs, U=U)                      # :28
+        self.outputs, self.Z = self.layer(A, self.net_outs, U=U, check_eigh=check)    # :28
         # :29-30  hidden1 = gc1(Z, outputs); hidden2 = gc2(hidden1, outputs) -- one autograd node for the two layers
         self.hidden1, self.hidden2 = F_.GraphConvPairFn.apply(self.Z, self.outputs, self.gc1.weight, self.gc2.weight)
         z = F_.sym_diag_abs(self.hidden2)                                             # :32-37

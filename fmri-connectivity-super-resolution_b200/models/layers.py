@@ -31,9 +31,10 @@ class GSRLayer(nn.Module):
         """models/layers.py:55-56: |W U^T f| with unit diagonal (materialised on demand)."""
         return None if self._F is None else K.abs_diag1(self._F)
 
-    def forward(self, A, X, U=None):
+    def forward(self, A, X, U=None, check_eigh=None):
         """``U`` (optional, extension) injects a precomputed eigenbasis of A, e.g. one cached
-        across epochs: the LR eigendecomposition depends on the data only."""
+        across epochs: the LR eigendecomposition depends on the data only.
+        ``check_eigh`` overrides ``self.check_eigh`` for this call."""
         A = A if A.is_cuda else A.to(device)
         f = X if X.is_cuda else X.to(device)
         if A.shape[-1] != self.lr_dim or f.shape[0] != self.lr_dim:
@@ -42,7 +43,7 @@ class GSRLayer(nn.Module):
         if f.shape[1] != self.hr_dim:
             raise RuntimeError(f"GSRLayer: X must have {self.hr_dim} feature columns (normalize_adj needs a square f_d)")
         if U is None:
-            self.eig_val_lr, U, self.eigh_info = F_.eigh(A, "U", check_errors=self.check_eigh)      # :27
+            self.eig_val_lr, U, self.eigh_info = F_.eigh(A, "U", check_errors=self.check_eigh if check_eigh is None else bool(check_eigh))      # :27
         self.U_lr = U
         adj, Z, self._F = F_.GSRLayerFn.apply(self.weights, A.detach(), f, U)
         return adj, Z

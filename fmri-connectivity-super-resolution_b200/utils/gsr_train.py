@@ -102,11 +102,12 @@ class GSRTrainStep:
 
     def __init__(self, model, lmbda=16, padding=0, check_errors=False):
         self.model, self.lmbda, self.padding, self.check_errors = model, lmbda, padding, check_errors
-        model.layer.check_eigh = False
 
     def forward_loss(self, lr, hr, U_hr_reduced=None, U_lr=None):
         model = self.model
-        out, net_outs, start_gcn_outs, _ = model(lr, U=U_lr)
+        # check_errors=True raises inside the forward pass, before any product consumes a failed basis; the
+        # caller's model keeps its own ``layer.check_eigh`` either way
+        out, net_outs, start_gcn_outs, _ = model(lr, U=U_lr, check_eigh=self.check_errors)
         out = unpad(out, self.padding)
         if U_hr_reduced is None:
             U_hr_reduced = hr_target_basis(hr, model.layer.lr_dim, self.padding, check_errors=False)
@@ -120,8 +121,6 @@ class GSRTrainStep:
     def __call__(self, lr, hr, U_hr_reduced=None, U_lr=None):
         loss, error = self.forward_loss(lr, hr, U_hr_reduced, U_lr)
         loss.backward()
-        if self.check_errors and self.model.layer.eigh_info is not None:
-            F_.raise_on_eigh_info(self.model.layer.eigh_info)
         return loss.detach(), error.detach()
 
 

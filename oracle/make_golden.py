@@ -87,6 +87,11 @@ def gsrnet_fixture(ref, name, lr_dim, hr_dim, n_subj, weight_seed, data_seed, ro
             out[p + "eigvals"] = w.numpy().copy()
             out[p + "U"] = U.numpy()[::row_stride].copy()
             out[p + "U_hr_reduced"] = U_hr_red.numpy()[::row_stride].copy()
+            # the reference's FULL bases (LAPACK, sign rule applied): the own-eigenbasis GPU tests align the kernel's
+            # eigenvectors to U_full column by column and feed U_hr_full to the |W - U_hr| term, so that every
+            # subject is asserted whatever the sign-pivot margin of its eigenvectors
+            out[p + "U_full"] = U.numpy().copy()
+            out[p + "U_hr_full"] = U_hr_red.numpy().copy()
             if s == 0:
                 out["net_outs"] = net_outs.detach().numpy().copy()
                 out["start_gcn_outs"] = start.detach().numpy().copy()
@@ -258,8 +263,8 @@ def main():
     vectorizer_fixture(ref)
     ops_fixture(ref)
     eval_fixture(ref)
-    gsrnet_fixture(ref, "gsrnet_small", lr_dim=136, hr_dim=268, n_subj=3, weight_seed=3, data_seed=40, row_stride=8)
-    gsrnet_fixture(ref, "gsrnet_full", lr_dim=160, hr_dim=268, n_subj=2, weight_seed=0, data_seed=1000, row_stride=4)
+    gsrnet_fixture(ref, "gsrnet_small", lr_dim=136, hr_dim=268, n_subj=4, weight_seed=3, data_seed=40, row_stride=8)
+    gsrnet_fixture(ref, "gsrnet_full", lr_dim=160, hr_dim=268, n_subj=8, weight_seed=0, data_seed=1000, row_stride=8)
 
 
 if __name__ == "__main__":

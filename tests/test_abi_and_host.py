@@ -227,3 +227,66 @@ def test_subject_parallel_gloo_world2(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"worker {r} ok" in o
+
+
+_FOLD_WORKER = r"""
+import importlib, os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+pkg = importlib.import_module({pkg!r})
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+assert world == 4
+folds, group, ranks = pkg.fold_groups(3)               # 4 ranks, 3 folds -> {{0, 1}}, {{2}}, {{3}}
+assert ranks == [[0, 1], [0, 1], [2], [3]][rank] and folds == [[0], [0], [1], [2]][rank]
+fold = folds[0]
+torch.manual_seed(100 + rank)                          # different weights on every rank before the broadcast
+model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+sp = pkg.SubjectParallel(model, group=group, broadcast_from=0)     # the fold's first rank seeds its group
+assert sp.world == len(ranks)
+# each fold trains on its own subjects; the ranks of a fold shard them
+g = torch.Generator().manual_seed(50 + fold)
+X, Y = torch.randn(8, 6, generator=g), torch.randn(8, 3, generator=g)
+lo, hi = pkg.shard_bounds(8, ranks.index(rank), len(ranks))
+loss = (model(X[lo:hi]) - Y[lo:hi]).abs().mean()
+loss.backward()
+local = [p.grad.clone() for p in model.parameters()]
+sp.sync_gradients()
+ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+ref.load_state_dict(model.state_dict())
+ref_loss = (ref(X) - Y).abs().mean()
+ref_loss.backward()
+for p, q in zip(model.parameters(), ref.parameters()):            # == the fold's whole batch on one rank
+    assert torch.allclose(p.grad, q.grad, atol=1e-7), (rank, (p.grad - q.grad).abs().max())
+if len(ranks) == 2:                                               # the multi-rank group really reduced
+    assert any(not torch.equal(a, p.grad) for a, p in zip(local, model.parameters()))
+else:                                                             # single-rank folds: nothing touched the gradient
+    assert all(torch.equal(a, p.grad) for a, p in zip(local, model.parameters()))
+# no traffic between folds: every fold has its own weights and its own loss; equal inside a fold
+flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()] + [ref_loss.detach().reshape(1)])
+everyone = [torch.zeros_like(flat) for _ in range(world)]
+dist.all_gather(everyone, flat)
+assert torch.equal(everyone[0], everyone[1])
+assert not torch.equal(everyone[0], everyone[2]) and not torch.equal(everyone[2], everyone[3])
+assert len({{float(e[-1]) for e in everyone}}) == 3
+dist.barrier()
+dist.destroy_process_group()
+print("worker", rank, "ok")
+"""
+
+
+def test_fold_groups_gloo_world4(tmp_path):
+    """BASELINE configs[2] host logic: 3 cross-validation folds on 4 ranks -> one two-rank fold group that
+    all-reduces its shards' gradients and two single-rank folds; nothing crosses fold boundaries."""
+    script = tmp_path / "fold_worker.py"
+    script.write_text(_FOLD_WORKER.format(root=ROOT, pkg=PKG_NAME))
+    port = 31500 + (os.getpid() % 2000)
+    procs = []
+    for r in range(4):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="4", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"worker {r} ok" in o

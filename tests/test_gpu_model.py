@@ -35,11 +35,23 @@ def rel_fro(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def sign_pivot_margin(U):
-    """Smallest relative gap between the two largest |components| of any eigenvector: when it is
-    ~0 the canonical sign of that vector is decided by rounding noise."""
-    top2 = U.abs().topk(2, dim=-2).values
-    return float(((top2[..., 0, :] - top2[..., 1, :]) / top2[..., 0, :]).min())
+def own_basis_aligned(pkg, lr, U_ref):
+    """The kernels' own eigendecomposition of the normalised LR adjacency, its eigenvectors sign-aligned column by
+    column to the reference's LAPACK basis ``U_ref`` (sign of <u_gpu_k, u_ref_k>).  Eigenvector signs are not
+    canonical and the stated sign rule is decided by rounding noise whenever the two largest
+    |components| of a vector are within ~1e-4 of each other, which is the normal case for 160-node connectomes
+    (72 % of random subjects have such a vector) -- so the comparison with the reference fixture is
+    made in the reference's sign convention, for EVERY subject, and the number of flipped columns is reported.
+    The sign rule itself is asserted on the raw kernel output.  Returns (w, U_raw, U_aligned, flips)."""
+    A = pkg.normalize_adj_torch(lr.cuda())
+    w, U, info = pkg.functional.eigh(A, "U")
+    assert int(info.min()) > 0
+    piv = torch.gather(U, -2, U.abs().argmax(dim=-2, keepdim=True))
+    assert bool((piv > 0).all()), "sign rule: the largest-|.| component of every eigenvector is positive"
+    dots = (U.double().cpu() * U_ref.double()).sum(0)
+    assert float(dots.abs().min()) > 0.9, "an eigenvector of the kernel does not match its LAPACK counterpart"
+    sign = torch.where(dots < 0, -1.0, 1.0).float()
+    return w, U, U * sign.cuda(), int((dots < 0).sum())
 
 
 @pytest.fixture(scope="module")
@@ -209,21 +221,37 @@ def test_gsrnet_forward_backward_single_subject_injected(setup):
 
 
 def test_gsrnet_own_eigh_matches_golden(setup, golden):
-    """Whole path on the GPU (own Jacobi eigh) against the fixture written by the reference."""
+    """Whole path on the GPU with the kernels' own eigendecomposition against the fixture written by the unmodified
+    reference, every subject asserted (no margin guard, no skip): outputs in the reference's sign convention
+    (own_basis_aligned), and -- for the subjects whose raw kernel basis already has the reference's signs -- the
+    plain ``model(lr)`` call bit-identical to that."""
     pkg, sd, model = setup
     G = golden("gsrnet_full")
-    rs = int(G["row_stride"])
-    for s in range(int(G["n_subj"])):
-        lr = O.synth_connectome(160, int(G["data_seed"]) + s)
-        with torch.no_grad():
-            out, net_outs, start, adj = model(lr.cuda())
-        if sign_pivot_margin(model.layer.U_lr) < 1e-3:
-            continue        # an eigenvector whose canonical sign is decided by rounding noise
+    rs, n_subj = int(G["row_stride"]), int(G["n_subj"])
+    assert n_subj >= 8
+    checked, flips_total, raw_identical = 0, 0, 0
+    for s in range(n_subj):
         p = f"s{s}_"
-        assert np.allclose(out.cpu().numpy()[::rs], G[p + "out"], rtol=0, atol=2e-5)
-        assert np.allclose(adj.cpu().numpy()[::rs], G[p + "adj"], rtol=0, atol=5e-6)
-        assert np.allclose(model.Z.cpu().numpy()[::rs], G[p + "Z"], rtol=0, atol=2e-5)
-        assert np.allclose(model.layer.eig_val_lr.cpu().numpy(), G[p + "eigvals"], rtol=0, atol=3e-6)
+        lr = O.synth_connectome(160, int(G["data_seed"]) + s)
+        w, U_raw, U_al, flips = own_basis_aligned(pkg, lr, torch.from_numpy(G[p + "U_full"]))
+        flips_total += flips
+        with torch.no_grad():
+            out, net_outs, start, adj = model(lr.cuda(), U=U_al)
+        assert np.allclose(out.cpu().numpy()[::rs], G[p + "out"], rtol=0, atol=2e-5), s
+        assert np.allclose(adj.cpu().numpy()[::rs], G[p + "adj"], rtol=0, atol=5e-6), s
+        assert np.allclose(model.Z.cpu().numpy()[::rs], G[p + "Z"], rtol=0, atol=2e-5), s
+        assert np.allclose(model.layer.f_d.cpu().numpy()[::rs], G[p + "f_d"], rtol=1e-3, atol=4e-4), s    # |F| ~ 0.36
+        assert np.allclose(w.cpu().numpy(), G[p + "eigvals"], rtol=0, atol=3e-6), s
+        assert np.allclose(U_al.cpu().numpy()[::rs], G[p + "U"], rtol=0, atol=2e-3), s
+        if flips == 0:
+            with torch.no_grad():
+                out2, _, _, adj2 = model(lr.cuda())             # own eigh AND own sign rule, nothing injected
+            assert torch.equal(out2, out) and torch.equal(adj2, adj)
+            raw_identical += 1
+        checked += 1
+    assert checked == n_subj
+    print(f"own-basis fixture parity: {checked} subjects asserted, {flips_total} of {160 * n_subj} eigenvector columns "
+          f"needed a sign flip, {raw_identical} subjects matched with the raw kernel signs")
 
 
 def test_gsrnet_batched_equals_per_subject_oracle(setup):
@@ -266,44 +294,66 @@ def test_gsrnet_batched_equals_per_subject_oracle(setup):
 
 
 def test_gsrnet_mean_gradients_match_golden(setup, golden):
-    """Own eigh for the LR basis; averaged gradients against the reference's fixture."""
+    """Loss and batch-mean parameter gradients with the kernels' own LR eigendecomposition (sign-aligned to the
+    reference's basis) against the reference-written fixture: all subjects in one batched step, nothing skipped."""
     pkg, sd, model = setup
     G = golden("gsrnet_full")
     n_subj, gs = int(G["n_subj"]), int(G["grad_stride"])
     lrs = [O.synth_connectome(160, int(G["data_seed"]) + s) for s in range(n_subj)]
     hrs = [O.synth_connectome(268, int(G["data_seed"]) + 500 + s) for s in range(n_subj)]
-    Uh = torch.stack([O.hr_target_basis(h, 160) for h in hrs]).cuda()
+    Uh = torch.stack([torch.from_numpy(G[f"s{s}_U_hr_full"]) for s in range(n_subj)]).cuda()
+    Ul = torch.stack([own_basis_aligned(pkg, lrs[s], torch.from_numpy(G[f"s{s}_U_full"]))[2] for s in range(n_subj)])
     model.zero_grad()
     step = pkg.GSRTrainStep(model, lmbda=16, padding=0, check_errors=True)
-    loss, err = step(torch.stack(lrs).cuda(), torch.stack(hrs).cuda(), U_hr_reduced=Uh)
+    loss, err = step(torch.stack(lrs).cuda(), torch.stack(hrs).cuda(), U_hr_reduced=Uh, U_lr=Ul)
     want_loss = np.mean([float(G[f"s{s}_loss"]) for s in range(n_subj)])
     want_err = np.mean([float(G[f"s{s}_error"]) for s in range(n_subj)])
     assert float(err) == pytest.approx(want_err, abs=5e-6)
-    if sign_pivot_margin(model.layer.U_lr) < 1e-3:
-        pytest.skip("canonical sign of an eigenvector is decided by rounding noise for this seed")
     assert float(loss) == pytest.approx(want_loss, abs=5e-5)
+    checked = 0
     for k, p in model.named_parameters():
         ref = G["mean_grad/" + k]
         a = p.grad.detach().cpu().numpy().reshape(-1)
         got = a if a.size <= 4096 else a[::gs]
         rel = np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-30)
         assert rel < 2e-2, (k, rel)           # gradients move O(1e-3..1e-2) with the basis (SURVEY H1)
+        checked += 1
+    assert checked == 33
+    # the GPU's own HR-target basis (268-node tridiagonal route) gives the same |W - U_hr| term up to its sign noise
+    Uh_own = pkg.hr_target_basis(torch.stack(hrs).cuda(), 160)
+    dots = (Uh_own.double() * Uh.double()).sum(1)
+    assert float(dots.abs().min()) > 0.9
+    l_own = pkg.functional.l1_loss_per_subject(Uh_own * torch.where(dots < 0, -1.0, 1.0).float()[:, None, :], model.layer.weights)
+    l_ref = pkg.functional.l1_loss_per_subject(Uh, model.layer.weights)
+    assert torch.allclose(l_own, l_ref, rtol=0, atol=2e-6)
+    # single-subject gradients (subject 0) against the fixture as well
+    model.zero_grad()
+    loss0, _ = step(lrs[0][None].cuda(), hrs[0][None].cuda(), U_hr_reduced=Uh[:1], U_lr=Ul[:1])
+    assert float(loss0) == pytest.approx(float(G["s0_loss"]), abs=5e-5)
+    for k, p in model.named_parameters():
+        ref = G["s0_grad/" + k]
+        a = p.grad.detach().cpu().numpy().reshape(-1)
+        got = a if a.size <= 4096 else a[::gs]
+        assert np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-30) < 2e-2, k
 
 
 def test_gsrnet_small_lr_dim_fixture(cuda_pkg, golden):
-    """lr_dim = 136 (ragged against the 32-row register tiling of the eigh kernel)."""
+    """lr_dim = 136 (ragged against the 32-row register tiling of the eigh kernel): every subject asserted."""
     G = golden("gsrnet_small")
     sd = O.make_state_dict(int(G["weight_seed"]), 136, 268, 268)
     model = make_model(cuda_pkg, sd, 136, 268)
-    rs = int(G["row_stride"])
-    for s in range(int(G["n_subj"])):
+    rs, n_subj = int(G["row_stride"]), int(G["n_subj"])
+    checked = 0
+    for s in range(n_subj):
         lr = O.synth_connectome(136, int(G["data_seed"]) + s)
+        w, U_raw, U_al, flips = own_basis_aligned(cuda_pkg, lr, torch.from_numpy(G[f"s{s}_U_full"]))
         with torch.no_grad():
-            out, _, _, adj = model(lr.cuda())
-        if sign_pivot_margin(model.layer.U_lr) < 1e-3:
-            continue
-        assert np.allclose(out.cpu().numpy()[::rs], G[f"s{s}_out"], rtol=0, atol=2e-5)
-        assert np.allclose(adj.cpu().numpy()[::rs], G[f"s{s}_adj"], rtol=0, atol=5e-6)
+            out, _, _, adj = model(lr.cuda(), U=U_al)
+        assert np.allclose(out.cpu().numpy()[::rs], G[f"s{s}_out"], rtol=0, atol=2e-5), s
+        assert np.allclose(adj.cpu().numpy()[::rs], G[f"s{s}_adj"], rtol=0, atol=5e-6), s
+        assert np.allclose(w.cpu().numpy(), G[f"s{s}_eigvals"], rtol=0, atol=3e-6), s
+        checked += 1
+    assert checked == n_subj >= 4
 
 
 def test_train_and_test_loops_match_oracle(cuda_pkg, capsys):
@@ -403,6 +453,120 @@ def test_full_batch_step_properties(setup):
     assert float(loss2) == pytest.approx(float(loss), rel=1e-5)
     for k, p in model.named_parameters():
         assert rel_fro(p.grad, g_ref[k]) < 1e-4, k
+
+
+def _synth_batch(n, B, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.rand(B, n, n, device="cuda", generator=g)
+    m = (x + x.transpose(1, 2)) / 2
+    m.diagonal(dim1=1, dim2=2).zero_()
+    return m.contiguous()
+
+
+def test_full_batch_matches_oracle_on_sampled_subjects(setup):
+    """BASELINE configs[1] (1024 subjects in one call, own eigendecompositions): 8 subjects of the batch against the
+    oracle (outputs, adjacency, eigenvalues, per-subject loss terms), the oracle fed the GPU's eigenbases of those
+    subjects so that the comparison is tight; plus the batch-mean gradient == mean of the 8 chunk gradients."""
+    pkg, sd, model = setup
+    F_ = pkg.functional
+    B = 1024
+    lr, hr = _synth_batch(160, B, 31), _synth_batch(268, B, 32)
+    Uh = pkg.hr_target_basis(hr, 160)
+    with torch.no_grad():
+        out, net_outs, start, adj = model(lr)
+        err_b = F_.l1_loss_per_subject(out, hr)
+        w_b = F_.l1_loss_per_subject(Uh, model.layer.weights)
+        reg = F_.l1_loss(net_outs, start)
+    assert int(model.layer.eigh_info.min()) > 0
+    U_lr, w_lr = model.layer.U_lr, model.layer.eig_val_lr
+    checked = 0
+    for s in (0, 1, 255, 256, 511, 700, 1022, 1023):
+        lr_s, hr_s = lr[s].cpu(), hr[s].cpu()
+        loss_ref, err_ref, (out_ref, _, _, adj_ref) = O.train_loss(sd, lr_s, hr_s, U=U_lr[s].cpu(), U_hr_reduced=Uh[s].cpu())
+        assert torch.allclose(out[s].cpu(), out_ref, rtol=0, atol=1e-5), s
+        assert torch.allclose(adj[s].cpu(), adj_ref, rtol=0, atol=1e-6), s
+        assert float(err_b[s]) == pytest.approx(float(err_ref), abs=2e-6), s
+        assert float(16 * reg + w_b[s] + err_b[s]) == pytest.approx(float(loss_ref), abs=5e-6), s
+        w64 = torch.linalg.eigvalsh(O.normalize_adj(lr_s).double(), UPLO="U")
+        assert float((w_lr[s].cpu().double() - w64).abs().max()) < 3e-6, s
+        A64 = O.normalize_adj(lr_s).double()
+        A64 = torch.triu(A64) + torch.triu(A64, 1).T
+        Us = U_lr[s].cpu().double()
+        assert float((A64 @ Us - Us * w_lr[s].cpu().double()).abs().max()) < 5e-6, s
+        checked += 1
+    assert checked == 8
+    # size-independent property at the full size: gradients are linear in the subjects
+    step = pkg.GSRTrainStep(model)
+    model.zero_grad()
+    step(lr, hr, U_hr_reduced=Uh, U_lr=U_lr)
+    g_full = {k: p.grad.clone() for k, p in model.named_parameters()}
+    acc = {k: torch.zeros_like(v) for k, v in g_full.items()}
+    for c in range(8):
+        sl = slice(128 * c, 128 * (c + 1))
+        model.zero_grad()
+        step(lr[sl], hr[sl], U_hr_reduced=Uh[sl], U_lr=U_lr[sl])
+        for k, p in model.named_parameters():
+            acc[k] += p.grad / 8
+    # (the subject-reduced products accumulate 14 subjects x 34 k-steps in tensor memory at B = 1024 against 2 x 34
+    # per chunk; the tensor core's accumulator rounds toward zero at every step, which shows as a ~3e-5 relative
+    # drift between the two groupings -- measured 3.6e-5 on gc1.weight)
+    for k in g_full:
+        assert rel_fro(g_full[k], acc[k]) < 1e-4, k
+
+
+def test_batched_gradients_match_oracle_through_the_split_reduction(setup):
+    """B = 96 subjects (> 74: the subject-reduced weight-gradient products run their full 74-way split with the
+    deterministic partial reduce in tensor memory) against the oracle's accumulated per-subject gradients, all 33
+    tensors, own LR eigendecomposition fed to both sides."""
+    pkg, sd, model = setup
+    B = 96
+    lr, hr = _synth_batch(160, B, 41), _synth_batch(268, B, 42)
+    Uh = pkg.hr_target_basis(hr, 160)
+    model.zero_grad()
+    step = pkg.GSRTrainStep(model, check_errors=True)
+    loss, err = step(lr, hr, U_hr_reduced=Uh)
+    U_lr = model.layer.U_lr
+    params = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in sd.items())
+    losses, errs = [], []
+    for s in range(B):
+        l, e, _ = O.train_loss(params, lr[s].cpu(), hr[s].cpu(), U=U_lr[s].cpu(), U_hr_reduced=Uh[s].cpu())
+        (l / B).backward()
+        losses.append(float(l)); errs.append(float(e))
+    assert float(loss) == pytest.approx(np.mean(losses), abs=5e-6)
+    assert float(err) == pytest.approx(np.mean(errs), abs=2e-6)
+    for k, p in model.named_parameters():
+        assert rel_fro(p.grad.cpu(), params[k].grad) < 2e-3, k
+
+
+@pytest.mark.parametrize("G", [2, 8])
+def test_subject_shards_reduce_to_the_one_gpu_gradient(setup, G):
+    """SURVEY section 4 shard emulation on one GPU: the batch split into G rank shards (shard_bounds), every shard's
+    gradients packed by FlatBucket.pack(1 / G) exactly as SubjectParallel.sync_gradients does, the flat buckets
+    summed (what the all-reduce computes) and unpacked -- must equal the gradient of the whole batch on one GPU."""
+    pkg, sd, model = setup
+    B = 16
+    lr, hr = _synth_batch(160, B, 51), _synth_batch(268, B, 52)
+    Uh = pkg.hr_target_basis(hr, 160)
+    step = pkg.GSRTrainStep(model)
+    model.zero_grad()
+    step(lr, hr, U_hr_reduced=Uh)
+    U_lr = model.layer.U_lr
+    g_one = [p.grad.clone() for p in model.parameters()]
+    total = None
+    for r in range(G):
+        lo, hi = pkg.shard_bounds(B, r, G)
+        assert hi - lo == B // G
+        model.zero_grad()
+        step(lr[lo:hi], hr[lo:hi], U_hr_reduced=Uh[lo:hi], U_lr=U_lr[lo:hi])
+        grads = [p.grad for p in model.parameters()]
+        bucket = pkg.kernels.FlatBucket(grads)
+        assert bucket.total == sum(p.numel() for p in model.parameters())
+        flat = bucket.pack(1.0 / G).clone()
+        total = flat if total is None else total + flat
+    bucket.flat.copy_(total)
+    bucket.unpack(1.0)
+    for a, p in zip(g_one, model.parameters()):
+        assert rel_fro(p.grad, a) < 2e-6
 
 
 @pytest.mark.gpu
