@@ -70,6 +70,7 @@ PROTOTYPES = {
     "gsr_flat_pack": (i32, [c_ptr, c_ptr, i32, c_ptr, i64, f32, c_ptr]),
     "gsr_flat_unpack": (i32, [c_ptr, c_ptr, i32, c_ptr, i64, f32, c_ptr]),
     "gsr_ffma_probe": (C.c_double, [i32, c_ptr, c_ptr]),
+    "gsr_tf32_probe": (C.c_double, [i32, c_ptr]),
     "gsr_adam_step": (i32, [c_ptr] * 5 + [i32, c_ptr, f32, f32, f32, f32, f32, c_ptr]),
     "gsr_bn_stats_f32": (i32, [c_ptr, i32, i32, c_ptr, c_ptr, c_ptr, c_ptr, f32, c_ptr]),
     "gsr_bn_act_fwd_f32": (i32, [c_ptr] * 5 + [f32, f32, C.c_ulonglong, i32, c_ptr, i32, i32, c_ptr]),

@@ -26,8 +26,25 @@ namespace gsr {
 namespace tc {
 
 int g_tma = 1;
+int g_utccp = 0;            // gsr_set_tuning("tcgemm_utccp", 0|1): K-major A through tcgen05.cp + tensor memory / from shared memory (default).
+                            // Measured (profiles/r2_tcgemm_tma_notes.txt): exact, and it removes 66 KB of the 252 KB of shared-memory
+                            // traffic per k-block, but the copies execute IN the tensor pipe, in order with the MMAs (8 x ~64 clk per
+                            // k-block): the MMA thread's issue -> commit time goes from 1.15 to 1.5 us and the stacked product from
+                            // 0.259 to 0.277 ms.  Kept as a switch.
+int g_mn_partial = 1;       // gsr_set_tuning("tcgemm_mn_partial", 0|1): MN-major B ranges may end inside a 32-column block (256 + 16)
 
 namespace t3 {
+
+#ifdef GSR_T3_TRACE
+// Pipeline trace (tools/tc3_trace.py builds a private copy of the library with -DGSR_T3_TRACE): cluster 1 stamps
+// %globaltimer at its pipeline events; slot layout [rank][role][k-block or tile][event].
+constexpr int TR_ITS = 64, TR_EVS = 12;
+__device__ unsigned long long g_trace[2 * 4 * TR_ITS * TR_EVS];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define T3_STAMP(role, it, ev) do { if ((blockIdx.x >> 1) == 1 && (it) < TR_ITS) g_trace[(((blockIdx.x & 1) * 4 + (role)) * TR_ITS + (it)) * TR_EVS + (ev)] = gtime(); } while (0)
+#else
+#define T3_STAMP(role, it, ev) do { } while (0)
+#endif
 
 constexpr int RAW_STAGES = 3, LO_STAGES = 2;
 constexpr int A_TILE = BM * BK * 4;                       // 16384
@@ -47,6 +64,10 @@ struct Plan {
     int splits;             // REDUCE: stride between the subjects of an item
     int M, N, K, nkb;
     int nr0, nr1;           // UMMA N of the two accumulator column ranges (nr1 may be 0)
+    int acc_base1;          // tensor-memory column of the odd tiles' accumulator (even tiles: 0); the two overlap when 2 (nr0 + nr1) > 512
+    int a_ring;             // tensor-memory column of the A-operand ring (tcgen05.cp, K-major A only); 0 = A is read from shared memory
+    int b_off1;             // byte offset of the second range inside a B tile
+    int b_bytes;            // bytes of this CTA's B tile per k-block (TMA transaction count)
     int a_batched, b_batched;
     float alpha;
     int epilogue;
@@ -67,6 +88,38 @@ __device__ __forceinline__ void tma_store(const CUtensorMap* map, uint32_t src, 
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory"); }
+
+// smem -> tensor memory copy of a 128-lane x 256-bit slice (8 fp32 columns) in both CTAs of the pair
+__device__ __forceinline__ void utccp2_128x256b(uint32_t taddr, uint32_t d_lo, uint32_t d_hi) {
+    asm volatile("{\n\t.reg .b64 da;\n\tmov.b64 da, {%1, %2};\n\ttcgen05.cp.cta_group::2.128x256b [%0], da;\n\t}"
+                 :: "r"(taddr), "r"(d_lo), "r"(d_hi) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void umma2_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], db, %4, p;\n\t}"
+                 :: "r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// tcgen05.ld without the wait, and a wait the compiler cannot move uses of the destination registers across
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
 
 // TA: op(A) = A^T (A stored [K][M], MN-major).  TB: op(B) = B^T (B stored [N][K], K-major).
 template <bool TA, bool TB, bool REDUCE>
@@ -91,7 +144,7 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const int total_tiles = p.items * p.tiles_m;
     const int R0 = p.nr0 >> 1, R1 = p.nr1 >> 1;                       // this CTA's share of the two B ranges
-    const uint32_t b_bytes = (uint32_t)(R0 + R1) * 128u;
+    const uint32_t b_bytes = (uint32_t)p.b_bytes;
     const int kb_per_tile = (REDUCE ? (p.nsub + p.splits - 1) / p.splits : 1) * p.nkb;   // upper bound, exact below
 
     if (tid == 0) {
@@ -123,7 +176,9 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
                     for (int kb = 0; kb < p.nkb; ++kb, ++it) {
                         const uint32_t s = it % RAW_STAGES, use = it / RAW_STAGES;
+                        T3_STAMP(0, it, 0);
                         if (use > 0) mbar_wait(bar_raw_empty + 8 * s, (use - 1) & 1);
+                        T3_STAMP(0, it, 1);
                         const uint32_t full = bar_raw_full + 8 * s;
                         mbar_expect_tx(full, (uint32_t)A_TILE + b_bytes);
                         const uint32_t a_dst = smem_u32(raw + s * SLOT_BYTES), b_dst = a_dst + A_TILE;
@@ -135,10 +190,11 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         }
                         if (TB) {                                                                   // boxes {32 k, R0 n}, {32 k, R1 n}
                             tma_load(b_dst, &mapB0, full, k0, R0 * (int)rank, bb);
-                            if (R1 > 0) tma_load(b_dst + R0 * 128, &mapB1, full, k0, p.nr0 + R1 * (int)rank, bb);
+                            if (R1 > 0) tma_load(b_dst + p.b_off1, &mapB1, full, k0, p.nr0 + R1 * (int)rank, bb);
                         } else {                                                                    // box {32 n, 32 k} per 32 columns
-                            for (int j = 0; j < R0 / 32; ++j) tma_load(b_dst + j * 4096, &mapB0, full, R0 * (int)rank + 32 * j, k0, bb);
-                            for (int j = 0; j < R1 / 32; ++j) tma_load(b_dst + R0 * 128 + j * 4096, &mapB0, full, p.nr0 + R1 * (int)rank + 32 * j, k0, bb);
+                            // (a range whose share is not a multiple of 32 columns uses the head of its last block only)
+                            for (int j = 0; j < (R0 + 31) / 32; ++j) tma_load(b_dst + j * 4096, &mapB0, full, R0 * (int)rank + 32 * j, k0, bb);
+                            for (int j = 0; j < (R1 + 31) / 32; ++j) tma_load(b_dst + p.b_off1 + j * 4096, &mapB0, full, p.nr0 + R1 * (int)rank + 32 * j, k0, bb);
                         }
                     }
                 }
@@ -155,36 +211,67 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint32_t a_dhi = TA ? desc_hi(512, 1) : desc_hi(1024, 2), b_dhi = TB ? desc_hi(1024, 2) : desc_hi(512, 1);
             const uint32_t a_lbo = TA ? 4096 : 16, b_lbo = TB ? 16 : 4096;
             const uint32_t a_step = (TA ? 1024u : 32u) >> 4, b_step = (TB ? 32u : 1024u) >> 4;
-            const uint32_t n1 = (uint32_t)(R0 * 128) >> 4;                  // start of the second range inside a B tile
-            uint32_t it = 0, tile_n = 0;
+            const uint32_t n1 = (uint32_t)p.b_off1 >> 4;                    // start of the second range inside a B tile
+            uint32_t it = 0, tile_n = 0, kstep_n = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++tile_n) {
                 const int z = tile / p.tiles_m;
                 const int nsub = REDUCE ? (p.nsub - z + p.splits - 1) / p.splits : 1;
-                if (tile_n > 0) { mbar_wait_cluster(bar_tmem_empty, (tile_n - 1) & 1); tc_fence_after(); }   // epilogues of both CTAs drained it
+                T3_STAMP(1, it, 3);
+                // every epilogue warp of both CTAs has read the columns tile t - 1 shares with this tile's accumulator
+                // (and, before that, all of tile t - 2, which used the same columns as this one)
+                if (tile_n > 0) { mbar_wait_cluster(bar_tmem_empty, (tile_n - 1) & 1); tc_fence_after(); }
+                T3_STAMP(1, it, 4);
+                // even tiles accumulate at column 0, odd tiles at acc_base1: the drain of tile t overlaps the MMAs of tile
+                // t + 1 (the epilogue releases the accumulator as soon as the columns the two share have been read)
+                const uint32_t tacc = tmem_base + ((tile_n & 1) ? (uint32_t)p.acc_base1 : 0u);
                 uint32_t acc = 0;
                 for (int sub = 0; sub < nsub; ++sub) {
                     for (int kb = 0; kb < p.nkb; ++kb, ++it) {
                         const uint32_t rs = it % RAW_STAGES, ls = it % LO_STAGES, luse = it / LO_STAGES;
+                        T3_STAMP(1, it, 0);
                         mbar_wait_cluster(bar_conv_full + 8 * ls, luse & 1);
                         tc_fence_after();
+                        T3_STAMP(1, it, 1);
                         const uint32_t hb = smem_u32(raw + rs * SLOT_BYTES), lb = smem_u32(lo + ls * SLOT_BYTES);
                         uint32_t ah = desc_lo(hb, a_lbo), al = desc_lo(lb, a_lbo);
                         uint32_t bh = desc_lo(hb + A_TILE, b_lbo), bl = desc_lo(lb + A_TILE, b_lbo);
                         const int ksteps = min(BK / 8, (p.K - kb * BK + 7) >> 3);
+                        if (!TA && p.a_ring) {
+                            // A through tensor memory: one tcgen05.cp per k-step and term moves the 128 x 8 slice of this
+                            // CTA's rows (both CTAs of the pair execute it) into 8 columns; the six MMAs of the k-step then
+                            // read A there instead of re-reading 6 x 4 KB of shared memory.  cp and mma execute in issue
+                            // order (tools/probes/utccp_probe.cu: a ring of two slots reused every other k-step is exact).
+                            for (int j = 0; j < ksteps; ++j, ++kstep_n) {
+                                const uint32_t t_hi = tmem_base + (uint32_t)p.a_ring + 16u * (kstep_n % 3u), t_lo = t_hi + 8u;
+                                utccp2_128x256b(t_hi, ah, a_dhi);
+                                utccp2_128x256b(t_lo, al, a_dhi);
+                                umma2_tf32_ts(tacc, t_lo, bh, b_dhi, idesc0, acc);
+                                umma2_tf32_ts(tacc, t_hi, bl, b_dhi, idesc0, 1u);
+                                umma2_tf32_ts(tacc, t_hi, bh, b_dhi, idesc0, 1u);
+                                if (p.nr1 > 0) {
+                                    umma2_tf32_ts(tacc + p.nr0, t_lo, bh + n1, b_dhi, idesc1, acc);
+                                    umma2_tf32_ts(tacc + p.nr0, t_hi, bl + n1, b_dhi, idesc1, 1u);
+                                    umma2_tf32_ts(tacc + p.nr0, t_hi, bh + n1, b_dhi, idesc1, 1u);
+                                }
+                                acc = 1u;
+                                ah += a_step; al += a_step; bh += b_step; bl += b_step;
+                            }
+                        } else
                         for (int j = 0; j < ksteps; ++j) {
-                            umma2_tf32(tmem_base, al, a_dhi, bh, b_dhi, idesc0, acc);              // small terms first
-                            umma2_tf32(tmem_base, ah, a_dhi, bl, b_dhi, idesc0, 1u);
-                            umma2_tf32(tmem_base, ah, a_dhi, bh, b_dhi, idesc0, 1u);
+                            umma2_tf32(tacc, al, a_dhi, bh, b_dhi, idesc0, acc);                  // small terms first
+                            umma2_tf32(tacc, ah, a_dhi, bl, b_dhi, idesc0, 1u);
+                            umma2_tf32(tacc, ah, a_dhi, bh, b_dhi, idesc0, 1u);
                             if (p.nr1 > 0) {
-                                umma2_tf32(tmem_base + p.nr0, al, a_dhi, bh + n1, b_dhi, idesc1, acc);
-                                umma2_tf32(tmem_base + p.nr0, ah, a_dhi, bl + n1, b_dhi, idesc1, 1u);
-                                umma2_tf32(tmem_base + p.nr0, ah, a_dhi, bh + n1, b_dhi, idesc1, 1u);
+                                umma2_tf32(tacc + p.nr0, al, a_dhi, bh + n1, b_dhi, idesc1, acc);
+                                umma2_tf32(tacc + p.nr0, ah, a_dhi, bl + n1, b_dhi, idesc1, 1u);
+                                umma2_tf32(tacc + p.nr0, ah, a_dhi, bh + n1, b_dhi, idesc1, 1u);
                             }
                             acc = 1u;
                             ah += a_step; al += a_step; bh += b_step; bl += b_step;
                         }
                         umma_commit2(bar_raw_empty + 8 * rs);                // both CTAs: raw slot free once these MMAs retire
                         umma_commit2(bar_lo_empty + 8 * ls);                 //            lo slot free
+                        T3_STAMP(1, it, 2);
                     }
                 }
                 umma_commit2(bar_tmem_full);                                 // accumulator of this tile complete
@@ -195,7 +282,7 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ===== converters: lo = tf32(x - trunc(x)), shared memory -> shared memory at the same offset
         const int ct = tid - 64;                                             // 0 .. 255
         const uint32_t conv_leader = map_to_cta(bar_conv_full, 0);
-        const int b_vec = (R0 + R1) * 8;                                     // float4s of this CTA's B tile
+        const int b_vec = p.b_bytes >> 4;                                    // float4s of this CTA's B tile
         uint32_t it = 0;
         for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
             const int z = tile / p.tiles_m;
@@ -204,7 +291,9 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint32_t rs = it % RAW_STAGES, ruse = it / RAW_STAGES, ls = it % LO_STAGES, luse = it / LO_STAGES;
                 const float4* src = reinterpret_cast<const float4*>(raw + rs * SLOT_BYTES);
                 float4* dst = reinterpret_cast<float4*>(lo + ls * SLOT_BYTES);
+                if (ct == 0) T3_STAMP(2, it, 0);
                 mbar_wait(bar_raw_full + 8 * rs, ruse & 1);                  // TMA bytes of this CTA landed
+                if (ct == 0) T3_STAMP(2, it, 1);
                 float4 v[9];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) v[i] = src[ct + 256 * i];                               // A: 1024 float4
@@ -214,6 +303,7 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     v[4 + i] = e < b_vec ? src[A_TILE / 16 + e] : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 if (luse > 0) mbar_wait(bar_lo_empty + 8 * ls, (luse - 1) & 1);                     // MMA drained the lo slot
+                if (ct == 0) T3_STAMP(2, it, 2);
 #pragma unroll
                 for (int i = 0; i < 9; ++i) {
                     float4 x = v[i], l;
@@ -227,6 +317,7 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 fence_async_smem();                                          // generic-proxy writes -> async proxy (UMMA)
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(conv_leader + 8 * ls);    // the leader's conv_full counts the warps of both CTAs
+                if (ct == 0) T3_STAMP(2, it, 3);
             }
         }
     } else {
@@ -235,55 +326,78 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         uint8_t* my_stg = stg + (warp - 2 - CONV_WARPS) * 2 * STG_BYTES;
         const uint32_t empty_leader = map_to_cta(bar_tmem_empty, 0);
         const int chunks = (p.N + 31) >> 5;
+        const int npad = p.nr0 + p.nr1;
+        // chunks of an even tile (accumulator at column 0) that lie in the columns the next (odd) tile accumulates
+        // into are drained first: [acc_base1 / 32, chunks); an odd tile shares its first (npad - acc_base1) columns
+        const int even_first = min(chunks, p.acc_base1 >> 5);
+        const int even_cnt = chunks - even_first, odd_cnt = min(chunks, (max(npad - p.acc_base1, 0) + 31) >> 5);
         uint32_t tile_n = 0, nstore = 0;
         for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++tile_n) {
             const int z = tile / p.tiles_m, mp = tile - z * p.tiles_m;
-            const int row = mp * 256 + (int)rank * BM + q * 32 + lane;       // output row of this thread
+            const int row0 = mp * 256 + (int)rank * BM + q * 32;             // first output row of this warp
             const float* extra_row = nullptr;
-            if (!REDUCE && p.epilogue == GSR_EPI_ADD) extra_row = p.extra + (size_t)z * p.s_extra + (size_t)row * p.ld_extra;
+            if (!REDUCE && p.epilogue == GSR_EPI_ADD) extra_row = p.extra + (size_t)z * p.s_extra + (size_t)(row0 + lane) * p.ld_extra;
             const float alpha = REDUCE ? 1.0f : p.alpha;
             const int epi = REDUCE ? GSR_EPI_NONE : p.epilogue;
-            mbar_wait(bar_tmem_full, tile_n & 1);
-            tc_fence_after();
-            for (int c = 0; c < chunks; ++c, ++nstore) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-                if (c == chunks - 1) {                                       // accumulator fully read by this warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(empty_leader);
-                }
-                float f[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * alpha;
+            const bool odd = tile_n & 1;
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (odd ? (uint32_t)p.acc_base1 : 0u);
+            const int first_cnt = odd ? odd_cnt : even_cnt;
+            auto chunk_at = [&](int i) { return odd ? i : (i < even_cnt ? even_first + i : i - even_cnt); };
+            auto release = [&]() {                                           // this warp is done with the shared columns
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(empty_leader);
+                if (q == 0 && lane == 0) T3_STAMP(3, tile_n, 2);
+            };
+            auto emit = [&](uint32_t (&v)[32], int c) {                      // alpha / bias / addend, staging block, TMA store
                 const int n0 = c * 32;
-                if (epi == GSR_EPI_BIAS) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        if (n0 + i < p.N) {                                  // N % 4 == 0 (launcher)
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.extra + n0 + i));
-                            f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-                        }
-                    }
-                } else if (epi == GSR_EPI_ADD) {
-                    if (row < p.M) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            if (n0 + i < p.N) {
-                                const float4 a4 = __ldg(reinterpret_cast<const float4*>(extra_row + n0 + i));
-                                f[i] += a4.x; f[i + 1] += a4.y; f[i + 2] += a4.z; f[i + 3] += a4.w;
-                            }
-                        }
-                    }
-                }
                 uint8_t* blk = my_stg + (nstore & 1) * STG_BYTES;
                 if (nstore >= 2) { if (lane == 0) tma_wait_read<1>(); __syncwarp(); }     // the store that last read this block is done
 #pragma unroll
-                for (int j = 0; j < 8; ++j)                                  // row = lane; 16-byte chunk j at (j ^ (lane & 7)): conflict free
-                    *reinterpret_cast<float4*>(blk + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                for (int j = 0; j < 8; ++j) {                                // row = lane; 16-byte chunk j at (j ^ (lane & 7)): conflict free
+                    float4 f = make_float4(__uint_as_float(v[4 * j]) * alpha, __uint_as_float(v[4 * j + 1]) * alpha,
+                                           __uint_as_float(v[4 * j + 2]) * alpha, __uint_as_float(v[4 * j + 3]) * alpha);
+                    if (epi != GSR_EPI_NONE && n0 + 4 * j < p.N) {           // N % 4 == 0 (launcher)
+                        const float4 e4 = __ldg(reinterpret_cast<const float4*>((epi == GSR_EPI_BIAS ? p.extra : extra_row) + n0 + 4 * j));
+                        f.x += e4.x; f.y += e4.y; f.z += e4.z; f.w += e4.w;
+                    }
+                    *reinterpret_cast<float4*>(blk + lane * 128 + ((j ^ (lane & 7)) << 4)) = f;
+                }
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) { tma_store(&mapC, smem_u32(blk), n0, mp * 256 + (int)rank * BM + q * 32, z); tma_commit(); }
+                if (lane == 0) { tma_store(&mapC, smem_u32(blk), n0, row0, z); tma_commit(); }
+                ++nstore;
+            };
+            if (q == 0 && lane == 0) T3_STAMP(3, tile_n, 0);
+            mbar_wait(bar_tmem_full, tile_n & 1);
+            tc_fence_after();
+            if (q == 0 && lane == 0) T3_STAMP(3, tile_n, 1);
+            if (first_cnt == 0) release();
+            // two register sets: the tensor-memory load of chunk i + 1 is in flight while chunk i is staged and stored;
+            // the first two chunks (drain order) are both read before anything is staged, so that the accumulator is
+            // released a load latency after it completes when the shared columns are <= 2 chunks (K-major B)
+            uint32_t va[32], vb[32];
+            tmem_ld32_async(tacc + (uint32_t)(chunk_at(0) * 32), va);
+            if (chunks > 1) tmem_ld32_async(tacc + (uint32_t)(chunk_at(1) * 32), vb);
+            tmem_ld_wait(va);
+            if (chunks > 1) tmem_ld_wait(vb);
+            if (first_cnt == 1 || first_cnt == 2) release();
+            for (int i = 0; i < chunks; i += 2) {
+                // here: va = chunk i, vb = chunk i + 1 (if it exists), both complete
+                emit(va, chunk_at(i));
+                if (q == 0 && lane == 0 && i < 9) T3_STAMP(3, tile_n, 3 + i);
+                if (i + 2 < chunks) tmem_ld32_async(tacc + (uint32_t)(chunk_at(i + 2) * 32), va);
+                if (i + 1 < chunks) {
+                    emit(vb, chunk_at(i + 1));
+                    if (q == 0 && lane == 0 && i + 1 < 9) T3_STAMP(3, tile_n, 3 + i + 1);
+                }
+                if (i + 3 < chunks) tmem_ld32_async(tacc + (uint32_t)(chunk_at(i + 3) * 32), vb);
+                if (i + 2 < chunks) {
+                    tmem_ld_wait(va);
+                    if (i + 3 == first_cnt) release();
+                    if (i + 3 < chunks) tmem_ld_wait(vb);
+                    if (i + 4 == first_cnt) release();
+                }
             }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -326,13 +440,47 @@ static bool make_map(CUtensorMap* m, const float* base, long long cols, long lon
                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Measurement aid (gsr_tf32_probe): every CTA pair issues `iters` x 4 tcgen05.mma.cta_group::2 kind::tf32 of
+// M 256 x N 256 x K 8 on one resident (zeroed) stage -- the issue rate of the tensor pipe with no operand traffic.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) tf32_probe_kernel(int iters) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t rank = cluster_rank();
+    for (int e = tid; e < 2 * 128 * 32; e += 128) reinterpret_cast<float*>(smem)[e] = 0.f;
+    if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    fence_async_smem();
+    if (warp == 0) tmem_alloc2(smem_u32(&slot), 256);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&slot);
+    if (rank == 0 && tid == 0) {
+        const uint32_t idesc = instr_desc2(256, 0, 0), dhi = desc_hi(1024, 2);
+        const uint32_t a0 = desc_lo(smem_u32(smem), 16), b0 = desc_lo(smem_u32(smem + 128 * 32 * 4), 16);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) umma2_tf32(tmem, a0 + 2 * j, dhi, b0 + 2 * j, dhi, idesc, 1u);
+        }
+        umma_commit2(smem_u32(&bar));
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) tmem_dealloc2(tmem, 256);
+}
+
 }  // namespace t3
 
 bool tma_ok(const Params& p, int transA, int transB) {
     (void)transA;
     if (!g_tma || !t3::encode_fn()) return false;
     if (p.M < 256 || p.K < 1 || p.N % 4 != 0) return false;
-    if (transB ? p.N > 272 : p.N > 320) return false;
+    if (p.N > 272) return false;
     if (p.lda % 4 || p.ldb % 4 || p.ldc % 4 || p.sA % 4 || p.sB % 4 || p.sC % 4) return false;
     if (!aligned16(p.A) || !aligned16(p.B) || !aligned16(p.C)) return false;
     if (p.epilogue != GSR_EPI_NONE && !aligned16(p.extra)) return false;
@@ -348,13 +496,28 @@ int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, c
     pl.nsub = reduce ? p.batch : 1;
     pl.splits = reduce ? p.splits : 1;
     pl.M = p.M; pl.N = p.N; pl.K = p.K; pl.nkb = (p.K + BK - 1) / BK;
-    if (transB) {                                   // K-major B: 8-row granularity per CTA
-        const int npad = (p.N + 15) & ~15;
-        if (npad <= 256) { pl.nr0 = npad; pl.nr1 = 0; } else { pl.nr0 = 160; pl.nr1 = npad - 160; }
-    } else {                                        // MN-major B: 32-column blocks per CTA
+    // Accumulator column ranges: UMMA N <= 256 per instruction, N / 2 per CTA a multiple of 8.  K-major B: 160 + 112 for
+    // the 268-wide products (the split round 1 probed).  MN-major B lives in 32-column blocks (SWIZZLE_128B_BASE32B
+    // atoms); a range may end inside a block -- 256 + 16 for 268 columns, the second range reading the first 8 columns
+    // of one block per CTA -- unless gsr_set_tuning("tcgemm_mn_partial", 0) restores whole blocks (192 + 128).
+    const int npad16 = (p.N + 15) & ~15;
+    if (transB) {
+        if (npad16 <= 256) { pl.nr0 = npad16; pl.nr1 = 0; } else { pl.nr0 = 160; pl.nr1 = npad16 - 160; }
+    } else if (g_mn_partial) {
+        if (npad16 <= 256) { pl.nr0 = npad16; pl.nr1 = 0; } else { pl.nr0 = 256; pl.nr1 = npad16 - 256; }
+    } else {
         const int npad = (p.N + 63) & ~63;
         if (npad <= 256) { pl.nr0 = npad; pl.nr1 = 0; } else { pl.nr0 = 192; pl.nr1 = npad - 192; }
     }
+    {
+        const int r0 = pl.nr0 / 2, r1 = pl.nr1 / 2;
+        if (transB) { pl.b_off1 = r0 * 128; pl.b_bytes = (r0 + r1) * 128; }
+        else { pl.b_off1 = ((r0 + 31) / 32) * 4096; pl.b_bytes = pl.b_off1 + ((r1 + 31) / 32) * 4096; }
+    }
+    // Tensor-memory plan: even tiles accumulate at column 0, odd tiles at acc_base1, the A ring (3 k-steps x (8 hi + 8 lo)
+    // columns) behind them: 272 columns -> [0, 272) / [192, 464) / ring at 464; <= 232 columns -> no overlap at all
+    pl.a_ring = (!transA && g_utccp) ? TMEM_COLS - 48 : 0;
+    pl.acc_base1 = std::min(256, ((pl.a_ring ? pl.a_ring : TMEM_COLS) - (pl.nr0 + pl.nr1)) & ~31);
     pl.a_batched = p.sA != 0; pl.b_batched = p.sB != 0;
     pl.alpha = p.alpha; pl.epilogue = p.epilogue; pl.extra = p.extra; pl.ld_extra = p.ld_extra; pl.s_extra = p.s_extra;
     const int R0 = pl.nr0 / 2, R1 = pl.nr1 / 2;
@@ -399,3 +562,19 @@ int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, c
 
 }  // namespace tc
 }  // namespace gsr
+
+#ifdef GSR_T3_TRACE
+extern "C" __attribute__((visibility("default"))) int gsr_tcgemm3_trace_read(unsigned long long* host, int count) {
+    return (int)cudaMemcpyFromSymbol(host, gsr::tc::t3::g_trace, sizeof(unsigned long long) * count);
+}
+#endif
+
+extern "C" double gsr_tf32_probe(int iters, void* stream) {
+    using namespace gsr;
+    if (iters <= 0) return 0.0;
+    const int smem = 2 * 128 * 32 * 4 + 1024;
+    if (cudaFuncSetAttribute(tc::t3::tf32_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 0.0;
+    tc::t3::tf32_probe_kernel<<<kNumSMs, 128, smem, (cudaStream_t)stream>>>(iters);
+    if (launched("tf32_probe")) return 0.0;
+    return (double)(kNumSMs / 2) * iters * 4.0 * 2.0 * 256.0 * 256.0 * 8.0;
+}

@@ -308,6 +308,10 @@ GSR_API int gsr_adam_step(float* const* params, const float* const* grads, float
  * and returns the flops it executes; timed by the caller with CUDA events to obtain the
  * FP32 SIMT peak that bounds the contraction kernels (bench.py roofline).           */
 GSR_API double gsr_ffma_probe(int iters, float* scratch, void* stream);
+/* The same for the tensor pipe: every CTA pair (74 per B200) issues iters x 4 tcgen05.mma.cta_group::2 kind::tf32 of
+ * M 256 x N 256 x K 8 on resident operands; returns the dense TF32 flops executed.  The fp32-accurate (3xTF32)
+ * contraction kernels issue three such MMAs per algorithmic product: their ceiling is a third of this rate.        */
+GSR_API double gsr_tf32_probe(int iters, void* stream);
 
 #ifdef __cplusplus
 }
