@@ -2,6 +2,7 @@
 """bench.py -- GSR-Net fwd+bwd subjects/s (LR 160 -> HR 268) on N B200s of one node.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+                    [--scaling weak|strong] [--folds F] [--e2e-format vector|matrix]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one training step of the reference's loop (utils/gsr_train.py:23-46) over a batch
@@ -10,7 +11,10 @@ GSR layer, two graph convolutions, the three-term L1 loss, the full backward, th
 all-reduce (N > 1) and the Adam update, captured once in a CUDA graph (GraphedTrainStep) and
 replayed; --no-graph launches every kernel from Python.  `value` = subjects of all ranks /
 max-over-ranks device time, inputs resident in HBM.  `e2e` = the same step through the public API with the
-LR / HR batches coming from pinned host memory and the loss read back, every step.
+LR / HR batches coming from pinned host memory -- as vectorised upper triangles, the dataset's on-disk form, rebuilt on
+the device by gsr_anti_vectorize (utils/preprocessing.py:72-73) -- and the loss read back, every step.
+--scaling strong keeps the GLOBAL batch at --batch (1024 subjects over all ranks); --folds F trains F independent
+cross-validation models on disjoint rank groups (BASELINE configs[2]; training_gsr.ipynb:88-96).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -52,6 +56,12 @@ def parse():
                     help="torch: torch.optim.Adam(fused=True) (default); flat: the library's gsr_adam_step (pkg.FlatAdam)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=None, help="subjects in the CPU baseline sample")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch subjects per GPU (default); strong: --batch subjects over all GPUs")
+    ap.add_argument("--folds", type=int, default=0, help="F > 0: fold-parallel cross-validation, F independent models on disjoint rank groups")
+    ap.add_argument("--e2e-format", default="vector", choices=["vector", "matrix"],
+                    help="what the end-to-end loop ships per step: vectorised upper triangles (default) or full matrices")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     return ap.parse_args()
 
 
@@ -152,6 +162,77 @@ def oracle_step_seconds(n_subjects: int, threads: int, with_adam: bool = True):
     return time.perf_counter() - t0
 
 
+def oracle_gpu_eager_seconds(n_subjects: int):
+    """The same per-subject training step (oracle port, op for op the reference's eager PyTorch graph: padded mat-muls,
+    diag-matmul normalisation, torch.linalg.eigh per subject, torch.optim.Adam) with every tensor on the B200: the
+    reference as it runs today with `device = cuda` (utils/gsr_train.py:12-13) -- cuBLAS / cuSOLVER / ATen kernels, none
+    of this library's.  A BASELINE leg like cpu_baseline; the product never routes through it."""
+    import torch
+    from collections import OrderedDict
+    from oracle import gsr_oracle as O
+    dev = torch.device("cuda", torch.cuda.current_device())
+    sd = O.make_state_dict(0)
+    params = OrderedDict((k, v.clone().to(dev).requires_grad_(True)) for k, v in sd.items())
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+    lrs = [O.synth_connectome(LR_DIM, 1000 + s).to(dev) for s in range(min(n_subjects, 16))]
+    hrs = [O.synth_connectome(HR_DIM, 1500 + s).to(dev) for s in range(min(n_subjects, 16))]
+
+    def one(s):
+        opt.zero_grad()
+        loss, err, _ = O.train_loss(params, lrs[s % len(lrs)], hrs[s % len(hrs)])
+        loss.backward()
+        opt.step()
+        return float(loss.detach()) + float(err.detach())          # the two .item() reads of utils/gsr_train.py:48-49
+
+    with torch.device(dev):                 # torch.eye / zeros inside the oracle land on the GPU, as the reference's `.to(device)` calls do
+        one(0); one(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(n_subjects):
+            one(s)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+
+def bind_to_gpu_numa_node(local_gpu: int):
+    """Pin this process to the CPUs NVML reports as local to its GPU BEFORE it allocates pinned host buffers, so that the
+    staging memory of every rank lives on the NUMA node its GPU's PCIe root hangs off.  Returns a note for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_gpu)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and 64 * w + b < ncpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"process bound to the {len(cpus)} CPUs local to GPU {local_gpu} (NVML) before the pinned buffers were allocated"
+    except Exception as e:          # noqa: BLE001 -- affinity is an optimisation, never a failure
+        return f"no NUMA binding ({type(e).__name__})"
+    return "no NUMA binding (empty affinity mask)"
+
+
+def ncu_traffic(summary_file: str, kernel_substr: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes) of the first launch of `kernel_substr` in a committed
+    profiles/*.txt summary (tools/ncu_summary.py output), or None."""
+    try:
+        lines = open(os.path.join(ROOT, "profiles", summary_file)).read().splitlines()
+    except OSError:
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    inside, got = False, {}
+    for ln in lines:
+        if ln.startswith("== "):
+            if inside and len(got) == 2:
+                break
+            inside, got = kernel_substr in ln, {}
+        elif inside and ln.startswith("dram__bytes_"):
+            key, rest = ln.split(" = ")
+            val, u = rest.split()[:2]
+            got[key.strip()] = float(val.replace(",", "")) * unit.get(u, 1.0)
+    return sum(got.values()) if len(got) == 2 else None
+
+
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the path (oracle port --
     /root/reference does not exist on the GPU box), all host threads, rank 0 only."""
@@ -213,7 +294,13 @@ def run_ours(args):
     if args.gemm_variant is not None:
         pkg.set_tuning("gemm_variant", args.gemm_variant)
 
-    B = args.batch
+    numa_note = bind_to_gpu_numa_node(local)
+    if args.scaling == "strong":
+        if args.batch % world:
+            raise SystemExit(f"bench.py --scaling strong: --batch {args.batch} is not divisible by {world} GPUs")
+        B = args.batch // world            # the GLOBAL batch is fixed; every rank takes its shard (shard_bounds)
+    else:
+        B = args.batch
     torch.manual_seed(0)
     model = pkg.GSRNet([0.9, 0.7, 0.6, 0.5], Args()).to(dev)
     sp = pkg.SubjectParallel(model) if world > 1 else None
@@ -312,14 +399,23 @@ def run_ours(args):
     value = world * B * args.steps / (elapsed_ms / 1e3)
 
     # ---- end to end: pinned host buffers -> device -> step -> loss back, every step.
-    # Double-buffered as a training loop over a host-resident dataset would be: the H2D copy of
-    # step i+1 runs on a copy stream while step i computes; every step's inputs are copied inside
-    # the timed region and every step's loss is read back to pinned host memory.
-    lr_host = lr.cpu().pin_memory()
-    hr_host = hr.cpu().pin_memory()
+    # Double-buffered as a training loop over a host-resident dataset would be: the H2D copy of step i+1 runs on a copy
+    # stream while step i computes; every step's inputs are copied inside the timed region and every step's loss is read
+    # back to pinned host memory.  Default format: the vectorised upper triangles the challenge data comes as
+    # (12 720 + 35 778 floats per subject, half the bytes of the matrices); gsr_anti_vectorize rebuilds the symmetric
+    # zero-diagonal matrices on the device, exactly what the reference's loader does per CSV row
+    # (utils/preprocessing.py:72-73), straight into the input buffers of the captured step.
+    vec_fmt = args.e2e_format == "vector"
+    if vec_fmt:
+        lr_src, hr_src = K.triu_flatten(lr), K.triu_flatten(hr)             # [B, 12720], [B, 35778]
+        assert torch.equal(K.anti_vectorize(lr_src, LR_DIM), lr) and torch.equal(K.anti_vectorize(hr_src, HR_DIM), hr)
+    else:
+        lr_src, hr_src = lr, hr
+    lr_host = lr_src.cpu().pin_memory()
+    hr_host = hr_src.cpu().pin_memory()
     if use_graph:
-        # the two input-buffer sets of the graphed step are the double buffer: the copy stream writes set (i + 1) % 2
-        # from pinned host memory while the graph captured on set i % 2 replays
+        # the two input-buffer sets of the graphed step are the double buffer: set (i + 1) % 2 is filled from pinned host
+        # memory while the graph captured on set i % 2 replays
         lr_dev = [graphed.inputs(0)[0], graphed.inputs(1)[0]]
         hr_dev = [graphed.inputs(0)[1], graphed.inputs(1)[1]]
         if U_hr is not None:
@@ -327,9 +423,12 @@ def run_ours(args):
     else:
         lr_dev = [torch.empty_like(lr), torch.empty_like(lr)]
         hr_dev = [torch.empty_like(hr), torch.empty_like(hr)]
+    lr_stage = [torch.empty_like(lr_src), torch.empty_like(lr_src)] if vec_fmt else lr_dev
+    hr_stage = [torch.empty_like(hr_src), torch.empty_like(hr_src)] if vec_fmt else hr_dev
+    U_host = U_hr.cpu().pin_memory() if U_hr is not None else None
     copy_stream = torch.cuda.Stream()
 
-    def e2e_run(nsteps):
+    def e2e_run(nsteps, copy_basis=False):
         loss_host = torch.empty((nsteps,), dtype=torch.float32).pin_memory()
         ev_copy = [torch.cuda.Event(), torch.cuda.Event()]
         ev_done = [torch.cuda.Event(), torch.cuda.Event()]
@@ -340,8 +439,10 @@ def run_ours(args):
             with torch.cuda.stream(copy_stream):
                 if i >= 2:
                     copy_stream.wait_event(ev_done[buf])          # step i-2 has consumed this buffer
-                lr_dev[buf].copy_(lr_host, non_blocking=True)
-                hr_dev[buf].copy_(hr_host, non_blocking=True)
+                lr_stage[buf].copy_(lr_host, non_blocking=True)
+                hr_stage[buf].copy_(hr_host, non_blocking=True)
+                if copy_basis and use_graph and U_host is not None:
+                    graphed.inputs(buf)[2].copy_(U_host, non_blocking=True)
                 ev_copy[buf].record(copy_stream)
 
         issue_copy(0)
@@ -350,6 +451,9 @@ def run_ours(args):
             if i + 1 < nsteps:
                 issue_copy(i + 1)
             main.wait_event(ev_copy[buf])
+            if vec_fmt:                                           # two launches: vectors -> the step's input matrices
+                K.anti_vectorize(lr_stage[buf], LR_DIM, out=lr_dev[buf])
+                K.anti_vectorize(hr_stage[buf], HR_DIM, out=hr_dev[buf])
             if use_graph:
                 loss, _ = graphed.replay(buf)
                 ev_done[buf].record(main)
@@ -360,18 +464,25 @@ def run_ours(args):
         main.synchronize()
         return loss_host
 
-    e2e_run(2)
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    e2e_losses = e2e_run(args.steps)
-    e3.record()
-    barrier()
-    assert bool(torch.isfinite(e2e_losses).all())
-    t = torch.tensor([e2.elapsed_time(e3)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / (float(t) / 1e3)
+    def e2e_timed(copy_basis):
+        e2e_run(2, copy_basis)
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        losses = e2e_run(args.steps, copy_basis)
+        e3.record()
+        barrier()
+        assert bool(torch.isfinite(losses).all())
+        t = torch.tensor([e2.elapsed_time(e3)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * B * args.steps / (float(t) / 1e3)
+
+    e2e_value = e2e_timed(False)
+    # a dataset of more than one batch: the data-only HR-target basis is either cached on the device (172 KB per subject;
+    # the default above), recomputed in the step (`with_hr_target_eigh_in_step`), or shipped with the batch -- this variant:
+    e2e_basis_value = e2e_timed(True) if (use_graph and U_host is not None) else None
+    h2d_per_rank = (lr_host.numel() + hr_host.numel()) * 4
 
     # ---- the same step with the HR-target eigendecomposition recomputed inside it, as utils/gsr_train.py:33-36
     #      literally does (2 steps; reported next to the headline, which hoists that data-only computation)
@@ -411,6 +522,29 @@ def run_ours(args):
         if it:
             ffma_best = max(ffma_best, flops / (a.elapsed_time(b) * 1e-3) / 1e12)
 
+    # ---- dense TF32 rate of the tensor pipe on this GPU (resident operands, no traffic): the measured denominator of the
+    #      3xTF32 contraction kernels (three MMAs per algorithmic product -> their ceiling is a third of it)
+    tf32_best = 0.0
+    for it in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        flops = pkg.lib().gsr_tf32_probe(8192, torch.cuda.current_stream().cuda_stream)
+        b.record()
+        torch.cuda.synchronize()
+        if it:
+            tf32_best = max(tf32_best, flops / (a.elapsed_time(b) * 1e-3) / 1e12)
+
+    # ---- the reference's eager PyTorch graph on this same B200 (cuBLAS / cuSOLVER / ATen; per-subject loop): the
+    #      "existing kernels" bar next to the CPU arm
+    gpu_eager = None
+    if world == 1 and rank == 0 and not args.no_gpu_eager_baseline:
+        n_eager = 48
+        secs = oracle_gpu_eager_seconds(n_eager)
+        gpu_eager = {"value": n_eager / secs, "unit": "subjects/s", "kind": "port on cuda",
+                     "sample": f"{n_eager} subjects, per-subject fwd+bwd+Adam incl. both torch.linalg.eigh calls "
+                               f"(utils/gsr_train.py:23-46 restated in oracle/, every tensor on the GPU: eager PyTorch / cuBLAS / "
+                               f"cuSOLVER kernels, none of this library's)"}
+
     def finish():
         # N > 1: the captured graph holds the communicator's all-reduce; tearing the process group down with it
         # alive was observed to block at exit.  Release the graph, meet the other ranks and leave without the
@@ -440,27 +574,35 @@ def run_ours(args):
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     # --- contraction kernel: tensor-bound.  tcgen05 kind::tf32 runs at half the bf16 rate and the 3xTF32 split
     #     issues three MMAs per algorithmic product, both stated so that `frac` is against the MEASURED bf16 peak.
+    tf32_peak = tf32_best if tf32_best > 0 else bf16_peak / 2.0
+    tma_on = backend == "tc"
+    traffic = ncu_traffic("r2_ncu_summary_tcgemm3.txt", "tcgemm3_kernel") if backend == "tc" else None
     gemm_roof = {
-        "kernel": ("gsr::tc::tcgemm2_kernel (tcgen05.mma.cta_group::2 kind::tf32, 3xTF32 split, CTA pair on a 256x272x32 tile, "
-                   "each CTA stages its 128 rows of A and half of B, accumulators in TMEM; odd last tile of 268 on the "
-                   "one-CTA gsr::tc::tcgemm_kernel, 128x288x32)"
+        "kernel": ("gsr::tc::t3::tcgemm3_kernel (persistent CTA pairs, tcgen05.mma.cta_group::2 kind::tf32, 3xTF32: operands by "
+                   "cp.async.bulk.tensor into SWIZZLE_128B / 128B_ATOM_32B tiles, the raw fp32 tile is the hi term, converter warps "
+                   "write lo, two overlapping accumulators in TMEM, TMA-store epilogue; 256 x 272 x 32 tiles) + the FP32 "
+                   "ragged-row kernels for rows 256..267 and the one-CTA gsr::tc::tcgemm_kernel for M < 256"
                    if backend == "tc" else "gsr::bgemm_kernel (136x136x16 SIMT FP32 tile)"),
         "bound": "tensor" if backend == "tc" else "fp32",
         "achieved": gemm_tflops, "unit": "TFLOP/s (algorithmic fp32 flops of the contractions)",
         "peak": bf16_peak if backend == "tc" else ffma_best,
         "frac": (gemm_tflops / (bf16_peak if backend == "tc" else ffma_best)) if gemm_tflops else None,
-        "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the step); TF32 peak is half of it "
-                        "and 3xTF32 needs 3 MMAs per product, so the fp32-accurate ceiling of this kernel is peak/6"
+        "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the step).  kind::tf32 runs at half the "
+                        "bf16 rate and the fp32-accurate 3xTF32 split issues three MMAs per product: see tf32_measured / "
+                        "frac_of_3xtf32_ceiling for the denominators this kernel can actually reach"
                         if backend == "tc" else "FP32 FFMA probe kernel measured in this run"),
-        "frac_of_3xtf32_ceiling": (gemm_tflops / (bf16_peak / 6.0)) if (gemm_tflops and backend == "tc") else None,
+        "tf32_measured_tflops": tf32_best if tma_on else None,
+        "tf32_measured_how": "gsr_tf32_probe in this run: 74 CTA pairs x 32768 tcgen05.mma.cta_group::2 kind::tf32 (M256 N256 K8) on "
+                             "resident zero operands (no operand traffic, so an upper bound under the power cap), best of 4",
+        "frac_of_measured_tf32": (gemm_tflops / tf32_peak) if (gemm_tflops and tma_on) else None,
+        "frac_of_3xtf32_ceiling": (gemm_tflops / (tf32_peak / 3.0)) if (gemm_tflops and tma_on) else None,
+        "frac_of_3xtf32_ceiling_bf16_derived": (gemm_tflops / (bf16_peak / 6.0)) if (gemm_tflops and tma_on) else None,
         "share_of_step": gemm_ms / elapsed_ms if elapsed_ms else None, "launches": gemm_launches,
         "algorithmic_flop_per_subject": GEMM_FLOP_PER_SUBJECT_FWD_BWD,
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE per-subject launch (rows 0..255 of 1024 TN products, CTA pairs)
-        # inside the step, from the committed ncu --set full capture; the algorithmic bytes of that launch are
-        # 1024 x (256 x 268 + 268 x 268 + 256 x 268) x 4 B = 856 MB (part of the operands is still L2 resident from the
-        # producing kernel, and the output is written once)
-        "traffic": 404.1e6 if backend == "tc" else None,
-        "traffic_source": "profiles/r1_ncu_summary_tcgemm2_tail.txt, tcgemm2_kernel<1,0,0> grid 2048: 175.8 MB read + 228.2 MB written per launch",
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (1024 per-subject 256 x 268 x 268 products) from the committed
+        # ncu --set full capture; the algorithmic bytes of that launch are 1024 x (256 x 268 + 268 x 268 + 256 x 268) x 4 B = 856 MB
+        "traffic": traffic,
+        "traffic_source": "profiles/r2_ncu_summary_tcgemm3.txt (tools/ncu_summary.py of the ncu --set full capture), first tcgemm3_kernel launch",
         "unet_simt_products": {"launches": simt_launches, "gflop_per_step": simt_flops / max(args.steps, 1) / 1e9,
                                "note": "Graph U-Net linears (once per step, subject independent) on gsr::bgemm_kernel, "
                                        "side stream under the eigendecomposition; not part of `achieved`"},
@@ -537,9 +679,10 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": "subjects/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[1]: GSR-Net fwd+bwd (+grad all-reduce, +Adam) batched over {B} "
-                               f"synthetic subjects per GPU, LR {LR_DIM} -> HR {HR_DIM}",
+                               f"synthetic subjects per GPU, LR {LR_DIM} -> HR {HR_DIM}"
+                               + (f" (strong scaling: {world * B} subjects over {world} GPUs)" if args.scaling == "strong" else ""),
                    "subjects_per_gpu": B, "global_subjects_per_step": world * B,
                    "parallelism": f"subject-data-parallel x{world}, one NCCL all-reduce of the flat 4.09 MB gradient bucket",
                    "lr_eigh": f"in step ({eigh_method or K.EIGH_METHOD} kernels)", "hr_target_eigh": hr_note,
@@ -556,14 +699,25 @@ def run_ours(args):
                                      f"durations / the timed (graph-replayed) step")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "subjects/s",
-                "h2d_bytes_per_step": world * B * (LR_DIM * LR_DIM + HR_DIM * HR_DIM) * 4,
+                "h2d_bytes_per_step": world * h2d_per_rank,
                 "d2h_bytes_per_step": world * 4,
+                "format": ("vectorised upper triangles (12 720 + 35 778 fp32 per subject, the dataset's on-disk form); "
+                           "gsr_anti_vectorize rebuilds the matrices on the device inside the timed region "
+                           "(utils/preprocessing.py:72-73)" if vec_fmt else "full fp32 matrices"),
+                "hr_target_basis": "cached on the device across steps (data-only, 172 KB per subject): a dataset of more than one "
+                                   "batch keeps it resident (1.7 GB per 10 000 subjects of the 180 GB), ships it with the batch "
+                                   "(`with_basis_copied`) or recomputes it (`config.with_hr_target_eigh_in_step`)",
+                "with_basis_copied": ({"value": e2e_basis_value, "unit": "subjects/s",
+                                       "h2d_bytes_per_step": world * (h2d_per_rank + B * HR_DIM * LR_DIM * 4)}
+                                      if e2e_basis_value else None),
+                "host_buffers": numa_note,
                 "pipeline": "H2D of step i+1 overlaps the compute of step i (two device buffers, copy stream)"
                             + ("; the copies land in the input buffers of the graph captured for that buffer set, which is then replayed" if use_graph else "")},
         "gpu_launches": launches,
         "roofline": roofline,
         "roofline_other_kernels": others,
         "cpu_baseline": cpu_baseline,
+        "gpu_eager_baseline": gpu_eager,
     }
     print(json.dumps(line), flush=True)
     finish()

@@ -449,12 +449,17 @@ def vectorize(matrix: torch.Tensor, include_diagonal: bool = False) -> torch.Ten
     return out
 
 
-def anti_vectorize(vec: torch.Tensor, n: int, include_diagonal: bool = False) -> torch.Tensor:
+def anti_vectorize(vec: torch.Tensor, n: int, include_diagonal: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out`` (optional): a contiguous float32 [..., n, n] buffer to fill, e.g. the input buffer of a captured step."""
     vec = _f32(vec, "anti_vectorize: vector")
     if vec.dim() not in (1, 2):
         raise ValueError("anti_vectorize: expected [len] or [batch, len]")
     batch = 1 if vec.dim() == 1 else vec.shape[0]
-    out = torch.empty(vec.shape[:-1] + (n, n), device=vec.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(vec.shape[:-1] + (n, n), device=vec.device, dtype=torch.float32)
+    elif (not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous()
+          or tuple(out.shape) != tuple(vec.shape[:-1]) + (n, n)):
+        raise ValueError("anti_vectorize: `out` must be a contiguous CUDA float32 tensor of shape [..., n, n]")
     check(lib().gsr_anti_vectorize(vec.data_ptr(), out.data_ptr(), batch, int(n), vec.shape[-1],
                                    int(include_diagonal), _stream()), "gsr_anti_vectorize")
     return out
