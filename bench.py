@@ -275,6 +275,99 @@ def synth_batch(torch, n, batch, seed, device):
     return m.contiguous()
 
 
+def run_folds(args):
+    """--folds F: fold-parallel cross-validation (BASELINE configs[2]; the KFold loop of training_gsr.ipynb:88-96 with one
+    model per fold, unet-transformer.py:484 for the 3 folds).  The ranks are split into F disjoint groups
+    (subject_parallel.fold_groups: 8 GPUs, 3 folds -> {0,1,2} {3,4,5} {6,7}); every group trains ITS OWN model on ITS OWN
+    subjects, subject-data-parallel inside the group with one NCCL all-reduce of the flat gradient bucket per step, and no
+    traffic between groups.  With fewer ranks than folds every rank trains its folds one after the other."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29513")
+    os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
+    dist.init_process_group("nccl", device_id=dev)
+    pkg = importlib.import_module(PKG_NAME)
+    pkg.lib()
+    F, B = args.folds, args.batch
+    my_folds, group, ranks = pkg.fold_groups(F)
+    results = []
+    for fold in my_folds:
+        torch.manual_seed(100 + fold)                                     # one model per fold
+        model = pkg.GSRNet([0.9, 0.7, 0.6, 0.5], Args()).to(dev)
+        gsize = len(ranks)
+        sp = pkg.SubjectParallel(model, group=group) if gsize > 1 else None
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=True)
+        gr = ranks.index(rank)
+        lr = synth_batch(torch, LR_DIM, B, 7000 + 97 * fold + gr, dev)    # the fold's own subjects, sharded over its ranks
+        hr = synth_batch(torch, HR_DIM, B, 9000 + 97 * fold + gr, dev)
+        U_hr = pkg.hr_target_basis(hr, LR_DIM, 0, check_errors=True)
+        graphed = pkg.GraphedTrainStep(model, opt, B, lmbda=Args.lmbda, padding=Args.padding,
+                                       grad_sync=sp.sync_gradients if sp is not None else None, warmup=max(args.warmup, 3))
+        graphed.load(lr, hr, U_hr)
+        for _ in range(max(args.warmup, 3)):
+            graphed.replay()
+        torch.cuda.synchronize()
+        if gsize > 1:
+            dist.barrier(group=group)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss, err = graphed.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if gsize > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        w0 = float(model.layer.weights.detach().double().sum())           # identical on the ranks of a fold, different across folds
+        results.append({"fold": fold, "ranks": ranks, "subjects_per_step": gsize * B, "ms_per_step": float(t) / args.steps,
+                        "subjects_per_s": gsize * B * args.steps / (float(t) / 1e3), "rank": rank,
+                        "loss_local_shard": float(loss), "weights_checksum": w0})
+        del graphed
+    gathered = [None] * world
+    dist.all_gather_object(gathered, results)
+    if rank == 0:
+        per_fold = {}
+        for rs in gathered:
+            for r in rs:
+                per_fold.setdefault(r["fold"], []).append(r)
+        folds_out, total = [], 0.0
+        for fold in sorted(per_fold):
+            rs = per_fold[fold]
+            same = all(abs(r["weights_checksum"] - rs[0]["weights_checksum"]) == 0.0 for r in rs)
+            folds_out.append({"fold": fold, "ranks": rs[0]["ranks"], "subjects_per_step": rs[0]["subjects_per_step"],
+                              "ms_per_step": max(r["ms_per_step"] for r in rs), "subjects_per_s": min(r["subjects_per_s"] for r in rs),
+                              "weights_identical_inside_fold": same, "weights_checksum": rs[0]["weights_checksum"],
+                              "loss_per_rank": [r["loss_local_shard"] for r in rs]})
+            total += folds_out[-1]["subjects_per_s"]
+        distinct = len({f["weights_checksum"] for f in folds_out}) == len(folds_out)
+        concurrent = world >= F
+        # whole-job rate: all subjects of all folds / the busiest rank's time (a rank that trains several folds runs them in turn)
+        busy_ms = max(sum(r["ms_per_step"] for r in rs) for rs in gathered if rs)
+        total_subjects_per_step = sum(f["subjects_per_step"] for f in folds_out)
+        line = {"metric": METRIC, "value": total_subjects_per_step / (busy_ms / 1e3),
+                "unit": "subjects/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": max(f["ms_per_step"] for f in folds_out), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[2]: {F}-fold cross-validation, fold-parallel x subject-data-parallel, "
+                                       f"{B} subjects per GPU per step, LR {LR_DIM} -> HR {HR_DIM}",
+                           "fold_groups": [f["ranks"] for f in folds_out],
+                           "folds_run": "concurrently on disjoint rank groups" if concurrent else "round-robin on the ranks, one after the other",
+                           "collectives": "one NCCL all-reduce of the 4.09 MB gradient bucket per step INSIDE each fold group; none across folds"},
+                "folds": folds_out, "weights_differ_across_folds": distinct,
+                "gpu_launches": None}
+        print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    torch.cuda.synchronize()
+    dist.barrier()
+    os._exit(0)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -727,6 +820,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.folds > 0:
+        run_folds(args)
     else:
         run_ours(args)
 

@@ -55,11 +55,13 @@ __global__ void pool_gather_scale_kernel(const float* __restrict__ X, const int6
 __global__ void pool_bwd_rows_kernel(const float* __restrict__ X, const float* __restrict__ p,
                                      const float* __restrict__ scores, const int64_t* __restrict__ idx,
                                      const float* __restrict__ g, float* __restrict__ dX,
-                                     float* __restrict__ ds, int d) {
+                                     float* __restrict__ ds, int d, int n) {
     __shared__ float s_part[32];
     __shared__ float s_ds;
     const int t = blockIdx.x;
-    const int i = (int)idx[t];
+    const int64_t i64 = idx[t];
+    if (i64 < 0 || i64 >= n) return;                       // uniform over the block
+    const int i = (int)i64;
     const float sig = scores[i];
     float acc = 0.f;
     for (int c = threadIdx.x; c < d; c += blockDim.x) acc = fmaf(g[(size_t)t * d + c], X[(size_t)i * d + c], acc);
@@ -101,14 +103,21 @@ __global__ void gather_rows_cols_kernel(const float* __restrict__ A, const int64
     const float* Ab = A + (size_t)blockIdx.y * n * n;
     float* ob = out + (size_t)blockIdx.y * k * k;
     const int r = blockIdx.x;
-    const size_t src = (size_t)idx[r] * n;
-    for (int c = threadIdx.x; c < k; c += blockDim.x) ob[(size_t)r * k + c] = Ab[src + idx[c]];
+    const int64_t ir = idx[r];
+    const bool row_ok = ir >= 0 && ir < n;                 // an index outside [0, n) never becomes an address (torch raises;
+    const size_t src = (size_t)(row_ok ? ir : 0) * n;      // the Python wrappers validate caller-supplied indices)
+    for (int c = threadIdx.x; c < k; c += blockDim.x) {
+        const int64_t ic = idx[c];
+        ob[(size_t)r * k + c] = (row_ok && ic >= 0 && ic < n) ? Ab[src + ic] : 0.f;
+    }
 }
 
 // models/ops.py:22-23 scatter (rows named by idx are distinct) and its autograd (gather)
 __global__ void scatter_rows_kernel(const float* __restrict__ X, const int64_t* __restrict__ idx,
-                                    float* __restrict__ out, int d) {
-    const size_t dst = (size_t)idx[blockIdx.x] * d;
+                                    float* __restrict__ out, int d, int n) {
+    const int64_t i = idx[blockIdx.x];
+    if (i < 0 || i >= n) return;                           // out of range: no write (never an out-of-bounds store)
+    const size_t dst = (size_t)i * d;
     for (int c = threadIdx.x; c < d; c += blockDim.x) out[dst + c] = X[(size_t)blockIdx.x * d + c];
 }
 __global__ void gather_rows_kernel(const float* __restrict__ X, const int64_t* __restrict__ idx,
@@ -152,7 +161,7 @@ extern "C" int gsr_pool_bwd(const float* X, const float* p, const float* scores,
     cudaError_t e = cudaMemsetAsync(grad_X, 0, (size_t)n * d * sizeof(float), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(ds_workspace, 0, (size_t)n * sizeof(float), st);
     if (e != cudaSuccess) return fail((int)e, "pool_bwd: memset failed");
-    pool_bwd_rows_kernel<<<k, 128, 0, st>>>(X, p, scores, idx, grad_new_X, grad_X, ds_workspace, d);
+    pool_bwd_rows_kernel<<<k, 128, 0, st>>>(X, p, scores, idx, grad_new_X, grad_X, ds_workspace, d, n);
     int rc = launched("pool_bwd_rows");
     if (rc) return rc;
     pool_bwd_proj_kernel<<<(d + 127) / 128, 128, 0, st>>>(X, ds_workspace, grad_p, grad_c, n, d);
@@ -173,7 +182,7 @@ extern "C" int gsr_unpool_fwd(const float* X, const int64_t* idx, float* new_X, 
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(new_X, 0, (size_t)n * d * sizeof(float), st);
     if (e != cudaSuccess) return fail((int)e, "unpool_fwd: memset failed");
-    scatter_rows_kernel<<<k, 128, 0, st>>>(X, idx, new_X, d);
+    scatter_rows_kernel<<<k, 128, 0, st>>>(X, idx, new_X, d, n);
     return launched("unpool_scatter");
 }
 

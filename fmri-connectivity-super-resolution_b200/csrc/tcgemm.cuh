@@ -163,7 +163,7 @@ __device__ __forceinline__ uint32_t instr_desc2(int n, int a_mn_major, int b_mn_
 
 // csrc/tcgemm_tma.cu: the TMA-fed persistent CTA-pair kernel.  tma_ok: shapes / alignments it takes (the caller has
 // already applied pair_ok); tma_launch covers the first 256 * floor(M / 256) rows of every batch item.
-extern int g_tma, g_utccp, g_mn_partial;       // gsr_set_tuning("tcgemm_tma" | "tcgemm_utccp" | "tcgemm_mn_partial", 0|1)
+extern int g_tma, g_utccp, g_mn_partial, g_pf_ahead;       // gsr_set_tuning("tcgemm_tma" | "tcgemm_utccp" | "tcgemm_mn_partial", 0|1)
 bool tma_ok(const Params& p, int transA, int transB);
 int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, cudaStream_t st);
 

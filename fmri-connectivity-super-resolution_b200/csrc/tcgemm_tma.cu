@@ -31,6 +31,9 @@ int g_utccp = 0;            // gsr_set_tuning("tcgemm_utccp", 0|1): K-major A th
                             // traffic per k-block, but the copies execute IN the tensor pipe, in order with the MMAs (8 x ~64 clk per
                             // k-block): the MMA thread's issue -> commit time goes from 1.15 to 1.5 us and the stacked product from
                             // 0.259 to 0.277 ms.  Kept as a switch.
+int g_pf_ahead = 0;         // gsr_set_tuning("tcgemm_prefetch", k): k-blocks of L2 prefetch (cp.async.bulk.prefetch.tensor) in front of the
+                            // TMA loads; default off -- measured monotonically slower (stacked NN 0.272 / 0.290 / 0.291 / 0.287 / 0.310 ms
+                            // for k = 0 / 3 / 6 / 9 / 12): the load latency is not what bounds the k-block rate
 int g_mn_partial = 1;       // gsr_set_tuning("tcgemm_mn_partial", 0|1): MN-major B ranges may end inside a 32-column block (256 + 16)
 
 namespace t3 {
@@ -68,6 +71,7 @@ struct Plan {
     int a_ring;             // tensor-memory column of the A-operand ring (tcgen05.cp, K-major A only); 0 = A is read from shared memory
     int b_off1;             // byte offset of the second range inside a B tile
     int b_bytes;            // bytes of this CTA's B tile per k-block (TMA transaction count)
+    int pf_ahead;           // k-blocks the L2 prefetch cursor runs in front of the loads (0 = off)
     int a_batched, b_batched;
     float alpha;
     int epilogue;
@@ -84,6 +88,9 @@ __device__ __forceinline__ void tma_load(uint32_t dst, const CUtensorMap* map, u
 __device__ __forceinline__ void tma_store(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                  :: "l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" :: "l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
@@ -164,40 +171,52 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     (void)kb_per_tile;
 
     if (warp == 0) {
-        // ===== TMA producer (one lane): every CTA loads its own 128 rows of op(A) and its half of op(B)
+        // ===== TMA producer (one lane): every CTA loads its own 128 rows of op(A) and its half of op(B).
+        // An optional second cursor runs p.pf_ahead k-blocks in front of the loads and issues the same boxes as
+        // cp.async.bulk.prefetch.tensor (L2 only); measured slower, off by default (g_pf_ahead).
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-                const int z = tile / p.tiles_m, mp = tile - z * p.tiles_m;
+            struct Blk { int tile, sub, kb; };
+            auto nsub_of = [&](int tile) { return REDUCE ? (p.nsub - tile / p.tiles_m + p.splits - 1) / p.splits : 1; };
+            auto next = [&](Blk& b) {
+                if (++b.kb == p.nkb) { b.kb = 0; if (++b.sub == nsub_of(b.tile)) { b.sub = 0; b.tile += n_clusters; } }
+            };
+            // issue the boxes of one k-block: PREFETCH -> into L2, else into raw slot `s` signalling `full`
+            auto boxes = [&](const Blk& blk, bool prefetch, uint32_t a_dst, uint32_t full) {
+                const int z = blk.tile / p.tiles_m, mp = blk.tile - z * p.tiles_m;
                 const int m0 = mp * 256 + (int)rank * BM;
-                const int nsub = REDUCE ? (p.nsub - z + p.splits - 1) / p.splits : 1;
-                for (int sub = 0; sub < nsub; ++sub) {
-                    const int b = REDUCE ? z + sub * p.splits : z;
-                    const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
-                    for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-                        const uint32_t s = it % RAW_STAGES, use = it / RAW_STAGES;
-                        T3_STAMP(0, it, 0);
-                        if (use > 0) mbar_wait(bar_raw_empty + 8 * s, (use - 1) & 1);
-                        T3_STAMP(0, it, 1);
-                        const uint32_t full = bar_raw_full + 8 * s;
-                        mbar_expect_tx(full, (uint32_t)A_TILE + b_bytes);
-                        const uint32_t a_dst = smem_u32(raw + s * SLOT_BYTES), b_dst = a_dst + A_TILE;
-                        const int k0 = kb * BK;
-                        if (!TA) tma_load(a_dst, &mapA, full, k0, m0, ba);                         // box {32 k, 128 m}
-                        else {
+                const int b = REDUCE ? z + blk.sub * p.splits : z;
+                const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
+                const int k0 = blk.kb * BK;
+                const uint32_t b_dst = a_dst + A_TILE;
+                auto ld = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2) {
+                    if (prefetch) tma_prefetch(map, c0, c1, c2); else tma_load(dst, map, full, c0, c1, c2);
+                };
+                if (!TA) ld(a_dst, &mapA, k0, m0, ba);                                              // box {32 k, 128 m}
+                else {
 #pragma unroll
-                            for (int j = 0; j < BM / 32; ++j) tma_load(a_dst + j * 4096, &mapA, full, m0 + 32 * j, k0, ba);   // box {32 m, 32 k}
-                        }
-                        if (TB) {                                                                   // boxes {32 k, R0 n}, {32 k, R1 n}
-                            tma_load(b_dst, &mapB0, full, k0, R0 * (int)rank, bb);
-                            if (R1 > 0) tma_load(b_dst + p.b_off1, &mapB1, full, k0, p.nr0 + R1 * (int)rank, bb);
-                        } else {                                                                    // box {32 n, 32 k} per 32 columns
-                            // (a range whose share is not a multiple of 32 columns uses the head of its last block only)
-                            for (int j = 0; j < (R0 + 31) / 32; ++j) tma_load(b_dst + j * 4096, &mapB0, full, R0 * (int)rank + 32 * j, k0, bb);
-                            for (int j = 0; j < (R1 + 31) / 32; ++j) tma_load(b_dst + p.b_off1 + j * 4096, &mapB0, full, p.nr0 + R1 * (int)rank + 32 * j, k0, bb);
-                        }
-                    }
+                    for (int j = 0; j < BM / 32; ++j) ld(a_dst + j * 4096, &mapA, m0 + 32 * j, k0, ba);        // box {32 m, 32 k}
                 }
+                if (TB) {                                                                           // boxes {32 k, R0 n}, {32 k, R1 n}
+                    ld(b_dst, &mapB0, k0, R0 * (int)rank, bb);
+                    if (R1 > 0) ld(b_dst + p.b_off1, &mapB1, k0, p.nr0 + R1 * (int)rank, bb);
+                } else {                                                                            // box {32 n, 32 k} per 32 columns
+                    // (a range whose share is not a multiple of 32 columns uses the head of its last block only)
+                    for (int j = 0; j < (R0 + 31) / 32; ++j) ld(b_dst + j * 4096, &mapB0, R0 * (int)rank + 32 * j, k0, bb);
+                    for (int j = 0; j < (R1 + 31) / 32; ++j) ld(b_dst + p.b_off1 + j * 4096, &mapB0, p.nr0 + R1 * (int)rank + 32 * j, k0, bb);
+                }
+            };
+            Blk cur{cluster_id, 0, 0}, pf{cluster_id, 0, 0};
+            const int pf_ahead = p.pf_ahead;
+            for (int i = 0; i < pf_ahead && pf.tile < total_tiles; ++i) { boxes(pf, true, 0, 0); next(pf); }
+            for (uint32_t it = 0; cur.tile < total_tiles; ++it, next(cur)) {
+                if (pf_ahead > 0 && pf.tile < total_tiles) { boxes(pf, true, 0, 0); next(pf); }
+                const uint32_t s = it % RAW_STAGES, use = it / RAW_STAGES;
+                T3_STAMP(0, it, 0);
+                if (use > 0) mbar_wait(bar_raw_empty + 8 * s, (use - 1) & 1);
+                T3_STAMP(0, it, 1);
+                const uint32_t full = bar_raw_full + 8 * s;
+                mbar_expect_tx(full, (uint32_t)A_TILE + b_bytes);
+                boxes(cur, false, smem_u32(raw + s * SLOT_BYTES), full);
             }
         }
         __syncwarp();
@@ -518,6 +537,7 @@ int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, c
     // columns) behind them: 272 columns -> [0, 272) / [192, 464) / ring at 464; <= 232 columns -> no overlap at all
     pl.a_ring = (!transA && g_utccp) ? TMEM_COLS - 48 : 0;
     pl.acc_base1 = std::min(256, ((pl.a_ring ? pl.a_ring : TMEM_COLS) - (pl.nr0 + pl.nr1)) & ~31);
+    pl.pf_ahead = g_pf_ahead;
     pl.a_batched = p.sA != 0; pl.b_batched = p.sB != 0;
     pl.alpha = p.alpha; pl.epilogue = p.epilogue; pl.extra = p.extra; pl.ld_extra = p.ld_extra; pl.s_extra = p.s_extra;
     const int R0 = pl.nr0 / 2, R1 = pl.nr1 / 2;

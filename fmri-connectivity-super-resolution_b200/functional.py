@@ -123,6 +123,11 @@ def batch_norm_act(x, gamma, beta, running_mean, running_var, training, momentum
     dropout active with a seed drawn from torch's default generator unless given.  Eval: running estimates, no
     dropout."""
     if training:
+        if x.shape[0] == 1:           # nn.BatchNorm1d's contract: batch statistics of one sample are undefined
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(x.shape)}")
+        if momentum is None:
+            raise NotImplementedError("batch_norm_act: momentum=None (cumulative moving average) is not on the MLP baseline's "
+                                      "path (models/mlp.py uses nn.BatchNorm1d's default momentum 0.1)")
         mean, var = K.bn_stats(x.detach(), running_mean, running_var, momentum)
         if p_drop > 0 and seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())

@@ -20,6 +20,18 @@ def _to_device(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_cuda else t.to(device)
 
 
+def _check_index(idx: torch.Tensor, n: int, what: str) -> None:
+    """Caller-supplied indices (the public GraphUnpool / gather entry points): torch raises IndexError for an index
+    outside [-n, n); the kernels take raw non-negative row numbers, so anything outside [0, n) is rejected here (one
+    device read).  Indices produced by gsr_pool_topk inside GraphPool / GraphUnet are valid by construction."""
+    if idx.dtype != torch.int64:
+        raise IndexError(f"{what}: tensors used as indices must be int64, got {idx.dtype}")
+    if idx.numel():
+        lo, hi = int(idx.min()), int(idx.max())
+        if lo < 0 or hi >= n:
+            raise IndexError(f"{what}: index {lo if lo < 0 else hi} is out of bounds for dimension 0 with size {n}")
+
+
 class GraphUnpool(nn.Module):
     """models/ops.py:7-24."""
 
@@ -29,6 +41,7 @@ class GraphUnpool(nn.Module):
     def forward(self, A, X, idx):
         A = A.to_dense() if A.is_sparse else A
         A, X, idx = _to_device(A), _to_device(X), _to_device(idx)
+        _check_index(idx, A.shape[-2], "GraphUnpool")
         new_X = F_.GraphUnpoolFn.apply(X, idx, A.shape[-2])
         return A, new_X
 

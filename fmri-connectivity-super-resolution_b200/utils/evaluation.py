@@ -5,6 +5,12 @@ concatenates and calls sklearn / scipy on the host.  All three numbers are invar
 order of that concatenation, so the kernels read the strict upper triangles in place (half of
 each matrix is touched, nothing is materialised) with fp64 accumulators.  The topological
 metrics of the same function (networkx centralities) are out of scope.
+
+Precision contract: the kernels read **float32** matrices (the model's output dtype and what the
+challenge CSVs hold to their printed digits) and accumulate in float64.  float64 inputs are
+rounded to float32 first -- a ~6e-8 relative perturbation of every element -- so against
+sklearn / scipy fed the float64 originals the three numbers agree to ~1e-7 relative; the
+1e-10 / 1e-8 tolerances of the tests are against float64 sums of the same float32 inputs.
 """
 from __future__ import annotations
 

@@ -30,61 +30,49 @@ def hr_target_basis(hr, lr_dim, padding=0, check_errors=True):
     return U_hr[..., :, :lr_dim].contiguous()
 
 
+def _as_device_matrix(a, device):
+    """numpy (any float dtype) or torch -> float32 on the device, as `.type(torch.FloatTensor).to(device)` does."""
+    t = torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else torch.as_tensor(a)
+    return t.to(device=device, dtype=torch.float32)
+
+
 def train(model, optimizer, subjects_adj, subjects_labels, args):
-    """utils/gsr_train.py:11-53."""
+    """Drop-in for utils/gsr_train.py:11-53: ``args.epochs`` passes over the subjects, ONE optimiser step per subject
+    (the reference is strictly batch 1), the three-term loss of :39-41, and the reference's only observable output --
+    one ``Epoch: i, Loss: ..., Error (MAE): ...`` line per epoch.  Returns None.  Each step is a ``GSRTrainStep`` on a
+    one-subject batch (forward, HR-target eigendecomposition, loss, backward on the library's kernels); ``loss`` /
+    ``error`` are read back per step as the reference's ``.item()`` calls do."""
     device = torch.device("cuda")
     model.to(device)
-    i = 0
-    all_epochs_loss = []
-    no_epochs = args.epochs
-    for epoch in range(no_epochs):
-        epoch_loss = []
-        epoch_error = []
+    step = GSRTrainStep(model, lmbda=args.lmbda, padding=args.padding, check_errors=True)
+    for epoch in range(args.epochs):
+        losses, errors = [], []
         for lr, hr in zip(subjects_adj, subjects_labels):
             model.train()
             optimizer.zero_grad()
-            lr = torch.from_numpy(lr).type(torch.FloatTensor).to(device)
-            hr = torch.from_numpy(hr).type(torch.FloatTensor).to(device)
-            model_outputs, net_outs, start_gcn_outs, layer_outs = model(lr)
-            model_outputs = unpad(model_outputs, args.padding)
-            U_hr_reduced = hr_target_basis(hr, model.layer.lr_dim, args.padding)
-            loss = args.lmbda * criterion(net_outs, start_gcn_outs) + \
-                criterion(model.layer.weights, U_hr_reduced) + \
-                criterion(model_outputs, hr)
-            error = criterion(model_outputs, hr)
-            loss.backward()
+            loss, error = step(_as_device_matrix(lr, device)[None], _as_device_matrix(hr, device)[None])
             optimizer.step()
-            epoch_loss.append(loss.item())
-            epoch_error.append(error.item())
-        i += 1
-        print(f"Epoch: {i}, Loss: {np.mean(epoch_loss)}, Error (MAE): {np.mean(epoch_error)}")
-        all_epochs_loss.append(np.mean(epoch_loss))
+            losses.append(loss.item())
+            errors.append(error.item())
+        print(f"Epoch: {epoch + 1}, Loss: {np.mean(losses)}, Error (MAE): {np.mean(errors)}")
 
 
 def test(model, test_adj, test_labels, args):
-    """utils/gsr_train.py:55-85 (including the in-place unit diagonal on the caller's array)."""
+    """Drop-in for utils/gsr_train.py:55-85: per-subject MAE of the prediction against the HR target with a unit diagonal
+    (set IN PLACE on the caller's array, :70), all-zero samples skipped (:65-68), one ``MAE:`` line per evaluated
+    subject and the mean at the end.  Returns None."""
     device = torch.device("cuda")
     model.to(device)
     test_error = []
-    preds_list = []
-    g_t = []
-    i = 0
     for lr, hr in zip(test_adj, test_labels):
-        all_zeros_lr = not np.any(lr)
-        all_zeros_hr = not np.any(hr)
-        if not all_zeros_lr and not all_zeros_hr:
-            lr = torch.from_numpy(lr).type(torch.FloatTensor).to(device)
-            np.fill_diagonal(hr, 1)
-            hr = torch.from_numpy(hr).type(torch.FloatTensor).to(device)
-            with torch.no_grad():           # the reference builds and discards a graph here
-                preds, _, _, _ = model(lr)
-            preds = unpad(preds, args.padding)
-            preds_list.append(preds.flatten().detach().cpu().numpy())
-            error = criterion(preds, hr)
-            g_t.append(hr.flatten().cpu().numpy())
-            print(f"MAE: {error.item()}")
-            test_error.append(error.item())
-            i += 1
+        if not np.any(lr) or not np.any(hr):
+            continue
+        np.fill_diagonal(hr, 1)
+        with torch.no_grad():           # the reference builds and discards an autograd graph here
+            preds = unpad(model(_as_device_matrix(lr, device))[0], args.padding)
+            error = criterion(preds, _as_device_matrix(hr, device)).item()
+        print(f"MAE: {error}")
+        test_error.append(error)
     print(f"Test error MAE: {np.mean(test_error)}")
 
 

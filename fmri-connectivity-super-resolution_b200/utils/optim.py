@@ -44,8 +44,18 @@ class FlatAdam(torch.optim.Optimizer):
                     raise RuntimeError("FlatAdam: parameters and gradients must be contiguous CUDA float32 (no CPU path)")
             if "step_tensor" not in group:
                 group["step_tensor"] = torch.zeros((), device=ps[0].device, dtype=torch.float32)
+            if group["step_tensor"].device != ps[0].device:          # e.g. after load_state_dict(map_location="cpu")
+                group["step_tensor"] = group["step_tensor"].to(ps[0].device, torch.float32)
             states = [self._state(p, group["step_tensor"]) for p in ps]
-            key = (gi,) + tuple(p.grad.data_ptr() for p in ps)
+            for p, st in zip(ps, states):                             # loaded moments may sit on another device
+                for k in ("exp_avg", "exp_avg_sq"):
+                    if st[k].device != p.device or st[k].dtype != torch.float32 or not st[k].is_contiguous():
+                        st[k] = st[k].to(p.device, torch.float32).contiguous()
+            # The pointer tables are cached per set of (parameter, gradient, moment) buffers: every raw pointer a table
+            # holds is part of its key, and the table keeps the tensors alive, so that a replaced state tensor
+            # (load_state_dict) or a fresh .grad (zero_grad(set_to_none=True)) can never leave a stale pointer behind.
+            key = (gi,) + tuple(x for p, st in zip(ps, states)
+                                for x in (p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()))
             tab = self._tables.get(key)
             if tab is None:
                 if len(self._tables) >= 8:
@@ -55,10 +65,19 @@ class FlatAdam(torch.optim.Optimizer):
                     (C.c_void_p * n)(*[p.data_ptr() for p in ps]), (C.c_void_p * n)(*[p.grad.data_ptr() for p in ps]),
                     (C.c_void_p * n)(*[s["exp_avg"].data_ptr() for s in states]),
                     (C.c_void_p * n)(*[s["exp_avg_sq"].data_ptr() for s in states]),
-                    (C.c_longlong * n)(*[p.numel() for p in ps]), n)
+                    (C.c_longlong * n)(*[p.numel() for p in ps]), n,
+                    [(p, p.grad, s["exp_avg"], s["exp_avg_sq"]) for p, s in zip(ps, states)])
             b1, b2 = group["betas"]
             check(lib().gsr_adam_step(tab[0], tab[1], tab[2], tab[3], tab[4], tab[5], group["step_tensor"].data_ptr(),
                                       float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                                       float(group["weight_decay"]), torch.cuda.current_stream().cuda_stream),
                   "gsr_adam_step")
         return loss
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables.clear()                      # the loaded state tensors are new buffers
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._tables = {}

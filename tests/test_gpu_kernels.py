@@ -401,14 +401,16 @@ def test_bgemm_vs_float64(K, gemm_backend, tA, tB, shape):
 
 
 def test_tcgemm_pair_kernel_equals_one_cta_kernel(cuda_pkg, K):
-    """cta_group::2 pairs (M = 256 per MMA) against one CTA per 128-row tile: same split, same MMA order, so the
-    results are bit identical; the FP32 ragged rows differ from the tensor kernel by rounding only."""
+    """Thread-staged kernels (gsr_set_tuning("tcgemm_tma", 0)): cta_group::2 pairs (M = 256 per MMA) against one CTA per
+    128-row tile -- same split, same MMA order, so the results are bit identical; the FP32 ragged rows differ from the
+    tensor kernel by rounding only."""
     g = torch.Generator(device="cuda").manual_seed(31)
     A = torch.randn(7, 268, 268, device="cuda", generator=g); B = torch.randn(7, 268, 268, device="cuda", generator=g)
     W = torch.randn(268, 268, device="cuda", generator=g)
     calls = [lambda: K.bgemm(A, B), lambda: K.bgemm(A, B, transA=True), lambda: K.bgemm(A, B, transB=True),
              lambda: K.bgemm(A, W), lambda: K.bgemm(A, W, transB=True), lambda: K.bgemm_reduce(A, B, transA=True)]
     try:
+        cuda_pkg.set_tuning("tcgemm_tma", 0)
         cuda_pkg.set_tuning("tcgemm_pairs", 0)
         one = [c() for c in calls]
         cuda_pkg.set_tuning("tcgemm_pairs", 1); cuda_pkg.set_tuning("tcgemm_ragged_rows", 0)
@@ -416,11 +418,54 @@ def test_tcgemm_pair_kernel_equals_one_cta_kernel(cuda_pkg, K):
         cuda_pkg.set_tuning("tcgemm_ragged_rows", 1)
         ragged = [c() for c in calls]
     finally:
-        cuda_pkg.set_tuning("tcgemm_pairs", 1); cuda_pkg.set_tuning("tcgemm_ragged_rows", 1)
+        cuda_pkg.set_tuning("tcgemm_pairs", 1); cuda_pkg.set_tuning("tcgemm_ragged_rows", 1); cuda_pkg.set_tuning("tcgemm_tma", 1)
     for a, b, c in zip(one, pairs, ragged):
         assert torch.equal(a, b)
         assert torch.equal(a[..., :256, :], c[..., :256, :])
         assert float((a - c).abs().max()) < 4e-6 * float(a.abs().max())
+
+
+@pytest.mark.parametrize("batch", [1, 3, 80])
+def test_tcgemm_tma_kernel(cuda_pkg, K, batch):
+    """The TMA-fed persistent CTA-pair kernel (csrc/tcgemm_tma.cu; default route for M >= 256, N <= 272): every operand
+    layout, epilogue and the subject reduction against the float64 product within 2e-6 sum|a||b| (its hi term is the
+    TRUNCATED tf32 of the operand -- kind::tf32 ignores the low mantissa bits of the raw tile -- so it is not bit
+    identical to the thread-staged kernels, which round); its switches (tensor-memory A operand via tcgen05.cp, whole
+    32-column blocks for MN-major B, L2 prefetch) change the data path, not one bit of the result; more tiles than CTA
+    pairs (batch 80 -> a second round of the persistent loop with the other accumulator)."""
+    g = torch.Generator(device="cuda").manual_seed(77 + batch)
+    A = torch.randn(batch, 268, 268, device="cuda", generator=g); B = torch.randn(batch, 268, 268, device="cuda", generator=g)
+    W = torch.randn(268, 268, device="cuda", generator=g); Wl = torch.randn(268, 160, device="cuda", generator=g)
+    U = torch.randn(batch, 160, 160, device="cuda", generator=g); add = torch.randn(batch, 268, 268, device="cuda", generator=g)
+    bias = torch.randn(268, device="cuda", generator=g)
+    Ad, Bd, Wd = A.double(), B.double(), W.double()
+    cases = [
+        (lambda: K.bgemm(A, B), Ad @ Bd, Ad.abs() @ Bd.abs()),
+        (lambda: K.bgemm(A, B, transA=True), Ad.transpose(1, 2) @ Bd, Ad.abs().transpose(1, 2) @ Bd.abs()),
+        (lambda: K.bgemm(A, B, transB=True), Ad @ Bd.transpose(1, 2), Ad.abs() @ Bd.abs().transpose(1, 2)),
+        (lambda: K.bgemm(A, B, alpha=2.0, add=add), 2 * (Ad @ Bd) + add.double(), 2 * (Ad.abs() @ Bd.abs())),
+        (lambda: K.bgemm(A, W), Ad @ Wd, Ad.abs() @ Wd.abs()),
+        (lambda: K.bgemm(A, W, transB=True, bias=bias), Ad @ Wd.T + bias.double(), Ad.abs() @ Wd.abs().T),
+        (lambda: K.bgemm(A, Wl), Ad @ Wl.double(), Ad.abs() @ Wl.double().abs()),
+        (lambda: K.bgemm(U, Wl, transB=True), U.double() @ Wl.double().T, U.double().abs() @ Wl.double().abs().T),
+        (lambda: K.bgemm_reduce(A, B, transA=True), (Ad.transpose(1, 2) @ Bd).sum(0), (Ad.abs().transpose(1, 2) @ Bd.abs()).sum(0)),
+        (lambda: K.bgemm_reduce(A, B), (Ad @ Bd).sum(0), (Ad.abs() @ Bd.abs()).sum(0)),
+    ]
+    n0 = cuda_pkg.launch_count()
+    base = []
+    for fn, ref, bound in cases:
+        out = fn()
+        assert float((out.double() - ref).abs().max()) <= 2e-6 * float(bound.max())
+        base.append(out)
+    assert cuda_pkg.launch_count() > n0
+    try:
+        for key, val in (("tcgemm_utccp", 1), ("tcgemm_mn_partial", 0), ("tcgemm_prefetch", 4)):
+            cuda_pkg.set_tuning(key, val)
+            for (fn, _, _), want in zip(cases, base):
+                assert torch.equal(fn(), want), key
+            cuda_pkg.set_tuning(key, {"tcgemm_utccp": 0, "tcgemm_mn_partial": 1, "tcgemm_prefetch": 0}[key])
+    finally:
+        cuda_pkg.set_tuning("tcgemm_utccp", 0); cuda_pkg.set_tuning("tcgemm_mn_partial", 1); cuda_pkg.set_tuning("tcgemm_prefetch", 0)
 
 
 @pytest.mark.parametrize("tA", [False, True])
@@ -755,3 +800,20 @@ def test_flat_bucket_pack_unpack_roundtrip(K):
     flat.mul_(2.0)
     bucket.unpack(1.0)
     assert torch.equal(torch.cat([t.reshape(-1) for t in tensors]), want * 2.0)
+
+
+def test_unpool_rejects_out_of_range_indices(cuda_pkg):
+    """caller-supplied indices never become out-of-bounds addresses -- the public module raises like torch's
+    indexing does, and the raw kernels skip / zero what is out of range."""
+    K = cuda_pkg.kernels
+    unp = cuda_pkg.GraphUnpool()
+    A, X = torch.zeros(6, 6, device="cuda"), torch.randn(3, 4, device="cuda")
+    for bad in ([4, 0, 6], [-1, 0, 2]):
+        with pytest.raises(IndexError):
+            unp(A, X, torch.tensor(bad, device="cuda"))
+    with pytest.raises(IndexError):
+        unp(A, X, torch.tensor([4, 0, 2], device="cuda", dtype=torch.int32))
+    out = K.unpool_fwd(X, torch.tensor([4, 99, 2], device="cuda"), 6)           # raw kernel: row 99 is dropped
+    assert torch.equal(out[4], X[0]) and torch.equal(out[2], X[2]) and float(out[[0, 1, 3, 5]].abs().max()) == 0.0
+    G = K.gather_rows_cols(torch.arange(36., device="cuda").reshape(6, 6), torch.tensor([1, 7, 3], device="cuda"))
+    assert torch.equal(G[0], torch.tensor([7., 0., 9.], device="cuda")) and float(G[1].abs().max()) == 0.0

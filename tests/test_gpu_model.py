@@ -647,6 +647,39 @@ def test_flat_adam_equals_torch_adam(cuda_pkg):
     with pytest.raises(RuntimeError):
         q = torch.nn.Parameter(torch.zeros(3)); q.grad = torch.zeros(3)
         pkg.FlatAdam([q]).step()
+    # load_state_dict on an optimiser that has already stepped: the loaded moments (host copies here, as after
+    # torch.load(map_location="cpu")) must be the ones the next step uses, and fresh .grad tensors every step
+    # (zero_grad(set_to_none=True)) must never leave a stale pointer table behind
+    init = [torch.randn(s, generator=g) for s in shapes[:7]]
+    p_a = [torch.nn.Parameter(t.clone().cuda()) for t in init]
+    p_b = [torch.nn.Parameter(t.clone().cuda()) for t in init]
+    o_a, o_b = pkg.FlatAdam(p_a, lr=1e-2), pkg.FlatAdam(p_b, lr=1e-2)
+    def step_both(opts_params):
+        grads = [torch.randn(s, generator=g).cuda() for s in shapes[:7]]
+        for opt, params in opts_params:
+            opt.zero_grad(set_to_none=True)
+            for q, gr in zip(params, grads):
+                q.grad = gr.clone()
+            opt.step()
+    for _ in range(3):
+        step_both([(o_a, p_a), (o_b, p_b)])
+    import copy
+    sd_a = copy.deepcopy(o_a.state_dict())
+    for st in sd_a["state"].values():
+        for kk in list(st):
+            if torch.is_tensor(st[kk]):
+                st[kk] = st[kk].cpu()
+    for gsd in sd_a["param_groups"]:
+        gsd["step_tensor"] = gsd["step_tensor"].cpu()
+    step_both([(o_b, p_b)])                                   # o_b moves on, then is rolled back to o_a's state
+    with torch.no_grad():
+        for a, b in zip(p_a, p_b):
+            b.copy_(a)
+    o_b.load_state_dict(sd_a)
+    for _ in range(2):
+        step_both([(o_a, p_a), (o_b, p_b)])
+    assert all(torch.equal(a, b) for a, b in zip(p_a, p_b))
+    assert float(o_b.param_groups[0]["step_tensor"]) == 5.0 and o_b.param_groups[0]["step_tensor"].is_cuda
 
 
 @pytest.mark.gpu

@@ -195,3 +195,18 @@ def test_mlp_challenge_size(cuda_pkg):
     bad = cuda_pkg.SuperResMLP(12720, 35778, 64, 1).cuda().eval()
     with pytest.raises(RuntimeError):
         bad(x)
+
+
+@pytest.mark.gpu
+def test_batch_norm_contract_matches_torch(cuda_pkg):
+    """a single training sample raises as nn.BatchNorm1d does (its batch variance is undefined), and
+    momentum=None is refused loudly instead of being silently read as 0."""
+    F_ = cuda_pkg.functional
+    x = torch.randn(1, 8, device="cuda")
+    g, b, rm, rv = torch.ones(8, device="cuda"), torch.zeros(8, device="cuda"), torch.zeros(8, device="cuda"), torch.ones(8, device="cuda")
+    with pytest.raises(ValueError):
+        F_.batch_norm_act(x, g, b, rm, rv, training=True)
+    with pytest.raises(NotImplementedError):
+        F_.batch_norm_act(torch.randn(4, 8, device="cuda"), g, b, rm, rv, training=True, momentum=None)
+    y = F_.batch_norm_act(x, g, b, rm, rv, training=False)          # eval mode: one sample is fine
+    assert torch.allclose(y, x / torch.sqrt(torch.tensor(1.0 + 1e-5)), atol=1e-6)

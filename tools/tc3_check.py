@@ -78,3 +78,13 @@ if "--time" in sys.argv:
             ms = timeit(fn); r[name] = [round(ms, 4), round(flops / ms / 1e9, 1)]
         print(json.dumps(r), flush=True)
 pkg.set_tuning("tcgemm_tma", 1)
+if "--sweep" in sys.argv:
+    for pf in (0, 3, 6, 9, 12):
+        pkg.set_tuning("tcgemm_prefetch", pf)
+        r = {"prefetch_ahead": pf}
+        for name, fn, flops in (("NN per-subject", lambda: K.bgemm(X, Y), fl), ("NT per-subject", lambda: K.bgemm(X, Y, transB=True), fl),
+                                ("NN stacked W", lambda: K.bgemm(X, W), fl), ("NT stacked W", lambda: K.bgemm(X, W, transB=True), fl),
+                                ("reduce TN", lambda: K.bgemm_reduce(X, Y, transA=True), fl)):
+            ms = timeit(fn); r[name] = [round(ms, 4), round(flops / ms / 1e9, 1)]
+        print(json.dumps(r), flush=True)
+    pkg.set_tuning("tcgemm_prefetch", 0)
