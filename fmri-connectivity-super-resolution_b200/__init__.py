@@ -16,7 +16,7 @@ include/gsr_sm100.h (libgsr_sm100.so, loaded with ctypes).  There is no CPU fall
 from ._lib import GsrLibraryError, LIB_PATH, launch_count, lib, set_tuning  # noqa: F401
 from . import kernels, functional  # noqa: F401
 from . import models, utils  # noqa: F401
-from .models import GSRNet, GSRLayer, GraphConvolution, GraphUnet, GraphPool, GraphUnpool, GCN, SuperResMLP  # noqa: F401
+from .models import GSRNet, GSRLayer, GraphConvolution, GraphUnet, GraphPool, GraphUnpool, GCN, SuperResMLP, SuperResMLPNotebook  # noqa: F401
 from .utils import MatrixVectorizer, normalize_adj_torch, pad_HR_adj, unpad  # noqa: F401
 from .utils.optim import FlatAdam  # noqa: F401
 from .utils.gsr_train import GSRTrainStep, GraphedTrainStep, train, test, train_batched, hr_target_basis  # noqa: F401
@@ -24,5 +24,5 @@ from .utils.evaluation import evaluation_reductions  # noqa: F401
 from .subject_parallel import SubjectParallel, shard_bounds, fold_assignment, fold_groups  # noqa: F401
 
 __all__ = ["lib", "GSRNet", "GSRLayer", "GraphConvolution", "GraphUnet", "GraphPool", "GraphUnpool", "GCN", "SuperResMLP",
-           "MatrixVectorizer", "normalize_adj_torch", "pad_HR_adj", "unpad", "train", "test", "train_batched",
+           "SuperResMLPNotebook", "MatrixVectorizer", "normalize_adj_torch", "pad_HR_adj", "unpad", "train", "test", "train_batched",
            "GSRTrainStep", "GraphedTrainStep", "FlatAdam", "evaluation_reductions", "SubjectParallel"]

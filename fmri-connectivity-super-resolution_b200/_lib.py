@@ -73,8 +73,12 @@ PROTOTYPES = {
     "gsr_tf32_probe": (C.c_double, [i32, c_ptr]),
     "gsr_adam_step": (i32, [c_ptr] * 5 + [i32, c_ptr, f32, f32, f32, f32, f32, c_ptr]),
     "gsr_bn_stats_f32": (i32, [c_ptr, i32, i32, c_ptr, c_ptr, c_ptr, c_ptr, f32, c_ptr]),
-    "gsr_bn_act_fwd_f32": (i32, [c_ptr] * 5 + [f32, f32, C.c_ulonglong, i32, c_ptr, i32, i32, c_ptr]),
-    "gsr_bn_act_bwd_f32": (i32, [c_ptr] * 6 + [f32, f32, C.c_ulonglong, i32, i32, c_ptr, c_ptr, c_ptr, i32, i32, c_ptr]),
+    "gsr_bn_act_fwd_f32": (i32, [c_ptr] * 5 + [f32, f32, C.c_ulonglong, f32, c_ptr, i32, i32, c_ptr]),
+    "gsr_bn_act_bwd_f32": (i32, [c_ptr] * 6 + [f32, f32, C.c_ulonglong, f32, i32, c_ptr, c_ptr, c_ptr, i32, i32, c_ptr]),
+    "gsr_add_act_fwd_f32": (i32, [c_ptr, c_ptr, c_ptr, i64, f32, c_ptr]),
+    "gsr_act_bwd_f32": (i32, [c_ptr, c_ptr, c_ptr, i64, f32, c_ptr]),
+    "gsr_sigmoid_fwd_f32": (i32, [c_ptr, c_ptr, i64, c_ptr]),
+    "gsr_sigmoid_bwd_f32": (i32, [c_ptr, c_ptr, c_ptr, i64, c_ptr]),
 }
 
 

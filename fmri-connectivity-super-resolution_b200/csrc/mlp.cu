@@ -4,6 +4,8 @@
 // memory-bound pass here (batch statistics first when training).  The dropout mask is a counter-based hash of
 // (seed, element index): nothing is stored, the backward pass recomputes it, and the CPU restatement used by the
 // tests reproduces it bit for bit.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gsr {
@@ -77,7 +79,7 @@ template <int VEC>
 __global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                                                                 const float* __restrict__ var, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, float eps, float p_drop,
-                                                                unsigned long long seed, int relu, float* __restrict__ y,
+                                                                unsigned long long seed, float slope, float* __restrict__ y,
                                                                 int batch, int features) {
     const int h = (blockIdx.x * EW_THREADS + threadIdx.x) * VEC;
     if (h >= features) return;
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const float* __r
         for (int i = 0; i < VEC; ++i) {
             float z = (v.v[i] - m.v[i]) * rstd[i] * ga.v[i] + be.v[i];
             z *= keep_scale(p_drop, seed, (unsigned long long)(e + i));
-            v.v[i] = relu ? fmaxf(z, 0.f) : z;
+            v.v[i] = z > 0.f ? z : slope * z;              // slope of the negative side: 0 = ReLU, 0.01 = LeakyReLU, 1 = none
         }
         store_pack<VEC>(y + e, v);
     }
@@ -101,16 +103,15 @@ __global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const float* __r
 
 // g = dy through ReLU and dropout; d beta = sum_b g, d gamma = sum_b g * xhat
 __device__ __forceinline__ float upstream(float dy, float xhat, float gamma, float beta, float p_drop,
-                                          unsigned long long seed, unsigned long long index, int relu) {
+                                          unsigned long long seed, unsigned long long index, float slope) {
     const float k = keep_scale(p_drop, seed, index);
-    if (relu && !((xhat * gamma + beta) * k > 0.f)) return 0.f;
-    return dy * k;
+    return ((xhat * gamma + beta) * k > 0.f) ? dy * k : dy * k * slope;
 }
 
 __global__ void __launch_bounds__(TX * TY) bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                                                                 const float* __restrict__ var, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, const float* __restrict__ dy,
-                                                                float eps, float p_drop, unsigned long long seed, int relu,
+                                                                float eps, float p_drop, unsigned long long seed, float relu,
                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                 int batch, int features) {
     __shared__ float red[TY][TX + 1];
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* _
                                                                   const float* __restrict__ var, const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, const float* __restrict__ dy,
                                                                   const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-                                                                  float eps, float p_drop, unsigned long long seed, int relu,
+                                                                  float eps, float p_drop, unsigned long long seed, float relu,
                                                                   int batch_stats, float* __restrict__ dx, int batch, int features) {
     const int h = (blockIdx.x * EW_THREADS + threadIdx.x) * VEC;
     if (h >= features) return;
@@ -159,6 +160,35 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* _
     }
 }
 
+// training_template.ipynb:176-180 (notebook MLP): x = leaky_relu(block(x) + residual) -- out = act(a + b), and its
+// backward (the same gradient flows to both addends); :132 nn.Sigmoid on the output layer and its backward.
+__global__ void __launch_bounds__(256) add_act_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                                          long long count, float slope) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) {
+        const float z = __ldg(a + e) + __ldg(b + e);
+        out[e] = z > 0.f ? z : slope * z;
+    }
+}
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ out, const float* __restrict__ g, float* __restrict__ gin,
+                                                      long long count, float slope) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride)
+        gin[e] = __ldg(out + e) > 0.f ? __ldg(g + e) : slope * __ldg(g + e);      // slope > 0: sign(out) = sign(a + b)
+}
+__global__ void __launch_bounds__(256) sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) y[e] = 1.0f / (1.0f + expf(-__ldg(x + e)));
+}
+__global__ void __launch_bounds__(256) sigmoid_bwd_kernel(const float* __restrict__ y, const float* __restrict__ g, float* __restrict__ gx, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) {
+        const float v = __ldg(y + e);
+        gx[e] = __ldg(g + e) * v * (1.0f - v);
+    }
+}
+static int ew_blocks(long long count) { return (int)std::min<long long>((count + 255) / 256, 148LL * 16); }
+
 static bool vec4_ok(int features, const void* a, const void* b, const void* c) {
     return features % 4 == 0 && aligned16(a) && aligned16(b) && (!c || aligned16(c));
 }
@@ -177,7 +207,7 @@ extern "C" int gsr_bn_stats_f32(const float* x, int batch, int features, float* 
 }
 
 extern "C" int gsr_bn_act_fwd_f32(const float* x, const float* mean, const float* var, const float* gamma,
-                                  const float* beta, float eps, float p_drop, unsigned long long seed, int relu,
+                                  const float* beta, float eps, float p_drop, unsigned long long seed, float relu,
                                   float* y, int batch, int features, void* stream) {
     if (!x || !mean || !var || !gamma || !beta || !y || batch <= 0 || features <= 0 || !(p_drop >= 0.f && p_drop < 1.f))
         return fail(GSR_E_ARG, "bn_act_fwd: bad argument");
@@ -192,7 +222,7 @@ extern "C" int gsr_bn_act_fwd_f32(const float* x, const float* mean, const float
 
 extern "C" int gsr_bn_act_bwd_f32(const float* x, const float* mean, const float* var, const float* gamma,
                                   const float* beta, const float* dy, float eps, float p_drop,
-                                  unsigned long long seed, int relu, int batch_stats, float* dx, float* dgamma,
+                                  unsigned long long seed, float relu, int batch_stats, float* dx, float* dgamma,
                                   float* dbeta, int batch, int features, void* stream) {
     if (!x || !mean || !var || !gamma || !beta || !dy || !dx || !dgamma || !dbeta || batch <= 0 || features <= 0 ||
         !(p_drop >= 0.f && p_drop < 1.f))
@@ -210,4 +240,29 @@ extern "C" int gsr_bn_act_bwd_f32(const float* x, const float* mean, const float
     if (v4) mlp::bn_bwd_apply_kernel<4><<<grid, mlp::EW_THREADS, 0, st>>>(x, mean, var, gamma, beta, dy, dgamma, dbeta, eps, p_drop, seed, relu, batch_stats, dx, batch, features);
     else mlp::bn_bwd_apply_kernel<1><<<grid, mlp::EW_THREADS, 0, st>>>(x, mean, var, gamma, beta, dy, dgamma, dbeta, eps, p_drop, seed, relu, batch_stats, dx, batch, features);
     return launched("bn_bwd_apply");
+}
+
+extern "C" int gsr_add_act_fwd_f32(const float* a, const float* b, float* out, long long count, float negative_slope, void* stream) {
+    if (!a || !b || !out || count < 0) return fail(GSR_E_ARG, "add_act_fwd: bad argument");
+    if (count == 0) return 0;
+    mlp::add_act_fwd_kernel<<<mlp::ew_blocks(count), 256, 0, (cudaStream_t)stream>>>(a, b, out, count, negative_slope);
+    return launched("add_act_fwd");
+}
+extern "C" int gsr_act_bwd_f32(const float* out, const float* grad_out, float* grad_in, long long count, float negative_slope, void* stream) {
+    if (!out || !grad_out || !grad_in || count < 0) return fail(GSR_E_ARG, "act_bwd: bad argument");
+    if (count == 0) return 0;
+    mlp::act_bwd_kernel<<<mlp::ew_blocks(count), 256, 0, (cudaStream_t)stream>>>(out, grad_out, grad_in, count, negative_slope);
+    return launched("act_bwd");
+}
+extern "C" int gsr_sigmoid_fwd_f32(const float* x, float* y, long long count, void* stream) {
+    if (!x || !y || count < 0) return fail(GSR_E_ARG, "sigmoid_fwd: bad argument");
+    if (count == 0) return 0;
+    mlp::sigmoid_fwd_kernel<<<mlp::ew_blocks(count), 256, 0, (cudaStream_t)stream>>>(x, y, count);
+    return launched("sigmoid_fwd");
+}
+extern "C" int gsr_sigmoid_bwd_f32(const float* y, const float* grad_y, float* grad_x, long long count, void* stream) {
+    if (!y || !grad_y || !grad_x || count < 0) return fail(GSR_E_ARG, "sigmoid_bwd: bad argument");
+    if (count == 0) return 0;
+    mlp::sigmoid_bwd_kernel<<<mlp::ew_blocks(count), 256, 0, (cudaStream_t)stream>>>(y, grad_y, grad_x, count);
+    return launched("sigmoid_bwd");
 }

@@ -928,7 +928,7 @@ extern "C" int gsr_tcgemm_f32(const float* A, const float* B, float* C,
     tc::Params p{A, B, C, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch, 1, alpha,
                  epilogue, extra, ld_extra, stride_extra};
     if (!tc::operands_ok(p)) return fail(GSR_E_ALIGN, "tcgemm: operands must be 16-byte aligned with leading dimensions % 4 == 0");
-    if (tc::g_pairs && tc::pair_ok(p) && tc::tma_ok(p, transA, transB)) {
+    if (tc::g_pairs && tc::tma_ok(p, transA, transB)) {
         // TMA-fed persistent CTA pairs (csrc/tcgemm_tma.cu) for the first 256 floor(M / 256) rows; the remaining rows on the
         // FP32 ragged-row kernels (<= 16 rows: the 12 rows a 268-row subject matrix leaves) or the one-CTA tensor kernel
         int rc = tc::tma_launch(p, transA, transB, false, batch, (cudaStream_t)stream);

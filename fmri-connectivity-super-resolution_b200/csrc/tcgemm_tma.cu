@@ -62,6 +62,7 @@ constexpr int TMEM_COLS = 512;
 
 struct Plan {
     int tiles_m;            // pair tiles along M per batch item
+    int tiles_n, n_tile;    // column tiles per row tile (1 unless N > 272: then 256 columns each, MLP-sized products)
     int items;              // output batch items (REDUCE: splits)
     int nsub;               // REDUCE: subjects accumulated in all (else 1 per item)
     int splits;             // REDUCE: stride between the subjects of an item
@@ -149,7 +150,8 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_rank();
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    const int total_tiles = p.items * p.tiles_m;
+    const int tiles_mn = p.tiles_m * p.tiles_n;                       // tile = (item z, row tile mp, column tile nt), nt fastest
+    const int total_tiles = p.items * tiles_mn;
     const int R0 = p.nr0 >> 1, R1 = p.nr1 >> 1;                       // this CTA's share of the two B ranges
     const uint32_t b_bytes = (uint32_t)p.b_bytes;
     const int kb_per_tile = (REDUCE ? (p.nsub + p.splits - 1) / p.splits : 1) * p.nkb;   // upper bound, exact below
@@ -176,14 +178,14 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // cp.async.bulk.prefetch.tensor (L2 only); measured slower, off by default (g_pf_ahead).
         if (lane == 0) {
             struct Blk { int tile, sub, kb; };
-            auto nsub_of = [&](int tile) { return REDUCE ? (p.nsub - tile / p.tiles_m + p.splits - 1) / p.splits : 1; };
+            auto nsub_of = [&](int tile) { return REDUCE ? (p.nsub - tile / tiles_mn + p.splits - 1) / p.splits : 1; };
             auto next = [&](Blk& b) {
                 if (++b.kb == p.nkb) { b.kb = 0; if (++b.sub == nsub_of(b.tile)) { b.sub = 0; b.tile += n_clusters; } }
             };
             // issue the boxes of one k-block: PREFETCH -> into L2, else into raw slot `s` signalling `full`
             auto boxes = [&](const Blk& blk, bool prefetch, uint32_t a_dst, uint32_t full) {
-                const int z = blk.tile / p.tiles_m, mp = blk.tile - z * p.tiles_m;
-                const int m0 = mp * 256 + (int)rank * BM;
+                const int z = blk.tile / tiles_mn, mn = blk.tile - z * tiles_mn, mp = mn / p.tiles_n;
+                const int m0 = mp * 256 + (int)rank * BM, n0 = (mn - mp * p.tiles_n) * p.n_tile;
                 const int b = REDUCE ? z + blk.sub * p.splits : z;
                 const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
                 const int k0 = blk.kb * BK;
@@ -197,12 +199,12 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     for (int j = 0; j < BM / 32; ++j) ld(a_dst + j * 4096, &mapA, m0 + 32 * j, k0, ba);        // box {32 m, 32 k}
                 }
                 if (TB) {                                                                           // boxes {32 k, R0 n}, {32 k, R1 n}
-                    ld(b_dst, &mapB0, k0, R0 * (int)rank, bb);
-                    if (R1 > 0) ld(b_dst + p.b_off1, &mapB1, k0, p.nr0 + R1 * (int)rank, bb);
+                    ld(b_dst, &mapB0, k0, n0 + R0 * (int)rank, bb);
+                    if (R1 > 0) ld(b_dst + p.b_off1, &mapB1, k0, n0 + p.nr0 + R1 * (int)rank, bb);
                 } else {                                                                            // box {32 n, 32 k} per 32 columns
                     // (a range whose share is not a multiple of 32 columns uses the head of its last block only)
-                    for (int j = 0; j < (R0 + 31) / 32; ++j) ld(b_dst + j * 4096, &mapB0, R0 * (int)rank + 32 * j, k0, bb);
-                    for (int j = 0; j < (R1 + 31) / 32; ++j) ld(b_dst + p.b_off1 + j * 4096, &mapB0, p.nr0 + R1 * (int)rank + 32 * j, k0, bb);
+                    for (int j = 0; j < (R0 + 31) / 32; ++j) ld(b_dst + j * 4096, &mapB0, n0 + R0 * (int)rank + 32 * j, k0, bb);
+                    for (int j = 0; j < (R1 + 31) / 32; ++j) ld(b_dst + p.b_off1 + j * 4096, &mapB0, n0 + p.nr0 + R1 * (int)rank + 32 * j, k0, bb);
                 }
             };
             Blk cur{cluster_id, 0, 0}, pf{cluster_id, 0, 0};
@@ -233,7 +235,7 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint32_t n1 = (uint32_t)p.b_off1 >> 4;                    // start of the second range inside a B tile
             uint32_t it = 0, tile_n = 0, kstep_n = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++tile_n) {
-                const int z = tile / p.tiles_m;
+                const int z = tile / tiles_mn;
                 const int nsub = REDUCE ? (p.nsub - z + p.splits - 1) / p.splits : 1;
                 T3_STAMP(1, it, 3);
                 // every epilogue warp of both CTAs has read the columns tile t - 1 shares with this tile's accumulator
@@ -304,7 +306,7 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int b_vec = p.b_bytes >> 4;                                    // float4s of this CTA's B tile
         uint32_t it = 0;
         for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-            const int z = tile / p.tiles_m;
+            const int z = tile / tiles_mn;
             const int nkbt = (REDUCE ? (p.nsub - z + p.splits - 1) / p.splits : 1) * p.nkb;
             for (int kbt = 0; kbt < nkbt; ++kbt, ++it) {
                 const uint32_t rs = it % RAW_STAGES, ruse = it / RAW_STAGES, ls = it % LO_STAGES, luse = it / LO_STAGES;
@@ -344,15 +346,18 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int q = warp & 3;                                              // tensor-memory lane quarter of this warp
         uint8_t* my_stg = stg + (warp - 2 - CONV_WARPS) * 2 * STG_BYTES;
         const uint32_t empty_leader = map_to_cta(bar_tmem_empty, 0);
-        const int chunks = (p.N + 31) >> 5;
+        const int chunks_full = (min(p.N, p.n_tile) + 31) >> 5;             // chunks of a full column tile
         const int npad = p.nr0 + p.nr1;
         // chunks of an even tile (accumulator at column 0) that lie in the columns the next (odd) tile accumulates
         // into are drained first: [acc_base1 / 32, chunks); an odd tile shares its first (npad - acc_base1) columns
-        const int even_first = min(chunks, p.acc_base1 >> 5);
-        const int even_cnt = chunks - even_first, odd_cnt = min(chunks, (max(npad - p.acc_base1, 0) + 31) >> 5);
+        const int even_first_full = min(chunks_full, p.acc_base1 >> 5);
+        const int odd_cnt_full = min(chunks_full, (max(npad - p.acc_base1, 0) + 31) >> 5);
         uint32_t tile_n = 0, nstore = 0;
         for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++tile_n) {
-            const int z = tile / p.tiles_m, mp = tile - z * p.tiles_m;
+            const int z = tile / tiles_mn, mn = tile - z * tiles_mn, mp = mn / p.tiles_n;
+            const int ncol0 = (mn - mp * p.tiles_n) * p.n_tile;              // first output column of this tile
+            const int chunks = min(chunks_full, (p.N - ncol0 + 31) >> 5);    // the last column tile may be ragged
+            const int even_first = min(chunks, even_first_full), even_cnt = chunks - even_first, odd_cnt = min(chunks, odd_cnt_full);
             const int row0 = mp * 256 + (int)rank * BM + q * 32;             // first output row of this warp
             const float* extra_row = nullptr;
             if (!REDUCE && p.epilogue == GSR_EPI_ADD) extra_row = p.extra + (size_t)z * p.s_extra + (size_t)(row0 + lane) * p.ld_extra;
@@ -369,7 +374,7 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (q == 0 && lane == 0) T3_STAMP(3, tile_n, 2);
             };
             auto emit = [&](uint32_t (&v)[32], int c) {                      // alpha / bias / addend, staging block, TMA store
-                const int n0 = c * 32;
+                const int n0 = ncol0 + c * 32;
                 uint8_t* blk = my_stg + (nstore & 1) * STG_BYTES;
                 if (nstore >= 2) { if (lane == 0) tma_wait_read<1>(); __syncwarp(); }     // the store that last read this block is done
 #pragma unroll
@@ -499,7 +504,6 @@ bool tma_ok(const Params& p, int transA, int transB) {
     (void)transA;
     if (!g_tma || !t3::encode_fn()) return false;
     if (p.M < 256 || p.K < 1 || p.N % 4 != 0) return false;
-    if (p.N > 272) return false;
     if (p.lda % 4 || p.ldb % 4 || p.ldc % 4 || p.sA % 4 || p.sB % 4 || p.sC % 4) return false;
     if (!aligned16(p.A) || !aligned16(p.B) || !aligned16(p.C)) return false;
     if (p.epilogue != GSR_EPI_NONE && !aligned16(p.extra)) return false;
@@ -511,6 +515,8 @@ int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, c
     using namespace t3;
     Plan pl{};
     pl.tiles_m = p.M / 256;
+    pl.n_tile = p.N <= 272 ? 272 : 256;
+    pl.tiles_n = p.N <= 272 ? 1 : (p.N + 255) / 256;
     pl.items = zdim;
     pl.nsub = reduce ? p.batch : 1;
     pl.splits = reduce ? p.splits : 1;
@@ -519,13 +525,13 @@ int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, c
     // the 268-wide products (the split round 1 probed).  MN-major B lives in 32-column blocks (SWIZZLE_128B_BASE32B
     // atoms); a range may end inside a block -- 256 + 16 for 268 columns, the second range reading the first 8 columns
     // of one block per CTA -- unless gsr_set_tuning("tcgemm_mn_partial", 0) restores whole blocks (192 + 128).
-    const int npad16 = (p.N + 15) & ~15;
+    const int npad16 = (std::min(p.N, pl.n_tile) + 15) & ~15;
     if (transB) {
         if (npad16 <= 256) { pl.nr0 = npad16; pl.nr1 = 0; } else { pl.nr0 = 160; pl.nr1 = npad16 - 160; }
     } else if (g_mn_partial) {
         if (npad16 <= 256) { pl.nr0 = npad16; pl.nr1 = 0; } else { pl.nr0 = 256; pl.nr1 = npad16 - 256; }
     } else {
-        const int npad = (p.N + 63) & ~63;
+        const int npad = (std::min(p.N, pl.n_tile) + 63) & ~63;
         if (npad <= 256) { pl.nr0 = npad; pl.nr1 = 0; } else { pl.nr0 = 192; pl.nr1 = npad - 192; }
     }
     {
@@ -557,7 +563,7 @@ int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, c
     // C: [items][M][N]; REDUCE writes partial sums of pitch sC = M * N, one per split
     ok = ok && make_map(&mC, p.C, p.N, p.M, zdim, reduce ? p.N : p.ldc, p.sC, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
     if (!ok) return fail(GSR_E_UNSUPPORTED, "tcgemm (TMA): cuTensorMapEncodeTiled failed");
-    const int total_tiles = pl.items * pl.tiles_m;
+    const int total_tiles = pl.items * pl.tiles_m * pl.tiles_n;
     const int clusters = std::min(total_tiles, kNumSMs / 2);
     dim3 grid(2 * clusters, 1, 1);
 #define GSR_T3_LAUNCH(TA, TB, RED)                                                                                \

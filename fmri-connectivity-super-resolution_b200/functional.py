@@ -133,7 +133,74 @@ def batch_norm_act(x, gamma, beta, running_mean, running_var, training, momentum
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     else:
         mean, var, p_drop = running_mean, running_var, 0.0
-    return BatchNormActFn.apply(x, gamma, beta, mean, var, float(eps), float(p_drop), int(seed or 0), bool(relu), bool(training))
+    relu = relu if isinstance(relu, float) else bool(relu)        # a float is the negative slope of a LeakyReLU
+    return BatchNormActFn.apply(x, gamma, beta, mean, var, float(eps), float(p_drop), int(seed or 0), relu, bool(training))
+
+
+class AddActFn(Function):
+    """training_template.ipynb:176-180: ``F.leaky_relu(block(x) + residual, negative_slope)`` in one pass."""
+
+    @staticmethod
+    def forward(ctx, a, b, negative_slope):
+        out = K.add_act_fwd(a, b, negative_slope)
+        ctx.save_for_backward(out)
+        ctx.slope = negative_slope
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        gi = K.act_bwd(out, _c(g), ctx.slope)
+        return gi, gi, None
+
+
+class SigmoidFn(Function):
+    """training_template.ipynb:132: nn.Sigmoid of the output layer."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = K.sigmoid_fwd(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        return K.sigmoid_bwd(y, _c(g))
+
+
+class TriuFlattenFn(Function):
+    """``x[:, mask]`` with the strict-upper-triangle mask (training_template.ipynb:121,166): row-major triangle of every
+    matrix; backward scatters into the upper triangle only (no mirror: the mask selects those entries alone)."""
+
+    @staticmethod
+    def forward(ctx, dense):
+        ctx.n = dense.shape[-1]
+        return K.triu_flatten(dense)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        full = K.anti_vectorize(_c(g), ctx.n)            # symmetric fill ...
+        return torch.triu(full, diagonal=1)              # ... of which the mask's gradient is the upper half
+
+
+class SymFromTriuFn(Function):
+    """``matrix[:, mask] = x; matrix + matrix^T`` (training_template.ipynb:186-190): symmetric zero-diagonal matrices from
+    row-major upper triangles -- gsr_anti_vectorize; backward = upper + lower triangle of the gradient, flattened."""
+
+    @staticmethod
+    def forward(ctx, vec, n):
+        ctx.n = n
+        return K.anti_vectorize(vec, n)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        g = _c(g)
+        return K.triu_flatten(g + g.transpose(-1, -2)), None
 
 
 # ----------------------------------------------------------------------------- a8 / a9

@@ -510,26 +510,66 @@ def bn_stats(x: torch.Tensor, running_mean=None, running_var=None, momentum: flo
     return mean, var
 
 
-def bn_act_fwd(x, mean, var, gamma, beta, eps: float, p_drop: float, seed: int, relu: bool) -> torch.Tensor:
+def _slope(relu) -> float:
+    """`relu` of the BatchNorm pass: True / False (nn.ReLU or nothing, models/mlp.py) or the negative slope of a
+    LeakyReLU as a float (0.01 in the notebook MLP)."""
+    if relu is True:
+        return 0.0
+    if relu is False or relu is None:
+        return 1.0
+    return float(relu)
+
+
+def bn_act_fwd(x, mean, var, gamma, beta, eps: float, p_drop: float, seed: int, relu) -> torch.Tensor:
     x = _f32(x, "bn_act_fwd: x")
     B, H = x.shape
     y = torch.empty_like(x)
     check(lib().gsr_bn_act_fwd_f32(x.data_ptr(), mean.data_ptr(), var.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                   float(eps), float(p_drop), int(seed), int(relu), y.data_ptr(), B, H, _stream()),
+                                   float(eps), float(p_drop), int(seed), _slope(relu), y.data_ptr(), B, H, _stream()),
           "gsr_bn_act_fwd_f32")
     return y
 
 
-def bn_act_bwd(x, mean, var, gamma, beta, dy, eps: float, p_drop: float, seed: int, relu: bool, batch_stats: bool):
+def bn_act_bwd(x, mean, var, gamma, beta, dy, eps: float, p_drop: float, seed: int, relu, batch_stats: bool):
     x, dy = _f32(x, "bn_act_bwd: x"), _f32(dy, "bn_act_bwd: dy")
     B, H = x.shape
     dx = torch.empty_like(x)
     dgamma, dbeta = torch.empty((H,), device=x.device), torch.empty((H,), device=x.device)
     check(lib().gsr_bn_act_bwd_f32(x.data_ptr(), mean.data_ptr(), var.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                   dy.data_ptr(), float(eps), float(p_drop), int(seed), int(relu), int(batch_stats),
+                                   dy.data_ptr(), float(eps), float(p_drop), int(seed), _slope(relu), int(batch_stats),
                                    dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), B, H, _stream()),
           "gsr_bn_act_bwd_f32")
     return dx, dgamma, dbeta
+
+
+def add_act_fwd(a: torch.Tensor, b: torch.Tensor, negative_slope: float) -> torch.Tensor:
+    a, b = _f32(a, "add_act: a"), _f32(b, "add_act: b")
+    if a.shape != b.shape:
+        raise ValueError("add_act: shape mismatch")
+    out = torch.empty_like(a)
+    check(lib().gsr_add_act_fwd_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), float(negative_slope), _stream()), "gsr_add_act_fwd_f32")
+    return out
+
+
+def act_bwd(out: torch.Tensor, grad_out: torch.Tensor, negative_slope: float) -> torch.Tensor:
+    out, grad_out = _f32(out, "act_bwd: out"), _f32(grad_out, "act_bwd: grad")
+    g = torch.empty_like(out)
+    check(lib().gsr_act_bwd_f32(out.data_ptr(), grad_out.data_ptr(), g.data_ptr(), out.numel(), float(negative_slope), _stream()), "gsr_act_bwd_f32")
+    return g
+
+
+def sigmoid_fwd(x: torch.Tensor) -> torch.Tensor:
+    x = _f32(x, "sigmoid: x")
+    y = torch.empty_like(x)
+    check(lib().gsr_sigmoid_fwd_f32(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "gsr_sigmoid_fwd_f32")
+    return y
+
+
+def sigmoid_bwd(y: torch.Tensor, grad_y: torch.Tensor) -> torch.Tensor:
+    y, grad_y = _f32(y, "sigmoid_bwd: y"), _f32(grad_y, "sigmoid_bwd: grad")
+    g = torch.empty_like(y)
+    check(lib().gsr_sigmoid_bwd_f32(y.data_ptr(), grad_y.data_ptr(), g.data_ptr(), y.numel(), _stream()), "gsr_sigmoid_bwd_f32")
+    return g
 
 
 # --------------------------------------------------------------------- flat gradient bucket

@@ -275,7 +275,9 @@ GSR_API int gsr_flat_unpack(float* const* ptrs, const long long* offsets, int n_
  * gsr_bn_stats_f32: training statistics of nn.BatchNorm1d -- mean[features], biased
  *   var[features]; when running_mean / running_var are given they are updated in place as
  *   torch does ((1 - momentum) * running + momentum * batch value, unbiased variance).
- * gsr_bn_act_fwd_f32: y = relu?( drop( gamma * (x - mean) / sqrt(var + eps) + beta ) ).
+ * gsr_bn_act_fwd_f32: y = act( drop( gamma * (x - mean) / sqrt(var + eps) + beta ) ), act(z) = z > 0 ? z :
+ *   negative_slope * z -- 0 is nn.ReLU (models/mlp.py), 0.01 the notebook model's nn.LeakyReLU
+ *   (training_template.ipynb:117), 1 no activation.
  *   (mean, var) are the batch statistics when training, the running estimates in eval mode.
  *   Dropout keeps element e iff u(seed, e) >= p_drop and scales by 1 / (1 - p_drop), u being
  *   the top 24 bits of splitmix64(seed + e * 0x9E3779B97F4A7C15) / 2^24; p_drop = 0 disables
@@ -285,12 +287,21 @@ GSR_API int gsr_flat_unpack(float* const* ptrs, const long long* offsets, int n_
 GSR_API int gsr_bn_stats_f32(const float* x, int batch, int features, float* mean, float* var,
                      float* running_mean, float* running_var, float momentum, void* stream);
 GSR_API int gsr_bn_act_fwd_f32(const float* x, const float* mean, const float* var, const float* gamma,
-                       const float* beta, float eps, float p_drop, unsigned long long seed, int relu,
+                       const float* beta, float eps, float p_drop, unsigned long long seed, float negative_slope,
                        float* y, int batch, int features, void* stream);
 GSR_API int gsr_bn_act_bwd_f32(const float* x, const float* mean, const float* var, const float* gamma,
                        const float* beta, const float* dy, float eps, float p_drop,
-                       unsigned long long seed, int relu, int batch_stats, float* dx, float* dgamma,
+                       unsigned long long seed, float negative_slope, int batch_stats, float* dx, float* dgamma,
                        float* dbeta, int batch, int features, void* stream);
+/* The notebook MLP of BASELINE configs[3] (training_template.ipynb:100-216: 12 720 -> hidden -> 35 778 on vectorised
+ * triangles) adds, around the same Linear / BatchNorm passes:
+ * gsr_add_act_fwd_f32: out = act(a + b)  -- the residual connection and F.leaky_relu of :176-180;
+ * gsr_act_bwd_f32:     grad_in = grad_out * (out > 0 ? 1 : negative_slope)  (the same for both addends);
+ * gsr_sigmoid_fwd_f32 / gsr_sigmoid_bwd_f32: nn.Sigmoid of the output layer (:132), grad_x = grad_y * y * (1 - y).   */
+GSR_API int gsr_add_act_fwd_f32(const float* a, const float* b, float* out, long long count, float negative_slope, void* stream);
+GSR_API int gsr_act_bwd_f32(const float* out, const float* grad_out, float* grad_in, long long count, float negative_slope, void* stream);
+GSR_API int gsr_sigmoid_fwd_f32(const float* x, float* y, long long count, void* stream);
+GSR_API int gsr_sigmoid_bwd_f32(const float* y, const float* grad_y, float* grad_x, long long count, void* stream);
 
 /* ------------------------------------------------------------------ N3 (SURVEY 8 f)
  * torch.optim.Adam(model.parameters(), lr) of training_gsr.ipynb:72 over all parameter tensors in

@@ -88,3 +88,21 @@ if "--sweep" in sys.argv:
             ms = timeit(fn); r[name] = [round(ms, 4), round(flops / ms / 1e9, 1)]
         print(json.dumps(r), flush=True)
     pkg.set_tuning("tcgemm_prefetch", 0)
+# MLP-sized products: N > 272 -> 256-column tiles in the TMA kernel
+for tma in (0, 1):
+    pkg.set_tuning("tcgemm_tma", tma)
+    Xm = torch.randn(512, 1024, device="cuda", generator=g); Wm = torch.randn(35778, 1024, device="cuda", generator=g) * 0.03
+    bm = torch.randn(35778, device="cuda", generator=g)
+    X1 = torch.randn(512, 12720, device="cuda", generator=g); W1 = torch.randn(1024, 12720, device="cuda", generator=g) * 0.01
+    for name, fn, ref, flops in (
+            ("MLP out 512x1024 . (35778x1024)^T + bias", lambda: K.bgemm(Xm, Wm, transB=True, bias=bm), lambda: Xm.double() @ Wm.double().T + bm.double(), 2 * 512 * 1024 * 35778),
+            ("MLP in 512x12720 . (1024x12720)^T", lambda: K.bgemm(X1, W1, transB=True), lambda: X1.double() @ W1.double().T, 2 * 512 * 12720 * 1024),
+            ("MLP dX 512x35778 . 35778x1024", lambda: K.bgemm(K.bgemm(Xm, Wm, transB=True), Wm), None, 2 * 512 * 1024 * 35778),
+            ("MLP dW (512x35778)^T . 512x1024", lambda: K.bgemm(K.bgemm(Xm, Wm, transB=True), Xm, transA=True), None, 2 * 512 * 1024 * 35778)):
+        out = fn(); torch.cuda.synchronize()
+        rec = {"tma": tma, "case": name}
+        if ref is not None:
+            r = ref(); rec["rel"] = float((out.double() - r).abs().max()) / float(r.abs().max())
+        ms = timeit(fn, reps=5); rec["ms"] = round(ms, 4); rec["tflops"] = round(flops / ms / 1e9, 1)
+        print(json.dumps(rec), flush=True)
+pkg.set_tuning("tcgemm_tma", 1)
