@@ -127,6 +127,13 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
+// Remote arrive with the default (release, CTA-scope) semantics.  For a producer whose DATA stays in its own CTA's shared
+// memory -- already fenced to the async proxy with fence.proxy.async -- and whose consumer is a tcgen05.mma the leader
+// issues afterwards: only the arrival itself crosses the CTA boundary.  The cluster-scope release above costs
+// 0.6-1.6 us per arrival inside the k-loop (profiles/r2_tcgemm3_pipeline_trace.txt).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
@@ -163,7 +170,7 @@ __device__ __forceinline__ uint32_t instr_desc2(int n, int a_mn_major, int b_mn_
 
 // csrc/tcgemm_tma.cu: the TMA-fed persistent CTA-pair kernel.  tma_ok: shapes / alignments it takes (the caller has
 // already applied pair_ok); tma_launch covers the first 256 * floor(M / 256) rows of every batch item.
-extern int g_tma, g_utccp, g_mn_partial, g_pf_ahead;       // gsr_set_tuning("tcgemm_tma" | "tcgemm_utccp" | "tcgemm_mn_partial", 0|1)
+extern int g_tma, g_utccp, g_mn_partial, g_pf_ahead, g_tmem_a, g_cluster_release;       // gsr_set_tuning("tcgemm_tma" | "tcgemm_utccp" | "tcgemm_mn_partial", 0|1)
 bool tma_ok(const Params& p, int transA, int transB);
 int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, cudaStream_t st);
 

@@ -31,6 +31,13 @@ int g_utccp = 0;            // gsr_set_tuning("tcgemm_utccp", 0|1): K-major A th
                             // traffic per k-block, but the copies execute IN the tensor pipe, in order with the MMAs (8 x ~64 clk per
                             // k-block): the MMA thread's issue -> commit time goes from 1.15 to 1.5 us and the stacked product from
                             // 0.259 to 0.277 ms.  Kept as a switch.
+int g_tmem_a = 0;           // gsr_set_tuning("tcgemm_tmem_a", 0|1): the hi term of op(A) in TENSOR MEMORY, written by the converter warps
+                            // with tcgen05.st while they compute lo -- four of the six MMAs of a k-step then read A there instead of
+                            // re-reading 4 KB of shared memory each (66 of the 252 KB of shared-memory traffic per k-block).  Exact, but
+                            // measured no faster (stacked NT 0.265 against 0.259 ms): the MMAs of a k-block take 1.15-1.25 us with either
+                            // operand source (the tensor pipe, not its shared-memory reads, is what they wait for), and the two 32-column
+                            // A stages leave room for a 4-chunk instead of a 2-chunk accumulator overlap.  Off by default.
+int g_cluster_release = 0;  // gsr_set_tuning("tcgemm_cluster_release", 0|1): see mbar_arrive_remote (csrc/tcgemm.cuh)
 int g_pf_ahead = 0;         // gsr_set_tuning("tcgemm_prefetch", k): k-blocks of L2 prefetch (cp.async.bulk.prefetch.tensor) in front of the
                             // TMA loads; default off -- measured monotonically slower (stacked NN 0.272 / 0.290 / 0.291 / 0.287 / 0.310 ms
                             // for k = 0 / 3 / 6 / 9 / 12): the load latency is not what bounds the k-block rate
@@ -70,9 +77,11 @@ struct Plan {
     int nr0, nr1;           // UMMA N of the two accumulator column ranges (nr1 may be 0)
     int acc_base1;          // tensor-memory column of the odd tiles' accumulator (even tiles: 0); the two overlap when 2 (nr0 + nr1) > 512
     int a_ring;             // tensor-memory column of the A-operand ring (tcgen05.cp, K-major A only); 0 = A is read from shared memory
+    int a_hi_col;           // tensor-memory column of the A-hi stages (2 x 32 columns, written by the converters); 0 = off
     int b_off1;             // byte offset of the second range inside a B tile
     int b_bytes;            // bytes of this CTA's B tile per k-block (TMA transaction count)
     int pf_ahead;           // k-blocks the L2 prefetch cursor runs in front of the loads (0 = off)
+    int cluster_release;    // remote mbarrier arrivals with release.cluster (1) or the default release.cta (0)
     int a_batched, b_batched;
     float alpha;
     int epilogue;
@@ -108,6 +117,14 @@ __device__ __forceinline__ void umma2_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, 
                  "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], db, %4, p;\n\t}"
                  :: "r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+
+// registers -> tensor memory: lane = this thread's row, 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // tcgen05.ld without the wait, and a wait the compiler cannot move uses of the destination registers across
 __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
@@ -227,6 +244,8 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (rank == 0 && lane == 0) {
             const uint32_t idesc0 = instr_desc2(p.nr0, TA ? 1 : 0, TB ? 0 : 1);
             const uint32_t idesc1 = instr_desc2(p.nr1 > 0 ? p.nr1 : 16, TA ? 1 : 0, TB ? 0 : 1);
+            // A in tensor memory is always "K-major" (lane = row, column = k)
+            const uint32_t idesc0t = instr_desc2(p.nr0, 0, TB ? 0 : 1), idesc1t = instr_desc2(p.nr1 > 0 ? p.nr1 : 16, 0, TB ? 0 : 1);
             // K-major (SWIZZLE_128B): 8-row groups 1024 bytes apart (SBO), k-step of 8 floats = +32 bytes
             // MN-major (SWIZZLE_128B_BASE32B): 32-wide blocks 4096 bytes apart (LBO), 4-k groups 512 bytes apart (SBO), k-step = +1024
             const uint32_t a_dhi = TA ? desc_hi(512, 1) : desc_hi(1024, 2), b_dhi = TB ? desc_hi(1024, 2) : desc_hi(512, 1);
@@ -257,7 +276,23 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         uint32_t ah = desc_lo(hb, a_lbo), al = desc_lo(lb, a_lbo);
                         uint32_t bh = desc_lo(hb + A_TILE, b_lbo), bl = desc_lo(lb + A_TILE, b_lbo);
                         const int ksteps = min(BK / 8, (p.K - kb * BK + 7) >> 3);
-                        if (!TA && p.a_ring) {
+                        if (p.a_hi_col) {
+                            // A-hi in tensor memory (converter warps, tcgen05.st): lo.hi reads A-lo from shared memory,
+                            // hi.lo and hi.hi read A-hi at 8 columns per k-step of stage `ls`
+                            const uint32_t t_a = tmem_base + (uint32_t)p.a_hi_col + 32u * ls;
+                            for (int j = 0; j < ksteps; ++j) {
+                                umma2_tf32(tacc, al, a_dhi, bh, b_dhi, idesc0, acc);
+                                umma2_tf32_ts(tacc, t_a + 8u * j, bl, b_dhi, idesc0t, 1u);
+                                umma2_tf32_ts(tacc, t_a + 8u * j, bh, b_dhi, idesc0t, 1u);
+                                if (p.nr1 > 0) {
+                                    umma2_tf32(tacc + p.nr0, al, a_dhi, bh + n1, b_dhi, idesc1, acc);
+                                    umma2_tf32_ts(tacc + p.nr0, t_a + 8u * j, bl + n1, b_dhi, idesc1t, 1u);
+                                    umma2_tf32_ts(tacc + p.nr0, t_a + 8u * j, bh + n1, b_dhi, idesc1t, 1u);
+                                }
+                                acc = 1u;
+                                al += a_step; bh += b_step; bl += b_step;
+                            }
+                        } else if (!TA && p.a_ring) {
                             // A through tensor memory: one tcgen05.cp per k-step and term moves the 128 x 8 slice of this
                             // CTA's rows (both CTAs of the pair execute it) into 8 columns; the six MMAs of the k-step then
                             // read A there instead of re-reading 6 x 4 KB of shared memory.  cp and mma execute in issue
@@ -315,6 +350,60 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (ct == 0) T3_STAMP(2, it, 0);
                 mbar_wait(bar_raw_full + 8 * rs, ruse & 1);                  // TMA bytes of this CTA landed
                 if (ct == 0) T3_STAMP(2, it, 1);
+                auto lo_of = [](float x) { return to_tf32(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); };
+                if (p.a_hi_col) {
+                    // A: thread = (row 32 q + lane, k half h); the raw values go to tensor memory as the hi term (the MMA
+                    // ignores their low mantissa bits), lo back to shared memory at the same place.  B: linear sweep.
+                    const int q = warp & 3, h = (warp - 2) >> 2, row = 32 * q + lane;
+                    uint32_t a[16];
+                    float4 v[5];
+                    const uint8_t* araw = raw + rs * SLOT_BYTES;
+                    uint8_t* alo = lo + ls * SLOT_BYTES;
+                    if (!TA) {                                               // SWIZZLE_128B K-major: 16-byte chunk c of row r at (c ^ (r & 7))
+                        const uint32_t rbase = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const uint4 t = *reinterpret_cast<const uint4*>(araw + rbase + (((4 * h + c) ^ (row & 7)) << 4));
+                            a[4 * c] = t.x; a[4 * c + 1] = t.y; a[4 * c + 2] = t.z; a[4 * c + 3] = t.w;
+                        }
+                    } else {                                                 // 128B_ATOM_32B MN-major: block q, k-row kk, 32-byte chunk (lane >> 3) ^ (kk & 3)
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int kk = 16 * h + i;
+                            a[i] = *reinterpret_cast<const uint32_t*>(araw + q * 4096 + kk * 128 + ((((lane >> 3) ^ (kk & 3))) << 5) + ((lane & 7) << 2));
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const int e = ct + 256 * i;
+                        v[i] = e < b_vec ? src[A_TILE / 16 + e] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (luse > 0) mbar_wait(bar_lo_empty + 8 * ls, (luse - 1) & 1);                 // MMA drained the lo slot and the A-hi stage
+                    if (ct == 0) T3_STAMP(2, it, 2);
+                    tc_fence_after();
+                    tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_hi_col + 32u * ls + 16u * h, a);
+                    if (!TA) {
+                        const uint32_t rbase = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            *reinterpret_cast<float4*>(alo + rbase + (((4 * h + c) ^ (row & 7)) << 4)) =
+                                make_float4(lo_of(__uint_as_float(a[4 * c])), lo_of(__uint_as_float(a[4 * c + 1])),
+                                            lo_of(__uint_as_float(a[4 * c + 2])), lo_of(__uint_as_float(a[4 * c + 3])));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int kk = 16 * h + i;
+                            *reinterpret_cast<float*>(alo + q * 4096 + kk * 128 + ((((lane >> 3) ^ (kk & 3))) << 5) + ((lane & 7) << 2)) = lo_of(__uint_as_float(a[i]));
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const int e = ct + 256 * i;
+                        if (e < b_vec) dst[A_TILE / 16 + e] = make_float4(lo_of(v[i].x), lo_of(v[i].y), lo_of(v[i].z), lo_of(v[i].w));
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                } else {
                 float4 v[9];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) v[i] = src[ct + 256 * i];                               // A: 1024 float4
@@ -335,9 +424,12 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (i < 4) dst[ct + 256 * i] = l;
                     else { const int e = ct + 256 * (i - 4); if (e < b_vec) dst[A_TILE / 16 + e] = l; }
                 }
+                }
+                if (ct == 0) T3_STAMP(2, it, 4);
                 fence_async_smem();                                          // generic-proxy writes -> async proxy (UMMA)
+                if (ct == 0) T3_STAMP(2, it, 5);
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(conv_leader + 8 * ls);    // the leader's conv_full counts the warps of both CTAs
+                if (lane == 0) { if (p.cluster_release) mbar_arrive_cluster(conv_leader + 8 * ls); else mbar_arrive_remote(conv_leader + 8 * ls); }    // the leader's conv_full counts the warps of both CTAs
                 if (ct == 0) T3_STAMP(2, it, 3);
             }
         }
@@ -370,7 +462,7 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             auto release = [&]() {                                           // this warp is done with the shared columns
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(empty_leader);
+                if (lane == 0) { if (p.cluster_release) mbar_arrive_cluster(empty_leader); else mbar_arrive_remote(empty_leader); }
                 if (q == 0 && lane == 0) T3_STAMP(3, tile_n, 2);
             };
             auto emit = [&](uint32_t (&v)[32], int c) {                      // alpha / bias / addend, staging block, TMA store
@@ -541,9 +633,12 @@ int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, c
     }
     // Tensor-memory plan: even tiles accumulate at column 0, odd tiles at acc_base1, the A ring (3 k-steps x (8 hi + 8 lo)
     // columns) behind them: 272 columns -> [0, 272) / [192, 464) / ring at 464; <= 232 columns -> no overlap at all
-    pl.a_ring = (!transA && g_utccp) ? TMEM_COLS - 48 : 0;
-    pl.acc_base1 = std::min(256, ((pl.a_ring ? pl.a_ring : TMEM_COLS) - (pl.nr0 + pl.nr1)) & ~31);
+    // (tcgemm_tmem_a: two 32-column A-hi stages at [448, 512) instead: 272 columns -> [0, 272) / [160, 432))
+    pl.a_hi_col = g_tmem_a ? TMEM_COLS - 64 : 0;
+    pl.a_ring = (!pl.a_hi_col && !transA && g_utccp) ? TMEM_COLS - 48 : 0;
+    pl.acc_base1 = std::min(256, ((pl.a_hi_col ? pl.a_hi_col : pl.a_ring ? pl.a_ring : TMEM_COLS) - (pl.nr0 + pl.nr1)) & ~31);
     pl.pf_ahead = g_pf_ahead;
+    pl.cluster_release = g_cluster_release;
     pl.a_batched = p.sA != 0; pl.b_batched = p.sB != 0;
     pl.alpha = p.alpha; pl.epilogue = p.epilogue; pl.extra = p.extra; pl.ld_extra = p.ld_extra; pl.s_extra = p.s_extra;
     const int R0 = pl.nr0 / 2, R1 = pl.nr1 / 2;

@@ -43,7 +43,7 @@ print("mode:", "per-subject" if per_subject else "stacked", "NT" if transB else 
 for rank in (0, 1):
     print(f"--- CTA rank {rank}")
     for it in range(30):
-        line = f"kb {it:2d}: tma wait={ev(rank,0,it,0):6d} got={ev(rank,0,it,1):6d} | conv wait={ev(rank,2,it,0):6d} landed={ev(rank,2,it,1):6d} lo_free={ev(rank,2,it,2):6d} arrived={ev(rank,2,it,3):6d}"
+        line = f"kb {it:2d}: tma wait={ev(rank,0,it,0):6d} got={ev(rank,0,it,1):6d} | conv wait={ev(rank,2,it,0):6d} landed={ev(rank,2,it,1):6d} lo_free={ev(rank,2,it,2):6d} stored={ev(rank,2,it,4):6d} fenced={ev(rank,2,it,5):6d} arrived={ev(rank,2,it,3):6d}"
         if rank == 0:
             line += f" | mma wait={ev(0,1,it,0):6d} full={ev(0,1,it,1):6d} committed={ev(0,1,it,2):6d}"
             if ev(0, 1, it, 3) >= 0:
