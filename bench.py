@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--workload", default="gsrnet", choices=["gsrnet", "mlp"],
                     help="mlp: only the notebook-MLP line of BASELINE configs[3] (also reported inside the default line at N = 1)")
     ap.add_argument("--no-mlp", action="store_true")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
+                    help="gsr_set_tuning(KEY, VALUE) before the run (A/B switches of the kernels, e.g. tcgemm_tma=0)")
     return ap.parse_args()
 
 
@@ -431,6 +433,9 @@ def run_ours(args):
     K = pkg.kernels
     if args.gemm_variant is not None:
         pkg.set_tuning("gemm_variant", args.gemm_variant)
+    for kv in args.tune:
+        key, val = kv.split("=")
+        pkg.set_tuning(key, int(val))
 
     numa_note = bind_to_gpu_numa_node(local)
     if args.scaling == "strong":
@@ -831,7 +836,7 @@ def run_ours(args):
                    "parallelism": f"subject-data-parallel x{world}, one NCCL all-reduce of the flat 4.09 MB gradient bucket",
                    "lr_eigh": f"in step ({eigh_method or K.EIGH_METHOD} kernels)", "hr_target_eigh": hr_note,
                    "with_hr_target_eigh_in_step": hr_in_step,
-                   "gemm_backend": K.GEMM_BACKEND,
+                   "gemm_backend": K.GEMM_BACKEND, "tuning": args.tune or "defaults",
                    "l2": "inputs of one step are 400 MB per GPU (> 126 MB L2); no flush needed",
                    "optimizer": ("pkg.FlatAdam (gsr_adam_step), in the timed region" if args.optimizer == "flat"
                                  else "torch.optim.Adam(fused=True, capturable=True), in the timed region"),

@@ -867,21 +867,45 @@ static int launch_tail(const Params& p, int transA, cudaStream_t st) {
 // own) hold `splits_tail` partials of pitch (M - m_head) * N at ws_tail.
 __global__ void reduce_partials_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc,
                                        int splits, int m_head, const float* __restrict__ ws_tail, int splits_tail,
-                                       float alpha, const float* __restrict__ extra, int ld_extra) {
+                                       float alpha, const float* __restrict__ extra, int ld_extra, int m_pitch = 0) {
+    // rows [0, M) are written; the head partials have a pitch of m_pitch * N (m_pitch = M unless fewer rows are reduced here)
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= M * N) return;
     const int m = e / N, n = e - m * N;
+    if (m_pitch == 0) m_pitch = M;
     float acc = 0.f;
     if (m < m_head) {
-        for (int z = 0; z < splits; ++z) acc += __ldg(ws + (size_t)z * M * N + e);
+        for (int z = 0; z < splits; ++z) acc += __ldg(ws + (size_t)z * m_pitch * N + e);
     } else {
-        const size_t pitch = (size_t)(M - m_head) * N;
+        const size_t pitch = (size_t)(m_pitch - m_head) * N;
         const float* src = ws_tail + (size_t)(m - m_head) * N + n;
         for (int z = 0; z < splits_tail; ++z) acc += __ldg(src + z * pitch);
     }
     acc *= alpha;
     if (extra) acc += __ldg(extra + (size_t)m * ld_extra + n);
     C[(size_t)m * ldc + n] = acc;
+}
+
+// C[m_head + r][n] = alpha * sum_b T[b][r][n] (+ extra): the ragged rows of a subject-reduced product, computed per subject
+// by the FP32 ragged-row kernels, summed over the subjects in a fixed order (8 phases of b, then the phases).
+__global__ void __launch_bounds__(256) batch_sum_rows_kernel(const float* __restrict__ T, float* __restrict__ C, int rows, int N, int ldc,
+                                                             int m_head, int batch, float alpha, const float* __restrict__ extra, int ld_extra) {
+    __shared__ float red[8][33];
+    const int e = blockIdx.x * 32 + threadIdx.x, total = rows * N;
+    float acc = 0.f;
+    if (e < total)
+        for (int b = threadIdx.y; b < batch; b += 8) acc += __ldg(T + (size_t)b * total + e);
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && e < total) {
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += red[j][threadIdx.x];
+        const int r = e / N, n = e - r * N;
+        sum *= alpha;
+        if (extra) sum += __ldg(extra + (size_t)(m_head + r) * ld_extra + n);
+        C[(size_t)(m_head + r) * ldc + n] = sum;
+    }
 }
 
 // Split counts of gsr_tcgemm_reduce_f32: `splits` CTAs per tile on the one-CTA path (every SM busy once);
@@ -896,6 +920,12 @@ static ReducePlan reduce_plan(int M, int N, int batch, int splits) {
     r.pair_splits = std::max(1, std::min(batch, kNumSMs / (2 * r.pairs)));
     if (r.m_head < M) r.tail_splits = std::max(1, std::min(batch, kNumSMs));
     r.floats = std::max(r.floats, (size_t)r.pair_splits * M * N + (size_t)r.tail_splits * (M - r.m_head) * N);
+    // the TMA route (csrc/tcgemm_tma.cu): 256-row head tiles, <= 16 ragged rows per subject on the FP32 kernels
+    const int head_tiles = tma_head_tiles(M);
+    if (head_tiles > 0) {
+        const int m_head = tma_head_rows(M), ps = std::max(1, std::min(batch, kNumSMs / (2 * head_tiles)));
+        r.floats = std::max(r.floats, (size_t)ps * M * N + (size_t)std::max(batch, kNumSMs) * (M - m_head) * N);
+    }
     return r;
 }
 
@@ -933,7 +963,7 @@ extern "C" int gsr_tcgemm_f32(const float* A, const float* B, float* C,
         // FP32 ragged-row kernels (<= 16 rows: the 12 rows a 268-row subject matrix leaves) or the one-CTA tensor kernel
         int rc = tc::tma_launch(p, transA, transB, false, batch, (cudaStream_t)stream);
         if (rc) return rc;
-        const int m_done = (M / 256) * 256;
+        const int m_done = tc::tma_head_rows(M);
         if (m_done == M) return 0;
         tc::Params t = p;
         t.M = M - m_done;
@@ -994,6 +1024,47 @@ extern "C" int gsr_tcgemm_reduce_f32(const float* A, const float* B, float* C,
     const tc::ReducePlan plan = tc::reduce_plan(M, N, batch, splits);
     const float* ws_tail = workspace;
     int rc;
+    if (tc::g_pairs && N <= 272 && tc::tma_ok(p, transA, transB)) {
+        // TMA route: persistent CTA pairs accumulate the subjects of a split in tensor memory for the 256-row head tiles
+        // (a last tile of >= 64 rows included: the whole of a 160-row product); <= 16 ragged rows (the 12 rows a 268-row
+        // product leaves) are computed per subject by the FP32 ragged-row kernels and summed over the subjects
+        const int head_tiles = tc::tma_head_tiles(M), m_head = tc::tma_head_rows(M);
+        const int ps = std::max(1, std::min(batch, kNumSMs / (2 * head_tiles)));
+        p.splits = ps;
+        rc = tc::tma_launch(p, transA, transB, true, ps, (cudaStream_t)stream);
+        if (rc) return rc;
+        int tail_splits = 0;
+        float* ws_t = workspace + (size_t)ps * M * N;
+        if (m_head < M) {
+            tc::Params q = p;
+            q.A = transA ? A + m_head : A + (size_t)m_head * lda;
+            q.C = ws_t;
+            q.M = M - m_head;
+            q.ldc = N;
+            q.sC = (long long)q.M * N;
+            q.alpha = 1.0f; q.epilogue = GSR_EPI_NONE; q.extra = nullptr;
+            const bool simt = tc::g_tail && tc::g_reduce_simt_tails && (tc::tail::tail_bt_ok(q, transB) || tc::tail::tail_ok(q, transB));
+            if (simt) {
+                rc = tc::tail::tail_bt_ok(q, transB) ? tc::tail::launch_tail_bt(q, transA, (cudaStream_t)stream)
+                                                     : tc::tail::launch_tail(q, transA, (cudaStream_t)stream);
+                if (rc) return rc;
+                const int total_t = q.M * N;
+                tc::batch_sum_rows_kernel<<<(total_t + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+                    ws_t, C, q.M, N, ldc, m_head, batch, alpha, epilogue == GSR_EPI_ADD ? extra : nullptr, ld_extra);
+                if ((rc = launched("tcgemm_reduce_tail_sum"))) return rc;
+                tail_splits = -1;                                    // rows m_head.. are final
+            } else {
+                q.splits = tail_splits = std::max(1, std::min(batch, kNumSMs));
+                rc = tc::launch<true>(q, transA, transB, dim3((q.M + tc::BM - 1) / tc::BM, 1, q.splits), (cudaStream_t)stream);
+                if (rc) return rc;
+            }
+        }
+        const int rows_out = tail_splits < 0 ? m_head : M;           // reduce_partials_kernel covers rows [0, rows_out)
+        tc::reduce_partials_kernel<<<(rows_out * N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+            workspace, C, rows_out, N, ldc, ps, m_head, ws_t, tail_splits < 0 ? 0 : tail_splits, alpha,
+            epilogue == GSR_EPI_ADD ? extra : nullptr, ld_extra, M);
+        return launched("tcgemm_reduce_partials");
+    }
     if (plan.pairs && tc::pair_ok(p)) {
         // CTA pairs take the even number of leading M tiles; the ragged last tile is launched on its own with its
         // own split count and compact partials behind those of the pairs.

@@ -171,6 +171,11 @@ __device__ __forceinline__ uint32_t instr_desc2(int n, int a_mn_major, int b_mn_
 // csrc/tcgemm_tma.cu: the TMA-fed persistent CTA-pair kernel.  tma_ok: shapes / alignments it takes (the caller has
 // already applied pair_ok); tma_launch covers the first 256 * floor(M / 256) rows of every batch item.
 extern int g_tma, g_utccp, g_mn_partial, g_pf_ahead, g_tmem_a, g_cluster_release;       // gsr_set_tuning("tcgemm_tma" | "tcgemm_utccp" | "tcgemm_mn_partial", 0|1)
+// 256-row tiles the TMA kernel takes: every full one and a last partial one with at least 64 rows (rows past M are
+// zero filled by the loads and clipped by the stores); fewer rows than that go to the FP32 ragged-row kernels.
+extern int g_partial_head, g_reduce_simt_tails;     // gsr_set_tuning("tcgemm_partial_head" | "tcgemm_reduce_simt_tails", 0|1)
+inline int tma_head_tiles(int M) { return M / 256 + ((g_partial_head && M % 256 >= 64) ? 1 : 0); }
+inline int tma_head_rows(int M) { const int r = tma_head_tiles(M) * 256; return r < M ? r : M; }
 bool tma_ok(const Params& p, int transA, int transB);
 int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, cudaStream_t st);
 

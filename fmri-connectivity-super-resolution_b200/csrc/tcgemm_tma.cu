@@ -37,6 +37,8 @@ int g_tmem_a = 0;           // gsr_set_tuning("tcgemm_tmem_a", 0|1): the hi term
                             // measured no faster (stacked NT 0.265 against 0.259 ms): the MMAs of a k-block take 1.15-1.25 us with either
                             // operand source (the tensor pipe, not its shared-memory reads, is what they wait for), and the two 32-column
                             // A stages leave room for a 4-chunk instead of a 2-chunk accumulator overlap.  Off by default.
+int g_partial_head = 1;     // a last 256-row tile with >= 64 valid rows runs on the TMA kernel (the 160-row subject-reduced product)
+int g_reduce_simt_tails = 1;    // <= 16 ragged rows of a subject-reduced product: FP32 ragged-row kernels per subject + a sum over subjects
 int g_cluster_release = 0;  // gsr_set_tuning("tcgemm_cluster_release", 0|1): see mbar_arrive_remote (csrc/tcgemm.cuh)
 int g_pf_ahead = 0;         // gsr_set_tuning("tcgemm_prefetch", k): k-blocks of L2 prefetch (cp.async.bulk.prefetch.tensor) in front of the
                             // TMA loads; default off -- measured monotonically slower (stacked NN 0.272 / 0.290 / 0.291 / 0.287 / 0.310 ms
@@ -473,7 +475,7 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int j = 0; j < 8; ++j) {                                // row = lane; 16-byte chunk j at (j ^ (lane & 7)): conflict free
                     float4 f = make_float4(__uint_as_float(v[4 * j]) * alpha, __uint_as_float(v[4 * j + 1]) * alpha,
                                            __uint_as_float(v[4 * j + 2]) * alpha, __uint_as_float(v[4 * j + 3]) * alpha);
-                    if (epi != GSR_EPI_NONE && n0 + 4 * j < p.N) {           // N % 4 == 0 (launcher)
+                    if (epi != GSR_EPI_NONE && n0 + 4 * j < p.N && (epi == GSR_EPI_BIAS || row0 + lane < p.M)) {   // N % 4 == 0 (launcher)
                         const float4 e4 = __ldg(reinterpret_cast<const float4*>((epi == GSR_EPI_BIAS ? p.extra : extra_row) + n0 + 4 * j));
                         f.x += e4.x; f.y += e4.y; f.z += e4.z; f.w += e4.w;
                     }
@@ -595,7 +597,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) tf32_probe_k
 bool tma_ok(const Params& p, int transA, int transB) {
     (void)transA;
     if (!g_tma || !t3::encode_fn()) return false;
-    if (p.M < 256 || p.K < 1 || p.N % 4 != 0) return false;
+    if (tma_head_tiles(p.M) < 1 || p.K < 1 || p.N % 4 != 0) return false;
+    // a persistent CTA-pair kernel is the wrong tool for a handful of tiles (the Graph U-Net's weight gradients: ONE
+    // 268 x k x 268 product, 15 us on three one-CTA tiles against 40 us + a ragged-row launch here)
+    if ((long long)p.batch * tma_head_tiles(p.M) * ((p.N + 255) / 256) < 4) return false;
     if (p.lda % 4 || p.ldb % 4 || p.ldc % 4 || p.sA % 4 || p.sB % 4 || p.sC % 4) return false;
     if (!aligned16(p.A) || !aligned16(p.B) || !aligned16(p.C)) return false;
     if (p.epilogue != GSR_EPI_NONE && !aligned16(p.extra)) return false;
@@ -606,7 +611,7 @@ bool tma_ok(const Params& p, int transA, int transB) {
 int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, cudaStream_t st) {
     using namespace t3;
     Plan pl{};
-    pl.tiles_m = p.M / 256;
+    pl.tiles_m = tma_head_tiles(p.M);
     pl.n_tile = p.N <= 272 ? 272 : 256;
     pl.tiles_n = p.N <= 272 ? 1 : (p.N + 255) / 256;
     pl.items = zdim;
