@@ -31,6 +31,7 @@ PROTOTYPES = {
     "gsr_normalize_adj_bwd": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, c_ptr]),
     "gsr_normalize_adj_bwd_workspace": (C.c_size_t, [i32, i32]),
     "gsr_normalize_adj_bwd_tiles": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, c_ptr]),
+    "gsr_normalize_adj_bwd_tiles2": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, c_ptr]),
     "gsr_eigh_workspace": (C.c_size_t, [i32, i32]),
     "gsr_eigh_jacobi_f32": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, f32, i32, c_ptr]),
     "gsr_eigh_tridiag_workspace": (C.c_size_t, [i32, i32]),
@@ -43,6 +44,8 @@ PROTOTYPES = {
     "gsr_tcgemm_supported": (i32, [i32, i32, i32, i32, i32]),
     "gsr_tcgemm_f32": (i32, [c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, i32, i32, i64, i64, i64,
                              i32, i32, i32, f32, i32, c_ptr, i32, i64, c_ptr]),
+    "gsr_tcgemm_dual_f32": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, i32, i32, i32, i32, i32,
+                                  i64, i64, i64, i64, i64, i32, i32, i32, f32, c_ptr]),
     "gsr_tcgemm_reduce_workspace": (C.c_size_t, [i32, i32, i32, C.POINTER(i32)]),
     "gsr_tcgemm_reduce_f32": (i32, [c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, i32, i32, i64, i64,
                                     i32, i32, i32, f32, i32, c_ptr, i32, c_ptr, i32, c_ptr]),

@@ -37,7 +37,7 @@ extern int g_eigh_oddeven;
 extern int g_eigh_max_polish;
 extern int g_eigh_ql_max_iter;
 extern int g_eigh_redo;
-namespace tc { extern int g_pairs, g_tail, g_tma, g_utccp, g_mn_partial, g_pf_ahead, g_tmem_a, g_cluster_release, g_partial_head, g_reduce_simt_tails; }
+namespace tc { extern int g_pairs, g_tail, g_dual, g_tma, g_utccp, g_mn_partial, g_pf_ahead, g_tmem_a, g_cluster_release, g_partial_head, g_reduce_simt_tails; }
 
 struct GemmParams {
     const float* A; const float* B; float* C;
@@ -314,6 +314,7 @@ extern "C" int gsr_set_tuning(const char* key, int value) {
     if (!strcmp(key, "tcgemm_partial_head")) { gsr::tc::g_partial_head = value; return 0; }
     if (!strcmp(key, "tcgemm_reduce_simt_tails")) { gsr::tc::g_reduce_simt_tails = value; return 0; }
     if (!strcmp(key, "tcgemm_prefetch")) { gsr::tc::g_pf_ahead = value < 0 ? 0 : value; return 0; }
+    if (!strcmp(key, "tcgemm_dual")) { gsr::tc::g_dual = value; return 0; }
     if (!strcmp(key, "tcgemm_mn_partial")) { gsr::tc::g_mn_partial = value; return 0; }
     return fail(GSR_E_ARG, "set_tuning: unknown key");
 }

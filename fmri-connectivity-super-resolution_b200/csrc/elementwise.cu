@@ -230,6 +230,15 @@ __device__ __forceinline__ float4 ld4_masked(const float* __restrict__ base, int
     if (row < n && col < n) v = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * n + col));   // n % 4 == 0: all or nothing
     return v;
 }
+// the incoming gradient as the sum of two tensors (the second may be null): the sum is formed as it is read
+__device__ __forceinline__ float4 ld4_masked2(const float* __restrict__ a, const float* __restrict__ b, int n, int row, int col) {
+    float4 v = ld4_masked(a, n, row, col);
+    if (b) {
+        const float4 w = ld4_masked(b, n, row, col);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    return v;
+}
 __device__ __forceinline__ void st_tile(float* t, int r, int c, float4 v) {
     t[r * kTP + c] = v.x; t[r * kTP + c + 1] = v.y; t[r * kTP + c + 2] = v.z; t[r * kTP + c + 3] = v.w;
 }
@@ -393,7 +402,7 @@ normalize_scale_tiles_kernel(const float* __restrict__ mx, const float* __restri
 template <int PRE>
 __global__ void __launch_bounds__(kTileThreads)
 normalize_bwd_partial_tiles_kernel(const float* __restrict__ mx, const float* __restrict__ r, const float* __restrict__ Tg,
-                                   float* __restrict__ part, int n, int T) {
+                                   const float* __restrict__ Tg2, float* __restrict__ part, int n, int T) {
     extern __shared__ float smem[];
     float* mb = smem;                          // M(J,I):  mb[jj][ii]
     float* tb = smem + kTS * kTP;              // T(J,I):  tb[jj][ii]
@@ -402,6 +411,7 @@ normalize_bwd_partial_tiles_kernel(const float* __restrict__ mx, const float* __
     float* rJ = rI + kTS;
     const size_t base = (size_t)blockIdx.y * n * n;
     mx += base; Tg += base;
+    if (Tg2) Tg2 += base;
     r += (size_t)blockIdx.y * n;
     part += (size_t)blockIdx.y * T * n;
     int I, J;
@@ -413,8 +423,8 @@ normalize_bwd_partial_tiles_kernel(const float* __restrict__ mx, const float* __
     for (int p = 0; p < 4; ++p) {
         ma[p] = ld4_pre<PRE>(mx, n, I0 + ty + 16 * p, J0 + 4 * tx);
         vmb[p] = ld4_pre<PRE>(mx, n, J0 + ty + 16 * p, I0 + 4 * tx);
-        tA[p] = ld4_masked(Tg, n, I0 + ty + 16 * p, J0 + 4 * tx);
-        vtb[p] = ld4_masked(Tg, n, J0 + ty + 16 * p, I0 + 4 * tx);
+        tA[p] = ld4_masked2(Tg, Tg2, n, I0 + ty + 16 * p, J0 + 4 * tx);
+        vtb[p] = ld4_masked2(Tg, Tg2, n, J0 + ty + 16 * p, I0 + 4 * tx);
     }
     if (threadIdx.x < kTS) rI[threadIdx.x] = (I0 + threadIdx.x < n) ? r[I0 + threadIdx.x] : 0.f;
     else if (threadIdx.x < 2 * kTS) rJ[threadIdx.x - kTS] = (J0 + threadIdx.x - kTS < n) ? r[J0 + threadIdx.x - kTS] : 0.f;
@@ -472,7 +482,7 @@ __global__ void normalize_bwd_drho_kernel(const float* __restrict__ part, const 
 template <int PRE>
 __global__ void __launch_bounds__(kTileThreads)
 normalize_bwd_apply_tiles_kernel(const float* __restrict__ mx, const float* __restrict__ r, const float* __restrict__ drho,
-                                 const float* __restrict__ Tg, float* __restrict__ dmx, int n, int T) {
+                                 const float* __restrict__ Tg, const float* __restrict__ Tg2, float* __restrict__ dmx, int n, int T) {
     extern __shared__ float smem[];
     float* ta = smem;                          // T(I,J): ta[ii][jj]
     float* tb = smem + kTS * kTP;              // T(J,I): tb[jj][ii]
@@ -482,6 +492,7 @@ normalize_bwd_apply_tiles_kernel(const float* __restrict__ mx, const float* __re
     float* dJ = dI + kTS;
     const size_t base = (size_t)blockIdx.y * n * n;
     mx += base; Tg += base; dmx += base;
+    if (Tg2) Tg2 += base;
     r += (size_t)blockIdx.y * n;
     drho += (size_t)blockIdx.y * n;
     int I, J;
@@ -491,8 +502,8 @@ normalize_bwd_apply_tiles_kernel(const float* __restrict__ mx, const float* __re
     float4 vta[4], vtb[4], xa[4], xb[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-        vta[p] = ld4_masked(Tg, n, I0 + ty + 16 * p, J0 + 4 * tx);
-        vtb[p] = ld4_masked(Tg, n, J0 + ty + 16 * p, I0 + 4 * tx);
+        vta[p] = ld4_masked2(Tg, Tg2, n, I0 + ty + 16 * p, J0 + 4 * tx);
+        vtb[p] = ld4_masked2(Tg, Tg2, n, J0 + ty + 16 * p, I0 + 4 * tx);
         if (PRE) { xa[p] = ld4_masked(mx, n, I0 + ty + 16 * p, J0 + 4 * tx); xb[p] = ld4_masked(mx, n, J0 + ty + 16 * p, I0 + 4 * tx); }
     }
     if (threadIdx.x < kTS) {
@@ -653,12 +664,18 @@ extern "C" size_t gsr_normalize_adj_bwd_workspace(int batch, int n) {
     return (size_t)batch * (T + 1) * n;                     // floats: [batch][T][n] partial sums + [batch][n] drho
 }
 
-extern "C" int gsr_normalize_adj_bwd_tiles(const float* mx, const float* r, const float* grad_out, float* grad_mx,
-                                           float* workspace, int batch, int n, int pre, void* stream) {
+// grad_out2 (may be NULL): a second contribution to the incoming gradient, added to grad_out element by element as the two
+// passes read it -- d adj = 2 dX0 adj (+) the graph convolutions' contribution (models/layers.py:57-59, models/gsr_model.py:30-32)
+// without a GEMM addend or a separate addition pass.  No strip-kernel fallback: GSR_E_UNSUPPORTED when the tile path does not apply.
+extern "C" int gsr_normalize_adj_bwd_tiles2(const float* mx, const float* r, const float* grad_out, const float* grad_out2, float* grad_mx,
+                                            float* workspace, int batch, int n, int pre, void* stream) {
     if (!mx || !r || !grad_out || !grad_mx || batch < 0 || n <= 0) return fail(GSR_E_ARG, "normalize_adj_bwd_tiles: bad argument");
     if (batch == 0) return 0;
-    if (!workspace || n % 4 != 0 || !aligned16(mx) || !aligned16(grad_out) || !aligned16(grad_mx) || batch > 65535)
+    if (!workspace || n % 4 != 0 || !aligned16(mx) || !aligned16(grad_out) || !aligned16(grad_mx) || batch > 65535 ||
+        (grad_out2 && !aligned16(grad_out2))) {
+        if (grad_out2) return fail(GSR_E_UNSUPPORTED, "normalize_adj_bwd_tiles2: two gradients need the tile path (workspace, n % 4 == 0, 16-byte aligned operands)");
         return gsr_normalize_adj_bwd(mx, r, grad_out, grad_mx, batch, n, pre, stream);      // strip kernel: any n, no workspace
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const int T = (n + kTS - 1) / kTS;
     float* part = workspace;
@@ -667,13 +684,18 @@ extern "C" int gsr_normalize_adj_bwd_tiles(const float* mx, const float* r, cons
     int rc = pre ? set_smem(normalize_bwd_partial_tiles_kernel<1>, smem1) : set_smem(normalize_bwd_partial_tiles_kernel<0>, smem1);
     if (rc) return fail(rc, "normalize_adj_bwd_tiles: cudaFuncSetAttribute failed");
     const dim3 grid(T * (T + 1) / 2, batch);
-    if (pre) normalize_bwd_partial_tiles_kernel<1><<<grid, kTileThreads, smem1, st>>>(mx, r, grad_out, part, n, T);
-    else     normalize_bwd_partial_tiles_kernel<0><<<grid, kTileThreads, smem1, st>>>(mx, r, grad_out, part, n, T);
+    if (pre) normalize_bwd_partial_tiles_kernel<1><<<grid, kTileThreads, smem1, st>>>(mx, r, grad_out, grad_out2, part, n, T);
+    else     normalize_bwd_partial_tiles_kernel<0><<<grid, kTileThreads, smem1, st>>>(mx, r, grad_out, grad_out2, part, n, T);
     if ((rc = launched("normalize_bwd_partial"))) return rc;
     const long long total = (long long)batch * n;
     normalize_bwd_drho_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(part, r, drho, n, T, total);
     if ((rc = launched("normalize_bwd_drho"))) return rc;
-    if (pre) normalize_bwd_apply_tiles_kernel<1><<<grid, kTileThreads, smem2, st>>>(mx, r, drho, grad_out, grad_mx, n, T);
-    else     normalize_bwd_apply_tiles_kernel<0><<<grid, kTileThreads, smem2, st>>>(mx, r, drho, grad_out, grad_mx, n, T);
+    if (pre) normalize_bwd_apply_tiles_kernel<1><<<grid, kTileThreads, smem2, st>>>(mx, r, drho, grad_out, grad_out2, grad_mx, n, T);
+    else     normalize_bwd_apply_tiles_kernel<0><<<grid, kTileThreads, smem2, st>>>(mx, r, drho, grad_out, grad_out2, grad_mx, n, T);
     return launched("normalize_adj_bwd");
+}
+
+extern "C" int gsr_normalize_adj_bwd_tiles(const float* mx, const float* r, const float* grad_out, float* grad_mx,
+                                           float* workspace, int batch, int n, int pre, void* stream) {
+    return gsr_normalize_adj_bwd_tiles2(mx, r, grad_out, nullptr, grad_mx, workspace, batch, n, pre, stream);
 }

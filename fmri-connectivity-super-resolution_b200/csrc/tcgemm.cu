@@ -28,6 +28,7 @@ namespace gsr {
 namespace tc {
 
 int g_pairs = 1;        // gsr_set_tuning("tcgemm_pairs"): CTA-pair kernel (cta_group::2) for gsr_tcgemm_f32 (default), 0 = one CTA per tile
+int g_dual = 1;         // gsr_set_tuning("tcgemm_dual"): gsr_tcgemm_dual_f32 accumulates both products in tensor memory (default), 0 = two launches, the second with the addend epilogue
 int g_tail = 1;         // gsr_set_tuning("tcgemm_ragged_rows"): FP32 kernels for the <= 16 ragged rows after the CTA pairs (default), 0 = one-CTA tensor kernel
 
 #ifdef GSR_TC_TRACE
@@ -335,7 +336,7 @@ tcgemm_kernel(const Params p) {
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.extra + n0 + c));
                     v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
                 } else if (epi == GSR_EPI_ADD) {
-                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(extra + (size_t)(m0 + r) * p.ld_extra + n0 + c));
+                    const float4 a4 = *reinterpret_cast<const float4*>(extra + (size_t)(m0 + r) * p.ld_extra + n0 + c);     // plain load: the addend may alias C
                     v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
                 }
                 *reinterpret_cast<float4*>(C + (size_t)(m0 + r) * ldc + n0 + c) = v;
@@ -347,7 +348,7 @@ tcgemm_kernel(const Params p) {
             for (int c = lane; c < cols; c += 32) {
                 float v = src[c] * alpha;
                 if (epi == GSR_EPI_BIAS) v += __ldg(p.extra + n0 + c);
-                else if (epi == GSR_EPI_ADD) v += __ldg(extra + (size_t)(m0 + r) * p.ld_extra + n0 + c);
+                else if (epi == GSR_EPI_ADD) v += extra[(size_t)(m0 + r) * p.ld_extra + n0 + c];
                 dst[c] = v;
             }
         }
@@ -554,7 +555,7 @@ tcgemm2_kernel(const Params p) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.extra + c));
                 v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
             } else if (epi == GSR_EPI_ADD) {
-                const float4 a4 = __ldg(reinterpret_cast<const float4*>(extra + (size_t)(m0 + r) * p.ld_extra + c));
+                const float4 a4 = *reinterpret_cast<const float4*>(extra + (size_t)(m0 + r) * p.ld_extra + c);
                 v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
             }
             *reinterpret_cast<float4*>(C + (size_t)(m0 + r) * ldc + c) = v;
@@ -641,9 +642,12 @@ __global__ void __launch_bounds__(T_THREADS, 4) tail_kernel(const Params p) {
     float* Bs = tsm + T_KMAX * T_ROWS;                 // [2][T_KC][T_COLS]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rows = p.M, K = p.K, N = p.N;
+    // subjects in REVERSE order: the tensor kernel that has just run on the same operands walked them upwards, so the
+    // last ones are the part of B still resident in the 126 MB L2
+    const int bz = (int)gridDim.z - 1 - (int)blockIdx.z;
     const int nchunks = (K + T_KC - 1) / T_KC, kpad = nchunks * T_KC;
-    const float* A = p.A + (size_t)blockIdx.z * p.sA;
-    const float* B = p.B + (size_t)blockIdx.z * p.sB;
+    const float* A = p.A + (size_t)bz * p.sA;
+    const float* B = p.B + (size_t)bz * p.sB;
 
     auto copy_b = [&](int c) {                         // a warp per k row; rows past K and columns past N are zero filled
         float* dst = Bs + (c & 1) * T_KC * T_COLS;
@@ -722,9 +726,9 @@ __global__ void __launch_bounds__(T_THREADS, 4) tail_kernel(const Params p) {
         __syncthreads();
     }
     if (tid >= T_HALF) return;
-    float* C = p.C + (size_t)blockIdx.z * p.sC;
+    float* C = p.C + (size_t)bz * p.sC;
     const int epi = p.epilogue;
-    const float* extra = epi == GSR_EPI_ADD ? p.extra + (size_t)blockIdx.z * p.s_extra : p.extra;
+    const float* extra = epi == GSR_EPI_ADD ? p.extra + (size_t)bz * p.s_extra : p.extra;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int n = tid + h * T_HALF;
@@ -734,7 +738,7 @@ __global__ void __launch_bounds__(T_THREADS, 4) tail_kernel(const Params p) {
         for (int r = 0; r < R4 * 4; ++r) {
             if (r < rows) {
                 float v = acc[r][h] * p.alpha + bias;
-                if (epi == GSR_EPI_ADD) v += __ldg(extra + (size_t)r * p.ld_extra + n);
+                if (epi == GSR_EPI_ADD) v += extra[(size_t)r * p.ld_extra + n];     // plain load: the addend may alias C
                 C[(size_t)r * p.ldc + n] = v;
             }
         }
@@ -751,9 +755,10 @@ __global__ void __launch_bounds__(D_THREADS, 4) tail_bt_kernel(const Params p) {
     __shared__ __align__(16) float As[T_KMAX * T_ROWS];
     const int tid = threadIdx.x;
     const int rows = p.M, K = p.K, N = p.N;
+    const int bz = (int)gridDim.z - 1 - (int)blockIdx.z;       // reverse subject order: see tail_kernel
     const int kpad = (K + 31) & ~31;
-    const float* A = p.A + (size_t)blockIdx.z * p.sA;
-    const float* B = p.B + (size_t)blockIdx.z * p.sB;
+    const float* A = p.A + (size_t)bz * p.sA;
+    const float* B = p.B + (size_t)bz * p.sB;
     if (!TA) {
         float v[R4 * 4];
 #pragma unroll
@@ -801,15 +806,15 @@ __global__ void __launch_bounds__(D_THREADS, 4) tail_bt_kernel(const Params p) {
             fma_k(4 * i + 2, As + k0 * T_ROWS, bv[i].z); fma_k(4 * i + 3, As + k0 * T_ROWS, bv[i].w);
         }
     }
-    float* C = p.C + (size_t)blockIdx.z * p.sC;
+    float* C = p.C + (size_t)bz * p.sC;
     const int epi = p.epilogue;
-    const float* extra = epi == GSR_EPI_ADD ? p.extra + (size_t)blockIdx.z * p.s_extra : p.extra;
+    const float* extra = epi == GSR_EPI_ADD ? p.extra + (size_t)bz * p.s_extra : p.extra;
     const float bias = epi == GSR_EPI_BIAS ? __ldg(extra + n) : 0.f;
 #pragma unroll
     for (int r = 0; r < R4 * 4; ++r) {
         if (r < rows) {
             float v = acc[r] * p.alpha + bias;
-            if (epi == GSR_EPI_ADD) v += __ldg(extra + (size_t)r * p.ld_extra + n);
+            if (epi == GSR_EPI_ADD) v += extra[(size_t)r * p.ld_extra + n];     // plain load: the addend may alias C
             C[(size_t)r * p.ldc + n] = v;
         }
     }
@@ -995,6 +1000,47 @@ extern "C" int gsr_tcgemm_f32(const float* A, const float* B, float* C,
     dim3 grid((M + tc::BM - 1) / tc::BM, (N + tc::BN - 1) / tc::BN, batch);
     if (grid.y > 65535) return fail(GSR_E_UNSUPPORTED, "tcgemm: N too large");
     return tc::launch<false>(p, transA, transB, grid, (cudaStream_t)stream);
+}
+
+// C = alpha (op(A1) op(B1) + op(A2) op(B2)): two products of the same shape and operand majors into one result -- the two
+// contributions to the gradient of the adjacency (models/layers.py:85-86 applied twice, models/gsr_model.py:30-32).  On the
+// TMA kernel both accumulate in tensor memory (one k-loop over the k-blocks of the first pair, then the second): no addend is
+// read back, one result is written.  The <= 16 ragged rows run on the FP32 kernels as two launches, the second adding in place.
+extern "C" int gsr_tcgemm_dual_f32(const float* A1, const float* B1, const float* A2, const float* B2, float* C,
+                                   int M, int N, int K1, int K2, int lda1, int ldb1, int lda2, int ldb2, int ldc,
+                                   long long strideA1, long long strideB1, long long strideA2, long long strideB2, long long strideC,
+                                   int transA, int transB, int batch, float alpha, void* stream) {
+    if (!A1 || !B1 || !A2 || !B2 || !C || M < 0 || N < 0 || K1 < 1 || K2 < 1 || batch < 0) return fail(GSR_E_ARG, "tcgemm_dual: bad argument");
+    if (M == 0 || N == 0 || batch == 0) return 0;
+    if (batch > 65535) return fail(GSR_E_UNSUPPORTED, "tcgemm_dual: batch > 65535");
+    tc::Params p{A1, B1, C, M, N, K1, lda1, ldb1, ldc, strideA1, strideB1, strideC, batch, 1, alpha, GSR_EPI_NONE, nullptr, 0, 0};
+    tc::Params q{A2, B2, C, M, N, K2, lda2, ldb2, ldc, strideA2, strideB2, strideC, batch, 1, alpha, GSR_EPI_NONE, nullptr, 0, 0};
+    if (!tc::operands_ok(p) || !tc::operands_ok(q)) return fail(GSR_E_ALIGN, "tcgemm_dual: operands must be 16-byte aligned with leading dimensions % 4 == 0");
+    const bool same_batching = (strideA1 != 0) == (strideA2 != 0) && (strideB1 != 0) == (strideB2 != 0);
+    if (tc::g_pairs && tc::g_dual && same_batching && tc::tma_ok(p, transA, transB) && tc::tma_ok(q, transA, transB)) {
+        int rc = tc::tma_launch(p, transA, transB, false, batch, (cudaStream_t)stream, &q);
+        if (rc) return rc;
+        const int m_done = tc::tma_head_rows(M);
+        if (m_done == M) return 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            tc::Params t = pass ? q : p;
+            t.M = M - m_done;
+            t.A = t.A + (transA ? (size_t)m_done : (size_t)m_done * t.lda);
+            t.C = C + (size_t)m_done * ldc;
+            if (pass) { t.epilogue = GSR_EPI_ADD; t.extra = t.C; t.ld_extra = ldc; t.s_extra = strideC; }
+            if (tc::g_tail && tc::tail::tail_bt_ok(t, transB)) rc = tc::tail::launch_tail_bt(t, transA, (cudaStream_t)stream);
+            else if (tc::g_tail && tc::tail::tail_ok(t, transB)) rc = tc::tail::launch_tail(t, transA, (cudaStream_t)stream);
+            else rc = tc::launch<false>(t, transA, transB, dim3((t.M + tc::BM - 1) / tc::BM, (N + tc::BN - 1) / tc::BN, batch), (cudaStream_t)stream);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    // anything else: two launches, the second with the first one's result as its addend
+    int rc = gsr_tcgemm_f32(A1, B1, C, M, N, K1, lda1, ldb1, ldc, strideA1, strideB1, strideC, transA, transB, batch, alpha,
+                            GSR_EPI_NONE, nullptr, 0, 0, stream);
+    if (rc) return rc;
+    return gsr_tcgemm_f32(A2, B2, C, M, N, K2, lda2, ldb2, ldc, strideA2, strideB2, strideC, transA, transB, batch, alpha,
+                          GSR_EPI_ADD, C, ldc, strideC, stream);
 }
 
 extern "C" size_t gsr_tcgemm_reduce_workspace(int M, int N, int batch, int* splits_out) {

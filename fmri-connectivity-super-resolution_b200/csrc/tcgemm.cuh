@@ -19,7 +19,7 @@ struct Params {
     const float* extra; int ld_extra; long long s_extra;
 };
 
-extern int g_pairs, g_tail;
+extern int g_pairs, g_tail, g_dual;
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -177,7 +177,9 @@ extern int g_partial_head, g_reduce_simt_tails;     // gsr_set_tuning("tcgemm_pa
 inline int tma_head_tiles(int M) { return M / 256 + ((g_partial_head && M % 256 >= 64) ? 1 : 0); }
 inline int tma_head_rows(int M) { const int r = tma_head_tiles(M) * 256; return r < M ? r : M; }
 bool tma_ok(const Params& p, int transA, int transB);
-int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, cudaStream_t st);
+// `second` (A, B, K, lda, ldb, sA, sB of a second pair of operands with the same shapes and majors): C = alpha (op(A) op(B) + op(A2) op(B2)) + ...,
+// both products accumulated in tensor memory (the k-loop runs over the first pair's k-blocks, then the second's).
+int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, cudaStream_t st, const Params* second = nullptr);
 
 }  // namespace tc
 }  // namespace gsr

@@ -76,6 +76,8 @@ struct Plan {
     int nsub;               // REDUCE: subjects accumulated in all (else 1 per item)
     int splits;             // REDUCE: stride between the subjects of an item
     int M, N, K, nkb;
+    int K2, nkb1;           // dual product C = op(A) op(B) + op(A2) op(B2): k-blocks [0, nkb1) come from the first pair of operands
+                            // (K columns), [nkb1, nkb) from the second (K2 columns); nkb1 = nkb when there is one pair
     int nr0, nr1;           // UMMA N of the two accumulator column ranges (nr1 may be 0)
     int acc_base1;          // tensor-memory column of the odd tiles' accumulator (even tiles: 0); the two overlap when 2 (nr0 + nr1) > 512
     int a_ring;             // tensor-memory column of the A-operand ring (tcgen05.cp, K-major A only); 0 = A is read from shared memory
@@ -152,7 +154,9 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 template <bool TA, bool TB, bool REDUCE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB0,
-               const __grid_constant__ CUtensorMap mapB1, const __grid_constant__ CUtensorMap mapC, const Plan p) {
+               const __grid_constant__ CUtensorMap mapB1, const __grid_constant__ CUtensorMap mapC,
+               const __grid_constant__ CUtensorMap mapE, const __grid_constant__ CUtensorMap mapA2,
+               const __grid_constant__ CUtensorMap mapB02, const __grid_constant__ CUtensorMap mapB12, const Plan p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* raw = smem;                                              // [RAW_STAGES][A | B]  fp32 as landed = hi
@@ -183,7 +187,7 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc2(smem_u32(tmem_slot), TMEM_COLS);
-    if (warp == 0 && lane == 0) { prefetch_map(&mapA); prefetch_map(&mapB0); prefetch_map(&mapB1); prefetch_map(&mapC); }
+    if (warp == 0 && lane == 0) { prefetch_map(&mapA); prefetch_map(&mapB0); prefetch_map(&mapB1); prefetch_map(&mapC); prefetch_map(&mapE); prefetch_map(&mapA2); prefetch_map(&mapB02); prefetch_map(&mapB12); }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
@@ -207,23 +211,27 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int m0 = mp * 256 + (int)rank * BM, n0 = (mn - mp * p.tiles_n) * p.n_tile;
                 const int b = REDUCE ? z + blk.sub * p.splits : z;
                 const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
-                const int k0 = blk.kb * BK;
+                const bool second = blk.kb >= p.nkb1;                                               // dual product: the second pair of operands
+                const int k0 = (second ? blk.kb - p.nkb1 : blk.kb) * BK;
+                const CUtensorMap* mA = second ? &mapA2 : &mapA;
+                const CUtensorMap* mB0 = second ? &mapB02 : &mapB0;
+                const CUtensorMap* mB1 = second ? &mapB12 : &mapB1;
                 const uint32_t b_dst = a_dst + A_TILE;
                 auto ld = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2) {
                     if (prefetch) tma_prefetch(map, c0, c1, c2); else tma_load(dst, map, full, c0, c1, c2);
                 };
-                if (!TA) ld(a_dst, &mapA, k0, m0, ba);                                              // box {32 k, 128 m}
+                if (!TA) ld(a_dst, mA, k0, m0, ba);                                                 // box {32 k, 128 m}
                 else {
 #pragma unroll
-                    for (int j = 0; j < BM / 32; ++j) ld(a_dst + j * 4096, &mapA, m0 + 32 * j, k0, ba);        // box {32 m, 32 k}
+                    for (int j = 0; j < BM / 32; ++j) ld(a_dst + j * 4096, mA, m0 + 32 * j, k0, ba);           // box {32 m, 32 k}
                 }
                 if (TB) {                                                                           // boxes {32 k, R0 n}, {32 k, R1 n}
-                    ld(b_dst, &mapB0, k0, n0 + R0 * (int)rank, bb);
-                    if (R1 > 0) ld(b_dst + p.b_off1, &mapB1, k0, n0 + p.nr0 + R1 * (int)rank, bb);
+                    ld(b_dst, mB0, k0, n0 + R0 * (int)rank, bb);
+                    if (R1 > 0) ld(b_dst + p.b_off1, mB1, k0, n0 + p.nr0 + R1 * (int)rank, bb);
                 } else {                                                                            // box {32 n, 32 k} per 32 columns
                     // (a range whose share is not a multiple of 32 columns uses the head of its last block only)
-                    for (int j = 0; j < (R0 + 31) / 32; ++j) ld(b_dst + j * 4096, &mapB0, n0 + R0 * (int)rank + 32 * j, k0, bb);
-                    for (int j = 0; j < (R1 + 31) / 32; ++j) ld(b_dst + p.b_off1 + j * 4096, &mapB0, n0 + p.nr0 + R1 * (int)rank + 32 * j, k0, bb);
+                    for (int j = 0; j < (R0 + 31) / 32; ++j) ld(b_dst + j * 4096, mB0, n0 + R0 * (int)rank + 32 * j, k0, bb);
+                    for (int j = 0; j < (R1 + 31) / 32; ++j) ld(b_dst + p.b_off1 + j * 4096, mB0, n0 + p.nr0 + R1 * (int)rank + 32 * j, k0, bb);
                 }
             };
             Blk cur{cluster_id, 0, 0}, pf{cluster_id, 0, 0};
@@ -277,7 +285,7 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         const uint32_t hb = smem_u32(raw + rs * SLOT_BYTES), lb = smem_u32(lo + ls * SLOT_BYTES);
                         uint32_t ah = desc_lo(hb, a_lbo), al = desc_lo(lb, a_lbo);
                         uint32_t bh = desc_lo(hb + A_TILE, b_lbo), bl = desc_lo(lb + A_TILE, b_lbo);
-                        const int ksteps = min(BK / 8, (p.K - kb * BK + 7) >> 3);
+                        const int ksteps = kb < p.nkb1 ? min(BK / 8, (p.K - kb * BK + 7) >> 3) : min(BK / 8, (p.K2 - (kb - p.nkb1) * BK + 7) >> 3);
                         if (p.a_hi_col) {
                             // A-hi in tensor memory (converter warps, tcgen05.st): lo.hi reads A-lo from shared memory,
                             // hi.lo and hi.hi read A-hi at 8 columns per k-step of stage `ls`
@@ -453,10 +461,23 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int chunks = min(chunks_full, (p.N - ncol0 + 31) >> 5);    // the last column tile may be ragged
             const int even_first = min(chunks, even_first_full), even_cnt = chunks - even_first, odd_cnt = min(chunks, odd_cnt_full);
             const int row0 = mp * 256 + (int)rank * BM + q * 32;             // first output row of this warp
-            const float* extra_row = nullptr;
-            if (!REDUCE && p.epilogue == GSR_EPI_ADD) extra_row = p.extra + (size_t)z * p.s_extra + (size_t)(row0 + lane) * p.ld_extra;
             const float alpha = REDUCE ? 1.0f : p.alpha;
             const int epi = REDUCE ? GSR_EPI_NONE : p.epilogue;
+            // The addend is read COALESCED, not by accumulator row: lane -> (row 4 i + lane / 8, 16-byte chunk lane % 8) of the
+            // 32 x 32 block, eight lanes per 128-byte row segment, and added in a second pass over the staging block.  (One
+            // row per lane -- the accumulator's own layout -- is 32 different lines per load and made the two products of the
+            // backward pass that carry an addend three times as slow as the others: 676 against 210-220 us.)  Its blocks are
+            // pulled into L2 a tile ahead by cp.async.bulk.prefetch.tensor, one block per lane.
+            if (epi == GSR_EPI_ADD) {
+                const int nxt = tile + n_clusters;
+                if (tile_n == 0 && lane < chunks) tma_prefetch(&mapE, ncol0 + 32 * lane, row0, p.s_extra ? z : 0);
+                if (nxt < total_tiles) {
+                    const int zn = nxt / tiles_mn, mnn = nxt - zn * tiles_mn, mpn = mnn / p.tiles_n;
+                    const int nc0 = (mnn - mpn * p.tiles_n) * p.n_tile;
+                    if (lane < min(chunks_full, (p.N - nc0 + 31) >> 5))
+                        tma_prefetch(&mapE, nc0 + 32 * lane, mpn * 256 + (int)rank * BM + q * 32, p.s_extra ? zn : 0);
+                }
+            }
             const bool odd = tile_n & 1;
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (odd ? (uint32_t)p.acc_base1 : 0u);
             const int first_cnt = odd ? odd_cnt : even_cnt;
@@ -475,11 +496,35 @@ tcgemm3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int j = 0; j < 8; ++j) {                                // row = lane; 16-byte chunk j at (j ^ (lane & 7)): conflict free
                     float4 f = make_float4(__uint_as_float(v[4 * j]) * alpha, __uint_as_float(v[4 * j + 1]) * alpha,
                                            __uint_as_float(v[4 * j + 2]) * alpha, __uint_as_float(v[4 * j + 3]) * alpha);
-                    if (epi != GSR_EPI_NONE && n0 + 4 * j < p.N && (epi == GSR_EPI_BIAS || row0 + lane < p.M)) {   // N % 4 == 0 (launcher)
-                        const float4 e4 = __ldg(reinterpret_cast<const float4*>((epi == GSR_EPI_BIAS ? p.extra : extra_row) + n0 + 4 * j));
-                        f.x += e4.x; f.y += e4.y; f.z += e4.z; f.w += e4.w;
+                    if (epi == GSR_EPI_BIAS && n0 + 4 * j < p.N) {           // one address for the whole warp
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.extra + n0 + 4 * j));
+                        f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
                     }
                     *reinterpret_cast<float4*>(blk + lane * 128 + ((j ^ (lane & 7)) << 4)) = f;
+                }
+                if (epi == GSR_EPI_ADD) {
+                    // loaded AFTER the staging pass: the accumulator registers are dead by now (loading earlier spills), and the
+                    // prefetch has made these L2 hits
+                    const int er = lane >> 3, ec = lane & 7;
+                    const float* extra_blk = p.extra + (size_t)z * p.s_extra + (size_t)(row0 + er) * p.ld_extra + 4 * ec;
+                    __syncwarp();
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {                            // two half passes of 16 rows: 16 registers of addend
+                        float4 e4[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            e4[i] = (row0 + 16 * h + 4 * i + er < p.M && n0 + 4 * ec < p.N)          // N % 4 == 0 (launcher)
+                                        ? __ldg(reinterpret_cast<const float4*>(extra_blk + (size_t)(16 * h + 4 * i) * p.ld_extra + n0))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {                        // row r, chunk ec: a quarter warp covers one 128-byte row
+                            const int r = 16 * h + 4 * i + er;
+                            float4* pos = reinterpret_cast<float4*>(blk + r * 128 + ((ec ^ (r & 7)) << 4));
+                            float4 f = *pos;
+                            f.x += e4[i].x; f.y += e4[i].y; f.z += e4[i].z; f.w += e4[i].w;
+                            *pos = f;
+                        }
+                    }
                 }
                 fence_async_smem();
                 __syncwarp();
@@ -608,7 +653,7 @@ bool tma_ok(const Params& p, int transA, int transB) {
     return true;
 }
 
-int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, cudaStream_t st) {
+int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, cudaStream_t st, const Params* second) {
     using namespace t3;
     Plan pl{};
     pl.tiles_m = tma_head_tiles(p.M);
@@ -617,7 +662,9 @@ int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, c
     pl.items = zdim;
     pl.nsub = reduce ? p.batch : 1;
     pl.splits = reduce ? p.splits : 1;
-    pl.M = p.M; pl.N = p.N; pl.K = p.K; pl.nkb = (p.K + BK - 1) / BK;
+    pl.M = p.M; pl.N = p.N; pl.K = p.K; pl.nkb1 = (p.K + BK - 1) / BK;
+    pl.K2 = second ? second->K : 0;
+    pl.nkb = pl.nkb1 + (pl.K2 + BK - 1) / BK;
     // Accumulator column ranges: UMMA N <= 256 per instruction, N / 2 per CTA a multiple of 8.  K-major B: 160 + 112 for
     // the 268-wide products (the split round 1 probed).  MN-major B lives in 32-column blocks (SWIZZLE_128B_BASE32B
     // atoms); a range may end inside a block -- 256 + 16 for 268 columns, the second range reading the first 8 columns
@@ -648,7 +695,7 @@ int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, c
     pl.alpha = p.alpha; pl.epilogue = p.epilogue; pl.extra = p.extra; pl.ld_extra = p.ld_extra; pl.s_extra = p.s_extra;
     const int R0 = pl.nr0 / 2, R1 = pl.nr1 / 2;
     const long long a_items = pl.a_batched ? p.batch : 1, b_items = pl.b_batched ? p.batch : 1;
-    CUtensorMap mA, mB0, mB1, mC;
+    CUtensorMap mA, mB0, mB1, mC, mE;
     bool ok = true;
     // op(A) rows = M; A stored [M][K] (K-major) or [K][M] (MN-major)
     if (!transA) ok = ok && make_map(&mA, p.A, p.K, p.M, a_items, p.lda, p.sA, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -660,8 +707,25 @@ int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, c
         ok = ok && make_map(&mB0, p.B, p.N, p.K, b_items, p.ldb, p.sB, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         mB1 = mB0;
     }
+    CUtensorMap mA2 = mA, mB02 = mB0, mB12 = mB1;
+    if (second) {                                   // the second pair of operands: same shapes and majors, its own K, pitches and bases
+        const Params& s = *second;
+        if (!transA) ok = ok && make_map(&mA2, s.A, s.K, p.M, a_items, s.lda, s.sA, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+        else         ok = ok && make_map(&mA2, s.A, p.M, s.K, a_items, s.lda, s.sA, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (transB) {
+            ok = ok && make_map(&mB02, s.B, s.K, p.N, b_items, s.ldb, s.sB, 32, R0, CU_TENSOR_MAP_SWIZZLE_128B);
+            ok = ok && make_map(&mB12, s.B, s.K, p.N, b_items, s.ldb, s.sB, 32, R1 > 0 ? R1 : 8, CU_TENSOR_MAP_SWIZZLE_128B);
+        } else {
+            ok = ok && make_map(&mB02, s.B, p.N, s.K, b_items, s.ldb, s.sB, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+            mB12 = mB02;
+        }
+    }
     // C: [items][M][N]; REDUCE writes partial sums of pitch sC = M * N, one per split
     ok = ok && make_map(&mC, p.C, p.N, p.M, zdim, reduce ? p.N : p.ldc, p.sC, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    // the addend of GSR_EPI_ADD, seen by the epilogue's L2 prefetch only (32 x 32 blocks, like the stores)
+    if (!reduce && p.epilogue == GSR_EPI_ADD)
+        ok = ok && make_map(&mE, p.extra, p.N, p.M, p.s_extra ? zdim : 1, p.ld_extra, p.s_extra, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+    else mE = mC;
     if (!ok) return fail(GSR_E_UNSUPPORTED, "tcgemm (TMA): cuTensorMapEncodeTiled failed");
     const int total_tiles = pl.items * pl.tiles_m * pl.tiles_n;
     const int clusters = std::min(total_tiles, kNumSMs / 2);
@@ -671,7 +735,7 @@ int tma_launch(const Params& p, int transA, int transB, bool reduce, int zdim, c
         auto k = tcgemm3_kernel<TA, TB, RED>;                                                                     \
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);         \
         if (e != cudaSuccess) return fail((int)e, "tcgemm (TMA): cudaFuncSetAttribute failed");                  \
-        k<<<grid, THREADS, SMEM_BYTES, st>>>(mA, mB0, mB1, mC, pl);                                               \
+        k<<<grid, THREADS, SMEM_BYTES, st>>>(mA, mB0, mB1, mC, mE, mA2, mB02, mB12, pl);                                               \
     } while (0)
 #define GSR_T3_TT(RED)                                                                                            \
     do {                                                                                                          \

@@ -264,12 +264,14 @@ class GSRLayerFn(Function):
         W, f, U, Pt, F, r, adj, X0 = ctx.saved_tensors
         if g_adj is None and g_Z is None:
             return None, None, None, None
-        g_adj = _c(g_adj) if g_adj is not None else torch.zeros_like(adj)
         g_Z = _c(g_Z) if g_Z is not None else torch.zeros_like(X0)
-        # dX0 = (dX + dX^T)/2 with dX = dZ * sgn(X), zero diagonal;  d_adj += (dX0 + dX0^T) adj = 2 dX0 adj
+        # dX0 = (dX + dX^T)/2 with dX = dZ * sgn(X), zero diagonal;  d_adj += (dX0 + dX0^T) adj = 2 dX0 adj.  The gradient
+        # that arrives for adj itself (the graph convolutions') is NOT added in the product's epilogue (an addend read per
+        # accumulator row made that product three times as slow): the normalise backward sums the two as it reads them.
         gX0 = K.sym_diag_abs_bwd(X0, g_Z)
-        d_adj = K.bgemm(gX0, adj, alpha=2.0, add=g_adj)
-        gF = K.normalize_adj_bwd(F, r, d_adj, pre=True)          # through normalise, abs and the diagonal fill
+        d_adj = K.bgemm(gX0, adj, alpha=2.0)
+        gF = K.normalize_adj_bwd(F, r, d_adj, pre=True,          # through normalise, abs and the diagonal fill
+                                 grad_out2=_c(g_adj) if g_adj is not None else None)
         gP = K.bgemm(gF, f, transB=True)                         # dP = dF f^T     [B, hr, lr] (stacked)
         gf = _wgrad(Pt, gF) if ctx.needs_input_grad[2] else None           # sum_b P^T dF
         gW = _wgrad(gP, U) if ctx.needs_input_grad[0] else None            # sum_b dP U
@@ -301,8 +303,8 @@ class GraphConvFn(Function):
 
 class GraphConvPairFn(Function):
     """models/gsr_model.py:29-30: hidden1 = gc1(Z, adj); hidden2 = gc2(hidden1, adj) as one node.  Same products as
-    two GraphConvFn nodes in the same order; the two contributions to the gradient of ``adj`` meet in the epilogue
-    of the second product instead of a separate 3 x 294 MB addition by autograd."""
+    two GraphConvFn nodes; the two contributions to the gradient of ``adj`` are accumulated in the tensor-memory
+    accumulator of one launch (``bgemm_dual``) instead of a separate 3 x 294 MB addition by autograd."""
 
     @staticmethod
     def forward(ctx, Z, adj, W1, W2):
@@ -322,15 +324,15 @@ class GraphConvPairFn(Function):
         if gH2 is not None:
             gH2 = _c(gH2)
             gS2 = K.bgemm(adj, gH2, transA=True)
-            g_adj = K.bgemm(gH2, S2, transB=True) if ctx.needs_input_grad[1] else None
             gW2 = _wgrad(H1, gS2, transA=True) if ctx.needs_input_grad[3] else None
             gH1 = K.bgemm(gS2, W2, transB=True, add=_c(gH1) if gH1 is not None else None)
-        if gH1 is None:
-            return None, g_adj, None, gW2
+        if gH1 is None:                                  # (cannot happen after the branch above: kept for symmetry)
+            return None, None, None, gW2
         gH1 = _c(gH1)
         gS1 = K.bgemm(adj, gH1, transA=True)
         if ctx.needs_input_grad[1]:
-            g_adj = K.bgemm(gH1, S1, transB=True, add=g_adj)
+            # d adj = dH2 S2^T + dH1 S1^T: ONE launch, both products accumulated in tensor memory
+            g_adj = K.bgemm_dual(gH2, S2, gH1, S1, transB=True) if gH2 is not None else K.bgemm(gH1, S1, transB=True)
         gW1 = _wgrad(Z, gS1, transA=True) if ctx.needs_input_grad[2] else None
         gZ = K.bgemm(gS1, W1, transB=True) if ctx.needs_input_grad[0] else None
         return gZ, g_adj, gW1, gW2

@@ -108,18 +108,32 @@ def normalize_adj_fwd(mx: torch.Tensor, pre: bool = False, want_m: bool = False)
     return out, r, m
 
 
-def normalize_adj_bwd(mx: torch.Tensor, r: torch.Tensor, grad_out: torch.Tensor, pre: bool = False) -> torch.Tensor:
+def normalize_adj_bwd(mx: torch.Tensor, r: torch.Tensor, grad_out: torch.Tensor, pre: bool = False,
+                      grad_out2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Backward of normalize_adj_fwd.  `grad_out2`: a second contribution to the incoming gradient, summed with
+    `grad_out` element by element as both passes read it (the sum is never materialised)."""
     mx, r, grad_out = _f32(mx, "mx"), _f32(r, "r"), _f32(grad_out, "grad_out")
     batch, n = _square_batch(mx, "normalize_adj_bwd: mx")
+    if grad_out2 is not None:
+        grad_out2 = _f32(grad_out2, "grad_out2")
+        if tuple(grad_out2.shape) != tuple(grad_out.shape):
+            raise ValueError("normalize_adj_bwd: grad_out2 shape != grad_out shape")
+        if n % 4 != 0 or any(t.data_ptr() % 16 for t in (mx, grad_out, grad_out2)):     # the strip kernel takes one gradient
+            grad_out, grad_out2 = grad_out + grad_out2, None
     grad = torch.empty_like(mx)
     timer = EW_TIMER
     e0 = timer.start() if timer is not None else None
     ws_floats = lib().gsr_normalize_adj_bwd_workspace(batch, n)
     ws = torch.empty((max(ws_floats, 1),), device=mx.device, dtype=torch.float32)
-    check(lib().gsr_normalize_adj_bwd_tiles(mx.data_ptr(), r.data_ptr(), grad_out.data_ptr(), grad.data_ptr(),
-                                            ws.data_ptr(), batch, n, int(pre), _stream()), "gsr_normalize_adj_bwd_tiles")
+    if grad_out2 is None:
+        check(lib().gsr_normalize_adj_bwd_tiles(mx.data_ptr(), r.data_ptr(), grad_out.data_ptr(), grad.data_ptr(),
+                                                ws.data_ptr(), batch, n, int(pre), _stream()), "gsr_normalize_adj_bwd_tiles")
+    else:
+        check(lib().gsr_normalize_adj_bwd_tiles2(mx.data_ptr(), r.data_ptr(), grad_out.data_ptr(), grad_out2.data_ptr(),
+                                                 grad.data_ptr(), ws.data_ptr(), batch, n, int(pre), _stream()),
+              "gsr_normalize_adj_bwd_tiles2")
     if timer is not None:
-        timer.stop(e0, 12.0 * batch * n * n)
+        timer.stop(e0, (12.0 if grad_out2 is None else 20.0) * batch * n * n)
     return grad
 
 
@@ -243,6 +257,44 @@ def bgemm(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB: bool =
           "gsr_bgemm_f32 / gsr_tcgemm_f32")
     if timer is not None:
         timer.stop(e0, 2.0 * M * N * K * batch, "tc" if use_tc else "simt")
+    return out
+
+
+def bgemm_dual(A1: torch.Tensor, B1: torch.Tensor, A2: torch.Tensor, B2: torch.Tensor, transA: bool = False,
+               transB: bool = False, alpha: float = 1.0) -> torch.Tensor:
+    """C[b] = alpha * (op(A1[b]) @ op(B1[b]) + op(A2[b]) @ op(B2[b])): two per-subject products of one shape summed in the
+    accumulator of ONE launch (gsr_tcgemm_dual_f32) -- the first product is never written out and read back as an addend.
+    Falls back to two launches (the second with add=) off the tensor-core path."""
+    A1, B1, A2, B2 = _f32(A1, "bgemm_dual: A1"), _f32(B1, "bgemm_dual: B1"), _f32(A2, "bgemm_dual: A2"), _f32(B2, "bgemm_dual: B2")
+    if all(t.dim() == 2 for t in (A1, B1, A2, B2)):      # one subject (the reference's batch-1 calls)
+        return bgemm_dual(A1[None], B1[None], A2[None], B2[None], transA=transA, transB=transB, alpha=alpha)[0]
+    if any(t.dim() != 3 for t in (A1, B1, A2, B2)) or len({t.shape[0] for t in (A1, B1, A2, B2)}) != 1:
+        raise ValueError("bgemm_dual: all four operands must be [batch, ., .] with equal batch (or all 2-D)")
+    batch = A1.shape[0]
+
+    def dims(A, B):
+        ar, ac, br, bc = A.shape[-2], A.shape[-1], B.shape[-2], B.shape[-1]
+        M, K = (ac, ar) if transA else (ar, ac)
+        Kb, N = (bc, br) if transB else (br, bc)
+        if K != Kb:
+            raise RuntimeError(f"bgemm_dual: inner dimensions differ: op(A) is {M}x{K}, op(B) is {Kb}x{N}")
+        return M, N, K, ac, bc, ar * ac, br * bc
+
+    M, N, K1, lda1, ldb1, sA1, sB1 = dims(A1, B1)
+    M2, N2, K2, lda2, ldb2, sA2, sB2 = dims(A2, B2)
+    if (M, N) != (M2, N2):
+        raise RuntimeError(f"bgemm_dual: the two products differ in shape: {M}x{N} vs {M2}x{N2}")
+    if not (_tc_ok(A1, B1, lda1, ldb1, sA1, sB1, M * batch) and _tc_ok(A2, B2, lda2, ldb2, sA2, sB2, M * batch)):
+        return bgemm(A2, B2, transA=transA, transB=transB, alpha=alpha,
+                     add=bgemm(A1, B1, transA=transA, transB=transB, alpha=alpha))
+    out = torch.empty((batch, M, N), device=A1.device, dtype=torch.float32)
+    timer = GEMM_TIMER
+    e0 = timer.start() if timer is not None else None
+    check(lib().gsr_tcgemm_dual_f32(A1.data_ptr(), B1.data_ptr(), A2.data_ptr(), B2.data_ptr(), out.data_ptr(),
+                                    M, N, K1, K2, lda1, ldb1, lda2, ldb2, N, sA1, sB1, sA2, sB2, M * N,
+                                    int(transA), int(transB), batch, float(alpha), _stream()), "gsr_tcgemm_dual_f32")
+    if timer is not None:
+        timer.stop(e0, 2.0 * M * N * (K1 + K2) * batch, "tc")
     return out
 
 

@@ -70,6 +70,11 @@ GSR_API int gsr_normalize_adj_bwd(const float* mx, const float* r, const float* 
 GSR_API size_t gsr_normalize_adj_bwd_workspace(int batch, int n);
 GSR_API int gsr_normalize_adj_bwd_tiles(const float* mx, const float* r, const float* grad_out, float* grad_mx,
                                 float* workspace, int batch, int n, int pre, void* stream);
+/* The same with the incoming gradient given as the SUM of two tensors (grad_out2 may be NULL), added as the passes read
+ * them: d adj = 2 dX0 adj + (dH2 S2^T + dH1 S1^T) (models/layers.py:57-59 and 85-86) without an addend epilogue on the
+ * contraction or a separate addition pass.  Tile path only (GSR_E_UNSUPPORTED otherwise when grad_out2 != NULL).        */
+GSR_API int gsr_normalize_adj_bwd_tiles2(const float* mx, const float* r, const float* grad_out, const float* grad_out2,
+                                 float* grad_mx, float* workspace, int batch, int n, int pre, void* stream);
 
 
 /* ------------------------------------------------------------------ a2 / a12
@@ -159,6 +164,14 @@ GSR_API int gsr_tcgemm_f32(const float* A, const float* B, float* C,
                    int transA, int transB, int batch, float alpha,
                    int epilogue, const float* extra, int ld_extra, long long stride_extra,
                    void* stream);
+/* C = alpha (op(A1) op(B1) + op(A2) op(B2)): two products of one shape (M x N, inner sizes K1 and K2) and the same operand
+ * majors summed into one result -- d adj = dH2 S2^T + dH1 S1^T of the two graph convolutions (models/layers.py:85-86 applied
+ * twice, models/gsr_model.py:30-32).  Both products accumulate in tensor memory inside one launch of the TMA kernel, so the
+ * first product is never written out and read back as an addend.                                                          */
+GSR_API int gsr_tcgemm_dual_f32(const float* A1, const float* B1, const float* A2, const float* B2, float* C,
+                        int M, int N, int K1, int K2, int lda1, int ldb1, int lda2, int ldb2, int ldc,
+                        long long strideA1, long long strideB1, long long strideA2, long long strideB2, long long strideC,
+                        int transA, int transB, int batch, float alpha, void* stream);
 GSR_API size_t gsr_tcgemm_reduce_workspace(int M, int N, int batch, int* splits_out);
 GSR_API int gsr_tcgemm_reduce_f32(const float* A, const float* B, float* C,
                           int M, int N, int K, int lda, int ldb, int ldc,

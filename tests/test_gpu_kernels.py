@@ -425,6 +425,62 @@ def test_tcgemm_pair_kernel_equals_one_cta_kernel(cuda_pkg, K):
         assert float((a - c).abs().max()) < 4e-6 * float(a.abs().max())
 
 
+@pytest.mark.parametrize("batch,k2", [(2, 268), (80, 268), (5, 160)])
+def test_tcgemm_dual_product(cuda_pkg, K, batch, k2):
+    """gsr_tcgemm_dual_f32: C = alpha (op(A1) op(B1) + op(A2) op(B2)) accumulated in tensor memory by ONE launch of the TMA
+    kernel (d adj = dH2 S2^T + dH1 S1^T of the two graph convolutions, models/layers.py:85-86 twice) against the float64
+    sum within 2e-6 sum|a||b| -- rows 0..255 (tensor kernel) and the ragged rows 256..267 (FP32 kernels, second launch
+    adding in place) -- for NT, NN and TN operands, inner sizes that differ, and more tiles than CTA pairs; and against
+    the two-launch route (tcgemm_dual = 0: second product with the addend epilogue), which differs by rounding only."""
+    g = torch.Generator(device="cuda").manual_seed(500 + batch)
+    A1 = torch.randn(batch, 268, 268, device="cuda", generator=g); B1 = torch.randn(batch, 268, 268, device="cuda", generator=g)
+    A2 = torch.randn(batch, 268, k2, device="cuda", generator=g); B2 = torch.randn(batch, 268, k2, device="cuda", generator=g)
+    d = lambda t: t.double()
+    T = lambda t: t.transpose(1, 2)
+    cases = [
+        (dict(transB=True, alpha=1.0), (A1, B1, A2, B2), d(A1) @ T(d(B1)) + d(A2) @ T(d(B2)), d(A1).abs() @ T(d(B1).abs()) + d(A2).abs() @ T(d(B2).abs())),
+        (dict(transB=True, alpha=-0.5), (A1, B1, A2, B2), -0.5 * (d(A1) @ T(d(B1)) + d(A2) @ T(d(B2))), 0.5 * (d(A1).abs() @ T(d(B1).abs()) + d(A2).abs() @ T(d(B2).abs()))),
+    ]
+    if k2 == 268:
+        cases += [
+            (dict(alpha=1.0), (A1, B1, A2, B2), d(A1) @ d(B1) + d(A2) @ d(B2), d(A1).abs() @ d(B1).abs() + d(A2).abs() @ d(B2).abs()),
+            (dict(transA=True, alpha=2.0), (A1, B1, A2, B2), 2 * (T(d(A1)) @ d(B1) + T(d(A2)) @ d(B2)), 2 * (T(d(A1).abs()) @ d(B1).abs() + T(d(A2).abs()) @ d(B2).abs())),
+        ]
+    n0 = cuda_pkg.launch_count()
+    for kw, ops, ref, bound in cases:
+        got = K.bgemm_dual(*ops, **kw)
+        err = (got.double() - ref).abs()
+        assert float(err[:, :256].max()) <= 2e-6 * float(bound.max()), kw
+        assert float(err[:, 256:].max()) <= 2e-6 * float(bound.max()), kw
+        try:
+            cuda_pkg.set_tuning("tcgemm_dual", 0)
+            two = K.bgemm_dual(*ops, **kw)
+        finally:
+            cuda_pkg.set_tuning("tcgemm_dual", 1)
+        assert float((two - got).abs().max()) <= 4e-6 * float(bound.max()), kw
+        assert float((two.double() - ref).abs().max()) <= 2e-6 * float(bound.max()), kw
+    assert cuda_pkg.launch_count() > n0
+    with pytest.raises(RuntimeError):
+        K.bgemm_dual(A1, B1, A2[:, :200].contiguous(), B2, transB=True)         # the two products differ in shape
+
+
+def test_normalize_bwd_two_gradients(cuda_pkg, K):
+    """gsr_normalize_adj_bwd_tiles2: the incoming gradient given as two tensors, summed as the passes read them, is BIT
+    identical to the backward of their materialised fp32 sum (pre = 0 and pre = 1; 268 nodes = the tile path, 30 nodes =
+    the wrapper adds first and takes the strip kernel)."""
+    for n, batch in ((268, 6), (160, 3), (30, 4)):
+        g = torch.Generator(device="cuda").manual_seed(900 + n)
+        mx = torch.rand(batch, n, n, device="cuda", generator=g) + 0.05      # positive row sums (r = rowsum^-1/2)
+        g1 = torch.randn(batch, n, n, device="cuda", generator=g); g2 = torch.randn(batch, n, n, device="cuda", generator=g)
+        for pre in (False, True):
+            _, r, _ = K.normalize_adj_fwd(mx, pre=pre)
+            want = K.normalize_adj_bwd(mx, r, g1 + g2, pre=pre)
+            got = K.normalize_adj_bwd(mx, r, g1, pre=pre, grad_out2=g2)
+            assert torch.equal(got, want), (n, pre)
+    with pytest.raises(ValueError):
+        K.normalize_adj_bwd(mx, r, g1, grad_out2=g2[:, :10])
+
+
 @pytest.mark.parametrize("batch", [1, 3, 80])
 def test_tcgemm_tma_kernel(cuda_pkg, K, batch):
     """The TMA-fed persistent CTA-pair kernel (csrc/tcgemm_tma.cu; default route for M >= 256, N <= 272): every operand

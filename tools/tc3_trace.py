@@ -20,9 +20,12 @@ fn = lib.gsr_tcgemm_f32
 fn.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, ll, ll, ll, i32, i32, i32, f32, i32, vp, i32, ll, vp]
 per_subject = "--per-subject" in sys.argv
 transB = 1 if "--nt" in sys.argv else 0
+with_add = "--add" in sys.argv          # per-subject product with the GSR_EPI_ADD epilogue (the d adj products of the backward pass)
+E = torch.rand(B, 268, 268, device="cuda", generator=g) if with_add else None
 for _ in range(3):
     if per_subject:
-        rc = fn(X.data_ptr(), Y.data_ptr(), C.data_ptr(), 268, 268, 268, 268, 268, 268, 268 * 268, 268 * 268, 268 * 268, 0, transB, B, 1.0, 0, None, 0, 0,
+        rc = fn(X.data_ptr(), Y.data_ptr(), C.data_ptr(), 268, 268, 268, 268, 268, 268, 268 * 268, 268 * 268, 268 * 268, 0, transB, B, 1.0,
+                2 if with_add else 0, E.data_ptr() if with_add else None, 268 if with_add else 0, 268 * 268 if with_add else 0,
                 torch.cuda.current_stream().cuda_stream)
     else:
         rc = fn(X.data_ptr(), W.data_ptr(), C.data_ptr(), B * 268, 268, 268, 268, 268, 268, 0, 0, 0, 0, transB, 1, 1.0, 0, None, 0, 0,
@@ -39,7 +42,7 @@ t0 = min(x for x in t if x)
 def ev(rank, role, it, e):
     x = t[((rank * 4 + role) * ITS + it) * EVS + e]
     return x - t0 if x else -1
-print("mode:", "per-subject" if per_subject else "stacked", "NT" if transB else "NN")
+print("mode:", "per-subject" if per_subject else "stacked", "NT" if transB else "NN", "+ addend" if with_add else "")
 for rank in (0, 1):
     print(f"--- CTA rank {rank}")
     for it in range(30):
