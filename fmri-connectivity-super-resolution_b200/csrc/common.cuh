@@ -35,6 +35,7 @@ inline int launched(const char* what) {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 constexpr int kNumSMs = 148;   // B200
+constexpr int kMaxDynSmem = 232448;   // dynamic shared memory one CTA may opt in to (227 KB)
 
 // csrc/eigh.cu: Jacobi pass over the graphs whose info is -2 (the fallback behind csrc/eigh_tridiag.cu)
 int eigh_jacobi_redo_failed(const float* A, float* w, float* U, int32_t* info, float* scratch, long long stride,

@@ -36,6 +36,10 @@
 
 namespace gsr {
 int g_eigh_ql_max_iter = 30;    // gsr_set_tuning("eigh_ql_max_iter", k): QL iterations allowed per eigenvalue (EISPACK: 30)
+int g_eigh_k2_lanes = 1;        // gsr_set_tuning("eigh_k2_lanes", 0|1): QL iteration with lane = graph (32 graphs per warp) for batches >= 32
+                                // (default), 0 = one warp per graph
+int g_eigh_chunks = 8;          // gsr_set_tuning("eigh_chunks", k): the n <= 160 decomposition of a batch of >= 256 graphs runs as up to k
+                                // chunks on internal streams (K2 of a chunk under K1 / K3 of the others); 0 or 1 = one launch per stage
 int g_eigh_redo = 1;            // gsr_set_tuning("eigh_redo_failed", 0|1): Jacobi pass over the graphs the QL iteration gave up on
                                 // (info == -2), in the same stream (default); 0 leaves them flagged with NaN results
 namespace tq {
@@ -61,6 +65,7 @@ struct Work {
     float* scale;        // [batch]           power-of-two input scaling
     int* counts;         // [batch][4]        QL iterations, stream entries, status, -
     uint32_t* hdr;       // [batch][hdr_cap]  lo16 | hi16 << 8 of every QL iteration (16-column blocks)
+    int* chunk_done;     // [64]              graphs of chunk c whose K1 has finished (chunked pipeline: K2 of the chunk waits on it)
     int cap, hdr_cap;
 };
 
@@ -81,6 +86,7 @@ static size_t carve(Work* wk, void* base, int batch, int n) {
     const size_t o_sc = take((size_t)batch * sizeof(float));
     const size_t o_cnt = take((size_t)batch * 4 * sizeof(int));
     const size_t o_hdr = take((size_t)batch * hcap * sizeof(uint32_t));
+    const size_t o_done = take(64 * sizeof(int));
     if (wk) {
         char* b = static_cast<char*>(base);
         wk->stream = reinterpret_cast<float2*>(b + o_stream);
@@ -91,6 +97,7 @@ static size_t carve(Work* wk, void* base, int batch, int n) {
         wk->scale = reinterpret_cast<float*>(b + o_sc);
         wk->counts = reinterpret_cast<int*>(b + o_cnt);
         wk->hdr = reinterpret_cast<uint32_t*>(b + o_hdr);
+        wk->chunk_done = reinterpret_cast<int*>(b + o_done);
         wk->cap = cap;
         wk->hdr_cap = hcap;
     }
@@ -100,7 +107,7 @@ static size_t carve(Work* wk, void* base, int batch, int n) {
 // ------------------------------------------------------------------------------------ K1
 __global__ void __launch_bounds__(MAXN, 2)
 tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* __restrict__ Uout,
-               int32_t* __restrict__ info, const Work wk, int n) {
+               int32_t* __restrict__ info, const Work wk, int n, int chunk_graphs) {
     __shared__ __align__(16) float tile[5 * 176];            // xbuf[2][176], vbuf, wbuf, pbuf
     __shared__ __align__(16) float red[8];
     __shared__ float dd[MAXN], ee[MAXN];
@@ -134,6 +141,10 @@ tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* _
         for (int e = tid; e < n * n; e += nthr) Uout[(size_t)g * n * n + e] = qnan;
         for (int e = tid; e < n; e += nthr) Wout[(size_t)g * n + e] = qnan;
         if (tid == 0) { info[g] = -1; wk.counts[4 * g + 0] = 0; wk.counts[4 * g + 1] = 0; wk.counts[4 * g + 2] = -1; }
+        if (chunk_graphs > 0) {                                        // chunked pipeline: this graph is done (see the end of the kernel)
+            __syncthreads();
+            if (tid == 0) { __threadfence(); atomicAdd(wk.chunk_done + g / chunk_graphs, 1); }
+        }
         return;
     }
 #pragma unroll
@@ -274,6 +285,12 @@ tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* _
         wk.d[(size_t)g * n + j] = dd[j];
         wk.e[(size_t)g * n + j] = (j < n - 1) ? ee[j] : 0.f;
     }
+    if (chunk_graphs > 0) {
+        // chunked pipeline: everything this CTA wrote (d, e, reflectors, counts) is visible device-wide before the count of
+        // finished graphs of its chunk goes up; the K2 CTA of the chunk -- resident since the fork -- polls that count
+        __syncthreads();
+        if (tid == 0) { __threadfence(); atomicAdd(wk.chunk_done + g / chunk_graphs, 1); }
+    }
 }
 
 // ------------------------------------------------------------------------------------ K2
@@ -386,6 +403,167 @@ tql_scalar_kernel(const Work wk, int n, int batch, int max_iter) {
     }
     for (int j = lane; j < n; j += 32) wk.d[(size_t)g * n + j] = d[j];
     if (lane == 0) { cnt[0] = nit; cnt[1] = pos; cnt[2] = status; }
+}
+
+// K2, lane = graph.  The kernel above keeps ONE lane of a warp busy per graph: with 1024 graphs resident it is bound by
+// instruction issue (7 warps per SM x ~40 instructions per rotation against a ~45-cycle dependent chain), i.e. 1/32 of the
+// issued lanes do work.  Here a warp runs the QL iterations of 32 graphs in lockstep, lane = graph: 32 warps for 1024
+// graphs, every one alone on its scheduler, so the time is the chain latency and the kernel leaves the SMs free for whatever
+// runs next to it.  Per-lane state (l, m, the tridiagonal in shared memory at [index][lane]: bank = lane whatever the index);
+// the lanes meet once per QL iteration ("trip"); the rotation loop of a trip runs to the longest lane's m - l.
+// Differences to the one-lane kernel, all inside the freedom of the algorithm:
+//   * the split search is not repeated before every iteration: the smallest index whose new off-diagonal is negligible is
+//     tracked while the rotations of an iteration produce it, and serves the next iteration (also after l advances by one;
+//     a full scan runs only at the start and after two eigenvalues deflate in a row).  It is judged with the tst1 of the
+//     iteration that produced it -- never larger than the current one, so a split may be found an iteration late, never
+//     wrongly;
+//   * the shift h is subtracted from d[l+2 .. m] as the rotation loop reads them (same values), from d[m+1 ..] in a loop.
+// Stream / header format and all arithmetic of a rotation are those of tql_scalar_kernel.
+constexpr int K2L_WARPS = 2;            // warps per CTA, each on its own scheduler (4 made the kernel LSU bound: a lane-strided STG is 32 sector requests)
+__global__ void __launch_bounds__(32 * K2L_WARPS)
+tql_scalar_lanes_kernel(const Work wk, int n, int g_first, int batch, int max_iter, const int* wait_count, int wait_target) {
+    extern __shared__ __align__(16) float sm_all[];
+    // graphs [g_first, batch): warp (blockIdx.x, wl) takes 32 of them.  Chunked pipeline: this CTA has been resident since the
+    // fork (it owns its SM: the launch asks for all of the shared memory) and polls the number of graphs of its chunk whose
+    // K1 has finished; K1 publishes with __threadfence + atomicAdd, the acquire load + barrier order every thread's reads.
+    if (wait_count) {
+        if (threadIdx.x == 0) {
+            for (unsigned spin = 0;; ++spin) {
+                int v;
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(wait_count) : "memory");
+                if (v >= wait_target) break;
+                if (spin > (1u << 22)) { printf("eigh K2: poll timeout, block %d count %d target %d\n", (int)blockIdx.x, v, wait_target); __trap(); }   // a protocol bug must fault, not hang the GPU
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int np = n + 16;                                   // 8 pad | n | 8 pad per array: index -1 and n .. n+3 are readable
+    float* sm = sm_all + (size_t)wl * 2 * np * 32;
+    const int g0 = g_first + (blockIdx.x * (blockDim.x >> 5) + wl) * 32, g = g0 + lane;
+    if (g0 >= batch) return;
+    float* d = sm + 8 * 32 + lane;                           // d[j] at d[32 * j]
+    float* e = sm + (np + 8) * 32 + lane;
+    for (int gg = 0; gg < 32; ++gg) {                        // coalesced over j per graph
+        const int gi = g0 + gg;
+        const bool ok = gi < batch && wk.counts[4 * gi + 2] != -1;
+        for (int j = lane - 8; j < n + 8; j += 32) {
+            float dv = 0.f, ev = 0.f;
+            if (ok && j >= 0 && j < n) { dv = wk.d[(size_t)gi * n + j]; if (j < n - 1) ev = wk.e[(size_t)gi * n + j]; }
+            sm[(8 + j) * 32 + gg] = dv;
+            sm[(np + 8 + j) * 32 + gg] = ev;
+        }
+    }
+    __syncwarp();
+    const bool live = g < batch && wk.counts[4 * min(g, batch - 1) + 2] != -1;      // -1: non-finite input (K1 wrote the outputs)
+    float2* out = wk.stream + (size_t)min(g, batch - 1) * wk.cap;
+    uint32_t* hdr = wk.hdr + (size_t)min(g, batch - 1) * wk.hdr_cap;
+    const float2 ident = make_float2(1.0f, 0.0f);
+    int status = live ? 0 : 1;                               // 1: lane without a graph
+    int l = 0, m = 0, jc = 0, pos = 0, nit = 0;
+    float f = 0.f, tst1 = 0.f;
+    auto negl = [&](float v) { return tst1 + fabsf(v) == tst1; };
+    auto scan = [&](int from) {                              // smallest m >= from with a negligible e[m]; e[n-1] = 0 ends it
+        int mm = from;
+        for (;;) {
+            const float v0 = e[32 * mm], v1 = e[32 * (mm + 1)], v2 = e[32 * (mm + 2)], v3 = e[32 * (mm + 3)];
+            if (negl(v0)) break;
+            if (negl(v1)) { mm += 1; break; }
+            if (negl(v2)) { mm += 2; break; }
+            if (negl(v3)) { mm += 3; break; }
+            mm += 4;
+        }
+        return min(mm, n - 1);
+    };
+    auto deflate = [&]() {                                   // eigenvalues that need no (further) iteration: m == l
+        while (m == l) {
+            d[32 * l] += f;
+            jc = 0;
+            if (++l >= n) break;
+            tst1 = fmaxf(tst1, fabsf(d[32 * l]) + fabsf(e[32 * l]));
+            m = scan(l);
+        }
+    };
+    if (status == 0) {
+        tst1 = fabsf(d[0]) + fabsf(e[0]);
+        m = scan(0);
+        deflate();
+    }
+    for (;;) {
+        const bool run = status == 0 && l < n;
+        if (!__any_sync(0xffffffffu, run)) break;
+        if (!run) continue;
+        const int lo = l & ~15, hi = (m + 15) & ~15;
+        if (++jc > max_iter) { status = 2; continue; }
+        if (pos + (hi - lo) > wk.cap - BLK || nit >= wk.hdr_cap) { status = 3; continue; }
+        // Wilkinson shift
+        const float gl = d[32 * l], el = e[32 * l];
+        const float p0 = (d[32 * (l + 1)] - gl) / (2.0f * el);
+        const float r0 = sqrtf(fmaf(p0, p0, 1.0f));
+        const float den = p0 + copysignf(r0, p0);
+        const float dl = el / den, dl1 = el * den;
+        const float h = gl - dl;
+        d[32 * l] = dl; d[32 * (l + 1)] = dl1;
+        for (int q = max(m + 1, l + 2); q < n; ++q) d[32 * q] -= h;          // below a split (rare); d[l+2 .. m] get it on the fly
+        f += h;
+        float2* o = out + pos;
+        hdr[nit] = (uint32_t)(lo >> 4) | ((uint32_t)(hi >> 4) << 8);
+        for (int k = 0; k < hi - m; ++k) o[k] = ident;                       // rotation indices hi-1 .. m
+        o += hi - m;
+        float p = d[32 * m] - (m >= l + 2 ? h : 0.f), c = 1.0f, s = 0.0f;
+        float s_prev = 0.0f, c_prev = 1.0f, c_prev2 = 1.0f;
+        const float el1 = e[32 * (l + 1)];
+        float ei = e[32 * (m - 1)], di = d[32 * (m - 1)] - (m - 1 >= l + 2 ? h : 0.f);
+        int mneg = m;                                                        // e[m] becomes s r = 0
+#pragma unroll 2
+        for (int q = m - 1; q >= l; --q) {
+            const float ein = e[32 * (q - 1)];                               // next rotation's operands (index -1 is padding)
+            const float din = d[32 * (q - 1)] - (q - 1 >= l + 2 ? h : 0.f);
+            const float gg = c * ei, hh = c * p;
+            const float x = fmaf(p, p, ei * ei);
+            float rinv;
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(x));
+            const float hd = fmaf(-0.5f * x, rinv * rinv, 0.5f);             // see tql_scalar_kernel: first-order unit-norm correction
+            const float c0 = p * rinv, s0 = ei * rinv, xr = x * rinv;
+            const float t = fmaf(c0, di, -s0 * gg);
+            float cn = fmaf(c0, hd, c0), sn = fmaf(s0, hd, s0), r = fmaf(xr, hd, xr), pn = fmaf(t, hd, t);
+            if (x < 1.17549435e-38f) { r = 0.f; cn = 1.0f; sn = 0.0f; pn = di; }
+            const float enew = s * r;
+            e[32 * (q + 1)] = enew;
+            if (negl(enew)) mneg = q + 1;                                    // q descends: the last hit is the smallest index
+            s_prev = s; c_prev2 = c_prev; c_prev = c;
+            s = sn; c = cn;
+            p = pn;
+            d[32 * (q + 1)] = hh + s * fmaf(c, gg, s * di);
+            *o++ = make_float2(c, s);
+            ei = ein; di = din;
+        }
+        p = -s * s_prev * c_prev2 * el1 * e[32 * l] / dl1;
+        e[32 * l] = s * p;
+        d[32 * l] = c * p;
+        for (int k = 0; k < l - lo; ++k) o[k] = ident;                       // rotation indices l-1 .. lo
+        pos += hi - lo;
+        ++nit;
+        if (tst1 + fabsf(e[32 * l]) <= tst1) {                               // eigenvalue l converged
+            d[32 * l] += f;
+            jc = 0;
+            if (++l < n) {
+                tst1 = fmaxf(tst1, fabsf(d[32 * l]) + fabsf(e[32 * l]));
+                m = negl(e[32 * l]) ? l : max(mneg, l);
+                deflate();
+            }
+        } else {
+            m = mneg;
+        }
+    }
+    __syncwarp();
+    for (int gg = 0; gg < 32; ++gg) {
+        const int gi = g0 + gg;
+        if (gi < batch && wk.counts[4 * gi + 2] != -1)
+            for (int j = lane; j < n; j += 32) wk.d[(size_t)gi * n + j] = sm[(8 + j) * 32 + gg];
+    }
+    if (live) { int* cnt = wk.counts + 4 * g; cnt[0] = nit; cnt[1] = pos; cnt[2] = status; }
 }
 
 // ------------------------------------------------------------------------------------ K3
@@ -960,6 +1138,117 @@ tql_finish_global_kernel(const Work wk, float* __restrict__ Wout, float* __restr
 
 using namespace gsr;
 
+// K2 for graphs [g_first, g_end): lane = graph for batches that fill warps, one warp per graph otherwise.  `hog`: ask for all of an
+// SM's shared memory so that the CTA runs alone on it (chunked pipeline); wait_count / wait_target: see the kernel.
+static int launch_k2(const gsr::tq::Work& wk, int n, int g_first, int g_end, cudaStream_t st, bool hog = false,
+                     const int* wait_count = nullptr, int wait_target = 0) {
+    using namespace gsr;
+    const int count = g_end - g_first;
+    if (g_eigh_k2_lanes && (count >= 32 || wait_count)) {
+        const size_t per_warp = (size_t)2 * (n + 16) * 32 * sizeof(float);
+        const int wpc = (int)std::max<size_t>(1, std::min<size_t>(tq::K2L_WARPS, kMaxDynSmem / per_warp));
+        const size_t smem = hog ? (size_t)kMaxDynSmem : per_warp * wpc;
+        cudaError_t e = cudaFuncSetAttribute(tq::tql_scalar_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+        if (e != cudaSuccess) return fail((int)e, "eigh_tridiag: cudaFuncSetAttribute failed");
+        tq::tql_scalar_lanes_kernel<<<(count + 32 * wpc - 1) / (32 * wpc), 32 * wpc, smem, st>>>(wk, n, g_first, g_end, g_eigh_ql_max_iter,
+                                                                                              wait_count, wait_target);
+        return launched("eigh_tql_scalar_lanes");
+    }
+    tq::Work w1 = wk;                                        // the one-warp kernel indexes from 0
+    w1.stream += (size_t)g_first * wk.cap; w1.d += (size_t)g_first * n; w1.e += (size_t)g_first * n;
+    w1.counts += 4 * (size_t)g_first; w1.hdr += (size_t)g_first * wk.hdr_cap;
+    tq::tql_scalar_kernel<<<(count + tq::K2_WARPS - 1) / tq::K2_WARPS, 32 * tq::K2_WARPS, 0, st>>>(w1, n, count, g_eigh_ql_max_iter);
+    return launched("eigh_tql_scalar");
+}
+
+// Internal streams of the chunked decomposition.  K2 is a latency chain that occupies 1 warp per 32 graphs for ~1.3 ms while K1
+// and K3 fill the SMs' register files but leave issue slots and ~10 K registers per SM free: with the batch cut into chunks, each
+// on its own stream (K1 -> K2 -> K3 -> K4 per chunk), the chain of one chunk runs under the K1 / K3 of the others.  Earlier chunks
+// get the higher stream priority so that the block scheduler drains them first (a pipeline, not a round robin).  The streams fork
+// from and join the caller's stream through events, so the whole thing is capturable into a CUDA graph.  Created on first use.
+namespace {
+constexpr int kMaxChunks = 8;
+struct ChunkPool {
+    cudaStream_t s[kMaxChunks];
+    cudaEvent_t fork, join[kMaxChunks];
+    bool ok = false;
+};
+ChunkPool* chunk_pool() {
+    static ChunkPool pool;
+    static bool tried = false;
+    if (tried) return pool.ok ? &pool : nullptr;
+    tried = true;
+    int lo = 0, hi = 0;                                  // lo: least priority (numerically greatest), hi: greatest
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { lo = hi = 0; }
+    for (int c = 0; c < kMaxChunks; ++c) {
+        const int prio = std::max(hi, std::min(lo, hi + c * std::max(1, (lo - hi + 1)) / kMaxChunks));
+        if (cudaStreamCreateWithPriority(&pool.s[c], cudaStreamNonBlocking, prio) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (cudaEventCreateWithFlags(&pool.join[c], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    if (cudaEventCreateWithFlags(&pool.fork, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    // Lazy module loading: the FIRST launch of a kernel may need a context synchronisation, which never returns while a K2
+    // CTA is resident and polling for exactly that kernel (K1) -- so every kernel of the pipeline is loaded here, before any
+    // of them can wait for another.
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, gsr::tq::tridiag_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tql_scalar_lanes_kernel) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa, gsr::tq::tql_apply_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tql_finish_kernel) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    pool.ok = true;
+    return &pool;
+}
+}  // namespace
+
+#ifdef GSR_EIGH_TRACE
+// Timeline of the chunked decomposition (tools/eigh_timeline.py builds a private copy of the library with -DGSR_EIGH_TRACE):
+// a timing event after every stage of every chunk, read back as milliseconds since the fork.
+static cudaEvent_t g_tr_ev[8][5], g_tr_fork;
+static bool g_tr_init = false;
+static int g_tr_chunk = 0;
+static void tr_mark(int stage, cudaStream_t st) { cudaEventRecord(g_tr_ev[g_tr_chunk][stage], st); }
+extern "C" __attribute__((visibility("default"))) int gsr_eigh_timeline_read(float* ms, int chunks) {
+    for (int c = 0; c < chunks; ++c)
+        for (int k = 0; k < 5; ++k)
+            if (cudaEventElapsedTime(&ms[c * 5 + k], g_tr_fork, g_tr_ev[c][k]) != cudaSuccess) { cudaGetLastError(); ms[c * 5 + k] = -1.f; }
+    return 0;
+}
+#define GSR_TR(stage) tr_mark(stage, st)
+#else
+#define GSR_TR(stage) do { } while (0)
+#endif
+
+// K3 + K4 of the n <= 160 route for graphs [g0, g0 + nb) on stream st
+static int launch_small_apply(float* w, float* U, int32_t* info, const gsr::tq::Work& full, int g0, int nb, int n,
+                              int canonical_sign, cudaStream_t st) {
+    using namespace gsr;
+    tq::Work wk = full;
+    wk.stream += (size_t)g0 * full.cap;
+    wk.V += (size_t)g0 * n * tq::ldv_of(n);
+    wk.Zt += (size_t)g0 * n * n;
+    wk.d += (size_t)g0 * n;
+    wk.e += (size_t)g0 * n;
+    wk.scale += g0;
+    wk.counts += 4 * (size_t)g0;
+    wk.hdr += (size_t)g0 * full.hdr_cap;
+    U += (size_t)g0 * n * n; w += (size_t)g0 * n; info += g0;
+    const int threads = 32 * ((n + 31) / 32);
+    const int units_per_graph = threads / 32, total_units = units_per_graph * nb;
+    const size_t smem3 = (size_t)tq::K3_WARPS * tq::RING_FLOATS * sizeof(float);
+    GSR_TR(2);
+    tq::tql_apply_kernel<<<(total_units + tq::K3_WARPS - 1) / tq::K3_WARPS, 32 * tq::K3_WARPS, smem3, st>>>(wk, n, units_per_graph, total_units);
+    int rc = launched("eigh_tql_apply");
+    if (rc) return rc;
+    GSR_TR(3);
+    const size_t smem4 = ((size_t)n * tq::LDZ + 3 * (size_t)n) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(tq::tql_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+    if (e != cudaSuccess) return fail((int)e, "eigh_tridiag: cudaFuncSetAttribute failed");
+    tq::tql_finish_kernel<<<nb, 256, smem4, st>>>(wk, w, U, info, n, canonical_sign);
+    rc = launched("eigh_tql_finish");
+    GSR_TR(4);
+    return rc;
+}
+
 extern "C" size_t gsr_eigh_tridiag_workspace(int batch, int n) {
     if (batch <= 0 || n <= 0 || n > tq::BIGN) return 0;
     return tq::carve(nullptr, nullptr, batch, n);
@@ -986,8 +1275,7 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
         tq::tridiag_packed_kernel<<<batch, threads, smem1, st>>>(A, w, U, info, wk, n);
         int rcb = launched("eigh_tridiag_packed");
         if (rcb) return rcb;
-        tq::tql_scalar_kernel<<<(batch + tq::K2_WARPS - 1) / tq::K2_WARPS, 32 * tq::K2_WARPS, 0, st>>>(wk, n, batch, g_eigh_ql_max_iter);
-        if ((rcb = launched("eigh_tql_scalar"))) return rcb;
+        if ((rcb = launch_k2(wk, n, 0, batch, st))) return rcb;
         const int rows_per_cta = (n + 1) / 2, thr3 = 32 * ((rows_per_cta + 31) / 32);
         const int ldr = (rows_per_cta + 1) | 1, ncols = ((n + 15) & ~15) + 1;
         const size_t smem3b = ((((size_t)ncols * ldr + 3) & ~(size_t)3) + (size_t)(thr3 / 32) * tq::RINGB) * sizeof(float);
@@ -1002,24 +1290,61 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
         return g_eigh_redo ? eigh_jacobi_redo_failed(A, w, U, info, reinterpret_cast<float*>(wk.stream), 2LL * wk.cap, batch, n, canonical_sign, st) : 0;
     }
 
-    tq::tridiag_kernel<<<batch, threads, 0, st>>>(A, w, U, info, wk, n);
-    int rc = launched("eigh_tridiag");
-    if (rc) return rc;
-
-    tq::tql_scalar_kernel<<<(batch + tq::K2_WARPS - 1) / tq::K2_WARPS, 32 * tq::K2_WARPS, 0, st>>>(wk, n, batch, g_eigh_ql_max_iter);
-    rc = launched("eigh_tql_scalar");
-    if (rc) return rc;
-
-    const int units_per_graph = threads / 32, total_units = units_per_graph * batch;
-    const size_t smem3 = (size_t)tq::K3_WARPS * tq::RING_FLOATS * sizeof(float);
-    tq::tql_apply_kernel<<<(total_units + tq::K3_WARPS - 1) / tq::K3_WARPS, 32 * tq::K3_WARPS, smem3, st>>>(wk, n, units_per_graph, total_units);
-    rc = launched("eigh_tql_apply");
-    if (rc) return rc;
-
-    const size_t smem4 = ((size_t)n * tq::LDZ + 3 * (size_t)n) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(tq::tql_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
-    if (e != cudaSuccess) return fail((int)e, "eigh_tridiag: cudaFuncSetAttribute failed");
-    tq::tql_finish_kernel<<<batch, 256, smem4, st>>>(wk, w, U, info, n, canonical_sign);
-    if ((rc = launched("eigh_tql_finish"))) return rc;
+    int rc = 0;
+    // Chunked pipeline (batch >= 256): K1 is ONE launch on the caller's stream (its CTAs run in graph order and count the
+    // finished graphs of each chunk); every chunk has a stream with K2 -> K3 -> K4.  The K2 CTAs are launched FIRST: each asks
+    // for a whole SM, becomes resident at the fork and polls its chunk's count, so the ~1.3 ms rotation chain of a chunk runs
+    // on its own SM (one warp per scheduler, nothing else to share issue slots with) under the K1 / K3 of the other chunks,
+    // which have the remaining SMs.  K1 never waits for anything, so the polling cannot deadlock; if a K2 CTA is placed late
+    // (no empty SM at the fork) it simply starts late.  Forks from / joins the caller's stream through events: capturable.
+    const int per = std::max(128, (((batch + kMaxChunks - 1) / kMaxChunks) + 127) & ~127);       // graphs per chunk
+    int nchunks = (g_eigh_chunks > 1 && g_eigh_k2_lanes && batch >= 256) ? (batch + per - 1) / per : 1;
+    ChunkPool* pool = nchunks > 1 ? chunk_pool() : nullptr;
+    if (!pool || nchunks > std::min(g_eigh_chunks, kMaxChunks)) nchunks = 1;
+#ifdef GSR_EIGH_TRACE
+    if (!g_tr_init) {
+        for (int c = 0; c < 8; ++c) for (int k = 0; k < 5; ++k) cudaEventCreate(&g_tr_ev[c][k]);
+        cudaEventCreate(&g_tr_fork);
+        g_tr_init = true;
+    }
+    cudaEventRecord(g_tr_fork, st);
+    g_tr_chunk = 0;
+#endif
+    if (nchunks == 1) {
+        GSR_TR(0);
+        tq::tridiag_kernel<<<batch, threads, 0, st>>>(A, w, U, info, wk, n, 0);
+        if ((rc = launched("eigh_tridiag"))) return rc;
+        GSR_TR(1);
+        if ((rc = launch_k2(wk, n, 0, batch, st))) return rc;
+        if ((rc = launch_small_apply(w, U, info, wk, 0, batch, n, canonical_sign, st))) return rc;
+    } else {
+        if (cudaMemsetAsync(wk.chunk_done, 0, 64 * sizeof(int), st) != cudaSuccess) return fail((int)cudaGetLastError(), "eigh_tridiag: cudaMemsetAsync failed");
+        if (cudaEventRecord(pool->fork, st) != cudaSuccess) return fail((int)cudaGetLastError(), "eigh_tridiag: cudaEventRecord failed");
+        int forked = 0;
+        for (int c = 0; c < nchunks && !rc; ++c) {
+            const int g0 = c * per, g1 = std::min(batch, g0 + per);
+            if (cudaStreamWaitEvent(pool->s[c], pool->fork, 0) != cudaSuccess) { rc = fail((int)cudaGetLastError(), "eigh_tridiag: cudaStreamWaitEvent failed"); break; }
+            forked = c + 1;
+#ifdef GSR_EIGH_TRACE
+            g_tr_chunk = c; tr_mark(1, pool->s[c]);
+#endif
+            rc = launch_k2(wk, n, g0, g1, pool->s[c], true, wk.chunk_done + c, g1 - g0);
+        }
+        if (!rc) {
+            GSR_TR(0);
+            tq::tridiag_kernel<<<batch, threads, 0, st>>>(A, w, U, info, wk, n, per);
+            rc = launched("eigh_tridiag");
+        }
+        for (int c = 0; c < nchunks && !rc; ++c) {
+            const int g0 = c * per, g1 = std::min(batch, g0 + per);
+#ifdef GSR_EIGH_TRACE
+            g_tr_chunk = c;
+#endif
+            rc = launch_small_apply(w, U, info, wk, g0, g1 - g0, n, canonical_sign, pool->s[c]);
+        }
+        // (on an error the streams forked so far are still joined, so that a capture is not left forked)
+        for (int c = 0; c < forked; ++c) { cudaEventRecord(pool->join[c], pool->s[c]); cudaStreamWaitEvent(st, pool->join[c], 0); }
+        if (rc) return rc;
+    }
     return g_eigh_redo ? eigh_jacobi_redo_failed(A, w, U, info, reinterpret_cast<float*>(wk.stream), 2LL * wk.cap, batch, n, canonical_sign, st) : 0;
 }
