@@ -38,6 +38,7 @@ namespace gsr {
 int g_eigh_ql_max_iter = 30;    // gsr_set_tuning("eigh_ql_max_iter", k): QL iterations allowed per eigenvalue (EISPACK: 30)
 int g_eigh_k2_lanes = 1;        // gsr_set_tuning("eigh_k2_lanes", 0|1): QL iteration with lane = graph (32 graphs per warp) for batches >= 32
                                 // (default), 0 = one warp per graph
+int g_eigh_k2_warps = 2;        // gsr_set_tuning("eigh_k2_warps", 1..4): warps (of 32 graphs) per CTA of the lane = graph QL kernel
 int g_eigh_chunks = 8;          // gsr_set_tuning("eigh_chunks", k): the n <= 160 decomposition of a batch of >= 256 graphs runs as up to k
                                 // chunks on internal streams (K2 of a chunk under K1 / K3 of the others); 0 or 1 = one launch per stage
 int g_eigh_redo = 1;            // gsr_set_tuning("eigh_redo_failed", 0|1): Jacobi pass over the graphs the QL iteration gave up on
@@ -419,7 +420,7 @@ tql_scalar_kernel(const Work wk, int n, int batch, int max_iter) {
 //     wrongly;
 //   * the shift h is subtracted from d[l+2 .. m] as the rotation loop reads them (same values), from d[m+1 ..] in a loop.
 // Stream / header format and all arithmetic of a rotation are those of tql_scalar_kernel.
-constexpr int K2L_WARPS = 2;            // warps per CTA, each on its own scheduler (4 made the kernel LSU bound: a lane-strided STG is 32 sector requests)
+constexpr int K2L_WARPS = 4;            // at most one warp per scheduler; the launcher picks g_eigh_k2_warps <= 4 (they share the SM's LSU)
 __global__ void __launch_bounds__(32 * K2L_WARPS)
 tql_scalar_lanes_kernel(const Work wk, int n, int g_first, int batch, int max_iter, const int* wait_count, int wait_target) {
     extern __shared__ __align__(16) float sm_all[];
@@ -507,19 +508,24 @@ tql_scalar_lanes_kernel(const Work wk, int n, int g_first, int batch, int max_it
         d[32 * l] = dl; d[32 * (l + 1)] = dl1;
         for (int q = max(m + 1, l + 2); q < n; ++q) d[32 * q] -= h;          // below a split (rare); d[l+2 .. m] get it on the fly
         f += h;
-        float2* o = out + pos;
+        // The entries of an iteration (identities for the rotation indices hi-1 .. m, the rotations m-1 .. l, identities for
+        // l-1 .. lo) go out as 16-byte PAIRS: position P of an entry inside the iteration is hi - 1 - (rotation index), the
+        // iteration starts at a multiple of 16 entries, so (even P, odd P) is one aligned float4.  A lane-strided store costs
+        // the LSU one sector request per lane whatever its width; pairs halve what was 32 requests per rotation and warp.
+        float4* o4 = reinterpret_cast<float4*>(out + pos);                   // pair k = positions 2k, 2k + 1
         hdr[nit] = (uint32_t)(lo >> 4) | ((uint32_t)(hi >> 4) << 8);
-        for (int k = 0; k < hi - m; ++k) o[k] = ident;                       // rotation indices hi-1 .. m
-        o += hi - m;
+        const float4 ident2 = make_float4(1.0f, 0.0f, 1.0f, 0.0f);
+        for (int k = 0; k < (hi - m) >> 1; ++k) o4[k] = ident2;              // whole pairs of leading identities
+        int P = hi - m;                                                      // position of the next rotation
         float p = d[32 * m] - (m >= l + 2 ? h : 0.f), c = 1.0f, s = 0.0f;
         float s_prev = 0.0f, c_prev = 1.0f, c_prev2 = 1.0f;
         const float el1 = e[32 * (l + 1)];
         float ei = e[32 * (m - 1)], di = d[32 * (m - 1)] - (m - 1 >= l + 2 ? h : 0.f);
         int mneg = m;                                                        // e[m] becomes s r = 0
-#pragma unroll 2
-        for (int q = m - 1; q >= l; --q) {
+        const int lsub = l + 3;                                              // rotation q reads d[q - 1]: shifted iff q >= l + 3
+        auto rotate = [&](int q) {                                           // rotation index q: updates (c, s), p, d / e[q + 1]
             const float ein = e[32 * (q - 1)];                               // next rotation's operands (index -1 is padding)
-            const float din = d[32 * (q - 1)] - (q - 1 >= l + 2 ? h : 0.f);
+            const float din = d[32 * (q - 1)] - (q >= lsub ? h : 0.f);
             const float gg = c * ei, hh = c * p;
             const float x = fmaf(p, p, ei * ei);
             float rinv;
@@ -528,7 +534,7 @@ tql_scalar_lanes_kernel(const Work wk, int n, int g_first, int batch, int max_it
             const float c0 = p * rinv, s0 = ei * rinv, xr = x * rinv;
             const float t = fmaf(c0, di, -s0 * gg);
             float cn = fmaf(c0, hd, c0), sn = fmaf(s0, hd, s0), r = fmaf(xr, hd, xr), pn = fmaf(t, hd, t);
-            if (x < 1.17549435e-38f) { r = 0.f; cn = 1.0f; sn = 0.0f; pn = di; }
+            if (__builtin_expect(x < 1.17549435e-38f, 0)) { r = 0.f; cn = 1.0f; sn = 0.0f; pn = di; }
             const float enew = s * r;
             e[32 * (q + 1)] = enew;
             if (negl(enew)) mneg = q + 1;                                    // q descends: the last hit is the smallest index
@@ -536,13 +542,30 @@ tql_scalar_lanes_kernel(const Work wk, int n, int g_first, int batch, int max_it
             s = sn; c = cn;
             p = pn;
             d[32 * (q + 1)] = hh + s * fmaf(c, gg, s * di);
-            *o++ = make_float2(c, s);
             ei = ein; di = din;
+        };
+        int q = m - 1;
+        if (P & 1) {                                                         // an odd first position pairs with the identity before it
+            rotate(q);
+            o4[P >> 1] = make_float4(1.0f, 0.0f, c, s);
+            ++P; --q;
+        }
+        for (; q > l; q -= 2) {                                              // two rotations, one 16-byte store
+            rotate(q);
+            const float ca = c, sa = s;
+            rotate(q - 1);
+            o4[P >> 1] = make_float4(ca, sa, c, s);
+            P += 2;
+        }
+        if (q == l) {                                                        // a last rotation at an even position pairs with the first
+            rotate(q);                                                       // trailing identity (l is odd then, so l > lo)
+            o4[P >> 1] = make_float4(c, s, 1.0f, 0.0f);
+            P += 2;
         }
         p = -s * s_prev * c_prev2 * el1 * e[32 * l] / dl1;
         e[32 * l] = s * p;
         d[32 * l] = c * p;
-        for (int k = 0; k < l - lo; ++k) o[k] = ident;                       // rotation indices l-1 .. lo
+        for (int k = P >> 1; k < (hi - lo) >> 1; ++k) o4[k] = ident2;        // whole pairs of trailing identities
         pos += hi - lo;
         ++nit;
         if (tst1 + fabsf(e[32 * l]) <= tst1) {                               // eigenvalue l converged
@@ -1146,7 +1169,7 @@ static int launch_k2(const gsr::tq::Work& wk, int n, int g_first, int g_end, cud
     const int count = g_end - g_first;
     if (g_eigh_k2_lanes && (count >= 32 || wait_count)) {
         const size_t per_warp = (size_t)2 * (n + 16) * 32 * sizeof(float);
-        const int wpc = (int)std::max<size_t>(1, std::min<size_t>(tq::K2L_WARPS, kMaxDynSmem / per_warp));
+        const int wpc = (int)std::max<size_t>(1, std::min<size_t>(std::min(tq::K2L_WARPS, std::max(1, g_eigh_k2_warps)), kMaxDynSmem / per_warp));
         const size_t smem = hog ? (size_t)kMaxDynSmem : per_warp * wpc;
         cudaError_t e = cudaFuncSetAttribute(tq::tql_scalar_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
         if (e != cudaSuccess) return fail((int)e, "eigh_tridiag: cudaFuncSetAttribute failed");

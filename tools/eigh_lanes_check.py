@@ -51,9 +51,9 @@ gen = torch.Generator(device="cuda").manual_seed(0)
 x = torch.rand(1024, 160, 160, device="cuda", generator=gen); lr = (x + x.transpose(1, 2)) / 2; lr.diagonal(dim1=1, dim2=2).zero_()
 A = pkg.normalize_adj_torch(lr)
 ref = None
-for lanes, chunks in ((0, 1), (1, 1), (1, 8)):
-    pkg.set_tuning("eigh_k2_lanes", lanes); pkg.set_tuning("eigh_chunks", chunks)
-    (w, U, info), ms = timed(K.eigh_tridiag, A, reps=5); report(f"tridiag 1024x160 k2_lanes={lanes} chunks={chunks}", A, w, U, info, ms)
+for lanes, chunks, warps in ((0, 1, 2), (1, 1, 1), (1, 1, 2), (1, 1, 4), (1, 8, 1), (1, 8, 4), (1, 8, 2)):
+    pkg.set_tuning("eigh_k2_lanes", lanes); pkg.set_tuning("eigh_chunks", chunks); pkg.set_tuning("eigh_k2_warps", warps)
+    (w, U, info), ms = timed(K.eigh_tridiag, A, reps=5); report(f"tridiag 1024x160 k2_lanes={lanes} chunks={chunks} k2_warps={warps}", A, w, U, info, ms)
     if lanes == 1:
         if ref is None: ref = (w, U)
         else: print(json.dumps({"chunks": chunks, "bit_identical_to_unchunked": bool(torch.equal(w, ref[0]) and torch.equal(U, ref[1]))}), flush=True)
