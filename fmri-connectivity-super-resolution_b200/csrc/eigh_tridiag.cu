@@ -32,6 +32,8 @@
 // Accuracy (fp32, measured on B200 against a float64 decomposition of normalised 160-node
 // connectomes): eigenvalues 1e-6, eigenvectors (median) 4e-5, ||U^T U - I||_max 2e-6 -- the
 // class of LAPACK ssyevd and of the Jacobi kernel after its polish phase.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gsr {
@@ -1322,6 +1324,11 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
     // (no empty SM at the fork) it simply starts late.  Forks from / joins the caller's stream through events: capturable.
     const int per = std::max(128, (((batch + kMaxChunks - 1) / kMaxChunks) + 127) & ~127);       // graphs per chunk
     int nchunks = (g_eigh_chunks > 1 && g_eigh_k2_lanes && batch >= 256) ? (batch + per - 1) / per : 1;
+    // the resident K2 CTAs need K1 to run NEXT to them: not when every launch blocks the host until its kernel has finished.
+    // (Profilers that serialise kernels -- ncu, compute-sanitizer -- need gsr_set_tuning("eigh_chunks", 1) for the same reason;
+    // a K2 CTA that never sees its count traps after ~4 s instead of hanging the GPU.)
+    static const bool launch_blocking = [] { const char* v = getenv("CUDA_LAUNCH_BLOCKING"); return v && atoi(v) != 0; }();
+    if (launch_blocking) nchunks = 1;
     ChunkPool* pool = nchunks > 1 ? chunk_pool() : nullptr;
     if (!pool || nchunks > std::min(g_eigh_chunks, kMaxChunks)) nchunks = 1;
 #ifdef GSR_EIGH_TRACE

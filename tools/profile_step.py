@@ -8,6 +8,8 @@ import torch
 import bench
 
 pkg = importlib.import_module(bench.PKG_NAME)
+for kv in os.environ.get("GSR_TUNE", "").split(","):           # e.g. GSR_TUNE=eigh_chunks=1 under ncu (serialised kernels)
+    if kv: pkg.set_tuning(kv.split("=")[0], int(kv.split("=")[1]))
 B = int(os.environ.get("GSR_B", "1024"))
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
