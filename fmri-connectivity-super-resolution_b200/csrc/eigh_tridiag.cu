@@ -1361,6 +1361,9 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
             rc = launch_k2(wk, n, g0, g1, pool->s[c], true, wk.chunk_done + c, g1 - g0);
         }
         if (!rc) {
+#ifdef GSR_EIGH_TRACE
+            g_tr_chunk = 0;
+#endif
             GSR_TR(0);
             tq::tridiag_kernel<<<batch, threads, 0, st>>>(A, w, U, info, wk, n, per);
             rc = launched("eigh_tridiag");
