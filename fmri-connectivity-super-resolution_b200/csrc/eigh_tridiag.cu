@@ -431,6 +431,7 @@ tql_scalar_lanes_kernel(const Work wk, int n, int g_first, int batch, int max_it
     // K1 has finished; K1 publishes with __threadfence + atomicAdd, the acquire load + barrier order every thread's reads.
     if (wait_count) {
         if (threadIdx.x == 0) {
+            atomicAdd(wk.chunk_done + 32, 1);                    // resident: the gate in front of K1 counts these
             for (unsigned spin = 0;; ++spin) {
                 int v;
                 asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(wait_count) : "memory");
@@ -589,6 +590,19 @@ tql_scalar_lanes_kernel(const Work wk, int n, int g_first, int batch, int max_it
             for (int j = lane; j < n; j += 32) wk.d[(size_t)gi * n + j] = sm[(8 + j) * 32 + gg];
     }
     if (live) { int* cnt = wk.counts + 4 * g; cnt[0] = nit; cnt[1] = pos; cnt[2] = status; }
+}
+
+// Gate in front of K1 (chunked pipeline): one thread waits -- for at most ~60 us -- until the K2 CTAs have checked in as
+// resident.  They are launched first, but on other streams: without the gate K1's 1024 CTAs can reach the SMs a few
+// microseconds before the last K2 launch and then that chunk's K2 CTAs (each needs an empty SM) are placed only when K1
+// drains (measured: 3.9 -> 5.5 ms).  The wait is bounded: if the SMs are busy with something else K1 simply starts.
+__global__ void k2_resident_gate_kernel(const int* resident, int expected) {
+    for (int spin = 0; spin < 600; ++spin) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(resident) : "memory");
+        if (v >= expected) break;
+        __nanosleep(100);
+    }
 }
 
 // ------------------------------------------------------------------------------------ K3
@@ -1166,7 +1180,7 @@ using namespace gsr;
 // K2 for graphs [g_first, g_end): lane = graph for batches that fill warps, one warp per graph otherwise.  `hog`: ask for all of an
 // SM's shared memory so that the CTA runs alone on it (chunked pipeline); wait_count / wait_target: see the kernel.
 static int launch_k2(const gsr::tq::Work& wk, int n, int g_first, int g_end, cudaStream_t st, bool hog = false,
-                     const int* wait_count = nullptr, int wait_target = 0) {
+                     const int* wait_count = nullptr, int wait_target = 0, int* ctas_launched = nullptr) {
     using namespace gsr;
     const int count = g_end - g_first;
     if (g_eigh_k2_lanes && (count >= 32 || wait_count)) {
@@ -1175,8 +1189,9 @@ static int launch_k2(const gsr::tq::Work& wk, int n, int g_first, int g_end, cud
         const size_t smem = hog ? (size_t)kMaxDynSmem : per_warp * wpc;
         cudaError_t e = cudaFuncSetAttribute(tq::tql_scalar_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
         if (e != cudaSuccess) return fail((int)e, "eigh_tridiag: cudaFuncSetAttribute failed");
-        tq::tql_scalar_lanes_kernel<<<(count + 32 * wpc - 1) / (32 * wpc), 32 * wpc, smem, st>>>(wk, n, g_first, g_end, g_eigh_ql_max_iter,
-                                                                                              wait_count, wait_target);
+        const int ctas = (count + 32 * wpc - 1) / (32 * wpc);
+        if (ctas_launched) *ctas_launched += ctas;
+        tq::tql_scalar_lanes_kernel<<<ctas, 32 * wpc, smem, st>>>(wk, n, g_first, g_end, g_eigh_ql_max_iter, wait_count, wait_target);
         return launched("eigh_tql_scalar_lanes");
     }
     tq::Work w1 = wk;                                        // the one-warp kernel indexes from 0
@@ -1216,7 +1231,7 @@ ChunkPool* chunk_pool() {
     // of them can wait for another.
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, gsr::tq::tridiag_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tql_scalar_lanes_kernel) != cudaSuccess ||
-        cudaFuncGetAttributes(&fa, gsr::tq::tql_apply_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tql_finish_kernel) != cudaSuccess) {
+        cudaFuncGetAttributes(&fa, gsr::tq::k2_resident_gate_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tql_apply_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tql_finish_kernel) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
@@ -1350,7 +1365,7 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
     } else {
         if (cudaMemsetAsync(wk.chunk_done, 0, 64 * sizeof(int), st) != cudaSuccess) return fail((int)cudaGetLastError(), "eigh_tridiag: cudaMemsetAsync failed");
         if (cudaEventRecord(pool->fork, st) != cudaSuccess) return fail((int)cudaGetLastError(), "eigh_tridiag: cudaEventRecord failed");
-        int forked = 0;
+        int forked = 0, k2_ctas = 0;
         for (int c = 0; c < nchunks && !rc; ++c) {
             const int g0 = c * per, g1 = std::min(batch, g0 + per);
             if (cudaStreamWaitEvent(pool->s[c], pool->fork, 0) != cudaSuccess) { rc = fail((int)cudaGetLastError(), "eigh_tridiag: cudaStreamWaitEvent failed"); break; }
@@ -1358,7 +1373,11 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
 #ifdef GSR_EIGH_TRACE
             g_tr_chunk = c; tr_mark(1, pool->s[c]);
 #endif
-            rc = launch_k2(wk, n, g0, g1, pool->s[c], true, wk.chunk_done + c, g1 - g0);
+            rc = launch_k2(wk, n, g0, g1, pool->s[c], true, wk.chunk_done + c, g1 - g0, &k2_ctas);
+        }
+        if (!rc) {
+            tq::k2_resident_gate_kernel<<<1, 1, 0, st>>>(wk.chunk_done + 32, k2_ctas);
+            rc = launched("eigh_k2_gate");
         }
         if (!rc) {
 #ifdef GSR_EIGH_TRACE
