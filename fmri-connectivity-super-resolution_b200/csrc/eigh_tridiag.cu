@@ -107,6 +107,21 @@ static size_t carve(Work* wk, void* base, int batch, int n) {
     return off;
 }
 
+
+// the workspace views of graphs [g0, ...): every per-graph array advanced, the chunk counters shared
+static Work offset_work(const Work& full, int g0, int n) {
+    Work wk = full;
+    wk.stream += (size_t)g0 * full.cap;
+    wk.V += (size_t)g0 * n * ldv_of(n);
+    wk.Zt += (size_t)g0 * n * n;
+    wk.d += (size_t)g0 * n;
+    wk.e += (size_t)g0 * n;
+    wk.scale += g0;
+    wk.counts += 4 * (size_t)g0;
+    wk.hdr += (size_t)g0 * full.hdr_cap;
+    return wk;
+}
+
 // ------------------------------------------------------------------------------------ K1
 __global__ void __launch_bounds__(MAXN, 2)
 tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* __restrict__ Uout,
@@ -1180,10 +1195,12 @@ using namespace gsr;
 // K2 for graphs [g_first, g_end): lane = graph for batches that fill warps, one warp per graph otherwise.  `hog`: ask for all of an
 // SM's shared memory so that the CTA runs alone on it (chunked pipeline); wait_count / wait_target: see the kernel.
 static int launch_k2(const gsr::tq::Work& wk, int n, int g_first, int g_end, cudaStream_t st, bool hog = false,
-                     const int* wait_count = nullptr, int wait_target = 0, int* ctas_launched = nullptr) {
+                     const int* wait_count = nullptr, int wait_target = 0, int* ctas_launched = nullptr, bool lanes_unchunked = true) {
     using namespace gsr;
     const int count = g_end - g_first;
-    if (g_eigh_k2_lanes && (count >= 32 || wait_count)) {
+    // lane = graph: always inside the chunked pipeline (wait_count); for one launch per stage it is never faster than one warp
+    // per graph at n <= 160 (tools/eigh_batch_sweep.py), so the segment launcher asks for it only under eigh_k2_lanes >= 2
+    if (g_eigh_k2_lanes && (wait_count || (lanes_unchunked && count >= 32))) {
         const size_t per_warp = (size_t)2 * (n + 16) * 32 * sizeof(float);
         const int wpc = (int)std::max<size_t>(1, std::min<size_t>(std::min(tq::K2L_WARPS, std::max(1, g_eigh_k2_warps)), kMaxDynSmem / per_warp));
         const size_t smem = hog ? (size_t)kMaxDynSmem : per_warp * wpc;
@@ -1262,15 +1279,7 @@ extern "C" __attribute__((visibility("default"))) int gsr_eigh_timeline_read(flo
 static int launch_small_apply(float* w, float* U, int32_t* info, const gsr::tq::Work& full, int g0, int nb, int n,
                               int canonical_sign, cudaStream_t st) {
     using namespace gsr;
-    tq::Work wk = full;
-    wk.stream += (size_t)g0 * full.cap;
-    wk.V += (size_t)g0 * n * tq::ldv_of(n);
-    wk.Zt += (size_t)g0 * n * n;
-    wk.d += (size_t)g0 * n;
-    wk.e += (size_t)g0 * n;
-    wk.scale += g0;
-    wk.counts += 4 * (size_t)g0;
-    wk.hdr += (size_t)g0 * full.hdr_cap;
+    const tq::Work wk = tq::offset_work(full, g0, n);
     U += (size_t)g0 * n * n; w += (size_t)g0 * n; info += g0;
     const int threads = 32 * ((n + 31) / 32);
     const int units_per_graph = threads / 32, total_units = units_per_graph * nb;
@@ -1287,6 +1296,83 @@ static int launch_small_apply(float* w, float* U, int32_t* info, const gsr::tq::
     rc = launched("eigh_tql_finish");
     GSR_TR(4);
     return rc;
+}
+
+// One segment (<= 1024 graphs) of the n <= 160 route; A, w, U, info and wk point at the segment's first graph.
+static int eigh_small_segment(const float* A, float* w, float* U, int32_t* info, const gsr::tq::Work& wk, int batch, int n,
+                              int canonical_sign, cudaStream_t st) {
+    using namespace gsr;
+    const int threads = 32 * ((n + 31) / 32);
+    int rc = 0;
+    // Chunked pipeline (384 graphs or more; measured, `tools/eigh_batch_sweep.py`: one launch per stage with the one-warp QL kernel is faster below:
+    // 2.25 against 2.62 ms for 256 graphs, 2.69 against 2.66 for 384, 5.09 against 3.92 for 1024): K1 is ONE launch on the caller's stream (its CTAs run in graph order and count the
+    // finished graphs of each chunk); every chunk has a stream with K2 -> K3 -> K4.  The K2 CTAs are launched FIRST: each asks
+    // for a whole SM, becomes resident at the fork and polls its chunk's count, so the ~1.3 ms rotation chain of a chunk runs
+    // on its own SM (one warp per scheduler, nothing else to share issue slots with) under the K1 / K3 of the other chunks,
+    // which have the remaining SMs.  K1 never waits for anything, so the polling cannot deadlock; if a K2 CTA is placed late
+    // (no empty SM at the fork) it simply starts late.  Forks from / joins the caller's stream through events: capturable.
+    const int per = std::max(128, (((batch + kMaxChunks - 1) / kMaxChunks) + 127) & ~127);       // graphs per chunk
+    int nchunks = (g_eigh_chunks > 1 && g_eigh_k2_lanes && batch >= 384) ? (batch + per - 1) / per : 1;
+    // the resident K2 CTAs need K1 to run NEXT to them: not when every launch blocks the host until its kernel has finished.
+    // (Profilers that serialise kernels -- ncu, compute-sanitizer -- need gsr_set_tuning("eigh_chunks", 1) for the same reason;
+    // a K2 CTA that never sees its count traps after ~4 s instead of hanging the GPU.)
+    static const bool launch_blocking = [] { const char* v = getenv("CUDA_LAUNCH_BLOCKING"); return v && atoi(v) != 0; }();
+    if (launch_blocking) nchunks = 1;
+    ChunkPool* pool = nchunks > 1 ? chunk_pool() : nullptr;
+    if (!pool || nchunks > std::min(g_eigh_chunks, kMaxChunks)) nchunks = 1;
+#ifdef GSR_EIGH_TRACE
+    if (!g_tr_init) {
+        for (int c = 0; c < 8; ++c) for (int k = 0; k < 5; ++k) cudaEventCreate(&g_tr_ev[c][k]);
+        cudaEventCreate(&g_tr_fork);
+        g_tr_init = true;
+    }
+    cudaEventRecord(g_tr_fork, st);
+    g_tr_chunk = 0;
+#endif
+    if (nchunks == 1) {
+        GSR_TR(0);
+        tq::tridiag_kernel<<<batch, threads, 0, st>>>(A, w, U, info, wk, n, 0);
+        if ((rc = launched("eigh_tridiag"))) return rc;
+        GSR_TR(1);
+        if ((rc = launch_k2(wk, n, 0, batch, st, false, nullptr, 0, nullptr, g_eigh_k2_lanes >= 2))) return rc;      // one warp per graph unless forced
+        if ((rc = launch_small_apply(w, U, info, wk, 0, batch, n, canonical_sign, st))) return rc;
+    } else {
+        if (cudaMemsetAsync(wk.chunk_done, 0, 64 * sizeof(int), st) != cudaSuccess) return fail((int)cudaGetLastError(), "eigh_tridiag: cudaMemsetAsync failed");
+        if (cudaEventRecord(pool->fork, st) != cudaSuccess) return fail((int)cudaGetLastError(), "eigh_tridiag: cudaEventRecord failed");
+        int forked = 0, k2_ctas = 0;
+        for (int c = 0; c < nchunks && !rc; ++c) {
+            const int g0 = c * per, g1 = std::min(batch, g0 + per);
+            if (cudaStreamWaitEvent(pool->s[c], pool->fork, 0) != cudaSuccess) { rc = fail((int)cudaGetLastError(), "eigh_tridiag: cudaStreamWaitEvent failed"); break; }
+            forked = c + 1;
+#ifdef GSR_EIGH_TRACE
+            g_tr_chunk = c; tr_mark(1, pool->s[c]);
+#endif
+            rc = launch_k2(wk, n, g0, g1, pool->s[c], true, wk.chunk_done + c, g1 - g0, &k2_ctas);
+        }
+        if (!rc) {
+            tq::k2_resident_gate_kernel<<<1, 1, 0, st>>>(wk.chunk_done + 32, k2_ctas);
+            rc = launched("eigh_k2_gate");
+        }
+        if (!rc) {
+#ifdef GSR_EIGH_TRACE
+            g_tr_chunk = 0;
+#endif
+            GSR_TR(0);
+            tq::tridiag_kernel<<<batch, threads, 0, st>>>(A, w, U, info, wk, n, per);
+            rc = launched("eigh_tridiag");
+        }
+        for (int c = 0; c < nchunks && !rc; ++c) {
+            const int g0 = c * per, g1 = std::min(batch, g0 + per);
+#ifdef GSR_EIGH_TRACE
+            g_tr_chunk = c;
+#endif
+            rc = launch_small_apply(w, U, info, wk, g0, g1 - g0, n, canonical_sign, pool->s[c]);
+        }
+        // (on an error the streams forked so far are still joined, so that a capture is not left forked)
+        for (int c = 0; c < forked; ++c) { cudaEventRecord(pool->join[c], pool->s[c]); cudaStreamWaitEvent(st, pool->join[c], 0); }
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 extern "C" size_t gsr_eigh_tridiag_workspace(int batch, int n) {
@@ -1330,72 +1416,13 @@ extern "C" int gsr_eigh_tridiag_f32(const float* A, float* w, float* U, int32_t*
         return g_eigh_redo ? eigh_jacobi_redo_failed(A, w, U, info, reinterpret_cast<float*>(wk.stream), 2LL * wk.cap, batch, n, canonical_sign, st) : 0;
     }
 
-    int rc = 0;
-    // Chunked pipeline (batch >= 256): K1 is ONE launch on the caller's stream (its CTAs run in graph order and count the
-    // finished graphs of each chunk); every chunk has a stream with K2 -> K3 -> K4.  The K2 CTAs are launched FIRST: each asks
-    // for a whole SM, becomes resident at the fork and polls its chunk's count, so the ~1.3 ms rotation chain of a chunk runs
-    // on its own SM (one warp per scheduler, nothing else to share issue slots with) under the K1 / K3 of the other chunks,
-    // which have the remaining SMs.  K1 never waits for anything, so the polling cannot deadlock; if a K2 CTA is placed late
-    // (no empty SM at the fork) it simply starts late.  Forks from / joins the caller's stream through events: capturable.
-    const int per = std::max(128, (((batch + kMaxChunks - 1) / kMaxChunks) + 127) & ~127);       // graphs per chunk
-    int nchunks = (g_eigh_chunks > 1 && g_eigh_k2_lanes && batch >= 256) ? (batch + per - 1) / per : 1;
-    // the resident K2 CTAs need K1 to run NEXT to them: not when every launch blocks the host until its kernel has finished.
-    // (Profilers that serialise kernels -- ncu, compute-sanitizer -- need gsr_set_tuning("eigh_chunks", 1) for the same reason;
-    // a K2 CTA that never sees its count traps after ~4 s instead of hanging the GPU.)
-    static const bool launch_blocking = [] { const char* v = getenv("CUDA_LAUNCH_BLOCKING"); return v && atoi(v) != 0; }();
-    if (launch_blocking) nchunks = 1;
-    ChunkPool* pool = nchunks > 1 ? chunk_pool() : nullptr;
-    if (!pool || nchunks > std::min(g_eigh_chunks, kMaxChunks)) nchunks = 1;
-#ifdef GSR_EIGH_TRACE
-    if (!g_tr_init) {
-        for (int c = 0; c < 8; ++c) for (int k = 0; k < 5; ++k) cudaEventCreate(&g_tr_ev[c][k]);
-        cudaEventCreate(&g_tr_fork);
-        g_tr_init = true;
-    }
-    cudaEventRecord(g_tr_fork, st);
-    g_tr_chunk = 0;
-#endif
-    if (nchunks == 1) {
-        GSR_TR(0);
-        tq::tridiag_kernel<<<batch, threads, 0, st>>>(A, w, U, info, wk, n, 0);
-        if ((rc = launched("eigh_tridiag"))) return rc;
-        GSR_TR(1);
-        if ((rc = launch_k2(wk, n, 0, batch, st))) return rc;
-        if ((rc = launch_small_apply(w, U, info, wk, 0, batch, n, canonical_sign, st))) return rc;
-    } else {
-        if (cudaMemsetAsync(wk.chunk_done, 0, 64 * sizeof(int), st) != cudaSuccess) return fail((int)cudaGetLastError(), "eigh_tridiag: cudaMemsetAsync failed");
-        if (cudaEventRecord(pool->fork, st) != cudaSuccess) return fail((int)cudaGetLastError(), "eigh_tridiag: cudaEventRecord failed");
-        int forked = 0, k2_ctas = 0;
-        for (int c = 0; c < nchunks && !rc; ++c) {
-            const int g0 = c * per, g1 = std::min(batch, g0 + per);
-            if (cudaStreamWaitEvent(pool->s[c], pool->fork, 0) != cudaSuccess) { rc = fail((int)cudaGetLastError(), "eigh_tridiag: cudaStreamWaitEvent failed"); break; }
-            forked = c + 1;
-#ifdef GSR_EIGH_TRACE
-            g_tr_chunk = c; tr_mark(1, pool->s[c]);
-#endif
-            rc = launch_k2(wk, n, g0, g1, pool->s[c], true, wk.chunk_done + c, g1 - g0, &k2_ctas);
-        }
-        if (!rc) {
-            tq::k2_resident_gate_kernel<<<1, 1, 0, st>>>(wk.chunk_done + 32, k2_ctas);
-            rc = launched("eigh_k2_gate");
-        }
-        if (!rc) {
-#ifdef GSR_EIGH_TRACE
-            g_tr_chunk = 0;
-#endif
-            GSR_TR(0);
-            tq::tridiag_kernel<<<batch, threads, 0, st>>>(A, w, U, info, wk, n, per);
-            rc = launched("eigh_tridiag");
-        }
-        for (int c = 0; c < nchunks && !rc; ++c) {
-            const int g0 = c * per, g1 = std::min(batch, g0 + per);
-#ifdef GSR_EIGH_TRACE
-            g_tr_chunk = c;
-#endif
-            rc = launch_small_apply(w, U, info, wk, g0, g1 - g0, n, canonical_sign, pool->s[c]);
-        }
-        // (on an error the streams forked so far are still joined, so that a capture is not left forked)
-        for (int c = 0; c < forked; ++c) { cudaEventRecord(pool->join[c], pool->s[c]); cudaStreamWaitEvent(st, pool->join[c], 0); }
+    // segments of at most 1024 graphs, one after the other (a pipeline over more graphs would give more than 16 SMs to the QL
+    // chains: 2048 graphs in one pipeline 8.7 ms, in two 7.8)
+    const int nseg = (batch + 1023) / 1024, seg = (((batch + nseg - 1) / nseg) + 127) & ~127;
+    for (int g0 = 0; g0 < batch; g0 += seg) {
+        const int nb = std::min(seg, batch - g0);
+        const int rc = eigh_small_segment(A + (size_t)g0 * n * n, w + (size_t)g0 * n, U + (size_t)g0 * n * n, info + g0,
+                                          tq::offset_work(wk, g0, n), nb, n, canonical_sign, st);
         if (rc) return rc;
     }
     return g_eigh_redo ? eigh_jacobi_redo_failed(A, w, U, info, reinterpret_cast<float*>(wk.stream), 2LL * wk.cap, batch, n, canonical_sign, st) : 0;
