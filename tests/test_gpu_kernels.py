@@ -329,6 +329,56 @@ def test_eigh_ql_failure_falls_back_to_jacobi(cuda_pkg):
 
 
 @pytest.mark.gpu
+def test_eigh_pipeline_matches_one_launch_per_stage(cuda_pkg):
+    """The chunked eigensolver pipeline (batches of 384 graphs or more: ONE K1 launch counting finished graphs per
+    128-graph chunk, the lane = graph QL kernel resident on its own SMs polling those counts, K3 / K4 per chunk on
+    internal streams; csrc/eigh_tridiag.cu) against (a) the same kernels run one launch per stage -- bit identical --
+    (b) the one-warp-per-graph QL kernel -- eigenvalues 3e-6 -- and (c) float64 LAPACK on sampled graphs; a ragged
+    batch (400 = 3 chunks + 16 graphs) with a NaN graph, a zero matrix, a multiple of the identity and a rank-one
+    matrix in different chunks; twice in a row (the per-chunk counters are reset by every call); 1100 graphs = two
+    segments; QL failures inside the pipeline are redone by the Jacobi kernel."""
+    K = cuda_pkg.kernels
+    g = torch.Generator().manual_seed(11)
+    B = 400
+    x = torch.rand(B, 160, 160, generator=g)
+    A = torch.stack([O.normalize_adj((m + m.T) / 2) for m in x])
+    A[5, 3, 9] = float("nan")
+    A[140] = 0.0
+    A[270] = 2.5 * torch.eye(160)
+    A[399] = torch.ones(160, 160) / 160
+    A = A.cuda()
+    try:
+        cuda_pkg.set_tuning("eigh_chunks", 8); cuda_pkg.set_tuning("eigh_k2_lanes", 1)
+        w_p, U_p, i_p = K.eigh_tridiag(A)
+        w_p2, U_p2, i_p2 = K.eigh_tridiag(A)
+        cuda_pkg.set_tuning("eigh_chunks", 1); cuda_pkg.set_tuning("eigh_k2_lanes", 2)       # lane = graph, one launch per stage
+        w_l, U_l, i_l = K.eigh_tridiag(A)
+        cuda_pkg.set_tuning("eigh_k2_lanes", 0)                                              # one warp per graph
+        w_w, U_w, i_w = K.eigh_tridiag(A)
+    finally:
+        cuda_pkg.set_tuning("eigh_chunks", 8); cuda_pkg.set_tuning("eigh_k2_lanes", 1)
+    ok = torch.ones(B, dtype=torch.bool); ok[5] = False
+    assert int(i_p[5]) == -1 and bool(torch.isnan(w_p[5]).all()) and bool(torch.isnan(U_p[5]).all())
+    assert int(i_p[ok].min()) > 0
+    assert torch.equal(w_p[ok], w_p2[ok]) and torch.equal(U_p[ok], U_p2[ok]) and torch.equal(i_p, i_p2)
+    assert torch.equal(w_p[ok], w_l[ok]) and torch.equal(U_p[ok], U_l[ok]) and torch.equal(i_p, i_l)
+    assert float((w_p[ok] - w_w[ok]).abs().max()) < 3e-6
+    assert float(w_p[140].abs().max()) == 0.0 and float((w_p[270] - 2.5).abs().max()) < 1e-6
+    assert abs(float(w_p[399].max()) - 1.0) < 2e-6 and float(w_p[399][:-1].abs().max()) < 2e-6
+    for b in (0, 127, 128, 255, 256, 383, 384, 398):
+        _eigh_checks(A[b].cpu(), w_p[b].cpu(), U_p[b].cpu())
+    # two segments (1100 > 1024 graphs), QL failures redone inside the pipeline
+    A2 = A[ok][:399].repeat(3, 1, 1)[:1100].contiguous()
+    w2, U2, i2 = K.eigh_tridiag(A2)
+    assert int(i2.min()) > 0 and torch.equal(w2[:399], w_p[ok][:399]) and torch.equal(w2[399:798], w2[:399]) and torch.equal(U2[798:1100], U2[:302])
+    cuda_pkg.set_tuning("eigh_ql_max_iter", 1)
+    try:
+        w3, U3, i3 = K.eigh_tridiag(A2[:384])
+    finally:
+        cuda_pkg.set_tuning("eigh_ql_max_iter", 30)
+    assert int(i3.min()) > 0 and float((w3 - w2[:384]).abs().max()) < 3e-6
+
+
 def test_eigh_tridiag_special_matrices(cuda_pkg):
     """Zero, identity multiples, rank one, repeated eigenvalues, tiny and huge scales (the kernel
     rescales by an exact power of two), diagonal input, and the NaN contract."""
