@@ -43,6 +43,8 @@ int g_eigh_k2_lanes = 1;        // gsr_set_tuning("eigh_k2_lanes", 0|1): QL iter
 int g_eigh_k2_warps = 2;        // gsr_set_tuning("eigh_k2_warps", 1..4): warps (of 32 graphs) per CTA of the lane = graph QL kernel
 int g_eigh_chunks = 8;          // gsr_set_tuning("eigh_chunks", k): the n <= 160 decomposition of a batch of >= 256 graphs runs as up to k
                                 // chunks on internal streams (K2 of a chunk under K1 / K3 of the others); 0 or 1 = one launch per stage
+int g_eigh_k1_regblocks = 8;   // gsr_set_tuning("eigh_k1_regblocks", 8|9|10): 16-column blocks of a row that K1 keeps in registers (the rest in
+                                // shared memory); 10 = the whole row, which leaves ptxas 8 registers for everything else (round 2, first sessions)
 int g_eigh_redo = 1;            // gsr_set_tuning("eigh_redo_failed", 0|1): Jacobi pass over the graphs the QL iteration gave up on
                                 // (info == -2), in the same stream (default); 0 leaves them flagged with NaN results
 namespace tq {
@@ -123,12 +125,25 @@ static Work offset_work(const Work& full, int g0, int n) {
 }
 
 // ------------------------------------------------------------------------------------ K1
+// Registers: 5 warps per CTA and 2 CTAs per SM put 3 warps on one of the four schedulers, whose 16 K registers then
+// allow 168 per thread.  With all 160 columns of the row in registers that leaves ~8 for everything else: ptxas spilled
+// and -- what cost the time -- kept ONE broadcast LDS.128 in flight in the mat-vec and the rank-2 update (120 loads of
+// ~33 clk per step one after the other: ~5000 clk per Householder step, FMA pipe 14 %).  RB = 16-column blocks of the
+// row kept in registers; the blocks above them (columns 16 RB .. 159) live in shared memory as tail[column][thread]
+// (bank = lane) and are only touched while k > 16 RB, i.e. during the first 160 - 16 RB steps.  The freed registers
+// hold the broadcast operands of a whole block, loaded before the block's FMAs.  Same arithmetic in the same order:
+// the variants are bit identical (tools/eigh_k1_ab.py).  Measured, 1024 graphs, one launch per stage: the decomposition
+// 5.04 ms (RB = 10) -> 4.83 (9) -> 4.63 (8, four LDS.128 in flight: the default); as the chunked pipeline 3.89 -> 3.78.
+template <int RB>
 __global__ void __launch_bounds__(MAXN, 2)
 tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* __restrict__ Uout,
                int32_t* __restrict__ info, const Work wk, int n, int chunk_graphs) {
+    constexpr int RC = 16 * RB;                              // columns in registers
+    constexpr int TC = MAXN - RC;                            // columns in shared memory
     __shared__ __align__(16) float tile[5 * 176];            // xbuf[2][176], vbuf, wbuf, pbuf
     __shared__ __align__(16) float red[8];
     __shared__ float dd[MAXN], ee[MAXN];
+    __shared__ float tail[(TC > 0 ? TC : 1) * MAXN];         // [column - RC][thread]
     float* xbuf = tile;                    // [2][176]  published pivot row (double buffered by step parity)
     float* vbuf = tile + 2 * 176;          // [176]
     float* wbuf = vbuf + 176;              // [176]
@@ -137,22 +152,32 @@ tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* _
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nwarps = nthr >> 5;
     const int g = blockIdx.x;
     const float* Ag = Ain + (size_t)g * n * n;
+    float* mytail = tail + tid;            // column c of this thread's row: mytail[(c - RC) * MAXN]
 
     // ---- load: thread i gets row i of the symmetric matrix = mirror of the upper triangle:
     //      A[i][j] for j >= i (row segment), A[j][i] for j < i (coalesced over the warp)
-    float a[MAXN];
+    float a[RC];
     int bad = 0;
     float amax = 0.f;
 #pragma unroll
-    for (int j = 0; j < MAXN; ++j) {
+    for (int j = 0; j < RC; ++j) {
         float v = 0.f;
         if (tid < n && j < n) v = __ldg(Ag + (j >= tid ? (size_t)tid * n + j : (size_t)j * n + tid));
         a[j] = v;
     }
 #pragma unroll
-    for (int j = 0; j < MAXN; ++j) {
+    for (int j = 0; j < RC; ++j) {
         if (!isfinite(a[j])) bad = 1;
         amax = fmaxf(amax, fabsf(a[j]));
+    }
+#pragma unroll
+    for (int c = 0; c < TC; ++c) {
+        const int j = RC + c;
+        float v = 0.f;
+        if (tid < n && j < n) v = __ldg(Ag + (j >= tid ? (size_t)tid * n + j : (size_t)j * n + tid));
+        mytail[c * MAXN] = v;
+        if (!isfinite(v)) bad = 1;
+        amax = fmaxf(amax, fabsf(v));
     }
     if (__syncthreads_or(bad)) {
         const float qnan = __int_as_float(0x7fc00000);
@@ -176,7 +201,9 @@ tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* _
     if (amax > 0.f && (amax < 9.5367431640625e-07f || amax > 1048576.0f)) sc = ldexpf(1.0f, -max(-120, min(120, ilogbf(amax))));
     if (sc != 1.0f) {
 #pragma unroll
-        for (int j = 0; j < MAXN; ++j) a[j] *= sc;
+        for (int j = 0; j < RC; ++j) a[j] *= sc;
+#pragma unroll
+        for (int c = 0; c < TC; ++c) mytail[c * MAXN] *= sc;
     }
     if (tid == 0) { wk.scale[g] = sc; wk.counts[4 * g + 2] = 0; }
     __syncthreads();
@@ -188,10 +215,16 @@ tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* _
 #define GSR_PUBLISH(parity, cnt)                                                                                   \
     do {                                                                                                           \
         float4* X4 = reinterpret_cast<float4*>(xbuf + (parity) * 176);                                             \
-        _Pragma("unroll") for (int cb = 0; cb < NB; ++cb) {                                                        \
+        _Pragma("unroll") for (int cb = 0; cb < RB; ++cb) {                                                        \
             if (16 * cb < (cnt)) {                                                                                 \
                 _Pragma("unroll") for (int c = 0; c < 4; ++c)                                                      \
                     X4[4 * cb + c] = make_float4(a[16 * cb + 4 * c], a[16 * cb + 4 * c + 1], a[16 * cb + 4 * c + 2], a[16 * cb + 4 * c + 3]); \
+            }                                                                                                      \
+        }                                                                                                          \
+        _Pragma("unroll") for (int cb = RB; cb < NB; ++cb) {                                                       \
+            if (16 * cb < (cnt)) {                                                                                 \
+                _Pragma("unroll") for (int c = 0; c < 16; ++c)                                                     \
+                    xbuf[(parity) * 176 + 16 * cb + c] = mytail[(16 * (cb - RB) + c) * MAXN];                      \
             }                                                                                                      \
         }                                                                                                          \
     } while (0)
@@ -229,19 +262,35 @@ tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* _
             __syncwarp();
             const float4* V4 = reinterpret_cast<const float4*>(vbuf);
             const bool act = tid < k;
-            // p = tau A v: thread-local
+            // p = tau A v: thread-local; the four broadcast loads of a block are issued before its FMAs
             float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
             if (act) {
 #pragma unroll
-                for (int cb = 0; cb < NB; ++cb) {
+                for (int cb = 0; cb < RB; ++cb) {
+                    if (16 * cb < k) {
+                        float4 v[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) v[c] = V4[4 * cb + c];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            q0 = fmaf(a[16 * cb + 4 * c + 0], v[c].x, q0);
+                            q1 = fmaf(a[16 * cb + 4 * c + 1], v[c].y, q1);
+                            q2 = fmaf(a[16 * cb + 4 * c + 2], v[c].z, q2);
+                            q3 = fmaf(a[16 * cb + 4 * c + 3], v[c].w, q3);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int cb = RB; cb < NB; ++cb) {
                     if (16 * cb < k) {
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const float4 v = V4[4 * cb + c];
-                            q0 = fmaf(a[16 * cb + 4 * c + 0], v.x, q0);
-                            q1 = fmaf(a[16 * cb + 4 * c + 1], v.y, q1);
-                            q2 = fmaf(a[16 * cb + 4 * c + 2], v.z, q2);
-                            q3 = fmaf(a[16 * cb + 4 * c + 3], v.w, q3);
+                            const float* t4 = mytail + (16 * (cb - RB) + 4 * c) * MAXN;
+                            q0 = fmaf(t4[0], v.x, q0);
+                            q1 = fmaf(t4[MAXN], v.y, q1);
+                            q2 = fmaf(t4[2 * MAXN], v.z, q2);
+                            q3 = fmaf(t4[3 * MAXN], v.w, q3);
                         }
                     }
                 }
@@ -273,15 +322,35 @@ tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* _
                 const float wi = wbuf[tid];
                 const float4* W4 = reinterpret_cast<const float4*>(wbuf);
 #pragma unroll
-                for (int cb = 0; cb < NB; ++cb) {
+                for (int cb = 0; cb < RB; ++cb) {
+                    if (16 * cb < k) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {                          // 8 columns: two v and two w quads in flight
+                            const float4 v0 = V4[4 * cb + 2 * h], v1 = V4[4 * cb + 2 * h + 1];
+                            const float4 w0 = W4[4 * cb + 2 * h], w1 = W4[4 * cb + 2 * h + 1];
+                            float* ar = a + 16 * cb + 8 * h;
+                            ar[0] = fmaf(-vi, w0.x, fmaf(-wi, v0.x, ar[0]));
+                            ar[1] = fmaf(-vi, w0.y, fmaf(-wi, v0.y, ar[1]));
+                            ar[2] = fmaf(-vi, w0.z, fmaf(-wi, v0.z, ar[2]));
+                            ar[3] = fmaf(-vi, w0.w, fmaf(-wi, v0.w, ar[3]));
+                            ar[4] = fmaf(-vi, w1.x, fmaf(-wi, v1.x, ar[4]));
+                            ar[5] = fmaf(-vi, w1.y, fmaf(-wi, v1.y, ar[5]));
+                            ar[6] = fmaf(-vi, w1.z, fmaf(-wi, v1.z, ar[6]));
+                            ar[7] = fmaf(-vi, w1.w, fmaf(-wi, v1.w, ar[7]));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int cb = RB; cb < NB; ++cb) {
                     if (16 * cb < k) {
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const float4 v = V4[4 * cb + c], ww = W4[4 * cb + c];
-                            a[16 * cb + 4 * c + 0] = fmaf(-vi, ww.x, fmaf(-wi, v.x, a[16 * cb + 4 * c + 0]));
-                            a[16 * cb + 4 * c + 1] = fmaf(-vi, ww.y, fmaf(-wi, v.y, a[16 * cb + 4 * c + 1]));
-                            a[16 * cb + 4 * c + 2] = fmaf(-vi, ww.z, fmaf(-wi, v.z, a[16 * cb + 4 * c + 2]));
-                            a[16 * cb + 4 * c + 3] = fmaf(-vi, ww.w, fmaf(-wi, v.w, a[16 * cb + 4 * c + 3]));
+                            float* t4 = mytail + (16 * (cb - RB) + 4 * c) * MAXN;
+                            t4[0] = fmaf(-vi, ww.x, fmaf(-wi, v.x, t4[0]));
+                            t4[MAXN] = fmaf(-vi, ww.y, fmaf(-wi, v.y, t4[MAXN]));
+                            t4[2 * MAXN] = fmaf(-vi, ww.z, fmaf(-wi, v.z, t4[2 * MAXN]));
+                            t4[3 * MAXN] = fmaf(-vi, ww.w, fmaf(-wi, v.w, t4[3 * MAXN]));
                         }
                     }
                 }
@@ -293,6 +362,7 @@ tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* _
         if (tid == k - 1) GSR_PUBLISH((k - 1) & 1, k);
         __syncthreads();                                                       // (B)
     }
+#undef GSR_PUBLISH
     if (tid == 0) {
         dd[0] = (n == 1) ? a[0] : xbuf[0];              // row 0 was published last (buffer 0, column 0)
         ee[n - 1] = 0.f;
@@ -1192,6 +1262,16 @@ tql_finish_global_kernel(const Work wk, float* __restrict__ Wout, float* __restr
 
 using namespace gsr;
 
+// K1 with g_eigh_k1_regblocks 16-column blocks of every row in registers
+static int launch_k1(const float* A, float* w, float* U, int32_t* info, const gsr::tq::Work& wk, int batch, int threads, int n,
+                     int chunk_graphs, cudaStream_t st) {
+    using namespace gsr;
+    if (g_eigh_k1_regblocks >= 10) tq::tridiag_kernel<10><<<batch, threads, 0, st>>>(A, w, U, info, wk, n, chunk_graphs);
+    else if (g_eigh_k1_regblocks == 9) tq::tridiag_kernel<9><<<batch, threads, 0, st>>>(A, w, U, info, wk, n, chunk_graphs);
+    else tq::tridiag_kernel<8><<<batch, threads, 0, st>>>(A, w, U, info, wk, n, chunk_graphs);
+    return launched("eigh_tridiag");
+}
+
 // K2 for graphs [g_first, g_end): lane = graph for batches that fill warps, one warp per graph otherwise.  `hog`: ask for all of an
 // SM's shared memory so that the CTA runs alone on it (chunked pipeline); wait_count / wait_target: see the kernel.
 static int launch_k2(const gsr::tq::Work& wk, int n, int g_first, int g_end, cudaStream_t st, bool hog = false,
@@ -1247,7 +1327,8 @@ ChunkPool* chunk_pool() {
     // CTA is resident and polling for exactly that kernel (K1) -- so every kernel of the pipeline is loaded here, before any
     // of them can wait for another.
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, gsr::tq::tridiag_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tql_scalar_lanes_kernel) != cudaSuccess ||
+    if (cudaFuncGetAttributes(&fa, gsr::tq::tridiag_kernel<8>) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tridiag_kernel<9>) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa, gsr::tq::tridiag_kernel<10>) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tql_scalar_lanes_kernel) != cudaSuccess ||
         cudaFuncGetAttributes(&fa, gsr::tq::k2_resident_gate_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tql_apply_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tql_finish_kernel) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
@@ -1331,8 +1412,7 @@ static int eigh_small_segment(const float* A, float* w, float* U, int32_t* info,
 #endif
     if (nchunks == 1) {
         GSR_TR(0);
-        tq::tridiag_kernel<<<batch, threads, 0, st>>>(A, w, U, info, wk, n, 0);
-        if ((rc = launched("eigh_tridiag"))) return rc;
+        if ((rc = launch_k1(A, w, U, info, wk, batch, threads, n, 0, st))) return rc;
         GSR_TR(1);
         if ((rc = launch_k2(wk, n, 0, batch, st, false, nullptr, 0, nullptr, g_eigh_k2_lanes >= 2))) return rc;      // one warp per graph unless forced
         if ((rc = launch_small_apply(w, U, info, wk, 0, batch, n, canonical_sign, st))) return rc;
@@ -1358,8 +1438,7 @@ static int eigh_small_segment(const float* A, float* w, float* U, int32_t* info,
             g_tr_chunk = 0;
 #endif
             GSR_TR(0);
-            tq::tridiag_kernel<<<batch, threads, 0, st>>>(A, w, U, info, wk, n, per);
-            rc = launched("eigh_tridiag");
+            rc = launch_k1(A, w, U, info, wk, batch, threads, n, per, st);
         }
         for (int c = 0; c < nchunks && !rc; ++c) {
             const int g0 = c * per, g1 = std::min(batch, g0 + per);

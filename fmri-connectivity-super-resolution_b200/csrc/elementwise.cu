@@ -400,7 +400,7 @@ normalize_scale_tiles_kernel(const float* __restrict__ mx, const float* __restri
 // bwd pass 1: partial dr over one tile pair.  part[b][slot][row]: rows of I from the pair (I, J) go to slot J,
 // rows of J to slot I (every (slot, row block) is written by exactly one CTA).
 template <int PRE>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 3)
 normalize_bwd_partial_tiles_kernel(const float* __restrict__ mx, const float* __restrict__ r, const float* __restrict__ Tg,
                                    const float* __restrict__ Tg2, float* __restrict__ part, int n, int T) {
     extern __shared__ float smem[];
@@ -480,7 +480,7 @@ __global__ void normalize_bwd_drho_kernel(const float* __restrict__ part, const 
 
 // bwd pass 2: dM(I,J)[i][j] = (T[j][i] r_i) r_j + drho_i;  PRE: x sgn(mx[i][j]), zero diagonal
 template <int PRE>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 3)
 normalize_bwd_apply_tiles_kernel(const float* __restrict__ mx, const float* __restrict__ r, const float* __restrict__ drho,
                                  const float* __restrict__ Tg, const float* __restrict__ Tg2, float* __restrict__ dmx, int n, int T) {
     extern __shared__ float smem[];

@@ -14,3 +14,20 @@ for _ in range(2):
     K.sym_diag_abs_bwd(x, g1)
 torch.cuda.synchronize()
 print("done")
+
+# outside a profiler: device time of each call (CUDA events, 10 calls)
+import json
+def t(fn, reps=10):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return round(e0.elapsed_time(e1) / reps * 1e3, 1)
+if not os.environ.get("GSR_NO_TIMES"):
+    print(json.dumps({"batch": B, "us": {
+        "normalize_fwd(pre)": t(lambda: K.normalize_adj_fwd(x, pre=True)),
+        "normalize_bwd(pre)": t(lambda: K.normalize_adj_bwd(x, r, g1, pre=True)),
+        "normalize_bwd(pre, two gradients)": t(lambda: K.normalize_adj_bwd(x, r, g1, pre=True, grad_out2=g2)),
+        "sym_diag_abs_fwd": t(lambda: K.sym_diag_abs_fwd(x)),
+        "sym_diag_abs_bwd": t(lambda: K.sym_diag_abs_bwd(x, g1))}}))
