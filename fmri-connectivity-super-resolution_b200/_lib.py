@@ -52,6 +52,9 @@ PROTOTYPES = {
     "gsr_colsum_f32": (i32, [c_ptr, c_ptr, i32, i32, i32, c_ptr]),
     "gsr_sym_diag_abs_fwd": (i32, [c_ptr, c_ptr, i32, i32, c_ptr]),
     "gsr_sym_diag_abs_bwd": (i32, [c_ptr, c_ptr, c_ptr, i32, i32, c_ptr]),
+    "gsr_sym_diag_abs_l1_partials": (i32, [i32]),
+    "gsr_sym_diag_abs_l1_fwd": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, c_ptr]),
+    "gsr_sym_diag_abs_l1_bwd": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, c_ptr]),
     "gsr_abs_diag1_fwd": (i32, [c_ptr, c_ptr, i32, i32, c_ptr]),
     "gsr_pool_scores": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, c_ptr]),
     "gsr_pool_topk": (i32, [c_ptr, i32, i32, c_ptr, c_ptr, c_ptr]),

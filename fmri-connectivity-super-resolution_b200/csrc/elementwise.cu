@@ -307,6 +307,115 @@ sym_diag_abs_tiles_kernel(const float* __restrict__ x, const float* __restrict__
     }
 }
 
+// ---------------------------------------------------------------- sym / diag / abs + L1 against a target, tile pairs
+// The last two operations of a training step (models/gsr_model.py:32-37, then nn.L1Loss against the HR target,
+// utils/gsr_train.py:39-43) as ONE pass: z = |(x + x^T) / 2| with a unit diagonal is formed in registers and
+// compared with the target tile and its mirror; the prediction is written only if the caller asks for it.
+//   FWD  partial[b][pair] = sum over the pair's elements of |z - y|  (double; folded in fixed order by
+//        sym_l1_final_kernel)                                  -- reads x and y once, writes nothing of size n^2
+//   BWD  dx = backward of sym-diag-abs applied to the L1 gradient sgn(z - y) * grad_loss[b] / n^2, recomputed from
+//        x and y instead of being read from a [B, n, n] gradient tensor: the same expressions in the same order as
+//        l1_bwd_kernel followed by sym_diag_abs_tiles_kernel<true>, so the result is bit identical to the two launches
+template <bool BWD>
+__global__ void __launch_bounds__(kTileThreads)
+sym_diag_abs_l1_tiles_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ grad_loss,
+                             float* __restrict__ out, double* __restrict__ partials, int n, int T) {
+    extern __shared__ float smem[];
+    float* bx = smem;                          // partner tile of x:  bx[jj][ii] = x[J0 + jj][I0 + ii]
+    float* by = smem + kTS * kTP;              // partner tile of y
+    float* res = by + kTS * kTP;               // result tile (I, J) (BWD, or FWD with a prediction to write)
+    __shared__ double s_red[kTileThreads / 32];
+    const size_t base = (size_t)blockIdx.y * n * n;
+    x += base; y += base;
+    if (out) out += base;
+    int I, J;
+    tile_pair_of(blockIdx.x, T, I, J);
+    const int I0 = I * kTS, J0 = J * kTS;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float4 ax[4], pbx[4], ay[4], pby[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int r = ty + 16 * p;
+        ax[p] = ld4_masked(x, n, I0 + r, J0 + 4 * tx);
+        pbx[p] = ld4_masked(x, n, J0 + r, I0 + 4 * tx);
+        ay[p] = ld4_masked(y, n, I0 + r, J0 + 4 * tx);
+        pby[p] = ld4_masked(y, n, J0 + r, I0 + 4 * tx);
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        st_tile(bx, ty + 16 * p, 4 * tx, pbx[p]);
+        st_tile(by, ty + 16 * p, 4 * tx, pby[p]);
+    }
+    __syncthreads();
+    const float scale = BWD ? grad_loss[blockIdx.y] / (float)((long long)n * n) : 0.f;
+    float acc = 0.f;                           // FWD: <= 32 terms per thread in fp32, fp64 across threads
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int ii = ty + 16 * p, i = I0 + ii;
+        const float a[4] = {ax[p].x, ax[p].y, ax[p].z, ax[p].w};
+        const float ya[4] = {ay[p].x, ay[p].y, ay[p].z, ay[p].w};
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int jj = 4 * tx + u, j = J0 + jj;
+            const float z = (a[u] + bx[jj * kTP + ii]) / 2.0f;                  // (x + x^T) / 2
+            const float pred = (i == j) ? 1.0f : fabsf(z);
+            const float yb = by[jj * kTP + ii];                                 // y[j][i]
+            if (!BWD) {
+                o[u] = pred;
+                if (i < n && j < n) {
+                    acc += fabsf(pred - ya[u]);
+                    if (I != J) acc += fabsf(pred - yb);                        // the mirror element
+                }
+            } else {
+                const float sg = sgnf(z);
+                const float ga = sgnf(pred - ya[u]) * scale, gb = sgnf(pred - yb) * scale;
+                const float v = (ga * sg + gb * sg) / 2.0f;
+                o[u] = (i == j) ? 0.f : v;
+            }
+        }
+        if (BWD || out) {
+            const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+            if (i < n && J0 + 4 * tx < n) *reinterpret_cast<float4*>(out + (size_t)i * n + J0 + 4 * tx) = o4;
+            st_tile(res, ii, 4 * tx, o4);
+        }
+    }
+    if (!BWD) {
+        double v = (double)acc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kTileThreads / 32; ++w) t += s_red[w];
+            partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+        }
+        if (!out) return;
+    }
+    if (I == J) return;                                                          // the diagonal tile is its own mirror
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int jj = ty + 16 * p, j = J0 + jj;                                // row of the mirror tile (J, I)
+        if (j < n && I0 + 4 * tx < n) {
+            const float4 o4 = make_float4(res[(4 * tx) * kTP + jj], res[(4 * tx + 1) * kTP + jj],
+                                          res[(4 * tx + 2) * kTP + jj], res[(4 * tx + 3) * kTP + jj]);
+            *reinterpret_cast<float4*>(out + (size_t)j * n + I0 + 4 * tx) = o4;
+        }
+    }
+}
+
+// loss[b] = (sum of the subject's pair partials, fixed order) / n^2
+__global__ void sym_l1_final_kernel(const double* __restrict__ partials, float* __restrict__ loss, int pairs, long long count, int batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    double t = 0.0;
+    for (int c = 0; c < pairs; ++c) t += partials[(size_t)b * pairs + c];
+    loss[b] = (float)(t / (double)count);
+}
+
 // ---------------------------------------------------------------- normalise, tile pairs
 // Same decomposition as sym_diag_abs_tiles_kernel for utils/preprocessing.py:16-25 and its autograd:
 //   fwd   rowsum kernel (warp per row, float4) -> r;  tile-pair kernel: out(I,J) = r_i r_j M(J,I)^T and its mirror
@@ -647,6 +756,41 @@ extern "C" int gsr_sym_diag_abs_bwd(const float* x, const float* grad_out, float
     if (rc) return fail(rc, "sym_diag_abs_bwd: n too large for one CTA");
     sym_diag_abs_bwd_kernel<<<batch, kEwThreads, smem, (cudaStream_t)stream>>>(x, grad_out, grad_x, n);
     return launched("sym_diag_abs_bwd");
+}
+
+extern "C" int gsr_sym_diag_abs_l1_partials(int n) {
+    const int T = (n + kTS - 1) / kTS;
+    return T * (T + 1) / 2;
+}
+
+extern "C" int gsr_sym_diag_abs_l1_fwd(const float* x, const float* y, float* pred_out, float* loss_out, double* partials,
+                                       int batch, int n, void* stream) {
+    if (!x || !y || !loss_out || !partials || batch < 0 || n <= 0) return fail(GSR_E_ARG, "sym_diag_abs_l1_fwd: bad argument");
+    if (batch == 0) return 0;
+    if (n % 4 != 0 || !aligned16(x) || !aligned16(y) || (pred_out && !aligned16(pred_out)) || batch > 65535)
+        return fail(GSR_E_UNSUPPORTED, "sym_diag_abs_l1_fwd: needs n % 4 == 0, 16-byte aligned tensors and batch <= 65535 (use sym_diag_abs + l1_loss)");
+    const int T = (n + kTS - 1) / kTS, pairs = T * (T + 1) / 2;
+    const size_t tsmem = 3 * kTS * kTP * sizeof(float);
+    int rc = set_smem(sym_diag_abs_l1_tiles_kernel<false>, tsmem);
+    if (rc) return fail(rc, "sym_diag_abs_l1_fwd: cudaFuncSetAttribute failed");
+    sym_diag_abs_l1_tiles_kernel<false><<<dim3(pairs, batch), kTileThreads, tsmem, (cudaStream_t)stream>>>(x, y, nullptr, pred_out, partials, n, T);
+    if ((rc = launched("sym_diag_abs_l1_fwd"))) return rc;
+    sym_l1_final_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, loss_out, pairs, (long long)n * n, batch);
+    return launched("sym_l1_final");
+}
+
+extern "C" int gsr_sym_diag_abs_l1_bwd(const float* x, const float* y, const float* grad_loss, float* grad_x,
+                                       int batch, int n, void* stream) {
+    if (!x || !y || !grad_loss || !grad_x || batch < 0 || n <= 0) return fail(GSR_E_ARG, "sym_diag_abs_l1_bwd: bad argument");
+    if (batch == 0) return 0;
+    if (n % 4 != 0 || !aligned16(x) || !aligned16(y) || !aligned16(grad_x) || batch > 65535)
+        return fail(GSR_E_UNSUPPORTED, "sym_diag_abs_l1_bwd: needs n % 4 == 0, 16-byte aligned tensors and batch <= 65535");
+    const int T = (n + kTS - 1) / kTS;
+    const size_t tsmem = 3 * kTS * kTP * sizeof(float);
+    int rc = set_smem(sym_diag_abs_l1_tiles_kernel<true>, tsmem);
+    if (rc) return fail(rc, "sym_diag_abs_l1_bwd: cudaFuncSetAttribute failed");
+    sym_diag_abs_l1_tiles_kernel<true><<<dim3(T * (T + 1) / 2, batch), kTileThreads, tsmem, (cudaStream_t)stream>>>(x, y, grad_loss, grad_x, nullptr, n, T);
+    return launched("sym_diag_abs_l1_bwd");
 }
 
 extern "C" int gsr_abs_diag1_fwd(const float* x, float* out, int batch, int n, void* stream) {

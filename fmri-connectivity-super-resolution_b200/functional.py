@@ -358,6 +358,33 @@ def sym_diag_abs(x: torch.Tensor) -> torch.Tensor:
     return SymDiagAbsFn.apply(x)
 
 
+class SymDiagAbsL1Fn(Function):
+    """models/gsr_model.py:32-37 followed by the L1 term against the HR target (utils/gsr_train.py:39-43) as one
+    autograd node: [B] per-subject means of | |(x + x^T)/2| (unit diagonal) - y |.  Neither the prediction nor its
+    gradient is materialised; the gradient of x is bit identical to ``l1_loss_per_subject(sym_diag_abs(x), y)``'s."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        x, y = x.contiguous(), y.contiguous()
+        ctx.save_for_backward(x, y)
+        return K.sym_diag_abs_l1_fwd(x, y)[0]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        return K.sym_diag_abs_l1_bwd(x, y, _c(g)), None
+
+
+def sym_diag_abs_l1_per_subject(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Per-subject L1 of the symmetrised prediction against ``y`` (no gradient for ``y``: it is data)."""
+    if y.requires_grad:
+        raise NotImplementedError("sym_diag_abs_l1_per_subject: the target is data (no gradient); use sym_diag_abs + l1_loss_per_subject")
+    if not K.sym_diag_abs_l1_supported(x.contiguous(), y.contiguous()):
+        return l1_loss_per_subject(sym_diag_abs(x), y)
+    return SymDiagAbsL1Fn.apply(x, y)
+
+
 # ----------------------------------------------------------------------------- a13
 class L1LossFn(Function):
     """nn.L1Loss() (utils/gsr_train.py:9): mean |x - y|, per subject when `batch` > 1.

@@ -370,6 +370,44 @@ def sym_diag_abs_bwd(x: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
     return grad
 
 
+def sym_diag_abs_l1_supported(x: torch.Tensor, y: torch.Tensor) -> bool:
+    """The fused pass takes contiguous fp32 [B, n, n] with n % 4 == 0 (the tile kernels' float4 rows)."""
+    return (x.dim() == 3 and x.shape == y.shape and x.shape[-1] == x.shape[-2] and x.shape[-1] % 4 == 0
+            and x.shape[0] <= 65535 and x.is_contiguous() and y.is_contiguous()
+            and x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0)
+
+
+def sym_diag_abs_l1_fwd(x: torch.Tensor, y: torch.Tensor, want_pred: bool = False):
+    """(per-subject mean | |(x + x^T)/2| (unit diagonal) - y |  [B], the prediction or None): one pass over x and y."""
+    x, y = _f32(x, "sym_diag_abs_l1: x"), _f32(y, "sym_diag_abs_l1: y")
+    batch, n = _square_batch(x, "sym_diag_abs_l1: x")
+    loss = torch.empty((batch,), device=x.device, dtype=torch.float32)
+    part = torch.empty((max(batch, 1) * lib().gsr_sym_diag_abs_l1_partials(n),), device=x.device, dtype=torch.float64)
+    pred = torch.empty_like(x) if want_pred else None
+    timer = EW_TIMER
+    e0 = timer.start() if timer is not None else None
+    check(lib().gsr_sym_diag_abs_l1_fwd(x.data_ptr(), y.data_ptr(), pred.data_ptr() if want_pred else None, loss.data_ptr(),
+                                        part.data_ptr(), batch, n, _stream()), "gsr_sym_diag_abs_l1_fwd")
+    if timer is not None:
+        timer.stop(e0, (12.0 if want_pred else 8.0) * batch * n * n)
+    return loss, pred
+
+
+def sym_diag_abs_l1_bwd(x: torch.Tensor, y: torch.Tensor, grad_loss: torch.Tensor) -> torch.Tensor:
+    x, y, grad_loss = _f32(x, "x"), _f32(y, "y"), _f32(grad_loss, "grad_loss")
+    batch, n = _square_batch(x, "sym_diag_abs_l1_bwd: x")
+    if grad_loss.numel() != batch:
+        raise ValueError("sym_diag_abs_l1_bwd: grad_loss must hold one value per subject")
+    grad = torch.empty_like(x)
+    timer = EW_TIMER
+    e0 = timer.start() if timer is not None else None
+    check(lib().gsr_sym_diag_abs_l1_bwd(x.data_ptr(), y.data_ptr(), grad_loss.data_ptr(), grad.data_ptr(), batch, n, _stream()),
+          "gsr_sym_diag_abs_l1_bwd")
+    if timer is not None:
+        timer.stop(e0, 12.0 * batch * n * n)
+    return grad
+
+
 def abs_diag1(x: torch.Tensor) -> torch.Tensor:
     x = _f32(x, "abs_diag1: x")
     batch, n = _square_batch(x, "abs_diag1: x")

@@ -36,6 +36,14 @@ class GSRNet(nn.Module):
         """``U`` (extension): a precomputed eigenbasis of the normalised LR adjacency.  ``check_eigh`` (extension):
         override ``self.layer.check_eigh`` for this call (False = no host synchronisation; the device-side Jacobi
         fallback for QL failures runs either way)."""
+        hidden2, net_outs, start_gcn_outs, outputs = self.forward_hidden(lr, U=U, check_eigh=check_eigh)
+        z = F_.sym_diag_abs(hidden2)                                                  # :32-37
+        return z, net_outs, start_gcn_outs, outputs
+
+    def forward_hidden(self, lr, U=None, check_eigh=None):
+        """``forward`` up to and including :30 -- ``hidden2`` instead of the symmetrised prediction.  The training step
+        feeds it to ``functional.sym_diag_abs_l1_per_subject``, which forms :32-37 and the L1 term against the HR target
+        in one pass (the prediction is never written)."""
         lr = lr if lr.is_cuda else lr.to(device)
         check = self.layer.check_eigh if check_eigh is None else bool(check_eigh)
         if self.layer.weights.device.type != "cuda":
@@ -62,5 +70,4 @@ class GSRNet(nn.Module):
         self.outputs, self.Z = self.layer(A, self.net_outs, U=U, check_eigh=check)    # :28
         # :29-30  hidden1 = gc1(Z, outputs); hidden2 = gc2(hidden1, outputs) -- one autograd node for the two layers
         self.hidden1, self.hidden2 = F_.GraphConvPairFn.apply(self.Z, self.outputs, self.gc1.weight, self.gc2.weight)
-        z = F_.sym_diag_abs(self.hidden2)                                             # :32-37
-        return z, self.net_outs, self.start_gcn_outs, self.outputs
+        return self.hidden2, self.net_outs, self.start_gcn_outs, self.outputs

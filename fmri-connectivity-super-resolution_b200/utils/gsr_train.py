@@ -88,18 +88,24 @@ class GSRTrainStep:
     unless ``check_errors`` asks for torch.linalg.eigh's raise-on-failure contract.
     ``U_hr_reduced`` may be passed when the caller caches the data-only HR target basis."""
 
-    def __init__(self, model, lmbda=16, padding=0, check_errors=False):
+    def __init__(self, model, lmbda=16, padding=0, check_errors=False, fuse_final=True):
         self.model, self.lmbda, self.padding, self.check_errors = model, lmbda, padding, check_errors
+        self.fuse_final = fuse_final      # False: the prediction is materialised (model(lr)) and compared by l1_loss
 
     def forward_loss(self, lr, hr, U_hr_reduced=None, U_lr=None):
         model = self.model
         # check_errors=True raises inside the forward pass, before any product consumes a failed basis; the
         # caller's model keeps its own ``layer.check_eigh`` either way
-        out, net_outs, start_gcn_outs, _ = model(lr, U=U_lr, check_eigh=self.check_errors)
-        out = unpad(out, self.padding)
+        fused = self.fuse_final and self.padding == 0 and lr.dim() == 3 and hasattr(model, "forward_hidden")
+        if fused:
+            # :32-37 of the model and the L1 term against the HR target in one pass over hidden2 and hr
+            hidden2, net_outs, start_gcn_outs, _ = model.forward_hidden(lr, U=U_lr, check_eigh=self.check_errors)
+        else:
+            out, net_outs, start_gcn_outs, _ = model(lr, U=U_lr, check_eigh=self.check_errors)
+            out = unpad(out, self.padding)
         if U_hr_reduced is None:
             U_hr_reduced = hr_target_basis(hr, model.layer.lr_dim, self.padding, check_errors=False)
-        err_b = F_.l1_loss_per_subject(out, hr)                                  # [B]
+        err_b = F_.sym_diag_abs_l1_per_subject(hidden2, hr) if fused else F_.l1_loss_per_subject(out, hr)      # [B]
         w_b = F_.l1_loss_per_subject(U_hr_reduced, model.layer.weights)          # |W - U_hr| per subject
         reg = F_.l1_loss(net_outs, start_gcn_outs)
         error = err_b.mean()

@@ -190,6 +190,18 @@ GSR_API int gsr_sym_diag_abs_fwd(const float* x, float* out, int batch, int n, v
  * diagonal), grad_x = (dz + dz^T)/2.                                             */
 GSR_API int gsr_sym_diag_abs_bwd(const float* x, const float* grad_out, float* grad_x,
                          int batch, int n, void* stream);
+/* models/gsr_model.py:32-37 followed by nn.L1Loss against the HR target (utils/gsr_train.py:9,39-43) in ONE pass:
+ *   loss_out[b] = mean | |(x_b + x_b^T)/2| (unit diagonal) - y_b |
+ * x, y [batch, n, n]; the prediction itself is written to pred_out only when it is not NULL.  partials: double
+ * [batch * gsr_sym_diag_abs_l1_partials(n)] (deterministic two-stage sum).  Needs n % 4 == 0 and 16-byte aligned
+ * tensors (GSR_E_UNSUPPORTED otherwise: callers then use gsr_sym_diag_abs_fwd + gsr_l1_loss_fwd).               */
+GSR_API int gsr_sym_diag_abs_l1_partials(int n);
+GSR_API int gsr_sym_diag_abs_l1_fwd(const float* x, const float* y, float* pred_out, float* loss_out, double* partials,
+                            int batch, int n, void* stream);
+/* autograd of the above with respect to x, given grad_loss [batch]: bit identical to gsr_l1_loss_bwd followed by
+ * gsr_sym_diag_abs_bwd, without the [batch, n, n] gradient tensor between them.                                */
+GSR_API int gsr_sym_diag_abs_l1_bwd(const float* x, const float* y, const float* grad_loss, float* grad_x,
+                            int batch, int n, void* stream);
 /* models/layers.py:55-56 alone (the stored `self.f_d`): out = |x|, unit diagonal. */
 GSR_API int gsr_abs_diag1_fwd(const float* x, float* out, int batch, int n, void* stream);
 

@@ -687,6 +687,54 @@ def test_sym_diag_abs(cuda_pkg, n, batch):
     assert torch.allclose(xc.grad.cpu(), xr.grad, rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("n,batch", [(268, 3), (64, 2), (12, 1), (200, 2), (4, 5)])
+def test_sym_diag_abs_l1_fused(cuda_pkg, K, n, batch):
+    """The fused final pass (sym-diag-abs + L1 against the target, prediction never written) against the two launches it
+    replaces: loss to rounding (a different summation order), prediction and gradient BIT identical -- also with exact
+    ties (pred == y: sgn 0), a zero pre-activation (sgn(z) = 0) and non-uniform upstream gradients -- and the loss against
+    float64."""
+    F_ = cuda_pkg.functional
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(batch, n, n, generator=g)
+    y = torch.rand(batch, n, n, generator=g)
+    z0 = ((x[0] + x[0].t()) / 2).abs()
+    y[0, 0, :] = z0[0, :]                                      # ties in one row of one subject
+    if n > 3:
+        x[0, 1, 2] = 0.25; x[0, 2, 1] = -0.25                  # z = 0 exactly
+    wt = torch.rand(batch, generator=g).cuda()
+    xc, yc = x.cuda(), y.cuda()
+    x1 = xc.clone().requires_grad_(True)
+    per1 = F_.l1_loss_per_subject(F_.sym_diag_abs(x1), yc)
+    (per1 * wt).sum().backward()
+    x2 = xc.clone().requires_grad_(True)
+    assert K.sym_diag_abs_l1_supported(x2, yc)
+    per2 = F_.sym_diag_abs_l1_per_subject(x2, yc)
+    (per2 * wt).sum().backward()
+    assert torch.allclose(per1, per2, rtol=1e-6, atol=0)
+    assert torch.equal(x1.grad, x2.grad)
+    zd = (x.double() + x.double().transpose(1, 2)) / 2
+    pred = zd.abs()
+    pred[:, torch.arange(n), torch.arange(n)] = 1.0
+    want = (pred.float().double() - y.double()).abs().mean((1, 2))
+    assert torch.allclose(per2.cpu().double(), want, rtol=2e-6, atol=0)
+    loss, p = K.sym_diag_abs_l1_fwd(xc, yc, want_pred=True)
+    assert torch.equal(p, K.sym_diag_abs_fwd(xc)) and torch.equal(loss, per2.detach())
+
+
+def test_sym_diag_abs_l1_fallback_and_contract(cuda_pkg, K):
+    """n % 4 != 0 takes the two-launch route; the C entry point itself refuses (GSR_E_UNSUPPORTED), never guesses."""
+    F_ = cuda_pkg.functional
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(2, 33, 33, generator=g).cuda(), torch.rand(2, 33, 33, generator=g).cuda()
+    assert not K.sym_diag_abs_l1_supported(x, y)
+    per = F_.sym_diag_abs_l1_per_subject(x.clone().requires_grad_(True), y)
+    assert torch.equal(per, F_.l1_loss_per_subject(F_.sym_diag_abs(x), y))
+    with pytest.raises(RuntimeError):
+        K.sym_diag_abs_l1_fwd(x, y)
+    with pytest.raises(NotImplementedError):
+        F_.sym_diag_abs_l1_per_subject(x, y.clone().requires_grad_(True))
+
+
 # ------------------------------------------------------------------ pooling
 def test_topk_bit_exact_with_ties(K, golden):
     G = golden("ops")

@@ -538,6 +538,26 @@ def test_batched_gradients_match_oracle_through_the_split_reduction(setup):
         assert rel_fro(p.grad.cpu(), params[k].grad) < 2e-3, k
 
 
+def test_fused_final_pass_equals_the_materialised_prediction(setup):
+    """GSRTrainStep's default (models/gsr_model.py:32-37 and the L1 term against the HR target in one pass, the prediction
+    never written) against the step that materialises model(lr) and calls l1_loss on it: every parameter gradient BIT
+    identical, loss and error to rounding (the per-subject sums are folded in a different order)."""
+    pkg, sd, model = setup
+    B = 5
+    lr, hr = _synth_batch(160, B, 61), _synth_batch(268, B, 62)
+    Uh = pkg.hr_target_basis(hr, 160)
+    model.zero_grad()
+    loss_a, err_a = pkg.GSRTrainStep(model, fuse_final=False)(lr, hr, U_hr_reduced=Uh)
+    U_lr = model.layer.U_lr
+    g_a = [p.grad.clone() for p in model.parameters()]
+    model.zero_grad()
+    loss_b, err_b = pkg.GSRTrainStep(model)(lr, hr, U_hr_reduced=Uh, U_lr=U_lr)
+    assert float(err_a) == pytest.approx(float(err_b), rel=1e-6)
+    assert float(loss_a) == pytest.approx(float(loss_b), rel=1e-6)
+    for a, p in zip(g_a, model.parameters()):
+        assert torch.equal(a, p.grad)
+
+
 @pytest.mark.parametrize("G", [2, 8])
 def test_subject_shards_reduce_to_the_one_gpu_gradient(setup, G):
     """SURVEY section 4 shard emulation on one GPU: the batch split into G rank shards (shard_bounds), every shard's
