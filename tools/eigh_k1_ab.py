@@ -16,7 +16,7 @@ for n in (1, 2, 17, 100, 127, 128, 129, 143, 144, 145, 159, 160):
         A[3] = A[3] * 1e-12; A[4] = A[4] * 1e9; A[5, 1, n - 1] = float("nan")      # rescaled rows, one NaN in the shared-memory columns
     res = {}
     for rb in (10, 9, 8):
-        pkg.set_tuning("eigh_k1_regblocks", rb)
+        pkg.set_tuning("eigh_k1_regblocks", rb); pkg.set_tuning("eigh_q_in_k1", 0 if rb == 10 else 1)      # 10 also = Q formed in K3
         res[rb] = K.eigh_tridiag(A)
     ok = [s for s in range(9) if not (n >= 17 and s == 5)]
     same = all(torch.equal(res[10][0][ok], res[rb][0][ok]) and torch.equal(res[10][1][ok], res[rb][1][ok]) and torch.equal(res[10][2], res[rb][2]) for rb in (9, 8))
@@ -27,11 +27,25 @@ for n in (1, 2, 17, 100, 127, 128, 129, 143, 144, 145, 159, 160):
 gen = torch.Generator(device="cuda").manual_seed(0)
 x = torch.rand(1024, 160, 160, device="cuda", generator=gen); lr = (x + x.transpose(1, 2)) / 2; lr.diagonal(dim1=1, dim2=2).zero_()
 A = pkg.normalize_adj_torch(lr)
-ref = None
 for chunks in (1, 8):
-    for rb in (10, 9, 8):
-        pkg.set_tuning("eigh_k1_regblocks", rb); pkg.set_tuning("eigh_chunks", chunks)
-        (w, U, info), ms = timed(K.eigh_tridiag, A, reps=5)
-        report(f"tridiag 1024x160 k1_regblocks={rb} chunks={chunks}", A, w, U, info, ms)
-        if ref is None: ref = (w, U)
-        else: print(json.dumps({"regblocks": rb, "chunks": chunks, "bit_identical_to_first": bool(torch.equal(w, ref[0]) and torch.equal(U, ref[1]))}), flush=True)
+    ref = None
+    for q_in_k1 in (0, 1, 2):
+        for rb in ((10, 9, 8) if q_in_k1 < 2 else (8,)):
+            pkg.set_tuning("eigh_k1_regblocks", rb); pkg.set_tuning("eigh_chunks", chunks); pkg.set_tuning("eigh_q_in_k1", q_in_k1)
+            (w, U, info), ms = timed(K.eigh_tridiag, A, reps=5)
+            report(f"tridiag 1024x160 k1_regblocks={rb} q_in_k1={q_in_k1} chunks={chunks}", A, w, U, info, ms)
+            if ref is None: ref = (w, U)
+            else: print(json.dumps({"regblocks": rb, "q_in_k1": q_in_k1, "chunks": chunks, "bit_identical_to_first_of_this_chunking": bool(torch.equal(w, ref[0]) and torch.equal(U, ref[1]))}), flush=True)
+# ragged batches through the pipeline with Q formed in K1 (the second per-chunk count): 32 k + r graphs, a NaN graph in the last chunk
+pkg.set_tuning("eigh_k1_regblocks", 8); pkg.set_tuning("eigh_chunks", 8)
+for B in (384, 400, 777, 1025):
+    Ab = A[:B].clone() if B <= 1024 else torch.cat([A, A[:B - 1024]])
+    Ab[B - 3, 0, 5] = float("nan")
+    out = {}
+    for q_in_k1 in (0, 1, 2):
+        pkg.set_tuning("eigh_q_in_k1", q_in_k1)
+        out[q_in_k1] = K.eigh_tridiag(Ab)
+    ok = [s for s in range(B) if s != B - 3]
+    print(json.dumps({"batch": B, "q_in_k1_bit_identical": bool(all(torch.equal(out[0][0][ok], out[q][0][ok]) and torch.equal(out[0][1][ok], out[q][1][ok]) and torch.equal(out[0][2], out[q][2]) for q in (1, 2))),
+                      "nan_graph_info": int(out[1][2][B - 3])}), flush=True)
+pkg.set_tuning("eigh_q_in_k1", 2)
