@@ -41,6 +41,7 @@ extern int g_eigh_k2_lanes;
 extern int g_eigh_chunks;
 extern int g_eigh_k2_warps;
 extern int g_eigh_k1_regblocks;
+extern int g_norm_bwd_cluster;
 extern int g_eigh_q_in_k1;
 namespace tc { extern int g_pairs, g_tail, g_dual, g_tma, g_utccp, g_mn_partial, g_pf_ahead, g_tmem_a, g_cluster_release, g_partial_head, g_reduce_simt_tails; }
 
@@ -312,6 +313,7 @@ extern "C" int gsr_set_tuning(const char* key, int value) {
     if (!strcmp(key, "eigh_k2_warps")) { gsr::g_eigh_k2_warps = value; return 0; }
     if (!strcmp(key, "eigh_k1_regblocks")) { gsr::g_eigh_k1_regblocks = value; return 0; }
     if (!strcmp(key, "eigh_q_in_k1")) { gsr::g_eigh_q_in_k1 = value; return 0; }
+    if (!strcmp(key, "normalize_bwd_cluster")) { gsr::g_norm_bwd_cluster = value; return 0; }
     if (!strcmp(key, "eigh_chunks")) { gsr::g_eigh_chunks = value; return 0; }
     if (!strcmp(key, "eigh_k2_lanes")) { gsr::g_eigh_k2_lanes = value; return 0; }
     if (!strcmp(key, "eigh_redo_failed")) { gsr::g_eigh_redo = value; return 0; }

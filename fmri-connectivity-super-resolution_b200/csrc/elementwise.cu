@@ -6,6 +6,7 @@
 // through padded shared memory so that both the global reads and the global
 // writes stay coalesced.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace gsr {
 
@@ -216,6 +217,8 @@ sym_diag_abs_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g
 // writes the mirror tile from a transposed read of the result.  15 pairs per 268 x 268 matrix
 // x 1024 subjects: enough independent CTAs (several per SM) to keep HBM busy, where the
 // one-CTA-per-matrix strip kernels above are bound by their own barriers (34-44 % of HBM).
+constexpr int kNormCluster = 16;        // normalise backward in one pass: CTAs (tile pairs) per subject cluster
+int g_norm_bwd_cluster = 0;             // gsr_set_tuning("normalize_bwd_cluster", 0|1): three launches (default) / the one-pass cluster kernel for n <= 320
 constexpr int kTS = 64;                 // tile edge
 constexpr int kTP = kTS + 1;            // padded pitch
 constexpr int kTileThreads = 256;       // thread (ty, tx): rows ty + 16 p (p < 4), columns 4 tx .. 4 tx + 3
@@ -662,6 +665,162 @@ normalize_bwd_apply_tiles_kernel(const float* __restrict__ mx, const float* __re
     }
 }
 
+// bwd as ONE pass (n <= 320: at most 15 tile pairs): the CTAs of a subject form a thread-block CLUSTER of 16, so they
+// are resident together and can exchange their partial sums through distributed shared memory between the two halves of
+// the algorithm -- every CTA keeps its pair of tiles on chip (T(I,J) + T(J,I) in shared memory, the signs of mx in two
+// registers) instead of reading T, T2 and mx a second time: 4 tensors of traffic (T, T2, mx in, dM out) instead of 7.
+// Same expressions and the same summation order as the three launches above (partial -> drho -> apply): bit identical.
+// MEASURED SLOWER and therefore off by default (1024 x 268, two incoming gradients: 611 us at 3 CTAs per SM, 770 us at 2,
+// against 550 us for the three launches): a cluster of 16 holds 16 CTA slots of one GPC from its first load to its last
+// store, every CTA waits twice for the slowest of the 16, and load, exchange and store phases of a CTA do not overlap;
+// the three launches keep 3 independent CTAs per SM streaming.  Kept as a switch with its parity test.
+__device__ __forceinline__ int tile_pair_rank(int I, int J, int T) { return I * T - I * (I - 1) / 2 + (J - I); }     // inverse of tile_pair_of, I <= J
+__device__ __forceinline__ uint32_t sign_code(float v) { return v > 0.f ? 1u : (v < 0.f ? 2u : 0u); }               // 2 bits: sgnf(v) = 0, +1, -1
+__device__ __forceinline__ float sign_of_code(uint32_t c) { return c == 1u ? 1.0f : (c == 2u ? -1.0f : 0.0f); }
+
+template <int PRE>
+__global__ void __launch_bounds__(kTileThreads, 3)
+normalize_bwd_cluster_kernel(const float* __restrict__ mx, const float* __restrict__ r, const float* __restrict__ Tg,
+                             const float* __restrict__ Tg2, float* __restrict__ dmx, int n, int T) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ float smem[];
+    float* mb = smem;                          // M(J,I):  mb[jj][ii]
+    float* tb = smem + kTS * kTP;              // T(J,I):  tb[jj][ii]
+    float* sS = tb + kTS * kTP;                // S[ii][jj], then T(I,J): ta[ii][jj]
+    float* rI = sS + kTS * kTP;
+    float* rJ = rI + kTS;
+    float* dI = rJ + kTS;
+    float* dJ = dI + kTS;
+    float* pout = dJ + kTS;                    // [2][64]: this pair's row part (rows of I, slot J) and column part (rows of J, slot I)
+    const int pairs = T * (T + 1) / 2;
+    const int rank = (int)blockIdx.x;          // = rank in the cluster (cluster = the grid's x extent)
+    const bool live = rank < pairs;
+    const size_t base = (size_t)blockIdx.y * n * n;
+    mx += base; Tg += base; dmx += base;
+    if (Tg2) Tg2 += base;
+    r += (size_t)blockIdx.y * n;
+    int I = 0, J = 0;
+    if (live) tile_pair_of(rank, T, I, J);
+    const int I0 = I * kTS, J0 = J * kTS;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float4 tA[4];
+    uint32_t sa = 0u, sb = 0u;                 // PRE: 2-bit signs of mx(I,J) / mx(J,I) at this thread's 16 + 16 positions
+    if (live) {
+        float4 ma[4], vmb[4], vtb[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            ma[p] = ld4_masked(mx, n, I0 + ty + 16 * p, J0 + 4 * tx);
+            vmb[p] = ld4_masked(mx, n, J0 + ty + 16 * p, I0 + 4 * tx);
+            tA[p] = ld4_masked2(Tg, Tg2, n, I0 + ty + 16 * p, J0 + 4 * tx);
+            vtb[p] = ld4_masked2(Tg, Tg2, n, J0 + ty + 16 * p, I0 + 4 * tx);
+        }
+        if (threadIdx.x < kTS) rI[threadIdx.x] = (I0 + threadIdx.x < n) ? r[I0 + threadIdx.x] : 0.f;
+        else if (threadIdx.x < 2 * kTS) rJ[threadIdx.x - kTS] = (J0 + threadIdx.x - kTS < n) ? r[J0 + threadIdx.x - kTS] : 0.f;
+        if (PRE) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float a4[4] = {ma[p].x, ma[p].y, ma[p].z, ma[p].w}, b4[4] = {vmb[p].x, vmb[p].y, vmb[p].z, vmb[p].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { sa |= sign_code(a4[u]) << (2 * (4 * p + u)); sb |= sign_code(b4[u]) << (2 * (4 * p + u)); }
+                const int ra = I0 + ty + 16 * p, ca = J0 + 4 * tx, rb = J0 + ty + 16 * p, cb = I0 + 4 * tx;
+                ma[p] = (ra >= n || ca >= n) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                        : make_float4(pre_value<1>(a4[0], ra, ca), pre_value<1>(a4[1], ra, ca + 1), pre_value<1>(a4[2], ra, ca + 2), pre_value<1>(a4[3], ra, ca + 3));
+                vmb[p] = (rb >= n || cb >= n) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                         : make_float4(pre_value<1>(b4[0], rb, cb), pre_value<1>(b4[1], rb, cb + 1), pre_value<1>(b4[2], rb, cb + 2), pre_value<1>(b4[3], rb, cb + 3));
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) { st_tile(mb, ty + 16 * p, 4 * tx, vmb[p]); st_tile(tb, ty + 16 * p, 4 * tx, vtb[p]); }
+        __syncthreads();
+        // S[ii][jj] = T[i][j] M[j][i] + T[j][i] M[i][j]
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int ii = ty + 16 * p;
+            const float a4[4] = {ma[p].x, ma[p].y, ma[p].z, ma[p].w};
+            const float t4[4] = {tA[p].x, tA[p].y, tA[p].z, tA[p].w};
+            float4 o;
+            float* op = &o.x;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int jj = 4 * tx + u;
+                op[u] = t4[u] * mb[jj * kTP + ii] + tb[jj * kTP + ii] * a4[u];
+            }
+            st_tile(sS, ii, 4 * tx, o);
+        }
+        __syncthreads();
+        if (threadIdx.x < kTS) {
+            const int ii = threadIdx.x;
+            float acc = 0.f;
+            for (int jj = 0; jj < kTS; ++jj) acc = fmaf(sS[ii * kTP + jj], rJ[jj], acc);
+            pout[ii] = acc;
+        } else if (threadIdx.x < 2 * kTS) {
+            const int jj = threadIdx.x - kTS;
+            float acc = 0.f;
+            if (I != J) for (int ii = 0; ii < kTS; ++ii) acc = fmaf(sS[ii * kTP + jj], rI[ii], acc);
+            pout[kTS + jj] = acc;
+        }
+    }
+    cluster.sync();                            // every pair's parts are in its CTA's shared memory
+    if (live) {
+        // drho_k = -1/2 r_k^3 sum over the slots sl = 0 .. T-1 (fixed order) of the part the pair {R, sl} holds for tile row R
+        if (threadIdx.x < 2 * kTS) {
+            const bool second = threadIdx.x >= kTS;
+            const int R = second ? J : I, k = threadIdx.x - (second ? kTS : 0);
+            float acc = 0.f;
+            for (int sl = 0; sl < T; ++sl) {
+                const int pi = min(R, sl), pj = max(R, sl);
+                const float* remote = cluster.map_shared_rank(pout, tile_pair_rank(pi, pj, T));
+                acc += remote[(R <= sl ? 0 : kTS) + k];       // rows of I (slot J = sl)  /  rows of J (slot I = sl)
+            }
+            const float rk = second ? rJ[k] : rI[k];
+            (second ? dJ : dI)[k] = -0.5f * rk * rk * rk * acc;
+        }
+        // T(I,J) into shared memory for the mirror tile (S is consumed)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) st_tile(sS, ty + 16 * p, 4 * tx, tA[p]);
+    }
+    cluster.barrier_arrive();                  // this CTA has read its peers' parts (the matching wait is at the end: nobody exits before)
+    if (live) {
+        __syncthreads();
+        const float* ta = sS;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int ii = ty + 16 * p, i = I0 + ii;
+            if (i < n && J0 + 4 * tx < n) {
+                const float ri = rI[ii], di = dI[ii];
+                float4 o;
+                float* op = &o.x;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int jj = 4 * tx + u;
+                    float gv = (tb[jj * kTP + ii] * ri) * rJ[jj] + di;
+                    if (PRE) gv = (i == J0 + jj) ? 0.f : gv * sign_of_code((sa >> (2 * (4 * p + u))) & 3u);
+                    op[u] = gv;
+                }
+                *reinterpret_cast<float4*>(dmx + (size_t)i * n + J0 + 4 * tx) = o;
+            }
+            if (I != J) {
+                const int jj = ty + 16 * p, j = J0 + jj;
+                if (j < n && I0 + 4 * tx < n) {
+                    const float rj = rJ[jj], dj = dJ[jj];
+                    float4 o;
+                    float* op = &o.x;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int ii2 = 4 * tx + u;
+                        float gv = (ta[ii2 * kTP + jj] * rj) * rI[ii2] + dj;
+                        if (PRE) gv = (j == I0 + ii2) ? 0.f : gv * sign_of_code((sb >> (2 * (4 * p + u))) & 3u);
+                        op[u] = gv;
+                    }
+                    *reinterpret_cast<float4*>(dmx + (size_t)j * n + I0 + 4 * tx) = o;
+                }
+            }
+        }
+    }
+    cluster.barrier_wait();
+}
+
 __global__ void abs_diag1_kernel(const float* __restrict__ x, float* __restrict__ out,
                                  long long total, int n) {
     const long long nn = (long long)n * n;
@@ -822,6 +981,32 @@ extern "C" int gsr_normalize_adj_bwd_tiles2(const float* mx, const float* r, con
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int T = (n + kTS - 1) / kTS;
+    if (g_norm_bwd_cluster && T * (T + 1) / 2 <= kNormCluster) {
+        // one pass: the tile pairs of a subject as a cluster of 16 CTAs (opt-in size); a refused launch falls back for good
+        static bool refused = false;
+        if (!refused) {
+            const size_t smemc = (3 * kTS * kTP + 6 * kTS) * sizeof(float);
+            auto kern = pre ? normalize_bwd_cluster_kernel<1> : normalize_bwd_cluster_kernel<0>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemc);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e == cudaSuccess) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(kNormCluster, batch, 1);
+                cfg.blockDim = dim3(kTileThreads, 1, 1);
+                cfg.dynamicSmemBytes = smemc;
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = kNormCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                e = cudaLaunchKernelEx(&cfg, kern, mx, r, grad_out, grad_out2, grad_mx, n, T);
+            }
+            if (e == cudaSuccess) return launched("normalize_adj_bwd_cluster");
+            cudaGetLastError();
+            refused = true;
+        }
+    }
     float* part = workspace;
     float* drho = workspace + (size_t)batch * T * n;
     const size_t smem1 = (3 * kTS * kTP + 2 * kTS) * sizeof(float), smem2 = (2 * kTS * kTP + 4 * kTS) * sizeof(float);

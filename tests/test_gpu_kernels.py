@@ -524,6 +524,36 @@ def test_tcgemm_dual_product(cuda_pkg, K, batch, k2):
         K.bgemm_dual(A1, B1, A2[:, :200].contiguous(), B2, transB=True)         # the two products differ in shape
 
 
+@pytest.mark.parametrize("n,batch", [(268, 7), (160, 3), (64, 2), (12, 5), (300, 2), (320, 1)])
+def test_normalize_bwd_cluster_kernel(cuda_pkg, K, n, batch):
+    """The one-pass normalise backward (the tile pairs of a subject as a cluster of 16 CTAs exchanging their partial sums
+    through distributed shared memory; csrc/elementwise.cu; a switch, measured slower than the default) is BIT identical to the three launches it replaces (partial,
+    drho, apply): one and two incoming gradients, pre = 0 / 1 with negative entries, an exact zero (sgn 0) and a zero row sum
+    (r = 0) in the data, and against the CPU oracle's autograd."""
+    g = torch.Generator(device="cuda").manual_seed(700 + n)
+    mx = torch.randn(batch, n, n, device="cuda", generator=g)
+    mx[0, 1, 0] = 0.0
+    pos = mx.abs() + 0.05
+    if n > 4:
+        pos[batch - 1, 3, :] = 0.0                                  # a zero row: r = 0 (the reference's inf -> 0 rule)
+    g1 = torch.randn(batch, n, n, device="cuda", generator=g); g2 = torch.randn(batch, n, n, device="cuda", generator=g)
+    for pre, x in ((True, mx), (False, pos)):
+        _, r, _ = K.normalize_adj_fwd(x, pre=pre)
+        got = {}
+        for cl in (0, 1):
+            cuda_pkg.set_tuning("normalize_bwd_cluster", cl)
+            try:
+                got[cl] = (K.normalize_adj_bwd(x, r, g1, pre=pre), K.normalize_adj_bwd(x, r, g1, pre=pre, grad_out2=g2))
+            finally:
+                cuda_pkg.set_tuning("normalize_bwd_cluster", 0)
+        assert torch.equal(got[0][0], got[1][0]) and torch.equal(got[0][1], got[1][1]), (n, pre)
+    if batch > 1:                                                   # subject 0 has no zero row (torch's autograd gives NaN there)
+        xr = pos[0].cpu().clone().requires_grad_(True)
+        (O.normalize_adj(xr) * g1[0].cpu()).sum().backward()
+        _, r, _ = K.normalize_adj_fwd(pos[:1], pre=False)
+        assert torch.allclose(K.normalize_adj_bwd(pos[:1], r, g1[:1])[0].cpu(), xr.grad, rtol=1e-5, atol=2e-6)
+
+
 def test_normalize_bwd_two_gradients(cuda_pkg, K):
     """gsr_normalize_adj_bwd_tiles2: the incoming gradient given as two tensors, summed as the passes read them, is BIT
     identical to the backward of their materialised fp32 sum (pre = 0 and pre = 1; 268 nodes = the tile path, 30 nodes =

@@ -4,6 +4,8 @@ import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 pkg = importlib.import_module("fmri-connectivity-super-resolution_b200"); K = pkg.kernels
+for kv in os.environ.get("GSR_TUNE", "").split(","):           # e.g. GSR_TUNE=normalize_bwd_cluster=1
+    if kv: pkg.set_tuning(kv.split("=")[0], int(kv.split("=")[1]))
 B = int(os.environ.get("GSR_B", "1024"))
 g = torch.Generator(device="cuda").manual_seed(2)
 x = torch.rand(B, 268, 268, device="cuda", generator=g) + 0.01; g1 = torch.randn(B, 268, 268, device="cuda", generator=g); g2 = torch.randn(B, 268, 268, device="cuda", generator=g)
