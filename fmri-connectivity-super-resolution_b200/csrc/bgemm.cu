@@ -42,7 +42,7 @@ extern int g_eigh_chunks;
 extern int g_eigh_k2_warps;
 extern int g_eigh_k1_regblocks;
 extern int g_norm_bwd_cluster;
-extern int g_eigh_q_in_k1;
+extern int g_eigh_q_launch;
 namespace tc { extern int g_pairs, g_tail, g_dual, g_tma, g_utccp, g_mn_partial, g_pf_ahead, g_tmem_a, g_cluster_release, g_partial_head, g_reduce_simt_tails; }
 
 struct GemmParams {
@@ -312,7 +312,7 @@ extern "C" int gsr_set_tuning(const char* key, int value) {
     if (!strcmp(key, "eigh_ql_max_iter")) { gsr::g_eigh_ql_max_iter = value; return 0; }
     if (!strcmp(key, "eigh_k2_warps")) { gsr::g_eigh_k2_warps = value; return 0; }
     if (!strcmp(key, "eigh_k1_regblocks")) { gsr::g_eigh_k1_regblocks = value; return 0; }
-    if (!strcmp(key, "eigh_q_in_k1")) { gsr::g_eigh_q_in_k1 = value; return 0; }
+    if (!strcmp(key, "eigh_q_launch")) { gsr::g_eigh_q_launch = value; return 0; }
     if (!strcmp(key, "normalize_bwd_cluster")) { gsr::g_norm_bwd_cluster = value; return 0; }
     if (!strcmp(key, "eigh_chunks")) { gsr::g_eigh_chunks = value; return 0; }
     if (!strcmp(key, "eigh_k2_lanes")) { gsr::g_eigh_k2_lanes = value; return 0; }

@@ -45,9 +45,8 @@ int g_eigh_chunks = 8;          // gsr_set_tuning("eigh_chunks", k): the n <= 16
                                 // chunks on internal streams (K2 of a chunk under K1 / K3 of the others); 0 or 1 = one launch per stage
 int g_eigh_k1_regblocks = 8;   // gsr_set_tuning("eigh_k1_regblocks", 8|9|10): 16-column blocks of a row that K1 keeps in registers (the rest in
                                 // shared memory); 10 = the whole row, which leaves ptxas 8 registers for everything else (round 2, first sessions)
-int g_eigh_q_in_k1 = 2;         // gsr_set_tuning("eigh_q_in_k1", 0|1|2): who forms Q = H_{n-1} ... H_1.  0 = K3, in front of its rotation replay (one
-                                // launch per stage always does this unless 1 is asked for); 1 = K1 itself, after it has published (d, e); 2 = a launch
-                                // of its own right behind K1 (chunked pipeline only, the default there): K3 then only replays the rotations
+int g_eigh_q_launch = 1;        // gsr_set_tuning("eigh_q_launch", 0|1): chunked pipeline: Q = H_{n-1} ... H_1 formed by a launch of its own right behind K1
+                                // (default; K3 then only replays the rotations) / by K3 in front of its rotation replay (one launch per stage: always K3)
 int g_eigh_redo = 1;            // gsr_set_tuning("eigh_redo_failed", 0|1): Jacobi pass over the graphs the QL iteration gave up on
                                 // (info == -2), in the same stream (default); 0 leaves them flagged with NaN results
 namespace tq {
@@ -61,7 +60,6 @@ __host__ __device__ inline int ldv_of(int n) { return n <= MAXN ? LDV : LDVB; }
 constexpr int LDZ = 161;                 // K3 epilogue: column pitch in shared memory, odd
 constexpr int BLK = 64;                  // rotations per cp.async block
 constexpr int STAGES = 3;
-constexpr int kQDone = 40;                 // chunk_done[kQDone + c]: graphs of chunk c whose Q is written (K1 with form_q)
 
 
 
@@ -146,17 +144,16 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // hold the broadcast operands of a whole block, loaded before the block's FMAs.  Same arithmetic in the same order:
 // the variants are bit identical (tools/eigh_k1_ab.py).  Measured, 1024 graphs, one launch per stage: the decomposition
 // 5.04 ms (RB = 10) -> 4.83 (9) -> 4.63 (8, four LDS.128 in flight: the default); as the chunked pipeline 3.89 -> 3.78.
-template <int RB>
-__global__ void __launch_bounds__(MAXN, 2)
+template <int RB, int MINB>
+__global__ void __launch_bounds__(MAXN, MINB)
 tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* __restrict__ Uout,
-               int32_t* __restrict__ info, const Work wk, int n, int chunk_graphs, int form_q) {
+               int32_t* __restrict__ info, const Work wk, int n, int chunk_graphs) {
     constexpr int RC = 16 * RB;                              // columns in registers
     constexpr int TC = MAXN - RC;                            // columns in shared memory
     __shared__ __align__(16) float tile[5 * 176];            // xbuf[2][176], vbuf, wbuf, pbuf
     __shared__ __align__(16) float red[8];
     __shared__ float dd[MAXN], ee[MAXN];
     __shared__ float tail[(TC > 0 ? TC : 1) * MAXN];         // [column - RC][thread]
-    __shared__ __align__(16) float qring[(MAXN / 32) * STAGES * 176];       // Q formation: per warp, 3 reflector rows in flight
     float* xbuf = tile;                    // [2][176]  published pivot row (double buffered by step parity)
     float* vbuf = tile + 2 * 176;          // [176]
     float* wbuf = vbuf + 176;              // [176]
@@ -199,7 +196,7 @@ tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* _
         if (tid == 0) { info[g] = -1; wk.counts[4 * g + 0] = 0; wk.counts[4 * g + 1] = 0; wk.counts[4 * g + 2] = -1; }
         if (chunk_graphs > 0) {                                        // chunked pipeline: this graph is done (see the end of the kernel)
             __syncthreads();
-            if (tid == 0) { __threadfence(); atomicAdd(wk.chunk_done + g / chunk_graphs, 1); atomicAdd(wk.chunk_done + kQDone + g / chunk_graphs, 1); }
+            if (tid == 0) { __threadfence(); atomicAdd(wk.chunk_done + g / chunk_graphs, 1); }
         }
         return;
     }
@@ -392,122 +389,6 @@ tridiag_kernel(const float* __restrict__ Ain, float* __restrict__ Wout, float* _
         __syncthreads();
         if (tid == 0) { __threadfence(); atomicAdd(wk.chunk_done + g / chunk_graphs, 1); }
     }
-    if (!form_q) return;
-
-    // ---- Q = H_{n-1} ... H_1, row `tid` of it (e_r^T H_{n-1} ... H_1, thread-local), AFTER (d, e) went out: the QL
-    //      iteration of this graph's chunk (K2: a latency chain of ~1.3 ms that nothing can shorten) starts while the
-    //      rows of Q are formed here, and K3 only has the rotations left to replay when the chain ends.  The matrix is
-    //      dead: z takes its registers (and its shared-memory columns); the reflectors come back from global memory
-    //      (written by this CTA, L1 / L2 hits) through a per-warp cp.async ring, so no CTA barrier is needed.  Same
-    //      arithmetic in the same order as K3's own Q formation: bit identical.
-    __syncthreads();
-    {
-        float z[RC];
-#pragma unroll
-        for (int j = 0; j < RC; ++j) z[j] = (j == tid && tid < n) ? 1.0f : 0.0f;
-#pragma unroll
-        for (int c = 0; c < TC; ++c) mytail[c * MAXN] = (RC + c == tid && tid < n) ? 1.0f : 0.0f;
-        float* ring = qring + w * (STAGES * 176);
-        auto issue = [&](int k) {
-            if (k >= 1) {
-                const float* src = Vg + (size_t)k * LDV;
-                float* dst = ring + (k % STAGES) * 176;
-                cp_async16(dst + 4 * lane, src + 4 * lane);
-                if (lane < LDV / 4 - 32) cp_async16(dst + 4 * (lane + 32), src + 4 * (lane + 32));
-            }
-            cp_async_commit();
-        };
-        issue(n - 1);
-        issue(n - 2);
-        for (int k = n - 1; k >= 1; --k) {
-            cp_async_wait<1>();
-            __syncwarp();                                              // row k landed; every lane is done with row k + 1
-            issue(k - 2);                                              // stage (k + 1) % 3: consumed one step ago
-            const float* vr = ring + (k % STAGES) * 176;
-            const float tau = vr[MAXN];
-            if (tau != 0.f) {                                          // uniform
-                const float4* V4 = reinterpret_cast<const float4*>(vr);
-                float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll
-                for (int cb = 0; cb < RB; ++cb) {
-                    if (16 * cb < k) {
-                        float4 v[4];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) v[c] = V4[4 * cb + c];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            q0 = fmaf(z[16 * cb + 4 * c + 0], v[c].x, q0);
-                            q1 = fmaf(z[16 * cb + 4 * c + 1], v[c].y, q1);
-                            q2 = fmaf(z[16 * cb + 4 * c + 2], v[c].z, q2);
-                            q3 = fmaf(z[16 * cb + 4 * c + 3], v[c].w, q3);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int cb = RB; cb < NB; ++cb) {
-                    if (16 * cb < k) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const float4 v = V4[4 * cb + c];
-                            const float* t4 = mytail + (16 * (cb - RB) + 4 * c) * MAXN;
-                            q0 = fmaf(t4[0], v.x, q0);
-                            q1 = fmaf(t4[MAXN], v.y, q1);
-                            q2 = fmaf(t4[2 * MAXN], v.z, q2);
-                            q3 = fmaf(t4[3 * MAXN], v.w, q3);
-                        }
-                    }
-                }
-                const float sq = -tau * ((q0 + q1) + (q2 + q3));
-#pragma unroll
-                for (int cb = 0; cb < RB; ++cb) {
-                    if (16 * cb < k) {
-                        float4 v[4];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) v[c] = V4[4 * cb + c];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            z[16 * cb + 4 * c + 0] = fmaf(sq, v[c].x, z[16 * cb + 4 * c + 0]);
-                            z[16 * cb + 4 * c + 1] = fmaf(sq, v[c].y, z[16 * cb + 4 * c + 1]);
-                            z[16 * cb + 4 * c + 2] = fmaf(sq, v[c].z, z[16 * cb + 4 * c + 2]);
-                            z[16 * cb + 4 * c + 3] = fmaf(sq, v[c].w, z[16 * cb + 4 * c + 3]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int cb = RB; cb < NB; ++cb) {
-                    if (16 * cb < k) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const float4 v = V4[4 * cb + c];
-                            float* t4 = mytail + (16 * (cb - RB) + 4 * c) * MAXN;
-                            t4[0] = fmaf(sq, v.x, t4[0]);
-                            t4[MAXN] = fmaf(sq, v.y, t4[MAXN]);
-                            t4[2 * MAXN] = fmaf(sq, v.z, t4[2 * MAXN]);
-                            t4[3 * MAXN] = fmaf(sq, v.w, t4[3 * MAXN]);
-                        }
-                    }
-                }
-            }
-        }
-        cp_async_wait<0>();
-        if (tid < n) {
-            float* Zg = wk.Zt + (size_t)g * n * n;                     // Zt[column][row]: coalesced over the warp
-#pragma unroll
-            for (int j = 0; j < RC; ++j) {
-                if (j < n) Zg[(size_t)j * n + tid] = z[j];
-            }
-#pragma unroll
-            for (int c = 0; c < TC; ++c) {
-                if (RC + c < n) Zg[(size_t)(RC + c) * n + tid] = mytail[c * MAXN];
-            }
-        }
-    }
-    if (chunk_graphs > 0) {
-        // second count of the chunk: Q is in global memory.  The chunk's K2 CTA waits for it before it exits, so K3 -- next
-        // on the chunk's stream -- is ordered after these writes.
-        __syncthreads();
-        if (tid == 0) { __threadfence(); atomicAdd(wk.chunk_done + kQDone + g / chunk_graphs, 1); }
-    }
 }
 
 // ------------------------------------------------------------------------------------ K2
@@ -638,7 +519,7 @@ tql_scalar_kernel(const Work wk, int n, int batch, int max_iter) {
 // Stream / header format and all arithmetic of a rotation are those of tql_scalar_kernel.
 constexpr int K2L_WARPS = 4;            // at most one warp per scheduler; the launcher picks g_eigh_k2_warps <= 4 (they share the SM's LSU)
 __global__ void __launch_bounds__(32 * K2L_WARPS)
-tql_scalar_lanes_kernel(const Work wk, int n, int g_first, int batch, int max_iter, const int* wait_count, int wait_target, int wait_q) {
+tql_scalar_lanes_kernel(const Work wk, int n, int g_first, int batch, int max_iter, const int* wait_count, int wait_target) {
     extern __shared__ __align__(16) float sm_all[];
     // graphs [g_first, batch): warp (blockIdx.x, wl) takes 32 of them.  Chunked pipeline: this CTA has been resident since the
     // fork (it owns its SM: the launch asks for all of the shared memory) and polls the number of graphs of its chunk whose
@@ -804,20 +685,6 @@ tql_scalar_lanes_kernel(const Work wk, int n, int g_first, int batch, int max_it
             for (int j = lane; j < n; j += 32) wk.d[(size_t)gi * n + j] = sm[(8 + j) * 32 + gg];
     }
     if (live) { int* cnt = wk.counts + 4 * g; cnt[0] = nit; cnt[1] = pos; cnt[2] = status; }
-    if (wait_count && wait_q) {
-        // K1 forms Q after it has released (d, e): K3 -- next on this stream -- needs it, so this warp does not leave before
-        // every graph of the chunk has its Q in global memory (normally long done: ~0.1 ms of work against the ~1.3 ms chain)
-        if (lane == 0) {
-            for (unsigned spin = 0;; ++spin) {
-                int v;
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(wait_count + kQDone) : "memory");
-                if (v >= wait_target) break;
-                if (spin > (1u << 22)) { printf("eigh K2: poll timeout (Q), block %d count %d target %d\n", (int)blockIdx.x, v, wait_target); __trap(); }
-                __nanosleep(200);
-            }
-        }
-        __syncwarp();
-    }
 }
 
 // Gate in front of K1 (chunked pipeline): one thread waits -- for at most ~60 us -- until the K2 CTAs have checked in as
@@ -898,7 +765,7 @@ __device__ __forceinline__ void form_q_row(float (&z)[MAXN + 1], const Work& wk,
     __syncwarp();
 }
 
-// Kq (chunked pipeline, eigh_q_in_k1 = 2): Q of every graph as its own launch right behind K1, written to Zt[column][row];
+// Kq (chunked pipeline, eigh_q_launch = 1): Q of every graph as its own launch right behind K1, written to Zt[column][row];
 // K3 then only replays the rotations.  It fills the SMs between the end of K1 and the end of the first chunks' rotation
 // chains (K2), which would otherwise idle, and takes the Q formation off the critical path K1 -> K2 -> K3 of the last chunk.
 __global__ void __launch_bounds__(32 * K3_WARPS, 2)
@@ -938,7 +805,7 @@ tql_apply_kernel(const Work wk, int n, int units_per_graph, int total_units, int
     // ---- Z = Q = H_{n-1} ... H_1, row `tid` of it: e_r^T H_{n-1} ... H_1, thread-local
     float z[MAXN + 1];
     if (q_from_zt) {
-        // K1 formed Q (eigh_q_in_k1): row `tid` of it comes back from Zt[column][row], coalesced over the warp
+        // Kq formed Q (eigh_q_launch): row `tid` of it comes back from Zt[column][row], coalesced over the warp
         const float* Zg = wk.Zt + (size_t)g * n * n;
 #pragma unroll
         for (int j = 0; j <= MAXN; ++j) z[j] = (j < n && tid < n) ? Zg[(size_t)j * n + tid] : 0.0f;
@@ -1433,19 +1300,20 @@ using namespace gsr;
 
 // K1 with g_eigh_k1_regblocks 16-column blocks of every row in registers
 static int launch_k1(const float* A, float* w, float* U, int32_t* info, const gsr::tq::Work& wk, int batch, int threads, int n,
-                     int chunk_graphs, int fq, cudaStream_t st) {
+                     int chunk_graphs, cudaStream_t st) {
     using namespace gsr;
-    if (g_eigh_k1_regblocks >= 10) tq::tridiag_kernel<10><<<batch, threads, 0, st>>>(A, w, U, info, wk, n, chunk_graphs, fq);
-    else if (g_eigh_k1_regblocks == 9) tq::tridiag_kernel<9><<<batch, threads, 0, st>>>(A, w, U, info, wk, n, chunk_graphs, fq);
-    else tq::tridiag_kernel<8><<<batch, threads, 0, st>>>(A, w, U, info, wk, n, chunk_graphs, fq);
+    if (g_eigh_k1_regblocks >= 10) tq::tridiag_kernel<10, 2><<<batch, threads, 0, st>>>(A, w, U, info, wk, n, chunk_graphs);
+    else if (g_eigh_k1_regblocks == 9) tq::tridiag_kernel<9, 2><<<batch, threads, 0, st>>>(A, w, U, info, wk, n, chunk_graphs);
+    else if (g_eigh_k1_regblocks == 8) tq::tridiag_kernel<8, 2><<<batch, threads, 0, st>>>(A, w, U, info, wk, n, chunk_graphs);
+    else if (g_eigh_k1_regblocks == 7) tq::tridiag_kernel<7, 3><<<batch, threads, 0, st>>>(A, w, U, info, wk, n, chunk_graphs);     // 3 CTAs per SM: 128 registers
+    else tq::tridiag_kernel<6, 3><<<batch, threads, 0, st>>>(A, w, U, info, wk, n, chunk_graphs);
     return launched("eigh_tridiag");
 }
 
 // K2 for graphs [g_first, g_end): lane = graph for batches that fill warps, one warp per graph otherwise.  `hog`: ask for all of an
 // SM's shared memory so that the CTA runs alone on it (chunked pipeline); wait_count / wait_target: see the kernel.
 static int launch_k2(const gsr::tq::Work& wk, int n, int g_first, int g_end, cudaStream_t st, bool hog = false,
-                     const int* wait_count = nullptr, int wait_target = 0, int* ctas_launched = nullptr, bool lanes_unchunked = true,
-                     int wait_q = 0) {
+                     const int* wait_count = nullptr, int wait_target = 0, int* ctas_launched = nullptr, bool lanes_unchunked = true) {
     using namespace gsr;
     const int count = g_end - g_first;
     // lane = graph: always inside the chunked pipeline (wait_count); for one launch per stage it is never faster than one warp
@@ -1458,7 +1326,7 @@ static int launch_k2(const gsr::tq::Work& wk, int n, int g_first, int g_end, cud
         if (e != cudaSuccess) return fail((int)e, "eigh_tridiag: cudaFuncSetAttribute failed");
         const int ctas = (count + 32 * wpc - 1) / (32 * wpc);
         if (ctas_launched) *ctas_launched += ctas;
-        tq::tql_scalar_lanes_kernel<<<ctas, 32 * wpc, smem, st>>>(wk, n, g_first, g_end, g_eigh_ql_max_iter, wait_count, wait_target, wait_q);
+        tq::tql_scalar_lanes_kernel<<<ctas, 32 * wpc, smem, st>>>(wk, n, g_first, g_end, g_eigh_ql_max_iter, wait_count, wait_target);
         return launched("eigh_tql_scalar_lanes");
     }
     tq::Work w1 = wk;                                        // the one-warp kernel indexes from 0
@@ -1498,8 +1366,9 @@ ChunkPool* chunk_pool() {
     // CTA is resident and polling for exactly that kernel (K1) -- so every kernel of the pipeline is loaded here, before any
     // of them can wait for another.
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, gsr::tq::tridiag_kernel<8>) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tridiag_kernel<9>) != cudaSuccess ||
-        cudaFuncGetAttributes(&fa, gsr::tq::tridiag_kernel<10>) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tql_scalar_lanes_kernel) != cudaSuccess ||
+    if (cudaFuncGetAttributes(&fa, gsr::tq::tridiag_kernel<8, 2>) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tridiag_kernel<9, 2>) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa, gsr::tq::tridiag_kernel<10, 2>) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tridiag_kernel<7, 3>) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa, gsr::tq::tridiag_kernel<6, 3>) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tql_scalar_lanes_kernel) != cudaSuccess ||
         cudaFuncGetAttributes(&fa, gsr::tq::k2_resident_gate_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tql_apply_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::form_q_kernel) != cudaSuccess || cudaFuncGetAttributes(&fa, gsr::tq::tql_finish_kernel) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
@@ -1526,6 +1395,15 @@ extern "C" __attribute__((visibility("default"))) int gsr_eigh_timeline_read(flo
 #else
 #define GSR_TR(stage) do { } while (0)
 #endif
+
+// Kq: Q of graphs [0, batch) into Zt
+static int launch_form_q(const gsr::tq::Work& wk, int batch, int threads, int n, cudaStream_t st) {
+    using namespace gsr;
+    const int upg = threads / 32, units = upg * batch;
+    const size_t smemq = (size_t)tq::K3_WARPS * tq::RING_FLOATS * sizeof(float);
+    tq::form_q_kernel<<<(units + tq::K3_WARPS - 1) / tq::K3_WARPS, 32 * tq::K3_WARPS, smemq, st>>>(wk, n, upg, units);
+    return launched("eigh_form_q");
+}
 
 // K3 + K4 of the n <= 160 route for graphs [g0, g0 + nb) on stream st
 static int launch_small_apply(float* w, float* U, int32_t* info, const gsr::tq::Work& full, int g0, int nb, int n,
@@ -1583,16 +1461,19 @@ static int eigh_small_segment(const float* A, float* w, float* U, int32_t* info,
 #endif
     if (nchunks == 1) {
         GSR_TR(0);
-        const int qk1 = g_eigh_q_in_k1 == 1 ? 1 : 0;             // a launch of its own only pays inside the pipeline
-        if ((rc = launch_k1(A, w, U, info, wk, batch, threads, n, 0, qk1, st))) return rc;
+        if ((rc = launch_k1(A, w, U, info, wk, batch, threads, n, 0, st))) return rc;
         GSR_TR(1);
         if ((rc = launch_k2(wk, n, 0, batch, st, false, nullptr, 0, nullptr, g_eigh_k2_lanes >= 2))) return rc;      // one warp per graph unless forced
-        if ((rc = launch_small_apply(w, U, info, wk, 0, batch, n, canonical_sign, qk1, st))) return rc;
+        // Q formed by K3: a launch of its own only pays inside the pipeline (eigh_q_launch = 2 forces it here too: profilers
+        // serialise kernels, so this is how Kq and the rotation-only K3 are captured)
+        const int qown = g_eigh_q_launch >= 2 ? 1 : 0;
+        if (qown && (rc = launch_form_q(wk, batch, threads, n, st))) return rc;
+        if ((rc = launch_small_apply(w, U, info, wk, 0, batch, n, canonical_sign, qown, st))) return rc;
     } else {
         if (cudaMemsetAsync(wk.chunk_done, 0, 64 * sizeof(int), st) != cudaSuccess) return fail((int)cudaGetLastError(), "eigh_tridiag: cudaMemsetAsync failed");
         if (cudaEventRecord(pool->fork, st) != cudaSuccess) return fail((int)cudaGetLastError(), "eigh_tridiag: cudaEventRecord failed");
         int forked = 0, k2_ctas = 0;
-        const int qmode = g_eigh_q_in_k1 < 0 ? 0 : std::min(g_eigh_q_in_k1, 2);
+        const int qmode = g_eigh_q_launch ? 1 : 0;
         for (int c = 0; c < nchunks && !rc; ++c) {
             const int g0 = c * per, g1 = std::min(batch, g0 + per);
             if (cudaStreamWaitEvent(pool->s[c], pool->fork, 0) != cudaSuccess) { rc = fail((int)cudaGetLastError(), "eigh_tridiag: cudaStreamWaitEvent failed"); break; }
@@ -1600,7 +1481,7 @@ static int eigh_small_segment(const float* A, float* w, float* U, int32_t* info,
 #ifdef GSR_EIGH_TRACE
             g_tr_chunk = c; tr_mark(1, pool->s[c]);
 #endif
-            rc = launch_k2(wk, n, g0, g1, pool->s[c], true, wk.chunk_done + c, g1 - g0, &k2_ctas, true, qmode == 1 ? 1 : 0);
+            rc = launch_k2(wk, n, g0, g1, pool->s[c], true, wk.chunk_done + c, g1 - g0, &k2_ctas);
         }
         if (!rc) {
             tq::k2_resident_gate_kernel<<<1, 1, 0, st>>>(wk.chunk_done + 32, k2_ctas);
@@ -1611,15 +1492,12 @@ static int eigh_small_segment(const float* A, float* w, float* U, int32_t* info,
             g_tr_chunk = 0;
 #endif
             GSR_TR(0);
-            rc = launch_k1(A, w, U, info, wk, batch, threads, n, per, qmode == 1 ? 1 : 0, st);
+            rc = launch_k1(A, w, U, info, wk, batch, threads, n, per, st);
         }
-        if (!rc && qmode == 2) {
+        if (!rc && qmode) {
             // Q of all graphs right behind K1 (it runs while the first chunks' rotation chains are still going); the chunk
             // streams wait for it before their K3
-            const int upg = threads / 32, units = upg * batch;
-            const size_t smemq = (size_t)tq::K3_WARPS * tq::RING_FLOATS * sizeof(float);
-            tq::form_q_kernel<<<(units + tq::K3_WARPS - 1) / tq::K3_WARPS, 32 * tq::K3_WARPS, smemq, st>>>(wk, n, upg, units);
-            rc = launched("eigh_form_q");
+            rc = launch_form_q(wk, batch, threads, n, st);
             if (!rc && cudaEventRecord(pool->qdone, st) != cudaSuccess) rc = fail((int)cudaGetLastError(), "eigh_tridiag: cudaEventRecord failed");
         }
         for (int c = 0; c < nchunks && !rc; ++c) {
@@ -1627,7 +1505,7 @@ static int eigh_small_segment(const float* A, float* w, float* U, int32_t* info,
 #ifdef GSR_EIGH_TRACE
             g_tr_chunk = c;
 #endif
-            if (qmode == 2 && cudaStreamWaitEvent(pool->s[c], pool->qdone, 0) != cudaSuccess) { rc = fail((int)cudaGetLastError(), "eigh_tridiag: cudaStreamWaitEvent failed"); break; }
+            if (qmode && cudaStreamWaitEvent(pool->s[c], pool->qdone, 0) != cudaSuccess) { rc = fail((int)cudaGetLastError(), "eigh_tridiag: cudaStreamWaitEvent failed"); break; }
             rc = launch_small_apply(w, U, info, wk, g0, g1 - g0, n, canonical_sign, qmode ? 1 : 0, pool->s[c]);
         }
         // (on an error the streams forked so far are still joined, so that a capture is not left forked)

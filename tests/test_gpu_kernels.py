@@ -351,20 +351,20 @@ def test_eigh_pipeline_matches_one_launch_per_stage(cuda_pkg):
         cuda_pkg.set_tuning("eigh_chunks", 8); cuda_pkg.set_tuning("eigh_k2_lanes", 1)
         w_p, U_p, i_p = K.eigh_tridiag(A)
         w_p2, U_p2, i_p2 = K.eigh_tridiag(A)
-        # who forms Q = H_{n-1} ... H_1: K3 (0), K1 after it released (d, e) with the second per-chunk count (1), its own
-        # launch behind K1 (2, the default); and the row of K1 entirely in registers (10 blocks) instead of 8 + shared memory
+        # who forms Q = H_{n-1} ... H_1: K3 in front of its rotation replay (0) or a launch of its own behind K1 (1, the
+        # default); and K1 with 10 (the whole row), 9, 7 or 6 of a row's ten 16-column blocks in registers instead of 8
         variants = []
-        for q_mode, rb in ((0, 8), (1, 8), (0, 10), (1, 9)):
-            cuda_pkg.set_tuning("eigh_q_in_k1", q_mode); cuda_pkg.set_tuning("eigh_k1_regblocks", rb)
+        for q_launch, rb in ((0, 8), (0, 10), (1, 9), (1, 7), (0, 6)):
+            cuda_pkg.set_tuning("eigh_q_launch", q_launch); cuda_pkg.set_tuning("eigh_k1_regblocks", rb)
             variants.append(K.eigh_tridiag(A))
-        cuda_pkg.set_tuning("eigh_q_in_k1", 2); cuda_pkg.set_tuning("eigh_k1_regblocks", 8)
+        cuda_pkg.set_tuning("eigh_q_launch", 1); cuda_pkg.set_tuning("eigh_k1_regblocks", 8)
         cuda_pkg.set_tuning("eigh_chunks", 1); cuda_pkg.set_tuning("eigh_k2_lanes", 2)       # lane = graph, one launch per stage
         w_l, U_l, i_l = K.eigh_tridiag(A)
         cuda_pkg.set_tuning("eigh_k2_lanes", 0)                                              # one warp per graph
         w_w, U_w, i_w = K.eigh_tridiag(A)
     finally:
         cuda_pkg.set_tuning("eigh_chunks", 8); cuda_pkg.set_tuning("eigh_k2_lanes", 1)
-        cuda_pkg.set_tuning("eigh_q_in_k1", 2); cuda_pkg.set_tuning("eigh_k1_regblocks", 8)
+        cuda_pkg.set_tuning("eigh_q_launch", 1); cuda_pkg.set_tuning("eigh_k1_regblocks", 8)
     ok = torch.ones(B, dtype=torch.bool); ok[5] = False
     for w_v, U_v, i_v in variants:
         assert torch.equal(w_p[ok], w_v[ok]) and torch.equal(U_p[ok], U_v[ok]) and torch.equal(i_p, i_v)

@@ -1,5 +1,5 @@
-"""K1 (Householder tridiagonalisation, thread = matrix row) with 8 / 9 / 10 of the ten 16-column blocks of a row in
-registers (gsr_set_tuning("eigh_k1_regblocks", k); the rest in shared memory): results of the variants against each
+"""K1 (Householder tridiagonalisation, thread = matrix row) with 6 .. 10 of the ten 16-column blocks of a row in
+registers (6, 7: 3 CTAs per SM at 128 registers) (gsr_set_tuning("eigh_k1_regblocks", k); the rest in shared memory): results of the variants against each
 other (the arithmetic is the same, so bit identity is expected), against float64, and the time of the whole
 decomposition of 1024 graphs of 160 nodes with one launch per stage and as the chunked pipeline."""
 import importlib, os, sys, json
@@ -15,12 +15,12 @@ for n in (1, 2, 17, 100, 127, 128, 129, 143, 144, 145, 159, 160):
     if n >= 17:
         A[3] = A[3] * 1e-12; A[4] = A[4] * 1e9; A[5, 1, n - 1] = float("nan")      # rescaled rows, one NaN in the shared-memory columns
     res = {}
-    for rb in (10, 9, 8):
-        pkg.set_tuning("eigh_k1_regblocks", rb); pkg.set_tuning("eigh_q_in_k1", 0 if rb == 10 else 1)      # 10 also = Q formed in K3
+    for rb in (10, 9, 8, 7, 6):
+        pkg.set_tuning("eigh_k1_regblocks", rb)
         res[rb] = K.eigh_tridiag(A)
     ok = [s for s in range(9) if not (n >= 17 and s == 5)]
-    same = all(torch.equal(res[10][0][ok], res[rb][0][ok]) and torch.equal(res[10][1][ok], res[rb][1][ok]) and torch.equal(res[10][2], res[rb][2]) for rb in (9, 8))
-    print(json.dumps({"n": n, "regblocks_9_8_bit_identical_to_10": bool(same), "info": res[8][2].tolist()}), flush=True)
+    same = all(torch.equal(res[10][0][ok], res[rb][0][ok]) and torch.equal(res[10][1][ok], res[rb][1][ok]) and torch.equal(res[10][2], res[rb][2]) for rb in (9, 8, 7, 6))
+    print(json.dumps({"n": n, "regblocks_9_8_7_6_bit_identical_to_10": bool(same), "info": res[8][2].tolist()}), flush=True)
     keep = [s for s in ok if not (n >= 17 and s in (3, 4))]
     report(f"k1 regblocks=8 n={n}", A[keep], res[8][0][keep], res[8][1][keep], res[8][2][keep])
 
@@ -29,23 +29,23 @@ x = torch.rand(1024, 160, 160, device="cuda", generator=gen); lr = (x + x.transp
 A = pkg.normalize_adj_torch(lr)
 for chunks in (1, 8):
     ref = None
-    for q_in_k1 in (0, 1, 2):
-        for rb in ((10, 9, 8) if q_in_k1 < 2 else (8,)):
-            pkg.set_tuning("eigh_k1_regblocks", rb); pkg.set_tuning("eigh_chunks", chunks); pkg.set_tuning("eigh_q_in_k1", q_in_k1)
+    for q_launch in ((0,) if chunks == 1 else (0, 1)):
+        for rb in (10, 9, 8, 7, 6):
+            pkg.set_tuning("eigh_k1_regblocks", rb); pkg.set_tuning("eigh_chunks", chunks); pkg.set_tuning("eigh_q_launch", q_launch)
             (w, U, info), ms = timed(K.eigh_tridiag, A, reps=5)
-            report(f"tridiag 1024x160 k1_regblocks={rb} q_in_k1={q_in_k1} chunks={chunks}", A, w, U, info, ms)
+            report(f"tridiag 1024x160 k1_regblocks={rb} q_launch={q_launch} chunks={chunks}", A, w, U, info, ms)
             if ref is None: ref = (w, U)
-            else: print(json.dumps({"regblocks": rb, "q_in_k1": q_in_k1, "chunks": chunks, "bit_identical_to_first_of_this_chunking": bool(torch.equal(w, ref[0]) and torch.equal(U, ref[1]))}), flush=True)
-# ragged batches through the pipeline with Q formed in K1 (the second per-chunk count): 32 k + r graphs, a NaN graph in the last chunk
+            else: print(json.dumps({"regblocks": rb, "q_launch": q_launch, "chunks": chunks, "bit_identical_to_first_of_this_chunking": bool(torch.equal(w, ref[0]) and torch.equal(U, ref[1]))}), flush=True)
+# ragged batches through the pipeline with Q formed by its own launch: 32 k + r graphs, a NaN graph in the last chunk
 pkg.set_tuning("eigh_k1_regblocks", 8); pkg.set_tuning("eigh_chunks", 8)
 for B in (384, 400, 777, 1025):
     Ab = A[:B].clone() if B <= 1024 else torch.cat([A, A[:B - 1024]])
     Ab[B - 3, 0, 5] = float("nan")
     out = {}
-    for q_in_k1 in (0, 1, 2):
-        pkg.set_tuning("eigh_q_in_k1", q_in_k1)
-        out[q_in_k1] = K.eigh_tridiag(Ab)
+    for q_launch in (0, 1):
+        pkg.set_tuning("eigh_q_launch", q_launch)
+        out[q_launch] = K.eigh_tridiag(Ab)
     ok = [s for s in range(B) if s != B - 3]
-    print(json.dumps({"batch": B, "q_in_k1_bit_identical": bool(all(torch.equal(out[0][0][ok], out[q][0][ok]) and torch.equal(out[0][1][ok], out[q][1][ok]) and torch.equal(out[0][2], out[q][2]) for q in (1, 2))),
+    print(json.dumps({"batch": B, "q_launch_bit_identical": bool(torch.equal(out[0][0][ok], out[1][0][ok]) and torch.equal(out[0][1][ok], out[1][1][ok]) and torch.equal(out[0][2], out[1][2])),
                       "nan_graph_info": int(out[1][2][B - 3])}), flush=True)
-pkg.set_tuning("eigh_q_in_k1", 2)
+pkg.set_tuning("eigh_q_launch", 1)
