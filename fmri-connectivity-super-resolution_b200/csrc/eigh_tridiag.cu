@@ -826,38 +826,59 @@ tql_apply_kernel(const Work wk, int n, int units_per_graph, int total_units, int
         };
         issue(0);
         issue(1);
-        int pos = 0;
+        // `slot`: where the next 16 rotations sit in the ring (float2 index, = ((pos / BLK) % STAGES) * BLK + pos % BLK for the
+        // running position pos), kept incrementally; `nextblk`: the next 64-rotation block to request.  An iteration ENTERS the
+        // statically indexed stanzas at block hb - 1 through a jump table and falls through down to block lb: one compare per
+        // executed stanza, nothing for the others (the ten-way if chain of the first version, with a division by 3 per stanza
+        // for the ring slot, was ~45 % of this kernel's stall samples: profiles/r2c_ncu_summary_eigh.txt).
+        int slot = 0, nextblk = 2;
         uint32_t h = nit > 0 ? __ldg(hdr) : 0u;
+#define GSR_STANZA(b)                                                                                              \
+        {                                                                                                          \
+            if ((slot & (BLK - 1)) == 0) {                     /* entering a new 64-rotation block */              \
+                cp_async_wait<1>();                                                                                \
+                __syncwarp();                                                                                      \
+                issue(nextblk);                                                                                    \
+                ++nextblk;                                                                                         \
+            }                                                                                                      \
+            const float4* cs4 = reinterpret_cast<const float4*>(cring + slot);                                     \
+            _Pragma("unroll") for (int u = 0; u < 8; ++u) {                                                        \
+                const float4 q = cs4[u];                       /* two rotations: (c, s) of i, (c, s) of i - 1 */   \
+                constexpr int i0 = 16 * (b) + 15;                                                                  \
+                const int i = i0 - 2 * u;                                                                          \
+                /* the running column t enters each product last, so the dependent chain is one FFMA per */       \
+                /* rotation (the products with z[i], z[i-1] are off it) */                                         \
+                float t = z[i + 1];                                                                                \
+                z[i + 1] = fmaf(q.x, t, q.y * z[i]);                                                               \
+                z[i] = fmaf(-q.y, t, q.x * z[i]);                                                                  \
+                t = z[i];                                                                                          \
+                z[i] = fmaf(q.z, t, q.w * z[i - 1]);                                                               \
+                z[i - 1] = fmaf(-q.w, t, q.z * z[i - 1]);                                                          \
+            }                                                                                                      \
+            slot += 16;                                                                                            \
+            if (slot == STAGES * BLK) slot = 0;                                                                    \
+        }
         for (int it = 0; it < nit; ++it) {
             const uint32_t hn = (it + 1 < nit) ? __ldg(hdr + it + 1) : 0u;
             const int lb = (int)(h & 0xffu), hb = (int)((h >> 8) & 0xffu);
-#pragma unroll
-            for (int b = NB - 1; b >= 0; --b) {
-                if (b < hb && b >= lb) {                               // uniform
-                    if ((pos & (BLK - 1)) == 0) {                      // entering a new 64-rotation block
-                        cp_async_wait<1>();
-                        __syncwarp();
-                        issue(pos / BLK + 2);
-                    }
-                    const float4* cs4 = reinterpret_cast<const float4*>(cring + (pos / BLK % STAGES) * BLK + (pos & (BLK - 1)));
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const float4 q = cs4[u];                       // two rotations: (c, s) of i, (c, s) of i - 1
-                        const int i = 16 * b + 15 - 2 * u;
-                        // the running column t enters each product last, so the dependent chain
-                        // is one FFMA per rotation (the products with z[i], z[i-1] are off it)
-                        float t = z[i + 1];
-                        z[i + 1] = fmaf(q.x, t, q.y * z[i]);
-                        z[i] = fmaf(-q.y, t, q.x * z[i]);
-                        t = z[i];
-                        z[i] = fmaf(q.z, t, q.w * z[i - 1]);
-                        z[i - 1] = fmaf(-q.w, t, q.z * z[i - 1]);
-                    }
-                    pos += 16;
+            static_assert(NB == 10, "the stanza switch below lists blocks 9 .. 0");
+            if (hb > lb) {                                                 // uniform
+                switch (min(hb, NB) - 1) {
+                    case 9: GSR_STANZA(9) if (lb == 9) break; [[fallthrough]];
+                    case 8: GSR_STANZA(8) if (lb == 8) break; [[fallthrough]];
+                    case 7: GSR_STANZA(7) if (lb == 7) break; [[fallthrough]];
+                    case 6: GSR_STANZA(6) if (lb == 6) break; [[fallthrough]];
+                    case 5: GSR_STANZA(5) if (lb == 5) break; [[fallthrough]];
+                    case 4: GSR_STANZA(4) if (lb == 4) break; [[fallthrough]];
+                    case 3: GSR_STANZA(3) if (lb == 3) break; [[fallthrough]];
+                    case 2: GSR_STANZA(2) if (lb == 2) break; [[fallthrough]];
+                    case 1: GSR_STANZA(1) if (lb == 1) break; [[fallthrough]];
+                    default: GSR_STANZA(0)
                 }
             }
             h = hn;
         }
+#undef GSR_STANZA
         cp_async_wait<0>();
     }
     if (tid < n) {
