@@ -747,7 +747,7 @@ def run_ours(args):
     #     issues three MMAs per algorithmic product, both stated so that `frac` is against the MEASURED bf16 peak.
     tf32_peak = tf32_best if tf32_best > 0 else bf16_peak / 2.0
     tma_on = backend == "tc"
-    traffic = ncu_traffic("r2b_ncu_summary_tcgemm3.txt", "tcgemm3_kernel") if backend == "tc" else None
+    traffic = ncu_traffic("r2c_ncu_summary_tcgemm3.txt", "tcgemm3_kernel") if backend == "tc" else None
     gemm_roof = {
         "kernel": ("gsr::tc::t3::tcgemm3_kernel (persistent CTA pairs, tcgen05.mma.cta_group::2 kind::tf32, 3xTF32: operands by "
                    "cp.async.bulk.tensor into SWIZZLE_128B / 128B_ATOM_32B tiles, the raw fp32 tile is the hi term, converter warps "
@@ -773,7 +773,7 @@ def run_ours(args):
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (1024 per-subject 256 x 268 x 268 products) from the committed
         # ncu --set full capture; the algorithmic bytes of that launch are 1024 x (256 x 268 + 268 x 268 + 256 x 268) x 4 B = 856 MB
         "traffic": traffic,
-        "traffic_source": "profiles/r2b_ncu_summary_tcgemm3.txt (tools/ncu_summary.py of the ncu --set full capture), first tcgemm3_kernel launch (1024 x 268^3 stacked product: 856 MB algorithmic)",
+        "traffic_source": "profiles/r2c_ncu_summary_tcgemm3.txt (tools/ncu_summary.py of the ncu --set full capture), first tcgemm3_kernel launch (1024 x 268^3 stacked product: 856 MB algorithmic)",
         "unet_simt_products": {"launches": simt_launches, "gflop_per_step": simt_flops / max(args.steps, 1) / 1e9,
                                "note": "Graph U-Net linears (once per step, subject independent) on gsr::bgemm_kernel, "
                                        "side stream under the eigendecomposition; not part of `achieved`"},
@@ -812,9 +812,10 @@ def run_ours(args):
         flops_per_graph = 4.0 * n ** 3 + 6.0 * n * rot_mean
         tflops = flops_per_graph * eigh_graphs / (eigh_ms * 1e-3) / 1e12
         eigh_roof = {
-            "kernel": "gsr::tq::{tridiag,tql_scalar_lanes,tql_apply,tql_finish}_kernel (Householder + implicit QL, one thread per "
-                      "matrix row, rows resident in registers; QL iteration with lane = graph; run as a pipeline: K1 in one launch, "
-                      "K2 CTAs resident on their own SMs polling K1's per-chunk counts, K3 / K4 per 128-graph chunk on internal streams)",
+            "kernel": "gsr::tq::{tridiag,form_q,tql_scalar_lanes,tql_apply,tql_finish}_kernel (Householder + implicit QL, one thread per "
+                      "matrix row, rows resident in registers (K1: 128 of 160 columns, the rest in shared memory); QL iteration with lane = "
+                      "graph; run as a pipeline: K1 in one launch, Q = H_{n-1} ... H_1 as a launch of its own behind it, K2 CTAs resident "
+                      "on their own SMs polling K1's per-chunk counts, K3 (rotation replay) / K4 per 128-graph chunk on internal streams)",
             "timed": "alone on the device, mean of 5 calls of 1024 graphs", "in_step_pass_ms": eigh_pass_ms, "alone_ms": eigh_alone_ms,
             "bound": "fp32", "achieved": tflops, "unit": "TFLOP/s (executed fp32 flops: 4 n^3 + 6 n per plane rotation)",
             "peak": ffma_best, "frac": tflops / ffma_best if ffma_best else None,
@@ -823,8 +824,9 @@ def run_ours(args):
             "us_per_graph": eigh_ms * 1e3 / eigh_graphs if eigh_graphs else None,
             "ql_iterations_mean": float(eigh_info.double().mean()), "rotations_mean": rot_mean,
             "conventional_9n3_tflops": 9.0 * n ** 3 * eigh_graphs / (eigh_ms * 1e-3) / 1e12,
-            "traffic": ncu_traffic_all("r2b_ncu_summary_eigh.txt"),
-            "traffic_source": "profiles/r2b_ncu_summary_eigh.txt: dram bytes per launch of each stage (1024 graphs, one launch per stage)",
+            "traffic": ncu_traffic_all("r2c_ncu_summary_eigh.txt"),
+            "traffic_source": "profiles/r2c_ncu_summary_eigh.txt: dram bytes per launch of each stage (1024 graphs, one launch per stage, "
+                              "the one-warp QL kernel in place of the lane = graph one)",
         }
     elif eigh_ms > 0 and eigh_info is not None:
         # Jacobi route: resident in shared memory, bound by the LSU / shared-memory data pipe
@@ -850,12 +852,14 @@ def run_ours(args):
     ew_roof = None
     if ew_ms > 0:
         gbs = ew_bytes / (ew_ms * 1e-3) / 1e9
-        ew_roof = {"kernel": "normalize_{fwd,bwd}_kernel + sym_diag_abs_{fwd,bwd}_kernel (memory-bound n x n kernels)",
+        ew_roof = {"kernel": "normalize_{rowsum,scale_tiles,bwd_partial_tiles,bwd_apply_tiles}_kernel + sym_diag_abs_tiles_kernel<fwd,bwd> + "
+                             "sym_diag_abs_l1_tiles_kernel<fwd,bwd> (the final sym-diag-abs and the L1 term against the HR target in one "
+                             "pass): the memory-bound n x n kernels",
                    "bound": "hbm", "achieved": gbs, "unit": "GB/s", "peak": peaks.get("hbm_gbs"),
                    "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                    "peak_source": "MEASURED_PEAKS.json hbm_gbs", "share_of_step": ew_ms / elapsed_ms,
-                   "launches": ew_launches, "traffic": ncu_traffic_all("r2b_ncu_summary_nxn.txt"),
-                   "traffic_source": "profiles/r2b_ncu_summary_nxn.txt: dram bytes per launch (1024 x 268 x 268; algorithmic: 2 tensors = 588 MB "
+                   "launches": ew_launches, "traffic": ncu_traffic_all("r2c_ncu_summary_nxn.txt"),
+                   "traffic_source": "profiles/r2c_ncu_summary_nxn.txt: dram bytes per launch (1024 x 268 x 268; algorithmic: 2 tensors = 588 MB "
                                      "per forward kernel, 3 = 882 MB per backward pass, 4 with two incoming gradients)"}
     by_kernel = [r for r in (eigh_roof, gemm_roof, ew_roof) if r]
     roofline = max(by_kernel, key=lambda r: r["share_of_step"] or 0.0)          # the dominant kernel of the step
