@@ -220,7 +220,16 @@ sym_diag_abs_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g
 constexpr int kNormCluster = 16;        // normalise backward in one pass: CTAs (tile pairs) per subject cluster
 int g_norm_bwd_cluster = 0;             // gsr_set_tuning("normalize_bwd_cluster", 0|1): three launches (default) / the one-pass cluster kernel for n <= 320
 constexpr int kTS = 64;                 // tile edge
-constexpr int kTP = kTS + 1;            // padded pitch
+// Shared-memory image of a 64 x 64 tile: element (r, c) at tix(r, c) = 67 r + 2 (r >> 5) + c + 2 (c >> 5).  A warp touches
+// a tile in two ways -- 16 lanes x 4 consecutive columns of one row (and the next row for the other 16 lanes) when a
+// float4 row segment is stored, and 16 rows 4 apart at one column (and the next column) when the transposed partner is
+// read.  With the plain 65-float pitch of the first version both patterns hit every bank twice (4 tx and 4 (tx + 8) are
+// 32 apart).  The odd pitch keeps 4 P tx distinct for tx < 8, the skew of 2 after 32 columns / 32 rows moves the lanes
+// tx >= 8 to the banks = 2 (mod 4), and the other half-warp (next row / next column: an odd offset) takes the odd banks:
+// both patterns are conflict free.
+constexpr int kTP = kTS + 3;            // pitch (odd)
+constexpr int kTileFloats = kTS * kTP + 4;
+__device__ __forceinline__ int tix(int r, int c) { return r * kTP + 2 * (r >> 5) + c + 2 * (c >> 5); }
 constexpr int kTileThreads = 256;       // thread (ty, tx): rows ty + 16 p (p < 4), columns 4 tx .. 4 tx + 3
 
 __device__ __forceinline__ void tile_pair_of(int pair, int T, int& I, int& J) {
@@ -243,7 +252,8 @@ __device__ __forceinline__ float4 ld4_masked2(const float* __restrict__ a, const
     return v;
 }
 __device__ __forceinline__ void st_tile(float* t, int r, int c, float4 v) {
-    t[r * kTP + c] = v.x; t[r * kTP + c + 1] = v.y; t[r * kTP + c + 2] = v.z; t[r * kTP + c + 3] = v.w;
+    float* q = t + tix(r, c);               // c is a multiple of 4: the four columns share their 32-column group
+    q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
 }
 
 template <bool BWD>
@@ -251,8 +261,8 @@ __global__ void __launch_bounds__(kTileThreads)
 sym_diag_abs_tiles_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ out, int n, int T) {
     extern __shared__ float smem[];
     float* bx = smem;                          // partner tile of x:  bx[jj][ii] = x[J0 + jj][I0 + ii]
-    float* res = smem + kTS * kTP;             // result tile (I, J)
-    float* bg = res + kTS * kTP;               // BWD: partner tile of g
+    float* res = smem + kTileFloats;             // result tile (I, J)
+    float* bg = res + kTileFloats;               // BWD: partner tile of g
     const size_t base = (size_t)blockIdx.y * n * n;
     x += base; out += base;
     if (BWD) g += base;
@@ -284,12 +294,12 @@ sym_diag_abs_tiles_kernel(const float* __restrict__ x, const float* __restrict__
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int jj = 4 * tx + u, j = J0 + jj;
-            const float z = (a[u] + bx[jj * kTP + ii]) / 2.0f;                  // (x + x^T) / 2
+            const float z = (a[u] + bx[tix(jj, ii)]) / 2.0f;                  // (x + x^T) / 2
             if (!BWD) {
                 o[u] = (i == j) ? 1.0f : fabsf(z);
             } else {
                 const float sg = sgnf(z);
-                const float v = (ga[u] * sg + bg[jj * kTP + ii] * sg) / 2.0f;
+                const float v = (ga[u] * sg + bg[tix(jj, ii)] * sg) / 2.0f;
                 o[u] = (i == j) ? 0.f : v;
             }
         }
@@ -303,8 +313,8 @@ sym_diag_abs_tiles_kernel(const float* __restrict__ x, const float* __restrict__
     for (int p = 0; p < 4; ++p) {
         const int jj = ty + 16 * p, j = J0 + jj;                                // row of the mirror tile (J, I)
         if (j < n && I0 + 4 * tx < n) {
-            const float4 o4 = make_float4(res[(4 * tx) * kTP + jj], res[(4 * tx + 1) * kTP + jj],
-                                          res[(4 * tx + 2) * kTP + jj], res[(4 * tx + 3) * kTP + jj]);
+            const float4 o4 = make_float4(res[tix(4 * tx, jj)], res[tix(4 * tx + 1, jj)],
+                                          res[tix(4 * tx + 2, jj)], res[tix(4 * tx + 3, jj)]);
             *reinterpret_cast<float4*>(out + (size_t)j * n + I0 + 4 * tx) = o4;
         }
     }
@@ -325,8 +335,8 @@ sym_diag_abs_l1_tiles_kernel(const float* __restrict__ x, const float* __restric
                              float* __restrict__ out, double* __restrict__ partials, int n, int T) {
     extern __shared__ float smem[];
     float* bx = smem;                          // partner tile of x:  bx[jj][ii] = x[J0 + jj][I0 + ii]
-    float* by = smem + kTS * kTP;              // partner tile of y
-    float* res = by + kTS * kTP;               // result tile (I, J) (BWD, or FWD with a prediction to write)
+    float* by = smem + kTileFloats;              // partner tile of y
+    float* res = by + kTileFloats;               // result tile (I, J) (BWD, or FWD with a prediction to write)
     __shared__ double s_red[kTileThreads / 32];
     const size_t base = (size_t)blockIdx.y * n * n;
     x += base; y += base;
@@ -361,9 +371,9 @@ sym_diag_abs_l1_tiles_kernel(const float* __restrict__ x, const float* __restric
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int jj = 4 * tx + u, j = J0 + jj;
-            const float z = (a[u] + bx[jj * kTP + ii]) / 2.0f;                  // (x + x^T) / 2
+            const float z = (a[u] + bx[tix(jj, ii)]) / 2.0f;                  // (x + x^T) / 2
             const float pred = (i == j) ? 1.0f : fabsf(z);
-            const float yb = by[jj * kTP + ii];                                 // y[j][i]
+            const float yb = by[tix(jj, ii)];                                 // y[j][i]
             if (!BWD) {
                 o[u] = pred;
                 if (i < n && j < n) {
@@ -403,8 +413,8 @@ sym_diag_abs_l1_tiles_kernel(const float* __restrict__ x, const float* __restric
     for (int p = 0; p < 4; ++p) {
         const int jj = ty + 16 * p, j = J0 + jj;                                // row of the mirror tile (J, I)
         if (j < n && I0 + 4 * tx < n) {
-            const float4 o4 = make_float4(res[(4 * tx) * kTP + jj], res[(4 * tx + 1) * kTP + jj],
-                                          res[(4 * tx + 2) * kTP + jj], res[(4 * tx + 3) * kTP + jj]);
+            const float4 o4 = make_float4(res[tix(4 * tx, jj)], res[tix(4 * tx + 1, jj)],
+                                          res[tix(4 * tx + 2, jj)], res[tix(4 * tx + 3, jj)]);
             *reinterpret_cast<float4*>(out + (size_t)j * n + I0 + 4 * tx) = o4;
         }
     }
@@ -461,8 +471,8 @@ __global__ void __launch_bounds__(kTileThreads)
 normalize_scale_tiles_kernel(const float* __restrict__ mx, const float* __restrict__ r, float* __restrict__ out, int n, int T) {
     extern __shared__ float smem[];
     float* ta = smem;                          // ta[ii][jj] = M[I0 + ii][J0 + jj]
-    float* tb = smem + kTS * kTP;              // tb[jj][ii] = M[J0 + jj][I0 + ii]
-    float* rI = tb + kTS * kTP;                // [64]
+    float* tb = smem + kTileFloats;              // tb[jj][ii] = M[J0 + jj][I0 + ii]
+    float* rI = tb + kTileFloats;                // [64]
     float* rJ = rI + kTS;                      // [64]
     const size_t base = (size_t)blockIdx.y * n * n;
     mx += base; out += base;
@@ -488,10 +498,10 @@ normalize_scale_tiles_kernel(const float* __restrict__ mx, const float* __restri
         if (i < n && J0 + 4 * tx < n) {                          // out[i][j] = (M[j][i] r_i) r_j
             const float ri = rI[ii];
             float4 o;
-            o.x = (tb[(4 * tx) * kTP + ii] * ri) * rJ[4 * tx];
-            o.y = (tb[(4 * tx + 1) * kTP + ii] * ri) * rJ[4 * tx + 1];
-            o.z = (tb[(4 * tx + 2) * kTP + ii] * ri) * rJ[4 * tx + 2];
-            o.w = (tb[(4 * tx + 3) * kTP + ii] * ri) * rJ[4 * tx + 3];
+            o.x = (tb[tix(4 * tx, ii)] * ri) * rJ[4 * tx];
+            o.y = (tb[tix(4 * tx + 1, ii)] * ri) * rJ[4 * tx + 1];
+            o.z = (tb[tix(4 * tx + 2, ii)] * ri) * rJ[4 * tx + 2];
+            o.w = (tb[tix(4 * tx + 3, ii)] * ri) * rJ[4 * tx + 3];
             *reinterpret_cast<float4*>(out + (size_t)i * n + J0 + 4 * tx) = o;
         }
         if (I != J) {
@@ -499,10 +509,10 @@ normalize_scale_tiles_kernel(const float* __restrict__ mx, const float* __restri
             if (j < n && I0 + 4 * tx < n) {                      // mirror tile: out[j][i] = (M[i][j] r_j) r_i
                 const float rj = rJ[jj];
                 float4 o;
-                o.x = (ta[(4 * tx) * kTP + jj] * rj) * rI[4 * tx];
-                o.y = (ta[(4 * tx + 1) * kTP + jj] * rj) * rI[4 * tx + 1];
-                o.z = (ta[(4 * tx + 2) * kTP + jj] * rj) * rI[4 * tx + 2];
-                o.w = (ta[(4 * tx + 3) * kTP + jj] * rj) * rI[4 * tx + 3];
+                o.x = (ta[tix(4 * tx, jj)] * rj) * rI[4 * tx];
+                o.y = (ta[tix(4 * tx + 1, jj)] * rj) * rI[4 * tx + 1];
+                o.z = (ta[tix(4 * tx + 2, jj)] * rj) * rI[4 * tx + 2];
+                o.w = (ta[tix(4 * tx + 3, jj)] * rj) * rI[4 * tx + 3];
                 *reinterpret_cast<float4*>(out + (size_t)j * n + I0 + 4 * tx) = o;
             }
         }
@@ -517,9 +527,9 @@ normalize_bwd_partial_tiles_kernel(const float* __restrict__ mx, const float* __
                                    const float* __restrict__ Tg2, float* __restrict__ part, int n, int T) {
     extern __shared__ float smem[];
     float* mb = smem;                          // M(J,I):  mb[jj][ii]
-    float* tb = smem + kTS * kTP;              // T(J,I):  tb[jj][ii]
-    float* sS = tb + kTS * kTP;                // S[ii][jj]
-    float* rI = sS + kTS * kTP;
+    float* tb = smem + kTileFloats;              // T(J,I):  tb[jj][ii]
+    float* sS = tb + kTileFloats;                // S[ii][jj]
+    float* rI = sS + kTileFloats;
     float* rJ = rI + kTS;
     const size_t base = (size_t)blockIdx.y * n * n;
     mx += base; Tg += base;
@@ -554,7 +564,7 @@ normalize_bwd_partial_tiles_kernel(const float* __restrict__ mx, const float* __
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int jj = 4 * tx + u;
-            op[u] = t4[u] * mb[jj * kTP + ii] + tb[jj * kTP + ii] * a4[u];
+            op[u] = t4[u] * mb[tix(jj, ii)] + tb[tix(jj, ii)] * a4[u];
         }
         st_tile(sS, ii, 4 * tx, o);
     }
@@ -564,14 +574,14 @@ normalize_bwd_partial_tiles_kernel(const float* __restrict__ mx, const float* __
         const int ii = threadIdx.x;
         if (I0 + ii < n) {
             float acc = 0.f;
-            for (int jj = 0; jj < kTS; ++jj) acc = fmaf(sS[ii * kTP + jj], rJ[jj], acc);
+            for (int jj = 0; jj < kTS; ++jj) acc = fmaf(sS[tix(ii, jj)], rJ[jj], acc);
             part[(size_t)J * n + I0 + ii] = acc;
         }
     } else if (threadIdx.x < 2 * kTS && I != J) {
         const int jj = threadIdx.x - kTS;
         if (J0 + jj < n) {
             float acc = 0.f;
-            for (int ii = 0; ii < kTS; ++ii) acc = fmaf(sS[ii * kTP + jj], rI[ii], acc);
+            for (int ii = 0; ii < kTS; ++ii) acc = fmaf(sS[tix(ii, jj)], rI[ii], acc);
             part[(size_t)I * n + J0 + jj] = acc;
         }
     }
@@ -597,8 +607,8 @@ normalize_bwd_apply_tiles_kernel(const float* __restrict__ mx, const float* __re
                                  const float* __restrict__ Tg, const float* __restrict__ Tg2, float* __restrict__ dmx, int n, int T) {
     extern __shared__ float smem[];
     float* ta = smem;                          // T(I,J): ta[ii][jj]
-    float* tb = smem + kTS * kTP;              // T(J,I): tb[jj][ii]
-    float* rI = tb + kTS * kTP;
+    float* tb = smem + kTileFloats;              // T(J,I): tb[jj][ii]
+    float* rI = tb + kTileFloats;
     float* rJ = rI + kTS;
     float* dI = rJ + kTS;
     float* dJ = dI + kTS;
@@ -639,7 +649,7 @@ normalize_bwd_apply_tiles_kernel(const float* __restrict__ mx, const float* __re
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int jj = 4 * tx + u;
-                float gv = (tb[jj * kTP + ii] * ri) * rJ[jj] + di;
+                float gv = (tb[tix(jj, ii)] * ri) * rJ[jj] + di;
                 if (PRE) gv = (i == J0 + jj) ? 0.f : gv * sgnf(xs[u]);
                 op[u] = gv;
             }
@@ -655,7 +665,7 @@ normalize_bwd_apply_tiles_kernel(const float* __restrict__ mx, const float* __re
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int ii2 = 4 * tx + u;
-                    float gv = (ta[ii2 * kTP + jj] * rj) * rI[ii2] + dj;
+                    float gv = (ta[tix(ii2, jj)] * rj) * rI[ii2] + dj;
                     if (PRE) gv = (j == I0 + ii2) ? 0.f : gv * sgnf(xs[u]);
                     op[u] = gv;
                 }
@@ -686,9 +696,9 @@ normalize_bwd_cluster_kernel(const float* __restrict__ mx, const float* __restri
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ float smem[];
     float* mb = smem;                          // M(J,I):  mb[jj][ii]
-    float* tb = smem + kTS * kTP;              // T(J,I):  tb[jj][ii]
-    float* sS = tb + kTS * kTP;                // S[ii][jj], then T(I,J): ta[ii][jj]
-    float* rI = sS + kTS * kTP;
+    float* tb = smem + kTileFloats;              // T(J,I):  tb[jj][ii]
+    float* sS = tb + kTileFloats;                // S[ii][jj], then T(I,J): ta[ii][jj]
+    float* rI = sS + kTileFloats;
     float* rJ = rI + kTS;
     float* dI = rJ + kTS;
     float* dJ = dI + kTS;
@@ -744,7 +754,7 @@ normalize_bwd_cluster_kernel(const float* __restrict__ mx, const float* __restri
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int jj = 4 * tx + u;
-                op[u] = t4[u] * mb[jj * kTP + ii] + tb[jj * kTP + ii] * a4[u];
+                op[u] = t4[u] * mb[tix(jj, ii)] + tb[tix(jj, ii)] * a4[u];
             }
             st_tile(sS, ii, 4 * tx, o);
         }
@@ -752,12 +762,12 @@ normalize_bwd_cluster_kernel(const float* __restrict__ mx, const float* __restri
         if (threadIdx.x < kTS) {
             const int ii = threadIdx.x;
             float acc = 0.f;
-            for (int jj = 0; jj < kTS; ++jj) acc = fmaf(sS[ii * kTP + jj], rJ[jj], acc);
+            for (int jj = 0; jj < kTS; ++jj) acc = fmaf(sS[tix(ii, jj)], rJ[jj], acc);
             pout[ii] = acc;
         } else if (threadIdx.x < 2 * kTS) {
             const int jj = threadIdx.x - kTS;
             float acc = 0.f;
-            if (I != J) for (int ii = 0; ii < kTS; ++ii) acc = fmaf(sS[ii * kTP + jj], rI[ii], acc);
+            if (I != J) for (int ii = 0; ii < kTS; ++ii) acc = fmaf(sS[tix(ii, jj)], rI[ii], acc);
             pout[kTS + jj] = acc;
         }
     }
@@ -794,7 +804,7 @@ normalize_bwd_cluster_kernel(const float* __restrict__ mx, const float* __restri
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int jj = 4 * tx + u;
-                    float gv = (tb[jj * kTP + ii] * ri) * rJ[jj] + di;
+                    float gv = (tb[tix(jj, ii)] * ri) * rJ[jj] + di;
                     if (PRE) gv = (i == J0 + jj) ? 0.f : gv * sign_of_code((sa >> (2 * (4 * p + u))) & 3u);
                     op[u] = gv;
                 }
@@ -809,7 +819,7 @@ normalize_bwd_cluster_kernel(const float* __restrict__ mx, const float* __restri
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int ii2 = 4 * tx + u;
-                        float gv = (ta[ii2 * kTP + jj] * rj) * rI[ii2] + dj;
+                        float gv = (ta[tix(ii2, jj)] * rj) * rI[ii2] + dj;
                         if (PRE) gv = (j == I0 + ii2) ? 0.f : gv * sign_of_code((sb >> (2 * (4 * p + u))) & 3u);
                         op[u] = gv;
                     }
@@ -853,7 +863,7 @@ extern "C" int gsr_normalize_adj_fwd(const float* mx, float* out, float* r_out, 
     if (n % 4 == 0 && n >= 2 * kTS && aligned16(mx) && aligned16(out) && (!m_out || aligned16(m_out)) && batch <= 65535) {
         cudaStream_t st = (cudaStream_t)stream;
         const int T = (n + kTS - 1) / kTS;
-        const size_t tsmem = (2 * kTS * kTP + 2 * kTS) * sizeof(float);
+        const size_t tsmem = (2 * kTileFloats + 2 * kTS) * sizeof(float);
         if (pre) normalize_rowsum_kernel<1><<<dim3((n + 7) / 8, batch), 256, 0, st>>>(mx, r_out, m_out, n);
         else     normalize_rowsum_kernel<0><<<dim3((n + 7) / 8, batch), 256, 0, st>>>(mx, r_out, m_out, n);
         int rc1 = launched("normalize_rowsum");
@@ -888,7 +898,7 @@ extern "C" int gsr_sym_diag_abs_fwd(const float* x, float* out, int batch, int n
     if (batch == 0) return 0;
     if (n % 4 == 0 && aligned16(x) && aligned16(out) && batch <= 65535) {
         const int T = (n + kTS - 1) / kTS;
-        sym_diag_abs_tiles_kernel<false><<<dim3(T * (T + 1) / 2, batch), kTileThreads, 2 * kTS * kTP * sizeof(float), (cudaStream_t)stream>>>(x, nullptr, out, n, T);
+        sym_diag_abs_tiles_kernel<false><<<dim3(T * (T + 1) / 2, batch), kTileThreads, 2 * kTileFloats * sizeof(float), (cudaStream_t)stream>>>(x, nullptr, out, n, T);
         return launched("sym_diag_abs_fwd");
     }
     const size_t smem = (size_t)n * kStripPad * sizeof(float);
@@ -904,7 +914,7 @@ extern "C" int gsr_sym_diag_abs_bwd(const float* x, const float* grad_out, float
     if (batch == 0) return 0;
     if (n % 4 == 0 && aligned16(x) && aligned16(grad_out) && aligned16(grad_x) && batch <= 65535) {
         const int T = (n + kTS - 1) / kTS;
-        const size_t tsmem = 3 * kTS * kTP * sizeof(float);
+        const size_t tsmem = 3 * kTileFloats * sizeof(float);
         int rc2 = set_smem(sym_diag_abs_tiles_kernel<true>, tsmem);
         if (rc2) return fail(rc2, "sym_diag_abs_bwd: cudaFuncSetAttribute failed");
         sym_diag_abs_tiles_kernel<true><<<dim3(T * (T + 1) / 2, batch), kTileThreads, tsmem, (cudaStream_t)stream>>>(x, grad_out, grad_x, n, T);
@@ -929,7 +939,7 @@ extern "C" int gsr_sym_diag_abs_l1_fwd(const float* x, const float* y, float* pr
     if (n % 4 != 0 || !aligned16(x) || !aligned16(y) || (pred_out && !aligned16(pred_out)) || batch > 65535)
         return fail(GSR_E_UNSUPPORTED, "sym_diag_abs_l1_fwd: needs n % 4 == 0, 16-byte aligned tensors and batch <= 65535 (use sym_diag_abs + l1_loss)");
     const int T = (n + kTS - 1) / kTS, pairs = T * (T + 1) / 2;
-    const size_t tsmem = 3 * kTS * kTP * sizeof(float);
+    const size_t tsmem = 3 * kTileFloats * sizeof(float);
     int rc = set_smem(sym_diag_abs_l1_tiles_kernel<false>, tsmem);
     if (rc) return fail(rc, "sym_diag_abs_l1_fwd: cudaFuncSetAttribute failed");
     sym_diag_abs_l1_tiles_kernel<false><<<dim3(pairs, batch), kTileThreads, tsmem, (cudaStream_t)stream>>>(x, y, nullptr, pred_out, partials, n, T);
@@ -945,7 +955,7 @@ extern "C" int gsr_sym_diag_abs_l1_bwd(const float* x, const float* y, const flo
     if (n % 4 != 0 || !aligned16(x) || !aligned16(y) || !aligned16(grad_x) || batch > 65535)
         return fail(GSR_E_UNSUPPORTED, "sym_diag_abs_l1_bwd: needs n % 4 == 0, 16-byte aligned tensors and batch <= 65535");
     const int T = (n + kTS - 1) / kTS;
-    const size_t tsmem = 3 * kTS * kTP * sizeof(float);
+    const size_t tsmem = 3 * kTileFloats * sizeof(float);
     int rc = set_smem(sym_diag_abs_l1_tiles_kernel<true>, tsmem);
     if (rc) return fail(rc, "sym_diag_abs_l1_bwd: cudaFuncSetAttribute failed");
     sym_diag_abs_l1_tiles_kernel<true><<<dim3(T * (T + 1) / 2, batch), kTileThreads, tsmem, (cudaStream_t)stream>>>(x, y, grad_loss, grad_x, nullptr, n, T);
@@ -985,7 +995,7 @@ extern "C" int gsr_normalize_adj_bwd_tiles2(const float* mx, const float* r, con
         // one pass: the tile pairs of a subject as a cluster of 16 CTAs (opt-in size); a refused launch falls back for good
         static bool refused = false;
         if (!refused) {
-            const size_t smemc = (3 * kTS * kTP + 6 * kTS) * sizeof(float);
+            const size_t smemc = (3 * kTileFloats + 6 * kTS) * sizeof(float);
             auto kern = pre ? normalize_bwd_cluster_kernel<1> : normalize_bwd_cluster_kernel<0>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemc);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -1009,7 +1019,7 @@ extern "C" int gsr_normalize_adj_bwd_tiles2(const float* mx, const float* r, con
     }
     float* part = workspace;
     float* drho = workspace + (size_t)batch * T * n;
-    const size_t smem1 = (3 * kTS * kTP + 2 * kTS) * sizeof(float), smem2 = (2 * kTS * kTP + 4 * kTS) * sizeof(float);
+    const size_t smem1 = (3 * kTileFloats + 2 * kTS) * sizeof(float), smem2 = (2 * kTileFloats + 4 * kTS) * sizeof(float);
     int rc = pre ? set_smem(normalize_bwd_partial_tiles_kernel<1>, smem1) : set_smem(normalize_bwd_partial_tiles_kernel<0>, smem1);
     if (rc) return fail(rc, "normalize_adj_bwd_tiles: cudaFuncSetAttribute failed");
     const dim3 grid(T * (T + 1) / 2, batch);
