@@ -257,7 +257,7 @@ __device__ __forceinline__ void st_tile(float* t, int r, int c, float4 v) {
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, BWD ? 3 : 5)
 sym_diag_abs_tiles_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ out, int n, int T) {
     extern __shared__ float smem[];
     float* bx = smem;                          // partner tile of x:  bx[jj][ii] = x[J0 + jj][I0 + ii]
@@ -330,7 +330,7 @@ sym_diag_abs_tiles_kernel(const float* __restrict__ x, const float* __restrict__
 //        x and y instead of being read from a [B, n, n] gradient tensor: the same expressions in the same order as
 //        l1_bwd_kernel followed by sym_diag_abs_tiles_kernel<true>, so the result is bit identical to the two launches
 template <bool BWD>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, BWD ? 3 : 5)
 sym_diag_abs_l1_tiles_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ grad_loss,
                              float* __restrict__ out, double* __restrict__ partials, int n, int T) {
     extern __shared__ float smem[];
@@ -939,7 +939,7 @@ extern "C" int gsr_sym_diag_abs_l1_fwd(const float* x, const float* y, float* pr
     if (n % 4 != 0 || !aligned16(x) || !aligned16(y) || (pred_out && !aligned16(pred_out)) || batch > 65535)
         return fail(GSR_E_UNSUPPORTED, "sym_diag_abs_l1_fwd: needs n % 4 == 0, 16-byte aligned tensors and batch <= 65535 (use sym_diag_abs + l1_loss)");
     const int T = (n + kTS - 1) / kTS, pairs = T * (T + 1) / 2;
-    const size_t tsmem = 3 * kTileFloats * sizeof(float);
+    const size_t tsmem = (pred_out ? 3 : 2) * kTileFloats * sizeof(float);      // the result tile only when a prediction is written
     int rc = set_smem(sym_diag_abs_l1_tiles_kernel<false>, tsmem);
     if (rc) return fail(rc, "sym_diag_abs_l1_fwd: cudaFuncSetAttribute failed");
     sym_diag_abs_l1_tiles_kernel<false><<<dim3(pairs, batch), kTileThreads, tsmem, (cudaStream_t)stream>>>(x, y, nullptr, pred_out, partials, n, T);
