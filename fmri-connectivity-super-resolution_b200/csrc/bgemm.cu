@@ -33,6 +33,7 @@ constexpr int kThreads = 320;        // 289 compute threads, all 320 load
 //   1: BK =  8, two CTAs per SM (96 registers, a few spills, 20 warps / SM)
 //   2: BK =  8, one CTA per SM
 int g_gemm_variant = 0;
+int g_lin_small = 1;      // one-subject products on lin::lin_kernel (gsr_set_tuning("bgemm_lin", 0): the 136 x 136 kernel for everything)
 extern int g_eigh_oddeven;
 extern int g_eigh_max_polish;
 extern int g_eigh_ql_max_iter;
@@ -240,14 +241,182 @@ __global__ void reduce_partials_kernel(const float* __restrict__ ws, float* __re
     C[(size_t)m * ldc + n] = acc;
 }
 
-// Column sums of X[rows][cols] (Linear bias gradient); one thread per column, fixed order.
-__global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ out, int rows, int cols, int ld) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// Column sums of X[rows][cols] (Linear bias gradient): 32 columns x 8 row phases per CTA, the eight partial sums of a
+// column folded in a fixed order (a thread per column walking all rows was a chain of `rows` dependent loads: 9-16 us
+// for the 160 x 320 gradients of the Graph U-Net, which sit on the tail of the step).
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, float* __restrict__ out, int rows, int cols, int ld) {
+    __shared__ float part[8][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + x;
     float acc = 0.f;
-    for (int r = 0; r < rows; ++r) acc += __ldg(X + (size_t)r * ld + c);
-    out[c] = acc;
+    if (c < cols)
+        for (int r = y; r < rows; r += 8) acc += __ldg(X + (size_t)r * ld + c);
+    part[y][x] = acc;
+    __syncthreads();
+    if (y == 0 && c < cols) {
+        float s = part[0][x];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) s += part[i][x];
+        out[c] = s;
+    }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// One-subject products of the Linear-layer class (models/ops.py:60 and its autograd: the Graph U-Net runs once per step
+// on <= 160 x 640 operands; also the reference's batch-1 calls).  These are latency problems, not throughput problems:
+// the 136 x 136 kernel above gives a 160 x 320 x 320 product 6 CTAs walking 20 k-tiles with one global-load round trip
+// each (42-48 us per launch, 21 launches per step, the backward ones on the step's tail).  Here a CTA owns a 32 x 32
+// tile of C, brings its WHOLE operand panels (32 x K of op(A), K x 32 of op(B)) into shared memory with one burst of
+// 16-byte cp.async (zero filled at the ragged edges by the copy's source size) in the orientation they have in global
+// memory, and its four 64-thread groups each take every fourth 4-k chunk with a 4 x 4 register tile; the four partial
+// tiles meet in shared memory in a fixed order (deterministic, no atomics).  160 x 320: 50 CTAs, one load round trip.
+namespace lin {
+
+constexpr int TM = 32, TN = 32, THREADS = 256, KG = 4;
+constexpr int PR = 36;                        // pitch of a [k][32 rows] panel image (16-byte aligned rows)
+constexpr int MAXK = 768;                     // two panels of 768 x 36 floats = 216 KB
+constexpr int RED_FLOATS = KG * TM * 33;
+
+__host__ __device__ inline int pitch_k(int K) { return ((K + 31) & ~31) + 4; }      // = 4 mod 32: rows of a [32][k] panel start one 16-byte bank group apart
+__host__ __device__ inline int panel_floats(bool kcontig, int K) { return kcontig ? TM * pitch_k(K) : ((K + 3) & ~3) * PR; }
+
+__device__ __forceinline__ void cp16z(float* dst, const float* src, int bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
+// KC: the operand is stored [row][k] (k contiguous) -> image [32][pitch_k]; else stored [k][row] -> image [k][PR].
+template <bool KC>
+__device__ __forceinline__ void stage(float* s, const float* __restrict__ g, int ld, int rows, int K, int row0, int PK, int tid) {
+    if (KC) {
+        const int cpr = (K + 3) >> 2;
+        for (int c = tid; c < TM * cpr; c += THREADS) {
+            const int r = c / cpr, k = (c - r * cpr) << 2;
+            const int bytes = (row0 + r < rows) ? min(16, 4 * (K - k)) : 0;
+            cp16z(s + r * PK + k, bytes ? g + (size_t)(row0 + r) * ld + k : g, bytes);
+        }
+    } else {
+        const int kr = (K + 3) & ~3;                                   // rows K .. kr-1 of the image are read by the last chunk: zero
+        for (int c = tid; c < 8 * kr; c += THREADS) {
+            const int k = c >> 3, rc = (c & 7) << 2;
+            const int left = (k < K) ? rows - row0 - rc : 0;
+            const int bytes = left > 0 ? min(16, 4 * left) : 0;
+            cp16z(s + k * PR + rc, bytes ? g + (size_t)k * ld + row0 + rc : g, bytes);
+        }
+    }
+}
+
+// TA: op(A) = A^T (A stored [K][M]);  TB: op(B) = B^T (B stored [N][K]).
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(THREADS) lin_kernel(const GemmParams p) {
+    extern __shared__ __align__(16) float lsm[];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    const int K = p.K, PK = pitch_k(K);
+    float* As = lsm;
+    float* Bs = lsm + panel_floats(!TA, K);
+    stage<!TA>(As, p.A, p.lda, p.M, K, m0, PK, tid);
+    stage<TB>(Bs, p.B, p.ldb, p.N, K, n0, PK, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // thread (tm, tn) of group kg: rows 4 tm + i; columns 4 tn + j of a [k][n] image, tn + 8 j of a [n][k] image (there the
+    // eight lanes of a quarter warp read eight different rows: one bank group apart only when the rows are consecutive)
+    const int kg = tid >> 6, tm = (tid & 63) >> 3, tn = tid & 7;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int nkc = (K + 3) >> 2;
+    for (int kc = kg; kc < nkc; kc += KG) {
+        float a[4][4], b[4][4];                                        // [k within the chunk][row | column]
+        if (!TA) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(As + (4 * tm + i) * PK + 4 * kc);
+                a[0][i] = v.x; a[1][i] = v.y; a[2][i] = v.z; a[3][i] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 v = *reinterpret_cast<const float4*>(As + (4 * kc + kk) * PR + 4 * tm);
+                a[kk][0] = v.x; a[kk][1] = v.y; a[kk][2] = v.z; a[kk][3] = v.w;
+            }
+        }
+        if (TB) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 v = *reinterpret_cast<const float4*>(Bs + (tn + 8 * j) * PK + 4 * kc);
+                b[0][j] = v.x; b[1][j] = v.y; b[2][j] = v.z; b[3][j] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 v = *reinterpret_cast<const float4*>(Bs + (4 * kc + kk) * PR + 4 * tn);
+                b[kk][0] = v.x; b[kk][1] = v.y; b[kk][2] = v.z; b[kk][3] = v.w;
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[kk][i], b[kk][j], acc[i][j]);
+    }
+
+    __syncthreads();                                                   // every group is done with the panels
+    float* red = lsm;                                                  // [KG][32][33]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[(kg * TM + 4 * tm + i) * 33 + (TB ? tn + 8 * j : 4 * tn + j)] = acc[i][j];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < TM * TN / THREADS; ++q) {
+        const int e = tid + THREADS * q, ml = e >> 5, nl = e & 31;
+        const int m = m0 + ml, n = n0 + nl;
+        if (m >= p.M || n >= p.N) continue;
+        float x = red[ml * 33 + nl];
+#pragma unroll
+        for (int g = 1; g < KG; ++g) x += red[(g * TM + ml) * 33 + nl];
+        x *= p.alpha;
+        if (p.epilogue == GSR_EPI_BIAS) x += __ldg(p.extra + n);
+        else if (p.epilogue == GSR_EPI_ADD) x += __ldg(p.extra + (size_t)m * p.ld_extra + n);
+        p.C[(size_t)m * p.ldc + n] = x;
+    }
+}
+
+static size_t smem_bytes(int transA, int transB, int K) {
+    const size_t f = (size_t)panel_floats(!transA, K) + (size_t)panel_floats(transB != 0, K);
+    return sizeof(float) * (f > (size_t)RED_FLOATS ? f : (size_t)RED_FLOATS);
+}
+
+static bool eligible(const GemmParams& p) {
+    return p.batch == 1 && p.K >= 1 && p.K <= MAXK && (long long)p.M * p.N <= (1LL << 18) && aligned16(p.A) && aligned16(p.B) &&
+           (p.lda % 4 == 0) && (p.ldb % 4 == 0);
+}
+
+static int launch(const GemmParams& p, int transA, int transB, cudaStream_t st) {
+    static const bool attr_ok = [] {
+        const int mx = (int)(sizeof(float) * 2 * (size_t)(((MAXK + 3) & ~3) * PR));
+        return cudaFuncSetAttribute(lin_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) == cudaSuccess &&
+               cudaFuncSetAttribute(lin_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) == cudaSuccess &&
+               cudaFuncSetAttribute(lin_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) == cudaSuccess &&
+               cudaFuncSetAttribute(lin_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) == cudaSuccess;
+    }();
+    if (!attr_ok) { cudaGetLastError(); return fail(GSR_E_UNSUPPORTED, "bgemm: shared-memory opt-in of the one-subject kernel failed"); }
+    const dim3 grid((p.N + TN - 1) / TN, (p.M + TM - 1) / TM, 1);
+    const size_t smem = smem_bytes(transA, transB, p.K);
+    if (!transA && !transB) lin_kernel<false, false><<<grid, THREADS, smem, st>>>(p);
+    else if (!transA && transB) lin_kernel<false, true><<<grid, THREADS, smem, st>>>(p);
+    else if (transA && !transB) lin_kernel<true, false><<<grid, THREADS, smem, st>>>(p);
+    else lin_kernel<true, true><<<grid, THREADS, smem, st>>>(p);
+    return launched("bgemm_lin");
+}
+
+}  // namespace lin
 
 template <int BK, int OCC, bool REDUCE>
 static void launch_variant(const GemmParams& p, int transA, int transB, bool vec, dim3 grid, cudaStream_t st) {
@@ -298,6 +467,7 @@ extern "C" int gsr_bgemm_f32(const float* A, const float* B, float* C,
     if (batch > 65535) return fail(GSR_E_UNSUPPORTED, "bgemm: batch > 65535");
     GemmParams p{A, B, C, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, batch, 1, alpha,
                  epilogue, extra, ld_extra, stride_extra};
+    if (g_lin_small && lin::eligible(p)) return lin::launch(p, transA, transB, (cudaStream_t)stream);
     dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, batch);
     if (grid.y > 65535) return fail(GSR_E_UNSUPPORTED, "bgemm: M too large");
     const bool vec = vec_ok(p) && (ldc % 4 == 0) && (strideC % 4 == 0);
@@ -307,6 +477,7 @@ extern "C" int gsr_bgemm_f32(const float* A, const float* B, float* C,
 extern "C" int gsr_set_tuning(const char* key, int value) {
     if (!key) return fail(GSR_E_ARG, "set_tuning: null key");
     if (!strcmp(key, "gemm_variant")) { gsr::g_gemm_variant = value; return 0; }
+    if (!strcmp(key, "bgemm_lin")) { gsr::g_lin_small = value; return 0; }
     if (!strcmp(key, "eigh_oddeven")) { gsr::g_eigh_oddeven = value; return 0; }
     if (!strcmp(key, "eigh_max_polish")) { gsr::g_eigh_max_polish = value; return 0; }
     if (!strcmp(key, "eigh_ql_max_iter")) { gsr::g_eigh_ql_max_iter = value; return 0; }
@@ -365,6 +536,6 @@ extern "C" int gsr_bgemm_reduce_f32(const float* A, const float* B, float* C,
 
 extern "C" int gsr_colsum_f32(const float* X, float* out, int rows, int cols, int ld, void* stream) {
     if (!X || !out || rows < 0 || cols <= 0) return fail(GSR_E_ARG, "colsum: bad argument");
-    colsum_kernel<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(X, out, rows, cols, ld);
+    colsum_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>(X, out, rows, cols, ld);
     return launched("colsum");
 }

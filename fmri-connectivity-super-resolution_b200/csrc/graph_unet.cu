@@ -81,19 +81,29 @@ __global__ void pool_bwd_rows_kernel(const float* __restrict__ X, const float* _
         dX[(size_t)i * d + c] = fmaf(dsi, p[c], g[(size_t)t * d + c] * sig);
 }
 
-// dp[c] = sum_i ds_i X[i][c];  dc = sum_i ds_i   (fixed order)
-__global__ void pool_bwd_proj_kernel(const float* __restrict__ X, const float* __restrict__ ds,
-                                     float* __restrict__ dp, float* __restrict__ dc, int n, int d) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < d) {
-        float acc = 0.f;
-        for (int i = 0; i < n; ++i) acc = fmaf(ds[i], X[(size_t)i * d + c], acc);
-        dp[c] = acc;
+// dp[c] = sum_i ds_i X[i][c];  dc = sum_i ds_i   (fixed order: 32 columns x 8 row phases per CTA, the phases folded in
+// order -- one thread per column walking all n rows was a chain of n dependent FMAs, 9-19 us on the step's tail)
+__global__ void __launch_bounds__(256) pool_bwd_proj_kernel(const float* __restrict__ X, const float* __restrict__ ds,
+                                                            float* __restrict__ dp, float* __restrict__ dc, int n, int d) {
+    __shared__ float part[8][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + x;
+    float acc = 0.f;
+    if (c < d)
+        for (int i = y; i < n; i += 8) acc = fmaf(ds[i], X[(size_t)i * d + c], acc);
+    part[y][x] = acc;
+    __syncthreads();
+    if (y == 0 && c < d) {
+        float s = part[0][x];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) s += part[i][x];
+        dp[c] = s;
     }
-    if (c == 0) {
-        float acc = 0.f;
-        for (int i = 0; i < n; ++i) acc += ds[i];
-        dc[0] = acc;
+    if (blockIdx.x == 0 && y == 1) {
+        float a = 0.f;
+        for (int i = x; i < n; i += 32) a += ds[i];
+        a = warp_sum(a);
+        if (x == 0) dc[0] = a;
     }
 }
 
@@ -164,7 +174,7 @@ extern "C" int gsr_pool_bwd(const float* X, const float* p, const float* scores,
     pool_bwd_rows_kernel<<<k, 128, 0, st>>>(X, p, scores, idx, grad_new_X, grad_X, ds_workspace, d, n);
     int rc = launched("pool_bwd_rows");
     if (rc) return rc;
-    pool_bwd_proj_kernel<<<(d + 127) / 128, 128, 0, st>>>(X, ds_workspace, grad_p, grad_c, n, d);
+    pool_bwd_proj_kernel<<<(d + 31) / 32, 256, 0, st>>>(X, ds_workspace, grad_p, grad_c, n, d);
     return launched("pool_bwd_proj");
 }
 

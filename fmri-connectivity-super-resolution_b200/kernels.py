@@ -51,6 +51,10 @@ EW_TIMER = None        # same, around the memory-bound n x n kernels (work = alg
 # (gsr_bgemm_f32) otherwise; "simt": always the SIMT kernel.  Same results to fp32 tolerance.
 GEMM_BACKEND = os.environ.get("GSR_GEMM_BACKEND", "tc")
 TC_MIN_ROWS = 256          # smaller products (the Graph U-Net linears) cannot fill a 128-row tensor-core tile
+# One product (no subject dimension left after stacking) of at most LIN_MAX_OUT outputs and K <= LIN_MAX_K is a latency
+# problem: gsr_bgemm_f32 runs it on its 32 x 32-tile whole-panel kernel (csrc/bgemm.cu, lin::lin_kernel) -- the Graph
+# U-Net's weight gradients (320 x 320 x <= 160) included, which the row rule alone would send to a tensor-core tile or two.
+LIN_MAX_OUT, LIN_MAX_K = 1 << 18, 768
 
 
 def set_gemm_backend(name: str) -> None:
@@ -249,7 +253,8 @@ def bgemm(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB: bool =
         Mk, bk, sAk, sCk, sEk = batch * M, 1, 0, 0, 0
     timer = GEMM_TIMER
     e0 = timer.start() if timer is not None else None
-    use_tc = _tc_ok(A, B, ac, bc, sAk, sB, Mk * bk)
+    tiny = bk == 1 and Mk * N <= LIN_MAX_OUT and K <= LIN_MAX_K
+    use_tc = not tiny and _tc_ok(A, B, ac, bc, sAk, sB, Mk * bk)
     fn = lib().gsr_tcgemm_f32 if use_tc else lib().gsr_bgemm_f32
     check(fn(A.data_ptr(), B.data_ptr(), out.data_ptr(), Mk, N, K, ac, bc, N,
              sAk, sB, sCk, int(transA), int(transB), bk, float(alpha),

@@ -35,12 +35,14 @@ def K(cuda_pkg):
 def gemm_backend(request, cuda_pkg):
     """Every contraction test runs on the SIMT FP32 kernel and on the tcgen05 3xTF32 kernel."""
     Kmod = cuda_pkg.kernels
-    old, old_rows = Kmod.GEMM_BACKEND, Kmod.TC_MIN_ROWS
+    old, old_rows, old_lin = Kmod.GEMM_BACKEND, Kmod.TC_MIN_ROWS, Kmod.LIN_MAX_OUT
     Kmod.set_gemm_backend(request.param)
     Kmod.TC_MIN_ROWS = 0
+    if request.param == "tc":
+        Kmod.LIN_MAX_OUT = 0          # one-subject products too: the tensor kernels keep their small-shape coverage
     yield request.param
     Kmod.set_gemm_backend(old)
-    Kmod.TC_MIN_ROWS = old_rows
+    Kmod.TC_MIN_ROWS, Kmod.LIN_MAX_OUT = old_rows, old_lin
 
 
 # ------------------------------------------------------------------ vectoriser (bit exact)
@@ -685,6 +687,77 @@ def test_bgemm_reduce(K, gemm_backend, tA, tB, M):
     assert float((got.double() - want).abs().max()) <= tol
     again = K.bgemm_reduce(A.cuda(), B.cuda(), transA=tA, transB=tB, alpha=0.5, add=add.cuda()).cpu()
     assert torch.equal(got, again)                       # deterministic reduction order
+
+
+# the Graph U-Net's Linear layers and their gradients at ks = [0.9, 0.7, 0.6, 0.5] (160 -> 144 -> 100 -> 60 -> 30 rows of width
+# 268: models/ops.py:60, 92-107), then ragged / minimal / maximal-K shapes
+LIN_SHAPES = [(160, 268, 160), (144, 268, 268), (100, 268, 268), (60, 268, 268), (30, 268, 268), (160, 268, 536),
+              (160, 536, 268), (268, 268, 144), (268, 268, 30), (268, 536, 160), (160, 320, 320), (1, 4, 4), (33, 36, 4),
+              (37, 100, 7), (64, 64, 768), (31, 29, 50)]
+
+
+@pytest.mark.parametrize("tA", [False, True])
+@pytest.mark.parametrize("tB", [False, True])
+def test_bgemm_one_subject_kernel(cuda_pkg, K, tA, tB):
+    """csrc/bgemm.cu lin::lin_kernel (one product, whole operand panels in shared memory, 32 x 32 tiles, four k groups):
+    against the float64 product for every layout and epilogue, against the 136 x 136 kernel it replaces for these shapes
+    (same fp32 class: a few ulp of sum |a||b|), deterministic, and never writing outside C."""
+    n0 = cuda_pkg.launch_count()
+    for M, N, Kd in LIN_SHAPES:
+        g = torch.Generator().manual_seed(1000 * M + 10 * N + Kd)
+        # leading dimensions rounded up to 4 floats (the kernel's alignment contract), operands are views into wider buffers
+        lda = ((M if tA else Kd) + 3) // 4 * 4
+        ldb = ((Kd if tB else N) + 3) // 4 * 4
+        Abuf = torch.randn((Kd, lda) if tA else (M, lda), generator=g)
+        Bbuf = torch.randn((N, ldb) if tB else (Kd, ldb), generator=g)
+        A = Abuf[:, :M] if tA else Abuf[:, :Kd]
+        B = Bbuf[:, :Kd] if tB else Bbuf[:, :N]
+        opA, opB = (A.T if tA else A), (B.T if tB else B)
+        want = opA.double() @ opB.double()
+        tol = 2e-6 * float((opA.abs().double() @ opB.abs().double()).max())
+        bias, add = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+        Ad, Bd = Abuf.cuda(), Bbuf.cuda()
+
+        def run(alpha=1.0, epi=0, extra=None, ld_extra=0):
+            out = torch.full((M + 2, N + 3), 7.0, device="cuda")             # guard rows / columns around C (ldc = N + 3)
+            K.check(cuda_pkg.lib().gsr_bgemm_f32(
+                Ad.data_ptr(), Bd.data_ptr(), out.data_ptr(), M, N, Kd, lda, ldb, N + 3, 0, 0, 0, int(tA), int(tB), 1,
+                float(alpha), epi, extra.data_ptr() if extra is not None else None, ld_extra, 0,
+                torch.cuda.current_stream().cuda_stream), "gsr_bgemm_f32")
+            assert bool((out[M:] == 7.0).all()) and bool((out[:, N:] == 7.0).all()), (M, N, Kd, "wrote outside C")
+            return out[:M, :N].cpu()
+
+        got = run()
+        assert float((got.double() - want).abs().max()) <= tol, (M, N, Kd, tA, tB)
+        assert torch.equal(got, run())
+        got_b = run(alpha=-0.5, epi=K.EPI_BIAS, extra=bias.cuda())
+        assert float((got_b.double() - (-0.5 * want + bias.double())).abs().max()) <= tol
+        got_a = run(alpha=2.0, epi=K.EPI_ADD, extra=add.cuda(), ld_extra=N)
+        assert float((got_a.double() - (2.0 * want + add.double())).abs().max()) <= 2 * tol
+        try:
+            cuda_pkg.set_tuning("bgemm_lin", 0)
+            old = run()
+        finally:
+            cuda_pkg.set_tuning("bgemm_lin", 1)
+        assert float((got - old).abs().max()) <= tol
+    assert cuda_pkg.launch_count() >= n0 + 5 * len(LIN_SHAPES)      # every run() above is one launch of this library
+
+
+def test_colsum_and_wrapper_routing(cuda_pkg, K):
+    """gsr_colsum_f32 (32 columns x 8 row phases, fixed fold order) against float64, ragged sizes; kernels.bgemm sends one
+    small product to the one-subject kernel whatever its row count and keeps batched / large products where they were."""
+    g = torch.Generator().manual_seed(77)
+    for rows, cols in ((160, 320), (30, 320), (1, 1), (7, 33), (512, 1024), (268, 268), (9, 31)):
+        X = torch.randn(rows, cols, generator=g)
+        got = K.colsum(X.cuda()).cpu()
+        assert float((got.double() - X.double().sum(0)).abs().max()) <= 2e-6 * float(X.abs().double().sum(0).max())
+        assert torch.equal(got, K.colsum(X.cuda()).cpu())
+    X, W, b = torch.randn(144, 268, generator=g), torch.randn(268, 268, generator=g), torch.randn(268, generator=g)
+    gY = torch.randn(144, 268, generator=g)
+    y = K.bgemm(X.cuda(), W.cuda(), transB=True, bias=b.cuda()).cpu()
+    assert float((y.double() - (X.double() @ W.double().T + b.double())).abs().max()) < 2e-6 * float((X.abs().double() @ W.abs().double().T).max())
+    gW = K.bgemm(gY.cuda(), X.cuda(), transA=True).cpu()                       # 268 rows: the row rule alone would pick a tensor tile
+    assert float((gW.double() - gY.double().T @ X.double()).abs().max()) < 2e-6 * float((gY.abs().double().T @ X.abs().double()).max())
 
 
 def test_bgemm_linearity_full_batch(K, gemm_backend):
