@@ -51,9 +51,11 @@ EW_TIMER = None        # same, around the memory-bound n x n kernels (work = alg
 # (gsr_bgemm_f32) otherwise; "simt": always the SIMT kernel.  Same results to fp32 tolerance.
 GEMM_BACKEND = os.environ.get("GSR_GEMM_BACKEND", "tc")
 TC_MIN_ROWS = 256          # smaller products (the Graph U-Net linears) cannot fill a 128-row tensor-core tile
-# One product (no subject dimension left after stacking) of at most LIN_MAX_OUT outputs and K <= LIN_MAX_K is a latency
-# problem: gsr_bgemm_f32 runs it on its 32 x 32-tile whole-panel kernel (csrc/bgemm.cu, lin::lin_kernel) -- the Graph
-# U-Net's weight gradients (320 x 320 x <= 160) included, which the row rule alone would send to a tensor-core tile or two.
+# One product of two 2-D operands (no subject dimension: the Graph U-Net's Linear layers and their gradients, models/ops.py:60)
+# with at most LIN_MAX_OUT outputs and K <= LIN_MAX_K is a latency problem: gsr_bgemm_f32 runs it on its 32 x 32-tile
+# whole-panel kernel (csrc/bgemm.cu, lin::lin_kernel) -- the weight gradients (268 x 268 x <= 160) included, which the row rule
+# alone would send to a tensor-core tile or two.  Operands with a subject dimension keep the row rule whatever the batch, so
+# that a shard of the batch runs on the same kernels as the whole batch.
 LIN_MAX_OUT, LIN_MAX_K = 1 << 18, 768
 
 
@@ -253,7 +255,7 @@ def bgemm(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB: bool =
         Mk, bk, sAk, sCk, sEk = batch * M, 1, 0, 0, 0
     timer = GEMM_TIMER
     e0 = timer.start() if timer is not None else None
-    tiny = bk == 1 and Mk * N <= LIN_MAX_OUT and K <= LIN_MAX_K
+    tiny = A.dim() == 2 and B.dim() == 2 and M * N <= LIN_MAX_OUT and K <= LIN_MAX_K
     use_tc = not tiny and _tc_ok(A, B, ac, bc, sAk, sB, Mk * bk)
     fn = lib().gsr_tcgemm_f32 if use_tc else lib().gsr_bgemm_f32
     check(fn(A.data_ptr(), B.data_ptr(), out.data_ptr(), Mk, N, K, ac, bc, N,
