@@ -747,7 +747,7 @@ def run_ours(args):
     #     issues three MMAs per algorithmic product, both stated so that `frac` is against the MEASURED bf16 peak.
     tf32_peak = tf32_best if tf32_best > 0 else bf16_peak / 2.0
     tma_on = backend == "tc"
-    traffic = ncu_traffic("r2c_ncu_summary_tcgemm3.txt", "tcgemm3_kernel") if backend == "tc" else None
+    traffic = ncu_traffic("r2d_ncu_summary_tcgemm3.txt", "tcgemm3_kernel") if backend == "tc" else None
     gemm_roof = {
         "kernel": ("gsr::tc::t3::tcgemm3_kernel (persistent CTA pairs, tcgen05.mma.cta_group::2 kind::tf32, 3xTF32: operands by "
                    "cp.async.bulk.tensor into SWIZZLE_128B / 128B_ATOM_32B tiles, the raw fp32 tile is the hi term, converter warps "
@@ -773,7 +773,7 @@ def run_ours(args):
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (1024 per-subject 256 x 268 x 268 products) from the committed
         # ncu --set full capture; the algorithmic bytes of that launch are 1024 x (256 x 268 + 268 x 268 + 256 x 268) x 4 B = 856 MB
         "traffic": traffic,
-        "traffic_source": "profiles/r2c_ncu_summary_tcgemm3.txt (tools/ncu_summary.py of the ncu --set full capture), first tcgemm3_kernel launch (1024 x 268^3 stacked product: 856 MB algorithmic)",
+        "traffic_source": "profiles/r2d_ncu_summary_tcgemm3.txt (tools/ncu_summary.py of the ncu --set full capture), first tcgemm3_kernel launch (1024 x 268^3 stacked product: 856 MB algorithmic)",
         "unet_simt_products": {"launches": simt_launches, "gflop_per_step": simt_flops / max(args.steps, 1) / 1e9,
                                "note": "Graph U-Net linears (once per step, subject independent) on gsr::bgemm_kernel, "
                                        "side stream under the eigendecomposition; not part of `achieved`"},
@@ -824,8 +824,8 @@ def run_ours(args):
             "us_per_graph": eigh_ms * 1e3 / eigh_graphs if eigh_graphs else None,
             "ql_iterations_mean": float(eigh_info.double().mean()), "rotations_mean": rot_mean,
             "conventional_9n3_tflops": 9.0 * n ** 3 * eigh_graphs / (eigh_ms * 1e-3) / 1e12,
-            "traffic": ncu_traffic_all("r2c_ncu_summary_eigh.txt"),
-            "traffic_source": "profiles/r2c_ncu_summary_eigh.txt: dram bytes per launch of each stage (1024 graphs, one launch per stage, "
+            "traffic": ncu_traffic_all("r2d_ncu_summary_eigh.txt"),
+            "traffic_source": "profiles/r2d_ncu_summary_eigh.txt: dram bytes per launch of each stage (1024 graphs, one launch per stage, "
                               "the one-warp QL kernel in place of the lane = graph one)",
         }
     elif eigh_ms > 0 and eigh_info is not None:
@@ -858,8 +858,8 @@ def run_ours(args):
                    "bound": "hbm", "achieved": gbs, "unit": "GB/s", "peak": peaks.get("hbm_gbs"),
                    "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                    "peak_source": "MEASURED_PEAKS.json hbm_gbs", "share_of_step": ew_ms / elapsed_ms,
-                   "launches": ew_launches, "traffic": ncu_traffic_all("r2c_ncu_summary_nxn.txt"),
-                   "traffic_source": "profiles/r2c_ncu_summary_nxn.txt: dram bytes per launch (1024 x 268 x 268; algorithmic: 2 tensors = 588 MB "
+                   "launches": ew_launches, "traffic": ncu_traffic_all("r2d_ncu_summary_nxn.txt"),
+                   "traffic_source": "profiles/r2d_ncu_summary_nxn.txt: dram bytes per launch (1024 x 268 x 268; algorithmic: 2 tensors = 588 MB "
                                      "per forward kernel, 3 = 882 MB per backward pass, 4 with two incoming gradients)"}
     by_kernel = [r for r in (eigh_roof, gemm_roof, ew_roof) if r]
     roofline = max(by_kernel, key=lambda r: r["share_of_step"] or 0.0)          # the dominant kernel of the step

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "gsr_tcgemm_reduce_f32": (i32, [c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, i32, i32, i64, i64,
                                     i32, i32, i32, f32, i32, c_ptr, i32, c_ptr, i32, c_ptr]),
     "gsr_colsum_f32": (i32, [c_ptr, c_ptr, i32, i32, i32, c_ptr]),
+    "gsr_splitk_reduce_f32": (i32, [c_ptr, c_ptr, i32, i32, i32, i32, f32, i32, c_ptr, i32, c_ptr]),
     "gsr_sym_diag_abs_fwd": (i32, [c_ptr, c_ptr, i32, i32, c_ptr]),
     "gsr_sym_diag_abs_bwd": (i32, [c_ptr, c_ptr, c_ptr, i32, i32, c_ptr]),
     "gsr_sym_diag_abs_l1_partials": (i32, [i32]),

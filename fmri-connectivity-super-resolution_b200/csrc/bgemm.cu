@@ -534,6 +534,32 @@ extern "C" int gsr_bgemm_reduce_f32(const float* A, const float* B, float* C,
     return launched("bgemm_reduce_partials");
 }
 
+// Sum of the `splits` partial products of a K-split contraction (workspace [splits][M][N], fixed order), scaled, with the
+// epilogue of the product: + bias[n] or + extra[m][n] (extra may be C itself: one thread reads and writes an element).
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* C, int M, int N, int ldc, int splits, float alpha,
+                                     int epilogue, const float* extra, int ld_extra) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x, total = (long long)M * N;
+    if (e >= total) return;
+    const int m = (int)(e / N), n = (int)(e - (long long)m * N);
+    float acc = 0.f;
+    for (int z = 0; z < splits; ++z) acc += __ldg(ws + (size_t)z * total + e);
+    acc *= alpha;
+    if (epilogue == GSR_EPI_BIAS) acc += extra[n];
+    else if (epilogue == GSR_EPI_ADD) acc += extra[(size_t)m * ld_extra + n];
+    C[(size_t)m * ldc + n] = acc;
+}
+
+extern "C" int gsr_splitk_reduce_f32(const float* workspace, float* C, int M, int N, int ldc, int splits, float alpha,
+                                     int epilogue, const float* extra, int ld_extra, void* stream) {
+    if (!workspace || !C || M <= 0 || N <= 0 || ldc < N || splits <= 0) return fail(GSR_E_ARG, "splitk_reduce: bad argument");
+    if (epilogue < 0 || epilogue > GSR_EPI_ADD || (epilogue != GSR_EPI_NONE && !extra)) return fail(GSR_E_ARG, "splitk_reduce: bad epilogue");
+    const long long total = (long long)M * N;
+    if ((total + 255) / 256 > 0x7fffffffLL) return fail(GSR_E_UNSUPPORTED, "splitk_reduce: M * N too large");
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(workspace, C, M, N, ldc, splits, alpha,
+                                                                                          epilogue, extra, ld_extra);
+    return launched("splitk_reduce");
+}
+
 extern "C" int gsr_colsum_f32(const float* X, float* out, int rows, int cols, int ld, void* stream) {
     if (!X || !out || rows < 0 || cols <= 0) return fail(GSR_E_ARG, "colsum: bad argument");
     colsum_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>(X, out, rows, cols, ld);

@@ -92,8 +92,15 @@ class LinearFn(Function):
     def backward(ctx, gY):
         X, W = ctx.saved_tensors
         gY = _c(gY)
-        gX = K.bgemm(gY, W) if ctx.needs_input_grad[0] else None
-        gW = K.bgemm(gY, X, transA=True) if ctx.needs_input_grad[1] else None
+        gYp = gY
+        if gY.dim() == 2 and gY.shape[1] % 4 != 0 and gY.shape[0] >= K.TC_MIN_ROWS and gY.numel() >= (1 << 20):
+            # rows of a [B, 35 778] gradient (the notebook MLP's output layer) are not 16-byte aligned, which keeps both of its
+            # products off the tensor-core kernels: a copy with the rows padded to a multiple of 4 floats (one pass over gY)
+            buf = torch.empty((gY.shape[0], (gY.shape[1] + 3) // 4 * 4), device=gY.device, dtype=gY.dtype)
+            gYp = buf[:, :gY.shape[1]]
+            gYp.copy_(gY)
+        gX = K.bgemm(gYp, W) if ctx.needs_input_grad[0] else None
+        gW = K.bgemm(gYp, X, transA=True) if ctx.needs_input_grad[1] else None
         gb = K.colsum(gY) if ctx.needs_input_grad[2] else None
         return gX, gW, gb
 

@@ -214,12 +214,43 @@ def set_eigh_method(name: str) -> None:
 
 
 # --------------------------------------------------------------------- GEMMs
+def _f32_rows(t: torch.Tensor, name: str):
+    """(tensor, leading dimension): a 2-D operand may be a view with padded rows (unit column stride, row stride >= columns:
+    e.g. ``buf[:, :35778]`` of a [B, 35780] buffer, whose rows start 16-byte aligned); anything else is made contiguous."""
+    if isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 \
+            and t.stride(0) >= t.shape[1] and t.shape[0] > 1:
+        return t, t.stride(0)
+    t = _f32(t, name)
+    return t, t.shape[-1]
+
+
+# K-split of ONE skinny product with a long inner dimension (the notebook MLP's 512 x 1024 x 12 720 / 35 778 layers): the
+# 256-row x 256-column tiles of such a product are few (8) and each walks all of K, so the 74 CTA pairs idle.  The K slices
+# run as the items of one batched call into a [splits, M, N] workspace and gsr_splitk_reduce_f32 sums them in a fixed order.
+SPLITK_MIN_K, SPLITK_MIN_SLICE, SPLITK_MAX_TILES = 1024, 256, 24
+
+
+def _splitk_plan(M: int, N: int, K: int):
+    """(splits, slice length, remainder) or None.  The slice is a multiple of 4 (16-byte aligned slice starts); the last
+    K - splits * slice < 4 * splits columns are a product of their own, which also carries the epilogue."""
+    if K < SPLITK_MIN_K or M < TC_MIN_ROWS:
+        return None
+    tiles = ((M + 255) // 256) * (1 if N <= 272 else (N + 255) // 256)
+    if tiles > SPLITK_MAX_TILES:
+        return None
+    splits = min(max(2, round(74 / tiles)), K // SPLITK_MIN_SLICE)
+    if splits < 2:
+        return None
+    kc = (K // splits) & ~3
+    return splits, kc, K - splits * kc
+
+
 def bgemm(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB: bool = False, alpha: float = 1.0,
           bias: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None) -> torch.Tensor:
     """C[b] = alpha * op(A[b]) @ op(B[b]) (+ bias[n] | + add[b]).  2-D operands are shared by
     all subjects.  A 3-D non-transposed A against a shared B is run as ONE stacked GEMM
     (M = batch * rows): the weight tile is reused across subjects and no tile is ragged."""
-    A, B = _f32(A, "bgemm: A"), _f32(B, "bgemm: B")
+    (A, lda), (B, ldb) = _f32_rows(A, "bgemm: A"), _f32_rows(B, "bgemm: B")
     if A.dim() not in (2, 3) or B.dim() not in (2, 3):
         raise ValueError("bgemm: operands must be 2-D or 3-D")
     ba = A.shape[0] if A.dim() == 3 else 1
@@ -256,12 +287,34 @@ def bgemm(A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB: bool =
     timer = GEMM_TIMER
     e0 = timer.start() if timer is not None else None
     tiny = A.dim() == 2 and B.dim() == 2 and M * N <= LIN_MAX_OUT and K <= LIN_MAX_K
-    use_tc = not tiny and _tc_ok(A, B, ac, bc, sAk, sB, Mk * bk)
-    fn = lib().gsr_tcgemm_f32 if use_tc else lib().gsr_bgemm_f32
-    check(fn(A.data_ptr(), B.data_ptr(), out.data_ptr(), Mk, N, K, ac, bc, N,
-             sAk, sB, sCk, int(transA), int(transB), bk, float(alpha),
-             epi, extra.data_ptr() if extra is not None else None, ld_extra, sEk, _stream()),
-          "gsr_bgemm_f32 / gsr_tcgemm_f32")
+    use_tc = not tiny and _tc_ok(A, B, lda, ldb, sAk, sB, Mk * bk)
+    plan = _splitk_plan(Mk, N, K) if (use_tc and bk == 1 and N % 4 == 0) else None
+    if plan is not None:
+        splits, kc, krem = plan
+        k0 = splits * kc
+        if krem:          # the last columns of K first, as a product of their own with the epilogue; the reduction adds to it
+            Ar = A.reshape(Mk, K)[:, k0:] if not transA else A[k0:, :]
+            Br = B[:, k0:] if transB else B[k0:, :]
+            check(lib().gsr_bgemm_f32(Ar.data_ptr(), Br.data_ptr(), out.data_ptr(), Mk, N, krem, lda, ldb, N, 0, 0, 0,
+                                      int(transA), int(transB), 1, float(alpha), epi,
+                                      extra.data_ptr() if extra is not None else None, ld_extra, 0, _stream()), "gsr_bgemm_f32")
+        ws = torch.empty((splits, Mk, N), device=A.device, dtype=torch.float32)
+        check(lib().gsr_tcgemm_f32(A.data_ptr(), B.data_ptr(), ws.data_ptr(), Mk, N, kc, lda, ldb, N,
+                                   kc * lda if transA else kc, kc if transB else kc * ldb, Mk * N,
+                                   int(transA), int(transB), splits, 1.0, EPI_NONE, None, 0, 0, _stream()), "gsr_tcgemm_f32 (K slices)")
+        if krem:
+            check(lib().gsr_splitk_reduce_f32(ws.data_ptr(), out.data_ptr(), Mk, N, N, splits, float(alpha), EPI_ADD,
+                                              out.data_ptr(), N, _stream()), "gsr_splitk_reduce_f32")
+        else:
+            check(lib().gsr_splitk_reduce_f32(ws.data_ptr(), out.data_ptr(), Mk, N, N, splits, float(alpha), epi,
+                                              extra.data_ptr() if extra is not None else None, ld_extra, _stream()),
+                  "gsr_splitk_reduce_f32")
+    else:
+        fn = lib().gsr_tcgemm_f32 if use_tc else lib().gsr_bgemm_f32
+        check(fn(A.data_ptr(), B.data_ptr(), out.data_ptr(), Mk, N, K, lda, ldb, N,
+                 sAk, sB, sCk, int(transA), int(transB), bk, float(alpha),
+                 epi, extra.data_ptr() if extra is not None else None, ld_extra, sEk, _stream()),
+              "gsr_bgemm_f32 / gsr_tcgemm_f32")
     if timer is not None:
         timer.stop(e0, 2.0 * M * N * K * batch, "tc" if use_tc else "simt")
     return out

@@ -179,6 +179,13 @@ GSR_API int gsr_tcgemm_reduce_f32(const float* A, const float* B, float* C,
                           int transA, int transB, int batch, float alpha,
                           int epilogue, const float* extra, int ld_extra,
                           float* workspace, int splits, void* stream);
+/* K-split contractions (one skinny product with a long inner dimension: the notebook MLP's 512 x 1024 x 12 720 /
+ * 35 778 layers, training_template.ipynb:123-145): the caller runs the K slices as the items of ONE batched
+ * gsr_tcgemm_f32 / gsr_bgemm_f32 call (strideA / strideB = the slice, strideC = M * N into workspace
+ * [splits, M, N]); this sums the partial products in a fixed order and applies the product's epilogue:
+ *   C[m][n] = alpha * sum_z workspace[z][m][n] (+ extra[n] | + extra[m][n]);  extra may alias C.               */
+GSR_API int gsr_splitk_reduce_f32(const float* workspace, float* C, int M, int N, int ldc, int splits, float alpha,
+                          int epilogue, const float* extra, int ld_extra, void* stream);
 /* Column sums of a [rows, cols] matrix (Linear bias gradient, models/ops.py:60). */
 GSR_API int gsr_colsum_f32(const float* X, float* out, int rows, int cols, int ld, void* stream);
 

@@ -85,6 +85,8 @@ def test_bad_arguments_are_rejected_without_a_gpu(pkg):
     for knob in (b"tcgemm_pairs", b"tcgemm_ragged_rows", b"gemm_variant"):
         assert lib.gsr_set_tuning(knob, 1 if knob != b"gemm_variant" else 0) == 0
     # round-1 additions: MLP passes, shared-target L1 backward, flat bucket, ragged-row / pair GEMM entry
+    assert lib.gsr_splitk_reduce_f32(None, None, 4, 4, 4, 2, 1.0, 0, None, 0, None) == -1
+    assert b"splitk_reduce" in lib.gsr_last_error()
     assert lib.gsr_bn_stats_f32(None, 4, 4, None, None, None, None, 0.1, None) == -1
     assert lib.gsr_bn_act_fwd_f32(None, None, None, None, None, 1e-5, 0.1, 0, 1, None, 4, 4, None) == -1
     assert lib.gsr_bn_act_bwd_f32(None, None, None, None, None, None, 1e-5, 0.1, 0, 1, 1, None, None, None, 4, 4, None) == -1

@@ -760,6 +760,61 @@ def test_colsum_and_wrapper_routing(cuda_pkg, K):
     assert float((gW.double() - gY.double().T @ X.double()).abs().max()) < 2e-6 * float((gY.abs().double().T @ X.abs().double()).max())
 
 
+@pytest.mark.parametrize("tA", [False, True])
+@pytest.mark.parametrize("tB", [False, True])
+@pytest.mark.parametrize("shape", [(512, 1024, 2048), (512, 1024, 2090), (300, 268, 1500), (512, 516, 1030)])
+def test_bgemm_split_k(cuda_pkg, K, tA, tB, shape):
+    """One skinny product with a long inner dimension (the notebook MLP's layers): K slices as the items of one batched tensor
+    launch + gsr_splitk_reduce_f32, with a remainder slice (K not a multiple of 4 x splits), every epilogue, ragged rows
+    (M = 300) and operands that are row-padded views; against float64 and against the unsplit product."""
+    M, N, Kd = shape
+    plan = K._splitk_plan(M, N, Kd)
+    assert plan is not None and plan[0] >= 2 and plan[1] % 4 == 0 and plan[0] * plan[1] + plan[2] == Kd
+    g = torch.Generator().manual_seed(M + N + Kd)
+    lda = ((M if tA else Kd) + 3) // 4 * 4 + 4              # padded rows: views of wider buffers
+    ldb = ((Kd if tB else N) + 3) // 4 * 4 + 8
+    Abuf = torch.randn((Kd, lda) if tA else (M, lda), generator=g).cuda()
+    Bbuf = torch.randn((N, ldb) if tB else (Kd, ldb), generator=g).cuda()
+    A = Abuf[:, :M] if tA else Abuf[:, :Kd]
+    B = Bbuf[:, :Kd] if tB else Bbuf[:, :N]
+    opA, opB = (A.T if tA else A).double().cpu(), (B.T if tB else B).double().cpu()
+    want = opA @ opB
+    tol = 2e-6 * float((opA.abs() @ opB.abs()).max())
+    bias, add = torch.randn(N, generator=g).cuda(), torch.randn(M, N, generator=g).cuda()
+    n0 = cuda_pkg.launch_count()
+    got = K.bgemm(A, B, transA=tA, transB=tB)
+    assert cuda_pkg.launch_count() - n0 >= 2                # the sliced product (+ its ragged rows) and the reduction
+    assert float((got.double().cpu() - want).abs().max()) <= tol
+    assert torch.equal(got, K.bgemm(A, B, transA=tA, transB=tB))
+    got = K.bgemm(A, B, transA=tA, transB=tB, alpha=-0.5, bias=bias)
+    assert float((got.double().cpu() - (-0.5 * want + bias.double().cpu())).abs().max()) <= tol
+    got = K.bgemm(A, B, transA=tA, transB=tB, alpha=2.0, add=add)
+    assert float((got.double().cpu() - (2.0 * want + add.double().cpu())).abs().max()) <= 2 * tol
+    old = K.SPLITK_MIN_K
+    try:
+        K.SPLITK_MIN_K = 1 << 30
+        unsplit = K.bgemm(A, B, transA=tA, transB=tB)
+    finally:
+        K.SPLITK_MIN_K = old
+    assert float((unsplit - K.bgemm(A, B, transA=tA, transB=tB)).abs().max()) <= 2 * tol     # each is within tol of float64
+
+
+def test_linear_backward_pads_unaligned_gradient_rows(cuda_pkg, K):
+    """LinearFn.backward with a [B, N] gradient whose N is not a multiple of 4 (the notebook MLP's 35 778 outputs): the
+    row-padded copy feeds both products; against torch's float64 Linear."""
+    F_ = cuda_pkg.functional
+    g = torch.Generator().manual_seed(12)
+    Bn, fin, fout = 256, 96, 4102
+    X = torch.randn(Bn, fin, generator=g); W = torch.randn(fout, fin, generator=g) * 0.1; b = torch.randn(fout, generator=g)
+    gY = torch.randn(Bn, fout, generator=g)
+    Xc, Wc, bc = (t.cuda().requires_grad_(True) for t in (X, W, b))
+    F_.LinearFn.apply(Xc, Wc, bc).backward(gY.cuda())
+    Xd, Wd, bd = (t.double().requires_grad_(True) for t in (X, W, b))
+    torch.nn.functional.linear(Xd, Wd, bd).backward(gY.double())
+    for got, want in ((Xc.grad, Xd.grad), (Wc.grad, Wd.grad), (bc.grad, bd.grad)):
+        assert float((got.double().cpu() - want).abs().max()) <= 2e-5 * float(want.abs().max())
+
+
 def test_bgemm_linearity_full_batch(K, gemm_backend):
     """BASELINE size (1024 subjects): C(A1 + A2) = C(A1) + C(A2) up to fp32 rounding, and the
     stacked shared-weight path equals the per-subject path bit for bit."""
