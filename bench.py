@@ -339,9 +339,12 @@ def mlp_measure(pkg, torch, dev, steps=5, batch=512, hidden=1024, n_layers=2):
                         f"triangle scatter: all on libgsr_sm100 kernels)",
             "samples_per_s": batch / (ms * 1e-3), "ms_per_step": ms, "gemm_tflops": flop / (ms * 1e-3) / 1e12,
             "loss_finite": bool(torch.isfinite(loss)), "gpu_launches_per_step": (pkg.launch_count() - n0) // (steps + 3),
-            "note": "M = batch = 512 rows against K = 12 720 / 35 778: the 256-row tiles of the TMA pair kernel give 2 row tiles x few "
-                    "column tiles (no split-K yet), and 35 778 % 4 != 0 keeps the output layer off the TMA store path -- this row is "
-                    "bounded by tile parallelism, not by the tensor pipe"}
+            "note": "M = batch = 512 rows against K = 12 720 / 35 778 gives 8 tiles of 256 x 256: the long inner dimensions run as K "
+                    "slices of one batched tensor launch + gsr_splitk_reduce_f32 (kernels.bgemm), the [512, 35 778] gradient is padded "
+                    "to 16-byte aligned rows for its two products (functional.LinearFn); gemm_tflops is the WHOLE step (BatchNorm, "
+                    "Sigmoid, triangle scatter, spectral-norm plumbing and Adam over 51.7 M parameters included) divided into the "
+                    "Linear flops; the forward of the output layer (N = 35 778, ldc not a multiple of 4) stays on the thread-staged "
+                    "tensor kernel"}
 
 
 def run_folds(args):
