@@ -341,8 +341,9 @@ def mlp_measure(pkg, torch, dev, steps=5, batch=512, hidden=1024, n_layers=2):
             "loss_finite": bool(torch.isfinite(loss)), "gpu_launches_per_step": (pkg.launch_count() - n0) // (steps + 3),
             "note": "M = batch = 512 rows against K = 12 720 / 35 778 gives 8 tiles of 256 x 256: the long inner dimensions run as K "
                     "slices of one batched tensor launch + gsr_splitk_reduce_f32 (kernels.bgemm), the [512, 35 778] gradient is padded "
-                    "to 16-byte aligned rows for its two products (functional.LinearFn); gemm_tflops is the WHOLE step (BatchNorm, "
-                    "Sigmoid, triangle scatter, spectral-norm plumbing and Adam over 51.7 M parameters included) divided into the "
+                    "to 16-byte aligned rows for its two products (functional.LinearFn), W / sigma of spectral_norm and its gradient run "
+                    "on gsr_scale_div_f32 / gsr_spectral_bwd_f32 (the power iteration's three mat-vecs per layer are torch's, as in its "
+                    "hook); gemm_tflops is the WHOLE step (BatchNorm, Sigmoid, triangle scatter and Adam over 51.7 M parameters included) divided into the "
                     "Linear flops; the forward of the output layer (N = 35 778, ldc not a multiple of 4) stays on the thread-staged "
                     "tensor kernel"}
 

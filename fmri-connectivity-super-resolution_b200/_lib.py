@@ -86,6 +86,9 @@ PROTOTYPES = {
     "gsr_act_bwd_f32": (i32, [c_ptr, c_ptr, c_ptr, i64, f32, c_ptr]),
     "gsr_sigmoid_fwd_f32": (i32, [c_ptr, c_ptr, i64, c_ptr]),
     "gsr_sigmoid_bwd_f32": (i32, [c_ptr, c_ptr, c_ptr, i64, c_ptr]),
+    "gsr_scale_div_f32": (i32, [c_ptr, c_ptr, c_ptr, i64, c_ptr]),
+    "gsr_spectral_bwd_workspace": (C.c_size_t, []),
+    "gsr_spectral_bwd_f32": (i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, c_ptr, c_ptr]),
 }
 
 

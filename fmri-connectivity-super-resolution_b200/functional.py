@@ -162,6 +162,26 @@ class AddActFn(Function):
         return gi, gi, None
 
 
+class SpectralScaleFn(Function):
+    """The weight a ``spectral_norm(nn.Linear)`` uses (training_template.ipynb:125,134,143; torch.nn.utils.spectral_norm
+    ``compute_weight``): W / sigma with sigma = u . (W v); u, v are the power-iteration buffers (constants for autograd).
+    sigma itself is torch's own ``dot(u, mv(W, v))`` (a gemv on the weight: parameter plumbing, as in the hook); the two
+    passes over the weight that follow and the three of the backward are the library's."""
+
+    @staticmethod
+    def forward(ctx, W, u, v):
+        sigma = torch.dot(u, torch.mv(W, v))
+        W_eff = K.scale_div(W, sigma)
+        ctx.save_for_backward(W_eff, u, v, sigma)
+        return W_eff
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, G):
+        W_eff, u, v, sigma = ctx.saved_tensors
+        return K.spectral_bwd(_c(G), W_eff, u, v, sigma), None, None
+
+
 class SigmoidFn(Function):
     """training_template.ipynb:132: nn.Sigmoid of the output layer."""
 

@@ -708,6 +708,29 @@ def act_bwd(out: torch.Tensor, grad_out: torch.Tensor, negative_slope: float) ->
     return g
 
 
+def scale_div(x: torch.Tensor, sigma: torch.Tensor) -> torch.Tensor:
+    """x / sigma with sigma a DEVICE scalar (spectral_norm: W / sigma); one streaming pass, nothing synchronises."""
+    x, sigma = _f32(x, "scale_div: x"), _f32(sigma, "scale_div: sigma")
+    if sigma.numel() != 1:
+        raise ValueError("scale_div: sigma must hold one element")
+    y = torch.empty_like(x)
+    check(lib().gsr_scale_div_f32(x.data_ptr(), sigma.data_ptr(), y.data_ptr(), x.numel(), _stream()), "gsr_scale_div_f32")
+    return y
+
+
+def spectral_bwd(grad_w_eff: torch.Tensor, w_eff: torch.Tensor, u: torch.Tensor, v: torch.Tensor, sigma: torch.Tensor) -> torch.Tensor:
+    """Gradient of W for W_eff = W / sigma, sigma = u . (W v):  G / sigma - (sum(G o W_eff) / sigma) u v^T."""
+    g, w = _f32(grad_w_eff, "spectral_bwd: grad"), _f32(w_eff, "spectral_bwd: w_eff")
+    u, v, sigma = _f32(u, "spectral_bwd: u"), _f32(v, "spectral_bwd: v"), _f32(sigma, "spectral_bwd: sigma")
+    if w.dim() != 2 or tuple(g.shape) != tuple(w.shape) or u.numel() != w.shape[0] or v.numel() != w.shape[1] or sigma.numel() != 1:
+        raise ValueError("spectral_bwd: expected grad / w_eff [rows, cols], u [rows], v [cols], sigma [1]")
+    out = torch.empty_like(w)
+    ws = torch.empty((lib().gsr_spectral_bwd_workspace(),), device=w.device, dtype=torch.float64)
+    check(lib().gsr_spectral_bwd_f32(g.data_ptr(), w.data_ptr(), u.data_ptr(), v.data_ptr(), sigma.data_ptr(), out.data_ptr(),
+                                     w.shape[0], w.shape[1], ws.data_ptr(), _stream()), "gsr_spectral_bwd_f32")
+    return out
+
+
 def sigmoid_fwd(x: torch.Tensor) -> torch.Tensor:
     x = _f32(x, "sigmoid: x")
     y = torch.empty_like(x)

@@ -10,9 +10,11 @@ Same constructor (``num_nodes_input, num_nodes_output, num_hidden_nodes, n_layer
 biases).  The arithmetic runs on the library's kernels:
   * ``x[:, input_mask]``                      -> ``gsr_triu_flatten``
   * every ``spectral_norm(nn.Linear)``        -> ``gsr_tcgemm_f32`` / ``gsr_bgemm_f32`` with the bias epilogue on the
-    spectrally normalised weight.  sigma comes from torch's own spectral-norm hook (one power iteration per training
-    forward on the ``weight_u`` / ``weight_v`` buffers: two mat-vecs and a division of the weight -- parameter
-    plumbing, as the optimiser is), so its buffers and gradients behave exactly as the reference's;
+    spectrally normalised weight W / sigma.  The power iteration on the ``weight_u`` / ``weight_v`` buffers and
+    sigma = u . (W v) are torch's own three mat-vecs, statement for statement as in its hook (parameter plumbing, as
+    the optimiser is), so the buffers behave exactly as the reference's; the passes over the weight -- W / sigma and,
+    backward, G / sigma - (sum(G o W_eff) / sigma) u v^T -- run on ``gsr_scale_div_f32`` / ``gsr_spectral_bwd_f32``
+    (torch's hook spends ~12 broadcast elementwise launches per layer on them);
   * ``BatchNorm1d -> Dropout -> LeakyReLU``   -> ``gsr_bn_stats_f32`` + ``gsr_bn_act_fwd_f32`` (negative slope 0.01)
   * ``leaky_relu(block(x) + residual)``       -> ``gsr_add_act_fwd_f32``
   * ``nn.Sigmoid``                            -> ``gsr_sigmoid_fwd_f32``
@@ -25,7 +27,8 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.utils.spectral_norm as spectral_norm
+import torch.nn.functional as nnF
+from torch.nn.utils.spectral_norm import SpectralNorm, spectral_norm
 
 from .. import functional as F_
 
@@ -66,10 +69,30 @@ class SuperResMLP(nn.Module):
         return next(self.parameters()).device
 
     # ---- the pieces, on the library's kernels
+    def _spectral_weight(self, lin: nn.Linear) -> torch.Tensor:
+        """``lin.weight = weight_orig / sigma`` as torch's SpectralNorm forward pre-hook computes it (``compute_weight``:
+        one power iteration on the ``weight_u`` / ``weight_v`` buffers per TRAINING forward, in place and without autograd,
+        then sigma = u . (W v)), with the passes over the weight on the library's kernels (``SpectralScaleFn``)."""
+        hook = next((h for h in lin._forward_pre_hooks.values() if isinstance(h, SpectralNorm)), None)
+        if hook is None or hook.dim != 0:                   # not the layout this model builds: torch's own hook
+            for h in lin._forward_pre_hooks.values():
+                h(lin, None)
+            return lin.weight
+        weight = getattr(lin, hook.name + "_orig")
+        u, v = getattr(lin, hook.name + "_u"), getattr(lin, hook.name + "_v")
+        if lin.training:
+            with torch.no_grad():
+                for _ in range(hook.n_power_iterations):
+                    v = nnF.normalize(torch.mv(weight.t(), u), dim=0, eps=hook.eps, out=v)
+                    u = nnF.normalize(torch.mv(weight, v), dim=0, eps=hook.eps, out=u)
+                if hook.n_power_iterations > 0:             # the buffers are updated in place; autograd sees copies
+                    u, v = u.clone(memory_format=torch.contiguous_format), v.clone(memory_format=torch.contiguous_format)
+        w = F_.SpectralScaleFn.apply(weight, u, v)
+        setattr(lin, hook.name, w)                          # as the hook does: ``lin.weight`` is the derived tensor
+        return w
+
     def _linear(self, lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:
-        for hook in lin._forward_pre_hooks.values():        # torch's SpectralNorm hook: lin.weight = weight_orig / sigma
-            hook(lin, (x,))
-        return F_.LinearFn.apply(x.contiguous(), lin.weight, lin.bias)
+        return F_.LinearFn.apply(x.contiguous(), self._spectral_weight(lin), lin.bias)
 
     def _bn_drop_act(self, bn: nn.BatchNorm1d, drop: nn.Dropout, act: nn.LeakyReLU, x: torch.Tensor) -> torch.Tensor:
         training = self.training or bn.running_mean is None

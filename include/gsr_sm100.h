@@ -334,6 +334,15 @@ GSR_API int gsr_add_act_fwd_f32(const float* a, const float* b, float* out, long
 GSR_API int gsr_act_bwd_f32(const float* out, const float* grad_out, float* grad_in, long long count, float negative_slope, void* stream);
 GSR_API int gsr_sigmoid_fwd_f32(const float* x, float* y, long long count, void* stream);
 GSR_API int gsr_sigmoid_bwd_f32(const float* y, const float* grad_y, float* grad_x, long long count, void* stream);
+/* spectral_norm(nn.Linear) of the same model (:125,134,143; torch.nn.utils.spectral_norm.compute_weight): the weight the
+ * layer uses is W / sigma with sigma = u . (W v) (u, v: the power-iteration buffers, constants for autograd).
+ * gsr_scale_div_f32:    y = x / *sigma  (sigma is a DEVICE scalar: nothing synchronises);
+ * gsr_spectral_bwd_f32: grad_w = grad_w_eff / sigma + dsigma u v^T with dsigma = -sum(grad_w_eff o w_eff) / sigma (the
+ *   sum as fp64 partials folded in a fixed order; workspace: gsr_spectral_bwd_workspace() doubles).                    */
+GSR_API int gsr_scale_div_f32(const float* x, const float* sigma, float* y, long long count, void* stream);
+GSR_API size_t gsr_spectral_bwd_workspace(void);
+GSR_API int gsr_spectral_bwd_f32(const float* grad_w_eff, const float* w_eff, const float* u, const float* v, const float* sigma,
+                         float* grad_w, int rows, int cols, double* workspace, void* stream);
 
 /* ------------------------------------------------------------------ N3 (SURVEY 8 f)
  * torch.optim.Adam(model.parameters(), lr) of training_gsr.ipynb:72 over all parameter tensors in

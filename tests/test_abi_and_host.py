@@ -85,6 +85,9 @@ def test_bad_arguments_are_rejected_without_a_gpu(pkg):
     for knob in (b"tcgemm_pairs", b"tcgemm_ragged_rows", b"gemm_variant"):
         assert lib.gsr_set_tuning(knob, 1 if knob != b"gemm_variant" else 0) == 0
     # round-1 additions: MLP passes, shared-target L1 backward, flat bucket, ragged-row / pair GEMM entry
+    assert lib.gsr_scale_div_f32(None, None, None, 4, None) == -1 and b"scale_div" in lib.gsr_last_error()
+    assert lib.gsr_spectral_bwd_f32(None, None, None, None, None, None, 4, 4, None, None) == -1
+    assert lib.gsr_spectral_bwd_workspace() >= 2
     assert lib.gsr_splitk_reduce_f32(None, None, 4, 4, 4, 2, 1.0, 0, None, 0, None) == -1
     assert b"splitk_reduce" in lib.gsr_last_error()
     assert lib.gsr_bn_stats_f32(None, 4, 4, None, None, None, None, 0.1, None) == -1
@@ -94,6 +97,19 @@ def test_bad_arguments_are_rejected_without_a_gpu(pkg):
     assert lib.gsr_flat_pack(None, None, 3, None, 10, 1.0, None) == -1
     assert lib.gsr_tcgemm_f32(None, None, None, 268, 268, 268, 268, 268, 268, 0, 0, 0, 0, 0, 1, 1.0, 0, None, 0, 0, None) == -1
     assert lib.gsr_launch_count() == 0
+
+
+def test_gemm_dispatch_host_rules(pkg):
+    """Host-side dispatch of kernels.bgemm (no GPU): the K-split plan of a skinny product covers K exactly with 16-byte aligned
+    slices, leaves the step's shapes alone, and the one-subject rule is about operands without a subject dimension."""
+    K = pkg.kernels
+    for M, N, Kd in ((512, 1024, 12720), (512, 1024, 35778), (512, 1024, 1024), (300, 268, 1500), (512, 516, 1030)):
+        splits, kc, krem = K._splitk_plan(M, N, Kd)
+        assert splits >= 2 and kc % 4 == 0 and kc >= K.SPLITK_MIN_SLICE - 3 and 0 <= krem < 4 * splits
+        assert splits * kc + krem == Kd
+    for shape in ((1024 * 268, 268, 268), (268, 268, 268), (512, 35778, 1024), (35778, 1024, 512), (160, 268, 536), (128, 1024, 4096)):
+        assert K._splitk_plan(*shape) is None, shape         # stacked / per-subject / wide / short-K / small-M products: no split
+    assert K.LIN_MAX_OUT >= 268 * 536 and K.LIN_MAX_K >= 536   # every Linear product of the Graph U-Net (models/ops.py:92-107)
 
 
 def test_product_package_never_imports_the_oracle():

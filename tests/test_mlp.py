@@ -237,6 +237,34 @@ def test_notebook_mlp_keys_and_seeded_init_equal_the_reference(pkg, golden):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols", [(1024, 12720), (37, 50), (130, 1024)])
+def test_spectral_scale_against_torch_autograd(cuda_pkg, rows, cols):
+    """W / sigma with sigma = u . (W v) and its gradient (gsr_scale_div_f32, gsr_spectral_bwd_f32) against torch's own
+    float64 autograd of the same expression (torch.nn.utils.spectral_norm.compute_weight)."""
+    F_ = cuda_pkg.functional
+    g = torch.Generator().manual_seed(rows + cols)
+    W = torch.randn(rows, cols, generator=g) * 0.05
+    u = torch.nn.functional.normalize(torch.randn(rows, generator=g), dim=0)
+    v = torch.nn.functional.normalize(torch.randn(cols, generator=g), dim=0)
+    G = torch.randn(rows, cols, generator=g)
+    Wc = W.cuda().requires_grad_(True)
+    out = F_.SpectralScaleFn.apply(Wc, u.cuda(), v.cuda())
+    out.backward(G.cuda())
+    Wd = W.double().requires_grad_(True)
+    ref = Wd / torch.dot(u.double(), torch.mv(Wd, v.double()))
+    ref.backward(G.double())
+    assert float((out.detach().double().cpu() - ref.detach()).abs().max()) <= 2e-6 * float(ref.detach().abs().max())
+    assert float((Wc.grad.double().cpu() - Wd.grad).abs().max()) <= 2e-5 * float(Wd.grad.abs().max())
+    out2 = F_.SpectralScaleFn.apply(Wc, u.cuda(), v.cuda())
+    Wc.grad = None
+    out2.backward(G.cuda())
+    assert torch.equal(out2, out)                                # deterministic, two-stage fp64 sum included
+    again = Wc.grad.clone(); Wc.grad = None
+    F_.SpectralScaleFn.apply(Wc, u.cuda(), v.cuda()).backward(G.cuda())
+    assert torch.equal(Wc.grad, again)
+
+
+@pytest.mark.gpu
 def test_notebook_mlp_matches_the_reference_fixture(cuda_pkg, golden):
     """Eval output, training-mode (p = 0) output, every parameter gradient, the updated BatchNorm statistics and the
     spectral-norm power-iteration buffers against the unmodified notebook class (oracle/make_golden_mlp_notebook.py)."""
