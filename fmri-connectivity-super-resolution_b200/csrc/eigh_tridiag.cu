@@ -765,6 +765,72 @@ __device__ __forceinline__ void form_q_row(float (&z)[MAXN + 1], const Work& wk,
     __syncwarp();
 }
 
+// COLUMN `col` of Q = H_{n-1} ... H_1 into z (z[j] = Q[j][col]): H_1 is applied first, and H_k -- whose vector lives in
+// coordinates [0, k) -- leaves e_col alone for every k <= col, so a warp that owns columns c0 .. c0 + 31 starts at
+// k = c0 + 1 (lanes whose column is still >= k see a zero dot product: no predicate needed).  4/3 n^3 flops over the graph
+// instead of the 2 n^3 of the row form above (there every row is dense from the first reflector on); same inner loops, the
+// reflector rows stream through the ring in ascending order.
+__device__ __forceinline__ void form_q_col(float (&z)[MAXN + 1], const Work& wk, int g, int n, int col, int c0, int lane, float* ring) {
+#pragma unroll
+    for (int j = 0; j <= MAXN; ++j) z[j] = (j == col && col < n) ? 1.0f : 0.0f;
+    const float* Vg = wk.V + (size_t)g * n * LDV;
+    auto issue = [&](int k) {
+        if (k < n) {
+            const float* src = Vg + (size_t)k * LDV;
+            float* dst = ring + (k % STAGES) * 176;
+            cp_async16(dst + 4 * lane, src + 4 * lane);
+            if (lane < LDV / 4 - 32) cp_async16(dst + 4 * (lane + 32), src + 4 * (lane + 32));
+        }
+        cp_async_commit();
+    };
+    const int k_first = c0 + 1;
+    issue(k_first);
+    issue(k_first + 1);
+    for (int k = k_first; k < n; ++k) {
+        cp_async_wait<1>();
+        __syncwarp();                                              // row k landed; every lane is done with row k - 1
+        issue(k + 2);                                              // stage (k - 1) % 3: consumed one step ago
+        const float* vr = ring + (k % STAGES) * 176;
+        const float tau = vr[MAXN];
+        if (tau != 0.f) {                                          // uniform
+            const float4* V4 = reinterpret_cast<const float4*>(vr);
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+            for (int cb = 0; cb < NB; ++cb) {
+                if (16 * cb < k) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 v = V4[4 * cb + c];
+                        q0 = fmaf(z[16 * cb + 4 * c + 0], v.x, q0);
+                        q1 = fmaf(z[16 * cb + 4 * c + 1], v.y, q1);
+                        q2 = fmaf(z[16 * cb + 4 * c + 2], v.z, q2);
+                        q3 = fmaf(z[16 * cb + 4 * c + 3], v.w, q3);
+                    }
+                }
+            }
+            const float s = -tau * ((q0 + q1) + (q2 + q3));
+#pragma unroll
+            for (int cb = 0; cb < NB; ++cb) {
+                if (16 * cb < k) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 v = V4[4 * cb + c];
+                        z[16 * cb + 4 * c + 0] = fmaf(s, v.x, z[16 * cb + 4 * c + 0]);
+                        z[16 * cb + 4 * c + 1] = fmaf(s, v.y, z[16 * cb + 4 * c + 1]);
+                        z[16 * cb + 4 * c + 2] = fmaf(s, v.z, z[16 * cb + 4 * c + 2]);
+                        z[16 * cb + 4 * c + 3] = fmaf(s, v.w, z[16 * cb + 4 * c + 3]);
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+}
+
+constexpr int QT_PITCH = 33;                         // Kq's per-warp transpose tile: [MAXN rows][33]
+constexpr int KQ_SMEM_FLOATS = K3_WARPS * (RING_FLOATS + MAXN * QT_PITCH);
+
 // Kq (chunked pipeline, eigh_q_launch = 1): Q of every graph as its own launch right behind K1, written to Zt[column][row];
 // K3 then only replays the rotations.  It fills the SMs between the end of K1 and the end of the first chunks' rotation
 // chains (K2), which would otherwise idle, and takes the Q formation off the critical path K1 -> K2 -> K3 of the last chunk.
@@ -772,17 +838,26 @@ __global__ void __launch_bounds__(32 * K3_WARPS, 2)
 form_q_kernel(const Work wk, int n, int units_per_graph, int total_units) {
     extern __shared__ __align__(16) float sm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int unit = blockIdx.x * K3_WARPS + w;
-    if (unit >= total_units) return;
-    const int g = unit / units_per_graph, tid = (unit - g * units_per_graph) * 32 + lane;     // tid = row of Q
+    // a CTA takes ONE block of 32 columns for four consecutive graphs: its warps then run the same number of reflectors
+    // (columns c0 .. c0 + 31 start at k = c0 + 1), so no warp idles inside a resident CTA while the longest one finishes
+    const int cblk = blockIdx.x % units_per_graph, g = (blockIdx.x / units_per_graph) * K3_WARPS + w;
+    if (g * units_per_graph >= total_units) return;
+    const int c0 = cblk * 32;                                                                 // the warp's 32 columns of Q
     if (wk.counts[4 * g + 2] == -1) return;                            // non-finite input: K1 wrote the outputs (K2 may be updating the status of the others)
     float z[MAXN + 1];
-    form_q_row(z, wk, g, n, tid, lane, sm + w * RING_FLOATS);
-    if (tid < n) {
-        float* Zg = wk.Zt + (size_t)g * n * n;
+    form_q_col(z, wk, g, n, c0 + lane, c0, lane, sm + w * RING_FLOATS);
+    // Zt[column][row]: the warp holds 32 columns; through its shared-memory tile every column leaves as coalesced runs of rows
+    float* tile = sm + K3_WARPS * RING_FLOATS + w * (MAXN * QT_PITCH);
 #pragma unroll
-        for (int j = 0; j < MAXN; ++j) {
-            if (j < n) Zg[(size_t)j * n + tid] = z[j];
+    for (int j = 0; j < MAXN; ++j) tile[j * QT_PITCH + lane] = z[j];
+    __syncwarp();
+    float* Zg = wk.Zt + (size_t)g * n * n;
+    for (int col = 0; col < 32 && c0 + col < n; ++col) {
+        float* dst = Zg + (size_t)(c0 + col) * n;
+#pragma unroll
+        for (int rb = 0; rb < MAXN / 32; ++rb) {
+            const int row = 32 * rb + lane;
+            if (row < n) dst[row] = tile[row * QT_PITCH + col];
         }
     }
 }
@@ -1421,8 +1496,10 @@ extern "C" __attribute__((visibility("default"))) int gsr_eigh_timeline_read(flo
 static int launch_form_q(const gsr::tq::Work& wk, int batch, int threads, int n, cudaStream_t st) {
     using namespace gsr;
     const int upg = threads / 32, units = upg * batch;
-    const size_t smemq = (size_t)tq::K3_WARPS * tq::RING_FLOATS * sizeof(float);
-    tq::form_q_kernel<<<(units + tq::K3_WARPS - 1) / tq::K3_WARPS, 32 * tq::K3_WARPS, smemq, st>>>(wk, n, upg, units);
+    const size_t smemq = (size_t)tq::KQ_SMEM_FLOATS * sizeof(float);
+    static const bool attr_ok = cudaFuncSetAttribute(tq::form_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)tq::KQ_SMEM_FLOATS * sizeof(float))) == cudaSuccess;
+    if (!attr_ok) { cudaGetLastError(); return fail(GSR_E_UNSUPPORTED, "eigh_tridiag: shared-memory opt-in of the Q kernel failed"); }
+    tq::form_q_kernel<<<upg * ((batch + tq::K3_WARPS - 1) / tq::K3_WARPS), 32 * tq::K3_WARPS, smemq, st>>>(wk, n, upg, units);
     return launched("eigh_form_q");
 }
 
@@ -1485,9 +1562,9 @@ static int eigh_small_segment(const float* A, float* w, float* U, int32_t* info,
         if ((rc = launch_k1(A, w, U, info, wk, batch, threads, n, 0, st))) return rc;
         GSR_TR(1);
         if ((rc = launch_k2(wk, n, 0, batch, st, false, nullptr, 0, nullptr, g_eigh_k2_lanes >= 2))) return rc;      // one warp per graph unless forced
-        // Q formed by K3: a launch of its own only pays inside the pipeline (eigh_q_launch = 2 forces it here too: profilers
-        // serialise kernels, so this is how Kq and the rotation-only K3 are captured)
-        const int qown = g_eigh_q_launch >= 2 ? 1 : 0;
+        // Q by its own launch here too (eigh_q_launch = 0: K3 forms it, in row form): Kq's column form does 2/3 of the flops,
+        // and every batch size forms Q with the same arithmetic (a shard of a batch reproduces the batch's eigenvectors)
+        const int qown = g_eigh_q_launch >= 1 ? 1 : 0;
         if (qown && (rc = launch_form_q(wk, batch, threads, n, st))) return rc;
         if ((rc = launch_small_apply(w, U, info, wk, 0, batch, n, canonical_sign, qown, st))) return rc;
     } else {
