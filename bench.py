@@ -756,7 +756,7 @@ def run_ours(args):
         "kernel": ("gsr::tc::t3::tcgemm3_kernel (persistent CTA pairs, tcgen05.mma.cta_group::2 kind::tf32, 3xTF32: operands by "
                    "cp.async.bulk.tensor into SWIZZLE_128B / 128B_ATOM_32B tiles, the raw fp32 tile is the hi term, converter warps "
                    "write lo, two overlapping accumulators in TMEM, TMA-store epilogue; 256 x 272 x 32 tiles) + the FP32 "
-                   "ragged-row kernels for rows 256..267 and the one-CTA gsr::tc::tcgemm_kernel for M < 256"
+                   "ragged-row kernels for rows 256..267 and the one-CTA gsr::tc::tcgemm_kernel for the few remaining M < 256 tiles"
                    if backend == "tc" else "gsr::bgemm_kernel (136x136x16 SIMT FP32 tile)"),
         "bound": "tensor" if backend == "tc" else "fp32",
         "achieved": gemm_tflops, "unit": "TFLOP/s (algorithmic fp32 flops of the contractions)",
@@ -779,17 +779,19 @@ def run_ours(args):
         "traffic": traffic,
         "traffic_source": "profiles/r2d_ncu_summary_tcgemm3.txt (tools/ncu_summary.py of the ncu --set full capture), first tcgemm3_kernel launch (1024 x 268^3 stacked product: 856 MB algorithmic)",
         "unet_simt_products": {"launches": simt_launches, "gflop_per_step": simt_flops / max(args.steps, 1) / 1e9,
-                               "note": "Graph U-Net linears (once per step, subject independent) on gsr::bgemm_kernel, "
-                                       "side stream under the eigendecomposition; not part of `achieved`"},
+                               "note": "Graph U-Net linears and their gradients (once per step, subject independent) on "
+                                       "gsr::lin::lin_kernel (one product: whole operand panels in shared memory, 32 x 32 tiles, 4-6 us "
+                                       "per launch), side stream under the eigendecomposition; not part of `achieved`"},
     }
     # --- LR eigendecomposition
     eigh_roof = None
     eigh_method = getattr(eigh_timer, "last_method", None)
     if eigh_ms > 0 and eigh_info is not None and eigh_method == "tridiag":
         # tridiagonal route (csrc/eigh_tridiag.cu): matrices in registers, bound by the FP32 FMA pipe.
-        # Executed flops per graph: Householder reduction 2 n^3 (n^3 FMAs), Q accumulation 2 n^3, and
-        # 6 n per replayed plane rotation (2 FMUL + 2 FFMA on each of the n rows); the rotation count
-        # (identity padding included, it is executed) is read back from one extra, untimed call.
+        # Executed flops per graph: Householder reduction 2 n^3 (n^3 FMAs), Q accumulation in column form (a warp owns 32
+        # columns and starts at reflector c0 + 1; a reflector k touches 16 ceil(k / 16) coordinates, 4 flops each: 6.6 MFLOP
+        # at n = 160 = 0.81 of the 2 n^3 the row form executed), and 6 n per replayed plane rotation (2 FMUL + 2 FFMA on each
+        # of the n rows); the rotation count (identity padding included, it is executed) is read back from one extra, untimed call.
         n = LR_DIM
         A_lr = pkg.normalize_adj_torch(lr)
         _, _, _, ws = K.eigh_tridiag(A_lr, _return_workspace=True)
@@ -813,15 +815,16 @@ def run_ours(args):
         off = al(B * cap * 8) + al(B * n * 164 * 4) + al(B * n * n * 4) + 2 * al(B * n * 4) + al(B * 4)
         counts = ws[off:off + B * 16].view(torch.int32).view(B, 4)
         rot_mean = float(counts[:, 1].double().mean())
-        flops_per_graph = 4.0 * n ** 3 + 6.0 * n * rot_mean
+        q_flops = float(sum(32 * sum(4 * 16 * ((k + 15) // 16) for k in range(c0 + 1, n)) for c0 in range(0, n, 32)))
+        flops_per_graph = 2.0 * n ** 3 + q_flops + 6.0 * n * rot_mean
         tflops = flops_per_graph * eigh_graphs / (eigh_ms * 1e-3) / 1e12
         eigh_roof = {
             "kernel": "gsr::tq::{tridiag,form_q,tql_scalar_lanes,tql_apply,tql_finish}_kernel (Householder + implicit QL, one thread per "
                       "matrix row, rows resident in registers (K1: 128 of 160 columns, the rest in shared memory); QL iteration with lane = "
-                      "graph; run as a pipeline: K1 in one launch, Q = H_{n-1} ... H_1 as a launch of its own behind it, K2 CTAs resident "
+                      "graph; run as a pipeline: K1 in one launch, Q = H_{n-1} ... H_1 as a launch of its own behind it (column form: thread = column of Q), K2 CTAs resident "
                       "on their own SMs polling K1's per-chunk counts, K3 (rotation replay) / K4 per 128-graph chunk on internal streams)",
             "timed": "alone on the device, mean of 5 calls of 1024 graphs", "in_step_pass_ms": eigh_pass_ms, "alone_ms": eigh_alone_ms,
-            "bound": "fp32", "achieved": tflops, "unit": "TFLOP/s (executed fp32 flops: 4 n^3 + 6 n per plane rotation)",
+            "bound": "fp32", "achieved": tflops, "unit": "TFLOP/s (executed fp32 flops: 2 n^3 + 1.6 n^3 (Q in column form) + 6 n per plane rotation)",
             "peak": ffma_best, "frac": tflops / ffma_best if ffma_best else None,
             "peak_source": "FP32 FFMA probe kernel measured in this run",
             "share_of_step": eigh_ms / elapsed_ms, "launches": eigh_launches,

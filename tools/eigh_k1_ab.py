@@ -1,7 +1,12 @@
 """K1 (Householder tridiagonalisation, thread = matrix row) with 6 .. 10 of the ten 16-column blocks of a row in
 registers (6, 7: 3 CTAs per SM at 128 registers) (gsr_set_tuning("eigh_k1_regblocks", k); the rest in shared memory): results of the variants against each
 other (the arithmetic is the same, so bit identity is expected), against float64, and the time of the whole
-decomposition of 1024 graphs of 160 nodes with one launch per stage and as the chunked pipeline."""
+decomposition of 1024 graphs of 160 nodes with one launch per stage and as the chunked pipeline.
+Since the fourth session of round 2 the Q launch works in COLUMN form (csrc/eigh_tridiag.cu, form_q_col): q_launch = 0 (K3 forms
+Q in row form) and q_launch = 1 agree up to the rounding of Q (2e-5 on the bases, asserted by
+test_eigh_pipeline_matches_one_launch_per_stage), so the `q_launch_bit_identical` lines below print false; the K1 register-block
+variants stay bit identical to each other.
+"""
 import importlib, os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
