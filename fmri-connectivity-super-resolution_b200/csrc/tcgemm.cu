@@ -626,7 +626,7 @@ static bool operands_ok(const Params& p) {
 // subject-reduced products stay on the tensor kernel (a reducing variant of this kernel with 4 x 148 splits was
 // measured twice, before and after the staging was tuned: 0.363 against 0.349 ms for the whole product).
 namespace tail {
-constexpr int T_THREADS = 160, T_HALF = 136, T_COLS = 2 * T_HALF, T_KC = 16, T_KMAX = 288, T_ROWS = 16;
+constexpr int T_THREADS = 128, T_COLS = 272, T_KC = 16, T_KMAX = 288, T_ROWS = 16;      // columns: tid, tid + 128; warp 0 also 256 + (tid & 15)
 constexpr int T_SMEM_FLOATS = T_KMAX * T_ROWS + 2 * T_KC * T_COLS;
 
 __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
@@ -667,18 +667,19 @@ __global__ void __launch_bounds__(T_THREADS, 4) tail_kernel(const Params p) {
     // op(A) rows, zero filled to 4 R4 rows and to whole chunks of k (all loads of a thread are issued before its
     // first store: one memory round trip, not one per row)
     if (!TA) {
-        float v[R4 * 4][2];
+        constexpr int KJ = (T_KMAX + T_THREADS - 1) / T_THREADS;
+        float v[R4 * 4][KJ];
 #pragma unroll
         for (int r = 0; r < R4 * 4; ++r)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < KJ; ++j) {
                 const int k = tid + j * T_THREADS;
                 v[r][j] = (r < rows && k < K) ? __ldg(A + (size_t)r * p.lda + k) : 0.f;
             }
 #pragma unroll
         for (int r = 0; r < R4 * 4; ++r)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < KJ; ++j) {
                 const int k = tid + j * T_THREADS;
                 if (k < kpad) As[k * T_ROWS + ((((r >> 2) ^ (k >> 1)) & 3) << 2) + (r & 3)] = v[r][j];
             }
@@ -700,18 +701,22 @@ __global__ void __launch_bounds__(T_THREADS, 4) tail_kernel(const Params p) {
     cp_wait<0>();
     __syncthreads();
 
-    float acc[R4 * 4][2];
+    // Four full warps own columns tid and tid + 128; the 16 columns from 256 on (the 12 that 268 leaves) are a third column of
+    // warp 0, in a loop of its own behind a warp-uniform branch (the first version gave them to a fifth warp with 8 live lanes
+    // that issued the whole loop: a fifth of the kernel's instructions for 4 % of its outputs).
+    float acc[R4 * 4][2], acc2[R4 * 4];
 #pragma unroll
-    for (int r = 0; r < R4 * 4; ++r) acc[r][0] = acc[r][1] = 0.f;
+    for (int r = 0; r < R4 * 4; ++r) acc[r][0] = acc[r][1] = acc2[r] = 0.f;
+    const bool third = warp == 0 && N > 2 * T_THREADS;
     for (int c = 0; c < nchunks; ++c) {
         // chunk c + 1 goes to the buffer whose last readers (chunk c - 1) all passed the barrier of iteration c - 1
         if (c + 1 < nchunks) copy_b(c + 1);
-        if (tid < T_HALF) {
+        {
             const float* bs = Bs + (c & 1) * T_KC * T_COLS + tid;
             const float* as = As + c * T_KC * T_ROWS;
 #pragma unroll
             for (int kk = 0; kk < T_KC; ++kk) {
-                const float b0 = bs[kk * T_COLS], b1 = bs[kk * T_COLS + T_HALF];
+                const float b0 = bs[kk * T_COLS], b1 = bs[kk * T_COLS + T_THREADS];
 #pragma unroll
                 for (int q = 0; q < R4; ++q) {
                     const float4 a = *reinterpret_cast<const float4*>(as + kk * T_ROWS + (((q ^ (kk >> 1)) & 3) << 2));
@@ -721,17 +726,29 @@ __global__ void __launch_bounds__(T_THREADS, 4) tail_kernel(const Params p) {
                     acc[4 * q + 3][0] = fmaf(a.w, b0, acc[4 * q + 3][0]); acc[4 * q + 3][1] = fmaf(a.w, b1, acc[4 * q + 3][1]);
                 }
             }
+            if (third) {                                                   // warp uniform
+                const float* bt = Bs + (c & 1) * T_KC * T_COLS + 2 * T_THREADS + (tid & 15);
+#pragma unroll 4
+                for (int kk = 0; kk < T_KC; ++kk) {
+                    const float b2 = bt[kk * T_COLS];
+#pragma unroll
+                    for (int q = 0; q < R4; ++q) {
+                        const float4 a = *reinterpret_cast<const float4*>(as + kk * T_ROWS + (((q ^ (kk >> 1)) & 3) << 2));
+                        acc2[4 * q + 0] = fmaf(a.x, b2, acc2[4 * q + 0]); acc2[4 * q + 1] = fmaf(a.y, b2, acc2[4 * q + 1]);
+                        acc2[4 * q + 2] = fmaf(a.z, b2, acc2[4 * q + 2]); acc2[4 * q + 3] = fmaf(a.w, b2, acc2[4 * q + 3]);
+                    }
+                }
+            }
         }
         cp_wait<0>();
         __syncthreads();
     }
-    if (tid >= T_HALF) return;
     float* C = p.C + (size_t)bz * p.sC;
     const int epi = p.epilogue;
     const float* extra = epi == GSR_EPI_ADD ? p.extra + (size_t)bz * p.s_extra : p.extra;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int n = tid + h * T_HALF;
+        const int n = tid + h * T_THREADS;
         if (n >= N) continue;
         const float bias = epi == GSR_EPI_BIAS ? __ldg(extra + n) : 0.f;
 #pragma unroll
@@ -739,6 +756,18 @@ __global__ void __launch_bounds__(T_THREADS, 4) tail_kernel(const Params p) {
             if (r < rows) {
                 float v = acc[r][h] * p.alpha + bias;
                 if (epi == GSR_EPI_ADD) v += extra[(size_t)r * p.ld_extra + n];     // plain load: the addend may alias C
+                C[(size_t)r * p.ldc + n] = v;
+            }
+        }
+    }
+    if (third && tid < 16 && 2 * T_THREADS + tid < N) {
+        const int n = 2 * T_THREADS + tid;
+        const float bias = epi == GSR_EPI_BIAS ? __ldg(extra + n) : 0.f;
+#pragma unroll
+        for (int r = 0; r < R4 * 4; ++r) {
+            if (r < rows) {
+                float v = acc2[r] * p.alpha + bias;
+                if (epi == GSR_EPI_ADD) v += extra[(size_t)r * p.ld_extra + n];
                 C[(size_t)r * p.ldc + n] = v;
             }
         }
